@@ -1,0 +1,256 @@
+// K1/K2 of SURVEY.md 2.5: N x 32-bit-limb Montgomery prime-field arithmetic held in registers.
+//
+// Replaces, on the device, what the reference gets from ark-ff's `Fp<MontBackend<_, N>>`
+// (the `BaseField<S>` / `ScalarField<S>` aliases re-exported at /root/reference/src/lib.rs:13-17).
+// Representation: a*R mod p, R = 2^(32N), limbs little-endian, always fully reduced (< p), so that
+// equality is limb equality and canonical bytes are one Montgomery reduction away.
+//
+// The header is also compilable for the host (HD_INLINE functions with plain-C twins of every PTX
+// block) so that tests/host_emul can check the arithmetic without a GPU.  The product never runs it
+// on the host: every entry point of the library launches kernels.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define HD_INLINE __device__ __forceinline__
+#define HD_NOINLINE static __device__ __noinline__   // free functions
+#define HD_NOINLINE_M __device__ __noinline__        // member functions
+#define VRFS_CONST_TABLE __device__ __constant__
+#else   // host emulation build (g++, tests only)
+#define HD_INLINE inline
+#define HD_NOINLINE static
+#define HD_NOINLINE_M
+#define VRFS_CONST_TABLE static const
+#endif
+
+#include "gen/mont_chains.cuh"
+
+namespace vrfs {
+
+// Modulus limbs: by default compile-time immediates (ptxas then emits IMAD.X + IMAD.HI.U32.X for the
+// reduction rows instead of one IMAD.WIDE.U32.X - the same number of multiplier passes, no registers
+// spent on the modulus).  VRFS_MOD_IN_REGS=1 XORs them with a zero loaded per lane from global memory,
+// which makes them ordinary vector registers and lets ptxas fuse the pairs; kept as a measured
+// alternative (see profiles/ and DESIGN.md "K1").
+#ifndef VRFS_MOD_IN_REGS
+#define VRFS_MOD_IN_REGS 0
+#endif
+#if defined(__CUDACC__) && VRFS_MOD_IN_REGS
+__device__ uint32_t g_opaque_zero[32];   // zero-initialised; indexed by lane so ptxas cannot prove the value warp-uniform
+#endif
+HD_INLINE uint32_t opaque_zero() {
+#if defined(__CUDA_ARCH__) && VRFS_MOD_IN_REGS
+  return g_opaque_zero[threadIdx.x & 31];
+#else
+  return 0;
+#endif
+}
+
+// Field parameter packs (generated: gen/field_consts.cuh) provide:
+//   static constexpr int N; static constexpr bool FULL (p >= 2^(32N-1)); static constexpr uint32_t NINV;
+//   HD_INLINE static uint32_t mod(i), one(i) [R mod p], r2(i), r3(i), pm2(i) [p-2], pm1h(i) [(p-1)/2]
+template <class P>
+struct alignas(16) Fp {
+  static constexpr int N = P::N;
+  uint32_t v[N];
+
+  HD_INLINE static Fp zero() { Fp r; for (int i = 0; i < N; i++) r.v[i] = 0; return r; }
+  HD_INLINE static Fp one() { Fp r; for (int i = 0; i < N; i++) r.v[i] = P::one(i); return r; }
+  HD_INLINE static Fp modulus() { Fp r; for (int i = 0; i < N; i++) r.v[i] = P::mod(i); return r; }
+  HD_INLINE static Fp r2() { Fp r; for (int i = 0; i < N; i++) r.v[i] = P::r2(i); return r; }
+  HD_INLINE static Fp r3() { Fp r; for (int i = 0; i < N; i++) r.v[i] = P::r3(i); return r; }
+
+  HD_INLINE bool is_zero() const { uint32_t o = 0; for (int i = 0; i < N; i++) o |= v[i]; return o == 0; }
+  HD_INLINE bool operator==(const Fp& b) const { uint32_t o = 0; for (int i = 0; i < N; i++) o |= v[i] ^ b.v[i]; return o == 0; }
+  HD_INLINE bool operator!=(const Fp& b) const { return !(*this == b); }
+};
+
+// raw comparisons on limb arrays --------------------------------------------------------------
+template <int N>
+HD_INLINE bool limbs_geq(const uint32_t* a, const uint32_t* b) {  // a >= b
+  uint32_t t[N];
+  return MontChains<N>::sub(t, a, b) == 0;
+}
+
+// r = (a >= p) ? a - p : a, also subtracting when `carry` (the 2^(32N) bit) is set
+template <class P>
+HD_INLINE void cond_sub_p(uint32_t* a, uint32_t carry) {
+  constexpr int N = P::N;
+  uint32_t t[N], m[N];
+  for (int i = 0; i < N; i++) m[i] = P::mod(i);
+  uint32_t borrow = MontChains<N>::sub(t, a, m);
+  bool take = (carry != 0) | (borrow == 0);
+  for (int i = 0; i < N; i++) a[i] = take ? t[i] : a[i];
+}
+
+template <class P>
+HD_INLINE Fp<P> operator+(const Fp<P>& a, const Fp<P>& b) {
+  Fp<P> r;
+  uint32_t c = MontChains<P::N>::add(r.v, a.v, b.v);
+  cond_sub_p<P>(r.v, P::FULL ? c : 0u);
+  return r;
+}
+template <class P>
+HD_INLINE Fp<P> operator-(const Fp<P>& a, const Fp<P>& b) {
+  constexpr int N = P::N;
+  Fp<P> r;
+  uint32_t borrow = MontChains<N>::sub(r.v, a.v, b.v);
+  uint32_t m[N], mask = 0u - borrow;
+  for (int i = 0; i < N; i++) m[i] = P::mod(i) & mask;
+  MontChains<N>::add(r.v, r.v, m);
+  return r;
+}
+template <class P>
+HD_INLINE Fp<P> neg(const Fp<P>& a) { return Fp<P>::zero() - a; }
+template <class P>
+HD_INLINE Fp<P> dbl(const Fp<P>& a) { return a + a; }
+template <class P>
+HD_INLINE Fp<P> select(bool c, const Fp<P>& a, const Fp<P>& b) {  // c ? a : b
+  Fp<P> r;
+  for (int i = 0; i < P::N; i++) r.v[i] = c ? a.v[i] : b.v[i];
+  return r;
+}
+template <class P>
+HD_INLINE Fp<P> cneg(const Fp<P>& a, bool c) { return select(c, neg(a), a); }
+
+// Montgomery product.  Requires a < p; b may be ANY N-limb value (used to reduce hash outputs).
+// p < 2^(32N-1): interleaved even/odd accumulators, 2N^2+N multiply-accumulates (IMAD.WIDE.U32).
+template <class P>
+HD_INLINE void mont_mul_limbs(uint32_t* out, const uint32_t* a, const uint32_t* b) {
+  constexpr int N = P::N;
+  typedef MontChains<N> C;
+  uint32_t mod[N];
+  if (!P::FULL) {
+    const uint32_t z = opaque_zero();
+    for (int i = 0; i < N; i++) mod[i] = P::mod(i) ^ z;
+    uint32_t u[N], v[N];
+    // first row: v = a_even*b0 (cols 0..N-1), u = a_odd*b0 (cols 1..N)
+    C::mul_row(v, a, b[0]);
+    C::mul_row(u, a + 1, b[0]);
+    {
+      uint32_t m = v[0] * P::NINV;
+      C::mad_row_top(u, mod + 1, m);
+      C::mad_row(v, u[N - 1], mod, m);
+    }
+#pragma unroll
+    for (int i = 1; i < N; i++) {
+      if (i & 1) {  // roles: dead-even = v, odd = u
+        C::shift_mad_row(v, u[0], a + 1, b[i]);
+        C::mad_row(u, v[N - 1], a, b[i]);
+        uint32_t m = u[0] * P::NINV;
+        C::mad_row_top(v, mod + 1, m);
+        C::mad_row(u, v[N - 1], mod, m);
+      } else {
+        C::shift_mad_row(u, v[0], a + 1, b[i]);
+        C::mad_row(v, u[N - 1], a, b[i]);
+        uint32_t m = v[0] * P::NINV;
+        C::mad_row_top(u, mod + 1, m);
+        C::mad_row(v, u[N - 1], mod, m);
+      }
+    }
+    // N even: after the last (odd-index) iteration the live odd array is v, the dead-even one is u
+    C::merge(v, u);
+    cond_sub_p<P>(v, 0u);
+    for (int i = 0; i < N; i++) out[i] = v[i];
+  } else {
+    // p >= 2^(32N-1) (P-256 p and n): textbook CIOS on 64-bit temporaries with the extra top word.
+    for (int i = 0; i < N; i++) mod[i] = P::mod(i);
+    uint32_t t[N + 2];
+    for (int i = 0; i < N + 2; i++) t[i] = 0;
+    for (int i = 0; i < N; i++) {
+      uint64_t c = 0;
+      for (int j = 0; j < N; j++) { uint64_t x = (uint64_t)a[j] * b[i] + t[j] + c; t[j] = (uint32_t)x; c = x >> 32; }
+      uint64_t x = (uint64_t)t[N] + c; t[N] = (uint32_t)x; t[N + 1] = (uint32_t)(x >> 32);
+      uint32_t m = t[0] * P::NINV;
+      x = (uint64_t)m * mod[0] + t[0]; c = x >> 32;
+      for (int j = 1; j < N; j++) { x = (uint64_t)m * mod[j] + t[j] + c; t[j - 1] = (uint32_t)x; c = x >> 32; }
+      x = (uint64_t)t[N] + c; t[N - 1] = (uint32_t)x; t[N] = t[N + 1] + (uint32_t)(x >> 32);
+    }
+    cond_sub_p<P>(t, t[N]);
+    for (int i = 0; i < N; i++) out[i] = t[i];
+  }
+}
+
+template <class P>
+HD_INLINE Fp<P> operator*(const Fp<P>& a, const Fp<P>& b) {
+  Fp<P> r;
+  mont_mul_limbs<P>(r.v, a.v, b.v);
+  return r;
+}
+template <class P>
+HD_INLINE Fp<P> sqr(const Fp<P>& a) { return a * a; }
+
+// canonical limbs (value < 2^(32N), not necessarily < p) -> Montgomery form, reduced
+template <class P>
+HD_INLINE Fp<P> to_mont(const uint32_t* raw) {
+  Fp<P> r, r2 = Fp<P>::r2();
+  mont_mul_limbs<P>(r.v, r2.v, raw);
+  return r;
+}
+// Montgomery form -> canonical limbs
+template <class P>
+HD_INLINE void from_mont(uint32_t* raw, const Fp<P>& a) {
+  uint32_t one[P::N];
+  one[0] = 1;
+  for (int i = 1; i < P::N; i++) one[i] = 0;
+  mont_mul_limbs<P>(raw, a.v, one);
+}
+// (hi * 2^(32N) + lo) mod p, in Montgomery form; hi, lo arbitrary N-limb values
+template <class P>
+HD_INLINE Fp<P> to_mont_wide(const uint32_t* lo, const uint32_t* hi) {
+  Fp<P> a, b, r2 = Fp<P>::r2(), r3 = Fp<P>::r3();
+  mont_mul_limbs<P>(a.v, r2.v, lo);
+  mont_mul_limbs<P>(b.v, r3.v, hi);
+  return a + b;
+}
+
+// a^e for a public exponent of the field (E::get<P>(i) = limb i, canonical); MSB-first
+// square-and-multiply.  The exponent is the same for every thread, so the branch is warp-uniform.
+struct ExpPM2 { template <class P> static HD_INLINE uint32_t get(int i) { return P::pm2(i); } };
+struct ExpPM1H { template <class P> static HD_INLINE uint32_t get(int i) { return P::pm1h(i); } };
+template <class P, class E>
+HD_NOINLINE Fp<P> pow_const(const Fp<P>& a) {
+  Fp<P> acc = Fp<P>::one();
+  bool started = false;
+  for (int i = P::N * 32 - 1; i >= 0; i--) {
+    if (started) acc = sqr(acc);
+    if ((E::template get<P>(i >> 5) >> (i & 31)) & 1u) {
+      acc = started ? acc * a : a;
+      started = true;
+    }
+  }
+  return acc;
+}
+// Fermat inverse; 0 -> 0 (same convention as the oracle's f_inv)
+template <class P>
+HD_INLINE Fp<P> inv(const Fp<P>& a) { return pow_const<P, ExpPM2>(a); }
+// Euler criterion; true for squares and for 0
+template <class P>
+HD_INLINE bool is_square(const Fp<P>& a) {
+  if (a.is_zero()) return true;
+  return pow_const<P, ExpPM1H>(a) == Fp<P>::one();
+}
+
+// canonical value > (p-1)/2 ?   (arkworks TE "x is negative" flag)
+template <class P>
+HD_INLINE bool is_high(const Fp<P>& a) {
+  uint32_t raw[P::N], h[P::N], t[P::N];
+  from_mont<P>(raw, a);
+  for (int i = 0; i < P::N; i++) h[i] = P::pm1h(i);
+  return MontChains<P::N>::sub(t, h, raw) != 0;  // borrow <=> raw > (p-1)/2
+}
+template <class P>
+HD_INLINE bool is_odd(const Fp<P>& a) {
+  uint32_t raw[P::N];
+  from_mont<P>(raw, a);
+  return raw[0] & 1u;
+}
+// is the raw N-limb value canonical (< p)?
+template <class P>
+HD_INLINE bool is_canonical(const uint32_t* raw) {
+  uint32_t m[P::N], t[P::N];
+  for (int i = 0; i < P::N; i++) m[i] = P::mod(i);
+  return MontChains<P::N>::sub(t, raw, m) != 0;
+}
+
+}  // namespace vrfs

@@ -1,0 +1,116 @@
+// K3 of SURVEY.md 2.5: twisted-Edwards points  a*x^2 + y^2 = 1 + d*x^2*y^2  in extended coordinates
+// (X:Y:Z:T), T = XY/Z - the device replacement for ark-ec's `twisted_edwards::Projective` behind
+// `AffinePoint<S>` (/root/reference/src/lib.rs:13-17) for Bandersnatch (a = -5) and Ed25519 (a = -1).
+// Formulas: add-2008-hwcd / dbl-2008-hwcd (unified; exception-free on the prime-order subgroup, and on
+// the whole curve when a is a square and d is not - Ed25519).
+#pragma once
+#include "gen/field_consts.cuh"
+
+namespace vrfs {
+
+// a generated constant (limb accessor) as a field element
+template <class P, uint32_t (*Fn)(int)> HD_INLINE Fp<P> fconst() { Fp<P> r; for (int i = 0; i < P::N; i++) r.v[i] = Fn(i); return r; }
+
+struct BandCurve {
+  typedef BlsFr Fq;
+  typedef BandFr Fr;
+  typedef BandConsts K;
+  typedef Fp<Fq> F;
+  static constexpr int COF_LOG2 = 2;
+  static constexpr bool HAS_GLV = true;
+  static HD_INLINE F mul_a(const F& x) { F t = dbl(dbl(x)); return neg(t + x); }   // a = -5
+  static HD_INLINE F d() { return fconst<Fq, K::D>(); }
+  static HD_INLINE F gx() { return fconst<Fq, K::GX>(); }
+  static HD_INLINE F gy() { return fconst<Fq, K::GY>(); }
+  static HD_INLINE F bx() { return fconst<Fq, K::BX>(); }
+  static HD_INLINE F by() { return fconst<Fq, K::BY>(); }
+};
+struct EdCurve {
+  typedef F25519 Fq;
+  typedef EdFr Fr;
+  typedef EdConsts K;
+  typedef Fp<Fq> F;
+  static constexpr int COF_LOG2 = 3;
+  static constexpr bool HAS_GLV = false;
+  static HD_INLINE F mul_a(const F& x) { return neg(x); }                           // a = -1
+  static HD_INLINE F d() { return fconst<Fq, K::D>(); }
+  static HD_INLINE F gx() { return fconst<Fq, K::GX>(); }
+  static HD_INLINE F gy() { return fconst<Fq, K::GY>(); }
+  static HD_INLINE F bx() { return fconst<Fq, K::BX>(); }
+  static HD_INLINE F by() { return fconst<Fq, K::BY>(); }
+};
+
+template <class C> struct TEPoint { typename C::F X, Y, Z, T; };
+// table entry forms: "cached" = (X, Y, Z, d*T); "affine cached" = (x, y, d*x*y) with Z = 1
+template <class C> struct TECached { typename C::F X, Y, Z, dT; };
+template <class C> struct TEAffCached { typename C::F x, y, dt; };
+
+template <class C> HD_INLINE void te_set_identity(TEPoint<C>& P) {
+  P.X = C::F::zero(); P.Y = C::F::one(); P.Z = C::F::one(); P.T = C::F::zero();
+}
+template <class C> HD_INLINE void te_from_affine(TEPoint<C>& P, const typename C::F& x, const typename C::F& y) {
+  P.X = x; P.Y = y; P.Z = C::F::one(); P.T = x * y;
+}
+template <class C> HD_INLINE bool te_is_identity(const TEPoint<C>& P) { return P.X.is_zero() && P.Y == P.Z; }
+template <class C> HD_INLINE bool te_on_curve(const typename C::F& x, const typename C::F& y) {
+  typename C::F xx = sqr(x), yy = sqr(y);
+  return C::mul_a(xx) + yy == C::F::one() + C::d() * xx * yy;
+}
+template <class C> HD_INLINE void te_to_cached(TECached<C>& r, const TEPoint<C>& P) {
+  r.X = P.X; r.Y = P.Y; r.Z = P.Z; r.dT = P.T * C::d();
+}
+
+// r = p + q (9M + 1 by d)
+template <class C> HD_NOINLINE void te_add(TEPoint<C>* r, const TEPoint<C>* p, const TEPoint<C>* q) {
+  typedef typename C::F F;
+  F A = p->X * q->X, B = p->Y * q->Y, Cc = p->T * q->T * C::d(), D = p->Z * q->Z;
+  F E = (p->X + p->Y) * (q->X + q->Y) - A - B;
+  F Fv = D - Cc, G = D + Cc, H = B - C::mul_a(A);
+  r->X = E * Fv; r->Y = G * H; r->T = E * H; r->Z = Fv * G;
+}
+// r = p + q, q cached, optionally negated (9M)
+template <class C> HD_NOINLINE void te_add_cached(TEPoint<C>* r, const TEPoint<C>* p, const TECached<C>* q, bool negate) {
+  typedef typename C::F F;
+  F qX = cneg(q->X, negate), qdT = cneg(q->dT, negate);
+  F A = p->X * qX, B = p->Y * q->Y, Cc = p->T * qdT, D = p->Z * q->Z;
+  F E = (p->X + p->Y) * (qX + q->Y) - A - B;
+  F Fv = D - Cc, G = D + Cc, H = B - C::mul_a(A);
+  r->X = E * Fv; r->Y = G * H; r->T = E * H; r->Z = Fv * G;
+}
+// r = p + q, q affine cached, optionally negated (8M)
+template <class C> HD_NOINLINE void te_madd(TEPoint<C>* r, const TEPoint<C>* p, const TEAffCached<C>* q, bool negate) {
+  typedef typename C::F F;
+  F qx = cneg(q->x, negate), qdt = cneg(q->dt, negate);
+  F A = p->X * qx, B = p->Y * q->y, Cc = p->T * qdt, D = p->Z;
+  F E = (p->X + p->Y) * (qx + q->y) - A - B;
+  F Fv = D - Cc, G = D + Cc, H = B - C::mul_a(A);
+  r->X = E * Fv; r->Y = G * H; r->T = E * H; r->Z = Fv * G;
+}
+// r = 2p (4S + 4M; T of the result is skipped when the next operation is another doubling)
+template <class C> HD_NOINLINE void te_dbl(TEPoint<C>* r, const TEPoint<C>* p, bool want_t) {
+  typedef typename C::F F;
+  F A = sqr(p->X), B = sqr(p->Y), Cc = dbl(sqr(p->Z)), D = C::mul_a(A);
+  F E = sqr(p->X + p->Y) - A - B;
+  F G = D + B, Fv = G - Cc, H = D - B;
+  r->X = E * Fv; r->Y = G * H; r->Z = Fv * G;
+  if (want_t) r->T = E * H;
+}
+template <class C> HD_INLINE void te_neg(TEPoint<C>& P) { P.X = neg(P.X); P.T = neg(P.T); }
+
+// ---- Bandersnatch GLV endomorphism psi(P) = lambda*P on the prime-order subgroup:
+// psi(x,y) = (c(1-y^2)/(xy), b(y^2+b)/(y^2-b));  projectively (f*h : g*XY : XY*h : f*g) with
+// f = c(Z^2-Y^2), g = b(Y^2+bZ^2), h = Y^2-bZ^2.  x = 0 (identity / the 2-torsion point) maps to identity.
+HD_NOINLINE void band_endo(TEPoint<BandCurve>* r, const TEPoint<BandCurve>* p) {
+  typedef BandCurve::F F;
+  F b = fconst<BlsFr, BandConsts::ENDO_B>(), c = fconst<BlsFr, BandConsts::ENDO_C>();
+  F yy = sqr(p->Y), zz = sqr(p->Z), xy = p->X * p->Y, bzz = b * zz;
+  F f = c * (zz - yy), g = b * (yy + bzz), h = yy - bzz;
+  bool degenerate = p->X.is_zero();
+  TEPoint<BandCurve> id; te_set_identity(id);
+  r->X = select(degenerate, id.X, f * h);
+  r->Y = select(degenerate, id.Y, g * xy);
+  r->Z = select(degenerate, id.Z, xy * h);
+  r->T = select(degenerate, id.T, f * g);
+}
+
+}  // namespace vrfs

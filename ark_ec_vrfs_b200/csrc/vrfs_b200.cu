@@ -1,0 +1,402 @@
+// vrfs_b200: kernels + the C ABI of include/vrfs_b200.h.  sm_100a only; no CPU fallback - every entry
+// point launches kernels on the context's device and reports CUDA failures as VRFS_CUDA_ERROR.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <new>
+
+#include "../../include/vrfs_b200.h"
+#include "suite.cuh"
+
+using namespace vrfs;
+
+// =================================================================================================
+// kernels
+// =================================================================================================
+#define LINCOMB_THREADS 128
+
+// one fixed-base table (K8): thread (w, d) computes (d * 256^w) * B in affine cached form
+template <class C>
+__global__ void k_te_fixed_table(TEAffCached<C>* out, int blinding) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= TeTraits<C>::FIX_WINDOWS * TeTraits<C>::FIX_ENTRIES) return;
+  int w = t / TeTraits<C>::FIX_ENTRIES, d = t % TeTraits<C>::FIX_ENTRIES;
+  TEAffCached<C> e;
+  te_fixed_table_entry<C>(e, blinding ? C::bx() : C::gx(), blinding ? C::by() : C::gy(), w, d);
+  out[t] = e;
+}
+
+// K7/K8/K9a: R_i = sum var + sum fixed, projective out.  Persistent grid-stride so that the window-table
+// slab is per resident thread (L2-resident), not per item.
+template <class C, int NV, int NF>
+__global__ void __launch_bounds__(LINCOMB_THREADS) k_te_lincomb(LincombArgs A) {
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+  TECached<C>* slab = reinterpret_cast<TECached<C>*>(A.slab + (size_t)tid * te_slab_bytes<C>(NV));
+  for (uint32_t item = tid; item < A.n; item += nthreads) {
+    TEPoint<C> acc;
+    bool ok = te_lincomb_item<C, NV, NF>(A, item, slab, acc);
+    uint4* o = reinterpret_cast<uint4*>(A.out_xyz + (size_t)item * 24);
+    const uint4* sx = reinterpret_cast<const uint4*>(acc.X.v);
+    const uint4* sy = reinterpret_cast<const uint4*>(acc.Y.v);
+    const uint4* sz = reinterpret_cast<const uint4*>(acc.Z.v);
+    o[0] = sx[0]; o[1] = sx[1]; o[2] = sy[0]; o[3] = sy[1]; o[4] = sz[0]; o[5] = sz[1];
+    if (A.valid != nullptr && !ok) A.valid[item] = 0;
+  }
+}
+
+// K9b: shared inversion, 5 point encodings, SHA-512 challenge, compare
+template <class S>
+__global__ void __launch_bounds__(128) k_ietf_verify_finish(uint32_t n, const uint8_t* pk, const uint8_t* input, const uint8_t* output,
+                                                             const uint8_t* c, const uint32_t* u_xyz, const uint32_t* v_xyz,
+                                                             const uint8_t* ad, const uint64_t* ad_off, const uint8_t* valid, uint8_t* out_ok) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint8_t* a = ad ? ad + ad_off[i] : nullptr;
+  uint32_t alen = ad ? (uint32_t)(ad_off[i + 1] - ad_off[i]) : 0u;
+  bool ok = ietf_verify_finish_item<S>(pk + (size_t)64 * i, input + (size_t)64 * i, output + (size_t)64 * i, c + (size_t)32 * i,
+                                       u_xyz + (size_t)24 * i, v_xyz + (size_t)24 * i, a, alen);
+  out_ok[i] = (uint8_t)(ok && valid[i]);
+}
+
+// integer-pipe roofline microbenchmarks: independent multiply-accumulate chains per thread
+template <int VARIANT>
+__global__ void __launch_bounds__(256) k_mac_bench(uint32_t* out, int iters, unsigned long long* cycles) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long c0 = clock64();
+  if (VARIANT == 0) {          // mad.wide.u32, 8 independent 64-bit accumulators
+    unsigned long long a0 = t, a1 = t + 1, a2 = t + 2, a3 = t + 3, a4 = t + 4, a5 = t + 5, a6 = t + 6, a7 = t + 7;
+    uint32_t x = t * 2654435761u + 12345u, y = t ^ 0x9e3779b9u;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        asm volatile("mad.wide.u32 %0, %8, %9, %0; mad.wide.u32 %1, %8, %9, %1; mad.wide.u32 %2, %8, %9, %2; mad.wide.u32 %3, %8, %9, %3;"
+                     "mad.wide.u32 %4, %8, %9, %4; mad.wide.u32 %5, %8, %9, %5; mad.wide.u32 %6, %8, %9, %6; mad.wide.u32 %7, %8, %9, %7;"
+                     : "+l"(a0), "+l"(a1), "+l"(a2), "+l"(a3), "+l"(a4), "+l"(a5), "+l"(a6), "+l"(a7) : "r"(x), "r"(y));
+      }
+    }
+    unsigned long long s = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+    out[t] = (uint32_t)s ^ (uint32_t)(s >> 32);
+  } else if (VARIANT == 1) {   // mad.lo.u32, 8 independent 32-bit accumulators
+    uint32_t a0 = t, a1 = t + 1, a2 = t + 2, a3 = t + 3, a4 = t + 4, a5 = t + 5, a6 = t + 6, a7 = t + 7;
+    uint32_t x = t * 2654435761u + 12345u, y = t ^ 0x9e3779b9u;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        asm volatile("mad.lo.u32 %0, %8, %9, %0; mad.lo.u32 %1, %8, %9, %1; mad.lo.u32 %2, %8, %9, %2; mad.lo.u32 %3, %8, %9, %3;"
+                     "mad.lo.u32 %4, %8, %9, %4; mad.lo.u32 %5, %8, %9, %5; mad.lo.u32 %6, %8, %9, %6; mad.lo.u32 %7, %8, %9, %7;"
+                     : "+r"(a0), "+r"(a1), "+r"(a2), "+r"(a3), "+r"(a4), "+r"(a5), "+r"(a6), "+r"(a7) : "r"(x), "r"(y));
+      }
+    }
+    out[t] = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+  } else if (VARIANT == 2) {   // dependent chain of BLS12-381 Fr Montgomery products (136 MAC32 each); 32 per iteration
+    Fp<BlsFr> a, b;
+    for (int i = 0; i < 8; i++) { a.v[i] = t + i; b.v[i] = (t ^ 0x5bd1e995u) + 7 * i; }
+    a.v[7] &= 0x3fffffffu; b.v[7] &= 0x3fffffffu;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll 1
+      for (int r = 0; r < 16; r++) { a = a * b; b = b * a; }
+    }
+    uint32_t s = 0;
+    for (int i = 0; i < 8; i++) s ^= a.v[i] ^ b.v[i];
+    out[t] = s;
+  } else if (VARIANT == 3) {   // two independent chains of products per thread (more ILP)
+    Fp<BlsFr> a, b, c, d;
+    for (int i = 0; i < 8; i++) { a.v[i] = t + i; b.v[i] = (t ^ 0x5bd1e995u) + 7 * i; c.v[i] = t * 3 + i; d.v[i] = t * 5 + i; }
+    a.v[7] &= 0x3fffffffu; b.v[7] &= 0x3fffffffu; c.v[7] &= 0x3fffffffu; d.v[7] &= 0x3fffffffu;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll 1
+      for (int r = 0; r < 8; r++) { a = a * b; c = c * d; b = b * a; d = d * c; }
+    }
+    uint32_t s = 0;
+    for (int i = 0; i < 8; i++) s ^= a.v[i] ^ b.v[i] ^ c.v[i] ^ d.v[i];
+    out[t] = s;
+  } else {                     // VARIANT 4: mad.hi.u32
+    uint32_t a0 = t, a1 = t + 1, a2 = t + 2, a3 = t + 3, a4 = t + 4, a5 = t + 5, a6 = t + 6, a7 = t + 7;
+    uint32_t x = t * 2654435761u + 12345u, y = t ^ 0x9e3779b9u;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        asm volatile("mad.hi.u32 %0, %8, %9, %0; mad.hi.u32 %1, %8, %9, %1; mad.hi.u32 %2, %8, %9, %2; mad.hi.u32 %3, %8, %9, %3;"
+                     "mad.hi.u32 %4, %8, %9, %4; mad.hi.u32 %5, %8, %9, %5; mad.hi.u32 %6, %8, %9, %6; mad.hi.u32 %7, %8, %9, %7;"
+                     : "+r"(a0), "+r"(a1), "+r"(a2), "+r"(a3), "+r"(a4), "+r"(a5), "+r"(a6), "+r"(a7) : "r"(x), "r"(y));
+      }
+    }
+    out[t] = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+  }
+  unsigned long long c1 = clock64();
+  if (threadIdx.x == 0 && blockIdx.x == 0) *cycles = c1 - c0;
+}
+
+// =================================================================================================
+// context
+// =================================================================================================
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+enum { BUF_IN0, BUF_IN1, BUF_IN2, BUF_IN3, BUF_IN4, BUF_AD, BUF_OFF, BUF_OUT0, BUF_OUT1, BUF_W0, BUF_W1, BUF_W2, BUF_W3, BUF_VALID, BUF_SLAB, BUF_COUNT };
+
+struct vrfs_ctx {
+  int device = 0, sms = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  char err[512] = {0};
+  uint64_t launches = 0;
+  DevBuf buf[BUF_COUNT];
+  void* fixtab[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};   // [suite][G | blinding base]
+};
+
+static vrfs_status fail(vrfs_ctx* c, vrfs_status st, const char* fmt, ...) {
+  if (c) { va_list ap; va_start(ap, fmt); vsnprintf(c->err, sizeof c->err, fmt, ap); va_end(ap); }
+  return st;
+}
+#define CU(call)                                                                                                   \
+  do {                                                                                                             \
+    cudaError_t e_ = (call);                                                                                       \
+    if (e_ != cudaSuccess) return fail(ctx, VRFS_CUDA_ERROR, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+#define ST(call)                          \
+  do {                                    \
+    vrfs_status s_ = (call);              \
+    if (s_ != VRFS_OK) return s_;         \
+  } while (0)
+#define LAUNCHED(ctx) do { (ctx)->launches++; CU(cudaGetLastError()); } while (0)
+
+static vrfs_status ensure(vrfs_ctx* ctx, int which, size_t bytes, void** out) {
+  DevBuf& b = ctx->buf[which];
+  if (bytes == 0) bytes = 16;
+  if (b.cap < bytes) {
+    if (b.p) { CU(cudaStreamSynchronize(ctx->stream)); CU(cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
+    size_t cap = bytes + bytes / 8 + 256;
+    CU(cudaMalloc(&b.p, cap));
+    b.cap = cap;
+  }
+  *out = b.p;
+  return VRFS_OK;
+}
+static inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
+
+template <class C>
+static vrfs_status build_fixed_tables(vrfs_ctx* ctx, int suite) {
+  const int n = TeTraits<C>::FIX_WINDOWS * TeTraits<C>::FIX_ENTRIES;
+  for (int b = 0; b < 2; b++) {
+    CU(cudaMalloc(&ctx->fixtab[suite][b], sizeof(TEAffCached<C>) * n));
+    k_te_fixed_table<C><<<(n + 63) / 64, 64, 0, ctx->stream>>>(reinterpret_cast<TEAffCached<C>*>(ctx->fixtab[suite][b]), b);
+    LAUNCHED(ctx);
+  }
+  return VRFS_OK;
+}
+
+extern "C" int vrfs_abi_version(void) { return 1; }
+
+extern "C" vrfs_status vrfs_ctx_create(int device, vrfs_ctx** out) {
+  if (!out) return VRFS_BAD_ARG;
+  *out = nullptr;
+  vrfs_ctx* ctx = new (std::nothrow) vrfs_ctx();
+  if (!ctx) return VRFS_CUDA_ERROR;
+  *out = ctx;   // returned even on failure so that vrfs_last_error can be read; destroy it either way
+  ctx->device = device;
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return fail(ctx, VRFS_CUDA_ERROR, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+  ctx->sms = prop.multiProcessorCount;
+  CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CU(cudaEventCreate(&ctx->ev0));
+  CU(cudaEventCreate(&ctx->ev1));
+  ST(build_fixed_tables<BandCurve>(ctx, VRFS_BANDERSNATCH_ELL2));
+  ST(build_fixed_tables<EdCurve>(ctx, VRFS_ED25519_TAI));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return VRFS_OK;
+}
+extern "C" void vrfs_ctx_destroy(vrfs_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  for (int i = 0; i < BUF_COUNT; i++) if (ctx->buf[i].p) cudaFree(ctx->buf[i].p);
+  for (int s = 0; s < 3; s++) for (int b = 0; b < 2; b++) if (ctx->fixtab[s][b]) cudaFree(ctx->fixtab[s][b]);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+extern "C" vrfs_status vrfs_ctx_sync(vrfs_ctx* ctx) {
+  if (!ctx) return VRFS_BAD_ARG;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return VRFS_OK;
+}
+extern "C" const char* vrfs_last_error(const vrfs_ctx* ctx) { return ctx ? ctx->err : "null context"; }
+extern "C" void* vrfs_ctx_stream(vrfs_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+extern "C" uint64_t vrfs_ctx_launch_count(const vrfs_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int vrfs_suite_challenge_len(vrfs_suite s) { return s == VRFS_BANDERSNATCH_ELL2 ? 32 : 16; }
+extern "C" int vrfs_suite_hash_len(vrfs_suite s) { return s == VRFS_P256_TAI ? 32 : 64; }
+extern "C" int vrfs_suite_point_enc_len(vrfs_suite s) { return s == VRFS_P256_TAI ? 33 : 32; }
+
+// =================================================================================================
+// lincomb launcher
+// =================================================================================================
+template <class C, int NV, int NF>
+static vrfs_status launch_lincomb(vrfs_ctx* ctx, LincombArgs A) {
+  if (A.n == 0) return VRFS_OK;
+  int per_sm = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_te_lincomb<C, NV, NF>, LINCOMB_THREADS, 0));
+  if (per_sm < 1) per_sm = 1;
+  uint32_t blocks = (uint32_t)(ctx->sms * per_sm);
+  uint32_t need = (A.n + LINCOMB_THREADS - 1) / LINCOMB_THREADS;
+  if (blocks > need) blocks = need;
+  void* slab = nullptr;
+  ST(ensure(ctx, BUF_SLAB, (size_t)blocks * LINCOMB_THREADS * te_slab_bytes<C>(NV), &slab));
+  A.slab = (uint8_t*)slab;
+  k_te_lincomb<C, NV, NF><<<blocks, LINCOMB_THREADS, 0, ctx->stream>>>(A);
+  LAUNCHED(ctx);
+  return VRFS_OK;
+}
+
+// =================================================================================================
+// ietf verify
+// =================================================================================================
+template <class S>
+static vrfs_status ietf_verify_dev(vrfs_ctx* ctx, size_t n, const uint8_t* pk, const uint8_t* input, const uint8_t* output, const uint8_t* c,
+                                   const uint8_t* s, const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_ok) {
+  typedef typename S::C C;
+  void *u = nullptr, *v = nullptr, *valid = nullptr;
+  ST(ensure(ctx, BUF_W0, n * 96, &u));
+  ST(ensure(ctx, BUF_W1, n * 96, &v));
+  ST(ensure(ctx, BUF_VALID, n, &valid));
+  CU(cudaMemsetAsync(valid, 1, n, ctx->stream));
+  LincombArgs A = {};
+  A.n = (uint32_t)n;
+  A.valid = (uint8_t*)valid;
+  // U = s*G - c*Y
+  A.var[0] = {pk, 64, c, 32, 1};
+  A.fix[0] = {s, 32, 0, ctx->fixtab[S::C::HAS_GLV ? VRFS_BANDERSNATCH_ELL2 : VRFS_ED25519_TAI][0]};
+  A.out_xyz = (uint32_t*)u;
+  ST((launch_lincomb<C, 1, 1>(ctx, A)));
+  // V = s*I - c*O
+  A.var[0] = {input, 64, s, 32, 0};
+  A.var[1] = {output, 64, c, 32, 1};
+  A.out_xyz = (uint32_t*)v;
+  ST((launch_lincomb<C, 2, 0>(ctx, A)));
+  k_ietf_verify_finish<S><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((uint32_t)n, pk, input, output, c, (const uint32_t*)u,
+                                                                                (const uint32_t*)v, ad, ad_off, (const uint8_t*)valid, out_ok);
+  LAUNCHED(ctx);
+  return VRFS_OK;
+}
+
+extern "C" vrfs_status vrfs_ietf_verify_batch_dev(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* pk, const uint8_t* input,
+                                                  const uint8_t* output, const uint8_t* c, const uint8_t* s, const uint8_t* ad,
+                                                  const uint64_t* ad_off, uint8_t* out_ok) {
+  if (!ctx) return VRFS_BAD_ARG;
+  if (n == 0) return VRFS_OK;
+  if (!pk || !input || !output || !c || !s || !out_ok || (ad && !ad_off)) return fail(ctx, VRFS_BAD_ARG, "null buffer");
+  if (n > 0x7fffffffu) return fail(ctx, VRFS_BAD_ARG, "batch too large (n < 2^31)");
+  if (!aligned16(pk) || !aligned16(input) || !aligned16(output) || !aligned16(c) || !aligned16(s)) return fail(ctx, VRFS_BAD_ARG, "device buffers must be 16-byte aligned");
+  CU(cudaSetDevice(ctx->device));
+  switch (suite) {
+    case VRFS_BANDERSNATCH_ELL2: return ietf_verify_dev<BandSuite>(ctx, n, pk, input, output, c, s, ad, ad_off, out_ok);
+    case VRFS_ED25519_TAI: return ietf_verify_dev<EdSuite>(ctx, n, pk, input, output, c, s, ad, ad_off, out_ok);
+    default: return fail(ctx, VRFS_UNSUPPORTED, "suite %d not implemented for ietf verify", (int)suite);
+  }
+}
+
+// host -> device staging of one input; returns the device pointer
+static vrfs_status stage_in(vrfs_ctx* ctx, int which, const void* host, size_t bytes, const uint8_t** dev) {
+  void* d = nullptr;
+  ST(ensure(ctx, which, bytes, &d));
+  if (bytes) CU(cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  *dev = (const uint8_t*)d;
+  return VRFS_OK;
+}
+static vrfs_status stage_ad(vrfs_ctx* ctx, size_t n, const uint8_t* ad, const uint64_t* ad_off, const uint8_t** d_ad, const uint64_t** d_off) {
+  *d_ad = nullptr; *d_off = nullptr;
+  if (!ad_off) return VRFS_OK;
+  for (size_t i = 0; i < n; i++) if (ad_off[i + 1] < ad_off[i]) return fail(ctx, VRFS_BAD_ARG, "offsets must be non-decreasing");
+  if (ad_off[n] > 0 && !ad) return fail(ctx, VRFS_BAD_ARG, "null data buffer with non-empty offsets");
+  const uint8_t* o = nullptr;
+  ST(stage_in(ctx, BUF_AD, ad, (size_t)ad_off[n], d_ad));
+  ST(stage_in(ctx, BUF_OFF, ad_off, (n + 1) * sizeof(uint64_t), &o));
+  *d_off = (const uint64_t*)o;
+  return VRFS_OK;
+}
+
+extern "C" vrfs_status vrfs_ietf_verify_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* pk, const uint8_t* input,
+                                              const uint8_t* output, const uint8_t* c, const uint8_t* s, const uint8_t* ad,
+                                              const uint64_t* ad_off, uint8_t* out_ok) {
+  if (!ctx) return VRFS_BAD_ARG;
+  if (n == 0) return VRFS_OK;
+  if (!pk || !input || !output || !c || !s || !out_ok) return fail(ctx, VRFS_BAD_ARG, "null buffer");
+  CU(cudaSetDevice(ctx->device));
+  const uint8_t *d_pk, *d_in, *d_out, *d_c, *d_s, *d_ad;
+  const uint64_t* d_off;
+  ST(stage_in(ctx, BUF_IN0, pk, n * 64, &d_pk));
+  ST(stage_in(ctx, BUF_IN1, input, n * 64, &d_in));
+  ST(stage_in(ctx, BUF_IN2, output, n * 64, &d_out));
+  ST(stage_in(ctx, BUF_IN3, c, n * 32, &d_c));
+  ST(stage_in(ctx, BUF_IN4, s, n * 32, &d_s));
+  ST(stage_ad(ctx, n, ad, ad_off, &d_ad, &d_off));
+  void* d_ok = nullptr;
+  ST(ensure(ctx, BUF_OUT0, n, &d_ok));
+  ST(vrfs_ietf_verify_batch_dev(ctx, suite, n, d_pk, d_in, d_out, d_c, d_s, d_ad, d_off, (uint8_t*)d_ok));
+  CU(cudaMemcpyAsync(out_ok, d_ok, n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return VRFS_OK;
+}
+
+// =================================================================================================
+// measurement helper
+// =================================================================================================
+extern "C" vrfs_status vrfs_measure_mac32_peak(vrfs_ctx* ctx, int variant, double* out_mac_per_s, double* out_sm_mhz_est) {
+  if (!ctx || !out_mac_per_s) return VRFS_BAD_ARG;
+  CU(cudaSetDevice(ctx->device));
+  const int threads = 256, blocks = ctx->sms * 8;
+  void *out = nullptr, *cyc = nullptr;
+  ST(ensure(ctx, BUF_W0, (size_t)threads * blocks * 4, &out));
+  ST(ensure(ctx, BUF_W1, 64, &cyc));
+  int iters = (variant == 2 || variant == 3) ? 64 : 4096;
+  double macs_per_thread_iter = (variant == 2 || variant == 3) ? 32.0 * 136.0 : 32.0;
+  float ms = 0;
+  for (int rep = 0; rep < 3; rep++) {
+    CU(cudaEventRecord(ctx->ev0, ctx->stream));
+    switch (variant) {
+      case 0: k_mac_bench<0><<<blocks, threads, 0, ctx->stream>>>((uint32_t*)out, iters, (unsigned long long*)cyc); break;
+      case 1: k_mac_bench<1><<<blocks, threads, 0, ctx->stream>>>((uint32_t*)out, iters, (unsigned long long*)cyc); break;
+      case 2: k_mac_bench<2><<<blocks, threads, 0, ctx->stream>>>((uint32_t*)out, iters, (unsigned long long*)cyc); break;
+      case 3: k_mac_bench<3><<<blocks, threads, 0, ctx->stream>>>((uint32_t*)out, iters, (unsigned long long*)cyc); break;
+      case 4: k_mac_bench<4><<<blocks, threads, 0, ctx->stream>>>((uint32_t*)out, iters, (unsigned long long*)cyc); break;
+      default: return fail(ctx, VRFS_BAD_ARG, "unknown variant %d", variant);
+    }
+    LAUNCHED(ctx);
+    CU(cudaEventRecord(ctx->ev1, ctx->stream));
+    CU(cudaEventSynchronize(ctx->ev1));
+    CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  }
+  unsigned long long cycles = 0;
+  CU(cudaMemcpy(&cycles, cyc, sizeof cycles, cudaMemcpyDeviceToHost));
+  *out_mac_per_s = macs_per_thread_iter * iters * (double)threads * blocks / (ms * 1e-3);
+  if (out_sm_mhz_est) *out_sm_mhz_est = (double)cycles / (ms * 1e-3) / 1e6;
+  return VRFS_OK;
+}
+
+// =================================================================================================
+// entry points still to be implemented in this round (they fail loudly, never fall back to the CPU)
+// =================================================================================================
+#define NOT_YET(name) return fail(ctx, VRFS_UNSUPPORTED, name " is not implemented yet")
+extern "C" vrfs_status vrfs_secret_from_seed_batch(vrfs_ctx* ctx, vrfs_suite, size_t, const uint8_t*, const uint64_t*, uint8_t*, uint8_t*) { NOT_YET("vrfs_secret_from_seed_batch"); }
+extern "C" vrfs_status vrfs_data_to_point_batch(vrfs_ctx* ctx, vrfs_suite, size_t, const uint8_t*, const uint64_t*, uint8_t*, uint8_t*) { NOT_YET("vrfs_data_to_point_batch"); }
+extern "C" vrfs_status vrfs_output_batch(vrfs_ctx* ctx, vrfs_suite, size_t, const uint8_t*, const uint8_t*, uint8_t*) { NOT_YET("vrfs_output_batch"); }
+extern "C" vrfs_status vrfs_point_to_hash_batch(vrfs_ctx* ctx, vrfs_suite, size_t, const uint8_t*, uint8_t*) { NOT_YET("vrfs_point_to_hash_batch"); }
+extern "C" vrfs_status vrfs_point_encode_batch(vrfs_ctx* ctx, vrfs_suite, size_t, const uint8_t*, uint8_t*) { NOT_YET("vrfs_point_encode_batch"); }
+extern "C" vrfs_status vrfs_point_decode_batch(vrfs_ctx* ctx, vrfs_suite, size_t, const uint8_t*, uint8_t*, uint8_t*) { NOT_YET("vrfs_point_decode_batch"); }
+extern "C" vrfs_status vrfs_nonce_batch(vrfs_ctx* ctx, vrfs_suite, size_t, const uint8_t*, const uint8_t*, uint8_t*) { NOT_YET("vrfs_nonce_batch"); }
+extern "C" vrfs_status vrfs_ietf_prove_batch(vrfs_ctx* ctx, vrfs_suite, size_t, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*, const uint64_t*, uint8_t*, uint8_t*) { NOT_YET("vrfs_ietf_prove_batch"); }
+extern "C" vrfs_status vrfs_pedersen_prove_batch(vrfs_ctx* ctx, vrfs_suite, size_t, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*, const uint64_t*, uint8_t*, uint8_t*) { NOT_YET("vrfs_pedersen_prove_batch"); }
+extern "C" vrfs_status vrfs_pedersen_verify_batch(vrfs_ctx* ctx, vrfs_suite, size_t, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*, const uint64_t*, uint8_t*) { NOT_YET("vrfs_pedersen_verify_batch"); }
+extern "C" vrfs_status vrfs_msm_g1_bls12_381(vrfs_ctx* ctx, size_t, const uint8_t*, const uint8_t*, int, uint8_t*) { NOT_YET("vrfs_msm_g1_bls12_381"); }
+extern "C" vrfs_status vrfs_msm_g1_partial(vrfs_ctx* ctx, size_t, const uint8_t*, const uint8_t*, int, uint8_t*) { NOT_YET("vrfs_msm_g1_partial"); }
+extern "C" vrfs_status vrfs_g1_sum_partials(vrfs_ctx* ctx, int, int, const uint8_t*, uint8_t*) { NOT_YET("vrfs_g1_sum_partials"); }

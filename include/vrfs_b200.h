@@ -1,0 +1,110 @@
+/* vrfs_b200 - C ABI of the B200 batched VRF engine.
+ *
+ * This is the drop-in boundary for the data-parallel hot path of `ark-ec-vrfs` (= `ark-vrf` 0.1.0, the
+ * sole dependency at /root/reference/Cargo.toml:12).  The reference has no FFI of its own: its boundary
+ * is the Rust trait API whose names are re-exported at /root/reference/src/lib.rs:13-17
+ * (`Suite, Secret, Public, Input, Output, ietf, pedersen, ring, codec, utils`).  Each entry point below
+ * is the BATCH form of one of those items; the Rust shim that keeps the crate's per-item API on top of
+ * it is shown in INTEGRATION.md.  Behaviour is specified in SURVEY.md Appendix A.
+ *
+ * Conventions (all entry points):
+ *   - scalars (`Secret`, proof `c`, `s`, `sb`, blinding): 32 bytes little-endian; values >= r are
+ *     reduced mod r on load, like `ScalarField::from_le_bytes_mod_order`.  For the SEC1 suite the wire
+ *     encoding is big-endian; the ABI is little-endian for every suite.
+ *   - points (`Public`, `Input`, `Output`, proof points): affine x || y, 32 bytes little-endian each,
+ *     canonical (< p).  Non-canonical or off-curve points make that item fail (out_ok = 0 / zeroed
+ *     output); the call itself still returns VRFS_OK.  Points must lie in the prime-order subgroup,
+ *     which the reference's typed values guarantee (arkworks validates on deserialisation); the
+ *     short-Weierstrass identity is 64 zero bytes.
+ *   - variable-length data (`ad`, h2c `data`, seeds): one concatenated byte buffer + n+1 offsets
+ *     (uint64).  A NULL `ad` means every item has empty additional data.
+ *   - BLS12-381 G1 points: affine x || y, 48 bytes little-endian each; identity = 96 zero bytes.
+ *   - The caller owns every buffer; nothing is retained after return.  No exceptions, no aborts:
+ *     every failure is a status code; `vrfs_last_error` gives text.  There is NO CPU fallback: without
+ *     a CUDA device every call fails with VRFS_CUDA_ERROR.
+ *   - `vrfs_*_batch`      : HOST buffers; copies in, runs, copies out, returns when done.
+ *     `vrfs_*_batch_dev`  : DEVICE buffers (16-byte aligned) of the same layout, enqueued on the
+ *                           context's stream; results are ready after `vrfs_ctx_sync`.
+ *   - One context per GPU (one process per GPU under torch.distributed / NCCL); calls on one context
+ *     must not overlap.
+ */
+#ifndef VRFS_B200_H
+#define VRFS_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vrfs_ctx vrfs_ctx;
+typedef enum { VRFS_OK = 0, VRFS_INVALID_DATA = 1, VRFS_CUDA_ERROR = 2, VRFS_BAD_ARG = 3, VRFS_UNSUPPORTED = 4 } vrfs_status;
+/* `suites::{bandersnatch, ed25519, secp256r1}` (lib.rs:13-17) */
+typedef enum { VRFS_BANDERSNATCH_ELL2 = 0, VRFS_ED25519_TAI = 1, VRFS_P256_TAI = 2 } vrfs_suite;
+
+int vrfs_abi_version(void);
+/* device = CUDA ordinal.  Builds the fixed-base tables for G and the Pedersen blinding base B. */
+vrfs_status vrfs_ctx_create(int device, vrfs_ctx** out);
+void vrfs_ctx_destroy(vrfs_ctx* ctx);
+vrfs_status vrfs_ctx_sync(vrfs_ctx* ctx);
+const char* vrfs_last_error(const vrfs_ctx* ctx);
+/* the CUDA stream (cudaStream_t) the context enqueues on; lets a caller order its own work after it */
+void* vrfs_ctx_stream(vrfs_ctx* ctx);
+/* number of kernel launches issued by this context so far (bench.py's `gpu_launches`) */
+uint64_t vrfs_ctx_launch_count(const vrfs_ctx* ctx);
+/* suite constants: SUITE_ID-independent sizes used by callers to size buffers */
+int vrfs_suite_challenge_len(vrfs_suite s);   /* Suite::CHALLENGE_LEN */
+int vrfs_suite_hash_len(vrfs_suite s);        /* HashOutput<S> length */
+int vrfs_suite_point_enc_len(vrfs_suite s);   /* Codec::point_encode length */
+
+/* Secret::from_seed + Public (lib.rs:13-17; A.3): sk = LE(H(seed)) mod r, pk = sk*G.  out_pk may be NULL. */
+vrfs_status vrfs_secret_from_seed_batch(vrfs_ctx*, vrfs_suite, size_t n, const uint8_t* seeds, const uint64_t* seed_off,
+                                        uint8_t* out_sk /*n*32*/, uint8_t* out_pk /*n*64*/);
+/* Input::new -> Suite::data_to_point (A.5).  out_ok[i] = 0 if no point was found. */
+vrfs_status vrfs_data_to_point_batch(vrfs_ctx*, vrfs_suite, size_t n, const uint8_t* data, const uint64_t* data_off,
+                                     uint8_t* out_pts /*n*64*/, uint8_t* out_ok /*n*/);
+/* Secret::output: O = sk * I */
+vrfs_status vrfs_output_batch(vrfs_ctx*, vrfs_suite, size_t n, const uint8_t* sk, const uint8_t* input, uint8_t* out_output /*n*64*/);
+/* Output::hash -> Suite::point_to_hash (A.8) */
+vrfs_status vrfs_point_to_hash_batch(vrfs_ctx*, vrfs_suite, size_t n, const uint8_t* pts, uint8_t* out_hash /*n*hash_len*/);
+/* codec::point_encode / point_decode (A.2) */
+vrfs_status vrfs_point_encode_batch(vrfs_ctx*, vrfs_suite, size_t n, const uint8_t* pts, uint8_t* out_enc /*n*enc_len*/);
+vrfs_status vrfs_point_decode_batch(vrfs_ctx*, vrfs_suite, size_t n, const uint8_t* enc, uint8_t* out_pts /*n*64*/, uint8_t* out_ok);
+/* Suite::nonce (A.6) */
+vrfs_status vrfs_nonce_batch(vrfs_ctx*, vrfs_suite, size_t n, const uint8_t* sk, const uint8_t* input, uint8_t* out_k /*n*32*/);
+
+/* ietf::Prover::prove (A.9).  out_c, out_s: n*32 (c is a full 32-byte LE scalar whose value fits cLen bytes). */
+vrfs_status vrfs_ietf_prove_batch(vrfs_ctx*, vrfs_suite, size_t n, const uint8_t* sk, const uint8_t* input, const uint8_t* output,
+                                  const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_c, uint8_t* out_s);
+/* ietf::Verifier::verify (A.9) - the headline metric.  out_ok[i] = 1 iff the proof verifies (Ok(())),
+ * 0 for Error::VerificationFailure / Error::InvalidData. */
+vrfs_status vrfs_ietf_verify_batch(vrfs_ctx*, vrfs_suite, size_t n, const uint8_t* pk, const uint8_t* input, const uint8_t* output,
+                                   const uint8_t* c, const uint8_t* s, const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_ok);
+vrfs_status vrfs_ietf_verify_batch_dev(vrfs_ctx*, vrfs_suite, size_t n, const uint8_t* d_pk, const uint8_t* d_input,
+                                       const uint8_t* d_output, const uint8_t* d_c, const uint8_t* d_s, const uint8_t* d_ad,
+                                       const uint64_t* d_ad_off, uint8_t* d_out_ok);
+
+/* pedersen::Prover::prove / Verifier::verify (A.10).  proof = pk_com || r || ok (3 x 64-byte affine) || s || sb (2 x 32 bytes) = 256 bytes. */
+vrfs_status vrfs_pedersen_prove_batch(vrfs_ctx*, vrfs_suite, size_t n, const uint8_t* sk, const uint8_t* input, const uint8_t* output,
+                                      const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_proof /*n*256*/, uint8_t* out_blinding /*n*32*/);
+vrfs_status vrfs_pedersen_verify_batch(vrfs_ctx*, vrfs_suite, size_t n, const uint8_t* input, const uint8_t* output, const uint8_t* proof,
+                                       const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_ok);
+
+/* ring commitment MSM (ark-ec VariableBaseMSM::msm behind ring-proof's KZG commit):
+ * n_columns scalar columns (column-major, n*32 bytes each) over one base vector of n affine G1 points.
+ * out: n_columns * 96 bytes affine. */
+vrfs_status vrfs_msm_g1_bls12_381(vrfs_ctx*, size_t n, const uint8_t* bases /*n*96*/, const uint8_t* scalars /*n_columns*n*32*/,
+                                  int n_columns, uint8_t* out /*n_columns*96*/);
+/* multi-GPU MSM helper: this rank's partial sums over its point range, projective (X,Y,Z 48-byte LE
+ * canonical each = 144 bytes per column), to be gathered (NCCL all-gather of 144*n_columns bytes) and
+ * folded with vrfs_g1_sum_partials on any rank. */
+vrfs_status vrfs_msm_g1_partial(vrfs_ctx*, size_t n, const uint8_t* bases, const uint8_t* scalars, int n_columns, uint8_t* out_partial /*n_columns*144*/);
+vrfs_status vrfs_g1_sum_partials(vrfs_ctx*, int n_parts, int n_columns, const uint8_t* partials /*n_parts*n_columns*144*/, uint8_t* out /*n_columns*96*/);
+
+/* measurement helper: runs the IMAD.WIDE.U32 issue-rate microbenchmark used as the integer-pipe roofline
+ * denominator; returns multiply-accumulates (32x32+64) per second over the whole GPU. */
+vrfs_status vrfs_measure_mac32_peak(vrfs_ctx*, int variant, double* out_mac_per_s, double* out_sm_mhz_est);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

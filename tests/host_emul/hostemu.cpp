@@ -1,0 +1,108 @@
+// TEST INFRASTRUCTURE ONLY: compiles the engine's device headers for the HOST (every PTX block has a
+// plain-C twin) so that the field / curve / hashing code can be checked on a box without a GPU.
+// Nothing in the product links this file.
+#include <stdint.h>
+#include <string.h>
+#include "../../ark_ec_vrfs_b200/csrc/gen/field_consts.cuh"
+using namespace vrfs;
+
+template <class P> static void field_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+  Fp<P> x, y, r;
+  memcpy(x.v, a, 4 * P::N); memcpy(y.v, b, 4 * P::N);
+  switch (op) {
+    case 0: r = x * y; break;                       // Montgomery product of raw limb arrays
+    case 1: r = x + y; break;
+    case 2: r = x - y; break;
+    case 3: r = to_mont<P>(a); break;               // any value -> Montgomery, reduced
+    case 4: from_mont<P>(r.v, x); break;
+    case 5: r = inv(x); break;
+    case 6: r = to_mont_wide<P>(a, b); break;
+    case 7: r = Fp<P>::zero(); r.v[0] = is_square(x); break;
+    case 8: r = Fp<P>::zero(); r.v[0] = is_high(x) | (is_odd(x) << 1); break;
+    default: r = Fp<P>::zero();
+  }
+  memcpy(out, r.v, 4 * P::N);
+}
+extern "C" void hostemu_field_op(int field, int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+  switch (field) {
+    case 0: field_op<BlsFr>(op, a, b, out); break;
+    case 1: field_op<BandFr>(op, a, b, out); break;
+    case 2: field_op<F25519>(op, a, b, out); break;
+    case 3: field_op<EdFr>(op, a, b, out); break;
+    case 4: field_op<P256Fp>(op, a, b, out); break;
+    case 5: field_op<P256Fr>(op, a, b, out); break;
+    case 6: field_op<BlsFq>(op, a, b, out); break;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-item engine code on the host: IETF verify (Bandersnatch / Ed25519)
+#include <vector>
+#include "../../ark_ec_vrfs_b200/csrc/suite.cuh"
+
+template <class C> static const TEAffCached<C>* fixed_table(bool blinding) {
+  static std::vector<TEAffCached<C>> tabs[2];
+  auto& t = tabs[blinding];
+  if (t.empty()) {
+    t.resize(32 * 129);
+    for (int w = 0; w < 32; w++) for (int d = 0; d <= 128; d++)
+      te_fixed_table_entry<C>(t[w * 129 + d], blinding ? C::bx() : C::gx(), blinding ? C::by() : C::gy(), w, d);
+  }
+  return t.data();
+}
+
+template <class S> static void ietf_verify(size_t n, const uint8_t* pk, const uint8_t* in, const uint8_t* out, const uint8_t* c,
+                                           const uint8_t* s, const uint8_t* ad, const uint64_t* ad_off, uint8_t* ok) {
+  typedef typename S::C C;
+  std::vector<TECached<C>> slab(4 * 9);
+  std::vector<uint32_t> u(24), v(24);
+  for (size_t i = 0; i < n; i++) {
+    LincombArgs A = {};
+    A.n = (uint32_t)n;
+    A.var[0] = {pk, 64, c, 32, 1};
+    A.fix[0] = {s, 32, 0, fixed_table<C>(false)};
+    TEPoint<C> acc;
+    bool valid = te_lincomb_item<C, 1, 1>(A, (uint32_t)i, slab.data(), acc);
+    memcpy(&u[0], acc.X.v, 32); memcpy(&u[8], acc.Y.v, 32); memcpy(&u[16], acc.Z.v, 32);
+    A.var[0] = {in, 64, s, 32, 0};
+    A.var[1] = {out, 64, c, 32, 1};
+    valid &= te_lincomb_item<C, 2, 0>(A, (uint32_t)i, slab.data(), acc);
+    memcpy(&v[0], acc.X.v, 32); memcpy(&v[8], acc.Y.v, 32); memcpy(&v[16], acc.Z.v, 32);
+    const uint8_t* a = ad ? ad + ad_off[i] : (const uint8_t*)"";
+    uint32_t alen = ad ? (uint32_t)(ad_off[i + 1] - ad_off[i]) : 0;
+    ok[i] = valid && ietf_verify_finish_item<S>(pk + 64 * i, in + 64 * i, out + 64 * i, c + 32 * i, u.data(), v.data(), a, alen);
+  }
+}
+extern "C" void hostemu_ietf_verify(int suite, size_t n, const uint8_t* pk, const uint8_t* in, const uint8_t* out, const uint8_t* c,
+                                    const uint8_t* s, const uint8_t* ad, const uint64_t* ad_off, uint8_t* ok) {
+  if (suite == 0) ietf_verify<BandSuite>(n, pk, in, out, c, s, ad, ad_off, ok);
+  else if (suite == 1) ietf_verify<EdSuite>(n, pk, in, out, c, s, ad, ad_off, ok);
+}
+
+// debug / unit-test entry: R = k1*P1 [+ k2*P2] [+ f*G], affine canonical out (x||y LE)
+template <class C> static int lincomb_dbg(int nv, int nf, const uint8_t* p1, const uint8_t* k1, const uint8_t* p2, const uint8_t* k2,
+                                          const uint8_t* f, int neg_mask, uint8_t* out) {
+  std::vector<TECached<C>> slab(4 * 9);
+  LincombArgs A = {};
+  A.n = 1;
+  A.var[0] = {p1, 64, k1, 32, (uint32_t)(neg_mask & 1)};
+  A.var[1] = {p2, 64, k2, 32, (uint32_t)((neg_mask >> 1) & 1)};
+  A.fix[0] = {f, 32, (uint32_t)((neg_mask >> 2) & 1), fixed_table<C>(false)};
+  TEPoint<C> acc; bool ok;
+  if (nv == 1 && nf == 0) ok = te_lincomb_item<C, 1, 0>(A, 0, slab.data(), acc);
+  else if (nv == 2 && nf == 0) ok = te_lincomb_item<C, 2, 0>(A, 0, slab.data(), acc);
+  else if (nv == 0 && nf == 1) ok = te_lincomb_item<C, 0, 1>(A, 0, slab.data(), acc);
+  else ok = te_lincomb_item<C, 1, 1>(A, 0, slab.data(), acc);
+  typename C::F zi = inv(acc.Z), x = acc.X * zi, y = acc.Y * zi;
+  uint32_t rx[8], ry[8]; from_mont<typename C::Fq>(rx, x); from_mont<typename C::Fq>(ry, y);
+  store_le<8>(out, rx); store_le<8>(out + 32, ry);
+  return ok;
+}
+extern "C" int hostemu_lincomb(int suite, int nv, int nf, const uint8_t* p1, const uint8_t* k1, const uint8_t* p2, const uint8_t* k2,
+                               const uint8_t* f, int neg_mask, uint8_t* out) {
+  return suite == 0 ? lincomb_dbg<BandCurve>(nv, nf, p1, k1, p2, k2, f, neg_mask, out) : lincomb_dbg<EdCurve>(nv, nf, p1, k1, p2, k2, f, neg_mask, out);
+}
+extern "C" void hostemu_glv(const uint32_t* k, uint32_t* out /*4+4+2*/) {
+  GlvHalf a, b; band_glv_split(&a, &b, k);
+  memcpy(out, a.mag, 16); memcpy(out + 4, b.mag, 16); out[8] = a.neg; out[9] = b.neg;
+}

@@ -1,0 +1,164 @@
+#!/usr/bin/env python3
+"""Emit ark_ec_vrfs_b200/csrc/gen/mont_chains.cuh: the carry-chain building blocks of the N-limb
+(32-bit limbs) Montgomery multiplier, N = 8 and 12, each as ONE inline-PTX block (the carry flag never
+leaves a block) plus a plain-C twin used only when the header is compiled for the host (the
+`tests/host_emul` harness that lets the field / curve code be checked without a GPU).
+
+The multiplier keeps the running sum in two interleaved accumulators so that every
+`mad.lo.cc / madc.hi.cc` pair covers two adjacent, not-yet-touched columns; ptxas fuses each pair
+into one IMAD.WIDE.U32(.X) ("K1").
+"""
+import os
+
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "ark_ec_vrfs_b200", "csrc", "gen", "mont_chains.cuh")
+
+
+def asm_block(lines, outs, ins):
+    """outs: list of C lvalues bound "+r"; ins: list of C rvalues bound "r"."""
+    body = " ".join(l + ";" for l in lines)
+    o = ", ".join(f'"+r"({x})' for x in outs)
+    i = ", ".join(f'"r"({x})' for x in ins)
+    return f'    asm("{body}" : {o} : {i});'
+
+
+def gen(N):
+    L = []
+    H = N // 2
+    L.append(f"template <> struct MontChains<{N}> {{")
+
+    # ---- mul_row: acc[0..N-1] = sum_{k=0..H-1} x[2k] * b  (two limbs each, no carries needed)
+    L.append("  // acc[2k+1]:acc[2k] = x[2k] * b")
+    L.append("  static HD_INLINE void mul_row(uint32_t* acc, const uint32_t* x, uint32_t b) {")
+    L.append("#ifdef __CUDA_ARCH__")
+    lines = []
+    for k in range(H):
+        lines.append(f"mul.lo.u32 %{2*k}, %{N+k}, %{N+H}")
+        lines.append(f"mul.hi.u32 %{2*k+1}, %{N+k}, %{N+H}")
+    o = ", ".join(f'"=r"(acc[{j}])' for j in range(N))
+    i = ", ".join([f'"r"(x[{2*k}])' for k in range(H)] + ['"r"(b)'])
+    L.append(f'    asm("{" ".join(l + ";" for l in lines)}" : {o} : {i});')
+    L.append("#else")
+    L.append(f"    for (int k = 0; k < {H}; k++) {{ uint64_t t = (uint64_t)x[2 * k] * b; acc[2 * k] = (uint32_t)t; acc[2 * k + 1] = (uint32_t)(t >> 32); }}")
+    L.append("#endif")
+    L.append("  }")
+
+    # ---- mad_row: acc += x_even * b ; top += carry-out
+    L.append("  // acc[0..N-1] += sum_k x[2k]*b*2^(64k) as one carry chain; the carry out of acc[N-1] is added to top")
+    L.append("  static HD_INLINE void mad_row(uint32_t* acc, uint32_t& top, const uint32_t* x, uint32_t b) {")
+    L.append("#ifdef __CUDA_ARCH__")
+    lines = []
+    for k in range(H):
+        lo = "mad.lo.cc.u32" if k == 0 else "madc.lo.cc.u32"
+        lines.append(f"{lo} %{2*k}, %{N+1+k}, %{N+1+H}, %{2*k}")
+        lines.append(f"madc.hi.cc.u32 %{2*k+1}, %{N+1+k}, %{N+1+H}, %{2*k+1}")
+    lines.append(f"addc.u32 %{N}, %{N}, 0")
+    L.append(asm_block(lines, [f"acc[{j}]" for j in range(N)] + ["top"], [f"x[{2*k}]" for k in range(H)] + ["b"]))
+    L.append("#else")
+    L.append("    uint32_t c = 0;")
+    L.append(f"    for (int k = 0; k < {H}; k++) {{")
+    L.append("      unsigned __int128 t = (unsigned __int128)x[2 * k] * b + acc[2 * k] + ((uint64_t)acc[2 * k + 1] << 32) + c;")
+    L.append("      acc[2 * k] = (uint32_t)t; acc[2 * k + 1] = (uint32_t)(t >> 32); c = (uint32_t)(t >> 64);")
+    L.append("    }")
+    L.append("    top += c;")
+    L.append("#endif")
+    L.append("  }")
+
+    # ---- mad_row_last: same but the carry out is known to be zero (bounds) and is dropped
+    L.append("  // same, for the accumulator that owns the top column: its carry out is zero by the size bound")
+    L.append("  static HD_INLINE void mad_row_top(uint32_t* acc, const uint32_t* x, uint32_t b) {")
+    L.append("#ifdef __CUDA_ARCH__")
+    lines = []
+    for k in range(H):
+        lo = "mad.lo.cc.u32" if k == 0 else "madc.lo.cc.u32"
+        hi = "madc.hi.cc.u32" if k < H - 1 else "madc.hi.u32"
+        lines.append(f"{lo} %{2*k}, %{N+k}, %{N+H}, %{2*k}")
+        lines.append(f"{hi} %{2*k+1}, %{N+k}, %{N+H}, %{2*k+1}")
+    L.append(asm_block(lines, [f"acc[{j}]" for j in range(N)], [f"x[{2*k}]" for k in range(H)] + ["b"]))
+    L.append("#else")
+    L.append("    uint32_t c = 0;")
+    L.append(f"    for (int k = 0; k < {H}; k++) {{")
+    L.append("      unsigned __int128 t = (unsigned __int128)x[2 * k] * b + acc[2 * k] + ((uint64_t)acc[2 * k + 1] << 32) + c;")
+    L.append("      acc[2 * k] = (uint32_t)t; acc[2 * k + 1] = (uint32_t)(t >> 32); c = (uint32_t)(t >> 64);")
+    L.append("    }")
+    L.append("#endif")
+    L.append("  }")
+
+    # ---- shift_mad_row: v0 += u[1]; u[j] = row(x,b)[j] + u[j+2] + carry chain (u[N], u[N+1] = 0)
+    L.append("  // v0 += u[1] (carry into the chain); then u[j] = (x[0],x[2],..)*b row + u[j+2], j = 0..N-1, u[N] = u[N+1] = 0")
+    L.append("  static HD_INLINE void shift_mad_row(uint32_t* u, uint32_t& v0, const uint32_t* x, uint32_t b) {")
+    L.append("#ifdef __CUDA_ARCH__")
+    lines = [f"add.cc.u32 %{N}, %{N}, %1"]
+    for k in range(H):
+        a_lo = f"%{2*k+2}" if 2 * k + 2 < N else "0"
+        a_hi = f"%{2*k+3}" if 2 * k + 3 < N else "0"
+        hi = "madc.hi.cc.u32" if k < H - 1 else "madc.hi.u32"
+        lines.append(f"madc.lo.cc.u32 %{2*k}, %{N+1+k}, %{N+1+H}, {a_lo}")
+        lines.append(f"{hi} %{2*k+1}, %{N+1+k}, %{N+1+H}, {a_hi}")
+    L.append(asm_block(lines, [f"u[{j}]" for j in range(N)] + ["v0"], [f"x[{2*k}]" for k in range(H)] + ["b"]))
+    L.append("#else")
+    L.append("    uint64_t s = (uint64_t)v0 + u[1]; v0 = (uint32_t)s; uint32_t c = (uint32_t)(s >> 32);")
+    L.append(f"    for (int k = 0; k < {H}; k++) {{")
+    L.append(f"      uint32_t lo = 2 * k + 2 < {N} ? u[2 * k + 2] : 0, hi = 2 * k + 3 < {N} ? u[2 * k + 3] : 0;")
+    L.append("      unsigned __int128 t = (unsigned __int128)x[2 * k] * b + lo + ((uint64_t)hi << 32) + c;")
+    L.append("      u[2 * k] = (uint32_t)t; u[2 * k + 1] = (uint32_t)(t >> 32); c = (uint32_t)(t >> 64);")
+    L.append("    }")
+    L.append("#endif")
+    L.append("  }")
+
+    # ---- merge: u[0..N-2] += v[1..N-1] with carry, u[N-1] += carry
+    L.append("  // u[0..N-2] += v[1..N-1], carry into u[N-1]")
+    L.append("  static HD_INLINE void merge(uint32_t* u, const uint32_t* v) {")
+    L.append("#ifdef __CUDA_ARCH__")
+    lines = []
+    for j in range(N - 1):
+        op = "add.cc.u32" if j == 0 else "addc.cc.u32"
+        lines.append(f"{op} %{j}, %{j}, %{N+j}")
+    lines.append(f"addc.u32 %{N-1}, %{N-1}, 0")
+    L.append(asm_block(lines, [f"u[{j}]" for j in range(N)], [f"v[{j+1}]" for j in range(N - 1)]))
+    L.append("#else")
+    L.append("    uint32_t c = 0;")
+    L.append(f"    for (int j = 0; j < {N-1}; j++) {{ uint64_t t = (uint64_t)u[j] + v[j + 1] + c; u[j] = (uint32_t)t; c = (uint32_t)(t >> 32); }}")
+    L.append(f"    u[{N-1}] += c;")
+    L.append("#endif")
+    L.append("  }")
+
+    # ---- add / sub with carry/borrow out
+    for name, op0, opc, opl, expr in (("add", "add.cc.u32", "addc.cc.u32", "addc.u32", "+"), ("sub", "sub.cc.u32", "subc.cc.u32", "subc.u32", "-")):
+        L.append(f"  // r = a {expr} b over N limbs; returns the carry (add) / borrow (sub) as 0 or 1")
+        L.append(f"  static HD_INLINE uint32_t {name}(uint32_t* r, const uint32_t* a, const uint32_t* b) {{")
+        L.append("#ifdef __CUDA_ARCH__")
+        L.append("    uint32_t c;")
+        lines = []
+        for j in range(N):
+            lines.append(f"{op0 if j == 0 else opc} %{j}, %{N+1+j}, %{2*N+1+j}")
+        if name == "add":
+            lines.append(f"addc.u32 %{N}, 0, 0")
+        else:
+            lines.append(f"subc.u32 %{N}, 0, 0")
+        o = ", ".join([f'"=r"(r[{j}])' for j in range(N)] + ['"=r"(c)'])
+        i = ", ".join([f'"r"(a[{j}])' for j in range(N)] + [f'"r"(b[{j}])' for j in range(N)])
+        L.append(f'    asm("{" ".join(l + ";" for l in lines)}" : {o} : {i});')
+        L.append("    return c & 1u;" if name == "sub" else "    return c;")
+        L.append("#else")
+        if name == "add":
+            L.append(f"    uint32_t c = 0; for (int j = 0; j < {N}; j++) {{ uint64_t t = (uint64_t)a[j] + b[j] + c; r[j] = (uint32_t)t; c = (uint32_t)(t >> 32); }} return c;")
+        else:
+            L.append(f"    uint32_t c = 0; for (int j = 0; j < {N}; j++) {{ uint64_t t = (uint64_t)a[j] - b[j] - c; r[j] = (uint32_t)t; c = (uint32_t)(t >> 32) & 1u; }} return c;")
+        L.append("#endif")
+        L.append("  }")
+    L.append("};")
+    return L
+
+
+def main():
+    L = ["// generated by tools/gen_mont_chains.py - do not edit", "#pragma once", "#include <stdint.h>",
+         "template <int N> struct MontChains;"]
+    for N in (8, 12):
+        L += gen(N)
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    open(OUT, "w").write("\n".join(L) + "\n")
+    print("wrote", OUT)
+
+
+if __name__ == "__main__":
+    main()
