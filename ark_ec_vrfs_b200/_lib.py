@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libvrfs_b200.so")
+LIB_PATH = os.environ.get("VRFS_B200_LIB") or os.path.join(HERE, "libvrfs_b200.so")
 
 OK, INVALID_DATA, CUDA_ERROR, BAD_ARG, UNSUPPORTED = range(5)
 STATUS_NAMES = {0: "VRFS_OK", 1: "VRFS_INVALID_DATA", 2: "VRFS_CUDA_ERROR", 3: "VRFS_BAD_ARG", 4: "VRFS_UNSUPPORTED"}
@@ -12,7 +12,7 @@ STATUS_NAMES = {0: "VRFS_OK", 1: "VRFS_INVALID_DATA", 2: "VRFS_CUDA_ERROR", 3: "
 # every symbol include/vrfs_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = [
     "vrfs_abi_version", "vrfs_ctx_create", "vrfs_ctx_destroy", "vrfs_ctx_sync", "vrfs_last_error", "vrfs_ctx_stream",
-    "vrfs_ctx_launch_count", "vrfs_suite_challenge_len", "vrfs_suite_hash_len", "vrfs_suite_point_enc_len",
+    "vrfs_ctx_launch_count", "vrfs_ctx_enable_kernel_timing", "vrfs_ctx_kernel_timings", "vrfs_suite_challenge_len", "vrfs_suite_hash_len", "vrfs_suite_point_enc_len",
     "vrfs_secret_from_seed_batch", "vrfs_data_to_point_batch", "vrfs_output_batch", "vrfs_point_to_hash_batch",
     "vrfs_point_encode_batch", "vrfs_point_decode_batch", "vrfs_nonce_batch",
     "vrfs_ietf_prove_batch", "vrfs_ietf_verify_batch", "vrfs_ietf_verify_batch_dev",

@@ -31,10 +31,10 @@ def nvcc():
     return "nvcc"
 
 
-def build(force=False, verbose=False, extra=()):
-    if not force and not stale():
+def build(force=False, verbose=False, extra=(), out=None):
+    if out is None and not force and not stale():
         return LIB
-    cmd = [nvcc()] + NVCC_FLAGS + list(extra) + ["-o", LIB, SRC]
+    cmd = [nvcc()] + NVCC_FLAGS + list(extra) + ["-o", out or LIB, SRC]
     if verbose:
         print(" ".join(cmd), flush=True)
     subprocess.run(cmd, check=True)
@@ -42,4 +42,6 @@ def build(force=False, verbose=False, extra=()):
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose=True, extra=[a for a in sys.argv[1:] if a.startswith("-D") or a.startswith("-X")])
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
+    build(force="--force" in sys.argv, verbose=True, extra=[a for a in sys.argv[1:] if a.startswith("-D") or a.startswith("-X")],
+          out=outs[0] if outs else None)

@@ -123,4 +123,125 @@ HD_INLINE bool ietf_verify_finish_item(const uint8_t* pk, const uint8_t* input, 
   return diff == 0;
 }
 
+// K projective points (X,Y,Z Montgomery limbs, 24 words each) -> affine Montgomery, ONE shared inversion
+template <class C, int K> HD_INLINE void te_to_affine_shared(typename C::F* ax, typename C::F* ay, const uint32_t* const* p) {
+  typedef typename C::F F;
+  F X[K], Y[K], Z[K], pre[K];
+  for (int k = 0; k < K; k++) for (int i = 0; i < 8; i++) { X[k].v[i] = p[k][i]; Y[k].v[i] = p[k][8 + i]; Z[k].v[i] = p[k][16 + i]; }
+  pre[0] = Z[0];
+  for (int k = 1; k < K; k++) pre[k] = pre[k - 1] * Z[k];
+  F acc = inv(pre[K - 1]);
+  for (int k = K - 1; k >= 0; k--) {
+    F zi = k ? acc * pre[k - 1] : acc;
+    if (k) acc = acc * Z[k];
+    ax[k] = X[k] * zi; ay[k] = Y[k] * zi;
+  }
+}
+template <class C> HD_INLINE void store_affine_bytes(uint8_t* out, const typename C::F& x, const typename C::F& y) {
+  uint32_t rx[8], ry[8];
+  from_mont<typename C::Fq>(rx, x); from_mont<typename C::Fq>(ry, y);
+  store_le<8>(out, rx); store_le<8>(out + 32, ry);
+}
+template <class C> HD_INLINE void load_scalar_bytes_mod_r(uint32_t* k, const uint8_t* p) {   // alignment-free variant
+  uint32_t raw[8];
+  load_le<8>(raw, p);
+  from_mont<typename C::Fr>(k, to_mont<typename C::Fr>(raw));
+}
+
+// ietf::Prover::prove, second half (A.9): Y = sk*G, kG, kI already computed (projective)
+template <class S>
+HD_INLINE void ietf_prove_finish_item(uint8_t* out_c, uint8_t* out_s, const uint8_t* sk_bytes, const uint8_t* k_bytes, const uint8_t* input,
+                                      const uint8_t* output, const uint32_t* y_xyz, const uint32_t* kg_xyz, const uint32_t* ki_xyz,
+                                      const uint8_t* ad, uint32_t adlen) {
+  typedef typename S::C C;
+  typename C::F ax[3], ay[3];
+  const uint32_t* pp[3] = {y_xyz, kg_xyz, ki_xyz};
+  te_to_affine_shared<C, 3>(ax, ay, pp);
+  uint8_t enc[5][32];
+  ark_encode_point_mont<C>(enc[0], ax[0], ay[0]);
+  ark_encode_point_bytes<C>(enc[1], input);
+  ark_encode_point_bytes<C>(enc[2], output);
+  ark_encode_point_mont<C>(enc[3], ax[1], ay[1]);
+  ark_encode_point_mont<C>(enc[4], ax[2], ay[2]);
+  uint32_t c[8], sk[8], k[8], sres[8];
+  suite_challenge<S>(c, enc, ad, adlen);
+  load_scalar_bytes_mod_r<C>(sk, sk_bytes);
+  load_le<8>(k, k_bytes);
+  scalar_muladd<C>(sres, k, c, sk);
+  store_le<8>(out_c, c); store_le<8>(out_s, sres);
+}
+
+// Suite::nonce for the rfc8032-style suites, from ABI bytes
+template <class S> HD_INLINE void te_nonce_item(uint8_t* out_k, const uint8_t* sk_bytes, const uint8_t* input) {
+  typedef typename S::C C;
+  uint32_t sk[8], k[8];
+  uint8_t enc[32];
+  load_scalar_bytes_mod_r<C>(sk, sk_bytes);
+  ark_encode_point_bytes<C>(enc, input);
+  suite_nonce_8032<S>(k, sk, enc);
+  store_le<8>(out_k, k);
+}
+
+// pedersen::Prover::prove, first part (A.10): blinding b, nonces k = nonce(sk, I), kb = nonce(b, I)
+template <class S> HD_INLINE void pedersen_prove_prep_item(uint8_t* out_b, uint8_t* out_k, uint8_t* out_kb, const uint8_t* sk_bytes,
+                                                           const uint8_t* input, const uint8_t* ad, uint32_t adlen) {
+  typedef typename S::C C;
+  uint32_t sk[8], b[8], k[8], kb[8];
+  uint8_t enc[32];
+  load_scalar_bytes_mod_r<C>(sk, sk_bytes);
+  ark_encode_point_bytes<C>(enc, input);
+  suite_blinding<S>(b, sk, enc, ad, adlen);
+  suite_nonce_8032<S>(k, sk, enc);
+  suite_nonce_8032<S>(kb, b, enc);
+  store_le<8>(out_b, b); store_le<8>(out_k, k); store_le<8>(out_kb, kb);
+}
+// second part: Yb, R, Ok (projective) -> proof bytes (3 x 64 affine || s || sb)
+template <class S> HD_INLINE void pedersen_prove_finish_item(uint8_t* proof, const uint8_t* sk_bytes, const uint8_t* b_bytes, const uint8_t* k_bytes,
+                                                             const uint8_t* kb_bytes, const uint8_t* input, const uint8_t* output,
+                                                             const uint32_t* yb_xyz, const uint32_t* r_xyz, const uint32_t* ok_xyz,
+                                                             const uint8_t* ad, uint32_t adlen) {
+  typedef typename S::C C;
+  typename C::F ax[3], ay[3];
+  const uint32_t* pp[3] = {yb_xyz, r_xyz, ok_xyz};
+  te_to_affine_shared<C, 3>(ax, ay, pp);
+  uint8_t enc[5][32];
+  ark_encode_point_mont<C>(enc[0], ax[0], ay[0]);
+  ark_encode_point_bytes<C>(enc[1], input);
+  ark_encode_point_bytes<C>(enc[2], output);
+  ark_encode_point_mont<C>(enc[3], ax[1], ay[1]);
+  ark_encode_point_mont<C>(enc[4], ax[2], ay[2]);
+  for (int j = 0; j < 3; j++) store_affine_bytes<C>(proof + 64 * j, ax[j], ay[j]);
+  uint32_t c[8], sk[8], b[8], k[8], kb[8], r[8];
+  suite_challenge<S>(c, enc, ad, adlen);
+  load_scalar_bytes_mod_r<C>(sk, sk_bytes);
+  load_le<8>(b, b_bytes); load_le<8>(k, k_bytes); load_le<8>(kb, kb_bytes);
+  scalar_muladd<C>(r, k, c, sk); store_le<8>(proof + 192, r);
+  scalar_muladd<C>(r, kb, c, b); store_le<8>(proof + 224, r);
+}
+// pedersen::Verifier::verify, first part: c = challenge(Yb, I, O, R, Ok, ad) from the proof bytes
+template <class S> HD_INLINE void pedersen_verify_prep_item(uint8_t* out_c, const uint8_t* input, const uint8_t* output, const uint8_t* proof,
+                                                            const uint8_t* ad, uint32_t adlen) {
+  typedef typename S::C C;
+  uint8_t enc[5][32];
+  ark_encode_point_bytes<C>(enc[0], proof);
+  ark_encode_point_bytes<C>(enc[1], input);
+  ark_encode_point_bytes<C>(enc[2], output);
+  ark_encode_point_bytes<C>(enc[3], proof + 64);
+  ark_encode_point_bytes<C>(enc[4], proof + 128);
+  uint32_t c[8];
+  suite_challenge<S>(c, enc, ad, adlen);
+  store_le<8>(out_c, c);
+}
+// is the projective point (X,Y,Z) equal to the affine point given as ABI bytes?  (also validates the affine point)
+template <class C> HD_INLINE bool te_proj_equals_affine_bytes(const uint32_t* xyz, const uint8_t* aff) {
+  typedef typename C::F F;
+  uint32_t rx[8], ry[8];
+  load_le<8>(rx, aff); load_le<8>(ry, aff + 32);
+  bool ok = is_canonical<typename C::Fq>(rx) & is_canonical<typename C::Fq>(ry);
+  F x = to_mont<typename C::Fq>(rx), y = to_mont<typename C::Fq>(ry), X, Y, Z;
+  ok &= te_on_curve<C>(x, y);
+  for (int i = 0; i < 8; i++) { X.v[i] = xyz[i]; Y.v[i] = xyz[8 + i]; Z.v[i] = xyz[16 + i]; }
+  return ok & !Z.is_zero() & (x * Z == X) & (y * Z == Y);
+}
+
 }  // namespace vrfs

@@ -7,7 +7,7 @@
 #include <new>
 
 #include "../../include/vrfs_b200.h"
-#include "suite.cuh"
+#include "h2c.cuh"
 
 using namespace vrfs;
 
@@ -115,6 +115,22 @@ __global__ void __launch_bounds__(256) k_mac_bench(uint32_t* out, int iters, uns
     uint32_t s = 0;
     for (int i = 0; i < 8; i++) s ^= a.v[i] ^ b.v[i] ^ c.v[i] ^ d.v[i];
     out[t] = s;
+  } else if (VARIANT == 5 || VARIANT == 6) {   // 4 independent 8-limb carry chains (the multiplier's row shape); 6: immediate multiplicand
+    uint32_t acc[4][8], top[4], x[8];
+    for (int c = 0; c < 4; c++) { top[c] = 0; for (int i = 0; i < 8; i++) acc[c][i] = t * (c + 3) + i; }
+    for (int i = 0; i < 8; i++) x[i] = VARIANT == 5 ? (t ^ (0x9e3779b9u * (i + 1))) : BlsFr::mod(i);
+    uint32_t y = t * 2654435761u + 12345u;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) MontChains<8>::mad_row(acc[c], top[c], x, y + c);
+      }
+    }
+    uint32_t s = 0;
+    for (int c = 0; c < 4; c++) { s ^= top[c]; for (int i = 0; i < 8; i++) s ^= acc[c][i]; }
+    out[t] = s;
   } else {                     // VARIANT 4: mad.hi.u32
     uint32_t a0 = t, a1 = t + 1, a2 = t + 2, a3 = t + 3, a4 = t + 4, a5 = t + 5, a6 = t + 6, a7 = t + 7;
     uint32_t x = t * 2654435761u + 12345u, y = t ^ 0x9e3779b9u;
@@ -142,8 +158,13 @@ struct DevBuf {
 };
 enum { BUF_IN0, BUF_IN1, BUF_IN2, BUF_IN3, BUF_IN4, BUF_AD, BUF_OFF, BUF_OUT0, BUF_OUT1, BUF_W0, BUF_W1, BUF_W2, BUF_W3, BUF_VALID, BUF_SLAB, BUF_COUNT };
 
+#define MAX_TIMED 64
 struct vrfs_ctx {
   int device = 0, sms = 0;
+  bool timing = false;
+  int n_timed = 0;
+  cudaEvent_t tev[MAX_TIMED + 1] = {nullptr};
+  const char* tname[MAX_TIMED] = {nullptr};
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   char err[512] = {0};
@@ -166,7 +187,44 @@ static vrfs_status fail(vrfs_ctx* c, vrfs_status st, const char* fmt, ...) {
     vrfs_status s_ = (call);              \
     if (s_ != VRFS_OK) return s_;         \
   } while (0)
-#define LAUNCHED(ctx) do { (ctx)->launches++; CU(cudaGetLastError()); } while (0)
+// bookkeeping after every kernel launch: count it, surface launch errors, and (when kernel timing is on)
+// drop an event so that bench.py can read each kernel's device time from the stream it ran on
+#define LAUNCHED(ctx) do { (ctx)->launches++; CU(cudaGetLastError()); ST(note_kernel((ctx), __func__)); } while (0)
+#define LAUNCHED_AS(ctx, name) do { (ctx)->launches++; CU(cudaGetLastError()); ST(note_kernel((ctx), (name))); } while (0)
+static vrfs_status note_kernel(vrfs_ctx* ctx, const char* name);
+static vrfs_status timing_begin(vrfs_ctx* ctx);
+
+static vrfs_status timing_begin(vrfs_ctx* ctx) {
+  ctx->n_timed = 0;
+  if (!ctx->timing) return VRFS_OK;
+  if (!ctx->tev[0]) for (int i = 0; i <= MAX_TIMED; i++) CU(cudaEventCreate(&ctx->tev[i]));
+  CU(cudaEventRecord(ctx->tev[0], ctx->stream));
+  return VRFS_OK;
+}
+static vrfs_status note_kernel(vrfs_ctx* ctx, const char* name) {
+  if (!ctx->timing || !ctx->tev[0] || ctx->n_timed >= MAX_TIMED) return VRFS_OK;
+  ctx->tname[ctx->n_timed] = name;
+  ctx->n_timed++;
+  CU(cudaEventRecord(ctx->tev[ctx->n_timed], ctx->stream));
+  return VRFS_OK;
+}
+extern "C" vrfs_status vrfs_ctx_enable_kernel_timing(vrfs_ctx* ctx, int on) {
+  if (!ctx) return VRFS_BAD_ARG;
+  ctx->timing = on != 0;
+  ctx->n_timed = 0;
+  return VRFS_OK;
+}
+// device time of every kernel of the most recent *_batch / *_batch_dev call (after a sync); returns the count
+extern "C" int vrfs_ctx_kernel_timings(vrfs_ctx* ctx, const char** names, float* ms, int cap) {
+  if (!ctx || !ctx->timing) return 0;
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return 0;
+  int n = ctx->n_timed < cap ? ctx->n_timed : cap;
+  for (int i = 0; i < n; i++) {
+    names[i] = ctx->tname[i];
+    if (cudaEventElapsedTime(&ms[i], ctx->tev[i], ctx->tev[i + 1]) != cudaSuccess) ms[i] = -1.f;
+  }
+  return n;
+}
 
 static vrfs_status ensure(vrfs_ctx* ctx, int which, size_t bytes, void** out) {
   DevBuf& b = ctx->buf[which];
@@ -254,7 +312,7 @@ static vrfs_status launch_lincomb(vrfs_ctx* ctx, LincombArgs A) {
   ST(ensure(ctx, BUF_SLAB, (size_t)blocks * LINCOMB_THREADS * te_slab_bytes<C>(NV), &slab));
   A.slab = (uint8_t*)slab;
   k_te_lincomb<C, NV, NF><<<blocks, LINCOMB_THREADS, 0, ctx->stream>>>(A);
-  LAUNCHED(ctx);
+  LAUNCHED_AS(ctx, NV == 2 ? "te_lincomb<2,0>" : NV == 1 && NF == 1 ? "te_lincomb<1,1>" : NV == 1 ? "te_lincomb<1,0>" : NF == 2 ? "te_lincomb<0,2>" : NV == 1 && NF == 2 ? "te_lincomb<1,2>" : "te_lincomb<0,1>");
   return VRFS_OK;
 }
 
@@ -266,6 +324,7 @@ static vrfs_status ietf_verify_dev(vrfs_ctx* ctx, size_t n, const uint8_t* pk, c
                                    const uint8_t* s, const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_ok) {
   typedef typename S::C C;
   void *u = nullptr, *v = nullptr, *valid = nullptr;
+  ST(timing_begin(ctx));
   ST(ensure(ctx, BUF_W0, n * 96, &u));
   ST(ensure(ctx, BUF_W1, n * 96, &v));
   ST(ensure(ctx, BUF_VALID, n, &valid));
@@ -285,7 +344,7 @@ static vrfs_status ietf_verify_dev(vrfs_ctx* ctx, size_t n, const uint8_t* pk, c
   ST((launch_lincomb<C, 2, 0>(ctx, A)));
   k_ietf_verify_finish<S><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((uint32_t)n, pk, input, output, c, (const uint32_t*)u,
                                                                                 (const uint32_t*)v, ad, ad_off, (const uint8_t*)valid, out_ok);
-  LAUNCHED(ctx);
+  LAUNCHED_AS(ctx, "ietf_verify_finish");
   return VRFS_OK;
 }
 
@@ -369,6 +428,8 @@ extern "C" vrfs_status vrfs_measure_mac32_peak(vrfs_ctx* ctx, int variant, doubl
       case 2: k_mac_bench<2><<<blocks, threads, 0, ctx->stream>>>((uint32_t*)out, iters, (unsigned long long*)cyc); break;
       case 3: k_mac_bench<3><<<blocks, threads, 0, ctx->stream>>>((uint32_t*)out, iters, (unsigned long long*)cyc); break;
       case 4: k_mac_bench<4><<<blocks, threads, 0, ctx->stream>>>((uint32_t*)out, iters, (unsigned long long*)cyc); break;
+      case 5: k_mac_bench<5><<<blocks, threads, 0, ctx->stream>>>((uint32_t*)out, iters, (unsigned long long*)cyc); break;
+      case 6: k_mac_bench<6><<<blocks, threads, 0, ctx->stream>>>((uint32_t*)out, iters, (unsigned long long*)cyc); break;
       default: return fail(ctx, VRFS_BAD_ARG, "unknown variant %d", variant);
     }
     LAUNCHED(ctx);
@@ -383,20 +444,417 @@ extern "C" vrfs_status vrfs_measure_mac32_peak(vrfs_ctx* ctx, int variant, doubl
   return VRFS_OK;
 }
 
+
+// =================================================================================================
+// per-item kernels of the remaining twisted-Edwards entry points (one thread per item)
+// =================================================================================================
+#define ITEM_THREADS 128
+#define ITEM_INDEX(n) uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= (n)) return
+#define VAR_SLICE(buf, off, i, ptr, len) const uint8_t* ptr = (buf) ? (buf) + (off)[i] : nullptr; uint32_t len = (buf) ? (uint32_t)((off)[(i) + 1] - (off)[i]) : 0u
+static inline unsigned item_blocks(size_t n) { return (unsigned)((n + ITEM_THREADS - 1) / ITEM_THREADS); }
+
+template <class S> __global__ void __launch_bounds__(ITEM_THREADS) k_te_nonce(uint32_t n, const uint8_t* sk, const uint8_t* input, uint8_t* out_k) {
+  ITEM_INDEX(n);
+  te_nonce_item<S>(out_k + (size_t)32 * i, sk + (size_t)32 * i, input + (size_t)64 * i);
+}
+template <class S> __global__ void __launch_bounds__(ITEM_THREADS) k_ietf_prove_finish(uint32_t n, const uint8_t* sk, const uint8_t* k, const uint8_t* input, const uint8_t* output,
+                                                                                        const uint32_t* y, const uint32_t* kg, const uint32_t* ki, const uint8_t* ad, const uint64_t* ad_off,
+                                                                                        const uint8_t* valid, uint8_t* out_c, uint8_t* out_s) {
+  ITEM_INDEX(n);
+  VAR_SLICE(ad, ad_off, i, a, alen);
+  uint8_t* oc = out_c + (size_t)32 * i; uint8_t* os = out_s + (size_t)32 * i;
+  if (!valid[i]) { for (int j = 0; j < 32; j++) { oc[j] = 0; os[j] = 0; } return; }
+  ietf_prove_finish_item<S>(oc, os, sk + (size_t)32 * i, k + (size_t)32 * i, input + (size_t)64 * i, output + (size_t)64 * i,
+                            y + (size_t)24 * i, kg + (size_t)24 * i, ki + (size_t)24 * i, a, alen);
+}
+// projective -> affine ABI bytes, one point per item (Secret::output, Public)
+template <class C> __global__ void __launch_bounds__(ITEM_THREADS) k_te_to_affine(uint32_t n, const uint32_t* xyz, const uint8_t* valid, uint8_t* out) {
+  ITEM_INDEX(n);
+  uint8_t* o = out + (size_t)64 * i;
+  if (valid && !valid[i]) { for (int j = 0; j < 64; j++) o[j] = 0; return; }
+  typename C::F ax[1], ay[1];
+  const uint32_t* pp[1] = {xyz + (size_t)24 * i};
+  te_to_affine_shared<C, 1>(ax, ay, pp);
+  store_affine_bytes<C>(o, ax[0], ay[0]);
+}
+// Secret::from_seed: sk = LE(H(seed)) mod r
+template <class S> __global__ void __launch_bounds__(ITEM_THREADS) k_te_secret_from_seed(uint32_t n, const uint8_t* seeds, const uint64_t* off, uint8_t* out_sk) {
+  ITEM_INDEX(n);
+  VAR_SLICE(seeds, off, i, p, len);
+  typename S::H h; h.init(); h.update(p, len);
+  uint8_t d[S::HLEN]; h.final(d);
+  uint32_t k[8];
+  hash_to_scalar<typename S::C>(k, d, S::HLEN, false);
+  store_le<8>(out_sk + (size_t)32 * i, k);
+}
+template <class S> __global__ void __launch_bounds__(ITEM_THREADS) k_te_point_to_hash(uint32_t n, const uint8_t* pts, uint8_t* out) {
+  ITEM_INDEX(n);
+  typedef typename S::C C;
+  typename C::F x, y;
+  uint8_t* o = out + (size_t)S::HLEN * i;
+  if (!te_load_affine<C>(x, y, pts + (size_t)64 * i)) { for (int j = 0; j < S::HLEN; j++) o[j] = 0; return; }
+  uint8_t enc[32];
+  ark_encode_point_bytes<C>(enc, pts + (size_t)64 * i);
+  suite_point_to_hash<S>(o, enc);
+}
+template <class C> __global__ void __launch_bounds__(ITEM_THREADS) k_te_point_encode(uint32_t n, const uint8_t* pts, uint8_t* out) {
+  ITEM_INDEX(n);
+  typename C::F x, y;
+  uint8_t* o = out + (size_t)32 * i;
+  if (!te_load_affine<C>(x, y, pts + (size_t)64 * i)) { for (int j = 0; j < 32; j++) o[j] = 0; return; }
+  ark_encode_point_bytes<C>(o, pts + (size_t)64 * i);
+}
+template <class C> __global__ void __launch_bounds__(ITEM_THREADS) k_te_point_decode(uint32_t n, const uint8_t* enc, uint8_t* out, uint8_t* out_ok) {
+  ITEM_INDEX(n);
+  typename C::F x, y;
+  uint8_t* o = out + (size_t)64 * i;
+  bool ok = ark_decode_point<C>(x, y, enc + (size_t)32 * i);
+  out_ok[i] = ok;
+  if (ok) store_affine_bytes<C>(o, x, y); else for (int j = 0; j < 64; j++) o[j] = 0;
+}
+// Suite::data_to_point (K6)
+template <class S> __global__ void __launch_bounds__(ITEM_THREADS) k_te_data_to_point(uint32_t n, const uint8_t* data, const uint64_t* off, uint8_t* out, uint8_t* out_ok) {
+  ITEM_INDEX(n);
+  typedef typename S::C C;
+  VAR_SLICE(data, off, i, p, len);
+  TEPoint<C> P;
+  bool ok;
+  if constexpr (C::HAS_GLV) { band_h2c_ell2(P, p, len); ok = true; } else { ok = te_h2c_tai<S>(P, p, len); }
+  uint8_t* o = out + (size_t)64 * i;
+  out_ok[i] = ok;
+  if (!ok) { for (int j = 0; j < 64; j++) o[j] = 0; return; }
+  typename C::F zi = inv(P.Z);
+  store_affine_bytes<C>(o, P.X * zi, P.Y * zi);
+}
+template <class S> __global__ void __launch_bounds__(ITEM_THREADS) k_pedersen_prove_prep(uint32_t n, const uint8_t* sk, const uint8_t* input, const uint8_t* ad, const uint64_t* ad_off,
+                                                                                          uint8_t* b, uint8_t* k, uint8_t* kb) {
+  ITEM_INDEX(n);
+  VAR_SLICE(ad, ad_off, i, a, alen);
+  pedersen_prove_prep_item<S>(b + (size_t)32 * i, k + (size_t)32 * i, kb + (size_t)32 * i, sk + (size_t)32 * i, input + (size_t)64 * i, a, alen);
+}
+template <class S> __global__ void __launch_bounds__(ITEM_THREADS) k_pedersen_prove_finish(uint32_t n, const uint8_t* sk, const uint8_t* b, const uint8_t* k, const uint8_t* kb,
+                                                                                            const uint8_t* input, const uint8_t* output, const uint32_t* yb, const uint32_t* r, const uint32_t* okp,
+                                                                                            const uint8_t* ad, const uint64_t* ad_off, const uint8_t* valid, uint8_t* proof, uint8_t* blinding) {
+  ITEM_INDEX(n);
+  VAR_SLICE(ad, ad_off, i, a, alen);
+  uint8_t* pr = proof + (size_t)256 * i; uint8_t* bl = blinding + (size_t)32 * i;
+  if (!valid[i]) { for (int j = 0; j < 256; j++) pr[j] = 0; for (int j = 0; j < 32; j++) bl[j] = 0; return; }
+  pedersen_prove_finish_item<S>(pr, sk + (size_t)32 * i, b + (size_t)32 * i, k + (size_t)32 * i, kb + (size_t)32 * i, input + (size_t)64 * i,
+                                output + (size_t)64 * i, yb + (size_t)24 * i, r + (size_t)24 * i, okp + (size_t)24 * i, a, alen);
+  for (int j = 0; j < 32; j++) bl[j] = b[(size_t)32 * i + j];
+}
+template <class S> __global__ void __launch_bounds__(ITEM_THREADS) k_pedersen_verify_prep(uint32_t n, const uint8_t* input, const uint8_t* output, const uint8_t* proof,
+                                                                                           const uint8_t* ad, const uint64_t* ad_off, uint8_t* c) {
+  ITEM_INDEX(n);
+  VAR_SLICE(ad, ad_off, i, a, alen);
+  pedersen_verify_prep_item<S>(c + (size_t)32 * i, input + (size_t)64 * i, output + (size_t)64 * i, proof + (size_t)256 * i, a, alen);
+}
+// Ok + c*O == s*I  and  R + c*Yb == s*G + sb*B, given T1 = s*I - c*O and T2 = s*G + sb*B - c*Yb (projective)
+template <class C> __global__ void __launch_bounds__(ITEM_THREADS) k_pedersen_verify_finish(uint32_t n, const uint8_t* proof, const uint32_t* t1, const uint32_t* t2,
+                                                                                             const uint8_t* valid, uint8_t* out_ok) {
+  ITEM_INDEX(n);
+  const uint8_t* pr = proof + (size_t)256 * i;
+  bool ok = te_proj_equals_affine_bytes<C>(t1 + (size_t)24 * i, pr + 128) & te_proj_equals_affine_bytes<C>(t2 + (size_t)24 * i, pr + 64);
+  out_ok[i] = (uint8_t)(ok && valid[i]);
+}
+
+// =================================================================================================
+// host-side plumbing shared by the entry points below
+// =================================================================================================
+struct Staged {   // device copies of a call's host inputs / device homes of its outputs
+  vrfs_ctx* ctx;
+  const uint8_t* in[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  const uint8_t* var = nullptr; const uint64_t* off = nullptr;
+  uint8_t* out[2] = {nullptr, nullptr};
+};
+static vrfs_status stage_out(vrfs_ctx* ctx, int which, size_t bytes, uint8_t** dev) {
+  void* d = nullptr;
+  ST(ensure(ctx, which, bytes, &d));
+  *dev = (uint8_t*)d;
+  return VRFS_OK;
+}
+static vrfs_status copy_out(vrfs_ctx* ctx, void* host, const void* dev, size_t bytes) {
+  if (bytes) CU(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return VRFS_OK;
+}
+static vrfs_status finish_call(vrfs_ctx* ctx) {
+  CU(cudaStreamSynchronize(ctx->stream));
+  return VRFS_OK;
+}
+static vrfs_status begin_call(vrfs_ctx* ctx, size_t n) {
+  if (n > 0x7fffffffu) return fail(ctx, VRFS_BAD_ARG, "batch too large (n < 2^31)");
+  CU(cudaSetDevice(ctx->device));
+  return timing_begin(ctx);
+}
+static vrfs_status fresh_valid(vrfs_ctx* ctx, size_t n, uint8_t** valid) {
+  void* v = nullptr;
+  ST(ensure(ctx, BUF_VALID, n, &v));
+  CU(cudaMemsetAsync(v, 1, n, ctx->stream));
+  *valid = (uint8_t*)v;
+  return VRFS_OK;
+}
+template <class S> static const void* fixtab(vrfs_ctx* ctx, int which) { return ctx->fixtab[S::C::HAS_GLV ? VRFS_BANDERSNATCH_ELL2 : VRFS_ED25519_TAI][which]; }
+#define SUITE_DISPATCH(suite, FN, ...)                                                         \
+  switch (suite) {                                                                             \
+    case VRFS_BANDERSNATCH_ELL2: return FN<BandSuite>(__VA_ARGS__);                            \
+    case VRFS_ED25519_TAI: return FN<EdSuite>(__VA_ARGS__);                                    \
+    default: return fail(ctx, VRFS_UNSUPPORTED, "suite %d is not implemented for %s", (int)suite, #FN); \
+  }
+
+// ---- ietf prove -----------------------------------------------------------------------------
+template <class S>
+static vrfs_status ietf_prove_dev(vrfs_ctx* ctx, size_t n, const uint8_t* sk, const uint8_t* input, const uint8_t* output, const uint8_t* ad,
+                                  const uint64_t* ad_off, uint8_t* out_c, uint8_t* out_s) {
+  typedef typename S::C C;
+  void *k = nullptr, *y = nullptr, *kg = nullptr, *ki = nullptr;
+  uint8_t* valid = nullptr;
+  ST(ensure(ctx, BUF_W0, n * 32, &k)); ST(ensure(ctx, BUF_W1, n * 96, &y)); ST(ensure(ctx, BUF_W2, n * 96, &kg)); ST(ensure(ctx, BUF_W3, n * 96, &ki));
+  ST(fresh_valid(ctx, n, &valid));
+  k_te_nonce<S><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, sk, input, (uint8_t*)k);
+  LAUNCHED_AS(ctx, "te_nonce");
+  LincombArgs A = {};
+  A.n = (uint32_t)n; A.valid = valid;
+  A.fix[0] = {sk, 32, 0, fixtab<S>(ctx, 0)}; A.out_xyz = (uint32_t*)y;
+  ST((launch_lincomb<C, 0, 1>(ctx, A)));
+  A.fix[0] = {(const uint8_t*)k, 32, 0, fixtab<S>(ctx, 0)}; A.out_xyz = (uint32_t*)kg;
+  ST((launch_lincomb<C, 0, 1>(ctx, A)));
+  A.var[0] = {input, 64, (const uint8_t*)k, 32, 0}; A.out_xyz = (uint32_t*)ki;
+  ST((launch_lincomb<C, 1, 0>(ctx, A)));
+  k_ietf_prove_finish<S><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, sk, (const uint8_t*)k, input, output, (const uint32_t*)y,
+                                                                           (const uint32_t*)kg, (const uint32_t*)ki, ad, ad_off, valid, out_c, out_s);
+  LAUNCHED_AS(ctx, "ietf_prove_finish");
+  return VRFS_OK;
+}
+extern "C" vrfs_status vrfs_ietf_prove_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* sk, const uint8_t* input, const uint8_t* output,
+                                             const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_c, uint8_t* out_s) {
+  if (!ctx) return VRFS_BAD_ARG;
+  if (n == 0) return VRFS_OK;
+  if (!sk || !input || !output || !out_c || !out_s) return fail(ctx, VRFS_BAD_ARG, "null buffer");
+  if (suite != VRFS_BANDERSNATCH_ELL2 && suite != VRFS_ED25519_TAI) return fail(ctx, VRFS_UNSUPPORTED, "suite %d is not implemented for ietf prove", (int)suite);
+  ST(begin_call(ctx, n));
+  const uint8_t *d_sk, *d_in, *d_out, *d_ad; const uint64_t* d_off; uint8_t *d_c, *d_s;
+  ST(stage_in(ctx, BUF_IN0, sk, n * 32, &d_sk)); ST(stage_in(ctx, BUF_IN1, input, n * 64, &d_in)); ST(stage_in(ctx, BUF_IN2, output, n * 64, &d_out));
+  ST(stage_ad(ctx, n, ad, ad_off, &d_ad, &d_off));
+  ST(stage_out(ctx, BUF_OUT0, n * 32, &d_c)); ST(stage_out(ctx, BUF_OUT1, n * 32, &d_s));
+  vrfs_status st = suite == VRFS_BANDERSNATCH_ELL2 ? ietf_prove_dev<BandSuite>(ctx, n, d_sk, d_in, d_out, d_ad, d_off, d_c, d_s)
+                                                   : ietf_prove_dev<EdSuite>(ctx, n, d_sk, d_in, d_out, d_ad, d_off, d_c, d_s);
+  ST(st);
+  ST(copy_out(ctx, out_c, d_c, n * 32)); ST(copy_out(ctx, out_s, d_s, n * 32));
+  return finish_call(ctx);
+}
+
+// ---- Secret::output, Secret::from_seed, nonce, point_to_hash, codec, data_to_point ------------
+template <class S> static vrfs_status output_dev(vrfs_ctx* ctx, size_t n, const uint8_t* sk, const uint8_t* input, uint8_t* out) {
+  typedef typename S::C C;
+  void* o = nullptr; uint8_t* valid = nullptr;
+  ST(ensure(ctx, BUF_W0, n * 96, &o)); ST(fresh_valid(ctx, n, &valid));
+  LincombArgs A = {};
+  A.n = (uint32_t)n; A.valid = valid; A.var[0] = {input, 64, sk, 32, 0}; A.out_xyz = (uint32_t*)o;
+  ST((launch_lincomb<C, 1, 0>(ctx, A)));
+  k_te_to_affine<C><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, (const uint32_t*)o, valid, out);
+  LAUNCHED_AS(ctx, "te_to_affine");
+  return VRFS_OK;
+}
+extern "C" vrfs_status vrfs_output_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* sk, const uint8_t* input, uint8_t* out_output) {
+  if (!ctx) return VRFS_BAD_ARG;
+  if (n == 0) return VRFS_OK;
+  if (!sk || !input || !out_output) return fail(ctx, VRFS_BAD_ARG, "null buffer");
+  if (suite != VRFS_BANDERSNATCH_ELL2 && suite != VRFS_ED25519_TAI) return fail(ctx, VRFS_UNSUPPORTED, "suite %d is not implemented for output", (int)suite);
+  ST(begin_call(ctx, n));
+  const uint8_t *d_sk, *d_in; uint8_t* d_o;
+  ST(stage_in(ctx, BUF_IN0, sk, n * 32, &d_sk)); ST(stage_in(ctx, BUF_IN1, input, n * 64, &d_in)); ST(stage_out(ctx, BUF_OUT0, n * 64, &d_o));
+  ST(suite == VRFS_BANDERSNATCH_ELL2 ? output_dev<BandSuite>(ctx, n, d_sk, d_in, d_o) : output_dev<EdSuite>(ctx, n, d_sk, d_in, d_o));
+  ST(copy_out(ctx, out_output, d_o, n * 64));
+  return finish_call(ctx);
+}
+template <class S> static vrfs_status from_seed_dev(vrfs_ctx* ctx, size_t n, const uint8_t* seeds, const uint64_t* off, uint8_t* out_sk, uint8_t* out_pk) {
+  typedef typename S::C C;
+  k_te_secret_from_seed<S><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, seeds, off, out_sk);
+  LAUNCHED_AS(ctx, "te_secret_from_seed");
+  if (!out_pk) return VRFS_OK;
+  void* o = nullptr;
+  ST(ensure(ctx, BUF_W0, n * 96, &o));
+  LincombArgs A = {};
+  A.n = (uint32_t)n; A.fix[0] = {out_sk, 32, 0, fixtab<S>(ctx, 0)}; A.out_xyz = (uint32_t*)o;
+  ST((launch_lincomb<C, 0, 1>(ctx, A)));
+  k_te_to_affine<C><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, (const uint32_t*)o, nullptr, out_pk);
+  LAUNCHED_AS(ctx, "te_to_affine");
+  return VRFS_OK;
+}
+extern "C" vrfs_status vrfs_secret_from_seed_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* seeds, const uint64_t* seed_off,
+                                                   uint8_t* out_sk, uint8_t* out_pk) {
+  if (!ctx) return VRFS_BAD_ARG;
+  if (n == 0) return VRFS_OK;
+  if (!seed_off || !out_sk) return fail(ctx, VRFS_BAD_ARG, "null buffer");
+  if (suite != VRFS_BANDERSNATCH_ELL2 && suite != VRFS_ED25519_TAI) return fail(ctx, VRFS_UNSUPPORTED, "suite %d is not implemented for from_seed", (int)suite);
+  ST(begin_call(ctx, n));
+  const uint8_t* d_seeds; const uint64_t* d_off; uint8_t *d_sk, *d_pk = nullptr;
+  ST(stage_ad(ctx, n, seeds, seed_off, &d_seeds, &d_off));
+  ST(stage_out(ctx, BUF_OUT0, n * 32, &d_sk));
+  if (out_pk) ST(stage_out(ctx, BUF_OUT1, n * 64, &d_pk));
+  ST(suite == VRFS_BANDERSNATCH_ELL2 ? from_seed_dev<BandSuite>(ctx, n, d_seeds, d_off, d_sk, d_pk) : from_seed_dev<EdSuite>(ctx, n, d_seeds, d_off, d_sk, d_pk));
+  ST(copy_out(ctx, out_sk, d_sk, n * 32));
+  if (out_pk) ST(copy_out(ctx, out_pk, d_pk, n * 64));
+  return finish_call(ctx);
+}
+extern "C" vrfs_status vrfs_nonce_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* sk, const uint8_t* input, uint8_t* out_k) {
+  if (!ctx) return VRFS_BAD_ARG;
+  if (n == 0) return VRFS_OK;
+  if (!sk || !input || !out_k) return fail(ctx, VRFS_BAD_ARG, "null buffer");
+  if (suite != VRFS_BANDERSNATCH_ELL2 && suite != VRFS_ED25519_TAI) return fail(ctx, VRFS_UNSUPPORTED, "suite %d is not implemented for nonce", (int)suite);
+  ST(begin_call(ctx, n));
+  const uint8_t *d_sk, *d_in; uint8_t* d_k;
+  ST(stage_in(ctx, BUF_IN0, sk, n * 32, &d_sk)); ST(stage_in(ctx, BUF_IN1, input, n * 64, &d_in)); ST(stage_out(ctx, BUF_OUT0, n * 32, &d_k));
+  if (suite == VRFS_BANDERSNATCH_ELL2) k_te_nonce<BandSuite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_sk, d_in, d_k);
+  else k_te_nonce<EdSuite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_sk, d_in, d_k);
+  LAUNCHED_AS(ctx, "te_nonce");
+  ST(copy_out(ctx, out_k, d_k, n * 32));
+  return finish_call(ctx);
+}
+extern "C" vrfs_status vrfs_point_to_hash_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* pts, uint8_t* out_hash) {
+  if (!ctx) return VRFS_BAD_ARG;
+  if (n == 0) return VRFS_OK;
+  if (!pts || !out_hash) return fail(ctx, VRFS_BAD_ARG, "null buffer");
+  if (suite != VRFS_BANDERSNATCH_ELL2 && suite != VRFS_ED25519_TAI) return fail(ctx, VRFS_UNSUPPORTED, "suite %d is not implemented for point_to_hash", (int)suite);
+  ST(begin_call(ctx, n));
+  const uint8_t* d_p; uint8_t* d_h;
+  ST(stage_in(ctx, BUF_IN0, pts, n * 64, &d_p)); ST(stage_out(ctx, BUF_OUT0, n * 64, &d_h));
+  if (suite == VRFS_BANDERSNATCH_ELL2) k_te_point_to_hash<BandSuite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_p, d_h);
+  else k_te_point_to_hash<EdSuite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_p, d_h);
+  LAUNCHED_AS(ctx, "te_point_to_hash");
+  ST(copy_out(ctx, out_hash, d_h, n * 64));
+  return finish_call(ctx);
+}
+extern "C" vrfs_status vrfs_point_encode_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* pts, uint8_t* out_enc) {
+  if (!ctx) return VRFS_BAD_ARG;
+  if (n == 0) return VRFS_OK;
+  if (!pts || !out_enc) return fail(ctx, VRFS_BAD_ARG, "null buffer");
+  if (suite != VRFS_BANDERSNATCH_ELL2 && suite != VRFS_ED25519_TAI) return fail(ctx, VRFS_UNSUPPORTED, "suite %d is not implemented for point_encode", (int)suite);
+  ST(begin_call(ctx, n));
+  const uint8_t* d_p; uint8_t* d_e;
+  ST(stage_in(ctx, BUF_IN0, pts, n * 64, &d_p)); ST(stage_out(ctx, BUF_OUT0, n * 32, &d_e));
+  if (suite == VRFS_BANDERSNATCH_ELL2) k_te_point_encode<BandCurve><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_p, d_e);
+  else k_te_point_encode<EdCurve><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_p, d_e);
+  LAUNCHED_AS(ctx, "te_point_encode");
+  ST(copy_out(ctx, out_enc, d_e, n * 32));
+  return finish_call(ctx);
+}
+extern "C" vrfs_status vrfs_point_decode_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* enc, uint8_t* out_pts, uint8_t* out_ok) {
+  if (!ctx) return VRFS_BAD_ARG;
+  if (n == 0) return VRFS_OK;
+  if (!enc || !out_pts || !out_ok) return fail(ctx, VRFS_BAD_ARG, "null buffer");
+  if (suite != VRFS_BANDERSNATCH_ELL2 && suite != VRFS_ED25519_TAI) return fail(ctx, VRFS_UNSUPPORTED, "suite %d is not implemented for point_decode", (int)suite);
+  ST(begin_call(ctx, n));
+  const uint8_t* d_e; uint8_t *d_p, *d_ok;
+  ST(stage_in(ctx, BUF_IN0, enc, n * 32, &d_e)); ST(stage_out(ctx, BUF_OUT0, n * 64, &d_p)); ST(stage_out(ctx, BUF_OUT1, n, &d_ok));
+  if (suite == VRFS_BANDERSNATCH_ELL2) k_te_point_decode<BandCurve><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_e, d_p, d_ok);
+  else k_te_point_decode<EdCurve><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_e, d_p, d_ok);
+  LAUNCHED_AS(ctx, "te_point_decode");
+  ST(copy_out(ctx, out_pts, d_p, n * 64)); ST(copy_out(ctx, out_ok, d_ok, n));
+  return finish_call(ctx);
+}
+extern "C" vrfs_status vrfs_data_to_point_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* data, const uint64_t* data_off,
+                                                uint8_t* out_pts, uint8_t* out_ok) {
+  if (!ctx) return VRFS_BAD_ARG;
+  if (n == 0) return VRFS_OK;
+  if (!data_off || !out_pts || !out_ok) return fail(ctx, VRFS_BAD_ARG, "null buffer");
+  if (suite != VRFS_BANDERSNATCH_ELL2 && suite != VRFS_ED25519_TAI) return fail(ctx, VRFS_UNSUPPORTED, "suite %d is not implemented for data_to_point", (int)suite);
+  ST(begin_call(ctx, n));
+  const uint8_t* d_d; const uint64_t* d_off; uint8_t *d_p, *d_ok;
+  ST(stage_ad(ctx, n, data, data_off, &d_d, &d_off));
+  ST(stage_out(ctx, BUF_OUT0, n * 64, &d_p)); ST(stage_out(ctx, BUF_OUT1, n, &d_ok));
+  if (suite == VRFS_BANDERSNATCH_ELL2) k_te_data_to_point<BandSuite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_d, d_off, d_p, d_ok);
+  else k_te_data_to_point<EdSuite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_d, d_off, d_p, d_ok);
+  LAUNCHED_AS(ctx, "te_data_to_point");
+  ST(copy_out(ctx, out_pts, d_p, n * 64)); ST(copy_out(ctx, out_ok, d_ok, n));
+  return finish_call(ctx);
+}
+
+// ---- pedersen ---------------------------------------------------------------------------------
+template <class S>
+static vrfs_status pedersen_prove_dev(vrfs_ctx* ctx, size_t n, const uint8_t* sk, const uint8_t* input, const uint8_t* output, const uint8_t* ad,
+                                      const uint64_t* ad_off, uint8_t* proof, uint8_t* blinding) {
+  typedef typename S::C C;
+  void *sc = nullptr, *yb = nullptr, *r = nullptr, *okp = nullptr;
+  uint8_t* valid = nullptr;
+  ST(ensure(ctx, BUF_W0, n * 96, &sc)); ST(ensure(ctx, BUF_W1, n * 96, &yb)); ST(ensure(ctx, BUF_W2, n * 96, &r)); ST(ensure(ctx, BUF_W3, n * 96, &okp));
+  ST(fresh_valid(ctx, n, &valid));
+  uint8_t *b = (uint8_t*)sc, *k = b + n * 32, *kb = k + n * 32;
+  k_pedersen_prove_prep<S><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, sk, input, ad, ad_off, b, k, kb);
+  LAUNCHED_AS(ctx, "pedersen_prove_prep");
+  LincombArgs A = {};
+  A.n = (uint32_t)n; A.valid = valid;
+  A.fix[0] = {sk, 32, 0, fixtab<S>(ctx, 0)}; A.fix[1] = {b, 32, 0, fixtab<S>(ctx, 1)}; A.out_xyz = (uint32_t*)yb;
+  ST((launch_lincomb<C, 0, 2>(ctx, A)));
+  A.fix[0] = {k, 32, 0, fixtab<S>(ctx, 0)}; A.fix[1] = {kb, 32, 0, fixtab<S>(ctx, 1)}; A.out_xyz = (uint32_t*)r;
+  ST((launch_lincomb<C, 0, 2>(ctx, A)));
+  A.var[0] = {input, 64, k, 32, 0}; A.out_xyz = (uint32_t*)okp;
+  ST((launch_lincomb<C, 1, 0>(ctx, A)));
+  k_pedersen_prove_finish<S><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, sk, b, k, kb, input, output, (const uint32_t*)yb, (const uint32_t*)r,
+                                                                               (const uint32_t*)okp, ad, ad_off, valid, proof, blinding);
+  LAUNCHED_AS(ctx, "pedersen_prove_finish");
+  return VRFS_OK;
+}
+extern "C" vrfs_status vrfs_pedersen_prove_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* sk, const uint8_t* input, const uint8_t* output,
+                                                 const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_proof, uint8_t* out_blinding) {
+  if (!ctx) return VRFS_BAD_ARG;
+  if (n == 0) return VRFS_OK;
+  if (!sk || !input || !output || !out_proof || !out_blinding) return fail(ctx, VRFS_BAD_ARG, "null buffer");
+  if (suite != VRFS_BANDERSNATCH_ELL2 && suite != VRFS_ED25519_TAI) return fail(ctx, VRFS_UNSUPPORTED, "suite %d is not implemented for pedersen prove", (int)suite);
+  ST(begin_call(ctx, n));
+  const uint8_t *d_sk, *d_in, *d_out, *d_ad; const uint64_t* d_off; uint8_t *d_pr, *d_bl;
+  ST(stage_in(ctx, BUF_IN0, sk, n * 32, &d_sk)); ST(stage_in(ctx, BUF_IN1, input, n * 64, &d_in)); ST(stage_in(ctx, BUF_IN2, output, n * 64, &d_out));
+  ST(stage_ad(ctx, n, ad, ad_off, &d_ad, &d_off));
+  ST(stage_out(ctx, BUF_OUT0, n * 256, &d_pr)); ST(stage_out(ctx, BUF_OUT1, n * 32, &d_bl));
+  ST(suite == VRFS_BANDERSNATCH_ELL2 ? pedersen_prove_dev<BandSuite>(ctx, n, d_sk, d_in, d_out, d_ad, d_off, d_pr, d_bl)
+                                     : pedersen_prove_dev<EdSuite>(ctx, n, d_sk, d_in, d_out, d_ad, d_off, d_pr, d_bl));
+  ST(copy_out(ctx, out_proof, d_pr, n * 256)); ST(copy_out(ctx, out_blinding, d_bl, n * 32));
+  return finish_call(ctx);
+}
+template <class S>
+static vrfs_status pedersen_verify_dev(vrfs_ctx* ctx, size_t n, const uint8_t* input, const uint8_t* output, const uint8_t* proof, const uint8_t* ad,
+                                       const uint64_t* ad_off, uint8_t* out_ok) {
+  typedef typename S::C C;
+  void *c = nullptr, *t1 = nullptr, *t2 = nullptr;
+  uint8_t* valid = nullptr;
+  ST(ensure(ctx, BUF_W0, n * 32, &c)); ST(ensure(ctx, BUF_W1, n * 96, &t1)); ST(ensure(ctx, BUF_W2, n * 96, &t2));
+  ST(fresh_valid(ctx, n, &valid));
+  k_pedersen_verify_prep<S><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, input, output, proof, ad, ad_off, (uint8_t*)c);
+  LAUNCHED_AS(ctx, "pedersen_verify_prep");
+  LincombArgs A = {};
+  A.n = (uint32_t)n; A.valid = valid;
+  // T1 = s*I - c*O
+  A.var[0] = {input, 64, proof + 192, 256, 0}; A.var[1] = {output, 64, (const uint8_t*)c, 32, 1}; A.out_xyz = (uint32_t*)t1;
+  ST((launch_lincomb<C, 2, 0>(ctx, A)));
+  // T2 = s*G + sb*B - c*Yb
+  A.var[0] = {proof, 256, (const uint8_t*)c, 32, 1};
+  A.fix[0] = {proof + 192, 256, 0, fixtab<S>(ctx, 0)}; A.fix[1] = {proof + 224, 256, 0, fixtab<S>(ctx, 1)}; A.out_xyz = (uint32_t*)t2;
+  ST((launch_lincomb<C, 1, 2>(ctx, A)));
+  k_pedersen_verify_finish<C><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, proof, (const uint32_t*)t1, (const uint32_t*)t2, valid, out_ok);
+  LAUNCHED_AS(ctx, "pedersen_verify_finish");
+  return VRFS_OK;
+}
+extern "C" vrfs_status vrfs_pedersen_verify_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* input, const uint8_t* output, const uint8_t* proof,
+                                                  const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_ok) {
+  if (!ctx) return VRFS_BAD_ARG;
+  if (n == 0) return VRFS_OK;
+  if (!input || !output || !proof || !out_ok) return fail(ctx, VRFS_BAD_ARG, "null buffer");
+  if (suite != VRFS_BANDERSNATCH_ELL2 && suite != VRFS_ED25519_TAI) return fail(ctx, VRFS_UNSUPPORTED, "suite %d is not implemented for pedersen verify", (int)suite);
+  ST(begin_call(ctx, n));
+  const uint8_t *d_in, *d_out, *d_pr, *d_ad; const uint64_t* d_off; uint8_t* d_ok;
+  ST(stage_in(ctx, BUF_IN0, input, n * 64, &d_in)); ST(stage_in(ctx, BUF_IN1, output, n * 64, &d_out)); ST(stage_in(ctx, BUF_IN2, proof, n * 256, &d_pr));
+  ST(stage_ad(ctx, n, ad, ad_off, &d_ad, &d_off));
+  ST(stage_out(ctx, BUF_OUT0, n, &d_ok));
+  ST(suite == VRFS_BANDERSNATCH_ELL2 ? pedersen_verify_dev<BandSuite>(ctx, n, d_in, d_out, d_pr, d_ad, d_off, d_ok)
+                                     : pedersen_verify_dev<EdSuite>(ctx, n, d_in, d_out, d_pr, d_ad, d_off, d_ok));
+  ST(copy_out(ctx, out_ok, d_ok, n));
+  return finish_call(ctx);
+}
+
 // =================================================================================================
 // entry points still to be implemented in this round (they fail loudly, never fall back to the CPU)
 // =================================================================================================
 #define NOT_YET(name) return fail(ctx, VRFS_UNSUPPORTED, name " is not implemented yet")
-extern "C" vrfs_status vrfs_secret_from_seed_batch(vrfs_ctx* ctx, vrfs_suite, size_t, const uint8_t*, const uint64_t*, uint8_t*, uint8_t*) { NOT_YET("vrfs_secret_from_seed_batch"); }
-extern "C" vrfs_status vrfs_data_to_point_batch(vrfs_ctx* ctx, vrfs_suite, size_t, const uint8_t*, const uint64_t*, uint8_t*, uint8_t*) { NOT_YET("vrfs_data_to_point_batch"); }
-extern "C" vrfs_status vrfs_output_batch(vrfs_ctx* ctx, vrfs_suite, size_t, const uint8_t*, const uint8_t*, uint8_t*) { NOT_YET("vrfs_output_batch"); }
-extern "C" vrfs_status vrfs_point_to_hash_batch(vrfs_ctx* ctx, vrfs_suite, size_t, const uint8_t*, uint8_t*) { NOT_YET("vrfs_point_to_hash_batch"); }
-extern "C" vrfs_status vrfs_point_encode_batch(vrfs_ctx* ctx, vrfs_suite, size_t, const uint8_t*, uint8_t*) { NOT_YET("vrfs_point_encode_batch"); }
-extern "C" vrfs_status vrfs_point_decode_batch(vrfs_ctx* ctx, vrfs_suite, size_t, const uint8_t*, uint8_t*, uint8_t*) { NOT_YET("vrfs_point_decode_batch"); }
-extern "C" vrfs_status vrfs_nonce_batch(vrfs_ctx* ctx, vrfs_suite, size_t, const uint8_t*, const uint8_t*, uint8_t*) { NOT_YET("vrfs_nonce_batch"); }
-extern "C" vrfs_status vrfs_ietf_prove_batch(vrfs_ctx* ctx, vrfs_suite, size_t, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*, const uint64_t*, uint8_t*, uint8_t*) { NOT_YET("vrfs_ietf_prove_batch"); }
-extern "C" vrfs_status vrfs_pedersen_prove_batch(vrfs_ctx* ctx, vrfs_suite, size_t, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*, const uint64_t*, uint8_t*, uint8_t*) { NOT_YET("vrfs_pedersen_prove_batch"); }
-extern "C" vrfs_status vrfs_pedersen_verify_batch(vrfs_ctx* ctx, vrfs_suite, size_t, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*, const uint64_t*, uint8_t*) { NOT_YET("vrfs_pedersen_verify_batch"); }
 extern "C" vrfs_status vrfs_msm_g1_bls12_381(vrfs_ctx* ctx, size_t, const uint8_t*, const uint8_t*, int, uint8_t*) { NOT_YET("vrfs_msm_g1_bls12_381"); }
 extern "C" vrfs_status vrfs_msm_g1_partial(vrfs_ctx* ctx, size_t, const uint8_t*, const uint8_t*, int, uint8_t*) { NOT_YET("vrfs_msm_g1_partial"); }
 extern "C" vrfs_status vrfs_g1_sum_partials(vrfs_ctx* ctx, int, int, const uint8_t*, uint8_t*) { NOT_YET("vrfs_g1_sum_partials"); }

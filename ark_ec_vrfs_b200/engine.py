@@ -98,6 +98,15 @@ class Engine:
         self._check(self._lib.vrfs_ietf_verify_batch(self._ctx, suite, C.c_size_t(n), v(pk), v(inp), v(outp), v(c), v(s), v(ad), v(off), v(ok)))
 
     # ---- measurement
+    def enable_kernel_timing(self, on=True):
+        self._check(self._lib.vrfs_ctx_enable_kernel_timing(self._ctx, int(bool(on))))
+
+    def kernel_timings(self):
+        """[(kernel name, device ms)] of the most recent batch call (syncs the stream)"""
+        names = (C.c_char_p * 64)(); ms = (C.c_float * 64)()
+        n = self._lib.vrfs_ctx_kernel_timings(self._ctx, names, ms, 64)
+        return [(names[i].decode(), float(ms[i])) for i in range(n)]
+
     def measure_mac32_peak(self, variant=0):
         macs = C.c_double(); mhz = C.c_double()
         self._check(self._lib.vrfs_measure_mac32_peak(self._ctx, int(variant), C.byref(macs), C.byref(mhz)))

@@ -51,6 +51,10 @@ const char* vrfs_last_error(const vrfs_ctx* ctx);
 void* vrfs_ctx_stream(vrfs_ctx* ctx);
 /* number of kernel launches issued by this context so far (bench.py's `gpu_launches`) */
 uint64_t vrfs_ctx_launch_count(const vrfs_ctx* ctx);
+/* per-kernel device times (CUDA events on the context's stream) of the most recent batch call; used by
+ * bench.py for the roofline of the dominant kernel.  names[i] are static strings. */
+vrfs_status vrfs_ctx_enable_kernel_timing(vrfs_ctx* ctx, int on);
+int vrfs_ctx_kernel_timings(vrfs_ctx* ctx, const char** names, float* ms, int cap);
 /* suite constants: SUITE_ID-independent sizes used by callers to size buffers */
 int vrfs_suite_challenge_len(vrfs_suite s);   /* Suite::CHALLENGE_LEN */
 int vrfs_suite_hash_len(vrfs_suite s);        /* HashOutput<S> length */

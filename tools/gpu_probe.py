@@ -9,8 +9,8 @@ import oracle_lib as O, vectors as V
 
 e = vrfs.Engine(0)
 res = {"nproc": os.cpu_count()}
-names = {0: "mad.wide.u32", 1: "mad.lo.u32", 2: "montmul_chain1", 3: "montmul_chain2", 4: "mad.hi.u32"}
-for v in range(5):
+names = {0: "mad.wide.u32", 1: "mad.lo.u32", 2: "montmul_chain1", 3: "montmul_chain2", 4: "mad.hi.u32", 5: "carry_chain_rows_reg", 6: "carry_chain_rows_imm"}
+for v in range(7):
     macs, mhz = e.measure_mac32_peak(v)
     res[names[v]] = {"Tmac_per_s": macs / 1e12, "sm_mhz_est": mhz, "mac_per_clk_per_sm": macs / (mhz * 1e6) / 148}
     print(names[v], res[names[v]], flush=True)
@@ -23,4 +23,7 @@ for logn in (12, 16, 20):
     res["verify_2^%d" % logn] = {"s": dt, "per_s": (1 << logn) / dt}
     print("verify 2^%d: %.4fs  %.3f M/s (host buffers, pageable)" % (logn, dt, (1 << logn) / dt / 1e6), flush=True)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-json.dump(res, open(os.path.join(ROOT, "gpurun_out", "probe.json"), "w"), indent=1)
+e.enable_kernel_timing(True)
+got = e.ietf_verify(0, w["pk"], w["inp"], w["out"], w["c"], w["s"], None)
+res["kernels_2^20_ms"] = e.kernel_timings(); print(res["kernels_2^20_ms"])
+json.dump(res, open(os.path.join(ROOT, "gpurun_out", "probe%s.json" % os.environ.get("PROBE_TAG", "")), "w"), indent=1)
