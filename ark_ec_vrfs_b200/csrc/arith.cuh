@@ -171,11 +171,28 @@ HD_INLINE void mont_mul_limbs(uint32_t* out, const uint32_t* a, const uint32_t* 
   }
 }
 
+// The product is a CALLED function (by-value arguments travel in registers under the device ABI), not
+// inlined: a point addition inlines 9 of them and the scalar-multiplication loop then no longer fits the
+// instruction caches - the first ncu capture of the inlined build showed `stall_no_instruction` as the top
+// stall reason by 4x (profiles/r1a_*).  VRFS_INLINE_MUL=1 restores the inlined form for comparison.
+#ifndef VRFS_INLINE_MUL
+#define VRFS_INLINE_MUL 0
+#endif
 template <class P>
-HD_INLINE Fp<P> operator*(const Fp<P>& a, const Fp<P>& b) {
+HD_NOINLINE Fp<P> mont_mul_call(Fp<P> a, Fp<P> b) {
   Fp<P> r;
   mont_mul_limbs<P>(r.v, a.v, b.v);
   return r;
+}
+template <class P>
+HD_INLINE Fp<P> operator*(const Fp<P>& a, const Fp<P>& b) {
+#if VRFS_INLINE_MUL
+  Fp<P> r;
+  mont_mul_limbs<P>(r.v, a.v, b.v);
+  return r;
+#else
+  return mont_mul_call<P>(a, b);
+#endif
 }
 template <class P>
 HD_INLINE Fp<P> sqr(const Fp<P>& a) { return a * a; }

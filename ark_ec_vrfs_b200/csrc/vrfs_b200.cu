@@ -30,7 +30,7 @@ __global__ void k_te_fixed_table(TEAffCached<C>* out, int blinding) {
 // K7/K8/K9a: R_i = sum var + sum fixed, projective out.  Persistent grid-stride so that the window-table
 // slab is per resident thread (L2-resident), not per item.
 template <class C, int NV, int NF>
-__global__ void __launch_bounds__(LINCOMB_THREADS) k_te_lincomb(LincombArgs A) {
+__global__ void __launch_bounds__(LINCOMB_THREADS, 4) k_te_lincomb(LincombArgs A) {
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
   TECached<C>* slab = reinterpret_cast<TECached<C>*>(A.slab + (size_t)tid * te_slab_bytes<C>(NV));
   for (uint32_t item = tid; item < A.n; item += nthreads) {

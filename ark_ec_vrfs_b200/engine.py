@@ -97,6 +97,79 @@ class Engine:
         v = lambda x: C.c_void_p(x) if x else None
         self._check(self._lib.vrfs_ietf_verify_batch(self._ctx, suite, C.c_size_t(n), v(pk), v(inp), v(outp), v(c), v(s), v(ad), v(off), v(ok)))
 
+    # ---- keys, inputs, outputs (Secret / Public / Input / Output of the reference API)
+    def _call(self, fn, *args):
+        self._check(getattr(self._lib, fn)(self._ctx, *args))
+
+    def hash_len(self, suite):
+        return self._lib.vrfs_suite_hash_len(suite)
+
+    def point_enc_len(self, suite):
+        return self._lib.vrfs_suite_point_enc_len(suite)
+
+    def challenge_len(self, suite):
+        return self._lib.vrfs_suite_challenge_len(suite)
+
+    def secret_from_seed(self, suite, seeds, want_pk=True):
+        data, off = pack_var(seeds); n = len(off) - 1
+        sk = np.zeros((n, 32), np.uint8); pk = np.zeros((n, 64), np.uint8) if want_pk else None
+        self._call("vrfs_secret_from_seed_batch", suite, C.c_size_t(n), _p(data), _p(off), _p(sk), _p(pk))
+        return (sk, pk) if want_pk else sk
+
+    def data_to_point(self, suite, datas):
+        data, off = pack_var(datas); n = len(off) - 1
+        pts = np.zeros((n, 64), np.uint8); ok = np.zeros(n, np.uint8)
+        self._call("vrfs_data_to_point_batch", suite, C.c_size_t(n), _p(data), _p(off), _p(pts), _p(ok))
+        return pts, ok
+
+    def output(self, suite, sk, inp):
+        sk = _u8(sk, (-1, 32)); n = len(sk); inp = _u8(inp, (n, 64)); out = np.zeros((n, 64), np.uint8)
+        self._call("vrfs_output_batch", suite, C.c_size_t(n), _p(sk), _p(inp), _p(out))
+        return out
+
+    def point_to_hash(self, suite, pts):
+        pts = _u8(pts, (-1, 64)); n = len(pts); out = np.zeros((n, self.hash_len(suite)), np.uint8)
+        self._call("vrfs_point_to_hash_batch", suite, C.c_size_t(n), _p(pts), _p(out))
+        return out
+
+    def point_encode(self, suite, pts):
+        pts = _u8(pts, (-1, 64)); n = len(pts); out = np.zeros((n, self.point_enc_len(suite)), np.uint8)
+        self._call("vrfs_point_encode_batch", suite, C.c_size_t(n), _p(pts), _p(out))
+        return out
+
+    def point_decode(self, suite, enc):
+        enc = _u8(enc, (-1, self.point_enc_len(suite))); n = len(enc)
+        pts = np.zeros((n, 64), np.uint8); ok = np.zeros(n, np.uint8)
+        self._call("vrfs_point_decode_batch", suite, C.c_size_t(n), _p(enc), _p(pts), _p(ok))
+        return pts, ok
+
+    def nonce(self, suite, sk, inp):
+        sk = _u8(sk, (-1, 32)); n = len(sk); inp = _u8(inp, (n, 64)); out = np.zeros((n, 32), np.uint8)
+        self._call("vrfs_nonce_batch", suite, C.c_size_t(n), _p(sk), _p(inp), _p(out))
+        return out
+
+    def ietf_prove(self, suite, sk, inp, outp, ad=None):
+        sk = _u8(sk, (-1, 32)); n = len(sk); inp = _u8(inp, (n, 64)); outp = _u8(outp, (n, 64))
+        adb, off = pack_var(ad)
+        c = np.zeros((n, 32), np.uint8); s = np.zeros((n, 32), np.uint8)
+        self._call("vrfs_ietf_prove_batch", suite, C.c_size_t(n), _p(sk), _p(inp), _p(outp), _p(adb), _p(off), _p(c), _p(s))
+        return c, s
+
+    # ---- pedersen
+    def pedersen_prove(self, suite, sk, inp, outp, ad=None):
+        sk = _u8(sk, (-1, 32)); n = len(sk); inp = _u8(inp, (n, 64)); outp = _u8(outp, (n, 64))
+        adb, off = pack_var(ad)
+        proof = np.zeros((n, 256), np.uint8); bl = np.zeros((n, 32), np.uint8)
+        self._call("vrfs_pedersen_prove_batch", suite, C.c_size_t(n), _p(sk), _p(inp), _p(outp), _p(adb), _p(off), _p(proof), _p(bl))
+        return proof, bl
+
+    def pedersen_verify(self, suite, inp, outp, proof, ad=None):
+        inp = _u8(inp, (-1, 64)); n = len(inp); outp = _u8(outp, (n, 64)); proof = _u8(proof, (n, 256))
+        adb, off = pack_var(ad)
+        ok = np.zeros(n, np.uint8)
+        self._call("vrfs_pedersen_verify_batch", suite, C.c_size_t(n), _p(inp), _p(outp), _p(proof), _p(adb), _p(off), _p(ok))
+        return ok
+
     # ---- measurement
     def enable_kernel_timing(self, on=True):
         self._check(self._lib.vrfs_ctx_enable_kernel_timing(self._ctx, int(bool(on))))

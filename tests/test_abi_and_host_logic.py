@@ -1,0 +1,132 @@
+"""CPU-only checks of the product's host side: the C-ABI library loads and exports every symbol of
+include/vrfs_b200.h, fails loudly without a GPU (no fallback), and the device headers - compiled for the
+host by tests/host_emul - agree with big-integer arithmetic and with the oracle."""
+import ctypes as C
+import os
+import random
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from oracle import pyref as R
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from ark_ec_vrfs_b200 import build, _lib
+    build.build()
+    return _lib.load()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from ark_ec_vrfs_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "vrfs_b200.h")).read()
+    declared = set(re.findall(r"\b(vrfs_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    for s in declared:
+        assert hasattr(lib, s), s
+    assert lib.vrfs_abi_version() == 1
+    assert [lib.vrfs_suite_challenge_len(i) for i in range(3)] == [32, 16, 16]
+    assert [lib.vrfs_suite_hash_len(i) for i in range(3)] == [64, 64, 32]
+    assert [lib.vrfs_suite_point_enc_len(i) for i in range(3)] == [32, 32, 33]
+
+
+def test_no_cpu_fallback_without_gpu(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import ark_ec_vrfs_b200 as vrfs
+    with pytest.raises(vrfs.VrfsError) as e:
+        vrfs.Engine(0)
+    assert "VRFS_CUDA_ERROR" in str(e.value)
+
+
+def test_product_does_not_reference_oracle():
+    """nothing under ark_ec_vrfs_b200/ may import, link or call the oracle"""
+    for root, _, files in os.walk(os.path.join(ROOT, "ark_ec_vrfs_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(root, f)).read()
+                assert "oracle_lib" not in txt and "liboracle" not in txt and "vrf_oracle" not in txt and "pyref" not in txt.replace("oracle/pyref.py", ""), f
+
+
+@pytest.fixture(scope="module")
+def emu():
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "tests", "host_emul")], check=True)
+    return C.CDLL(os.path.join(ROOT, "tests", "host_emul", "libhostemu.so"))
+
+
+FIELDS = [(R.BLS_FR, 8), (R.BANDERSNATCH.r, 8), (R.ED25519.p, 8), (R.ED25519.r, 8), (R.P256.p, 8), (R.P256.r, 8), (R.BLS_FQ, 12)]
+
+
+def _fop(emu, f, o, a, b, n):
+    A = (C.c_uint32 * n)(*[(a >> (32 * i)) & 0xFFFFFFFF for i in range(n)])
+    B = (C.c_uint32 * n)(*[(b >> (32 * i)) & 0xFFFFFFFF for i in range(n)])
+    out = (C.c_uint32 * n)()
+    emu.hostemu_field_op(f, o, A, B, out)
+    return sum(int(out[i]) << (32 * i) for i in range(n))
+
+
+@pytest.mark.parametrize("fi", range(len(FIELDS)))
+def test_montgomery_field_arithmetic(emu, fi):
+    p, n = FIELDS[fi]
+    Rm = 1 << (32 * n); Ri = pow(Rm, -1, p)
+    rnd = random.Random(fi)
+    for t in range(200):
+        a = [0, 1, p - 1, p - 2][t] if t < 4 else rnd.randrange(p)
+        b = rnd.randrange(Rm) if t % 2 else rnd.choice([0, 1, p - 1, Rm - 1, p])
+        assert _fop(emu, fi, 0, a, b, n) == a * b * Ri % p
+        b2 = rnd.randrange(p)
+        assert _fop(emu, fi, 1, a, b2, n) == (a + b2) % p
+        assert _fop(emu, fi, 2, a, b2, n) == (a - b2) % p
+        assert _fop(emu, fi, 3, b, 0, n) == b * Rm % p
+        assert _fop(emu, fi, 4, a, 0, n) == a * Ri % p
+        assert _fop(emu, fi, 6, b, a, n) == (a * Rm + b) * Rm % p
+    for t in range(4):
+        a = rnd.randrange(1, p)
+        assert _fop(emu, fi, 5, a * Rm % p, 0, n) == pow(a, -1, p) * Rm % p
+        assert _fop(emu, fi, 7, a * Rm % p, 0, n) == (1 if R.legendre(a, p) == 1 else 0)
+        assert _fop(emu, fi, 8, a * Rm % p, 0, n) == (1 if a > (p - 1) // 2 else 0) | ((a & 1) << 1)
+
+
+def test_glv_split_and_lincomb(emu):
+    cv = R.BANDERSNATCH; r = cv.r; lam = R.BANDERSNATCH_GLV_LAMBDA
+    rnd = random.Random(11)
+    for k in [0, 1, r - 1, r // 2] + [rnd.randrange(r) for _ in range(300)]:
+        K = (C.c_uint32 * 8)(*[(k >> (32 * i)) & 0xFFFFFFFF for i in range(8)]); out = (C.c_uint32 * 10)()
+        emu.hostemu_glv(K, out)
+        k1 = sum(out[i] << (32 * i) for i in range(4)) * (-1 if out[8] else 1)
+        k2 = sum(out[4 + i] << (32 * i) for i in range(4)) * (-1 if out[9] else 1)
+        assert (k1 + k2 * lam - k) % r == 0 and abs(k1) < (1 << 127) * 7 // 15 and abs(k2) < (1 << 127) * 7 // 15
+    le = lambda x: x.to_bytes(32, "little")
+    pt = lambda P: le(P[0]) + le(P[1])
+    for suite, cv in ((0, R.BANDERSNATCH), (1, R.ED25519)):
+        r = cv.r
+        P1 = cv.mul(rnd.randrange(r), cv.G); P2 = cv.mul(rnd.randrange(r), cv.G)
+        for nv, nf in ((0, 1), (1, 0), (2, 0), (1, 1)):
+            for neg in (0, 3, 5, 6):
+                k1, k2, f = (rnd.choice([0, 1, r - 1, rnd.randrange(r)]) for _ in range(3))
+                out = C.create_string_buffer(64)
+                assert emu.hostemu_lincomb(suite, nv, nf, pt(P1), le(k1), pt(P2), le(k2), le(f), neg, out) == 1
+                E = cv.identity()
+                if nv >= 1: E = cv.add(E, cv.mul((-k1 if neg & 1 else k1) % r, P1))
+                if nv >= 2: E = cv.add(E, cv.mul((-k2 if neg & 2 else k2) % r, P2))
+                if nf >= 1: E = cv.add(E, cv.mul((-f if neg & 4 else f) % r, cv.G))
+                assert out.raw == pt(E), (suite, nv, nf, neg)
+
+
+@pytest.mark.parametrize("suite", [0, 1])
+def test_host_emulated_ietf_verify_matches_oracle(emu, suite):
+    import vectors as V
+    n = 24
+    w = V.make_ietf_proofs(suite, n, "ragged")
+    ad, off = O.pack_var(w["ads"])
+    got = np.zeros(n, np.uint8)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    emu.hostemu_ietf_verify(suite, C.c_size_t(n), p(w["pk"]), p(w["inp"]), p(w["out"]), p(w["c"]), p(w["s"]), p(ad), p(off), p(got))
+    assert np.array_equal(got, w["expect"]) and 0 < got.sum() < n
