@@ -126,20 +126,42 @@ HD_INLINE bool ark_decode_point(typename C::F& x, typename C::F& y, const uint8_
   return true;
 }
 
-// hash_to_curve_tai_rfc_9381 with the LE codec (Ed25519 suite): first ctr whose hash decodes to a point
-// whose cofactor multiple is not the identity.
+// Sec1Codec point_decode (A.2): (0x02|0x03) || BE32(x); y = sqrt(x^3 + a x + b) with the requested parity
+template <class C>
+HD_INLINE bool sec1_decode_point(typename C::F& x, typename C::F& y, const uint8_t* in) {
+  typedef typename C::F F;
+  if (in[0] != 2 && in[0] != 3) return false;
+  uint32_t raw[8];
+  load_be<8>(raw, in + 1);
+  if (!is_canonical<typename C::Fq>(raw)) return false;
+  x = to_mont<typename C::Fq>(raw);
+  F rhs = (sqr(x) + C::mul_a(F::one())) * x + C::b();
+  if (rhs.is_zero()) y = F::zero();
+  else if (!sqrt_ct<typename C::Fq>(&y, &rhs)) return false;
+  if (is_odd(y) != (bool)(in[0] & 1)) y = neg(y);
+  return true;
+}
+template <class S> HD_INLINE bool decode_point(typename S::C::F& x, typename S::C::F& y, const uint8_t* in) {
+  if constexpr (S::SEC1) return sec1_decode_point<typename S::C>(x, y, in); else return ark_decode_point<typename S::C>(x, y, in);
+}
+
+// hash_to_curve_tai_rfc_9381 (A.5): first ctr whose hash decodes to a point whose cofactor multiple is not
+// the identity.  LE codec: decode hs[0..32]; SEC1 codec: decode 0x02 || hs.
 template <class S>
-HD_INLINE bool te_h2c_tai(TEPoint<typename S::C>& P, const uint8_t* data, uint32_t len) {
+HD_INLINE bool h2c_tai(typename Grp<typename S::C>::Pt& P, const uint8_t* data, uint32_t len) {
   typedef typename S::C C;
+  typedef Grp<C> G;
   for (int ctr = 0; ctr < 256; ctr++) {
     typename S::H h; h.init();
     put_suite_id<S>(h); h.put(0x01); h.update(data, len); h.put((uint8_t)ctr); h.put(0x00);
-    uint8_t hs[S::HLEN]; h.final(hs);
+    uint8_t hs[S::HLEN + 1];
+    hs[0] = 0x02;
+    h.final(hs + 1);
     typename C::F x, y;
-    if (!ark_decode_point<C>(x, y, hs)) continue;
-    te_from_affine<C>(P, x, y);
-    for (int i = 0; i < C::COF_LOG2; i++) te_dbl<C>(&P, &P, true);
-    if (te_is_identity<C>(P)) continue;
+    if (!decode_point<S>(x, y, S::SEC1 ? hs : hs + 1)) continue;
+    G::from_affine(P, x, y);
+    for (int i = 0; i < C::COF_LOG2; i++) G::dbl(&P);
+    if constexpr (C::IS_TE) { if (te_is_identity<C>(P)) continue; }
     return true;
   }
   return false;

@@ -1,0 +1,228 @@
+// K7 + K8 of SURVEY.md 2.5: one item's linear combination
+//     R = sum_j  (+/-) k_j * P_j   (variable bases, per item)   +   sum_f (+/-) s_f * B_f  (fixed bases)
+// which is every group computation of the hot path:
+//   ietf verify   U = s*G - c*Y            (NV=1, NF=1)      V = s*I - c*O      (NV=2)
+//   ietf prove    k*G (NF=1), k*I (NV=1);  Secret::output  sk*I (NV=1);  Public  sk*G (NF=1)
+//   pedersen      sk*G + b*B (NF=2), k*G + kb*B (NF=2), k*I, s*I - c*O (NV=2), c*Yb - s*G - sb*B (NV=1, NF=2)
+// The reference does each k*P with ark-ec's bit-serial `mul_bigint`; the result is the same group
+// element, and every consumer works on its canonical affine encoding.
+//
+// Variable bases: signed radix-16 fixed windows (no data-dependent branches -> no warp divergence),
+// Bandersnatch scalars GLV-split into two 127-bit halves acting on P and psi(P) so a K-term sum costs
+// 124 shared doublings + 32*2K additions.  Window tables (9 entries per base incl. the identity)
+// live in a per-thread slab of global memory (L2-resident across the resident grid), read with 16-byte loads.
+// Fixed bases: signed radix-256 windows over a precomputed table (32-33 x 129 entries, ~400 KB, L2-resident).
+// One implementation serves the twisted-Edwards suites (Bandersnatch, Ed25519) and the short-Weierstrass
+// one (secp256r1) through the Grp<C> adapter below.
+#pragma once
+#include "te.cuh"
+#include "sw.cuh"
+#include "scalar.cuh"
+
+namespace vrfs {
+
+#if !defined(__CUDACC__)
+struct uint4 { uint32_t x, y, z, w; };
+#endif
+#if defined(__CUDACC__)
+#define VRFS_HD __host__ __device__
+#else
+#define VRFS_HD
+#endif
+
+template <class T> HD_INLINE void copy_words16(T* dst, const T* src_) {  // sizeof(T) % 16 == 0, both 16-byte aligned
+  const uint4* s = reinterpret_cast<const uint4*>(src_);
+  uint4* d = reinterpret_cast<uint4*>(dst);
+  for (unsigned i = 0; i < sizeof(T) / 16; i++) d[i] = s[i];
+}
+
+// ---- group adapters ---------------------------------------------------------------------------
+template <class C, bool TE = C::IS_TE> struct Grp;
+template <class C> struct Grp<C, true> {
+  typedef TEPoint<C> Pt;
+  typedef TECached<C> Entry;        // window-table entry
+  typedef TEAffCached<C> FixEntry;  // fixed-base table entry
+  static constexpr int SPLIT = C::HAS_GLV ? 2 : 1;          // tables per variable base
+  static constexpr int WINDOWS = C::HAS_GLV ? 32 : 64;      // radix-16 windows per (half-)scalar
+  static constexpr int KB_LIMBS = C::HAS_GLV ? 4 : 8;
+  static constexpr int FIX_WINDOWS = 32;
+  static HD_INLINE void set_identity(Pt& P) { te_set_identity(P); }
+  static HD_INLINE void from_affine(Pt& P, const typename C::F& x, const typename C::F& y) { te_from_affine<C>(P, x, y); }
+  static HD_INLINE bool on_curve(const typename C::F& x, const typename C::F& y) { return te_on_curve<C>(x, y); }
+  static HD_INLINE void to_entry(Entry& e, const Pt& P) { te_to_cached(e, P); }
+  static HD_INLINE void add_entry(Pt* acc, const Entry* e, bool negate) { te_add_cached<C>(acc, acc, e, negate); }
+  static HD_INLINE void add_fix(Pt* acc, const FixEntry* e, bool negate) { te_madd<C>(acc, acc, e, negate); }
+  static HD_INLINE void dbl4(Pt* acc) { te_dbl<C>(acc, acc, false); te_dbl<C>(acc, acc, false); te_dbl<C>(acc, acc, false); te_dbl<C>(acc, acc, true); }
+  static HD_INLINE void dbl(Pt* acc) { te_dbl<C>(acc, acc, true); }
+  static HD_INLINE void add(Pt* r, const Pt* p, const Pt* q) { te_add<C>(r, p, q); }
+  static HD_INLINE void to_fix(FixEntry& e, const Pt& P) {
+    typename C::F zi = inv(P.Z);
+    e.x = P.X * zi; e.y = P.Y * zi; e.dt = e.x * e.y * C::d();
+  }
+};
+template <class C> struct Grp<C, false> {
+  typedef SWPoint<C> Pt;
+  typedef SWPoint<C> Entry;
+  typedef SWPoint<C> FixEntry;
+  static constexpr int SPLIT = 1;
+  static constexpr int WINDOWS = 65;       // 64 radix-16 digits + the carry of the bias addition (n ~ 2^256)
+  static constexpr int KB_LIMBS = 9;
+  static constexpr int FIX_WINDOWS = 33;
+  static HD_INLINE void set_identity(Pt& P) { sw_set_identity(P); }
+  static HD_INLINE void from_affine(Pt& P, const typename C::F& x, const typename C::F& y) { sw_from_affine<C>(P, x, y); }
+  static HD_INLINE bool on_curve(const typename C::F& x, const typename C::F& y) { return sw_on_curve<C>(x, y); }
+  static HD_INLINE void to_entry(Entry& e, const Pt& P) { e = P; }
+  static HD_INLINE void add_entry(Pt* acc, const Entry* e, bool negate) { Entry q = *e; sw_cneg(q, negate); sw_add<C>(acc, acc, &q); }
+  static HD_INLINE void add_fix(Pt* acc, const FixEntry* e, bool negate) { add_entry(acc, e, negate); }
+  static HD_INLINE void dbl4(Pt* acc) { for (int i = 0; i < 4; i++) sw_add<C>(acc, acc, acc); }
+  static HD_INLINE void dbl(Pt* acc) { sw_add<C>(acc, acc, acc); }
+  static HD_INLINE void add(Pt* r, const Pt* p, const Pt* q) { sw_add<C>(r, p, q); }
+  static HD_INLINE void to_fix(FixEntry& e, const Pt& P) {            // normalise to Z = 1 (identity stays (0:1:0))
+    bool inf = P.Z.is_zero();
+    typename C::F zi = inv(P.Z);
+    e.X = P.X * zi; e.Y = select(inf, C::F::one(), P.Y * zi); e.Z = select(inf, C::F::zero(), C::F::one());
+  }
+};
+static constexpr int TBL_ENTRIES = 9;     // 0*P .. 8*P
+static constexpr int FIX_ENTRIES = 129;   // 0 .. 128 times 256^w * B
+// bytes of per-thread table slab for NV variable bases
+template <class C> VRFS_HD constexpr size_t slab_bytes(int nv) { return (size_t)nv * Grp<C>::SPLIT * TBL_ENTRIES * sizeof(typename Grp<C>::Entry); }
+template <class C> VRFS_HD constexpr size_t fix_table_entries() { return (size_t)Grp<C>::FIX_WINDOWS * FIX_ENTRIES; }
+
+struct VarTerm { const uint8_t* pts; uint32_t pt_stride; const uint8_t* sc; uint32_t sc_stride; uint32_t negate; };
+struct FixTerm { const uint8_t* sc; uint32_t sc_stride; uint32_t negate; const void* table; };
+struct LincombArgs {
+  uint32_t n;
+  VarTerm var[2];
+  FixTerm fix[2];
+  uint32_t* out_xyz;     // n x 3N limbs: X, Y, Z (Montgomery form)
+  uint8_t* valid;        // n bytes, AND-ed with "all variable bases canonical and on the curve" (may be null)
+  uint8_t* slab;         // per-thread table slabs
+};
+
+// affine x||y, 32-byte little-endian canonical each -> Montgomery; false if not canonical / not on the curve.
+// Short-Weierstrass: 64 zero bytes are the identity (valid; *is_inf set).
+template <class C> HD_INLINE bool load_affine(typename C::F& x, typename C::F& y, bool* is_inf, const uint8_t* p) {
+  uint32_t rx[8], ry[8];
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 a = q[0], b = q[1], c = q[2], d = q[3];
+  rx[0] = a.x; rx[1] = a.y; rx[2] = a.z; rx[3] = a.w; rx[4] = b.x; rx[5] = b.y; rx[6] = b.z; rx[7] = b.w;
+  ry[0] = c.x; ry[1] = c.y; ry[2] = c.z; ry[3] = c.w; ry[4] = d.x; ry[5] = d.y; ry[6] = d.z; ry[7] = d.w;
+  bool ok = is_canonical<typename C::Fq>(rx) & is_canonical<typename C::Fq>(ry);
+  x = to_mont<typename C::Fq>(rx); y = to_mont<typename C::Fq>(ry);
+  bool inf = false;
+  if (!C::IS_TE) { uint32_t o = 0; for (int i = 0; i < 8; i++) o |= rx[i] | ry[i]; inf = (o == 0); }
+  if (is_inf) *is_inf = inf;
+  return inf | (ok & Grp<C>::on_curve(x, y));
+}
+template <class C> HD_INLINE bool te_load_affine(typename C::F& x, typename C::F& y, const uint8_t* p) { return load_affine<C>(x, y, nullptr, p); }
+// 32-byte little-endian scalar, reduced mod r (codec scalar_decode = from_le_bytes_mod_order) -> canonical limbs
+template <class C> HD_INLINE void load_scalar_mod_r(uint32_t* k, const uint8_t* p) {
+  uint32_t raw[8];
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 a = q[0], b = q[1];
+  raw[0] = a.x; raw[1] = a.y; raw[2] = a.z; raw[3] = a.w; raw[4] = b.x; raw[5] = b.y; raw[6] = b.z; raw[7] = b.w;
+  Fp<typename C::Fr> m = to_mont<typename C::Fr>(raw);
+  from_mont<typename C::Fr>(k, m);
+}
+
+// table of j*B, j = 0..8; B in projective/extended coordinates
+template <class C> HD_INLINE void build_table(typename Grp<C>::Entry* tbl, const typename Grp<C>::Pt& B) {
+  typedef Grp<C> G;
+  typename G::Pt cur; G::set_identity(cur);
+  typename G::Entry cb, e;
+  G::to_entry(cb, B);
+  G::to_entry(e, cur); copy_words16(&tbl[0], &e);
+  copy_words16(&tbl[1], &cb);
+  cur = B;
+#pragma unroll 1
+  for (int j = 2; j <= 8; j++) {
+    G::add_entry(&cur, &cb, false);
+    G::to_entry(e, cur); copy_words16(&tbl[j], &e);
+  }
+}
+
+template <class C, int NV, int NF>
+HD_INLINE bool lincomb_item(const LincombArgs& A, uint32_t item, typename Grp<C>::Entry* slab, typename Grp<C>::Pt& acc) {
+  typedef Grp<C> G;
+  typedef typename C::F F;
+  constexpr int NT = NV * G::SPLIT;
+  bool ok = true;
+  G::set_identity(acc);
+  if (NV > 0) {
+    uint32_t kb[NT > 0 ? NT : 1][G::KB_LIMBS];
+    bool kneg[NT > 0 ? NT : 1];
+#pragma unroll
+    for (int v = 0; v < NV; v++) {
+      F x, y;
+      bool inf = false;
+      ok &= load_affine<C>(x, y, &inf, A.var[v].pts + (size_t)item * A.var[v].pt_stride);
+      typename G::Pt B; G::from_affine(B, x, y);
+      if (!C::IS_TE && inf) G::set_identity(B);
+      uint32_t k[8];
+      load_scalar_mod_r<C>(k, A.var[v].sc + (size_t)item * A.var[v].sc_stride);
+      bool neg = A.var[v].negate != 0;
+      if constexpr (C::IS_TE && G::SPLIT == 2) {
+        GlvHalf h1, h2;
+        band_glv_split(&h1, &h2, k);
+        for (int i = 0; i < 4; i++) { kb[2 * v][i] = h1.mag[i]; kb[2 * v + 1][i] = h2.mag[i]; }
+        kneg[2 * v] = h1.neg ^ neg; kneg[2 * v + 1] = h2.neg ^ neg;
+        build_table<C>(slab + (2 * v) * TBL_ENTRIES, B);
+        typename G::Pt E;
+        band_endo(reinterpret_cast<TEPoint<BandCurve>*>(&E), reinterpret_cast<const TEPoint<BandCurve>*>(&B));
+        build_table<C>(slab + (2 * v + 1) * TBL_ENTRIES, E);
+      } else {
+        for (int i = 0; i < G::KB_LIMBS; i++) kb[v][i] = i < 8 ? k[i] : 0u;
+        kneg[v] = neg;
+        build_table<C>(slab + v * TBL_ENTRIES, B);
+      }
+    }
+    for (int t = 0; t < NT; t++) add_window_bias<G::KB_LIMBS>(kb[t], 0x88888888u, G::KB_LIMBS > 8 ? 8 : G::KB_LIMBS);
+#pragma unroll 1
+    for (int w = G::WINDOWS - 1; w >= 0; w--) {
+      if (w != G::WINDOWS - 1) G::dbl4(&acc);
+#pragma unroll
+      for (int t = 0; t < NT; t++) {
+        int d = (G::KB_LIMBS > 8 && w == 64) ? (int)kb[t][8] : digit4(kb[t], w);   // the top digit is the bias carry, unbiased
+        int idx = d < 0 ? -d : d;
+        typename G::Entry e;
+        copy_words16(&e, &slab[t * TBL_ENTRIES + idx]);
+        G::add_entry(&acc, &e, (d < 0) != kneg[t]);
+      }
+    }
+  }
+#pragma unroll
+  for (int f = 0; f < NF; f++) {
+    uint32_t k[9];
+    load_scalar_mod_r<C>(k, A.fix[f].sc + (size_t)item * A.fix[f].sc_stride);
+    k[8] = 0;
+    add_window_bias<9>(k, 0x80808080u, 8);
+    const typename G::FixEntry* tbl = reinterpret_cast<const typename G::FixEntry*>(A.fix[f].table);
+    bool neg = A.fix[f].negate != 0;
+#pragma unroll 1
+    for (int w = 0; w < G::FIX_WINDOWS; w++) {
+      int d = w == 32 ? (int)k[8] : digit8(k, w);
+      int idx = d < 0 ? -d : d;
+      typename G::FixEntry e;
+      copy_words16(&e, &tbl[w * FIX_ENTRIES + idx]);
+      G::add_fix(&acc, &e, (d < 0) != neg);
+    }
+  }
+  return ok;
+}
+
+// one fixed-base table entry: (d * 256^w) * B.  Used once per context by the table kernel.
+template <class C>
+HD_INLINE void fixed_table_entry(typename Grp<C>::FixEntry& out, const typename C::F& bx, const typename C::F& by, int w, int d) {
+  typedef Grp<C> G;
+  typename G::Pt P, R; G::from_affine(P, bx, by);
+  for (int i = 0; i < 8 * w; i++) G::dbl(&P);
+  G::set_identity(R);
+  for (int bit = 7; bit >= 0; bit--) {
+    G::dbl(&R);
+    if ((d >> bit) & 1) G::add(&R, &R, &P);
+  }
+  G::to_fix(out, R);
+}
+
+}  // namespace vrfs

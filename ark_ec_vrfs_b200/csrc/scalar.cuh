@@ -75,9 +75,10 @@ HD_NOINLINE void band_glv_split(GlvHalf* h1, GlvHalf* h2, const uint32_t* k) {
 
 // Signed fixed windows without a carry loop: with K' = K + 0x88..8 (resp. 0x80..80) the radix-16
 // (radix-256) digit of K is nibble_i(K') - 8 (byte_i(K') - 128), in [-8,7] ([-128,127]).
-template <int N> HD_INLINE void add_window_bias(uint32_t* k, uint32_t pattern) {  // returns k + pattern repeated; caller guarantees no overflow unless noted
+// k (N limbs) += pattern repeated over the low `plimbs` limbs; limbs above only receive the carry
+template <int N> HD_INLINE void add_window_bias(uint32_t* k, uint32_t pattern, int plimbs) {
   uint64_t c = 0;
-  for (int i = 0; i < N; i++) { uint64_t t = (uint64_t)k[i] + pattern + c; k[i] = (uint32_t)t; c = t >> 32; }
+  for (int i = 0; i < N; i++) { uint64_t t = (uint64_t)k[i] + (i < plimbs ? pattern : 0u) + c; k[i] = (uint32_t)t; c = t >> 32; }
 }
 HD_INLINE int digit4(const uint32_t* kb, int w) { return (int)((kb[w >> 3] >> ((w & 7) * 4)) & 15u) - 8; }
 HD_INLINE int digit8(const uint32_t* kb, int w) { return (int)((kb[w >> 2] >> ((w & 3) * 8)) & 255u) - 128; }

@@ -2,7 +2,7 @@
 // `utils::{challenge_rfc_9381, nonce_rfc_8032, point_to_hash_rfc_9381}` + `codec::ArkworksCodec`, all
 // named at /root/reference/src/lib.rs:13-17 and specified in SURVEY.md Appendix A (A.2, A.6-A.10).
 #pragma once
-#include "te_lincomb.cuh"
+#include "lincomb.cuh"
 #include "sha2.cuh"
 
 namespace vrfs {
@@ -10,37 +10,61 @@ namespace vrfs {
 struct BandSuite {
   typedef BandCurve C;
   typedef Sha512 H;
-  static constexpr int CLEN = 32, HLEN = 64, ID_LEN = 25;
+  static constexpr int CLEN = 32, HLEN = 64, ID_LEN = 25, ENC_LEN = 32;
+  static constexpr bool SEC1 = false, RFC6979 = false;
+  static constexpr int ID = 0;
   static HD_INLINE uint8_t id(int i) { constexpr char s[] = "Bandersnatch_SHA-512_ELL2"; return (uint8_t)s[i]; }
 };
 struct EdSuite {
   typedef EdCurve C;
   typedef Sha512 H;
-  static constexpr int CLEN = 16, HLEN = 64, ID_LEN = 19;
+  static constexpr int CLEN = 16, HLEN = 64, ID_LEN = 19, ENC_LEN = 32;
+  static constexpr bool SEC1 = false, RFC6979 = false;
+  static constexpr int ID = 1;
   static HD_INLINE uint8_t id(int i) { constexpr char s[] = "Ed25519_SHA-512_TAI"; return (uint8_t)s[i]; }
+};
+struct P256Suite {          // RFC 9381 ECVRF-P256-SHA256-TAI, suite string 0x01
+  typedef P256Curve C;
+  typedef Sha256 H;
+  static constexpr int CLEN = 16, HLEN = 32, ID_LEN = 1, ENC_LEN = 33;
+  static constexpr bool SEC1 = true, RFC6979 = true;
+  static constexpr int ID = 2;
+  static HD_INLINE uint8_t id(int) { return 0x01; }
 };
 
 template <class S> HD_INLINE void put_suite_id(typename S::H& h) { for (int i = 0; i < S::ID_LEN; i++) h.put(S::id(i)); }
 
-// ArkworksCodec point_encode (A.2): 32-byte LE y, bit 255 set iff x > (p-1)/2.  x, y canonical limbs.
-template <class C> HD_INLINE void ark_encode_point(uint8_t* out, const uint32_t* x, const uint32_t* y) {
-  uint32_t h[8], t[8];
-  for (int i = 0; i < 8; i++) h[i] = C::Fq::pm1h(i);
-  bool high = MontChains<8>::sub(t, h, x) != 0;
-  store_le<8>(out, y);
-  if (high) out[31] |= 0x80;
+// // codec::Codec::point_encode (A.2) from canonical limbs.
+//   ArkworksCodec (TE): 32-byte LE y, bit 255 set iff x > (p-1)/2.
+//   Sec1Codec (SW):     (0x02 | (y & 1)) || 32-byte BE x.
+template <class S> HD_INLINE void encode_point(uint8_t* out, const uint32_t* x, const uint32_t* y) {
+  if (S::SEC1) {
+    out[0] = (uint8_t)(2u | (y[0] & 1u));
+    store_be<8>(out + 1, x);
+  } else {
+    uint32_t h[8], t[8];
+    for (int i = 0; i < 8; i++) h[i] = S::C::Fq::pm1h(i);
+    bool high = MontChains<8>::sub(t, h, x) != 0;
+    store_le<8>(out, y);
+    if (high) out[31] |= 0x80;
+  }
 }
-template <class C> HD_INLINE void ark_encode_point_mont(uint8_t* out, const typename C::F& x, const typename C::F& y) {
+template <class S> HD_INLINE void encode_point_mont(uint8_t* out, const typename S::C::F& x, const typename S::C::F& y) {
   uint32_t rx[8], ry[8];
-  from_mont<typename C::Fq>(rx, x); from_mont<typename C::Fq>(ry, y);
-  ark_encode_point<C>(out, rx, ry);
+  from_mont<typename S::C::Fq>(rx, x); from_mont<typename S::C::Fq>(ry, y);
+  encode_point<S>(out, rx, ry);
 }
 // encode straight from the ABI's affine bytes (x||y LE canonical, already validated)
-template <class C> HD_INLINE void ark_encode_point_bytes(uint8_t* out, const uint8_t* p) {
+template <class S> HD_INLINE void encode_point_bytes(uint8_t* out, const uint8_t* p) {
   uint32_t rx[8], ry[8];
   load_le<8>(rx, p); load_le<8>(ry, p + 32);
-  ark_encode_point<C>(out, rx, ry);
+  encode_point<S>(out, rx, ry);
 }
+// codec scalar_encode: 32 bytes, LE (arkworks) or BE (SEC1)
+template <class S> HD_INLINE void encode_scalar(uint8_t* out, const uint32_t* k) {
+  if (S::SEC1) store_be<8>(out, k); else store_le<8>(out, k);
+}
+HD_INLINE bool bytes_all_zero(const uint8_t* p, int n) { uint32_t o = 0; for (int i = 0; i < n; i++) o |= p[i]; return o == 0; }
 
 // hash output -> scalar mod r, canonical limbs.  nbytes = 16, 32 or 64; big- or little-endian (A.6, A.7, A.10)
 template <class C> HD_INLINE void hash_to_scalar(uint32_t* k, const uint8_t* d, int nbytes, bool big_endian) {
@@ -56,10 +80,10 @@ template <class C> HD_INLINE void hash_to_scalar(uint32_t* k, const uint8_t* d, 
 }
 
 // challenge_rfc_9381 (A.7): c = BE(H(suite || 0x02 || enc(P1..P5) || ad || 0x00)[..cLen]) mod r
-template <class S> HD_INLINE void suite_challenge(uint32_t* c, const uint8_t (*enc)[32], const uint8_t* ad, uint32_t adlen) {
+template <class S> HD_INLINE void suite_challenge(uint32_t* c, const uint8_t (*enc)[S::ENC_LEN], const uint8_t* ad, uint32_t adlen) {
   typename S::H h; h.init();
   put_suite_id<S>(h); h.put(0x02);
-  for (int p = 0; p < 5; p++) h.update(enc[p], 32);
+  for (int p = 0; p < 5; p++) h.update(enc[p], S::ENC_LEN);
   h.update(ad, adlen); h.put(0x00);
   uint8_t dig[S::HLEN]; h.final(dig);
   hash_to_scalar<typename S::C>(c, dig, S::CLEN, true);
@@ -67,22 +91,53 @@ template <class S> HD_INLINE void suite_challenge(uint32_t* c, const uint8_t (*e
 // point_to_hash_rfc_9381 (A.8)
 template <class S> HD_INLINE void suite_point_to_hash(uint8_t* out, const uint8_t* enc) {
   typename S::H h; h.init();
-  put_suite_id<S>(h); h.put(0x03); h.update(enc, 32); h.put(0x00); h.final(out);
+  put_suite_id<S>(h); h.put(0x03); h.update(enc, S::ENC_LEN); h.put(0x00); h.final(out);
 }
 // nonce_rfc_8032 (A.6): k = LE(H(H(enc_sc(sk))[32..64] || enc_pt(I))) mod r
 template <class S> HD_INLINE void suite_nonce_8032(uint32_t* k, const uint32_t* sk, const uint8_t* enc_input) {
   uint8_t e[32], d[64];
-  store_le<8>(e, sk);
+  encode_scalar<S>(e, sk);
   typename S::H h; h.init(); h.update(e, 32); h.final(d);
-  h.init(); h.update(d + 32, 32); h.update(enc_input, 32); h.final(d);
+  h.init(); h.update(d + 32, 32); h.update(enc_input, S::ENC_LEN); h.final(d);
   hash_to_scalar<typename S::C>(k, d, 64, false);
+}
+// nonce_rfc_6979 (A.6; RFC 6979 3.2 with HMAC-SHA-256): x = BE32(sk), h1 = SHA-256(enc_pt(I)) reduced mod n
+template <class S> HD_INLINE void suite_nonce_6979(uint32_t* k, const uint32_t* sk, const uint8_t* enc_input) {
+  typedef typename S::C C;
+  uint8_t h1[32], xb[32], hb[32], V[32], K[32];
+  Sha256 h; h.init(); h.update(enc_input, S::ENC_LEN); h.final(h1);
+  uint32_t hr[8];
+  hash_to_scalar<C>(hr, h1, 32, true);           // bits2octets
+  store_be<8>(hb, hr); store_be<8>(xb, sk);
+  for (int i = 0; i < 32; i++) { V[i] = 0x01; K[i] = 0x00; }
+  HmacSha256 m;
+  for (int sep = 0; sep < 2; sep++) {
+    uint8_t sb = (uint8_t)sep;
+    m.init(K, 32); m.update(V, 32); m.update(&sb, 1); m.update(xb, 32); m.update(hb, 32); m.final(K);
+    m.init(K, 32); m.update(V, 32); m.final(V);
+  }
+  for (;;) {
+    m.init(K, 32); m.update(V, 32); m.final(V);
+    uint32_t cand[8], nmod[8], t[8];
+    load_be<8>(cand, V);
+    for (int i = 0; i < 8; i++) nmod[i] = C::Fr::mod(i);
+    uint32_t nz = 0;
+    for (int i = 0; i < 8; i++) nz |= cand[i];
+    if (nz != 0 && MontChains<8>::sub(t, cand, nmod) != 0) { for (int i = 0; i < 8; i++) k[i] = cand[i]; return; }
+    uint8_t zero = 0;
+    m.init(K, 32); m.update(V, 32); m.update(&zero, 1); m.final(K);
+    m.init(K, 32); m.update(V, 32); m.final(V);
+  }
+}
+template <class S> HD_INLINE void suite_nonce(uint32_t* k, const uint32_t* sk, const uint8_t* enc_input) {
+  if constexpr (S::RFC6979) suite_nonce_6979<S>(k, sk, enc_input); else suite_nonce_8032<S>(k, sk, enc_input);
 }
 // Pedersen blinding (A.10): b = BE(H(suite || 0xCC || enc_sc(sk) || enc_pt(I) || ad || 0x00)) mod r
 template <class S> HD_INLINE void suite_blinding(uint32_t* b, const uint32_t* sk, const uint8_t* enc_input, const uint8_t* ad, uint32_t adlen) {
   uint8_t e[32], d[64];
-  store_le<8>(e, sk);
+  encode_scalar<S>(e, sk);
   typename S::H h; h.init();
-  put_suite_id<S>(h); h.put(0xCC); h.update(e, 32); h.update(enc_input, 32); h.update(ad, adlen); h.put(0x00); h.final(d);
+  put_suite_id<S>(h); h.put(0xCC); h.update(e, 32); h.update(enc_input, S::ENC_LEN); h.update(ad, adlen); h.put(0x00); h.final(d);
   hash_to_scalar<typename S::C>(b, d, S::HLEN, true);
 }
 // s = k + c*x mod r (canonical limbs in and out)
@@ -93,7 +148,7 @@ template <class C> HD_INLINE void scalar_muladd(uint32_t* s, const uint32_t* k, 
 }
 
 // two projective points (X,Y,Z Montgomery limbs) -> affine with one shared inversion
-template <class C> HD_INLINE void te_two_to_affine(typename C::F* ax, typename C::F* ay, const uint32_t* p0, const uint32_t* p1) {
+template <class C> HD_INLINE void two_to_affine(typename C::F* ax, typename C::F* ay, const uint32_t* p0, const uint32_t* p1) {
   typedef typename C::F F;
   F X0, Y0, Z0, X1, Y1, Z1;
   for (int i = 0; i < 8; i++) { X0.v[i] = p0[i]; Y0.v[i] = p0[8 + i]; Z0.v[i] = p0[16 + i]; X1.v[i] = p1[i]; Y1.v[i] = p1[8 + i]; Z1.v[i] = p1[16 + i]; }
@@ -108,13 +163,18 @@ HD_INLINE bool ietf_verify_finish_item(const uint8_t* pk, const uint8_t* input, 
                                        const uint32_t* u_xyz, const uint32_t* v_xyz, const uint8_t* ad, uint32_t adlen) {
   typedef typename S::C C;
   typename C::F ax[2], ay[2];
-  te_two_to_affine<C>(ax, ay, u_xyz, v_xyz);
-  uint8_t enc[5][32];
-  ark_encode_point_bytes<C>(enc[0], pk);
-  ark_encode_point_bytes<C>(enc[1], input);
-  ark_encode_point_bytes<C>(enc[2], output);
-  ark_encode_point_mont<C>(enc[3], ax[0], ay[0]);
-  ark_encode_point_mont<C>(enc[4], ax[1], ay[1]);
+  if (!C::IS_TE) {   // the identity has no SEC1-compressed encoding: Error::InvalidData / VerificationFailure
+    uint32_t zu = 0, zv = 0;
+    for (int i = 0; i < 8; i++) { zu |= u_xyz[16 + i]; zv |= v_xyz[16 + i]; }
+    if (zu == 0 || zv == 0 || bytes_all_zero(pk, 64) || bytes_all_zero(input, 64) || bytes_all_zero(output, 64)) return false;
+  }
+  two_to_affine<C>(ax, ay, u_xyz, v_xyz);
+  uint8_t enc[5][S::ENC_LEN];
+  encode_point_bytes<S>(enc[0], pk);
+  encode_point_bytes<S>(enc[1], input);
+  encode_point_bytes<S>(enc[2], output);
+  encode_point_mont<S>(enc[3], ax[0], ay[0]);
+  encode_point_mont<S>(enc[4], ax[1], ay[1]);
   uint32_t c2[8], c[8];
   suite_challenge<S>(c2, enc, ad, adlen);
   hash_to_scalar<C>(c, c_bytes, 32, false);
@@ -124,7 +184,7 @@ HD_INLINE bool ietf_verify_finish_item(const uint8_t* pk, const uint8_t* input, 
 }
 
 // K projective points (X,Y,Z Montgomery limbs, 24 words each) -> affine Montgomery, ONE shared inversion
-template <class C, int K> HD_INLINE void te_to_affine_shared(typename C::F* ax, typename C::F* ay, const uint32_t* const* p) {
+template <class C, int K> HD_INLINE void to_affine_shared(typename C::F* ax, typename C::F* ay, const uint32_t* const* p) {
   typedef typename C::F F;
   F X[K], Y[K], Z[K], pre[K];
   for (int k = 0; k < K; k++) for (int i = 0; i < 8; i++) { X[k].v[i] = p[k][i]; Y[k].v[i] = p[k][8 + i]; Z[k].v[i] = p[k][16 + i]; }
@@ -156,13 +216,13 @@ HD_INLINE void ietf_prove_finish_item(uint8_t* out_c, uint8_t* out_s, const uint
   typedef typename S::C C;
   typename C::F ax[3], ay[3];
   const uint32_t* pp[3] = {y_xyz, kg_xyz, ki_xyz};
-  te_to_affine_shared<C, 3>(ax, ay, pp);
-  uint8_t enc[5][32];
-  ark_encode_point_mont<C>(enc[0], ax[0], ay[0]);
-  ark_encode_point_bytes<C>(enc[1], input);
-  ark_encode_point_bytes<C>(enc[2], output);
-  ark_encode_point_mont<C>(enc[3], ax[1], ay[1]);
-  ark_encode_point_mont<C>(enc[4], ax[2], ay[2]);
+  to_affine_shared<C, 3>(ax, ay, pp);
+  uint8_t enc[5][S::ENC_LEN];
+  encode_point_mont<S>(enc[0], ax[0], ay[0]);
+  encode_point_bytes<S>(enc[1], input);
+  encode_point_bytes<S>(enc[2], output);
+  encode_point_mont<S>(enc[3], ax[1], ay[1]);
+  encode_point_mont<S>(enc[4], ax[2], ay[2]);
   uint32_t c[8], sk[8], k[8], sres[8];
   suite_challenge<S>(c, enc, ad, adlen);
   load_scalar_bytes_mod_r<C>(sk, sk_bytes);
@@ -171,14 +231,14 @@ HD_INLINE void ietf_prove_finish_item(uint8_t* out_c, uint8_t* out_s, const uint
   store_le<8>(out_c, c); store_le<8>(out_s, sres);
 }
 
-// Suite::nonce for the rfc8032-style suites, from ABI bytes
-template <class S> HD_INLINE void te_nonce_item(uint8_t* out_k, const uint8_t* sk_bytes, const uint8_t* input) {
+// Suite::nonce from ABI bytes
+template <class S> HD_INLINE void nonce_item(uint8_t* out_k, const uint8_t* sk_bytes, const uint8_t* input) {
   typedef typename S::C C;
   uint32_t sk[8], k[8];
-  uint8_t enc[32];
+  uint8_t enc[S::ENC_LEN];
   load_scalar_bytes_mod_r<C>(sk, sk_bytes);
-  ark_encode_point_bytes<C>(enc, input);
-  suite_nonce_8032<S>(k, sk, enc);
+  encode_point_bytes<S>(enc, input);
+  suite_nonce<S>(k, sk, enc);
   store_le<8>(out_k, k);
 }
 
@@ -187,12 +247,12 @@ template <class S> HD_INLINE void pedersen_prove_prep_item(uint8_t* out_b, uint8
                                                            const uint8_t* input, const uint8_t* ad, uint32_t adlen) {
   typedef typename S::C C;
   uint32_t sk[8], b[8], k[8], kb[8];
-  uint8_t enc[32];
+  uint8_t enc[S::ENC_LEN];
   load_scalar_bytes_mod_r<C>(sk, sk_bytes);
-  ark_encode_point_bytes<C>(enc, input);
+  encode_point_bytes<S>(enc, input);
   suite_blinding<S>(b, sk, enc, ad, adlen);
-  suite_nonce_8032<S>(k, sk, enc);
-  suite_nonce_8032<S>(kb, b, enc);
+  suite_nonce<S>(k, sk, enc);
+  suite_nonce<S>(kb, b, enc);
   store_le<8>(out_b, b); store_le<8>(out_k, k); store_le<8>(out_kb, kb);
 }
 // second part: Yb, R, Ok (projective) -> proof bytes (3 x 64 affine || s || sb)
@@ -203,13 +263,13 @@ template <class S> HD_INLINE void pedersen_prove_finish_item(uint8_t* proof, con
   typedef typename S::C C;
   typename C::F ax[3], ay[3];
   const uint32_t* pp[3] = {yb_xyz, r_xyz, ok_xyz};
-  te_to_affine_shared<C, 3>(ax, ay, pp);
-  uint8_t enc[5][32];
-  ark_encode_point_mont<C>(enc[0], ax[0], ay[0]);
-  ark_encode_point_bytes<C>(enc[1], input);
-  ark_encode_point_bytes<C>(enc[2], output);
-  ark_encode_point_mont<C>(enc[3], ax[1], ay[1]);
-  ark_encode_point_mont<C>(enc[4], ax[2], ay[2]);
+  to_affine_shared<C, 3>(ax, ay, pp);
+  uint8_t enc[5][S::ENC_LEN];
+  encode_point_mont<S>(enc[0], ax[0], ay[0]);
+  encode_point_bytes<S>(enc[1], input);
+  encode_point_bytes<S>(enc[2], output);
+  encode_point_mont<S>(enc[3], ax[1], ay[1]);
+  encode_point_mont<S>(enc[4], ax[2], ay[2]);
   for (int j = 0; j < 3; j++) store_affine_bytes<C>(proof + 64 * j, ax[j], ay[j]);
   uint32_t c[8], sk[8], b[8], k[8], kb[8], r[8];
   suite_challenge<S>(c, enc, ad, adlen);
@@ -219,27 +279,31 @@ template <class S> HD_INLINE void pedersen_prove_finish_item(uint8_t* proof, con
   scalar_muladd<C>(r, kb, c, b); store_le<8>(proof + 224, r);
 }
 // pedersen::Verifier::verify, first part: c = challenge(Yb, I, O, R, Ok, ad) from the proof bytes
-template <class S> HD_INLINE void pedersen_verify_prep_item(uint8_t* out_c, const uint8_t* input, const uint8_t* output, const uint8_t* proof,
+// returns false when a point is the short-Weierstrass identity (not encodable -> the reference rejects)
+template <class S> HD_INLINE bool pedersen_verify_prep_item(uint8_t* out_c, const uint8_t* input, const uint8_t* output, const uint8_t* proof,
                                                             const uint8_t* ad, uint32_t adlen) {
   typedef typename S::C C;
-  uint8_t enc[5][32];
-  ark_encode_point_bytes<C>(enc[0], proof);
-  ark_encode_point_bytes<C>(enc[1], input);
-  ark_encode_point_bytes<C>(enc[2], output);
-  ark_encode_point_bytes<C>(enc[3], proof + 64);
-  ark_encode_point_bytes<C>(enc[4], proof + 128);
+  bool ok = true;
+  if (!C::IS_TE) ok = !(bytes_all_zero(input, 64) || bytes_all_zero(output, 64) || bytes_all_zero(proof, 64) || bytes_all_zero(proof + 64, 64) || bytes_all_zero(proof + 128, 64));
+  uint8_t enc[5][S::ENC_LEN];
+  encode_point_bytes<S>(enc[0], proof);
+  encode_point_bytes<S>(enc[1], input);
+  encode_point_bytes<S>(enc[2], output);
+  encode_point_bytes<S>(enc[3], proof + 64);
+  encode_point_bytes<S>(enc[4], proof + 128);
   uint32_t c[8];
   suite_challenge<S>(c, enc, ad, adlen);
   store_le<8>(out_c, c);
+  return ok;
 }
 // is the projective point (X,Y,Z) equal to the affine point given as ABI bytes?  (also validates the affine point)
-template <class C> HD_INLINE bool te_proj_equals_affine_bytes(const uint32_t* xyz, const uint8_t* aff) {
+template <class C> HD_INLINE bool proj_equals_affine_bytes(const uint32_t* xyz, const uint8_t* aff) {
   typedef typename C::F F;
   uint32_t rx[8], ry[8];
   load_le<8>(rx, aff); load_le<8>(ry, aff + 32);
   bool ok = is_canonical<typename C::Fq>(rx) & is_canonical<typename C::Fq>(ry);
   F x = to_mont<typename C::Fq>(rx), y = to_mont<typename C::Fq>(ry), X, Y, Z;
-  ok &= te_on_curve<C>(x, y);
+  ok &= Grp<C>::on_curve(x, y);
   for (int i = 0; i < 8; i++) { X.v[i] = xyz[i]; Y.v[i] = xyz[8 + i]; Z.v[i] = xyz[16 + i]; }
   return ok & !Z.is_zero() & (x * Z == X) & (y * Z == Y);
 }

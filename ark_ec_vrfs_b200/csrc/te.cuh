@@ -17,6 +17,7 @@ struct BandCurve {
   typedef BandConsts K;
   typedef Fp<Fq> F;
   static constexpr int COF_LOG2 = 2;
+  static constexpr bool IS_TE = true;
   static constexpr bool HAS_GLV = true;
   static HD_INLINE F mul_a(const F& x) { F t = dbl(dbl(x)); return neg(t + x); }   // a = -5
   static HD_INLINE F d() { return fconst<Fq, K::D>(); }
@@ -31,6 +32,7 @@ struct EdCurve {
   typedef EdConsts K;
   typedef Fp<Fq> F;
   static constexpr int COF_LOG2 = 3;
+  static constexpr bool IS_TE = true;
   static constexpr bool HAS_GLV = false;
   static HD_INLINE F mul_a(const F& x) { return neg(x); }                           // a = -1
   static HD_INLINE F d() { return fconst<Fq, K::D>(); }

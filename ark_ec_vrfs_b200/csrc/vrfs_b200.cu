@@ -18,24 +18,24 @@ using namespace vrfs;
 
 // one fixed-base table (K8): thread (w, d) computes (d * 256^w) * B in affine cached form
 template <class C>
-__global__ void k_te_fixed_table(TEAffCached<C>* out, int blinding) {
+__global__ void k_fixed_table(typename Grp<C>::FixEntry* out, int blinding) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= TeTraits<C>::FIX_WINDOWS * TeTraits<C>::FIX_ENTRIES) return;
-  int w = t / TeTraits<C>::FIX_ENTRIES, d = t % TeTraits<C>::FIX_ENTRIES;
-  TEAffCached<C> e;
-  te_fixed_table_entry<C>(e, blinding ? C::bx() : C::gx(), blinding ? C::by() : C::gy(), w, d);
+  if (t >= (int)fix_table_entries<C>()) return;
+  int w = t / FIX_ENTRIES, d = t % FIX_ENTRIES;
+  typename Grp<C>::FixEntry e;
+  fixed_table_entry<C>(e, blinding ? C::bx() : C::gx(), blinding ? C::by() : C::gy(), w, d);
   out[t] = e;
 }
 
 // K7/K8/K9a: R_i = sum var + sum fixed, projective out.  Persistent grid-stride so that the window-table
 // slab is per resident thread (L2-resident), not per item.
 template <class C, int NV, int NF>
-__global__ void __launch_bounds__(LINCOMB_THREADS, 4) k_te_lincomb(LincombArgs A) {
+__global__ void __launch_bounds__(LINCOMB_THREADS, 4) k_lincomb(LincombArgs A) {
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
-  TECached<C>* slab = reinterpret_cast<TECached<C>*>(A.slab + (size_t)tid * te_slab_bytes<C>(NV));
+  typename Grp<C>::Entry* slab = reinterpret_cast<typename Grp<C>::Entry*>(A.slab + (size_t)tid * slab_bytes<C>(NV));
   for (uint32_t item = tid; item < A.n; item += nthreads) {
-    TEPoint<C> acc;
-    bool ok = te_lincomb_item<C, NV, NF>(A, item, slab, acc);
+    typename Grp<C>::Pt acc;
+    bool ok = lincomb_item<C, NV, NF>(A, item, slab, acc);
     uint4* o = reinterpret_cast<uint4*>(A.out_xyz + (size_t)item * 24);
     const uint4* sx = reinterpret_cast<const uint4*>(acc.X.v);
     const uint4* sy = reinterpret_cast<const uint4*>(acc.Y.v);
@@ -242,10 +242,10 @@ static inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0
 
 template <class C>
 static vrfs_status build_fixed_tables(vrfs_ctx* ctx, int suite) {
-  const int n = TeTraits<C>::FIX_WINDOWS * TeTraits<C>::FIX_ENTRIES;
+  const int n = (int)fix_table_entries<C>();
   for (int b = 0; b < 2; b++) {
-    CU(cudaMalloc(&ctx->fixtab[suite][b], sizeof(TEAffCached<C>) * n));
-    k_te_fixed_table<C><<<(n + 63) / 64, 64, 0, ctx->stream>>>(reinterpret_cast<TEAffCached<C>*>(ctx->fixtab[suite][b]), b);
+    CU(cudaMalloc(&ctx->fixtab[suite][b], sizeof(typename Grp<C>::FixEntry) * n));
+    k_fixed_table<C><<<(n + 63) / 64, 64, 0, ctx->stream>>>(reinterpret_cast<typename Grp<C>::FixEntry*>(ctx->fixtab[suite][b]), b);
     LAUNCHED(ctx);
   }
   return VRFS_OK;
@@ -270,6 +270,7 @@ extern "C" vrfs_status vrfs_ctx_create(int device, vrfs_ctx** out) {
   CU(cudaEventCreate(&ctx->ev1));
   ST(build_fixed_tables<BandCurve>(ctx, VRFS_BANDERSNATCH_ELL2));
   ST(build_fixed_tables<EdCurve>(ctx, VRFS_ED25519_TAI));
+  ST(build_fixed_tables<P256Curve>(ctx, VRFS_P256_TAI));
   CU(cudaStreamSynchronize(ctx->stream));
   return VRFS_OK;
 }
@@ -303,16 +304,16 @@ template <class C, int NV, int NF>
 static vrfs_status launch_lincomb(vrfs_ctx* ctx, LincombArgs A) {
   if (A.n == 0) return VRFS_OK;
   int per_sm = 0;
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_te_lincomb<C, NV, NF>, LINCOMB_THREADS, 0));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lincomb<C, NV, NF>, LINCOMB_THREADS, 0));
   if (per_sm < 1) per_sm = 1;
   uint32_t blocks = (uint32_t)(ctx->sms * per_sm);
   uint32_t need = (A.n + LINCOMB_THREADS - 1) / LINCOMB_THREADS;
   if (blocks > need) blocks = need;
   void* slab = nullptr;
-  ST(ensure(ctx, BUF_SLAB, (size_t)blocks * LINCOMB_THREADS * te_slab_bytes<C>(NV), &slab));
+  ST(ensure(ctx, BUF_SLAB, (size_t)blocks * LINCOMB_THREADS * slab_bytes<C>(NV), &slab));
   A.slab = (uint8_t*)slab;
-  k_te_lincomb<C, NV, NF><<<blocks, LINCOMB_THREADS, 0, ctx->stream>>>(A);
-  LAUNCHED_AS(ctx, NV == 2 ? "te_lincomb<2,0>" : NV == 1 && NF == 1 ? "te_lincomb<1,1>" : NV == 1 ? "te_lincomb<1,0>" : NF == 2 ? "te_lincomb<0,2>" : NV == 1 && NF == 2 ? "te_lincomb<1,2>" : "te_lincomb<0,1>");
+  k_lincomb<C, NV, NF><<<blocks, LINCOMB_THREADS, 0, ctx->stream>>>(A);
+  LAUNCHED_AS(ctx, NV == 2 ? "lincomb<2,0>" : NV == 1 && NF == 1 ? "lincomb<1,1>" : NV == 1 ? "lincomb<1,0>" : NF == 2 ? "lincomb<0,2>" : NV == 1 && NF == 2 ? "lincomb<1,2>" : "lincomb<0,1>");
   return VRFS_OK;
 }
 
@@ -334,7 +335,7 @@ static vrfs_status ietf_verify_dev(vrfs_ctx* ctx, size_t n, const uint8_t* pk, c
   A.valid = (uint8_t*)valid;
   // U = s*G - c*Y
   A.var[0] = {pk, 64, c, 32, 1};
-  A.fix[0] = {s, 32, 0, ctx->fixtab[S::C::HAS_GLV ? VRFS_BANDERSNATCH_ELL2 : VRFS_ED25519_TAI][0]};
+  A.fix[0] = {s, 32, 0, ctx->fixtab[S::ID][0]};
   A.out_xyz = (uint32_t*)u;
   ST((launch_lincomb<C, 1, 1>(ctx, A)));
   // V = s*I - c*O
@@ -360,7 +361,8 @@ extern "C" vrfs_status vrfs_ietf_verify_batch_dev(vrfs_ctx* ctx, vrfs_suite suit
   switch (suite) {
     case VRFS_BANDERSNATCH_ELL2: return ietf_verify_dev<BandSuite>(ctx, n, pk, input, output, c, s, ad, ad_off, out_ok);
     case VRFS_ED25519_TAI: return ietf_verify_dev<EdSuite>(ctx, n, pk, input, output, c, s, ad, ad_off, out_ok);
-    default: return fail(ctx, VRFS_UNSUPPORTED, "suite %d not implemented for ietf verify", (int)suite);
+    case VRFS_P256_TAI: return ietf_verify_dev<P256Suite>(ctx, n, pk, input, output, c, s, ad, ad_off, out_ok);
+    default: return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
   }
 }
 
@@ -453,9 +455,9 @@ extern "C" vrfs_status vrfs_measure_mac32_peak(vrfs_ctx* ctx, int variant, doubl
 #define VAR_SLICE(buf, off, i, ptr, len) const uint8_t* ptr = (buf) ? (buf) + (off)[i] : nullptr; uint32_t len = (buf) ? (uint32_t)((off)[(i) + 1] - (off)[i]) : 0u
 static inline unsigned item_blocks(size_t n) { return (unsigned)((n + ITEM_THREADS - 1) / ITEM_THREADS); }
 
-template <class S> __global__ void __launch_bounds__(ITEM_THREADS) k_te_nonce(uint32_t n, const uint8_t* sk, const uint8_t* input, uint8_t* out_k) {
+template <class S> __global__ void __launch_bounds__(ITEM_THREADS) k_nonce(uint32_t n, const uint8_t* sk, const uint8_t* input, uint8_t* out_k) {
   ITEM_INDEX(n);
-  te_nonce_item<S>(out_k + (size_t)32 * i, sk + (size_t)32 * i, input + (size_t)64 * i);
+  nonce_item<S>(out_k + (size_t)32 * i, sk + (size_t)32 * i, input + (size_t)64 * i);
 }
 template <class S> __global__ void __launch_bounds__(ITEM_THREADS) k_ietf_prove_finish(uint32_t n, const uint8_t* sk, const uint8_t* k, const uint8_t* input, const uint8_t* output,
                                                                                         const uint32_t* y, const uint32_t* kg, const uint32_t* ki, const uint8_t* ad, const uint64_t* ad_off,
@@ -468,17 +470,17 @@ template <class S> __global__ void __launch_bounds__(ITEM_THREADS) k_ietf_prove_
                             y + (size_t)24 * i, kg + (size_t)24 * i, ki + (size_t)24 * i, a, alen);
 }
 // projective -> affine ABI bytes, one point per item (Secret::output, Public)
-template <class C> __global__ void __launch_bounds__(ITEM_THREADS) k_te_to_affine(uint32_t n, const uint32_t* xyz, const uint8_t* valid, uint8_t* out) {
+template <class C> __global__ void __launch_bounds__(ITEM_THREADS) k_to_affine(uint32_t n, const uint32_t* xyz, const uint8_t* valid, uint8_t* out) {
   ITEM_INDEX(n);
   uint8_t* o = out + (size_t)64 * i;
   if (valid && !valid[i]) { for (int j = 0; j < 64; j++) o[j] = 0; return; }
   typename C::F ax[1], ay[1];
   const uint32_t* pp[1] = {xyz + (size_t)24 * i};
-  te_to_affine_shared<C, 1>(ax, ay, pp);
+  to_affine_shared<C, 1>(ax, ay, pp);
   store_affine_bytes<C>(o, ax[0], ay[0]);
 }
 // Secret::from_seed: sk = LE(H(seed)) mod r
-template <class S> __global__ void __launch_bounds__(ITEM_THREADS) k_te_secret_from_seed(uint32_t n, const uint8_t* seeds, const uint64_t* off, uint8_t* out_sk) {
+template <class S> __global__ void __launch_bounds__(ITEM_THREADS) k_secret_from_seed(uint32_t n, const uint8_t* seeds, const uint64_t* off, uint8_t* out_sk) {
   ITEM_INDEX(n);
   VAR_SLICE(seeds, off, i, p, len);
   typename S::H h; h.init(); h.update(p, len);
@@ -487,39 +489,43 @@ template <class S> __global__ void __launch_bounds__(ITEM_THREADS) k_te_secret_f
   hash_to_scalar<typename S::C>(k, d, S::HLEN, false);
   store_le<8>(out_sk + (size_t)32 * i, k);
 }
-template <class S> __global__ void __launch_bounds__(ITEM_THREADS) k_te_point_to_hash(uint32_t n, const uint8_t* pts, uint8_t* out) {
+template <class S> __global__ void __launch_bounds__(ITEM_THREADS) k_point_to_hash(uint32_t n, const uint8_t* pts, uint8_t* out) {
   ITEM_INDEX(n);
   typedef typename S::C C;
   typename C::F x, y;
+  bool inf = false;
   uint8_t* o = out + (size_t)S::HLEN * i;
-  if (!te_load_affine<C>(x, y, pts + (size_t)64 * i)) { for (int j = 0; j < S::HLEN; j++) o[j] = 0; return; }
-  uint8_t enc[32];
-  ark_encode_point_bytes<C>(enc, pts + (size_t)64 * i);
+  if (!load_affine<C>(x, y, &inf, pts + (size_t)64 * i) || inf) { for (int j = 0; j < S::HLEN; j++) o[j] = 0; return; }
+  uint8_t enc[S::ENC_LEN];
+  encode_point_bytes<S>(enc, pts + (size_t)64 * i);
   suite_point_to_hash<S>(o, enc);
 }
-template <class C> __global__ void __launch_bounds__(ITEM_THREADS) k_te_point_encode(uint32_t n, const uint8_t* pts, uint8_t* out) {
+template <class S> __global__ void __launch_bounds__(ITEM_THREADS) k_point_encode(uint32_t n, const uint8_t* pts, uint8_t* out) {
   ITEM_INDEX(n);
+  typedef typename S::C C;
   typename C::F x, y;
-  uint8_t* o = out + (size_t)32 * i;
-  if (!te_load_affine<C>(x, y, pts + (size_t)64 * i)) { for (int j = 0; j < 32; j++) o[j] = 0; return; }
-  ark_encode_point_bytes<C>(o, pts + (size_t)64 * i);
+  bool inf = false;
+  uint8_t* o = out + (size_t)S::ENC_LEN * i;
+  if (!load_affine<C>(x, y, &inf, pts + (size_t)64 * i) || inf) { for (int j = 0; j < S::ENC_LEN; j++) o[j] = 0; return; }
+  encode_point_bytes<S>(o, pts + (size_t)64 * i);
 }
-template <class C> __global__ void __launch_bounds__(ITEM_THREADS) k_te_point_decode(uint32_t n, const uint8_t* enc, uint8_t* out, uint8_t* out_ok) {
+template <class S> __global__ void __launch_bounds__(ITEM_THREADS) k_point_decode(uint32_t n, const uint8_t* enc, uint8_t* out, uint8_t* out_ok) {
   ITEM_INDEX(n);
+  typedef typename S::C C;
   typename C::F x, y;
   uint8_t* o = out + (size_t)64 * i;
-  bool ok = ark_decode_point<C>(x, y, enc + (size_t)32 * i);
+  bool ok = decode_point<S>(x, y, enc + (size_t)S::ENC_LEN * i);
   out_ok[i] = ok;
   if (ok) store_affine_bytes<C>(o, x, y); else for (int j = 0; j < 64; j++) o[j] = 0;
 }
 // Suite::data_to_point (K6)
-template <class S> __global__ void __launch_bounds__(ITEM_THREADS) k_te_data_to_point(uint32_t n, const uint8_t* data, const uint64_t* off, uint8_t* out, uint8_t* out_ok) {
+template <class S> __global__ void __launch_bounds__(ITEM_THREADS) k_data_to_point(uint32_t n, const uint8_t* data, const uint64_t* off, uint8_t* out, uint8_t* out_ok) {
   ITEM_INDEX(n);
   typedef typename S::C C;
   VAR_SLICE(data, off, i, p, len);
-  TEPoint<C> P;
+  typename Grp<C>::Pt P;
   bool ok;
-  if constexpr (C::HAS_GLV) { band_h2c_ell2(P, p, len); ok = true; } else { ok = te_h2c_tai<S>(P, p, len); }
+  if constexpr (C::HAS_GLV) { band_h2c_ell2(P, p, len); ok = true; } else { ok = h2c_tai<S>(P, p, len); }
   uint8_t* o = out + (size_t)64 * i;
   out_ok[i] = ok;
   if (!ok) { for (int j = 0; j < 64; j++) o[j] = 0; return; }
@@ -544,17 +550,17 @@ template <class S> __global__ void __launch_bounds__(ITEM_THREADS) k_pedersen_pr
   for (int j = 0; j < 32; j++) bl[j] = b[(size_t)32 * i + j];
 }
 template <class S> __global__ void __launch_bounds__(ITEM_THREADS) k_pedersen_verify_prep(uint32_t n, const uint8_t* input, const uint8_t* output, const uint8_t* proof,
-                                                                                           const uint8_t* ad, const uint64_t* ad_off, uint8_t* c) {
+                                                                                           const uint8_t* ad, const uint64_t* ad_off, uint8_t* c, uint8_t* valid) {
   ITEM_INDEX(n);
   VAR_SLICE(ad, ad_off, i, a, alen);
-  pedersen_verify_prep_item<S>(c + (size_t)32 * i, input + (size_t)64 * i, output + (size_t)64 * i, proof + (size_t)256 * i, a, alen);
+  if (!pedersen_verify_prep_item<S>(c + (size_t)32 * i, input + (size_t)64 * i, output + (size_t)64 * i, proof + (size_t)256 * i, a, alen)) valid[i] = 0;
 }
 // Ok + c*O == s*I  and  R + c*Yb == s*G + sb*B, given T1 = s*I - c*O and T2 = s*G + sb*B - c*Yb (projective)
 template <class C> __global__ void __launch_bounds__(ITEM_THREADS) k_pedersen_verify_finish(uint32_t n, const uint8_t* proof, const uint32_t* t1, const uint32_t* t2,
                                                                                              const uint8_t* valid, uint8_t* out_ok) {
   ITEM_INDEX(n);
   const uint8_t* pr = proof + (size_t)256 * i;
-  bool ok = te_proj_equals_affine_bytes<C>(t1 + (size_t)24 * i, pr + 128) & te_proj_equals_affine_bytes<C>(t2 + (size_t)24 * i, pr + 64);
+  bool ok = proj_equals_affine_bytes<C>(t1 + (size_t)24 * i, pr + 128) & proj_equals_affine_bytes<C>(t2 + (size_t)24 * i, pr + 64);
   out_ok[i] = (uint8_t)(ok && valid[i]);
 }
 
@@ -593,7 +599,7 @@ static vrfs_status fresh_valid(vrfs_ctx* ctx, size_t n, uint8_t** valid) {
   *valid = (uint8_t*)v;
   return VRFS_OK;
 }
-template <class S> static const void* fixtab(vrfs_ctx* ctx, int which) { return ctx->fixtab[S::C::HAS_GLV ? VRFS_BANDERSNATCH_ELL2 : VRFS_ED25519_TAI][which]; }
+template <class S> static const void* fixtab(vrfs_ctx* ctx, int which) { return ctx->fixtab[S::ID][which]; }
 #define SUITE_DISPATCH(suite, FN, ...)                                                         \
   switch (suite) {                                                                             \
     case VRFS_BANDERSNATCH_ELL2: return FN<BandSuite>(__VA_ARGS__);                            \
@@ -610,8 +616,8 @@ static vrfs_status ietf_prove_dev(vrfs_ctx* ctx, size_t n, const uint8_t* sk, co
   uint8_t* valid = nullptr;
   ST(ensure(ctx, BUF_W0, n * 32, &k)); ST(ensure(ctx, BUF_W1, n * 96, &y)); ST(ensure(ctx, BUF_W2, n * 96, &kg)); ST(ensure(ctx, BUF_W3, n * 96, &ki));
   ST(fresh_valid(ctx, n, &valid));
-  k_te_nonce<S><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, sk, input, (uint8_t*)k);
-  LAUNCHED_AS(ctx, "te_nonce");
+  k_nonce<S><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, sk, input, (uint8_t*)k);
+  LAUNCHED_AS(ctx, "nonce");
   LincombArgs A = {};
   A.n = (uint32_t)n; A.valid = valid;
   A.fix[0] = {sk, 32, 0, fixtab<S>(ctx, 0)}; A.out_xyz = (uint32_t*)y;
@@ -630,14 +636,14 @@ extern "C" vrfs_status vrfs_ietf_prove_batch(vrfs_ctx* ctx, vrfs_suite suite, si
   if (!ctx) return VRFS_BAD_ARG;
   if (n == 0) return VRFS_OK;
   if (!sk || !input || !output || !out_c || !out_s) return fail(ctx, VRFS_BAD_ARG, "null buffer");
-  if (suite != VRFS_BANDERSNATCH_ELL2 && suite != VRFS_ED25519_TAI) return fail(ctx, VRFS_UNSUPPORTED, "suite %d is not implemented for ietf prove", (int)suite);
+  if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
   ST(begin_call(ctx, n));
   const uint8_t *d_sk, *d_in, *d_out, *d_ad; const uint64_t* d_off; uint8_t *d_c, *d_s;
   ST(stage_in(ctx, BUF_IN0, sk, n * 32, &d_sk)); ST(stage_in(ctx, BUF_IN1, input, n * 64, &d_in)); ST(stage_in(ctx, BUF_IN2, output, n * 64, &d_out));
   ST(stage_ad(ctx, n, ad, ad_off, &d_ad, &d_off));
   ST(stage_out(ctx, BUF_OUT0, n * 32, &d_c)); ST(stage_out(ctx, BUF_OUT1, n * 32, &d_s));
   vrfs_status st = suite == VRFS_BANDERSNATCH_ELL2 ? ietf_prove_dev<BandSuite>(ctx, n, d_sk, d_in, d_out, d_ad, d_off, d_c, d_s)
-                                                   : ietf_prove_dev<EdSuite>(ctx, n, d_sk, d_in, d_out, d_ad, d_off, d_c, d_s);
+     : suite == VRFS_ED25519_TAI ? ietf_prove_dev<EdSuite>(ctx, n, d_sk, d_in, d_out, d_ad, d_off, d_c, d_s) : ietf_prove_dev<P256Suite>(ctx, n, d_sk, d_in, d_out, d_ad, d_off, d_c, d_s);
   ST(st);
   ST(copy_out(ctx, out_c, d_c, n * 32)); ST(copy_out(ctx, out_s, d_s, n * 32));
   return finish_call(ctx);
@@ -651,34 +657,35 @@ template <class S> static vrfs_status output_dev(vrfs_ctx* ctx, size_t n, const 
   LincombArgs A = {};
   A.n = (uint32_t)n; A.valid = valid; A.var[0] = {input, 64, sk, 32, 0}; A.out_xyz = (uint32_t*)o;
   ST((launch_lincomb<C, 1, 0>(ctx, A)));
-  k_te_to_affine<C><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, (const uint32_t*)o, valid, out);
-  LAUNCHED_AS(ctx, "te_to_affine");
+  k_to_affine<C><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, (const uint32_t*)o, valid, out);
+  LAUNCHED_AS(ctx, "to_affine");
   return VRFS_OK;
 }
 extern "C" vrfs_status vrfs_output_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* sk, const uint8_t* input, uint8_t* out_output) {
   if (!ctx) return VRFS_BAD_ARG;
   if (n == 0) return VRFS_OK;
   if (!sk || !input || !out_output) return fail(ctx, VRFS_BAD_ARG, "null buffer");
-  if (suite != VRFS_BANDERSNATCH_ELL2 && suite != VRFS_ED25519_TAI) return fail(ctx, VRFS_UNSUPPORTED, "suite %d is not implemented for output", (int)suite);
+  if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
   ST(begin_call(ctx, n));
   const uint8_t *d_sk, *d_in; uint8_t* d_o;
   ST(stage_in(ctx, BUF_IN0, sk, n * 32, &d_sk)); ST(stage_in(ctx, BUF_IN1, input, n * 64, &d_in)); ST(stage_out(ctx, BUF_OUT0, n * 64, &d_o));
-  ST(suite == VRFS_BANDERSNATCH_ELL2 ? output_dev<BandSuite>(ctx, n, d_sk, d_in, d_o) : output_dev<EdSuite>(ctx, n, d_sk, d_in, d_o));
+  ST(suite == VRFS_BANDERSNATCH_ELL2 ? output_dev<BandSuite>(ctx, n, d_sk, d_in, d_o)
+     : suite == VRFS_ED25519_TAI ? output_dev<EdSuite>(ctx, n, d_sk, d_in, d_o) : output_dev<P256Suite>(ctx, n, d_sk, d_in, d_o));
   ST(copy_out(ctx, out_output, d_o, n * 64));
   return finish_call(ctx);
 }
 template <class S> static vrfs_status from_seed_dev(vrfs_ctx* ctx, size_t n, const uint8_t* seeds, const uint64_t* off, uint8_t* out_sk, uint8_t* out_pk) {
   typedef typename S::C C;
-  k_te_secret_from_seed<S><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, seeds, off, out_sk);
-  LAUNCHED_AS(ctx, "te_secret_from_seed");
+  k_secret_from_seed<S><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, seeds, off, out_sk);
+  LAUNCHED_AS(ctx, "secret_from_seed");
   if (!out_pk) return VRFS_OK;
   void* o = nullptr;
   ST(ensure(ctx, BUF_W0, n * 96, &o));
   LincombArgs A = {};
   A.n = (uint32_t)n; A.fix[0] = {out_sk, 32, 0, fixtab<S>(ctx, 0)}; A.out_xyz = (uint32_t*)o;
   ST((launch_lincomb<C, 0, 1>(ctx, A)));
-  k_te_to_affine<C><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, (const uint32_t*)o, nullptr, out_pk);
-  LAUNCHED_AS(ctx, "te_to_affine");
+  k_to_affine<C><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, (const uint32_t*)o, nullptr, out_pk);
+  LAUNCHED_AS(ctx, "to_affine");
   return VRFS_OK;
 }
 extern "C" vrfs_status vrfs_secret_from_seed_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* seeds, const uint64_t* seed_off,
@@ -686,13 +693,14 @@ extern "C" vrfs_status vrfs_secret_from_seed_batch(vrfs_ctx* ctx, vrfs_suite sui
   if (!ctx) return VRFS_BAD_ARG;
   if (n == 0) return VRFS_OK;
   if (!seed_off || !out_sk) return fail(ctx, VRFS_BAD_ARG, "null buffer");
-  if (suite != VRFS_BANDERSNATCH_ELL2 && suite != VRFS_ED25519_TAI) return fail(ctx, VRFS_UNSUPPORTED, "suite %d is not implemented for from_seed", (int)suite);
+  if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
   ST(begin_call(ctx, n));
   const uint8_t* d_seeds; const uint64_t* d_off; uint8_t *d_sk, *d_pk = nullptr;
   ST(stage_ad(ctx, n, seeds, seed_off, &d_seeds, &d_off));
   ST(stage_out(ctx, BUF_OUT0, n * 32, &d_sk));
   if (out_pk) ST(stage_out(ctx, BUF_OUT1, n * 64, &d_pk));
-  ST(suite == VRFS_BANDERSNATCH_ELL2 ? from_seed_dev<BandSuite>(ctx, n, d_seeds, d_off, d_sk, d_pk) : from_seed_dev<EdSuite>(ctx, n, d_seeds, d_off, d_sk, d_pk));
+  ST(suite == VRFS_BANDERSNATCH_ELL2 ? from_seed_dev<BandSuite>(ctx, n, d_seeds, d_off, d_sk, d_pk)
+     : suite == VRFS_ED25519_TAI ? from_seed_dev<EdSuite>(ctx, n, d_seeds, d_off, d_sk, d_pk) : from_seed_dev<P256Suite>(ctx, n, d_seeds, d_off, d_sk, d_pk));
   ST(copy_out(ctx, out_sk, d_sk, n * 32));
   if (out_pk) ST(copy_out(ctx, out_pk, d_pk, n * 64));
   return finish_call(ctx);
@@ -701,13 +709,14 @@ extern "C" vrfs_status vrfs_nonce_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t 
   if (!ctx) return VRFS_BAD_ARG;
   if (n == 0) return VRFS_OK;
   if (!sk || !input || !out_k) return fail(ctx, VRFS_BAD_ARG, "null buffer");
-  if (suite != VRFS_BANDERSNATCH_ELL2 && suite != VRFS_ED25519_TAI) return fail(ctx, VRFS_UNSUPPORTED, "suite %d is not implemented for nonce", (int)suite);
+  if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
   ST(begin_call(ctx, n));
   const uint8_t *d_sk, *d_in; uint8_t* d_k;
   ST(stage_in(ctx, BUF_IN0, sk, n * 32, &d_sk)); ST(stage_in(ctx, BUF_IN1, input, n * 64, &d_in)); ST(stage_out(ctx, BUF_OUT0, n * 32, &d_k));
-  if (suite == VRFS_BANDERSNATCH_ELL2) k_te_nonce<BandSuite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_sk, d_in, d_k);
-  else k_te_nonce<EdSuite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_sk, d_in, d_k);
-  LAUNCHED_AS(ctx, "te_nonce");
+  if (suite == VRFS_BANDERSNATCH_ELL2) k_nonce<BandSuite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_sk, d_in, d_k);
+  else if (suite == VRFS_ED25519_TAI) k_nonce<EdSuite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_sk, d_in, d_k);
+  else k_nonce<P256Suite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_sk, d_in, d_k);
+  LAUNCHED_AS(ctx, "nonce");
   ST(copy_out(ctx, out_k, d_k, n * 32));
   return finish_call(ctx);
 }
@@ -715,41 +724,47 @@ extern "C" vrfs_status vrfs_point_to_hash_batch(vrfs_ctx* ctx, vrfs_suite suite,
   if (!ctx) return VRFS_BAD_ARG;
   if (n == 0) return VRFS_OK;
   if (!pts || !out_hash) return fail(ctx, VRFS_BAD_ARG, "null buffer");
-  if (suite != VRFS_BANDERSNATCH_ELL2 && suite != VRFS_ED25519_TAI) return fail(ctx, VRFS_UNSUPPORTED, "suite %d is not implemented for point_to_hash", (int)suite);
+  if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
   ST(begin_call(ctx, n));
   const uint8_t* d_p; uint8_t* d_h;
-  ST(stage_in(ctx, BUF_IN0, pts, n * 64, &d_p)); ST(stage_out(ctx, BUF_OUT0, n * 64, &d_h));
-  if (suite == VRFS_BANDERSNATCH_ELL2) k_te_point_to_hash<BandSuite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_p, d_h);
-  else k_te_point_to_hash<EdSuite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_p, d_h);
-  LAUNCHED_AS(ctx, "te_point_to_hash");
-  ST(copy_out(ctx, out_hash, d_h, n * 64));
+  const size_t hl = (size_t)vrfs_suite_hash_len(suite);
+  ST(stage_in(ctx, BUF_IN0, pts, n * 64, &d_p)); ST(stage_out(ctx, BUF_OUT0, n * hl, &d_h));
+  if (suite == VRFS_BANDERSNATCH_ELL2) k_point_to_hash<BandSuite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_p, d_h);
+  else if (suite == VRFS_ED25519_TAI) k_point_to_hash<EdSuite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_p, d_h);
+  else k_point_to_hash<P256Suite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_p, d_h);
+  LAUNCHED_AS(ctx, "point_to_hash");
+  ST(copy_out(ctx, out_hash, d_h, n * hl));
   return finish_call(ctx);
 }
 extern "C" vrfs_status vrfs_point_encode_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* pts, uint8_t* out_enc) {
   if (!ctx) return VRFS_BAD_ARG;
   if (n == 0) return VRFS_OK;
   if (!pts || !out_enc) return fail(ctx, VRFS_BAD_ARG, "null buffer");
-  if (suite != VRFS_BANDERSNATCH_ELL2 && suite != VRFS_ED25519_TAI) return fail(ctx, VRFS_UNSUPPORTED, "suite %d is not implemented for point_encode", (int)suite);
+  if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
   ST(begin_call(ctx, n));
   const uint8_t* d_p; uint8_t* d_e;
-  ST(stage_in(ctx, BUF_IN0, pts, n * 64, &d_p)); ST(stage_out(ctx, BUF_OUT0, n * 32, &d_e));
-  if (suite == VRFS_BANDERSNATCH_ELL2) k_te_point_encode<BandCurve><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_p, d_e);
-  else k_te_point_encode<EdCurve><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_p, d_e);
-  LAUNCHED_AS(ctx, "te_point_encode");
-  ST(copy_out(ctx, out_enc, d_e, n * 32));
+  const size_t el = (size_t)vrfs_suite_point_enc_len(suite);
+  ST(stage_in(ctx, BUF_IN0, pts, n * 64, &d_p)); ST(stage_out(ctx, BUF_OUT0, n * el, &d_e));
+  if (suite == VRFS_BANDERSNATCH_ELL2) k_point_encode<BandSuite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_p, d_e);
+  else if (suite == VRFS_ED25519_TAI) k_point_encode<EdSuite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_p, d_e);
+  else k_point_encode<P256Suite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_p, d_e);
+  LAUNCHED_AS(ctx, "point_encode");
+  ST(copy_out(ctx, out_enc, d_e, n * el));
   return finish_call(ctx);
 }
 extern "C" vrfs_status vrfs_point_decode_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* enc, uint8_t* out_pts, uint8_t* out_ok) {
   if (!ctx) return VRFS_BAD_ARG;
   if (n == 0) return VRFS_OK;
   if (!enc || !out_pts || !out_ok) return fail(ctx, VRFS_BAD_ARG, "null buffer");
-  if (suite != VRFS_BANDERSNATCH_ELL2 && suite != VRFS_ED25519_TAI) return fail(ctx, VRFS_UNSUPPORTED, "suite %d is not implemented for point_decode", (int)suite);
+  if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
   ST(begin_call(ctx, n));
   const uint8_t* d_e; uint8_t *d_p, *d_ok;
-  ST(stage_in(ctx, BUF_IN0, enc, n * 32, &d_e)); ST(stage_out(ctx, BUF_OUT0, n * 64, &d_p)); ST(stage_out(ctx, BUF_OUT1, n, &d_ok));
-  if (suite == VRFS_BANDERSNATCH_ELL2) k_te_point_decode<BandCurve><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_e, d_p, d_ok);
-  else k_te_point_decode<EdCurve><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_e, d_p, d_ok);
-  LAUNCHED_AS(ctx, "te_point_decode");
+  const size_t el = (size_t)vrfs_suite_point_enc_len(suite);
+  ST(stage_in(ctx, BUF_IN0, enc, n * el, &d_e)); ST(stage_out(ctx, BUF_OUT0, n * 64, &d_p)); ST(stage_out(ctx, BUF_OUT1, n, &d_ok));
+  if (suite == VRFS_BANDERSNATCH_ELL2) k_point_decode<BandSuite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_e, d_p, d_ok);
+  else if (suite == VRFS_ED25519_TAI) k_point_decode<EdSuite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_e, d_p, d_ok);
+  else k_point_decode<P256Suite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_e, d_p, d_ok);
+  LAUNCHED_AS(ctx, "point_decode");
   ST(copy_out(ctx, out_pts, d_p, n * 64)); ST(copy_out(ctx, out_ok, d_ok, n));
   return finish_call(ctx);
 }
@@ -758,14 +773,15 @@ extern "C" vrfs_status vrfs_data_to_point_batch(vrfs_ctx* ctx, vrfs_suite suite,
   if (!ctx) return VRFS_BAD_ARG;
   if (n == 0) return VRFS_OK;
   if (!data_off || !out_pts || !out_ok) return fail(ctx, VRFS_BAD_ARG, "null buffer");
-  if (suite != VRFS_BANDERSNATCH_ELL2 && suite != VRFS_ED25519_TAI) return fail(ctx, VRFS_UNSUPPORTED, "suite %d is not implemented for data_to_point", (int)suite);
+  if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
   ST(begin_call(ctx, n));
   const uint8_t* d_d; const uint64_t* d_off; uint8_t *d_p, *d_ok;
   ST(stage_ad(ctx, n, data, data_off, &d_d, &d_off));
   ST(stage_out(ctx, BUF_OUT0, n * 64, &d_p)); ST(stage_out(ctx, BUF_OUT1, n, &d_ok));
-  if (suite == VRFS_BANDERSNATCH_ELL2) k_te_data_to_point<BandSuite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_d, d_off, d_p, d_ok);
-  else k_te_data_to_point<EdSuite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_d, d_off, d_p, d_ok);
-  LAUNCHED_AS(ctx, "te_data_to_point");
+  if (suite == VRFS_BANDERSNATCH_ELL2) k_data_to_point<BandSuite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_d, d_off, d_p, d_ok);
+  else if (suite == VRFS_ED25519_TAI) k_data_to_point<EdSuite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_d, d_off, d_p, d_ok);
+  else k_data_to_point<P256Suite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_d, d_off, d_p, d_ok);
+  LAUNCHED_AS(ctx, "data_to_point");
   ST(copy_out(ctx, out_pts, d_p, n * 64)); ST(copy_out(ctx, out_ok, d_ok, n));
   return finish_call(ctx);
 }
@@ -800,14 +816,14 @@ extern "C" vrfs_status vrfs_pedersen_prove_batch(vrfs_ctx* ctx, vrfs_suite suite
   if (!ctx) return VRFS_BAD_ARG;
   if (n == 0) return VRFS_OK;
   if (!sk || !input || !output || !out_proof || !out_blinding) return fail(ctx, VRFS_BAD_ARG, "null buffer");
-  if (suite != VRFS_BANDERSNATCH_ELL2 && suite != VRFS_ED25519_TAI) return fail(ctx, VRFS_UNSUPPORTED, "suite %d is not implemented for pedersen prove", (int)suite);
+  if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
   ST(begin_call(ctx, n));
   const uint8_t *d_sk, *d_in, *d_out, *d_ad; const uint64_t* d_off; uint8_t *d_pr, *d_bl;
   ST(stage_in(ctx, BUF_IN0, sk, n * 32, &d_sk)); ST(stage_in(ctx, BUF_IN1, input, n * 64, &d_in)); ST(stage_in(ctx, BUF_IN2, output, n * 64, &d_out));
   ST(stage_ad(ctx, n, ad, ad_off, &d_ad, &d_off));
   ST(stage_out(ctx, BUF_OUT0, n * 256, &d_pr)); ST(stage_out(ctx, BUF_OUT1, n * 32, &d_bl));
   ST(suite == VRFS_BANDERSNATCH_ELL2 ? pedersen_prove_dev<BandSuite>(ctx, n, d_sk, d_in, d_out, d_ad, d_off, d_pr, d_bl)
-                                     : pedersen_prove_dev<EdSuite>(ctx, n, d_sk, d_in, d_out, d_ad, d_off, d_pr, d_bl));
+     : suite == VRFS_ED25519_TAI ? pedersen_prove_dev<EdSuite>(ctx, n, d_sk, d_in, d_out, d_ad, d_off, d_pr, d_bl) : pedersen_prove_dev<P256Suite>(ctx, n, d_sk, d_in, d_out, d_ad, d_off, d_pr, d_bl));
   ST(copy_out(ctx, out_proof, d_pr, n * 256)); ST(copy_out(ctx, out_blinding, d_bl, n * 32));
   return finish_call(ctx);
 }
@@ -819,7 +835,7 @@ static vrfs_status pedersen_verify_dev(vrfs_ctx* ctx, size_t n, const uint8_t* i
   uint8_t* valid = nullptr;
   ST(ensure(ctx, BUF_W0, n * 32, &c)); ST(ensure(ctx, BUF_W1, n * 96, &t1)); ST(ensure(ctx, BUF_W2, n * 96, &t2));
   ST(fresh_valid(ctx, n, &valid));
-  k_pedersen_verify_prep<S><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, input, output, proof, ad, ad_off, (uint8_t*)c);
+  k_pedersen_verify_prep<S><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, input, output, proof, ad, ad_off, (uint8_t*)c, valid);
   LAUNCHED_AS(ctx, "pedersen_verify_prep");
   LincombArgs A = {};
   A.n = (uint32_t)n; A.valid = valid;
@@ -839,14 +855,14 @@ extern "C" vrfs_status vrfs_pedersen_verify_batch(vrfs_ctx* ctx, vrfs_suite suit
   if (!ctx) return VRFS_BAD_ARG;
   if (n == 0) return VRFS_OK;
   if (!input || !output || !proof || !out_ok) return fail(ctx, VRFS_BAD_ARG, "null buffer");
-  if (suite != VRFS_BANDERSNATCH_ELL2 && suite != VRFS_ED25519_TAI) return fail(ctx, VRFS_UNSUPPORTED, "suite %d is not implemented for pedersen verify", (int)suite);
+  if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
   ST(begin_call(ctx, n));
   const uint8_t *d_in, *d_out, *d_pr, *d_ad; const uint64_t* d_off; uint8_t* d_ok;
   ST(stage_in(ctx, BUF_IN0, input, n * 64, &d_in)); ST(stage_in(ctx, BUF_IN1, output, n * 64, &d_out)); ST(stage_in(ctx, BUF_IN2, proof, n * 256, &d_pr));
   ST(stage_ad(ctx, n, ad, ad_off, &d_ad, &d_off));
   ST(stage_out(ctx, BUF_OUT0, n, &d_ok));
   ST(suite == VRFS_BANDERSNATCH_ELL2 ? pedersen_verify_dev<BandSuite>(ctx, n, d_in, d_out, d_pr, d_ad, d_off, d_ok)
-                                     : pedersen_verify_dev<EdSuite>(ctx, n, d_in, d_out, d_pr, d_ad, d_off, d_ok));
+     : suite == VRFS_ED25519_TAI ? pedersen_verify_dev<EdSuite>(ctx, n, d_in, d_out, d_pr, d_ad, d_off, d_ok) : pedersen_verify_dev<P256Suite>(ctx, n, d_in, d_out, d_pr, d_ad, d_off, d_ok));
   ST(copy_out(ctx, out_ok, d_ok, n));
   return finish_call(ctx);
 }

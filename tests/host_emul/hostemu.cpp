@@ -38,15 +38,15 @@ extern "C" void hostemu_field_op(int field, int op, const uint32_t* a, const uin
 // ---------------------------------------------------------------------------------------------
 // per-item engine code on the host: IETF verify (Bandersnatch / Ed25519)
 #include <vector>
-#include "../../ark_ec_vrfs_b200/csrc/suite.cuh"
+#include "../../ark_ec_vrfs_b200/csrc/h2c.cuh"
 
-template <class C> static const TEAffCached<C>* fixed_table(bool blinding) {
-  static std::vector<TEAffCached<C>> tabs[2];
+template <class C> static const typename Grp<C>::FixEntry* fixed_table(bool blinding) {
+  static std::vector<typename Grp<C>::FixEntry> tabs[2];
   auto& t = tabs[blinding];
   if (t.empty()) {
-    t.resize(32 * 129);
-    for (int w = 0; w < 32; w++) for (int d = 0; d <= 128; d++)
-      te_fixed_table_entry<C>(t[w * 129 + d], blinding ? C::bx() : C::gx(), blinding ? C::by() : C::gy(), w, d);
+    t.resize(fix_table_entries<C>());
+    for (int w = 0; w < Grp<C>::FIX_WINDOWS; w++) for (int d = 0; d <= 128; d++)
+      fixed_table_entry<C>(t[w * 129 + d], blinding ? C::bx() : C::gx(), blinding ? C::by() : C::gy(), w, d);
   }
   return t.data();
 }
@@ -54,19 +54,19 @@ template <class C> static const TEAffCached<C>* fixed_table(bool blinding) {
 template <class S> static void ietf_verify(size_t n, const uint8_t* pk, const uint8_t* in, const uint8_t* out, const uint8_t* c,
                                            const uint8_t* s, const uint8_t* ad, const uint64_t* ad_off, uint8_t* ok) {
   typedef typename S::C C;
-  std::vector<TECached<C>> slab(4 * 9);
+  std::vector<typename Grp<C>::Entry> slab(4 * 9);
   std::vector<uint32_t> u(24), v(24);
   for (size_t i = 0; i < n; i++) {
     LincombArgs A = {};
     A.n = (uint32_t)n;
     A.var[0] = {pk, 64, c, 32, 1};
     A.fix[0] = {s, 32, 0, fixed_table<C>(false)};
-    TEPoint<C> acc;
-    bool valid = te_lincomb_item<C, 1, 1>(A, (uint32_t)i, slab.data(), acc);
+    typename Grp<C>::Pt acc;
+    bool valid = lincomb_item<C, 1, 1>(A, (uint32_t)i, slab.data(), acc);
     memcpy(&u[0], acc.X.v, 32); memcpy(&u[8], acc.Y.v, 32); memcpy(&u[16], acc.Z.v, 32);
     A.var[0] = {in, 64, s, 32, 0};
     A.var[1] = {out, 64, c, 32, 1};
-    valid &= te_lincomb_item<C, 2, 0>(A, (uint32_t)i, slab.data(), acc);
+    valid &= lincomb_item<C, 2, 0>(A, (uint32_t)i, slab.data(), acc);
     memcpy(&v[0], acc.X.v, 32); memcpy(&v[8], acc.Y.v, 32); memcpy(&v[16], acc.Z.v, 32);
     const uint8_t* a = ad ? ad + ad_off[i] : (const uint8_t*)"";
     uint32_t alen = ad ? (uint32_t)(ad_off[i + 1] - ad_off[i]) : 0;
@@ -77,22 +77,23 @@ extern "C" void hostemu_ietf_verify(int suite, size_t n, const uint8_t* pk, cons
                                     const uint8_t* s, const uint8_t* ad, const uint64_t* ad_off, uint8_t* ok) {
   if (suite == 0) ietf_verify<BandSuite>(n, pk, in, out, c, s, ad, ad_off, ok);
   else if (suite == 1) ietf_verify<EdSuite>(n, pk, in, out, c, s, ad, ad_off, ok);
+  else ietf_verify<P256Suite>(n, pk, in, out, c, s, ad, ad_off, ok);
 }
 
 // debug / unit-test entry: R = k1*P1 [+ k2*P2] [+ f*G], affine canonical out (x||y LE)
 template <class C> static int lincomb_dbg(int nv, int nf, const uint8_t* p1, const uint8_t* k1, const uint8_t* p2, const uint8_t* k2,
                                           const uint8_t* f, int neg_mask, uint8_t* out) {
-  std::vector<TECached<C>> slab(4 * 9);
+  std::vector<typename Grp<C>::Entry> slab(4 * 9);
   LincombArgs A = {};
   A.n = 1;
   A.var[0] = {p1, 64, k1, 32, (uint32_t)(neg_mask & 1)};
   A.var[1] = {p2, 64, k2, 32, (uint32_t)((neg_mask >> 1) & 1)};
   A.fix[0] = {f, 32, (uint32_t)((neg_mask >> 2) & 1), fixed_table<C>(false)};
-  TEPoint<C> acc; bool ok;
-  if (nv == 1 && nf == 0) ok = te_lincomb_item<C, 1, 0>(A, 0, slab.data(), acc);
-  else if (nv == 2 && nf == 0) ok = te_lincomb_item<C, 2, 0>(A, 0, slab.data(), acc);
-  else if (nv == 0 && nf == 1) ok = te_lincomb_item<C, 0, 1>(A, 0, slab.data(), acc);
-  else ok = te_lincomb_item<C, 1, 1>(A, 0, slab.data(), acc);
+  typename Grp<C>::Pt acc; bool ok;
+  if (nv == 1 && nf == 0) ok = lincomb_item<C, 1, 0>(A, 0, slab.data(), acc);
+  else if (nv == 2 && nf == 0) ok = lincomb_item<C, 2, 0>(A, 0, slab.data(), acc);
+  else if (nv == 0 && nf == 1) ok = lincomb_item<C, 0, 1>(A, 0, slab.data(), acc);
+  else ok = lincomb_item<C, 1, 1>(A, 0, slab.data(), acc);
   typename C::F zi = inv(acc.Z), x = acc.X * zi, y = acc.Y * zi;
   uint32_t rx[8], ry[8]; from_mont<typename C::Fq>(rx, x); from_mont<typename C::Fq>(ry, y);
   store_le<8>(out, rx); store_le<8>(out + 32, ry);
@@ -100,7 +101,8 @@ template <class C> static int lincomb_dbg(int nv, int nf, const uint8_t* p1, con
 }
 extern "C" int hostemu_lincomb(int suite, int nv, int nf, const uint8_t* p1, const uint8_t* k1, const uint8_t* p2, const uint8_t* k2,
                                const uint8_t* f, int neg_mask, uint8_t* out) {
-  return suite == 0 ? lincomb_dbg<BandCurve>(nv, nf, p1, k1, p2, k2, f, neg_mask, out) : lincomb_dbg<EdCurve>(nv, nf, p1, k1, p2, k2, f, neg_mask, out);
+  return suite == 0 ? lincomb_dbg<BandCurve>(nv, nf, p1, k1, p2, k2, f, neg_mask, out)
+       : suite == 1 ? lincomb_dbg<EdCurve>(nv, nf, p1, k1, p2, k2, f, neg_mask, out) : lincomb_dbg<P256Curve>(nv, nf, p1, k1, p2, k2, f, neg_mask, out);
 }
 extern "C" void hostemu_glv(const uint32_t* k, uint32_t* out /*4+4+2*/) {
   GlvHalf a, b; band_glv_split(&a, &b, k);

@@ -1,4 +1,4 @@
-"""GPU parity for every twisted-Edwards entry point of the C ABI (Bandersnatch + Ed25519) against the CPU
+"""GPU parity for every per-suite entry point of the C ABI (Bandersnatch, Ed25519, secp256r1) against the CPU
 oracle and the golden vectors: Secret / Public / Input / Output, codec, nonce, ietf prove, pedersen."""
 import json
 import os
@@ -11,7 +11,7 @@ import vectors as V
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
-TE_SUITES = [O.BANDERSNATCH, O.ED25519]
+TE_SUITES = [O.BANDERSNATCH, O.ED25519, O.P256]
 
 
 @pytest.fixture(scope="module")
@@ -46,7 +46,11 @@ def test_keys_inputs_outputs(eng, suite):
     dec, dok = eng.point_decode(suite, enc_o)
     assert dok.all() and np.array_equal(dec, out_o)
     # decoding arbitrary bytes: same accept/reject decisions and same points as the oracle
-    rnd = np.frombuffer(b"".join(O.sha512(b"dec%d" % i) for i in range(n)), np.uint8).reshape(n, 64)[:, :32].copy()
+    L = eng.point_enc_len(suite)
+    rnd = np.frombuffer(b"".join(O.sha512(b"dec%d" % i) for i in range(n)), np.uint8).reshape(n, 64)[:, :L].copy()
+    if suite == O.P256:
+        rnd[:, 0] = 2 + (rnd[:, 0] & 1)
+        rnd[::7, 0] = 4                      # invalid SEC1 tag
     d_o, k_o = O.point_decode(suite, rnd)
     d_g, k_g = eng.point_decode(suite, rnd)
     assert np.array_equal(k_g, k_o) and 0 < k_o.sum() < n and np.array_equal(d_g, d_o)
@@ -119,7 +123,7 @@ def test_upstream_bandersnatch_vectors_through_gpu(eng):
         assert eng.pedersen_verify(0, inp, out, pr, [bytes.fromhex(v["ad"])]).tolist() == [1]
 
 
-@pytest.mark.parametrize("fname,suite", [("bandersnatch_regression.json", 0), ("ed25519_regression.json", 1)])
+@pytest.mark.parametrize("fname,suite", [("bandersnatch_regression.json", 0), ("ed25519_regression.json", 1), ("p256_regression.json", 2)])
 def test_regression_vectors_through_gpu(eng, fname, suite):
     """tests/golden/*_regression.json (generated by the independent Python model; Ed25519 has no upstream vector)"""
     with open(os.path.join(GOLDEN, fname)) as f:
@@ -136,12 +140,48 @@ def test_regression_vectors_through_gpu(eng, fname, suite):
     c, s = eng.ietf_prove(suite, sk, inp, out, ads)
     pr, bl = eng.pedersen_prove(suite, sk, inp, out, ads)
     e_pk, e_in, e_out = eng.point_encode(suite, pk), eng.point_encode(suite, inp), eng.point_encode(suite, out)
-    e_pr = eng.point_encode(suite, pr[:, :192].reshape(-1, 64)).reshape(len(vs), 3, 32)
+    e_pr = eng.point_encode(suite, pr[:, :192].reshape(-1, 64)).reshape(len(vs), 3, -1)
+    sc = (lambda a: hx(np.asarray(a)[::-1])) if suite == 2 else hx     # golden scalars are in suite encoding (BE for SEC1)
     for i, v in enumerate(vs):
-        assert hx(sk[i]) == v["sk"] and hx(e_pk[i]) == v["pk"] and hx(e_in[i]) == v["h"] and hx(e_out[i]) == v["gamma"], v["comment"]
-        assert hx(beta[i]) == v["beta"] and hx(k[i]) == v["nonce"], v["comment"]
-        assert hx(c[i]) == v["proof_c"] and hx(s[i]) == v["proof_s"], v["comment"]
-        assert hx(bl[i]) == v["blinding"] and hx(e_pr[i, 0]) == v["ped_pk_com"] and hx(e_pr[i, 1]) == v["ped_r"] and hx(e_pr[i, 2]) == v["ped_ok"], v["comment"]
-        assert hx(pr[i, 192:224]) == v["ped_s"] and hx(pr[i, 224:256]) == v["ped_sb"], v["comment"]
+        assert sc(sk[i]) == v["sk"] and hx(e_pk[i]) == v["pk"] and hx(e_in[i]) == v["h"] and hx(e_out[i]) == v["gamma"], v["comment"]
+        assert hx(beta[i]) == v["beta"] and sc(k[i]) == v["nonce"], v["comment"]
+        assert sc(c[i]) == v["proof_c"] and sc(s[i]) == v["proof_s"], v["comment"]
+        assert sc(bl[i]) == v["blinding"] and hx(e_pr[i, 0]) == v["ped_pk_com"] and hx(e_pr[i, 1]) == v["ped_r"] and hx(e_pr[i, 2]) == v["ped_ok"], v["comment"]
+        assert sc(pr[i, 192:224]) == v["ped_s"] and sc(pr[i, 224:256]) == v["ped_sb"], v["comment"]
     assert eng.ietf_verify(suite, pk, inp, out, c, s, ads).all()
     assert eng.pedersen_verify(suite, inp, out, pr, ads).all()
+
+
+def test_rfc9381_p256_examples_through_gpu(eng):
+    """RFC 9381 Appendix B Examples 10-11: pi = enc(Gamma) || BE16(c) || BE32(s), produced by the CUDA path"""
+    with open(os.path.join(GOLDEN, "p256_rfc9381.json")) as f:
+        g = json.load(f)
+    vs = g["vectors"] if "vectors" in g else g["ietf"]
+    for v in vs:
+        sk = np.frombuffer(bytes.fromhex(v["sk"])[::-1], np.uint8).reshape(1, 32)
+        pk_enc = bytes.fromhex(v["pk"])
+        pk, ok = eng.point_decode(2, pk_enc)
+        assert ok.all()
+        inp, ok = eng.data_to_point(2, [pk_enc + bytes.fromhex(v["alpha"])])
+        assert ok.all()
+        if "h" in v:
+            assert hx(eng.point_encode(2, inp)) == v["h"]
+        if "k" in v:
+            assert hx(eng.nonce(2, sk, inp)[0][::-1]) == v["k"]
+        out = eng.output(2, sk, inp)
+        c, s = eng.ietf_prove(2, sk, inp, out, [b""])
+        pi = hx(eng.point_encode(2, out)) + hx(c[0, :16][::-1]) + hx(s[0][::-1])
+        assert pi == v["pi"], v["comment"]
+        if "beta" in v:
+            assert hx(eng.point_to_hash(2, out)) == v["beta"]
+        assert eng.ietf_verify(2, pk, inp, out, c, s, [b""]).tolist() == [1]
+
+
+def test_p256_identity_points_are_rejected(eng):
+    w = V.make_ietf_proofs(O.P256, 6, "empty", corrupt=False)
+    pk, inp, out, c, s = (w[k].copy() for k in ("pk", "inp", "out", "c", "s"))
+    pk[0] = 0; inp[1] = 0; out[2] = 0
+    c[3] = 0; s[3] = 0                                   # U = V = identity
+    exp = O.ietf_verify(O.P256, pk, inp, out, c, s)
+    got = eng.ietf_verify(O.P256, pk, inp, out, c, s)
+    assert np.array_equal(got, exp) and exp.tolist() == [0, 0, 0, 0, 1, 1]
