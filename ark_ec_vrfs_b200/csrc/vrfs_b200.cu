@@ -8,6 +8,7 @@
 
 #include "../../include/vrfs_b200.h"
 #include "h2c.cuh"
+#include "msm.cuh"
 
 using namespace vrfs;
 
@@ -868,9 +869,73 @@ extern "C" vrfs_status vrfs_pedersen_verify_batch(vrfs_ctx* ctx, vrfs_suite suit
 }
 
 // =================================================================================================
-// entry points still to be implemented in this round (they fail loudly, never fall back to the CPU)
+// ring commitment MSM (K12)
 // =================================================================================================
-#define NOT_YET(name) return fail(ctx, VRFS_UNSUPPORTED, name " is not implemented yet")
-extern "C" vrfs_status vrfs_msm_g1_bls12_381(vrfs_ctx* ctx, size_t, const uint8_t*, const uint8_t*, int, uint8_t*) { NOT_YET("vrfs_msm_g1_bls12_381"); }
-extern "C" vrfs_status vrfs_msm_g1_partial(vrfs_ctx* ctx, size_t, const uint8_t*, const uint8_t*, int, uint8_t*) { NOT_YET("vrfs_msm_g1_partial"); }
-extern "C" vrfs_status vrfs_g1_sum_partials(vrfs_ctx* ctx, int, int, const uint8_t*, uint8_t*) { NOT_YET("vrfs_g1_sum_partials"); }
+enum { MBUF_BASES, MBUF_COUNTS, MBUF_OFFSETS, MBUF_CURSORS, MBUF_LIST, MBUF_BUCKETS, MBUF_WINDOWS, MBUF_COUNT };
+static vrfs_status msm_dev(vrfs_ctx* ctx, size_t n, const uint8_t* d_bases, const uint8_t* d_scalars, int ncol, uint8_t* d_out, int out_mode) {
+  MsmPlan p = msm_plan((uint32_t)n, (uint32_t)ncol);
+  const size_t segs = (size_t)ncol * p.windows, nbuckets = segs * p.nb;
+  void *bases_m, *counts, *offsets, *cursors, *list, *buckets, *wsum;
+  ST(ensure(ctx, BUF_W0, n * sizeof(G1Aff), &bases_m));
+  ST(ensure(ctx, BUF_W1, nbuckets * 3 * sizeof(uint32_t), &counts));
+  offsets = (uint32_t*)counts + nbuckets; cursors = (uint32_t*)counts + 2 * nbuckets;
+  ST(ensure(ctx, BUF_W2, segs * n * sizeof(uint32_t), &list));
+  ST(ensure(ctx, BUF_W3, nbuckets * sizeof(G1Pt), &buckets));
+  ST(ensure(ctx, BUF_SLAB, segs * sizeof(G1Pt), &wsum));
+  CU(cudaMemsetAsync(counts, 0, nbuckets * 3 * sizeof(uint32_t), ctx->stream));
+  const unsigned tn = (unsigned)((n + 127) / 128), tsc = (unsigned)((n * ncol + 127) / 128);
+  k_msm_prep_bases<<<tn, 128, 0, ctx->stream>>>((uint32_t)n, d_bases, (G1Aff*)bases_m);
+  LAUNCHED_AS(ctx, "msm_prep_bases");
+  k_msm_histogram<<<tsc, 128, 0, ctx->stream>>>(p, d_scalars, (uint32_t*)counts);
+  LAUNCHED_AS(ctx, "msm_histogram");
+  k_msm_scan<<<(unsigned)segs, 256, 0, ctx->stream>>>(p, (const uint32_t*)counts, (uint32_t*)offsets);
+  LAUNCHED_AS(ctx, "msm_scan");
+  k_msm_scatter<<<tsc, 128, 0, ctx->stream>>>(p, d_scalars, (const uint32_t*)offsets, (uint32_t*)cursors, (uint32_t*)list);
+  LAUNCHED_AS(ctx, "msm_scatter");
+  k_msm_accumulate<<<(unsigned)((nbuckets + 127) / 128), 128, 0, ctx->stream>>>(p, (const G1Aff*)bases_m, (const uint32_t*)counts, (const uint32_t*)offsets,
+                                                                               (const uint32_t*)list, (G1Pt*)buckets);
+  LAUNCHED_AS(ctx, "msm_accumulate");
+  const unsigned wt = (unsigned)(p.nb / MSM_CHUNK);
+  k_msm_window<<<(unsigned)segs, wt, wt * sizeof(G1Pt), ctx->stream>>>(p, (const G1Pt*)buckets, (G1Pt*)wsum);
+  LAUNCHED_AS(ctx, "msm_window");
+  k_msm_final<<<1, 32, 0, ctx->stream>>>(p, (const G1Pt*)wsum, d_out, out_mode);
+  LAUNCHED_AS(ctx, "msm_final");
+  return VRFS_OK;
+}
+static vrfs_status msm_host(vrfs_ctx* ctx, size_t n, const uint8_t* bases, const uint8_t* scalars, int ncol, uint8_t* out, int out_mode) {
+  if (!ctx) return VRFS_BAD_ARG;
+  if (ncol < 1 || ncol > 32) return fail(ctx, VRFS_BAD_ARG, "n_columns must be in 1..32");
+  if (!out || (n && (!bases || !scalars))) return fail(ctx, VRFS_BAD_ARG, "null buffer");
+  const size_t ob = out_mode ? 144 : 96;
+  if (n == 0) {                                   // empty sum = identity
+    memset(out, 0, ob * ncol);
+    if (out_mode) for (int c = 0; c < ncol; c++) out[ob * c + 48] = 1;   // (0 : 1 : 0)
+    return VRFS_OK;
+  }
+  if (n > (1u << 26)) return fail(ctx, VRFS_BAD_ARG, "MSM size above 2^26 is not supported");
+  ST(begin_call(ctx, n));
+  const uint8_t *d_b, *d_s; uint8_t* d_o;
+  ST(stage_in(ctx, BUF_IN0, bases, n * 96, &d_b)); ST(stage_in(ctx, BUF_IN1, scalars, n * 32 * (size_t)ncol, &d_s));
+  ST(stage_out(ctx, BUF_OUT0, ob * ncol, &d_o));
+  ST(msm_dev(ctx, n, d_b, d_s, ncol, d_o, out_mode));
+  ST(copy_out(ctx, out, d_o, ob * ncol));
+  return finish_call(ctx);
+}
+extern "C" vrfs_status vrfs_msm_g1_bls12_381(vrfs_ctx* ctx, size_t n, const uint8_t* bases, const uint8_t* scalars, int n_columns, uint8_t* out) {
+  return msm_host(ctx, n, bases, scalars, n_columns, out, 0);
+}
+extern "C" vrfs_status vrfs_msm_g1_partial(vrfs_ctx* ctx, size_t n, const uint8_t* bases, const uint8_t* scalars, int n_columns, uint8_t* out_partial) {
+  return msm_host(ctx, n, bases, scalars, n_columns, out_partial, 1);
+}
+extern "C" vrfs_status vrfs_g1_sum_partials(vrfs_ctx* ctx, int n_parts, int n_columns, const uint8_t* partials, uint8_t* out) {
+  if (!ctx) return VRFS_BAD_ARG;
+  if (n_parts < 1 || n_columns < 1 || n_columns > 32 || !partials || !out) return fail(ctx, VRFS_BAD_ARG, "bad argument");
+  ST(begin_call(ctx, 1));
+  const uint8_t* d_p; uint8_t* d_o;
+  ST(stage_in(ctx, BUF_IN0, partials, (size_t)n_parts * n_columns * 144, &d_p));
+  ST(stage_out(ctx, BUF_OUT0, (size_t)96 * n_columns, &d_o));
+  k_g1_sum_partials<<<1, 32, 0, ctx->stream>>>(n_parts, n_columns, d_p, d_o);
+  LAUNCHED_AS(ctx, "g1_sum_partials");
+  ST(copy_out(ctx, out, d_o, (size_t)96 * n_columns));
+  return finish_call(ctx);
+}

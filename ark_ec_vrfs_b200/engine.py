@@ -170,6 +170,24 @@ class Engine:
         self._call("vrfs_pedersen_verify_batch", suite, C.c_size_t(n), _p(inp), _p(outp), _p(proof), _p(adb), _p(off), _p(ok))
         return ok
 
+    # ---- ring commitment MSM (BLS12-381 G1)
+    def msm_g1(self, bases, scalars, n_columns=1):
+        bases = _u8(bases, (-1, 96)); n = len(bases); scalars = _u8(scalars, (n_columns * n, 32))
+        out = np.zeros((n_columns, 96), np.uint8)
+        self._call("vrfs_msm_g1_bls12_381", C.c_size_t(n), _p(bases), _p(scalars), int(n_columns), _p(out))
+        return out
+
+    def msm_g1_partial(self, bases, scalars, n_columns=1):
+        bases = _u8(bases, (-1, 96)); n = len(bases); scalars = _u8(scalars, (n_columns * n, 32))
+        out = np.zeros((n_columns, 144), np.uint8)
+        self._call("vrfs_msm_g1_partial", C.c_size_t(n), _p(bases), _p(scalars), int(n_columns), _p(out))
+        return out
+
+    def g1_sum_partials(self, partials, n_columns=1):
+        partials = _u8(partials, (-1, n_columns, 144)); out = np.zeros((n_columns, 96), np.uint8)
+        self._call("vrfs_g1_sum_partials", int(len(partials)), int(n_columns), _p(partials), _p(out))
+        return out
+
     # ---- measurement
     def enable_kernel_timing(self, on=True):
         self._check(self._lib.vrfs_ctx_enable_kernel_timing(self._ctx, int(bool(on))))

@@ -1,0 +1,96 @@
+"""GPU parity: vrfs_msm_g1_bls12_381 (Pippenger, CUDA) against the oracle's ark-ec-style MSM and against
+size-independent properties (linearity, point-range splitting) at the BASELINE ring sizes."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+R_BLS = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import ark_ec_vrfs_b200 as vrfs
+    e = vrfs.Engine(0)
+    yield e
+    e.close()
+
+
+def synth(n, ncol, tag=b"msm"):
+    """bases tau^j * G for a public test-only tau, scalars from SHA-512"""
+    tau = int.from_bytes(hashlib.sha512(b"vrfs-b200-bench-tau").digest(), "little") % R_BLS
+    pw, t = [], 1
+    for _ in range(n):
+        pw.append(t.to_bytes(32, "little")); t = t * tau % R_BLS
+    bases = O.g1_mul_gen(np.frombuffer(b"".join(pw), np.uint8).reshape(n, 32))
+    sc = np.frombuffer(b"".join(hashlib.sha512(tag + b"%d" % j).digest()[:32] for j in range(n * ncol)), np.uint8).reshape(n * ncol, 32).copy()
+    return bases, sc
+
+
+@pytest.mark.parametrize("n,ncol", [(1, 1), (2, 3), (31, 1), (32, 2), (1000, 3), (2048, 3)])
+def test_msm_matches_oracle(eng, n, ncol):
+    bases, sc = synth(n, ncol)
+    assert np.array_equal(eng.msm_g1(bases, sc, ncol), O.msm_g1(bases, sc, ncol))
+
+
+def test_msm_edge_cases(eng):
+    n = 64
+    bases, sc = synth(n, 3)
+    sc[:n] = 0                                                   # column 0: all-zero scalars -> identity (zeros)
+    sc[n:2 * n] = np.frombuffer((R_BLS - 1).to_bytes(32, "little"), np.uint8)   # column 1: all r-1
+    sc[2 * n:] = 0xFF                                            # column 2: scalars >= r, reduced on load
+    bases[3] = 0                                                 # an identity base
+    bases[7] = bases[8]                                          # repeated bases (P + P inside a bucket)
+    got = eng.msm_g1(bases, sc, 3)
+    exp = O.msm_g1(bases, sc, 3)
+    assert np.array_equal(got, exp) and not got[0].any()
+    assert np.array_equal(eng.msm_g1(np.zeros((0, 96), np.uint8), np.zeros((0, 32), np.uint8), 1), np.zeros((1, 96), np.uint8))
+
+
+def test_msm_regression_golden(eng):
+    """tests/golden/msm_g1_regression.json: big-endian hex x||y computed by the independent Python model"""
+    with open(os.path.join(GOLDEN, "msm_g1_regression.json")) as f:
+        g = json.load(f)
+    for case in g["cases"]:
+        bases = b"".join(bytes.fromhex(b[:96])[::-1] + bytes.fromhex(b[96:])[::-1] for b in case["bases"])
+        scalars = b"".join(bytes.fromhex(x)[::-1] for x in case["scalars"])
+        res = eng.msm_g1(bases, scalars, 1)[0].tobytes()
+        exp = bytes(96) if case["result"] is None else bytes.fromhex(case["result"][:96])[::-1] + bytes.fromhex(case["result"][96:])[::-1]
+        assert res == exp, case["n"]
+
+
+@pytest.mark.parametrize("logn", [11, 14, 17])
+def test_msm_ring_sizes_split_and_linearity(eng, logn):
+    """BASELINE config 5 domain sizes: (a) splitting the point range in two and folding the partials
+    (the multi-GPU path) equals the one-shot MSM; (b) MSM(s1 + s2) = MSM(s1) + MSM(s2), checked through
+    the 3-column call: column 2 holds s1 + s2 mod r"""
+    n = 1 << logn
+    rng = np.random.default_rng(logn)
+    k = rng.integers(1, 2 ** 62, size=n, dtype=np.uint64)
+    ks = np.zeros((n, 32), np.uint8); ks[:, :8] = k.view(np.uint8).reshape(n, 8)
+    bases = O.g1_mul_gen(ks)                                                    # k_i * G, cheap 62-bit multiples
+    s1 = rng.integers(0, 256, size=(n, 32), dtype=np.uint8); s1[:, 31] &= 0x3F
+    s2 = rng.integers(0, 256, size=(n, 32), dtype=np.uint8); s2[:, 31] &= 0x3F
+    s3 = np.zeros((n, 32), np.uint8)
+    for i in range(n):
+        v = (int.from_bytes(s1[i].tobytes(), "little") + int.from_bytes(s2[i].tobytes(), "little")) % R_BLS
+        s3[i] = np.frombuffer(v.to_bytes(32, "little"), np.uint8)
+    sc = np.concatenate([s1, s2, s3])
+    full = eng.msm_g1(bases, sc, 3)
+    h = n // 2
+    sc_lo = np.concatenate([s1[:h], s2[:h], s3[:h]]); sc_hi = np.concatenate([s1[h:], s2[h:], s3[h:]])
+    parts = np.stack([eng.msm_g1_partial(bases[:h], sc_lo, 3), eng.msm_g1_partial(bases[h:], sc_hi, 3)])
+    assert np.array_equal(eng.g1_sum_partials(parts, 3), full)
+    # linearity: column0 + column1 == column2, folded on the GPU from affine -> projective (Z = 1) partials
+    def as_partial(aff):
+        p = np.zeros((1, 144), np.uint8); p[0, :96] = aff; p[0, 96] = 1; return p
+    s = eng.g1_sum_partials(np.stack([as_partial(full[0]), as_partial(full[1])]), 1)
+    assert np.array_equal(s[0], full[2])
+    if logn == 11:
+        assert np.array_equal(full, O.msm_g1(bases, sc, 3))
