@@ -1,0 +1,147 @@
+"""Host-side mirror of the reference's public API for the hot path, in batch form.
+
+The reference (ark-ec-vrfs = ark-vrf 0.1.0; names re-exported at /root/reference/src/lib.rs:13-17) exposes,
+per item:  Secret::from_seed / Secret::public / Secret::output,  Input::new,  Output::hash,
+ietf::Prover::prove / ietf::Verifier::verify,  pedersen::Prover::prove / pedersen::Verifier::verify,
+and the ring commitment built by RingContext::verifier_key.  Here every type holds a BATCH of n values
+(numpy uint8 arrays in the C ABI's layout) and every method is one call into libvrfs_b200.so; same names,
+same argument meaning, and the reference's error behaviour mapped onto arrays:
+   Result<(), Error>  ->  uint8[n], 1 = Ok(()), 0 = Err(VerificationFailure | InvalidData)
+   Option<Input>      ->  (Input, uint8[n] ok)
+There is no CPU implementation behind these classes: constructing a Suite needs a CUDA device."""
+from dataclasses import dataclass
+
+import numpy as np
+
+from .engine import Engine, BANDERSNATCH, ED25519, P256
+
+
+class Error(Exception):
+    """mirror of ark_vrf::Error for whole-call failures; per-item failures come back as flags"""
+
+
+@dataclass
+class Suite:
+    """ark_vrf::Suite: one ciphersuite bound to one GPU context"""
+    suite_id: int
+    engine: Engine
+
+    @classmethod
+    def bandersnatch(cls, device=0):
+        return cls(BANDERSNATCH, Engine(device))
+
+    @classmethod
+    def ed25519(cls, device=0):
+        return cls(ED25519, Engine(device))
+
+    @classmethod
+    def secp256r1(cls, device=0):
+        return cls(P256, Engine(device))
+
+    @property
+    def CHALLENGE_LEN(self):
+        return self.engine.challenge_len(self.suite_id)
+
+    # Suite::data_to_point / nonce / challenge / point_to_hash live on the typed values below
+    def data_to_point(self, datas):
+        pts, ok = self.engine.data_to_point(self.suite_id, datas)
+        return pts, ok
+
+
+@dataclass
+class Public:
+    suite: Suite
+    points: np.ndarray          # (n, 64)
+
+    def verify(self, input, output, ad, proof):
+        """ietf::Verifier::verify -> uint8[n]"""
+        return self.suite.engine.ietf_verify(self.suite.suite_id, self.points, input.points, output.points, proof.c, proof.s, ad)
+
+    def encode(self):
+        return self.suite.engine.point_encode(self.suite.suite_id, self.points)
+
+
+@dataclass
+class Input:
+    suite: Suite
+    points: np.ndarray
+
+    @classmethod
+    def new(cls, suite, datas):
+        """Input::new(data) = Suite::data_to_point; returns (Input, ok flags) for Option<Input>"""
+        pts, ok = suite.engine.data_to_point(suite.suite_id, datas)
+        return cls(suite, pts), ok
+
+
+@dataclass
+class Output:
+    suite: Suite
+    points: np.ndarray
+
+    def hash(self):
+        """Output::hash = Suite::point_to_hash"""
+        return self.suite.engine.point_to_hash(self.suite.suite_id, self.points)
+
+
+@dataclass
+class IetfProof:
+    c: np.ndarray               # (n, 32) little-endian scalars
+    s: np.ndarray
+
+    def to_bytes(self, suite):
+        """codec layout c (cLen bytes) || s (32 bytes), in the suite's scalar encoding"""
+        cl = suite.CHALLENGE_LEN
+        if suite.suite_id == P256:
+            return np.concatenate([self.c[:, :cl][:, ::-1], self.s[:, ::-1]], axis=1)
+        return np.concatenate([self.c[:, :cl], self.s], axis=1)
+
+
+@dataclass
+class PedersenProof:
+    raw: np.ndarray             # (n, 256): pk_com || r || ok || s || sb
+
+    pk_com = property(lambda self: self.raw[:, 0:64])
+    r = property(lambda self: self.raw[:, 64:128])
+    ok = property(lambda self: self.raw[:, 128:192])
+    s = property(lambda self: self.raw[:, 192:224])
+    sb = property(lambda self: self.raw[:, 224:256])
+
+
+@dataclass
+class Secret:
+    suite: Suite
+    scalars: np.ndarray         # (n, 32)
+    public_points: np.ndarray   # (n, 64)
+
+    @classmethod
+    def from_seed(cls, suite, seeds):
+        sk, pk = suite.engine.secret_from_seed(suite.suite_id, seeds)
+        return cls(suite, sk, pk)
+
+    def public(self):
+        return Public(self.suite, self.public_points)
+
+    def output(self, input):
+        return Output(self.suite, self.suite.engine.output(self.suite.suite_id, self.scalars, input.points))
+
+    def prove(self, input, output, ad=None):
+        """ietf::Prover::prove"""
+        c, s = self.suite.engine.ietf_prove(self.suite.suite_id, self.scalars, input.points, output.points, ad)
+        return IetfProof(c, s)
+
+    def pedersen_prove(self, input, output, ad=None):
+        """pedersen::Prover::prove -> (Proof, blinding)"""
+        pr, bl = self.suite.engine.pedersen_prove(self.suite.suite_id, self.scalars, input.points, output.points, ad)
+        return PedersenProof(pr), bl
+
+
+def pedersen_verify(suite, input, output, ad, proof):
+    """pedersen::Verifier::verify (needs no public key) -> uint8[n]"""
+    return suite.engine.pedersen_verify(suite.suite_id, input.points, output.points, proof.raw, ad)
+
+
+def ring_commitment_msm(suite_or_engine, bases, scalar_columns):
+    """the three KZG commitments behind RingContext::verifier_key: one MSM per column over the SRS bases"""
+    eng = suite_or_engine.engine if isinstance(suite_or_engine, Suite) else suite_or_engine
+    cols = np.concatenate([np.asarray(c, np.uint8).reshape(-1, 32) for c in scalar_columns])
+    return eng.msm_g1(bases, cols, len(scalar_columns))

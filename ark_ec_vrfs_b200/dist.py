@@ -1,0 +1,50 @@
+"""Multi-GPU plumbing: one process per GPU under torch.distributed.
+
+VRF batches are independent items: rank g takes the contiguous index range [g*n/G, (g+1)*n/G) and there is
+NO data-path collective.  The MSM splits by point range; each rank produces one projective partial per
+column (144 bytes) and the only exchange is an all-gather of those bytes (NCCL on GPU boxes, gloo in the
+CPU tests), folded by `Engine.g1_sum_partials`."""
+import numpy as np
+
+
+def shard_range(n, rank, world):
+    """contiguous, balanced, covering: the ranges of ranks 0..world-1 partition [0, n)"""
+    return (n * rank) // world, (n * (rank + 1)) // world
+
+
+def shard_arrays(arrays, rank, world):
+    n = len(arrays[0])
+    lo, hi = shard_range(n, rank, world)
+    return [a[lo:hi] for a in arrays]
+
+
+def shard_var(items, rank, world):
+    if items is None:
+        return None
+    lo, hi = shard_range(len(items), rank, world)
+    return items[lo:hi]
+
+
+def gather_bytes(local: np.ndarray, group=None, device=None):
+    """all-gather equal-sized uint8 arrays; returns (world, ...) on every rank"""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    t = torch.from_numpy(np.ascontiguousarray(local))
+    if device is not None:
+        t = t.to(device)
+    outs = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(outs, t, group=group)
+    return np.stack([o.cpu().numpy() for o in outs])
+
+
+def msm_g1_sharded(engine, bases, scalars, n_columns, group=None, device=None):
+    """each rank passes the FULL inputs; computes its point range; all ranks return the same affine result"""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    n = len(bases)
+    lo, hi = shard_range(n, rank, world)
+    sc = np.asarray(scalars, np.uint8).reshape(n_columns, n, 32)[:, lo:hi].reshape(-1, 32)
+    part = engine.msm_g1_partial(bases[lo:hi], sc, n_columns)
+    parts = gather_bytes(part, group, device)
+    return engine.g1_sum_partials(parts, n_columns)
