@@ -16,6 +16,7 @@
 // one (secp256r1) through the Grp<C> adapter below.
 #pragma once
 #include "te.cuh"
+#include "te29.cuh"
 #include "sw.cuh"
 #include "scalar.cuh"
 
@@ -30,6 +31,12 @@ struct uint4 { uint32_t x, y, z, w; };
 #define VRFS_HD
 #endif
 
+template <class F> HD_INLINE void store_fp_xyz(uint32_t* o, const F& X, const F& Y, const F& Z) {   // 3N limbs, 16-byte aligned
+  uint4* d = reinterpret_cast<uint4*>(o);
+  const uint4 *sx = reinterpret_cast<const uint4*>(X.v), *sy = reinterpret_cast<const uint4*>(Y.v), *sz = reinterpret_cast<const uint4*>(Z.v);
+  constexpr int Q = F::N / 4;
+  for (int i = 0; i < Q; i++) { d[i] = sx[i]; d[Q + i] = sy[i]; d[2 * Q + i] = sz[i]; }
+}
 template <class T> HD_INLINE void copy_words16(T* dst, const T* src_) {  // sizeof(T) % 16 == 0, both 16-byte aligned
   const uint4* s = reinterpret_cast<const uint4*>(src_);
   uint4* d = reinterpret_cast<uint4*>(dst);
@@ -55,11 +62,42 @@ template <class C> struct Grp<C, true> {
   static HD_INLINE void dbl4(Pt* acc) { te_dbl<C>(acc, acc, false); te_dbl<C>(acc, acc, false); te_dbl<C>(acc, acc, false); te_dbl<C>(acc, acc, true); }
   static HD_INLINE void dbl(Pt* acc) { te_dbl<C>(acc, acc, true); }
   static HD_INLINE void add(Pt* r, const Pt* p, const Pt* q) { te_add<C>(r, p, q); }
+  static HD_INLINE void endo(Pt* r, const Pt* p) { band_endo(reinterpret_cast<TEPoint<BandCurve>*>(r), reinterpret_cast<const TEPoint<BandCurve>*>(p)); }
   static HD_INLINE void to_fix(FixEntry& e, const Pt& P) {
     typename C::F zi = inv(P.Z);
     e.x = P.X * zi; e.y = P.Y * zi; e.dt = e.x * e.y * C::d();
   }
+  static HD_INLINE void store_xyz(uint32_t* o, const Pt& P) { store_fp_xyz(o, P.X, P.Y, P.Z); }
 };
+// optional: Bandersnatch on the unsaturated 9x29-bit field (f29.cuh / te29.cuh); Fp<BlsFr> only at the boundary
+#ifndef VRFS_BAND_F29
+#define VRFS_BAND_F29 0   // measured SLOWER than the saturated path on B200 (IMAD.WIDE itself is half-rate): kept as an experiment
+#endif
+#if VRFS_BAND_F29
+template <> struct Grp<BandCurve, true> {
+  typedef BandCurve C;
+  typedef TE29Point Pt;
+  typedef TE29Cached Entry;
+  typedef TE29AffCached FixEntry;
+  static constexpr int SPLIT = 2, WINDOWS = 32, KB_LIMBS = 4, FIX_WINDOWS = 32;
+  static HD_INLINE void set_identity(Pt& P) { te29_set_identity(P); }
+  static HD_INLINE void from_affine(Pt& P, const C::F& x, const C::F& y) { P.X = f29_from_fp(x); P.Y = f29_from_fp(y); P.Z = f29_one(); P.T = f29_mul(P.X, P.Y); }
+  static HD_INLINE bool on_curve(const C::F& x, const C::F& y) { return te_on_curve<C>(x, y); }
+  static HD_INLINE void to_entry(Entry& e, const Pt& P) { te29_to_cached(e, P); }
+  static HD_INLINE void add_entry(Pt* acc, const Entry* e, bool negate) { te29_add_cached(acc, acc, e, negate); }
+  static HD_INLINE void add_fix(Pt* acc, const FixEntry* e, bool negate) { te29_madd(acc, acc, e, negate); }
+  static HD_INLINE void dbl4(Pt* acc) { te29_dbl(acc, acc, false); te29_dbl(acc, acc, false); te29_dbl(acc, acc, false); te29_dbl(acc, acc, true); }
+  static HD_INLINE void dbl(Pt* acc) { te29_dbl(acc, acc, true); }
+  static HD_INLINE void add(Pt* r, const Pt* p, const Pt* q) { Entry e; te29_to_cached(e, *q); te29_add_cached(r, p, &e, false); }
+  static HD_INLINE void endo(Pt* r, const Pt* p) { te29_endo(r, p); }
+  static HD_INLINE void to_fix(FixEntry& e, const Pt& P) {
+    C::F X = f29_to_fp(P.X), Y = f29_to_fp(P.Y), Z = f29_to_fp(P.Z);
+    C::F zi = inv(Z), x = X * zi, y = Y * zi;
+    e.x = f29_from_fp(x); e.y = f29_from_fp(y); e.dt = f29_from_fp(x * y * C::d()); e.pad = 0;
+  }
+  static HD_INLINE void store_xyz(uint32_t* o, const Pt& P) { store_fp_xyz(o, f29_to_fp(P.X), f29_to_fp(P.Y), f29_to_fp(P.Z)); }
+};
+#endif
 template <class C> struct Grp<C, false> {
   typedef SWPoint<C> Pt;
   typedef SWPoint<C> Entry;
@@ -82,6 +120,7 @@ template <class C> struct Grp<C, false> {
     typename C::F zi = inv(P.Z);
     e.X = P.X * zi; e.Y = select(inf, C::F::one(), P.Y * zi); e.Z = select(inf, C::F::zero(), C::F::one());
   }
+  static HD_INLINE void store_xyz(uint32_t* o, const Pt& P) { store_fp_xyz(o, P.X, P.Y, P.Z); }
 };
 static constexpr int TBL_ENTRIES = 9;     // 0*P .. 8*P
 static constexpr int FIX_ENTRIES = 129;   // 0 .. 128 times 256^w * B
@@ -169,7 +208,7 @@ HD_INLINE bool lincomb_item(const LincombArgs& A, uint32_t item, typename Grp<C>
         kneg[2 * v] = h1.neg ^ neg; kneg[2 * v + 1] = h2.neg ^ neg;
         build_table<C>(slab + (2 * v) * TBL_ENTRIES, B);
         typename G::Pt E;
-        band_endo(reinterpret_cast<TEPoint<BandCurve>*>(&E), reinterpret_cast<const TEPoint<BandCurve>*>(&B));
+        G::endo(&E, &B);
         build_table<C>(slab + (2 * v + 1) * TBL_ENTRIES, E);
       } else {
         for (int i = 0; i < G::KB_LIMBS; i++) kb[v][i] = i < 8 ? k[i] : 0u;

@@ -5,13 +5,17 @@
 // the window size, signed digits and bucket order used here need not match ark-ec's.
 //
 // Pipeline (all on the context's stream):
-//   k_msm_prep_bases   canonical LE affine -> Montgomery affine (identity = all zero)
-//   k_msm_histogram    signed radix-2^c digits of every scalar; per-(column, window, bucket) counts
-//   k_msm_scan         exclusive scan of the counts inside each (column, window) segment
-//   k_msm_scatter      point indices (+ sign bit) grouped by bucket
-//   k_msm_accumulate   one thread per bucket: complete additions of its points
-//   k_msm_window       one block per (column, window): chunked running sums  sum_j j*B_j, shared-memory tree
-//   k_msm_final        one thread per column: Horner over the windows; projective partial or affine out
+//   k_msm_prep_bases      canonical LE affine -> Montgomery affine (identity = all zero)
+//   k_msm_prepare         (prepared mode, once per SRS) Q[w][i] = 2^(c w) P_i, so all windows share one bucket set
+//   k_msm_histogram       signed radix-2^c digits of every scalar; per-(segment, bucket) counts
+//   k_msm_scan            exclusive scan of the counts inside each segment; lists buckets with > MSM_BIG entries
+//   k_msm_scatter         point indices (+ sign bit) grouped by bucket (counting sort)
+//   k_msm_accumulate      one thread per bucket: complete additions of its points
+//   k_msm_accumulate_big  one block per oversized bucket (top window / skewed scalar columns such as ring selectors)
+//   k_msm_window          one block per segment: chunked running sums  sum_j j*B_j, shared-memory tree
+//   k_msm_final           one thread per column: Horner over the windows (stateless mode only); partial or affine out
+// Stateless mode (vrfs_msm_g1_bls12_381): segment = (column, window).  Prepared mode (vrfs_msm_g1_prepare + _prepared,
+// the analogue of RingContext holding the SRS): segment = column, no Horner chain (255 dependent doublings ~ 2.5 ms).
 #pragma once
 #include "lincomb.cuh"
 
@@ -23,17 +27,28 @@ struct G1Aff { Fq381 x, y; };   // Montgomery form; x = y = 0 encodes the identi
 
 struct MsmPlan {
   uint32_t n, ncol;
-  int c, windows, nb;            // window bits, window count, buckets per window (2^(c-1))
+  int c, windows, nb;            // window bits, digit windows per scalar, buckets per segment (2^(c-1))
+  int prepared;                  // 1: bases pre-multiplied by 2^(c*w) -> ONE bucket segment per column, no Horner
+  int seg_windows;               // segments per column: `windows` (stateless) or 1 (prepared)
+  int chunk;                     // buckets per thread in the segment reduction
+  int tpb;                       // threads cooperating on one bucket in k_msm_accumulate (power of two <= 32)
+  uint32_t big;                  // buckets with more entries than this go to k_msm_accumulate_big
 };
-VRFS_HD inline MsmPlan msm_plan(uint32_t n, uint32_t ncol) {
-  MsmPlan p; p.n = n; p.ncol = ncol;
+VRFS_HD inline MsmPlan msm_plan(uint32_t n, uint32_t ncol, int prepared) {
+  MsmPlan p; p.n = n; p.ncol = ncol; p.prepared = prepared;
   int lg = 0; while ((1u << (lg + 1)) <= n) lg++;
-  p.c = lg <= 9 ? 7 : lg <= 11 ? 9 : lg <= 13 ? 11 : lg <= 15 ? 12 : 13;
+  if (prepared) p.c = lg <= 8 ? 8 : lg <= 10 ? 10 : lg <= 12 ? 12 : lg <= 14 ? 14 : 16;
+  else p.c = lg <= 9 ? 7 : lg <= 11 ? 9 : lg <= 13 ? 11 : lg <= 15 ? 12 : 13;
   p.windows = (255 + p.c) / p.c;          // 255 scalar bits + the top carry of the signed recoding
   p.nb = 1 << (p.c - 1);
+  p.seg_windows = prepared ? 1 : p.windows;
+  p.chunk = 16;
+  uint64_t avg = ((uint64_t)n * (prepared ? p.windows : 1)) / p.nb;      // expected entries per bucket for uniform digits
+  p.tpb = 1; while (p.tpb < 32 && avg / p.tpb > 24) p.tpb *= 2;
+  p.big = (uint32_t)(8 * (avg + 8));
   return p;
 }
-#define MSM_CHUNK 16   // buckets per thread in the window reduction
+#define MSM_BIG_THREADS 128
 
 HD_INLINE void g1_load_aff(G1Pt& P, const G1Aff* a, bool negate) {
   uint4* d = reinterpret_cast<uint4*>(&P);
@@ -43,6 +58,20 @@ HD_INLINE void g1_load_aff(G1Pt& P, const G1Aff* a, bool negate) {
   P.Y = cneg(P.Y, negate);
   P.Z = select(inf, Fq381::zero(), Fq381::one());
   P.Y = select(inf, Fq381::one(), P.Y);
+}
+HD_INLINE void g1_load_proj(G1Pt& P, const G1Pt* a, bool negate) {
+  copy_words16(&P, a);
+  P.Y = cneg(P.Y, negate);
+}
+// r = 2p, complete, a = 0 (RCB16 Algorithm 9: 6M + 2S + 1 mul_b3); checked against affine arithmetic in this container
+HD_NOINLINE void g1_dbl(G1Pt* r, const G1Pt* p) {
+  Fq381 t0 = sqr(p->Y), Z3 = dbl(dbl(dbl(t0))), t1 = p->Y * p->Z, t2 = G1Curve::mul_b3(sqr(p->Z));
+  Fq381 X3 = t2 * Z3, Y3 = t0 + t2;
+  Z3 = t1 * Z3;
+  t0 = t0 - (dbl(t2) + t2);
+  Y3 = t0 * Y3 + X3;
+  X3 = dbl(t0 * (p->X * p->Y));
+  r->X = X3; r->Y = Y3; r->Z = Z3;
 }
 // signed radix-2^c digit w of the canonical scalar k (8 limbs): digits in [-2^(c-1), 2^(c-1)]
 HD_INLINE int msm_digit(const uint32_t* k, int w, int c, int& carry) {
@@ -75,7 +104,19 @@ __global__ void __launch_bounds__(128) k_msm_prep_bases(uint32_t n, const uint8_
   o.x = to_mont<BlsFq>(rx); o.y = to_mont<BlsFq>(ry);
   out[i] = o;
 }
-// counts[(col*W + w)*nb + (|d|-1)]++
+// prepared bases (the RingContext analogue: the SRS is fixed): Q[w*n + i] = 2^(c*w) * P_i, projective
+__global__ void __launch_bounds__(128) k_msm_prepare(uint32_t n, int c, int windows, const G1Aff* aff, G1Pt* Q) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  G1Pt P;
+  g1_load_aff(P, &aff[i], false);
+  copy_words16(&Q[i], &P);
+  for (int w = 1; w < windows; w++) {
+    for (int k = 0; k < c; k++) g1_dbl(&P, &P);
+    copy_words16(&Q[(size_t)w * n + i], &P);
+  }
+}
+// counts[seg*nb + (|d|-1)]++ ; seg = col*seg_windows + (prepared ? 0 : w)
 __global__ void __launch_bounds__(128) k_msm_histogram(MsmPlan p, const uint8_t* scalars, uint32_t* counts) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= p.n * p.ncol) return;
@@ -85,11 +126,12 @@ __global__ void __launch_bounds__(128) k_msm_histogram(MsmPlan p, const uint8_t*
   int carry = 0;
   for (int w = 0; w < p.windows; w++) {
     int d = msm_digit(k, w, p.c, carry);
-    if (d != 0) atomicAdd(&counts[((size_t)col * p.windows + w) * p.nb + (d < 0 ? -d : d) - 1], 1u);
+    size_t seg = (size_t)col * p.seg_windows + (p.prepared ? 0 : w);
+    if (d != 0) atomicAdd(&counts[seg * p.nb + (d < 0 ? -d : d) - 1], 1u);
   }
 }
-// one block per (col, window): exclusive scan of nb counts -> offsets (relative to the segment), cursors zeroed
-__global__ void __launch_bounds__(256) k_msm_scan(MsmPlan p, const uint32_t* counts, uint32_t* offsets) {
+// one block per segment: exclusive scan of nb counts -> offsets (relative to the segment); also lists the big buckets
+__global__ void __launch_bounds__(256) k_msm_scan(MsmPlan p, const uint32_t* counts, uint32_t* offsets, uint32_t* big_list, uint32_t* big_count) {
   __shared__ uint32_t part[256];
   const uint32_t seg = blockIdx.x;
   const uint32_t* c = counts + (size_t)seg * p.nb;
@@ -103,82 +145,150 @@ __global__ void __launch_bounds__(256) k_msm_scan(MsmPlan p, const uint32_t* cou
   if (threadIdx.x == 0) { uint32_t run = 0; for (int i = 0; i < 256; i++) { uint32_t v = part[i]; part[i] = run; run += v; } }
   __syncthreads();
   uint32_t run = part[threadIdx.x];
-  for (int i = lo; i < hi; i++) { o[i] = run; run += c[i]; }
+  for (int i = lo; i < hi; i++) {
+    o[i] = run; run += c[i];
+    if (c[i] > p.big) big_list[atomicAdd(big_count, 1u)] = seg * p.nb + i;
+  }
 }
-// list[seg*n + offsets[bucket] + pos] = i | sign << 31
+// list[seg*seg_len + offsets[bucket] + pos] = point index | sign << 31
 __global__ void __launch_bounds__(128) k_msm_scatter(MsmPlan p, const uint8_t* scalars, const uint32_t* offsets, uint32_t* cursors, uint32_t* list) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= p.n * p.ncol) return;
   uint32_t col = t / p.n, i = t % p.n;
   uint32_t k[8];
   msm_load_scalar(k, scalars + (size_t)32 * t);
+  const size_t seg_len = (size_t)p.n * (p.prepared ? p.windows : 1);
   int carry = 0;
   for (int w = 0; w < p.windows; w++) {
     int d = msm_digit(k, w, p.c, carry);
     if (d == 0) continue;
-    size_t seg = (size_t)col * p.windows + w;
+    size_t seg = (size_t)col * p.seg_windows + (p.prepared ? 0 : w);
     size_t b = seg * p.nb + (d < 0 ? -d : d) - 1;
     uint32_t pos = atomicAdd(&cursors[b], 1u);
-    list[seg * p.n + offsets[b] + pos] = i | (d < 0 ? 0x80000000u : 0u);
+    uint32_t idx = p.prepared ? (uint32_t)w * p.n + i : i;
+    list[seg * seg_len + offsets[b] + pos] = idx | (d < 0 ? 0x80000000u : 0u);
   }
 }
-// one thread per bucket
-__global__ void __launch_bounds__(128) k_msm_accumulate(MsmPlan p, const G1Aff* bases, const uint32_t* counts, const uint32_t* offsets,
+template <bool PREP> __device__ __forceinline__ void msm_load_entry(G1Pt& q, const void* bases, uint32_t e) {
+  if (PREP) g1_load_proj(q, reinterpret_cast<const G1Pt*>(bases) + (e & 0x7fffffffu), (e >> 31) != 0);
+  else g1_load_aff(q, reinterpret_cast<const G1Aff*>(bases) + (e & 0x7fffffffu), (e >> 31) != 0);
+}
+// p.tpb threads per bucket (strided over its entries, shared-memory tree inside the group); buckets above p.big
+// entries are left to k_msm_accumulate_big
+template <bool PREP>
+__global__ void __launch_bounds__(128) k_msm_accumulate(MsmPlan p, const void* bases, const uint32_t* counts, const uint32_t* offsets,
                                                          const uint32_t* list, G1Pt* buckets) {
-  size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  size_t total = (size_t)p.ncol * p.windows * p.nb;
-  if (b >= total) return;
-  size_t seg = b / p.nb;
-  const uint32_t* l = list + seg * p.n + offsets[b];
-  uint32_t cnt = counts[b];
+  __shared__ uint4 sh_raw[128 * sizeof(G1Pt) / 16];
+  G1Pt* sh = reinterpret_cast<G1Pt*>(sh_raw);
+  const size_t total = (size_t)p.ncol * p.seg_windows * p.nb;
+  const uint32_t lane = threadIdx.x % p.tpb;
+  const size_t b = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) / p.tpb;
+  const bool live = b < total;
+  uint32_t cnt = live ? counts[b] : 0u;
+  if (cnt > p.big) cnt = 0;                       // handled by the big path (which also writes the bucket)
   G1Pt acc; sw_set_identity(acc);
-  for (uint32_t j = 0; j < cnt; j++) {
-    uint32_t e = l[j];
-    G1Pt q;
-    g1_load_aff(q, &bases[e & 0x7fffffffu], (e >> 31) != 0);
-    sw_add<G1Curve>(&acc, &acc, &q);
+  if (cnt) {
+    const size_t seg = b / p.nb;
+    const size_t seg_len = (size_t)p.n * (p.prepared ? p.windows : 1);
+    const uint32_t* l = list + seg * seg_len + offsets[b];
+    for (uint32_t j = lane; j < cnt; j += p.tpb) {
+      G1Pt q;
+      msm_load_entry<PREP>(q, bases, l[j]);
+      sw_add<G1Curve>(&acc, &acc, &q);
+    }
   }
-  buckets[b] = acc;
+  if (p.tpb > 1) {
+    copy_words16(&sh[threadIdx.x], &acc);
+    __syncthreads();
+    for (int stride = p.tpb >> 1; stride > 0; stride >>= 1) {
+      if ((int)lane < stride) { G1Pt y; copy_words16(&y, &sh[threadIdx.x + stride]); sw_add<G1Curve>(&acc, &acc, &y); copy_words16(&sh[threadIdx.x], &acc); }
+      __syncthreads();
+    }
+  }
+  if (live && lane == 0 && counts[b] <= p.big) copy_words16(&buckets[b], &acc);
+}
+// one block per big bucket: strided partial sums + shared-memory tree
+template <bool PREP>
+__global__ void __launch_bounds__(MSM_BIG_THREADS) k_msm_accumulate_big(MsmPlan p, const void* bases, const uint32_t* counts, const uint32_t* offsets,
+                                                                         const uint32_t* list, const uint32_t* big_list, const uint32_t* big_count, G1Pt* buckets) {
+  __shared__ uint4 sh_raw[MSM_BIG_THREADS * sizeof(G1Pt) / 16];
+  G1Pt* sh = reinterpret_cast<G1Pt*>(sh_raw);
+  const uint32_t nbig = *big_count;
+  for (uint32_t bi = blockIdx.x; bi < nbig; bi += gridDim.x) {
+    const size_t b = big_list[bi];
+    const size_t seg = b / p.nb;
+    const size_t seg_len = (size_t)p.n * (p.prepared ? p.windows : 1);
+    const uint32_t* l = list + seg * seg_len + offsets[b];
+    const uint32_t cnt = counts[b];
+    G1Pt acc; sw_set_identity(acc);
+    for (uint32_t j = threadIdx.x; j < cnt; j += MSM_BIG_THREADS) {
+      G1Pt q;
+      msm_load_entry<PREP>(q, bases, l[j]);
+      sw_add<G1Curve>(&acc, &acc, &q);
+    }
+    copy_words16(&sh[threadIdx.x], &acc);
+    __syncthreads();
+    for (int stride = MSM_BIG_THREADS >> 1; stride > 0; stride >>= 1) {
+      if ((int)threadIdx.x < stride) { G1Pt x, y; copy_words16(&x, &sh[threadIdx.x]); copy_words16(&y, &sh[threadIdx.x + stride]); sw_add<G1Curve>(&x, &x, &y); copy_words16(&sh[threadIdx.x], &x); }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) copy_words16(&buckets[b], &sh[0]);
+    __syncthreads();
+  }
 }
 // r = k * p for a small non-negative k (double-and-add, MSB first)
 __device__ __forceinline__ void g1_mul_small(G1Pt& r, const G1Pt& p, uint32_t k) {
   sw_set_identity(r);
   for (int bit = 31 - __clz(k | 1u); bit >= 0; bit--) {
-    sw_add<G1Curve>(&r, &r, &r);
+    g1_dbl(&r, &r);
     if ((k >> bit) & 1u) sw_add<G1Curve>(&r, &r, &p);
   }
 }
-// one block per (col, window), nb / MSM_CHUNK threads: window sum = sum_{j=1..nb} j * B_j
-__global__ void k_msm_window(MsmPlan p, const G1Pt* buckets, G1Pt* window_sums) {
-  extern __shared__ uint4 smem_raw[];
-  G1Pt* sh = reinterpret_cast<G1Pt*>(smem_raw);
-  const uint32_t seg = blockIdx.x, t = threadIdx.x;
-  const G1Pt* B = buckets + (size_t)seg * p.nb;
-  const int lo = t * MSM_CHUNK;            // bucket index j-1 in [lo, lo + CHUNK)
+// segment sum = sum_{j=1..nb} j * B_j in two stages.  Stage 1: one thread per chunk of p.chunk buckets (running sums),
+// partial[seg][t] = sum over its chunk of j * B_j.  Stage 2: one block per segment tree-sums the nb / chunk partials.
+__global__ void __launch_bounds__(128) k_msm_window_chunks(MsmPlan p, const G1Pt* buckets, G1Pt* partials) {
+  const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t per_seg = p.nb / p.chunk;
+  const size_t segs = (size_t)p.ncol * p.seg_windows;
+  if (g >= segs * per_seg) return;
+  const size_t seg = g / per_seg;
+  const uint32_t t = (uint32_t)(g % per_seg);
+  const G1Pt* B = buckets + seg * p.nb;
+  const int lo = t * p.chunk;              // bucket index j-1 in [lo, lo + chunk)
   G1Pt run, tot; sw_set_identity(run); sw_set_identity(tot);
-  for (int j = lo + MSM_CHUNK - 1; j >= lo; j--) {
-    G1Pt q = B[j];
+  for (int j = lo + p.chunk - 1; j >= lo; j--) {
+    G1Pt q; copy_words16(&q, &B[j]);
     sw_add<G1Curve>(&run, &run, &q);
     sw_add<G1Curve>(&tot, &tot, &run);
   }
   // tot = sum (j - lo + 1) * B_j (bucket value j+1 at index j)  ->  add lo * run
   if (lo > 0) { G1Pt m; g1_mul_small(m, run, (uint32_t)lo); sw_add<G1Curve>(&tot, &tot, &m); }
-  sh[t] = tot;
+  copy_words16(&partials[g], &tot);
+}
+__global__ void __launch_bounds__(256) k_msm_window_sum(MsmPlan p, const G1Pt* partials, G1Pt* window_sums) {
+  __shared__ uint4 sh_raw[256 * sizeof(G1Pt) / 16];
+  G1Pt* sh = reinterpret_cast<G1Pt*>(sh_raw);
+  const uint32_t seg = blockIdx.x, t = threadIdx.x, per_seg = p.nb / p.chunk;
+  const G1Pt* P = partials + (size_t)seg * per_seg;
+  G1Pt acc; sw_set_identity(acc);
+  for (uint32_t j = t; j < per_seg; j += 256) { G1Pt q; copy_words16(&q, &P[j]); sw_add<G1Curve>(&acc, &acc, &q); }
+  copy_words16(&sh[t], &acc);
   __syncthreads();
-  for (int stride = blockDim.x >> 1; stride > 0; stride >>= 1) {
-    if ((int)t < stride) { G1Pt a = sh[t], b = sh[t + stride]; sw_add<G1Curve>(&a, &a, &b); sh[t] = a; }
+  for (int stride = 128; stride > 0; stride >>= 1) {
+    if ((int)t < stride) { G1Pt y; copy_words16(&y, &sh[t + stride]); sw_add<G1Curve>(&acc, &acc, &y); copy_words16(&sh[t], &acc); }
     __syncthreads();
   }
-  if (t == 0) window_sums[seg] = sh[0];
+  if (t == 0) copy_words16(&window_sums[seg], &sh[0]);
 }
-// Horner over windows; out_mode 0: affine LE canonical (96 B, identity = zeros); 1: projective X,Y,Z LE canonical (144 B)
+// combine the segments of a column (Horner over windows when not prepared);
+// out_mode 0: affine LE canonical (96 B, identity = zeros); 1: projective X,Y,Z LE canonical (144 B)
 __global__ void k_msm_final(MsmPlan p, const G1Pt* window_sums, uint8_t* out, int out_mode) {
   uint32_t col = blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= p.ncol) return;
-  const G1Pt* W = window_sums + (size_t)col * p.windows;
-  G1Pt acc = W[p.windows - 1];
-  for (int w = p.windows - 2; w >= 0; w--) {
-    for (int k = 0; k < p.c; k++) sw_add<G1Curve>(&acc, &acc, &acc);
+  const G1Pt* W = window_sums + (size_t)col * p.seg_windows;
+  G1Pt acc = W[p.seg_windows - 1];
+  for (int w = p.seg_windows - 2; w >= 0; w--) {
+    for (int k = 0; k < p.c; k++) g1_dbl(&acc, &acc);
     G1Pt q = W[w];
     sw_add<G1Curve>(&acc, &acc, &q);
   }

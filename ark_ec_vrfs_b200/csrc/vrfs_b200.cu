@@ -15,7 +15,13 @@ using namespace vrfs;
 // =================================================================================================
 // kernels
 // =================================================================================================
-#define LINCOMB_THREADS 128
+// launch shape of the lincomb kernels: measured on B200 (tools/cfg_probe.sh) 256x2 > 128x5 > 128x4 > 128x3, all within 4 %
+#ifndef LINCOMB_THREADS
+#define LINCOMB_THREADS 256
+#endif
+#ifndef LINCOMB_MINBLOCKS
+#define LINCOMB_MINBLOCKS 2
+#endif
 
 // one fixed-base table (K8): thread (w, d) computes (d * 256^w) * B in affine cached form
 template <class C>
@@ -31,17 +37,13 @@ __global__ void k_fixed_table(typename Grp<C>::FixEntry* out, int blinding) {
 // K7/K8/K9a: R_i = sum var + sum fixed, projective out.  Persistent grid-stride so that the window-table
 // slab is per resident thread (L2-resident), not per item.
 template <class C, int NV, int NF>
-__global__ void __launch_bounds__(LINCOMB_THREADS, 4) k_lincomb(LincombArgs A) {
+__global__ void __launch_bounds__(LINCOMB_THREADS, LINCOMB_MINBLOCKS) k_lincomb(LincombArgs A) {
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
   typename Grp<C>::Entry* slab = reinterpret_cast<typename Grp<C>::Entry*>(A.slab + (size_t)tid * slab_bytes<C>(NV));
   for (uint32_t item = tid; item < A.n; item += nthreads) {
     typename Grp<C>::Pt acc;
     bool ok = lincomb_item<C, NV, NF>(A, item, slab, acc);
-    uint4* o = reinterpret_cast<uint4*>(A.out_xyz + (size_t)item * 24);
-    const uint4* sx = reinterpret_cast<const uint4*>(acc.X.v);
-    const uint4* sy = reinterpret_cast<const uint4*>(acc.Y.v);
-    const uint4* sz = reinterpret_cast<const uint4*>(acc.Z.v);
-    o[0] = sx[0]; o[1] = sx[1]; o[2] = sy[0]; o[3] = sy[1]; o[4] = sz[0]; o[5] = sz[1];
+    Grp<C>::store_xyz(A.out_xyz + (size_t)item * 24, acc);
     if (A.valid != nullptr && !ok) A.valid[item] = 0;
   }
 }
@@ -65,33 +67,36 @@ template <int VARIANT>
 __global__ void __launch_bounds__(256) k_mac_bench(uint32_t* out, int iters, unsigned long long* cycles) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long c0 = clock64();
-  if (VARIANT == 0) {          // mad.wide.u32, 8 independent 64-bit accumulators
-    unsigned long long a0 = t, a1 = t + 1, a2 = t + 2, a3 = t + 3, a4 = t + 4, a5 = t + 5, a6 = t + 6, a7 = t + 7;
-    uint32_t x = t * 2654435761u + 12345u, y = t ^ 0x9e3779b9u;
+  // NOTE: every multiply below takes one operand from its own accumulator.  With loop-invariant multiplicands ptxas
+  // hoists the product and the loop measures 64-bit ADDs (that mistake gave a bogus 18.5 T "peak" in profiles/r1a_*).
+  if (VARIANT == 0) {          // IMAD.WIDE.U32: acc = lo(acc) * y + acc, 8 independent chains
+    unsigned long long a[8];
+    for (int k = 0; k < 8; k++) a[k] = ((unsigned long long)(t * 2654435761u + k) << 32) | (t + k * 40503u + 1u);
+    uint32_t y = (t ^ 0x9e3779b9u) | 1u;
 #pragma unroll 1
     for (int i = 0; i < iters; i++) {
 #pragma unroll
-      for (int r = 0; r < 4; r++) {
-        asm volatile("mad.wide.u32 %0, %8, %9, %0; mad.wide.u32 %1, %8, %9, %1; mad.wide.u32 %2, %8, %9, %2; mad.wide.u32 %3, %8, %9, %3;"
-                     "mad.wide.u32 %4, %8, %9, %4; mad.wide.u32 %5, %8, %9, %5; mad.wide.u32 %6, %8, %9, %6; mad.wide.u32 %7, %8, %9, %7;"
-                     : "+l"(a0), "+l"(a1), "+l"(a2), "+l"(a3), "+l"(a4), "+l"(a5), "+l"(a6), "+l"(a7) : "r"(x), "r"(y));
-      }
+      for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int k = 0; k < 8; k++) a[k] = (unsigned long long)(uint32_t)a[k] * y + a[k];
     }
-    unsigned long long s = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+    unsigned long long s = 0;
+    for (int k = 0; k < 8; k++) s ^= a[k];
     out[t] = (uint32_t)s ^ (uint32_t)(s >> 32);
-  } else if (VARIANT == 1) {   // mad.lo.u32, 8 independent 32-bit accumulators
-    uint32_t a0 = t, a1 = t + 1, a2 = t + 2, a3 = t + 3, a4 = t + 4, a5 = t + 5, a6 = t + 6, a7 = t + 7;
-    uint32_t x = t * 2654435761u + 12345u, y = t ^ 0x9e3779b9u;
+  } else if (VARIANT == 1) {   // IMAD (32-bit): acc = acc * y + x
+    uint32_t a[8];
+    for (int k = 0; k < 8; k++) a[k] = t * 2654435761u + k * 40503u + 1u;
+    uint32_t y = (t ^ 0x9e3779b9u) | 1u, x = t + 12345u;
 #pragma unroll 1
     for (int i = 0; i < iters; i++) {
 #pragma unroll
-      for (int r = 0; r < 4; r++) {
-        asm volatile("mad.lo.u32 %0, %8, %9, %0; mad.lo.u32 %1, %8, %9, %1; mad.lo.u32 %2, %8, %9, %2; mad.lo.u32 %3, %8, %9, %3;"
-                     "mad.lo.u32 %4, %8, %9, %4; mad.lo.u32 %5, %8, %9, %5; mad.lo.u32 %6, %8, %9, %6; mad.lo.u32 %7, %8, %9, %7;"
-                     : "+r"(a0), "+r"(a1), "+r"(a2), "+r"(a3), "+r"(a4), "+r"(a5), "+r"(a6), "+r"(a7) : "r"(x), "r"(y));
-      }
+      for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int k = 0; k < 8; k++) a[k] = a[k] * y + x;
     }
-    out[t] = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+    uint32_t s = 0;
+    for (int k = 0; k < 8; k++) s ^= a[k];
+    out[t] = s;
   } else if (VARIANT == 2) {   // dependent chain of BLS12-381 Fr Montgomery products (136 MAC32 each); 32 per iteration
     Fp<BlsFr> a, b;
     for (int i = 0; i < 8; i++) { a.v[i] = t + i; b.v[i] = (t ^ 0x5bd1e995u) + 7 * i; }
@@ -132,19 +137,46 @@ __global__ void __launch_bounds__(256) k_mac_bench(uint32_t* out, int iters, uns
     uint32_t s = 0;
     for (int c = 0; c < 4; c++) { s ^= top[c]; for (int i = 0; i < 8; i++) s ^= acc[c][i]; }
     out[t] = s;
-  } else {                     // VARIANT 4: mad.hi.u32
-    uint32_t a0 = t, a1 = t + 1, a2 = t + 2, a3 = t + 3, a4 = t + 4, a5 = t + 5, a6 = t + 6, a7 = t + 7;
-    uint32_t x = t * 2654435761u + 12345u, y = t ^ 0x9e3779b9u;
+  } else if (VARIANT == 7 || VARIANT == 8) {   // unsaturated 9x29 products (f29.cuh): 7 = mul chain, 8 = mul + sqr; 32 products per iteration
+    F29 a, b;
+    for (int i = 0; i < 9; i++) { a.v[i] = (int32_t)((t * 2654435761u + i * 40503u) & F29_MASK); b.v[i] = (int32_t)(((t ^ 0x5bd1e995u) * 2246822519u + i) & F29_MASK); }
+    a.v[8] &= 0xffff; b.v[8] &= 0xffff;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll 1
+      for (int r = 0; r < 16; r++) { a = f29_mul(a, b); b = VARIANT == 7 ? f29_mul(b, a) : f29_sqr(a); }
+    }
+    uint32_t s = 0;
+    for (int i = 0; i < 9; i++) s ^= (uint32_t)(a.v[i] ^ b.v[i]);
+    out[t] = s;
+  } else if (VARIANT == 9) {   // DFMA: acc = acc * y + x, 8 independent chains (FP64 pipe, for the Emmart-style alternative)
+    double a[8];
+    for (int k = 0; k < 8; k++) a[k] = 1.0 + (double)((t + k) & 1023) * 1e-9;
+    double y = 1.0 + (double)(t & 255) * 1e-12, x = 1e-30;
 #pragma unroll 1
     for (int i = 0; i < iters; i++) {
 #pragma unroll
-      for (int r = 0; r < 4; r++) {
-        asm volatile("mad.hi.u32 %0, %8, %9, %0; mad.hi.u32 %1, %8, %9, %1; mad.hi.u32 %2, %8, %9, %2; mad.hi.u32 %3, %8, %9, %3;"
-                     "mad.hi.u32 %4, %8, %9, %4; mad.hi.u32 %5, %8, %9, %5; mad.hi.u32 %6, %8, %9, %6; mad.hi.u32 %7, %8, %9, %7;"
-                     : "+r"(a0), "+r"(a1), "+r"(a2), "+r"(a3), "+r"(a4), "+r"(a5), "+r"(a6), "+r"(a7) : "r"(x), "r"(y));
-      }
+      for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int k = 0; k < 8; k++) a[k] = __fma_rn(a[k], y, x);
     }
-    out[t] = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+    double s = 0;
+    for (int k = 0; k < 8; k++) s += a[k];
+    out[t] = (uint32_t)__double2loint(s) ^ (uint32_t)__double2hiint(s);
+  } else {                     // VARIANT 4: IMAD.HI.U32: acc = hi(acc * y) + x
+    uint32_t a[8];
+    for (int k = 0; k < 8; k++) a[k] = t * 2654435761u + k * 40503u + 0x80000001u;
+    uint32_t y = (t ^ 0x9e3779b9u) | 0xc0000000u, x = t + 12345u;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+      for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int k = 0; k < 8; k++) a[k] = __umulhi(a[k], y) + x;
+    }
+    uint32_t s = 0;
+    for (int k = 0; k < 8; k++) s ^= a[k];
+    out[t] = s;
   }
   unsigned long long c1 = clock64();
   if (threadIdx.x == 0 && blockIdx.x == 0) *cycles = c1 - c0;
@@ -420,8 +452,8 @@ extern "C" vrfs_status vrfs_measure_mac32_peak(vrfs_ctx* ctx, int variant, doubl
   void *out = nullptr, *cyc = nullptr;
   ST(ensure(ctx, BUF_W0, (size_t)threads * blocks * 4, &out));
   ST(ensure(ctx, BUF_W1, 64, &cyc));
-  int iters = (variant == 2 || variant == 3) ? 64 : 4096;
-  double macs_per_thread_iter = (variant == 2 || variant == 3) ? 32.0 * 136.0 : 32.0;
+  int iters = (variant == 2 || variant == 3 || variant >= 7) ? 64 : 4096;
+  double macs_per_thread_iter = (variant == 2 || variant == 3 || variant >= 7) ? 32.0 * 136.0 : 32.0;   // field products are counted as 136 MAC32 (the saturated 8-limb model) in every representation
   float ms = 0;
   for (int rep = 0; rep < 3; rep++) {
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
@@ -433,6 +465,9 @@ extern "C" vrfs_status vrfs_measure_mac32_peak(vrfs_ctx* ctx, int variant, doubl
       case 4: k_mac_bench<4><<<blocks, threads, 0, ctx->stream>>>((uint32_t*)out, iters, (unsigned long long*)cyc); break;
       case 5: k_mac_bench<5><<<blocks, threads, 0, ctx->stream>>>((uint32_t*)out, iters, (unsigned long long*)cyc); break;
       case 6: k_mac_bench<6><<<blocks, threads, 0, ctx->stream>>>((uint32_t*)out, iters, (unsigned long long*)cyc); break;
+      case 7: k_mac_bench<7><<<blocks, threads, 0, ctx->stream>>>((uint32_t*)out, iters, (unsigned long long*)cyc); break;
+      case 8: k_mac_bench<8><<<blocks, threads, 0, ctx->stream>>>((uint32_t*)out, iters, (unsigned long long*)cyc); break;
+      case 9: k_mac_bench<9><<<blocks, threads, 0, ctx->stream>>>((uint32_t*)out, iters, (unsigned long long*)cyc); break;
       default: return fail(ctx, VRFS_BAD_ARG, "unknown variant %d", variant);
     }
     LAUNCHED(ctx);
@@ -524,14 +559,15 @@ template <class S> __global__ void __launch_bounds__(ITEM_THREADS) k_data_to_poi
   ITEM_INDEX(n);
   typedef typename S::C C;
   VAR_SLICE(data, off, i, p, len);
-  typename Grp<C>::Pt P;
+  typename C::F X, Y, Z;
   bool ok;
-  if constexpr (C::HAS_GLV) { band_h2c_ell2(P, p, len); ok = true; } else { ok = h2c_tai<S>(P, p, len); }
+  if constexpr (C::HAS_GLV) { TEPoint<C> P; band_h2c_ell2(P, p, len); ok = true; X = P.X; Y = P.Y; Z = P.Z; }
+  else { typename Grp<C>::Pt P; ok = h2c_tai<S>(P, p, len); X = P.X; Y = P.Y; Z = P.Z; }
   uint8_t* o = out + (size_t)64 * i;
   out_ok[i] = ok;
   if (!ok) { for (int j = 0; j < 64; j++) o[j] = 0; return; }
-  typename C::F zi = inv(P.Z);
-  store_affine_bytes<C>(o, P.X * zi, P.Y * zi);
+  typename C::F zi = inv(Z);
+  store_affine_bytes<C>(o, X * zi, Y * zi);
 }
 template <class S> __global__ void __launch_bounds__(ITEM_THREADS) k_pedersen_prove_prep(uint32_t n, const uint8_t* sk, const uint8_t* input, const uint8_t* ad, const uint64_t* ad_off,
                                                                                           uint8_t* b, uint8_t* k, uint8_t* kb) {
@@ -871,33 +907,49 @@ extern "C" vrfs_status vrfs_pedersen_verify_batch(vrfs_ctx* ctx, vrfs_suite suit
 // =================================================================================================
 // ring commitment MSM (K12)
 // =================================================================================================
-enum { MBUF_BASES, MBUF_COUNTS, MBUF_OFFSETS, MBUF_CURSORS, MBUF_LIST, MBUF_BUCKETS, MBUF_WINDOWS, MBUF_COUNT };
-static vrfs_status msm_dev(vrfs_ctx* ctx, size_t n, const uint8_t* d_bases, const uint8_t* d_scalars, int ncol, uint8_t* d_out, int out_mode) {
-  MsmPlan p = msm_plan((uint32_t)n, (uint32_t)ncol);
-  const size_t segs = (size_t)ncol * p.windows, nbuckets = segs * p.nb;
-  void *bases_m, *counts, *offsets, *cursors, *list, *buckets, *wsum;
-  ST(ensure(ctx, BUF_W0, n * sizeof(G1Aff), &bases_m));
-  ST(ensure(ctx, BUF_W1, nbuckets * 3 * sizeof(uint32_t), &counts));
-  offsets = (uint32_t*)counts + nbuckets; cursors = (uint32_t*)counts + 2 * nbuckets;
-  ST(ensure(ctx, BUF_W2, segs * n * sizeof(uint32_t), &list));
+// prepared bases (vrfs_msm_g1_prepare): the RingContext analogue - the SRS is fixed, so 2^(c w) P_i is computed once
+struct vrfs_msm_bases {
+  vrfs_ctx* ctx;
+  size_t n;
+  MsmPlan plan;
+  void* Q;          // windows * n projective points
+};
+// bases: G1Aff[n] (stateless) or the prepared table Q; scalars on the device
+static vrfs_status msm_dev(vrfs_ctx* ctx, MsmPlan p, const void* d_bases, const uint8_t* d_scalars, uint8_t* d_out, int out_mode) {
+  const size_t n = p.n, ncol = p.ncol;
+  const size_t segs = ncol * p.seg_windows, nbuckets = segs * p.nb, seg_len = n * (p.prepared ? p.windows : 1);
+  const size_t per_seg = p.nb / p.chunk;
+  void *counts, *list, *buckets, *wsum;
+  ST(ensure(ctx, BUF_W1, (nbuckets * 4 + 16) * sizeof(uint32_t), &counts));
+  uint32_t *offsets = (uint32_t*)counts + nbuckets, *cursors = offsets + nbuckets, *big_list = cursors + nbuckets, *big_count = big_list + nbuckets;
+  ST(ensure(ctx, BUF_W2, segs * seg_len * sizeof(uint32_t), &list));
   ST(ensure(ctx, BUF_W3, nbuckets * sizeof(G1Pt), &buckets));
-  ST(ensure(ctx, BUF_SLAB, segs * sizeof(G1Pt), &wsum));
-  CU(cudaMemsetAsync(counts, 0, nbuckets * 3 * sizeof(uint32_t), ctx->stream));
-  const unsigned tn = (unsigned)((n + 127) / 128), tsc = (unsigned)((n * ncol + 127) / 128);
-  k_msm_prep_bases<<<tn, 128, 0, ctx->stream>>>((uint32_t)n, d_bases, (G1Aff*)bases_m);
-  LAUNCHED_AS(ctx, "msm_prep_bases");
+  ST(ensure(ctx, BUF_SLAB, (segs + segs * per_seg) * sizeof(G1Pt), &wsum));
+  G1Pt* partials = (G1Pt*)wsum + segs;
+  CU(cudaMemsetAsync(counts, 0, (nbuckets * 4 + 16) * sizeof(uint32_t), ctx->stream));
+  const unsigned tsc = (unsigned)((n * ncol + 127) / 128);
   k_msm_histogram<<<tsc, 128, 0, ctx->stream>>>(p, d_scalars, (uint32_t*)counts);
   LAUNCHED_AS(ctx, "msm_histogram");
-  k_msm_scan<<<(unsigned)segs, 256, 0, ctx->stream>>>(p, (const uint32_t*)counts, (uint32_t*)offsets);
+  k_msm_scan<<<(unsigned)segs, 256, 0, ctx->stream>>>(p, (const uint32_t*)counts, offsets, big_list, big_count);
   LAUNCHED_AS(ctx, "msm_scan");
-  k_msm_scatter<<<tsc, 128, 0, ctx->stream>>>(p, d_scalars, (const uint32_t*)offsets, (uint32_t*)cursors, (uint32_t*)list);
+  k_msm_scatter<<<tsc, 128, 0, ctx->stream>>>(p, d_scalars, offsets, cursors, (uint32_t*)list);
   LAUNCHED_AS(ctx, "msm_scatter");
-  k_msm_accumulate<<<(unsigned)((nbuckets + 127) / 128), 128, 0, ctx->stream>>>(p, (const G1Aff*)bases_m, (const uint32_t*)counts, (const uint32_t*)offsets,
-                                                                               (const uint32_t*)list, (G1Pt*)buckets);
-  LAUNCHED_AS(ctx, "msm_accumulate");
-  const unsigned wt = (unsigned)(p.nb / MSM_CHUNK);
-  k_msm_window<<<(unsigned)segs, wt, wt * sizeof(G1Pt), ctx->stream>>>(p, (const G1Pt*)buckets, (G1Pt*)wsum);
-  LAUNCHED_AS(ctx, "msm_window");
+  const unsigned ab = (unsigned)((nbuckets * p.tpb + 127) / 128);
+  const unsigned bigb = (unsigned)(ctx->sms * 4);
+  if (p.prepared) {
+    k_msm_accumulate<true><<<ab, 128, 0, ctx->stream>>>(p, d_bases, (const uint32_t*)counts, offsets, (const uint32_t*)list, (G1Pt*)buckets);
+    LAUNCHED_AS(ctx, "msm_accumulate");
+    k_msm_accumulate_big<true><<<bigb, MSM_BIG_THREADS, 0, ctx->stream>>>(p, d_bases, (const uint32_t*)counts, offsets, (const uint32_t*)list, big_list, big_count, (G1Pt*)buckets);
+  } else {
+    k_msm_accumulate<false><<<ab, 128, 0, ctx->stream>>>(p, d_bases, (const uint32_t*)counts, offsets, (const uint32_t*)list, (G1Pt*)buckets);
+    LAUNCHED_AS(ctx, "msm_accumulate");
+    k_msm_accumulate_big<false><<<bigb, MSM_BIG_THREADS, 0, ctx->stream>>>(p, d_bases, (const uint32_t*)counts, offsets, (const uint32_t*)list, big_list, big_count, (G1Pt*)buckets);
+  }
+  LAUNCHED_AS(ctx, "msm_accumulate_big");
+  k_msm_window_chunks<<<(unsigned)((segs * per_seg + 127) / 128), 128, 0, ctx->stream>>>(p, (const G1Pt*)buckets, partials);
+  LAUNCHED_AS(ctx, "msm_window_chunks");
+  k_msm_window_sum<<<(unsigned)segs, 256, 0, ctx->stream>>>(p, partials, (G1Pt*)wsum);
+  LAUNCHED_AS(ctx, "msm_window_sum");
   k_msm_final<<<1, 32, 0, ctx->stream>>>(p, (const G1Pt*)wsum, d_out, out_mode);
   LAUNCHED_AS(ctx, "msm_final");
   return VRFS_OK;
@@ -917,7 +969,11 @@ static vrfs_status msm_host(vrfs_ctx* ctx, size_t n, const uint8_t* bases, const
   const uint8_t *d_b, *d_s; uint8_t* d_o;
   ST(stage_in(ctx, BUF_IN0, bases, n * 96, &d_b)); ST(stage_in(ctx, BUF_IN1, scalars, n * 32 * (size_t)ncol, &d_s));
   ST(stage_out(ctx, BUF_OUT0, ob * ncol, &d_o));
-  ST(msm_dev(ctx, n, d_b, d_s, ncol, d_o, out_mode));
+  void* bases_m = nullptr;
+  ST(ensure(ctx, BUF_W0, n * sizeof(G1Aff), &bases_m));
+  k_msm_prep_bases<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((uint32_t)n, d_b, (G1Aff*)bases_m);
+  LAUNCHED_AS(ctx, "msm_prep_bases");
+  ST(msm_dev(ctx, msm_plan((uint32_t)n, (uint32_t)ncol, 0), bases_m, d_s, d_o, out_mode));
   ST(copy_out(ctx, out, d_o, ob * ncol));
   return finish_call(ctx);
 }
@@ -926,6 +982,46 @@ extern "C" vrfs_status vrfs_msm_g1_bls12_381(vrfs_ctx* ctx, size_t n, const uint
 }
 extern "C" vrfs_status vrfs_msm_g1_partial(vrfs_ctx* ctx, size_t n, const uint8_t* bases, const uint8_t* scalars, int n_columns, uint8_t* out_partial) {
   return msm_host(ctx, n, bases, scalars, n_columns, out_partial, 1);
+}
+extern "C" vrfs_status vrfs_msm_g1_prepare(vrfs_ctx* ctx, size_t n, const uint8_t* bases, vrfs_msm_bases** out) {
+  if (!ctx || !out) return VRFS_BAD_ARG;
+  *out = nullptr;
+  if (n == 0 || !bases) return fail(ctx, VRFS_BAD_ARG, "empty base vector");
+  if (n > (1u << 24)) return fail(ctx, VRFS_BAD_ARG, "prepared MSM size above 2^24 is not supported");
+  ST(begin_call(ctx, n));
+  vrfs_msm_bases* h = new (std::nothrow) vrfs_msm_bases();
+  if (!h) return fail(ctx, VRFS_CUDA_ERROR, "out of host memory");
+  h->ctx = ctx; h->n = n; h->plan = msm_plan((uint32_t)n, 1, 1); h->Q = nullptr;
+  cudaError_t e = cudaMalloc(&h->Q, (size_t)h->plan.windows * n * sizeof(G1Pt));
+  if (e != cudaSuccess) { delete h; return fail(ctx, VRFS_CUDA_ERROR, "cudaMalloc of the prepared table failed: %s", cudaGetErrorString(e)); }
+  *out = h;
+  const uint8_t* d_b; void* bases_m = nullptr;
+  ST(stage_in(ctx, BUF_IN0, bases, n * 96, &d_b));
+  ST(ensure(ctx, BUF_W0, n * sizeof(G1Aff), &bases_m));
+  k_msm_prep_bases<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((uint32_t)n, d_b, (G1Aff*)bases_m);
+  LAUNCHED_AS(ctx, "msm_prep_bases");
+  k_msm_prepare<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((uint32_t)n, h->plan.c, h->plan.windows, (const G1Aff*)bases_m, (G1Pt*)h->Q);
+  LAUNCHED_AS(ctx, "msm_prepare");
+  return finish_call(ctx);
+}
+extern "C" void vrfs_msm_g1_release(vrfs_msm_bases* h) {
+  if (!h) return;
+  cudaSetDevice(h->ctx->device);
+  cudaStreamSynchronize(h->ctx->stream);
+  if (h->Q) cudaFree(h->Q);
+  delete h;
+}
+extern "C" vrfs_status vrfs_msm_g1_prepared(vrfs_ctx* ctx, const vrfs_msm_bases* h, const uint8_t* scalars, int n_columns, uint8_t* out) {
+  if (!ctx || !h || h->ctx != ctx) return VRFS_BAD_ARG;
+  if (n_columns < 1 || n_columns > 32 || !scalars || !out) return fail(ctx, VRFS_BAD_ARG, "bad argument");
+  ST(begin_call(ctx, h->n));
+  const uint8_t* d_s; uint8_t* d_o;
+  ST(stage_in(ctx, BUF_IN1, scalars, h->n * 32 * (size_t)n_columns, &d_s));
+  ST(stage_out(ctx, BUF_OUT0, (size_t)96 * n_columns, &d_o));
+  MsmPlan p = msm_plan((uint32_t)h->n, (uint32_t)n_columns, 1);
+  ST(msm_dev(ctx, p, h->Q, d_s, d_o, 0));
+  ST(copy_out(ctx, out, d_o, (size_t)96 * n_columns));
+  return finish_call(ctx);
 }
 extern "C" vrfs_status vrfs_g1_sum_partials(vrfs_ctx* ctx, int n_parts, int n_columns, const uint8_t* partials, uint8_t* out) {
   if (!ctx) return VRFS_BAD_ARG;

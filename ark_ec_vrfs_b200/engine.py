@@ -31,6 +31,21 @@ def pack_var(items):
     return data, off
 
 
+class PreparedBases:
+    def __init__(self, engine, handle, n):
+        self.engine, self.handle, self.n = engine, handle, n
+
+    def msm(self, scalars, n_columns=1):
+        scalars = _u8(scalars, (n_columns * self.n, 32)); out = np.zeros((n_columns, 96), np.uint8)
+        self.engine._call("vrfs_msm_g1_prepared", self.handle, _p(scalars), int(n_columns), _p(out))
+        return out
+
+    def release(self):
+        if self.handle:
+            self.engine._lib.vrfs_msm_g1_release(self.handle)
+            self.handle = None
+
+
 class Engine:
     """One context on one GPU (`device` = CUDA ordinal).  Not thread-safe; one per process per GPU."""
 
@@ -176,6 +191,13 @@ class Engine:
         out = np.zeros((n_columns, 96), np.uint8)
         self._call("vrfs_msm_g1_bls12_381", C.c_size_t(n), _p(bases), _p(scalars), int(n_columns), _p(out))
         return out
+
+    def msm_g1_prepare(self, bases):
+        """RingContext analogue: returns a handle holding 2^(c w) * P_i on the device"""
+        bases = _u8(bases, (-1, 96)); n = len(bases)
+        h = C.c_void_p()
+        self._call("vrfs_msm_g1_prepare", C.c_size_t(n), _p(bases), C.byref(h))
+        return PreparedBases(self, h, n)
 
     def msm_g1_partial(self, bases, scalars, n_columns=1):
         bases = _u8(bases, (-1, 96)); n = len(bases); scalars = _u8(scalars, (n_columns * n, 32))

@@ -55,7 +55,7 @@ template <class S> static void ietf_verify(size_t n, const uint8_t* pk, const ui
                                            const uint8_t* s, const uint8_t* ad, const uint64_t* ad_off, uint8_t* ok) {
   typedef typename S::C C;
   std::vector<typename Grp<C>::Entry> slab(4 * 9);
-  std::vector<uint32_t> u(24), v(24);
+  std::vector<uint32_t> u(28), v(28);
   for (size_t i = 0; i < n; i++) {
     LincombArgs A = {};
     A.n = (uint32_t)n;
@@ -63,11 +63,11 @@ template <class S> static void ietf_verify(size_t n, const uint8_t* pk, const ui
     A.fix[0] = {s, 32, 0, fixed_table<C>(false)};
     typename Grp<C>::Pt acc;
     bool valid = lincomb_item<C, 1, 1>(A, (uint32_t)i, slab.data(), acc);
-    memcpy(&u[0], acc.X.v, 32); memcpy(&u[8], acc.Y.v, 32); memcpy(&u[16], acc.Z.v, 32);
+    Grp<C>::store_xyz(u.data(), acc);
     A.var[0] = {in, 64, s, 32, 0};
     A.var[1] = {out, 64, c, 32, 1};
     valid &= lincomb_item<C, 2, 0>(A, (uint32_t)i, slab.data(), acc);
-    memcpy(&v[0], acc.X.v, 32); memcpy(&v[8], acc.Y.v, 32); memcpy(&v[16], acc.Z.v, 32);
+    Grp<C>::store_xyz(v.data(), acc);
     const uint8_t* a = ad ? ad + ad_off[i] : (const uint8_t*)"";
     uint32_t alen = ad ? (uint32_t)(ad_off[i + 1] - ad_off[i]) : 0;
     ok[i] = valid && ietf_verify_finish_item<S>(pk + 64 * i, in + 64 * i, out + 64 * i, c + 32 * i, u.data(), v.data(), a, alen);
@@ -94,7 +94,11 @@ template <class C> static int lincomb_dbg(int nv, int nf, const uint8_t* p1, con
   else if (nv == 2 && nf == 0) ok = lincomb_item<C, 2, 0>(A, 0, slab.data(), acc);
   else if (nv == 0 && nf == 1) ok = lincomb_item<C, 0, 1>(A, 0, slab.data(), acc);
   else ok = lincomb_item<C, 1, 1>(A, 0, slab.data(), acc);
-  typename C::F zi = inv(acc.Z), x = acc.X * zi, y = acc.Y * zi;
+  alignas(16) uint32_t xyz[24];
+  Grp<C>::store_xyz(xyz, acc);
+  typename C::F X, Y, Z;
+  memcpy(X.v, xyz, 32); memcpy(Y.v, xyz + 8, 32); memcpy(Z.v, xyz + 16, 32);
+  typename C::F zi = inv(Z), x = X * zi, y = Y * zi;
   uint32_t rx[8], ry[8]; from_mont<typename C::Fq>(rx, x); from_mont<typename C::Fq>(ry, y);
   store_le<8>(out, rx); store_le<8>(out + 32, ry);
   return ok;
@@ -107,4 +111,21 @@ extern "C" int hostemu_lincomb(int suite, int nv, int nf, const uint8_t* p1, con
 extern "C" void hostemu_glv(const uint32_t* k, uint32_t* out /*4+4+2*/) {
   GlvHalf a, b; band_glv_split(&a, &b, k);
   memcpy(out, a.mag, 16); memcpy(out + 4, b.mag, 16); out[8] = a.neg; out[9] = b.neg;
+}
+
+// f29 unit tests: op 0 mul, 1 sqr, 2 from_fp->to_fp round trip of a Montgomery-256 value, 3 canonical limbs of a lazy value
+extern "C" void hostemu_f29(int op, const int32_t* a, const int32_t* b, int32_t* out) {
+  F29 x, y, r = f29_zero();
+  memcpy(x.v, a, 36); memcpy(y.v, b, 36);
+  if (op == 0) r = f29_mul(x, y);
+  else if (op == 1) r = f29_sqr(x);
+  else if (op == 3) { uint32_t l[9]; f29_canonical_limbs(l, x); memcpy(r.v, l, 36); }
+  memcpy(out, r.v, 36);
+}
+extern "C" void hostemu_f29_roundtrip(const uint32_t* fp_in, uint32_t* fp_out, int32_t* f29_out) {
+  Fp<BlsFr> x; memcpy(x.v, fp_in, 32);
+  F29 y = f29_from_fp(x);
+  memcpy(f29_out, y.v, 36);
+  Fp<BlsFr> z = f29_to_fp(y);
+  memcpy(fp_out, z.v, 32);
 }

@@ -94,3 +94,27 @@ def test_msm_ring_sizes_split_and_linearity(eng, logn):
     assert np.array_equal(s[0], full[2])
     if logn == 11:
         assert np.array_equal(full, O.msm_g1(bases, sc, 3))
+
+
+@pytest.mark.parametrize("logn", [8, 11, 13, 16])
+def test_msm_prepared_equals_stateless_and_handles_skew(eng, logn):
+    """prepared bases (RingContext analogue) give the same commitments; columns shaped like the ring's fixed
+    columns (0/1 selector, mostly-equal values) exercise the oversized-bucket path"""
+    n = 1 << logn
+    rng = np.random.default_rng(100 + logn)
+    k = rng.integers(1, 2 ** 62, size=n, dtype=np.uint64)
+    ks = np.zeros((n, 32), np.uint8); ks[:, :8] = k.view(np.uint8).reshape(n, 8)
+    bases = O.g1_mul_gen(ks)
+    col0 = rng.integers(0, 256, size=(n, 32), dtype=np.uint8); col0[:, 31] &= 0x3F        # random
+    col1 = np.zeros((n, 32), np.uint8); col1[: (3 * n) // 4, 0] = 1                        # selector 1..1 0..0
+    col2 = np.tile(col0[0], (n, 1)); col2[::5] = col0[::5]                                 # 80 % identical scalars
+    sc = np.concatenate([col0, col1, col2])
+    full = eng.msm_g1(bases, sc, 3)
+    h = eng.msm_g1_prepare(bases)
+    try:
+        assert np.array_equal(h.msm(sc, 3), full)
+        assert np.array_equal(h.msm(col1, 1), full[1:2])
+    finally:
+        h.release()
+    if logn <= 11:
+        assert np.array_equal(full, O.msm_g1(bases, sc, 3))
