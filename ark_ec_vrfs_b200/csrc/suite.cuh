@@ -157,30 +157,79 @@ template <class C> HD_INLINE void two_to_affine(typename C::F* ax, typename C::F
   ax[0] = X0 * z0i; ay[0] = Y0 * z0i; ax[1] = X1 * z1i; ay[1] = Y1 * z1i;
 }
 
-// ietf::Verifier::verify, second half (A.9): U, V already computed; accept iff challenge(Y,I,O,U,V,ad) == c
+// ietf::Verifier::verify, second half (A.9): U, V already computed; accept iff challenge(Y,I,O,U,V,ad) == c.
+// zinv = 1 / (Z_U * Z_V), shared by the two points (and itself obtained from a batched inversion, see
+// ietf_verify_finish_batched).
 template <class S>
-HD_INLINE bool ietf_verify_finish_item(const uint8_t* pk, const uint8_t* input, const uint8_t* output, const uint8_t* c_bytes,
-                                       const uint32_t* u_xyz, const uint32_t* v_xyz, const uint8_t* ad, uint32_t adlen) {
+HD_INLINE bool ietf_verify_finish_with_zinv(const uint8_t* pk, const uint8_t* input, const uint8_t* output, const uint8_t* c_bytes,
+                                            const uint32_t* u_xyz, const uint32_t* v_xyz, const typename S::C::F& zinv,
+                                            const uint8_t* ad, uint32_t adlen) {
   typedef typename S::C C;
-  typename C::F ax[2], ay[2];
+  typedef typename C::F F;
+  F XU, YU, ZU, XV, YV, ZV;
+  for (int i = 0; i < 8; i++) { XU.v[i] = u_xyz[i]; YU.v[i] = u_xyz[8 + i]; ZU.v[i] = u_xyz[16 + i]; XV.v[i] = v_xyz[i]; YV.v[i] = v_xyz[8 + i]; ZV.v[i] = v_xyz[16 + i]; }
   if (!C::IS_TE) {   // the identity has no SEC1-compressed encoding: Error::InvalidData / VerificationFailure
-    uint32_t zu = 0, zv = 0;
-    for (int i = 0; i < 8; i++) { zu |= u_xyz[16 + i]; zv |= v_xyz[16 + i]; }
-    if (zu == 0 || zv == 0 || bytes_all_zero(pk, 64) || bytes_all_zero(input, 64) || bytes_all_zero(output, 64)) return false;
+    if (ZU.is_zero() || ZV.is_zero() || bytes_all_zero(pk, 64) || bytes_all_zero(input, 64) || bytes_all_zero(output, 64)) return false;
   }
-  two_to_affine<C>(ax, ay, u_xyz, v_xyz);
+  F zui = zinv * ZV, zvi = zinv * ZU;
   uint8_t enc[5][S::ENC_LEN];
   encode_point_bytes<S>(enc[0], pk);
   encode_point_bytes<S>(enc[1], input);
   encode_point_bytes<S>(enc[2], output);
-  encode_point_mont<S>(enc[3], ax[0], ay[0]);
-  encode_point_mont<S>(enc[4], ax[1], ay[1]);
+  encode_point_mont<S>(enc[3], XU * zui, YU * zui);
+  encode_point_mont<S>(enc[4], XV * zvi, YV * zvi);
   uint32_t c2[8], c[8];
   suite_challenge<S>(c2, enc, ad, adlen);
   hash_to_scalar<C>(c, c_bytes, 32, false);
   uint32_t diff = 0;
   for (int i = 0; i < 8; i++) diff |= c[i] ^ c2[i];
   return diff == 0;
+}
+template <class C> HD_INLINE typename C::F zz_product(const uint32_t* u_xyz, const uint32_t* v_xyz) {
+  typename C::F ZU, ZV;
+  for (int i = 0; i < 8; i++) { ZU.v[i] = u_xyz[16 + i]; ZV.v[i] = v_xyz[16 + i]; }
+  return ZU * ZV;
+}
+template <class S>
+HD_INLINE bool ietf_verify_finish_item(const uint8_t* pk, const uint8_t* input, const uint8_t* output, const uint8_t* c_bytes,
+                                       const uint32_t* u_xyz, const uint32_t* v_xyz, const uint8_t* ad, uint32_t adlen) {
+  typename S::C::F zinv = inv(zz_product<typename S::C>(u_xyz, v_xyz));
+  return ietf_verify_finish_with_zinv<S>(pk, input, output, c_bytes, u_xyz, v_xyz, zinv, ad, adlen);
+}
+// K items per thread share ONE field inversion (Montgomery's trick): item k of this thread is `first + k * stride`.
+// A zero Z (only possible for invalid / identity inputs) is replaced by 1 in the product chain so that it cannot
+// poison the other items; that item's own zinv is then wrong-but-unused (it fails the Z checks / validity flag).
+template <class S, int K>
+HD_INLINE void ietf_verify_finish_batched(uint32_t n, uint32_t first, uint32_t stride, const uint8_t* pk, const uint8_t* input, const uint8_t* output,
+                                          const uint8_t* c, const uint32_t* u_xyz, const uint32_t* v_xyz, const uint8_t* ad, const uint64_t* ad_off,
+                                          const uint8_t* valid, uint8_t* out_ok) {
+  typedef typename S::C C;
+  typedef typename C::F F;
+  F z[K], pre[K];
+  int cnt = 0;
+  for (int k = 0; k < K; k++) {
+    uint32_t i = first + (uint32_t)k * stride;
+    if (i >= n) break;
+    F t = zz_product<C>(u_xyz + (size_t)24 * i, v_xyz + (size_t)24 * i);
+    z[k] = select(t.is_zero(), F::one(), t);
+    pre[k] = k ? pre[k - 1] * z[k] : z[k];
+    cnt = k + 1;
+  }
+  if (cnt == 0) return;
+  F acc = inv(pre[cnt - 1]);
+  for (int k = K - 1; k >= 0; k--) {
+    if (k >= cnt) continue;
+    uint32_t i = first + (uint32_t)k * stride;
+    F zinv = k ? acc * pre[k - 1] : acc;
+    if (k) acc = acc * z[k];
+    const uint8_t* a = ad ? ad + ad_off[i] : nullptr;
+    uint32_t alen = ad ? (uint32_t)(ad_off[i + 1] - ad_off[i]) : 0u;
+    bool ok = ietf_verify_finish_with_zinv<S>(pk + (size_t)64 * i, input + (size_t)64 * i, output + (size_t)64 * i, c + (size_t)32 * i,
+                                              u_xyz + (size_t)24 * i, v_xyz + (size_t)24 * i, zinv, a, alen);
+    // TE with Z = 0 cannot happen for on-curve inputs; guard anyway so a forged zero never verifies
+    F t = zz_product<C>(u_xyz + (size_t)24 * i, v_xyz + (size_t)24 * i);
+    out_ok[i] = (uint8_t)(ok && valid[i] && !t.is_zero());
+  }
 }
 
 // K projective points (X,Y,Z Montgomery limbs, 24 words each) -> affine Montgomery, ONE shared inversion

@@ -48,18 +48,15 @@ __global__ void __launch_bounds__(LINCOMB_THREADS, LINCOMB_MINBLOCKS) k_lincomb(
   }
 }
 
-// K9b: shared inversion, 5 point encodings, SHA-512 challenge, compare
+// K9b: inversion shared by FINISH_K items per thread (Montgomery's trick), 5 point encodings, challenge hash, compare
+#define FINISH_K 8
 template <class S>
 __global__ void __launch_bounds__(128) k_ietf_verify_finish(uint32_t n, const uint8_t* pk, const uint8_t* input, const uint8_t* output,
                                                              const uint8_t* c, const uint32_t* u_xyz, const uint32_t* v_xyz,
                                                              const uint8_t* ad, const uint64_t* ad_off, const uint8_t* valid, uint8_t* out_ok) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint8_t* a = ad ? ad + ad_off[i] : nullptr;
-  uint32_t alen = ad ? (uint32_t)(ad_off[i + 1] - ad_off[i]) : 0u;
-  bool ok = ietf_verify_finish_item<S>(pk + (size_t)64 * i, input + (size_t)64 * i, output + (size_t)64 * i, c + (size_t)32 * i,
-                                       u_xyz + (size_t)24 * i, v_xyz + (size_t)24 * i, a, alen);
-  out_ok[i] = (uint8_t)(ok && valid[i]);
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+  if (t >= n) return;
+  ietf_verify_finish_batched<S, FINISH_K>(n, t, stride, pk, input, output, c, u_xyz, v_xyz, ad, ad_off, valid, out_ok);
 }
 
 // integer-pipe roofline microbenchmarks: independent multiply-accumulate chains per thread
@@ -149,16 +146,16 @@ __global__ void __launch_bounds__(256) k_mac_bench(uint32_t* out, int iters, uns
     uint32_t s = 0;
     for (int i = 0; i < 9; i++) s ^= (uint32_t)(a.v[i] ^ b.v[i]);
     out[t] = s;
-  } else if (VARIANT == 9) {   // DFMA: acc = acc * y + x, 8 independent chains (FP64 pipe, for the Emmart-style alternative)
+  } else if (VARIANT == 9) {   // DFMA: acc = fma(acc, y, x) with round-toward-zero, 8 independent chains (FP64 pipe)
     double a[8];
-    for (int k = 0; k < 8; k++) a[k] = 1.0 + (double)((t + k) & 1023) * 1e-9;
-    double y = 1.0 + (double)(t & 255) * 1e-12, x = 1e-30;
+    for (int k = 0; k < 8; k++) a[k] = 1.0 + (double)((t + k) & 1023) * 1e-3;
+    double y = __longlong_as_double(0x3ff0000000000000ll | (long long)(t & 0xffff)), x = (double)(t & 7) * 1e-9;
 #pragma unroll 1
     for (int i = 0; i < iters; i++) {
 #pragma unroll
       for (int r = 0; r < 4; r++)
 #pragma unroll
-        for (int k = 0; k < 8; k++) a[k] = __fma_rn(a[k], y, x);
+        for (int k = 0; k < 8; k++) a[k] = __fma_rz(a[k], y, x);
     }
     double s = 0;
     for (int k = 0; k < 8; k++) s += a[k];
@@ -376,7 +373,7 @@ static vrfs_status ietf_verify_dev(vrfs_ctx* ctx, size_t n, const uint8_t* pk, c
   A.var[1] = {output, 64, c, 32, 1};
   A.out_xyz = (uint32_t*)v;
   ST((launch_lincomb<C, 2, 0>(ctx, A)));
-  k_ietf_verify_finish<S><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((uint32_t)n, pk, input, output, c, (const uint32_t*)u,
+  k_ietf_verify_finish<S><<<(unsigned)((n + 128 * FINISH_K - 1) / (128 * FINISH_K)), 128, 0, ctx->stream>>>((uint32_t)n, pk, input, output, c, (const uint32_t*)u,
                                                                                 (const uint32_t*)v, ad, ad_off, (const uint8_t*)valid, out_ok);
   LAUNCHED_AS(ctx, "ietf_verify_finish");
   return VRFS_OK;
@@ -452,8 +449,9 @@ extern "C" vrfs_status vrfs_measure_mac32_peak(vrfs_ctx* ctx, int variant, doubl
   void *out = nullptr, *cyc = nullptr;
   ST(ensure(ctx, BUF_W0, (size_t)threads * blocks * 4, &out));
   ST(ensure(ctx, BUF_W1, 64, &cyc));
-  int iters = (variant == 2 || variant == 3 || variant >= 7) ? 64 : 4096;
-  double macs_per_thread_iter = (variant == 2 || variant == 3 || variant >= 7) ? 32.0 * 136.0 : 32.0;   // field products are counted as 136 MAC32 (the saturated 8-limb model) in every representation
+  const bool field_mul = (variant == 2 || variant == 3 || variant == 7 || variant == 8);
+  int iters = field_mul ? 64 : 4096;
+  double macs_per_thread_iter = field_mul ? 32.0 * 136.0 : 32.0;   // field products are counted as 136 MAC32 (the saturated 8-limb model) in every representation
   float ms = 0;
   for (int rep = 0; rep < 3; rep++) {
     CU(cudaEventRecord(ctx->ev0, ctx->stream));

@@ -55,7 +55,8 @@ template <class S> static void ietf_verify(size_t n, const uint8_t* pk, const ui
                                            const uint8_t* s, const uint8_t* ad, const uint64_t* ad_off, uint8_t* ok) {
   typedef typename S::C C;
   std::vector<typename Grp<C>::Entry> slab(4 * 9);
-  std::vector<uint32_t> u(28), v(28);
+  std::vector<uint32_t> u(28), v(28), us(24 * n), vs(24 * n);
+  std::vector<uint8_t> valids(n);
   for (size_t i = 0; i < n; i++) {
     LincombArgs A = {};
     A.n = (uint32_t)n;
@@ -71,7 +72,14 @@ template <class S> static void ietf_verify(size_t n, const uint8_t* pk, const ui
     const uint8_t* a = ad ? ad + ad_off[i] : (const uint8_t*)"";
     uint32_t alen = ad ? (uint32_t)(ad_off[i + 1] - ad_off[i]) : 0;
     ok[i] = valid && ietf_verify_finish_item<S>(pk + 64 * i, in + 64 * i, out + 64 * i, c + 32 * i, u.data(), v.data(), a, alen);
+    memcpy(&us[24 * i], u.data(), 96); memcpy(&vs[24 * i], v.data(), 96); valids[i] = valid;
   }
+  // the batched-inversion form used by the kernel must agree item by item
+  std::vector<uint8_t> ok2(n, 7);
+  const uint32_t threads = (uint32_t)((n + 2) / 3);
+  for (uint32_t t = 0; t < threads; t++)
+    ietf_verify_finish_batched<S, 3>((uint32_t)n, t, threads, pk, in, out, c, us.data(), vs.data(), ad, ad_off, valids.data(), ok2.data());
+  for (size_t i = 0; i < n; i++) if (ok2[i] != ok[i]) ok[i] = 0xEE;
 }
 extern "C" void hostemu_ietf_verify(int suite, size_t n, const uint8_t* pk, const uint8_t* in, const uint8_t* out, const uint8_t* c,
                                     const uint8_t* s, const uint8_t* ad, const uint64_t* ad_off, uint8_t* ok) {
