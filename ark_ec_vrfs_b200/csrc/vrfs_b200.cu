@@ -196,7 +196,9 @@ struct vrfs_ctx {
   cudaEvent_t tev[MAX_TIMED + 1] = {nullptr};
   const char* tname[MAX_TIMED] = {nullptr};
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;                 // H2D of later chunks overlaps the kernels of earlier ones
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev_chunk[4] = {nullptr, nullptr, nullptr, nullptr};
   char err[512] = {0};
   uint64_t launches = 0;
   DevBuf buf[BUF_COUNT];
@@ -296,6 +298,8 @@ extern "C" vrfs_status vrfs_ctx_create(int device, vrfs_ctx** out) {
   if (prop.major < 10) return fail(ctx, VRFS_CUDA_ERROR, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
   ctx->sms = prop.multiProcessorCount;
   CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 4; i++) CU(cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming));
   CU(cudaEventCreate(&ctx->ev0));
   CU(cudaEventCreate(&ctx->ev1));
   ST(build_fixed_tables<BandCurve>(ctx, VRFS_BANDERSNATCH_ELL2));
@@ -312,6 +316,8 @@ extern "C" void vrfs_ctx_destroy(vrfs_ctx* ctx) {
   for (int s = 0; s < 3; s++) for (int b = 0; b < 2; b++) if (ctx->fixtab[s][b]) cudaFree(ctx->fixtab[s][b]);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  for (int i = 0; i < 4; i++) if (ctx->ev_chunk[i]) cudaEventDestroy(ctx->ev_chunk[i]);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -423,17 +429,34 @@ extern "C" vrfs_status vrfs_ietf_verify_batch(vrfs_ctx* ctx, vrfs_suite suite, s
   if (n == 0) return VRFS_OK;
   if (!pk || !input || !output || !c || !s || !out_ok) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   CU(cudaSetDevice(ctx->device));
-  const uint8_t *d_pk, *d_in, *d_out, *d_c, *d_s, *d_ad;
+  // Host buffers: the batch is cut into a first piece of one resident wave of the lincomb grid and the remainder, the
+  // H2D copies run on their own stream, and the kernels of piece k wait only for piece k's copies - so all but the
+  // first ~20 MB of the 256 B/item input transfer hides behind arithmetic (pinned host memory; pageable memory still
+  // works, the copies then serialise inside the driver).
+  const uint8_t* d_ad;
   const uint64_t* d_off;
-  ST(stage_in(ctx, BUF_IN0, pk, n * 64, &d_pk));
-  ST(stage_in(ctx, BUF_IN1, input, n * 64, &d_in));
-  ST(stage_in(ctx, BUF_IN2, output, n * 64, &d_out));
-  ST(stage_in(ctx, BUF_IN3, c, n * 32, &d_c));
-  ST(stage_in(ctx, BUF_IN4, s, n * 32, &d_s));
+  void *d_pk = nullptr, *d_in = nullptr, *d_out = nullptr, *d_c = nullptr, *d_s = nullptr, *d_ok = nullptr;
+  ST(ensure(ctx, BUF_IN0, n * 64, &d_pk)); ST(ensure(ctx, BUF_IN1, n * 64, &d_in)); ST(ensure(ctx, BUF_IN2, n * 64, &d_out));
+  ST(ensure(ctx, BUF_IN3, n * 32, &d_c)); ST(ensure(ctx, BUF_IN4, n * 32, &d_s)); ST(ensure(ctx, BUF_OUT0, n, &d_ok));
   ST(stage_ad(ctx, n, ad, ad_off, &d_ad, &d_off));
-  void* d_ok = nullptr;
-  ST(ensure(ctx, BUF_OUT0, n, &d_ok));
-  ST(vrfs_ietf_verify_batch_dev(ctx, suite, n, d_pk, d_in, d_out, d_c, d_s, d_ad, d_off, (uint8_t*)d_ok));
+  const size_t wave = (size_t)ctx->sms * LINCOMB_MINBLOCKS * LINCOMB_THREADS;
+  size_t cut[3] = {0, n > 3 * wave ? wave : n, n};
+  const int pieces = cut[1] < n ? 2 : 1;
+  for (int k = 0; k < pieces; k++) {
+    const size_t o = cut[k], m = cut[k + 1] - cut[k];
+    CU(cudaMemcpyAsync((uint8_t*)d_pk + o * 64, pk + o * 64, m * 64, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CU(cudaMemcpyAsync((uint8_t*)d_in + o * 64, input + o * 64, m * 64, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CU(cudaMemcpyAsync((uint8_t*)d_out + o * 64, output + o * 64, m * 64, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CU(cudaMemcpyAsync((uint8_t*)d_c + o * 32, c + o * 32, m * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CU(cudaMemcpyAsync((uint8_t*)d_s + o * 32, s + o * 32, m * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CU(cudaEventRecord(ctx->ev_chunk[k], ctx->copy_stream));
+  }
+  for (int k = 0; k < pieces; k++) {
+    const size_t o = cut[k], m = cut[k + 1] - cut[k];
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[k], 0));
+    ST(vrfs_ietf_verify_batch_dev(ctx, suite, m, (const uint8_t*)d_pk + o * 64, (const uint8_t*)d_in + o * 64, (const uint8_t*)d_out + o * 64,
+                                  (const uint8_t*)d_c + o * 32, (const uint8_t*)d_s + o * 32, d_ad, d_off ? d_off + o : nullptr, (uint8_t*)d_ok + o));
+  }
   CU(cudaMemcpyAsync(out_ok, d_ok, n, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return VRFS_OK;

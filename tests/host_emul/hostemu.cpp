@@ -19,6 +19,7 @@ template <class P> static void field_op(int op, const uint32_t* a, const uint32_
     case 6: r = to_mont_wide<P>(a, b); break;
     case 7: r = Fp<P>::zero(); r.v[0] = is_square(x); break;
     case 8: r = Fp<P>::zero(); r.v[0] = is_high(x) | (is_odd(x) << 1); break;
+    case 9: r = sqr(x); break;                      // dedicated squaring path (SOS reduction)
     default: r = Fp<P>::zero();
   }
   memcpy(out, r.v, 4 * P::N);

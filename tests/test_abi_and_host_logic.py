@@ -81,6 +81,7 @@ def test_montgomery_field_arithmetic(emu, fi):
         a = [0, 1, p - 1, p - 2][t] if t < 4 else rnd.randrange(p)
         b = rnd.randrange(Rm) if t % 2 else rnd.choice([0, 1, p - 1, Rm - 1, p])
         assert _fop(emu, fi, 0, a, b, n) == a * b * Ri % p
+        assert _fop(emu, fi, 9, a, 0, n) == a * a * Ri % p          # dedicated squaring
         b2 = rnd.randrange(p)
         assert _fop(emu, fi, 1, a, b2, n) == (a + b2) % p
         assert _fop(emu, fi, 2, a, b2, n) == (a - b2) % p

@@ -146,7 +146,82 @@ def gen(N):
             L.append(f"    uint32_t c = 0; for (int j = 0; j < {N}; j++) {{ uint64_t t = (uint64_t)a[j] - b[j] - c; r[j] = (uint32_t)t; c = (uint32_t)(t >> 32) & 1u; }} return c;")
         L.append("#endif")
         L.append("  }")
+    L += gen_sqr(N)
     L.append("};")
+    return L
+
+
+def sqr_chains(N):
+    """Triangular squaring a^2 = sum_i a_i * Q_i * 2^(64 i), Q_i = [a_i, 2a_{i+1} (no carry-in), limbs of 2a above i+1]:
+    N(N+1)/2 wide products instead of N^2.  Products of row i land at columns 2i+k; even k go to the even-aligned
+    accumulator e[], odd k to the odd-aligned accumulator o[] (both indexed by absolute column), so that every
+    mad.lo.cc/madc.hi.cc pair covers one aligned 64-bit slot and fuses into IMAD.WIDE.U32(.X).
+    Returns [(acc_name, first_col, [(multiplicand_expr)...], row, emit_carry_out)]"""
+    chains = []
+    touched = {"e": set(), "o": set()}
+    for i in range(N):
+        q = []
+        for k in range(N - i):
+            q.append(f"a[{i}]" if k == 0 else (f"s{i+1}" if k == 1 else f"d[{i+k}]"))
+        for acc, par in (("e", 0), ("o", 1)):
+            ks = [k for k in range(N - i) if k % 2 == par]
+            if not ks:
+                continue
+            first = 2 * i + ks[0]
+            top_hi = 2 * i + ks[-1] + 1
+            carry = (top_hi in touched[acc]) and top_hi + 1 < 2 * N
+            chains.append((acc, first, [q[k] for k in ks], i, carry))
+            for k in ks:
+                touched[acc].add(2 * i + k); touched[acc].add(2 * i + k + 1)
+            if carry:
+                assert top_hi + 1 not in touched[acc], "carry-out must land in an untouched column"
+                touched[acc].add(top_hi + 1)
+    return chains
+
+
+def gen_sqr(N):
+    L = []
+    L.append("  // t[0..2N-1] = a^2 (a < 2^(32N-1)): N(N+1)/2 wide products (see tools/gen_mont_chains.py sqr_chains)")
+    L.append("  static HD_INLINE void sqr_wide(uint32_t* t, const uint32_t* a) {")
+    L.append("#ifdef __CUDA_ARCH__")
+    L.append(f"    uint32_t d[{N}], e[{2*N}], o[{2*N}];")
+    L.append(f"    for (int k = 0; k < {2*N}; k++) {{ e[k] = 0; o[k] = 0; }}")
+    L.append(f"    d[0] = 0; for (int k = 1; k < {N}; k++) d[k] = __funnelshift_l(a[k - 1], a[k], 1);   // limbs of 2a")
+    cur_row = -1
+    for acc, first, mults, row, carry in sqr_chains(N):
+        if row != cur_row:
+            cur_row = row
+            if row + 1 < N:
+                L.append(f"    const uint32_t s{row+1} = a[{row+1}] << 1;")
+        n = len(mults)
+        outs = [f"{acc}[{first + j}]" for j in range(2 * n)] + ([f"{acc}[{first + 2*n}]"] if carry else [])
+        no = len(outs)
+        ins = mults + [f"a[{row}]"]
+        lines = []
+        for j in range(n):
+            lo = "mad.lo.cc.u32" if j == 0 else "madc.lo.cc.u32"
+            hi = "madc.hi.cc.u32" if (j < n - 1 or carry) else "madc.hi.u32"
+            lines.append(f"{lo} %{2*j}, %{no+j}, %{no+n}, %{2*j}")
+            lines.append(f"{hi} %{2*j+1}, %{no+j}, %{no+n}, %{2*j+1}")
+        if carry:
+            lines.append(f"addc.u32 %{2*n}, %{2*n}, 0")
+        L.append(asm_block(lines, outs, ins))
+    # merge t = e + o
+    lines = []
+    for c in range(1, 2 * N):
+        op = "add.cc.u32" if c == 1 else ("addc.cc.u32" if c < 2 * N - 1 else "addc.u32")
+        lines.append(f"{op} %{c-1}, %{c-1}, %{2*N-1+c-1}")
+    L.append(asm_block(lines, [f"e[{c}]" for c in range(1, 2 * N)], [f"o[{c}]" for c in range(1, 2 * N)]))
+    L.append(f"    for (int k = 0; k < {2*N}; k++) t[k] = e[k];")
+    L.append("#else")
+    L.append(f"    unsigned __int128 acc = 0;")
+    L.append(f"    for (int c = 0; c < {2*N}; c++) {{")
+    L.append(f"      unsigned __int128 nxt = 0;")
+    L.append(f"      for (int i = 0; i < {N}; i++) {{ int j = c - i; if (j < 0 || j >= {N}) continue; uint64_t pr = (uint64_t)a[i] * a[j]; acc += (uint32_t)pr; nxt += pr >> 32; }}")
+    L.append(f"      t[c] = (uint32_t)acc; acc = (acc >> 32) + nxt;")
+    L.append("    }")
+    L.append("#endif")
+    L.append("  }")
     return L
 
 
