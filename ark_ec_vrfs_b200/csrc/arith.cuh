@@ -113,6 +113,27 @@ HD_INLINE Fp<P> select(bool c, const Fp<P>& a, const Fp<P>& b) {  // c ? a : b
 template <class P>
 HD_INLINE Fp<P> cneg(const Fp<P>& a, bool c) { return select(c, neg(a), a); }
 
+// Reduction rows m*p of the Montgomery product/square.  For p = 1 - 2^32 (mod 2^64) (BLS12-381 Fr: p[0] = 1,
+// p[1] = 2^32-1, so NINV = -1 and m = -column0) the lowest limb pair of each chain needs no multiplier:
+// m*1 = (0 : m) and m*(2^32-1) = (m - [m != 0] : -m).  VRFS_LOW_SPECIAL=0 keeps the generic rows for comparison.
+#ifndef VRFS_LOW_SPECIAL
+#define VRFS_LOW_SPECIAL 1
+#endif
+template <class P> struct RedRows {
+  typedef MontChains<P::N> C;
+  static constexpr bool SPECIAL = P::LOW_1_FF && VRFS_LOW_SPECIAL;
+  static HD_INLINE uint32_t bm1(uint32_t m) { return m - (m != 0u ? 1u : 0u); }
+  static HD_INLINE void even(uint32_t* acc, uint32_t& top, const uint32_t* mod, uint32_t m) {
+    if (SPECIAL) C::mad_row_lo1(acc, top, mod, m); else C::mad_row(acc, top, mod, m);
+  }
+  static HD_INLINE void odd_top(uint32_t* acc, const uint32_t* mod, uint32_t m) {
+    if (SPECIAL) C::mad_row_top_loff(acc, mod + 1, m, 0u - m, bm1(m)); else C::mad_row_top(acc, mod + 1, m);
+  }
+  static HD_INLINE void odd_shift(uint32_t* u, uint32_t& v0, const uint32_t* mod, uint32_t m) {
+    if (SPECIAL) C::shift_mad_row_loff(u, v0, mod + 1, m, 0u - m, bm1(m)); else C::shift_mad_row(u, v0, mod + 1, m);
+  }
+};
+
 // Montgomery product.  Requires a < p; b may be ANY N-limb value (used to reduce hash outputs).
 // p < 2^(32N-1): interleaved even/odd accumulators, 2N^2+N multiply-accumulates (IMAD.WIDE.U32).
 template <class P>
@@ -129,8 +150,8 @@ HD_INLINE void mont_mul_limbs(uint32_t* out, const uint32_t* a, const uint32_t* 
     C::mul_row(u, a + 1, b[0]);
     {
       uint32_t m = v[0] * P::NINV;
-      C::mad_row_top(u, mod + 1, m);
-      C::mad_row(v, u[N - 1], mod, m);
+      RedRows<P>::odd_top(u, mod, m);
+      RedRows<P>::even(v, u[N - 1], mod, m);
     }
 #pragma unroll
     for (int i = 1; i < N; i++) {
@@ -138,14 +159,14 @@ HD_INLINE void mont_mul_limbs(uint32_t* out, const uint32_t* a, const uint32_t* 
         C::shift_mad_row(v, u[0], a + 1, b[i]);
         C::mad_row(u, v[N - 1], a, b[i]);
         uint32_t m = u[0] * P::NINV;
-        C::mad_row_top(v, mod + 1, m);
-        C::mad_row(u, v[N - 1], mod, m);
+        RedRows<P>::odd_top(v, mod, m);
+        RedRows<P>::even(u, v[N - 1], mod, m);
       } else {
         C::shift_mad_row(u, v[0], a + 1, b[i]);
         C::mad_row(v, u[N - 1], a, b[i]);
         uint32_t m = v[0] * P::NINV;
-        C::mad_row_top(u, mod + 1, m);
-        C::mad_row(v, u[N - 1], mod, m);
+        RedRows<P>::odd_top(u, mod, m);
+        RedRows<P>::even(v, u[N - 1], mod, m);
       }
     }
     // N even: after the last (odd-index) iteration the live odd array is v, the dead-even one is u
@@ -215,12 +236,12 @@ HD_INLINE void mont_sqr_limbs(uint32_t* out, const uint32_t* a) {
   for (int i = 0; i < N; i++) {
     if (i & 1) {   // live-even = u, dead-even (to be shifted) = v
       uint32_t m = (u[0] + v[1]) * P::NINV;
-      C::shift_mad_row(v, u[0], mod + 1, m);
-      C::mad_row(u, v[N - 1], mod, m);
+      RedRows<P>::odd_shift(v, u[0], mod, m);
+      RedRows<P>::even(u, v[N - 1], mod, m);
     } else {
       uint32_t m = (v[0] + u[1]) * P::NINV;
-      C::shift_mad_row(u, v[0], mod + 1, m);
-      C::mad_row(v, u[N - 1], mod, m);
+      RedRows<P>::odd_shift(u, v[0], mod, m);
+      RedRows<P>::even(v, u[N - 1], mod, m);
     }
   }
   // N even: the last step (odd i) left u as the dead-even array (u[0] = 0) and v as the odd-aligned one

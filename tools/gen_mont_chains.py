@@ -105,6 +105,53 @@ def gen(N):
     L.append("#endif")
     L.append("  }")
 
+    # ---- reduction rows for a modulus with p[0] = 1, p[1] = 2^32 - 1 (BLS12-381 Fr): the lowest pair of each chain is
+    #      m*1 = (0 : m)  resp.  m*(2^32-1) = (m - [m != 0] : -m), i.e. two additions instead of one wide multiply
+    L.append("  // mad_row with x[0] == 1: acc[1]:acc[0] += b, remaining pairs multiplied as usual")
+    L.append("  static HD_INLINE void mad_row_lo1(uint32_t* acc, uint32_t& top, const uint32_t* x, uint32_t b) {")
+    L.append("#ifdef __CUDA_ARCH__")
+    no = N + 1
+    lines = [f"add.cc.u32 %0, %0, %{no+H-1}", "addc.cc.u32 %1, %1, 0"]
+    for k in range(1, H):
+        lines.append(f"madc.lo.cc.u32 %{2*k}, %{no+k-1}, %{no+H-1}, %{2*k}")
+        lines.append(f"madc.hi.cc.u32 %{2*k+1}, %{no+k-1}, %{no+H-1}, %{2*k+1}")
+    lines.append(f"addc.u32 %{N}, %{N}, 0")
+    L.append(asm_block(lines, [f"acc[{j}]" for j in range(N)] + ["top"], [f"x[{2*k}]" for k in range(1, H)] + ["b"]))
+    L.append("#else")
+    L.append("    mad_row(acc, top, x, b);")
+    L.append("#endif")
+    L.append("  }")
+    L.append("  // mad_row_top with x[0] == 2^32-1: nb = -b, bm1 = b - (b != 0)")
+    L.append("  static HD_INLINE void mad_row_top_loff(uint32_t* acc, const uint32_t* x, uint32_t b, uint32_t nb, uint32_t bm1) {")
+    L.append("#ifdef __CUDA_ARCH__")
+    no = N
+    lines = [f"add.cc.u32 %0, %0, %{no+H}", f"addc.cc.u32 %1, %1, %{no+H+1}"]
+    for k in range(1, H):
+        hi = "madc.hi.cc.u32" if k < H - 1 else "madc.hi.u32"
+        lines.append(f"madc.lo.cc.u32 %{2*k}, %{no+k-1}, %{no+H-1}, %{2*k}")
+        lines.append(f"{hi} %{2*k+1}, %{no+k-1}, %{no+H-1}, %{2*k+1}")
+    L.append(asm_block(lines, [f"acc[{j}]" for j in range(N)], [f"x[{2*k}]" for k in range(1, H)] + ["b", "nb", "bm1"]))
+    L.append("#else")
+    L.append("    (void)nb; (void)bm1; mad_row_top(acc, x, b);")
+    L.append("#endif")
+    L.append("  }")
+    L.append("  // shift_mad_row with x[0] == 2^32-1")
+    L.append("  static HD_INLINE void shift_mad_row_loff(uint32_t* u, uint32_t& v0, const uint32_t* x, uint32_t b, uint32_t nb, uint32_t bm1) {")
+    L.append("#ifdef __CUDA_ARCH__")
+    no = N + 1
+    lines = [f"add.cc.u32 %{N}, %{N}, %1", f"addc.cc.u32 %0, %{no+H}, %2", f"addc.cc.u32 %1, %{no+H+1}, %3"]
+    for k in range(1, H):
+        a_lo = f"%{2*k+2}" if 2 * k + 2 < N else "0"
+        a_hi = f"%{2*k+3}" if 2 * k + 3 < N else "0"
+        hi = "madc.hi.cc.u32" if k < H - 1 else "madc.hi.u32"
+        lines.append(f"madc.lo.cc.u32 %{2*k}, %{no+k-1}, %{no+H-1}, {a_lo}")
+        lines.append(f"{hi} %{2*k+1}, %{no+k-1}, %{no+H-1}, {a_hi}")
+    L.append(asm_block(lines, [f"u[{j}]" for j in range(N)] + ["v0"], [f"x[{2*k}]" for k in range(1, H)] + ["b", "nb", "bm1"]))
+    L.append("#else")
+    L.append("    (void)nb; (void)bm1; shift_mad_row(u, v0, x, b);")
+    L.append("#endif")
+    L.append("  }")
+
     # ---- merge: u[0..N-2] += v[1..N-1] with carry, u[N-1] += carry
     L.append("  // u[0..N-2] += v[1..N-1], carry into u[N-1]")
     L.append("  static HD_INLINE void merge(uint32_t* u, const uint32_t* v) {")
