@@ -37,6 +37,14 @@ template <class F> HD_INLINE void store_fp_xyz(uint32_t* o, const F& X, const F&
   constexpr int Q = F::N / 4;
   for (int i = 0; i < Q; i++) { d[i] = sx[i]; d[Q + i] = sy[i]; d[2 * Q + i] = sz[i]; }
 }
+HD_INLINE void prefetch_l1(const void* p, unsigned bytes) {
+#ifdef __CUDA_ARCH__
+  for (unsigned o = 0; o < bytes; o += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"((const char*)p + o));
+  if (bytes % 128) asm volatile("prefetch.global.L1 [%0];" ::"l"((const char*)p + bytes - 1));   // entry may straddle two lines
+#else
+  (void)p; (void)bytes;
+#endif
+}
 template <class T> HD_INLINE void copy_words16(T* dst, const T* src_) {  // sizeof(T) % 16 == 0, both 16-byte aligned
   const uint4* s = reinterpret_cast<const uint4*>(src_);
   uint4* d = reinterpret_cast<uint4*>(dst);
@@ -219,6 +227,13 @@ HD_INLINE bool lincomb_item(const LincombArgs& A, uint32_t item, typename Grp<C>
     for (int t = 0; t < NT; t++) add_window_bias<G::KB_LIMBS>(kb[t], 0x88888888u, G::KB_LIMBS > 8 ? 8 : G::KB_LIMBS);
 #pragma unroll 1
     for (int w = G::WINDOWS - 1; w >= 0; w--) {
+      // the table entries of this window do not depend on acc: pull them into L1 while the four doublings run
+      // (the slab is L2/DRAM-resident; without this the loads below stall ~7 % of the kernel's issue slots)
+#pragma unroll
+      for (int t = 0; t < NT; t++) {
+        int d = (G::KB_LIMBS > 8 && w == 64) ? (int)kb[t][8] : digit4(kb[t], w);
+        prefetch_l1(&slab[t * TBL_ENTRIES + (d < 0 ? -d : d)], sizeof(typename G::Entry));
+      }
       if (w != G::WINDOWS - 1) G::dbl4(&acc);
 #pragma unroll
       for (int t = 0; t < NT; t++) {
@@ -240,6 +255,10 @@ HD_INLINE bool lincomb_item(const LincombArgs& A, uint32_t item, typename Grp<C>
     bool neg = A.fix[f].negate != 0;
 #pragma unroll 1
     for (int w = 0; w < G::FIX_WINDOWS; w++) {
+      if (w + 1 < G::FIX_WINDOWS) {   // next window's entry -> L1 while this addition runs
+        int dn = w + 1 == 32 ? (int)k[8] : digit8(k, w + 1);
+        prefetch_l1(&tbl[(w + 1) * FIX_ENTRIES + (dn < 0 ? -dn : dn)], sizeof(typename G::FixEntry));
+      }
       int d = w == 32 ? (int)k[8] : digit8(k, w);
       int idx = d < 0 ? -d : d;
       typename G::FixEntry e;
