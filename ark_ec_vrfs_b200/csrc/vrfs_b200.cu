@@ -8,6 +8,7 @@
 
 #include "../../include/vrfs_b200.h"
 #include "h2c.cuh"
+#include "wire.cuh"
 #include "msm.cuh"
 
 using namespace vrfs;
@@ -186,7 +187,8 @@ struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
 };
-enum { BUF_IN0, BUF_IN1, BUF_IN2, BUF_IN3, BUF_IN4, BUF_AD, BUF_OFF, BUF_OUT0, BUF_OUT1, BUF_W0, BUF_W1, BUF_W2, BUF_W3, BUF_VALID, BUF_SLAB, BUF_COUNT };
+enum { BUF_IN0, BUF_IN1, BUF_IN2, BUF_IN3, BUF_IN4, BUF_AD, BUF_OFF, BUF_OUT0, BUF_OUT1, BUF_W0, BUF_W1, BUF_W2, BUF_W3, BUF_VALID, BUF_SLAB,
+       BUF_X0, BUF_X1, BUF_X2, BUF_X3, BUF_X4, BUF_COUNT };   // X*: wire-format staging (encoded keys, signatures, h2c data, flags)
 
 #define MAX_TIMED 64
 struct vrfs_ctx {
@@ -922,6 +924,176 @@ extern "C" vrfs_status vrfs_pedersen_verify_batch(vrfs_ctx* ctx, vrfs_suite suit
   ST(suite == VRFS_BANDERSNATCH_ELL2 ? pedersen_verify_dev<BandSuite>(ctx, n, d_in, d_out, d_pr, d_ad, d_off, d_ok)
      : suite == VRFS_ED25519_TAI ? pedersen_verify_dev<EdSuite>(ctx, n, d_in, d_out, d_pr, d_ad, d_off, d_ok) : pedersen_verify_dev<P256Suite>(ctx, n, d_in, d_out, d_pr, d_ad, d_off, d_ok));
   ST(copy_out(ctx, out_ok, d_ok, n));
+  return finish_call(ctx);
+}
+
+// =================================================================================================
+// wire formats: serialised keys / signatures in, verdicts out
+// =================================================================================================
+// Public / Output deserialisation: codec decode + on-curve + prime-order subgroup.  One thread per encoded point; `enc_b`
+// (stride_b) is an optional second array processed by threads n..2n-1 (the verify path decodes keys and gammas together).
+template <class S> __global__ void __launch_bounds__(ITEM_THREADS) k_decode_checked(uint32_t n, const uint8_t* enc_a, uint32_t stride_a, uint8_t* out_a,
+                                                                                     const uint8_t* enc_b, uint32_t stride_b, uint8_t* out_b, uint8_t* flags) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (enc_b ? 2 * n : n)) return;
+  const bool second = t >= n;
+  const uint32_t i = second ? t - n : t;
+  const uint8_t* e = second ? enc_b + (size_t)stride_b * i : enc_a + (size_t)stride_a * i;
+  uint8_t tmp[S::ENC_LEN];
+  for (int j = 0; j < S::ENC_LEN; j++) tmp[j] = e[j];
+  flags[t] = (uint8_t)wire_decode_point_checked<S>((second ? out_b : out_a) + (size_t)64 * i, tmp);
+}
+template <class S> __global__ void __launch_bounds__(ITEM_THREADS) k_subgroup_check(uint32_t n, const uint8_t* pts, uint8_t* out_ok) {
+  ITEM_INDEX(n);
+  typedef typename S::C C;
+  typename C::F x, y;
+  bool inf = false;
+  bool ok = load_affine<C>(x, y, &inf, pts + (size_t)64 * i);
+  out_ok[i] = (uint8_t)(ok && (inf || SubgroupCheck<C>::run(x, y)));
+}
+// ietf::Proof deserialisation + merge of the two point flags
+template <class S> __global__ void __launch_bounds__(ITEM_THREADS) k_wire_parse_proof(uint32_t n, const uint8_t* sig, const uint8_t* flags2, uint8_t* c, uint8_t* s, uint8_t* valid) {
+  ITEM_INDEX(n);
+  constexpr int SL = S::ENC_LEN + S::CLEN + 32;
+  bool ok = wire_parse_proof<S>(c + (size_t)32 * i, s + (size_t)32 * i, sig + (size_t)SL * i + S::ENC_LEN);
+  valid[i] = (uint8_t)(ok && flags2[i] && flags2[n + i]);
+}
+template <class S> __global__ void __launch_bounds__(ITEM_THREADS) k_wire_pack_sig(uint32_t n, const uint8_t* output, const uint8_t* c, const uint8_t* s, const uint8_t* ok, uint8_t* sig) {
+  ITEM_INDEX(n);
+  constexpr int SL = S::ENC_LEN + S::CLEN + 32;
+  uint8_t* o = sig + (size_t)SL * i;
+  if (!ok[i]) { for (int j = 0; j < SL; j++) o[j] = 0; return; }
+  uint8_t tmp[SL];
+  wire_pack_signature<S>(tmp, output + (size_t)64 * i, c + (size_t)32 * i, s + (size_t)32 * i);
+  for (int j = 0; j < SL; j++) o[j] = tmp[j];
+}
+// out_ok &= a & b; rejected items get a zero hash
+__global__ void k_merge_flags(uint32_t n, const uint8_t* a, const uint8_t* b, uint8_t* out_ok, uint8_t* hash, uint32_t hlen) {
+  ITEM_INDEX(n);
+  uint8_t ok = out_ok[i] & a[i] & (b ? b[i] : 1);
+  out_ok[i] = ok;
+  if (hash && !ok) for (uint32_t j = 0; j < hlen; j++) hash[(size_t)hlen * i + j] = 0;
+}
+
+extern "C" int vrfs_suite_ietf_signature_len(vrfs_suite s) { return vrfs_suite_point_enc_len(s) + vrfs_suite_challenge_len(s) + 32; }
+
+template <class S> static vrfs_status decode_checked_launch(vrfs_ctx* ctx, size_t n, const uint8_t* a, uint32_t sa, uint8_t* oa, const uint8_t* b, uint32_t sb, uint8_t* ob, uint8_t* flags) {
+  const size_t threads = b ? 2 * n : n;
+  k_decode_checked<S><<<item_blocks(threads), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, a, sa, oa, b, sb, ob, flags);
+  LAUNCHED_AS(ctx, "decode_checked");
+  return VRFS_OK;
+}
+extern "C" vrfs_status vrfs_point_decode_checked_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* enc, uint8_t* out_pts, uint8_t* out_ok) {
+  if (!ctx) return VRFS_BAD_ARG;
+  if (n == 0) return VRFS_OK;
+  if (!enc || !out_pts || !out_ok) return fail(ctx, VRFS_BAD_ARG, "null buffer");
+  if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
+  ST(begin_call(ctx, n));
+  const uint32_t el = (uint32_t)vrfs_suite_point_enc_len(suite);
+  const uint8_t* d_e; uint8_t *d_p, *d_ok;
+  ST(stage_in(ctx, BUF_X0, enc, n * el, &d_e)); ST(stage_out(ctx, BUF_OUT0, n * 64, &d_p)); ST(stage_out(ctx, BUF_OUT1, n, &d_ok));
+  ST(suite == VRFS_BANDERSNATCH_ELL2 ? decode_checked_launch<BandSuite>(ctx, n, d_e, el, d_p, nullptr, 0, nullptr, d_ok)
+     : suite == VRFS_ED25519_TAI ? decode_checked_launch<EdSuite>(ctx, n, d_e, el, d_p, nullptr, 0, nullptr, d_ok)
+                                 : decode_checked_launch<P256Suite>(ctx, n, d_e, el, d_p, nullptr, 0, nullptr, d_ok));
+  ST(copy_out(ctx, out_pts, d_p, n * 64)); ST(copy_out(ctx, out_ok, d_ok, n));
+  return finish_call(ctx);
+}
+extern "C" vrfs_status vrfs_subgroup_check_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* pts, uint8_t* out_ok) {
+  if (!ctx) return VRFS_BAD_ARG;
+  if (n == 0) return VRFS_OK;
+  if (!pts || !out_ok) return fail(ctx, VRFS_BAD_ARG, "null buffer");
+  if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
+  ST(begin_call(ctx, n));
+  const uint8_t* d_p; uint8_t* d_ok;
+  ST(stage_in(ctx, BUF_IN0, pts, n * 64, &d_p)); ST(stage_out(ctx, BUF_OUT0, n, &d_ok));
+  if (suite == VRFS_BANDERSNATCH_ELL2) k_subgroup_check<BandSuite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_p, d_ok);
+  else if (suite == VRFS_ED25519_TAI) k_subgroup_check<EdSuite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_p, d_ok);
+  else k_subgroup_check<P256Suite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_p, d_ok);
+  LAUNCHED_AS(ctx, "subgroup_check");
+  ST(copy_out(ctx, out_ok, d_ok, n));
+  return finish_call(ctx);
+}
+
+// Secret -> signature: Input::new(data), Secret::output, ietf::Prover::prove, serialise
+template <class S> static vrfs_status ietf_sign_wire_dev(vrfs_ctx* ctx, size_t n, const uint8_t* sk, const uint8_t* data, const uint64_t* data_off,
+                                                         const uint8_t* ad, const uint64_t* ad_off, uint8_t* input, uint8_t* output, uint8_t* c, uint8_t* s,
+                                                         uint8_t* h2c_ok, uint8_t* sig) {
+  k_data_to_point<S><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, data, data_off, input, h2c_ok);
+  LAUNCHED_AS(ctx, "data_to_point");
+  ST(output_dev<S>(ctx, n, sk, input, output));
+  ST(ietf_prove_dev<S>(ctx, n, sk, input, output, ad, ad_off, c, s));
+  k_wire_pack_sig<S><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, output, c, s, h2c_ok, sig);
+  LAUNCHED_AS(ctx, "wire_pack_sig");
+  return VRFS_OK;
+}
+extern "C" vrfs_status vrfs_ietf_sign_wire_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* sk, const uint8_t* data, const uint64_t* data_off,
+                                                 const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_sig, uint8_t* out_ok) {
+  if (!ctx) return VRFS_BAD_ARG;
+  if (n == 0) return VRFS_OK;
+  if (!sk || !data_off || !out_sig) return fail(ctx, VRFS_BAD_ARG, "null buffer");
+  if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
+  ST(begin_call(ctx, n));
+  const size_t sl = (size_t)vrfs_suite_ietf_signature_len(suite);
+  const uint8_t *d_sk, *d_ad, *d_data; const uint64_t *d_off, *d_doff;
+  uint8_t *d_in, *d_out, *d_c, *d_s, *d_ok, *d_sig;
+  ST(stage_in(ctx, BUF_IN0, sk, n * 32, &d_sk));
+  ST(stage_ad(ctx, n, ad, ad_off, &d_ad, &d_off));
+  for (size_t i = 0; i < n; i++) if (data_off[i + 1] < data_off[i]) return fail(ctx, VRFS_BAD_ARG, "offsets must be non-decreasing");
+  if (data_off[n] > 0 && !data) return fail(ctx, VRFS_BAD_ARG, "null data buffer with non-empty offsets");
+  { const uint8_t* o; ST(stage_in(ctx, BUF_X2, data, (size_t)data_off[n], &d_data)); ST(stage_in(ctx, BUF_X3, data_off, (n + 1) * sizeof(uint64_t), &o)); d_doff = (const uint64_t*)o; }
+  ST(stage_out(ctx, BUF_IN1, n * 64, &d_in)); ST(stage_out(ctx, BUF_IN2, n * 64, &d_out)); ST(stage_out(ctx, BUF_IN3, n * 32, &d_c)); ST(stage_out(ctx, BUF_IN4, n * 32, &d_s));
+  ST(stage_out(ctx, BUF_X4, n, &d_ok)); ST(stage_out(ctx, BUF_X1, n * sl, &d_sig));
+  ST(suite == VRFS_BANDERSNATCH_ELL2 ? ietf_sign_wire_dev<BandSuite>(ctx, n, d_sk, d_data, d_doff, d_ad, d_off, d_in, d_out, d_c, d_s, d_ok, d_sig)
+     : suite == VRFS_ED25519_TAI ? ietf_sign_wire_dev<EdSuite>(ctx, n, d_sk, d_data, d_doff, d_ad, d_off, d_in, d_out, d_c, d_s, d_ok, d_sig)
+                                 : ietf_sign_wire_dev<P256Suite>(ctx, n, d_sk, d_data, d_doff, d_ad, d_off, d_in, d_out, d_c, d_s, d_ok, d_sig));
+  ST(copy_out(ctx, out_sig, d_sig, n * sl));
+  if (out_ok) ST(copy_out(ctx, out_ok, d_ok, n));
+  return finish_call(ctx);
+}
+
+// serialised Public + data + signature -> verdict (+ Output::hash of accepted items)
+template <class S> static vrfs_status ietf_verify_wire_dev(vrfs_ctx* ctx, size_t n, const uint8_t* pk_enc, const uint8_t* data, const uint64_t* data_off, const uint8_t* sig,
+                                                           const uint8_t* ad, const uint64_t* ad_off, uint8_t* pk, uint8_t* input, uint8_t* output, uint8_t* c, uint8_t* s,
+                                                           uint8_t* flags /*4n*/, uint8_t* out_ok, uint8_t* out_hash) {
+  constexpr uint32_t SL = S::ENC_LEN + S::CLEN + 32;
+  ST((decode_checked_launch<S>(ctx, n, pk_enc, S::ENC_LEN, pk, sig, SL, output, flags)));
+  k_wire_parse_proof<S><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, sig, flags, c, s, flags + 2 * n);
+  LAUNCHED_AS(ctx, "wire_parse_proof");
+  k_data_to_point<S><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, data, data_off, input, flags + 3 * n);
+  LAUNCHED_AS(ctx, "data_to_point");
+  ST(ietf_verify_dev<S>(ctx, n, pk, input, output, c, s, ad, ad_off, out_ok));
+  if (out_hash) {
+    k_point_to_hash<S><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, output, out_hash);
+    LAUNCHED_AS(ctx, "point_to_hash");
+  }
+  k_merge_flags<<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, flags + 2 * n, flags + 3 * n, out_ok, out_hash, (uint32_t)S::HLEN);
+  LAUNCHED_AS(ctx, "merge_flags");
+  return VRFS_OK;
+}
+extern "C" vrfs_status vrfs_ietf_verify_wire_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* pk_enc, const uint8_t* data, const uint64_t* data_off,
+                                                   const uint8_t* sig, const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_ok, uint8_t* out_hash) {
+  if (!ctx) return VRFS_BAD_ARG;
+  if (n == 0) return VRFS_OK;
+  if (!pk_enc || !data_off || !sig || !out_ok) return fail(ctx, VRFS_BAD_ARG, "null buffer");
+  if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
+  ST(begin_call(ctx, n));
+  const size_t sl = (size_t)vrfs_suite_ietf_signature_len(suite), el = (size_t)vrfs_suite_point_enc_len(suite), hl = (size_t)vrfs_suite_hash_len(suite);
+  const uint8_t *d_pke, *d_sig, *d_ad, *d_data; const uint64_t *d_off, *d_doff;
+  uint8_t *d_pk, *d_in, *d_out, *d_c, *d_s, *d_flags, *d_ok, *d_hash = nullptr;
+  ST(stage_in(ctx, BUF_X0, pk_enc, n * el, &d_pke)); ST(stage_in(ctx, BUF_X1, sig, n * sl, &d_sig));
+  ST(stage_ad(ctx, n, ad, ad_off, &d_ad, &d_off));
+  for (size_t i = 0; i < n; i++) if (data_off[i + 1] < data_off[i]) return fail(ctx, VRFS_BAD_ARG, "offsets must be non-decreasing");
+  if (data_off[n] > 0 && !data) return fail(ctx, VRFS_BAD_ARG, "null data buffer with non-empty offsets");
+  { const uint8_t* o; ST(stage_in(ctx, BUF_X2, data, (size_t)data_off[n], &d_data)); ST(stage_in(ctx, BUF_X3, data_off, (n + 1) * sizeof(uint64_t), &o)); d_doff = (const uint64_t*)o; }
+  ST(stage_out(ctx, BUF_IN0, n * 64, &d_pk)); ST(stage_out(ctx, BUF_IN1, n * 64, &d_in)); ST(stage_out(ctx, BUF_IN2, n * 64, &d_out));
+  ST(stage_out(ctx, BUF_IN3, n * 32, &d_c)); ST(stage_out(ctx, BUF_IN4, n * 32, &d_s)); ST(stage_out(ctx, BUF_X4, 4 * n, &d_flags));
+  ST(stage_out(ctx, BUF_OUT0, n, &d_ok));
+  if (out_hash) ST(stage_out(ctx, BUF_OUT1, n * hl, &d_hash));
+  ST(suite == VRFS_BANDERSNATCH_ELL2 ? ietf_verify_wire_dev<BandSuite>(ctx, n, d_pke, d_data, d_doff, d_sig, d_ad, d_off, d_pk, d_in, d_out, d_c, d_s, d_flags, d_ok, d_hash)
+     : suite == VRFS_ED25519_TAI ? ietf_verify_wire_dev<EdSuite>(ctx, n, d_pke, d_data, d_doff, d_sig, d_ad, d_off, d_pk, d_in, d_out, d_c, d_s, d_flags, d_ok, d_hash)
+                                 : ietf_verify_wire_dev<P256Suite>(ctx, n, d_pke, d_data, d_doff, d_sig, d_ad, d_off, d_pk, d_in, d_out, d_c, d_s, d_flags, d_ok, d_hash));
+  ST(copy_out(ctx, out_ok, d_ok, n));
+  if (out_hash) ST(copy_out(ctx, out_hash, d_hash, n * hl));
   return finish_call(ctx);
 }
 

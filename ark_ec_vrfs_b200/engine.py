@@ -170,6 +170,37 @@ class Engine:
         self._call("vrfs_ietf_prove_batch", suite, C.c_size_t(n), _p(sk), _p(inp), _p(outp), _p(adb), _p(off), _p(c), _p(s))
         return c, s
 
+    # ---- wire formats (CanonicalSerialize / CanonicalDeserialize of Public, Output, ietf::Proof)
+    def ietf_signature_len(self, suite):
+        return int(self._lib.vrfs_suite_ietf_signature_len(suite))
+
+    def point_decode_checked(self, suite, enc):
+        """`Public` / `Output` deserialisation: codec decode + on-curve + prime-order-subgroup check."""
+        enc = _u8(enc, (-1, self.point_enc_len(suite))); n = len(enc)
+        pts = np.zeros((n, 64), np.uint8); ok = np.zeros(n, np.uint8)
+        self._call("vrfs_point_decode_checked_batch", suite, C.c_size_t(n), _p(enc), _p(pts), _p(ok))
+        return pts, ok
+
+    def subgroup_check(self, suite, pts):
+        pts = _u8(pts, (-1, 64)); n = len(pts); ok = np.zeros(n, np.uint8)
+        self._call("vrfs_subgroup_check_batch", suite, C.c_size_t(n), _p(pts), _p(ok))
+        return ok
+
+    def ietf_sign_wire(self, suite, sk, datas, ad=None):
+        """signature_i = point_encode(Output) || c || s for Input::new(datas[i]); returns (sig (n, sig_len), ok)."""
+        sk = _u8(sk, (-1, 32)); n = len(sk); data, doff = pack_var(datas); adb, off = pack_var(ad)
+        sig = np.zeros((n, self.ietf_signature_len(suite)), np.uint8); ok = np.zeros(n, np.uint8)
+        self._call("vrfs_ietf_sign_wire_batch", suite, C.c_size_t(n), _p(sk), _p(data), _p(doff), _p(adb), _p(off), _p(sig), _p(ok))
+        return sig, ok
+
+    def ietf_verify_wire(self, suite, pk_enc, datas, sig, ad=None, want_hash=True):
+        """serialised public keys + VRF input data + signatures -> (ok, beta) with beta = Output::hash of accepted items."""
+        pk_enc = _u8(pk_enc, (-1, self.point_enc_len(suite))); n = len(pk_enc)
+        sig = _u8(sig, (n, self.ietf_signature_len(suite))); data, doff = pack_var(datas); adb, off = pack_var(ad)
+        ok = np.zeros(n, np.uint8); h = np.zeros((n, self.hash_len(suite)), np.uint8) if want_hash else None
+        self._call("vrfs_ietf_verify_wire_batch", suite, C.c_size_t(n), _p(pk_enc), _p(data), _p(doff), _p(sig), _p(adb), _p(off), _p(ok), _p(h))
+        return (ok, h) if want_hash else ok
+
     # ---- pedersen
     def pedersen_prove(self, suite, sk, inp, outp, ad=None):
         sk = _u8(sk, (-1, 32)); n = len(sk); inp = _u8(inp, (n, 64)); outp = _u8(outp, (n, 64))

@@ -93,6 +93,26 @@ vrfs_status vrfs_pedersen_prove_batch(vrfs_ctx*, vrfs_suite, size_t n, const uin
 vrfs_status vrfs_pedersen_verify_batch(vrfs_ctx*, vrfs_suite, size_t n, const uint8_t* input, const uint8_t* output, const uint8_t* proof,
                                        const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_ok);
 
+/* Wire formats: the serialised forms `CanonicalSerialize/Deserialize` (Compress::Yes, Validate::Yes)
+ * give `Public`, `Output` and `ietf::Proof` (names at /root/reference/src/lib.rs:13-17), so that keys and signatures
+ * can be verified straight off the wire:
+ *   encoded point : Codec::point_encode bytes (32 B arkworks / 33 B SEC1); deserialisation = canonical + on curve +
+ *                   prime-order subgroup (the reference: ark-ec `mul_bigint(r).is_zero()`; here a 2-descent for
+ *                   Bandersnatch, [L]P for Ed25519, nothing for cofactor-1 secp256r1 - same predicate)
+ *   proof         : c (CHALLENGE_LEN bytes, codec byte order, reduced mod r) || s (32 bytes, rejected when >= r)
+ *   signature     : point_encode(Output) || proof   (Bandersnatch 96 B, Ed25519 80 B, secp256r1 81 B = RFC 9381 pi_string) */
+int vrfs_suite_ietf_signature_len(vrfs_suite s);
+vrfs_status vrfs_point_decode_checked_batch(vrfs_ctx*, vrfs_suite, size_t n, const uint8_t* enc, uint8_t* out_pts /*n*64*/, uint8_t* out_ok);
+vrfs_status vrfs_subgroup_check_batch(vrfs_ctx*, vrfs_suite, size_t n, const uint8_t* pts /*n*64*/, uint8_t* out_ok);
+/* Input::new(data_i) -> Secret::output -> ietf::Prover::prove -> serialise.  out_ok may be NULL (0 = no input point found). */
+vrfs_status vrfs_ietf_sign_wire_batch(vrfs_ctx*, vrfs_suite, size_t n, const uint8_t* sk, const uint8_t* data, const uint64_t* data_off,
+                                      const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_sig /*n*sig_len*/, uint8_t* out_ok);
+/* Public::deserialize + Input::new(data_i) + Output/Proof::deserialize + ietf::Verifier::verify.  out_hash (may be NULL):
+ * Output::hash of the accepted items (zero for rejected ones), n*hash_len. */
+vrfs_status vrfs_ietf_verify_wire_batch(vrfs_ctx*, vrfs_suite, size_t n, const uint8_t* pk_enc /*n*enc_len*/, const uint8_t* data,
+                                        const uint64_t* data_off, const uint8_t* sig /*n*sig_len*/, const uint8_t* ad,
+                                        const uint64_t* ad_off, uint8_t* out_ok, uint8_t* out_hash);
+
 /* ring commitment MSM (ark-ec VariableBaseMSM::msm behind ring-proof's KZG commit):
  * n_columns scalar columns (column-major, n*32 bytes each) over one base vector of n affine G1 points.
  * out: n_columns * 96 bytes affine. */

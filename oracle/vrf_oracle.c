@@ -798,6 +798,88 @@ void oracle_pedersen_verify_batch(int suite, size_t n, const uint8_t *input, con
 }
 
 /* ======================================================================================
+ * Wire formats: what ark-serialize's CanonicalDeserialize (Compress::Yes, Validate::Yes) accepts for
+ * `Public` / `Output` (codec point + on-curve + ark-ec's default `is_in_correct_subgroup_assuming_on_curve`, i.e.
+ * mul_bigint(r).is_zero()) and for `ietf::Proof` (c: CHALLENGE_LEN bytes through the codec's scalar_decode, i.e. reduced
+ * mod r; s: a canonical scalar, rejected when >= r).  Byte layout per A.9: c || s in codec byte order.  [RECALL] for the
+ * two scalar rules; the point rules are arkworks' documented behaviour.
+ * signature = point_encode(Output) || c || s   (Bandersnatch 96 B; secp256r1 81 B = RFC 9381 pi_string)
+ * ====================================================================================== */
+static int in_prime_subgroup(const curve *C, const aff *A) {
+    if (!C->is_te) return 1;                       /* cofactor 1 */
+    const fctx *F = C->F; proj p, r; pt_from_aff(C, &p, A);
+    pt_mul(C, &r, C->Fr->p.v, C->Fr->n, &p);
+    /* ark-ec twisted_edwards::Projective::is_zero: x == 0 && y == z && y != 0 && t == 0 */
+    return f_is_zero(F, &r.X) && f_eq(F, &r.Y, &r.Z) && !f_is_zero(F, &r.Y) && f_is_zero(F, &r.T);
+}
+static int dec_point_checked(const suite_t *S, aff *A, const uint8_t *in) {
+    return dec_point(S, A, in) && aff_on_curve(S->C, A) && in_prime_subgroup(S->C, A);
+}
+static void it_subgroup(void *p, size_t i) {
+    bctx *x = p; aff A; int ok = load_point(x->S->C, &A, x->a + 64 * i) && aff_on_curve(x->S->C, &A) && in_prime_subgroup(x->S->C, &A);
+    x->o1[i] = (uint8_t)ok;
+}
+void oracle_subgroup_check_batch(int suite, size_t n, const uint8_t *pts, uint8_t *out_ok, int nthreads) {
+    bctx x = {0}; x.S = get_suite(suite); x.a = pts; x.o1 = out_ok; parallel_for(n, nthreads, it_subgroup, &x);
+}
+static void it_dec_checked(void *p, size_t i) {
+    bctx *x = p; aff A; size_t L = x->S->sec1 ? 33 : 32; int ok = dec_point_checked(x->S, &A, x->a + L * i);
+    x->o2[i] = (uint8_t)ok; if (ok) store_point(x->S->C, &A, x->o1 + 64 * i); else memset(x->o1 + 64 * i, 0, 64);
+}
+void oracle_point_decode_checked_batch(int suite, size_t n, const uint8_t *enc, uint8_t *out_pts, uint8_t *out_ok, int nthreads) {
+    bctx x = {0}; x.S = get_suite(suite); x.a = enc; x.o1 = out_pts; x.o2 = out_ok; parallel_for(n, nthreads, it_dec_checked, &x);
+}
+int oracle_ietf_signature_len(int suite) { const suite_t *S = get_suite(suite); return (S->sec1 ? 33 : 32) + S->clen + 32; }
+/* c (canonical raw) -> CHALLENGE_LEN bytes in codec order */
+static void enc_challenge(const suite_t *S, const fe *c_raw, uint8_t *out) {
+    uint8_t t[32]; fe k = *c_raw; store_scalar(&k, t);
+    if (S->sec1) for (int i = 0; i < S->clen; i++) out[i] = t[S->clen - 1 - i]; else memcpy(out, t, (size_t)S->clen);
+}
+static void it_sign_wire(void *p, size_t i) {
+    bctx *x = p; const suite_t *S = x->S; const curve *C = S->C; size_t PL = S->sec1 ? 33 : 32, SL = PL + (size_t)S->clen + 32;
+    uint8_t *sig = x->o1 + SL * i; fe sk, c, s; aff I, O;
+    load_scalar(C, &sk, x->a + 32 * i);
+    if (!data_to_point(S, &I, x->b + x->off[i], (size_t)(x->off[i + 1] - x->off[i]))) { memset(sig, 0, SL); x->o2[i] = 0; return; }
+    aff_mul(C, &O, &sk, &I);
+    const uint8_t *ad = x->c ? x->c + ((const uint64_t *)x->d)[i] : (const uint8_t *)"";
+    size_t adlen = x->c ? (size_t)(((const uint64_t *)x->d)[i + 1] - ((const uint64_t *)x->d)[i]) : 0;
+    ietf_prove_one(S, &sk, &I, &O, ad, adlen, &c, &s);
+    enc_point(S, &O, sig); enc_challenge(S, &c, sig + PL); enc_scalar(S, &s, sig + PL + S->clen);
+    x->o2[i] = 1;
+}
+/* Secret::from(sk): Input::new(data) -> Secret::output -> ietf::Prover::prove -> serialise */
+void oracle_ietf_sign_wire_batch(int suite, size_t n, const uint8_t *sk, const uint8_t *data, const uint64_t *data_off,
+                                 const uint8_t *ad, const uint64_t *ad_off, uint8_t *out_sig, uint8_t *out_ok, int nthreads) {
+    bctx x = {0}; x.S = get_suite(suite); x.a = sk; x.b = data; x.off = data_off; x.c = ad; x.d = (const uint8_t *)ad_off; x.o1 = out_sig; x.o2 = out_ok;
+    parallel_for(n, nthreads, it_sign_wire, &x);
+}
+static void it_verify_wire(void *p, size_t i) {
+    bctx *x = p; const suite_t *S = x->S; const curve *C = S->C; size_t PL = S->sec1 ? 33 : 32, SL = PL + (size_t)S->clen + 32;
+    const uint8_t *sig = x->e + SL * i; aff Y, I, O; fe c, s, m;
+    x->o1[i] = 0; if (x->o2) memset(x->o2 + (size_t)(S->is512 ? 64 : 32) * i, 0, S->is512 ? 64 : 32);
+    if (!dec_point_checked(S, &Y, x->a + PL * i)) return;                                /* Public::deserialize_compressed */
+    if (!dec_point_checked(S, &O, sig)) return;                                          /* Output */
+    if (!C->is_te && (Y.inf || O.inf)) return;
+    uint8_t le[32] = {0};                                                                /* Proof.c: clen bytes, reduced mod r */
+    for (int j = 0; j < S->clen; j++) le[j] = S->sec1 ? sig[PL + S->clen - 1 - j] : sig[PL + j];
+    f_from_bytes_mod(C->Fr, &m, le, 32, 0); f_to_raw(C->Fr, &c, &m);
+    for (int j = 0; j < 32; j++) le[j] = S->sec1 ? sig[PL + S->clen + 31 - j] : sig[PL + S->clen + j];   /* Proof.s: canonical */
+    if (!f_from_le_canonical(C->Fr, &m, le)) return;
+    f_to_raw(C->Fr, &s, &m);
+    if (!data_to_point(S, &I, x->b + x->off[i], (size_t)(x->off[i + 1] - x->off[i]))) return;   /* Input::new */
+    const uint8_t *ad = x->c ? x->c + ((const uint64_t *)x->d)[i] : (const uint8_t *)"";
+    size_t adlen = x->c ? (size_t)(((const uint64_t *)x->d)[i + 1] - ((const uint64_t *)x->d)[i]) : 0;
+    if (!ietf_verify_one(S, &Y, &I, &O, &c, &s, ad, adlen)) return;
+    x->o1[i] = 1; if (x->o2) suite_point_to_hash(S, &O, x->o2 + (size_t)(S->is512 ? 64 : 32) * i);
+}
+/* Public::deserialize + Input::new(data) + Output/Proof::deserialize + ietf::Verifier::verify (+ Output::hash for accepted items) */
+void oracle_ietf_verify_wire_batch(int suite, size_t n, const uint8_t *pk_enc, const uint8_t *data, const uint64_t *data_off, const uint8_t *sig,
+                                   const uint8_t *ad, const uint64_t *ad_off, uint8_t *out_ok, uint8_t *out_hash, int nthreads) {
+    bctx x = {0}; x.S = get_suite(suite); x.a = pk_enc; x.b = data; x.off = data_off; x.e = sig; x.c = ad; x.d = (const uint8_t *)ad_off; x.o1 = out_ok; x.o2 = out_hash;
+    parallel_for(n, nthreads, it_verify_wire, &x);
+}
+
+/* ======================================================================================
  * BLS12-381 G1 MSM  (ark-ec VariableBaseMSM::msm -> msm_bigint: Pippenger with
  * c = 3 for n < 32, else ln(n) + 2; per-window bucket accumulation + running sum; windows
  * combined MSB-first with c doublings).  rayon parallelises over windows; so do we.

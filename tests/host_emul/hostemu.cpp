@@ -138,3 +138,23 @@ extern "C" void hostemu_f29_roundtrip(const uint32_t* fp_in, uint32_t* fp_out, i
   Fp<BlsFr> z = f29_to_fp(y);
   memcpy(fp_out, z.v, 32);
 }
+
+// wire formats (csrc/wire.cuh) on the host: checked point decode, proof parse, signature pack
+#include "../../ark_ec_vrfs_b200/csrc/wire.cuh"
+template <class S> static void wire_decode_checked(size_t n, const uint8_t* enc, uint8_t* out, uint8_t* ok) {
+  for (size_t i = 0; i < n; i++) ok[i] = wire_decode_point_checked<S>(out + 64 * i, enc + (size_t)S::ENC_LEN * i);
+}
+extern "C" void hostemu_decode_checked(int suite, size_t n, const uint8_t* enc, uint8_t* out, uint8_t* ok) {
+  if (suite == 0) wire_decode_checked<BandSuite>(n, enc, out, ok);
+  else if (suite == 1) wire_decode_checked<EdSuite>(n, enc, out, ok);
+  else wire_decode_checked<P256Suite>(n, enc, out, ok);
+}
+template <class S> static void wire_roundtrip(const uint8_t* out64, const uint8_t* c32, const uint8_t* s32, uint8_t* sig, uint8_t* c_back, uint8_t* s_back, uint8_t* ok) {
+  wire_pack_signature<S>(sig, out64, c32, s32);
+  *ok = wire_parse_proof<S>(c_back, s_back, sig + S::ENC_LEN);
+}
+extern "C" void hostemu_wire_roundtrip(int suite, const uint8_t* out64, const uint8_t* c32, const uint8_t* s32, uint8_t* sig, uint8_t* c_back, uint8_t* s_back, uint8_t* ok) {
+  if (suite == 0) wire_roundtrip<BandSuite>(out64, c32, s32, sig, c_back, s_back, ok);
+  else if (suite == 1) wire_roundtrip<EdSuite>(out64, c32, s32, sig, c_back, s_back, ok);
+  else wire_roundtrip<P256Suite>(out64, c32, s32, sig, c_back, s_back, ok);
+}

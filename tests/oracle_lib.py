@@ -148,3 +148,34 @@ def msm_g1(bases, scalars, n_columns=1, nthreads=NTHREADS):
 def g1_mul_gen(scalars, nthreads=NTHREADS):
     scalars = _u8(scalars, (-1, 32)); n = len(scalars); out = np.zeros((n, 96), np.uint8)
     lib().oracle_g1_mul_gen_batch(C.c_size_t(n), _p(scalars), _p(out), nthreads); return out
+
+
+# ---- wire formats ----------------------------------------------------------------------
+def subgroup_check(suite, pts, nthreads=NTHREADS):
+    pts = _u8(pts, (-1, 64)); n = len(pts); ok = np.zeros(n, np.uint8)
+    lib().oracle_subgroup_check_batch(suite, C.c_size_t(n), _p(pts), _p(ok), nthreads); return ok
+
+
+def point_decode_checked(suite, enc, nthreads=NTHREADS):
+    L = lib().oracle_point_enc_len(suite); enc = _u8(enc, (-1, L)); n = len(enc)
+    out = np.zeros((n, 64), np.uint8); ok = np.zeros(n, np.uint8)
+    lib().oracle_point_decode_checked_batch(suite, C.c_size_t(n), _p(enc), _p(out), _p(ok), nthreads); return out, ok
+
+
+def ietf_signature_len(suite):
+    return int(lib().oracle_ietf_signature_len(suite))
+
+
+def ietf_sign_wire(suite, sk, datas, ads=None, nthreads=NTHREADS):
+    sk = _u8(sk, (-1, 32)); n = len(sk); data, off = pack_var(datas); ad, aoff = _ad(ads, n)
+    sig = np.zeros((n, ietf_signature_len(suite)), np.uint8); ok = np.zeros(n, np.uint8)
+    lib().oracle_ietf_sign_wire_batch(suite, C.c_size_t(n), _p(sk), _p(data), _p(off), _p(ad), _p(aoff), _p(sig), _p(ok), nthreads)
+    return sig, ok
+
+
+def ietf_verify_wire(suite, pk_enc, datas, sig, ads=None, want_hash=True, nthreads=NTHREADS):
+    L = lib().oracle_point_enc_len(suite); pk_enc = _u8(pk_enc, (-1, L)); n = len(pk_enc)
+    sig = _u8(sig, (n, ietf_signature_len(suite))); data, off = pack_var(datas); ad, aoff = _ad(ads, n)
+    ok = np.zeros(n, np.uint8); h = np.zeros((n, lib().oracle_hash_len(suite)), np.uint8) if want_hash else None
+    lib().oracle_ietf_verify_wire_batch(suite, C.c_size_t(n), _p(pk_enc), _p(data), _p(off), _p(sig), _p(ad), _p(aoff), _p(ok), _p(h), nthreads)
+    return (ok, h) if want_hash else ok
