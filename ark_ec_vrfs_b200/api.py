@@ -16,6 +16,12 @@ import numpy as np
 from .engine import Engine, BANDERSNATCH, ED25519, P256
 
 
+# prime subgroup orders, used only to judge whether a serialised scalar is canonical
+_ORDER = {BANDERSNATCH: 0x1cfb69d4ca675f520cce760202687600ff8f87007419047174fd06b52876e7e1,
+          ED25519: 2**252 + 27742317777372353535851937790883648493,
+          P256: 0xffffffff00000000ffffffffffffffffbce6faada7179e84f3b9cac2fc632551}
+
+
 class Error(Exception):
     """mirror of ark_vrf::Error for whole-call failures; per-item failures come back as flags"""
 
@@ -60,6 +66,20 @@ class Public:
     def encode(self):
         return self.suite.engine.point_encode(self.suite.suite_id, self.points)
 
+    serialize_compressed = encode
+
+    @classmethod
+    def deserialize_compressed(cls, suite, enc):
+        """CanonicalDeserialize with validation (canonical, on curve, prime-order subgroup) -> (Public, ok flags)"""
+        pts, ok = suite.engine.point_decode_checked(suite.suite_id, enc)
+        return cls(suite, pts), ok
+
+    @staticmethod
+    def verify_signatures(suite, pk_enc, datas, signatures, ad=None):
+        """serialised keys + VRF input data + serialised signatures (Output || ietf::Proof) -> (ok flags, Output::hash);
+        one call: deserialise, Input::new, verify, hash"""
+        return suite.engine.ietf_verify_wire(suite.suite_id, pk_enc, datas, signatures, ad)
+
 
 @dataclass
 class Input:
@@ -82,6 +102,14 @@ class Output:
         """Output::hash = Suite::point_to_hash"""
         return self.suite.engine.point_to_hash(self.suite.suite_id, self.points)
 
+    def serialize_compressed(self):
+        return self.suite.engine.point_encode(self.suite.suite_id, self.points)
+
+    @classmethod
+    def deserialize_compressed(cls, suite, enc):
+        pts, ok = suite.engine.point_decode_checked(suite.suite_id, enc)
+        return cls(suite, pts), ok
+
 
 @dataclass
 class IetfProof:
@@ -95,6 +123,19 @@ class IetfProof:
             return np.concatenate([self.c[:, :cl][:, ::-1], self.s[:, ::-1]], axis=1)
         return np.concatenate([self.c[:, :cl], self.s], axis=1)
 
+    @classmethod
+    def from_bytes(cls, suite, raw):
+        """inverse of to_bytes; returns (proof, ok) - ok = 0 where s is not a canonical scalar (the engine reduces c mod r)"""
+        cl = suite.CHALLENGE_LEN
+        raw = np.asarray(raw, np.uint8).reshape(-1, cl + 32)
+        be = suite.suite_id == P256
+        c = np.zeros((len(raw), 32), np.uint8)
+        c[:, :cl] = raw[:, :cl][:, ::-1] if be else raw[:, :cl]
+        s = np.ascontiguousarray(raw[:, cl:][:, ::-1] if be else raw[:, cl:])
+        r = _ORDER[suite.suite_id]
+        ok = np.array([int.from_bytes(x.tobytes(), "little") < r for x in s], np.uint8)
+        return cls(c, s), ok
+
 
 @dataclass
 class PedersenProof:
@@ -105,6 +146,24 @@ class PedersenProof:
     ok = property(lambda self: self.raw[:, 128:192])
     s = property(lambda self: self.raw[:, 192:224])
     sb = property(lambda self: self.raw[:, 224:256])
+
+    def to_bytes(self, suite):
+        """CanonicalSerialize: point_encode(pk_com) || point_encode(r) || point_encode(ok) || s || sb (160 B for the 32-byte codecs)"""
+        e = suite.engine; sid = suite.suite_id
+        sc = (lambda a: a[:, ::-1]) if sid == P256 else (lambda a: a)
+        return np.concatenate([e.point_encode(sid, self.pk_com), e.point_encode(sid, self.r), e.point_encode(sid, self.ok), sc(self.s), sc(self.sb)], axis=1)
+
+    @classmethod
+    def from_bytes(cls, suite, raw):
+        """CanonicalDeserialize with validation of the three points -> (proof, ok flags)"""
+        e = suite.engine; sid = suite.suite_id; L = e.point_enc_len(sid)
+        raw = np.asarray(raw, np.uint8).reshape(-1, 3 * L + 64)
+        pts, oks = zip(*(e.point_decode_checked(sid, np.ascontiguousarray(raw[:, k * L:(k + 1) * L])) for k in range(3)))
+        sc = (lambda a: a[:, ::-1]) if sid == P256 else (lambda a: a)
+        s, sb = sc(raw[:, 3 * L:3 * L + 32]), sc(raw[:, 3 * L + 32:])
+        r = _ORDER[sid]
+        canon = np.array([int.from_bytes(a.tobytes(), "little") < r and int.from_bytes(b.tobytes(), "little") < r for a, b in zip(s, sb)], np.uint8)
+        return cls(np.ascontiguousarray(np.concatenate(list(pts) + [s, sb], axis=1))), oks[0] & oks[1] & oks[2] & canon
 
 
 @dataclass
@@ -128,6 +187,10 @@ class Secret:
         """ietf::Prover::prove"""
         c, s = self.suite.engine.ietf_prove(self.suite.suite_id, self.scalars, input.points, output.points, ad)
         return IetfProof(c, s)
+
+    def sign(self, datas, ad=None):
+        """Input::new(data) -> output -> ietf prove -> serialised signatures point_encode(Output) || c || s; returns (sig, ok)"""
+        return self.suite.engine.ietf_sign_wire(self.suite.suite_id, self.scalars, datas, ad)
 
     def pedersen_prove(self, input, output, ad=None):
         """pedersen::Prover::prove -> (Proof, blinding)"""

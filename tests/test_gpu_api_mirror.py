@@ -29,4 +29,21 @@ def test_prove_verify_roundtrip(ctor):
     # Pedersen key commitment opens to the public key: pk_com - blinding*B == pk is checked by the verifier
     # equations above; here just the shapes of the typed accessors
     assert ped.pk_com.shape == (n, 64) and ped.s.shape == (n, 32) and blinding.shape == (n, 32)
+    # serialisation round trips (CanonicalSerialize / CanonicalDeserialize of Public, Output, ietf::Proof, pedersen::Proof)
+    proof2, pok = api.IetfProof.from_bytes(suite, wire)
+    assert pok.all() and np.array_equal(proof2.c, proof.c) and np.array_equal(proof2.s, proof.s)
+    public2, kok = api.Public.deserialize_compressed(suite, public.serialize_compressed())
+    output2, ook = api.Output.deserialize_compressed(suite, output.serialize_compressed())
+    assert kok.all() and ook.all() and np.array_equal(public2.points, public.points) and np.array_equal(output2.points, output.points)
+    assert public2.verify(input, output2, ad, proof2).all()
+    ped_wire = ped.to_bytes(suite)
+    assert ped_wire.shape == (n, 3 * suite.engine.point_enc_len(suite.suite_id) + 64)
+    ped2, dok = api.PedersenProof.from_bytes(suite, ped_wire)
+    assert dok.all() and np.array_equal(ped2.raw, ped.raw) and api.pedersen_verify(suite, input, output, ad, ped2).all()
+    # one-call signatures off the wire
+    datas = [b"foo-%d" % i for i in range(n)]
+    sig, sok = secret.sign(datas, ad)
+    assert sok.all() and np.array_equal(sig, np.concatenate([output.serialize_compressed(), wire], axis=1))
+    vok, beta = api.Public.verify_signatures(suite, public.serialize_compressed(), datas, sig, ad)
+    assert vok.all() and np.array_equal(beta, output.hash())
     suite.engine.close()
