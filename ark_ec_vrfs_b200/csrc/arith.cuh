@@ -16,11 +16,13 @@
 #define HD_NOINLINE static __device__ __noinline__   // free functions
 #define HD_NOINLINE_M __device__ __noinline__        // member functions
 #define VRFS_CONST_TABLE __device__ __constant__
+#define VRFS_GLOBAL_TABLE __device__ const            // per-thread indexed tables: global memory (L1/L2), not the constant bank
 #else   // host emulation build (g++, tests only)
 #define HD_INLINE inline
 #define HD_NOINLINE static
 #define HD_NOINLINE_M
 #define VRFS_CONST_TABLE static const
+#define VRFS_GLOBAL_TABLE static const
 #endif
 
 #include "gen/mont_chains.cuh"
@@ -297,14 +299,19 @@ struct ExpPM2 { template <class P> static HD_INLINE uint32_t get(int i) { return
 struct ExpPM1H { template <class P> static HD_INLINE uint32_t get(int i) { return P::pm1h(i); } };
 template <class P, class E>
 HD_NOINLINE Fp<P> pow_const(const Fp<P>& a) {
+  // 4-bit fixed windows, MSB first: 32N squarings + at most 8N + 14 products (bit-serial square-and-multiply needed
+  // ~16N products); the exponent is public, so the table index and the skip of zero windows are warp-uniform
+  Fp<P> tbl[16];
+  tbl[0] = Fp<P>::one(); tbl[1] = a;
+#pragma unroll 1
+  for (int i = 2; i < 16; i++) tbl[i] = (i & 1) ? tbl[i - 1] * a : sqr(tbl[i >> 1]);
   Fp<P> acc = Fp<P>::one();
   bool started = false;
-  for (int i = P::N * 32 - 1; i >= 0; i--) {
-    if (started) acc = sqr(acc);
-    if ((E::template get<P>(i >> 5) >> (i & 31)) & 1u) {
-      acc = started ? acc * a : a;
-      started = true;
-    }
+#pragma unroll 1
+  for (int i = P::N * 8 - 1; i >= 0; i--) {
+    const uint32_t d = (E::template get<P>(i >> 3) >> ((i & 7) * 4)) & 15u;
+    if (started) { acc = sqr(acc); acc = sqr(acc); acc = sqr(acc); acc = sqr(acc); }
+    if (d) { acc = started ? acc * tbl[d] : tbl[d]; started = true; }
   }
   return acc;
 }

@@ -3,7 +3,9 @@
 // (`utils::hash_to_curve_tai_rfc_9381`), both named at /root/reference/src/lib.rs:13-17; exact byte
 // layouts in SURVEY.md A.5 (incl. ark-ff's 48-byte Z_pad).  Also codec point_decode (A.2).
 #pragma once
+#include <type_traits>
 #include "suite.cuh"
+#include "gen/bls_torsion.cuh"
 
 namespace vrfs {
 
@@ -13,7 +15,7 @@ struct ExpTM1H { template <class P> static HD_INLINE uint32_t get(int i) { retur
 // conditional moves).  Returns false (out unspecified) if a is not a square.  WHICH root is returned is
 // irrelevant to callers: every use fixes the sign afterwards (parity / "is_high" flag).
 template <class P>
-HD_NOINLINE bool sqrt_ct(Fp<P>* out, const Fp<P>* a_) {
+HD_NOINLINE bool sqrt_ts(Fp<P>* out, const Fp<P>* a_) {
   typedef Fp<P> F;
   const F a = *a_;
   F w = pow_const<P, ExpTM1H>(a);       // a^((t-1)/2)
@@ -35,6 +37,81 @@ HD_NOINLINE bool sqrt_ct(Fp<P>* out, const Fp<P>* a_) {
   return sqr(z) == a;
 }
 
+// ---- BLS12-381 Fr (Bandersnatch base field), q - 1 = 2^32 t: the 2^32-torsion part of a^t is resolved by a
+// Pohlig-Hellman discrete logarithm over four 8-bit windows with precomputed tables (gen/bls_torsion.cuh) instead of
+// Tonelli-Shanks' quadratic loop: with g = 5^t, a^t = g^k,  a square <=> k even,  sqrt(a) = a^((t+1)/2) g^(-k/2),
+// 1/a = (a^((t-1)/2))^2 g^(-k).  One exponentiation therefore yields the square root, the quadratic character AND
+// the inverse - which makes Elligator2 and point decompression inversion-free.
+HD_INLINE Fp<BlsFr> bls_torsion_w(int i, uint32_t j) {
+  Fp<BlsFr> r;
+  const uint4* p = reinterpret_cast<const uint4*>(&BLS_TORSION_W[i][j][0]);
+  uint4 a = p[0], b = p[1];
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+HD_INLINE uint32_t bls_torsion_lookup(const Fp<BlsFr>& x) {    // x = g^(2^24 j) -> j
+  return BLS_TORSION_HASH[(x.v[0] * BLS_TORSION_HASH_MUL) >> BLS_TORSION_HASH_SHIFT];
+}
+// k with tt = g^k, tt in the 2^32-torsion
+HD_NOINLINE uint32_t bls_torsion_dlog(const Fp<BlsFr>* tt) {
+  typedef Fp<BlsFr> F;
+  F y0 = *tt, y1 = y0;
+#pragma unroll 1
+  for (int i = 0; i < 8; i++) y1 = sqr(y1);
+  F y2 = y1;
+#pragma unroll 1
+  for (int i = 0; i < 8; i++) y2 = sqr(y2);
+  F y3 = y2;
+#pragma unroll 1
+  for (int i = 0; i < 8; i++) y3 = sqr(y3);
+  uint32_t k0 = bls_torsion_lookup(y3);
+  uint32_t k1 = bls_torsion_lookup(y2 * bls_torsion_w(2, k0));
+  uint32_t k2 = bls_torsion_lookup(y1 * bls_torsion_w(1, k0) * bls_torsion_w(2, k1));
+  uint32_t k3 = bls_torsion_lookup(y0 * bls_torsion_w(0, k0) * bls_torsion_w(1, k1) * bls_torsion_w(2, k2));
+  return k0 | (k1 << 8) | (k2 << 16) | (k3 << 24);
+}
+// g^(-m)
+HD_NOINLINE Fp<BlsFr> bls_torsion_pow_neg(uint32_t m) {
+  return bls_torsion_w(0, m & 255u) * bls_torsion_w(1, (m >> 8) & 255u) * bls_torsion_w(2, (m >> 16) & 255u) * bls_torsion_w(3, m >> 24);
+}
+// a != 0:  w = a^((t-1)/2),  z = a^((t+1)/2),  k = log_g(a^t)
+HD_INLINE void bls_sqrt_parts(Fp<BlsFr>& w, Fp<BlsFr>& z, uint32_t& k, const Fp<BlsFr>& a) {
+  w = pow_const<BlsFr, ExpTM1H>(a);
+  z = w * a;
+  Fp<BlsFr> tt = z * w;
+  k = bls_torsion_dlog(&tt);
+}
+HD_NOINLINE bool bls_sqrt(Fp<BlsFr>* out, const Fp<BlsFr>* a_) {
+  typedef Fp<BlsFr> F;
+  const F a = *a_;
+  if (a.is_zero()) { *out = F::zero(); return true; }
+  F w, z; uint32_t k;
+  bls_sqrt_parts(w, z, k, a);
+  if (k & 1u) return false;
+  *out = z * bls_torsion_pow_neg(k >> 1);
+  return sqr(*out) == a;
+}
+template <class P> HD_INLINE bool sqrt_ct(Fp<P>* out, const Fp<P>* a) {
+  if constexpr (std::is_same<P, BlsFr>::value) return bls_sqrt(out, a); else return sqrt_ts<P>(out, a);
+}
+// x with x^2 = num/den (den != 0), no inversion: false if num/den is not a square.  Also usable for other fields (generic path).
+template <class P> HD_INLINE bool sqrt_ratio(Fp<P>* x, const Fp<P>& num, const Fp<P>& den) {
+  Fp<P> x2 = num * inv(den);
+  if (x2.is_zero()) { *x = Fp<P>::zero(); return true; }
+  return sqrt_ct<P>(x, &x2);
+}
+template <> HD_INLINE bool sqrt_ratio<BlsFr>(Fp<BlsFr>* x, const Fp<BlsFr>& num, const Fp<BlsFr>& den) {
+  typedef Fp<BlsFr> F;
+  if (num.is_zero()) { *x = F::zero(); return true; }
+  F a = num * den, w, z; uint32_t k;
+  bls_sqrt_parts(w, z, k, a);
+  if (k & 1u) return false;
+  F r = z * bls_torsion_pow_neg(k >> 1);              // sqrt(num den)
+  F ia = sqr(w) * bls_torsion_pow_neg(k);             // 1/(num den)
+  *x = r * num * ia;                                  // sqrt(num den)/den
+  return sqr(*x) * den == num;
+}
+
 // ---- Elligator2 for Bandersnatch (A.5): Montgomery J = A, K = B, Z = 5; result in extended TE coordinates
 HD_NOINLINE void band_elligator2(TEPoint<BandCurve>* out, const Fp<BlsFr>* u_) {
   typedef Fp<BlsFr> F;
@@ -42,20 +119,31 @@ HD_NOINLINE void band_elligator2(TEPoint<BandCurve>* out, const Fp<BlsFr>* u_) {
   const F one = F::one(), JK = fconst<BlsFr, K::ELL2_JK>(), KSQI = fconst<BlsFr, K::ELL2_KSQI>(), Kc = fconst<BlsFr, K::ELL2_K>();
   F u = *u_;
   F uu = sqr(u);
-  F den = dbl(dbl(uu)) + uu + one;                   // 1 + Z*u^2, Z = 5
-  if (den.is_zero()) den = one;
-  F x1 = neg(JK * inv(den));
-  F t = sqr(x1);
-  F gx1 = t * x1 + t * JK + x1 * KSQI;               // g(x) = x^3 + (J/K) x^2 + x/K^2
-  F x2 = neg(x1) - JK;
-  t = sqr(x2);
-  F gx2 = t * x2 + t * JK + x2 * KSQI;
-  F y1, y2;
-  bool sq1 = gx1.is_zero() | sqrt_ct<BlsFr>(&y1, &gx1);
-  if (gx1.is_zero()) y1 = F::zero();
-  bool sq2 = sqrt_ct<BlsFr>(&y2, &gx2);
-  (void)sq2;                                          // exactly one of gx1, gx2 is a square (Z non-square)
-  F x = select(sq1, x1, x2), y = select(sq1, y1, y2);
+  F D = dbl(dbl(uu)) + uu + one;                     // 1 + Z*u^2, Z = 5 (never 0: -1/5 is not a square)
+  if (D.is_zero()) D = one;
+  // x1 = N/D with N = -J/K;  g(x1) = G1/D^4 with G1 = N (N^2 + (J/K) N D + D^2/K^2) D, so sqrt(g(x1)) = sqrt(G1)/D^2 and
+  // 1/D = N (N^2 + ...)/G1: one exponentiation (bls_sqrt_parts) gives the root, the character and the inverse.
+  const F N = neg(JK);
+  F ND = N * D, NP = N * (sqr(N) + JK * ND + KSQI * sqr(D));
+  F G1 = NP * D;
+  F x, y;
+  bool sq1;
+  if (G1.is_zero()) {                                // x1 is a root of g: y = 0 (measure-zero case, plain inversion)
+    sq1 = true; x = N * inv(D); y = F::zero();
+  } else {
+    F w, z; uint32_t k;
+    bls_sqrt_parts(w, z, k, G1);
+    sq1 = !(k & 1u);
+    F invD = NP * sqr(w) * bls_torsion_pow_neg(k);   // NP / G1
+    F x1 = N * invD;
+    // k even: sqrt(G1) = z g^(-k/2).  k odd: g(x2) = Z u^2 g(x1) and (Z G1)^t = g^(k+1) (Z = 5 generates the torsion part),
+    // so sqrt(g(x2)) = u Z^((t+1)/2) z g^(-(k+1)/2) / D^2
+    uint32_t m = (uint32_t)(((unsigned long long)k + (k & 1u)) >> 1);
+    F r = z * bls_torsion_pow_neg(m);
+    if (!sq1) r = r * fconst<BlsFr, K::ELL2_C2>() * u;
+    y = r * sqr(invD);
+    x = sq1 ? x1 : neg(x1) - JK;
+  }
   if (is_odd(y) != sq1) y = neg(y);                   // sgn0(y) = 1 on the first branch, 0 on the second
   F s = x * Kc, tm = y * Kc;                          // Montgomery (s, t) -> TE (s/t, (s-1)/(s+1))
   F sp1 = s + one, sm1 = s - one;
@@ -119,9 +207,7 @@ HD_INLINE bool ark_decode_point(typename C::F& x, typename C::F& y, const uint8_
   y = to_mont<typename C::Fq>(raw);
   F yy = sqr(y), num = F::one() - yy, den = C::mul_a(F::one()) - C::d() * yy;
   if (den.is_zero()) return false;
-  F x2 = num * inv(den);
-  if (x2.is_zero()) x = F::zero();
-  else if (!sqrt_ct<typename C::Fq>(&x, &x2)) return false;
+  if (!sqrt_ratio<typename C::Fq>(&x, num, den)) return false;
   if (is_high(x) != sign) x = neg(x);
   return true;
 }

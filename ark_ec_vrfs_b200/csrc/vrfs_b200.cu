@@ -363,7 +363,6 @@ static vrfs_status ietf_verify_dev(vrfs_ctx* ctx, size_t n, const uint8_t* pk, c
                                    const uint8_t* s, const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_ok) {
   typedef typename S::C C;
   void *u = nullptr, *v = nullptr, *valid = nullptr;
-  ST(timing_begin(ctx));
   ST(ensure(ctx, BUF_W0, n * 96, &u));
   ST(ensure(ctx, BUF_W1, n * 96, &v));
   ST(ensure(ctx, BUF_VALID, n, &valid));
@@ -396,6 +395,7 @@ extern "C" vrfs_status vrfs_ietf_verify_batch_dev(vrfs_ctx* ctx, vrfs_suite suit
   if (n > 0x7fffffffu) return fail(ctx, VRFS_BAD_ARG, "batch too large (n < 2^31)");
   if (!aligned16(pk) || !aligned16(input) || !aligned16(output) || !aligned16(c) || !aligned16(s)) return fail(ctx, VRFS_BAD_ARG, "device buffers must be 16-byte aligned");
   CU(cudaSetDevice(ctx->device));
+  ST(timing_begin(ctx));
   switch (suite) {
     case VRFS_BANDERSNATCH_ELL2: return ietf_verify_dev<BandSuite>(ctx, n, pk, input, output, c, s, ad, ad_off, out_ok);
     case VRFS_ED25519_TAI: return ietf_verify_dev<EdSuite>(ctx, n, pk, input, output, c, s, ad, ad_off, out_ok);

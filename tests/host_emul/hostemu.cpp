@@ -158,3 +158,17 @@ extern "C" void hostemu_wire_roundtrip(int suite, const uint8_t* out64, const ui
   else if (suite == 1) wire_roundtrip<EdSuite>(out64, c32, s32, sig, c_back, s_back, ok);
   else wire_roundtrip<P256Suite>(out64, c32, s32, sig, c_back, s_back, ok);
 }
+
+// Suite::data_to_point for Bandersnatch (Elligator2 with the table-based torsion logarithm) and a bare square root
+extern "C" void hostemu_band_h2c(const uint8_t* data, uint32_t len, uint8_t* out64) {
+  TEPoint<BandCurve> P;
+  band_h2c_ell2(P, data, len);
+  Fp<BlsFr> zi = inv(P.Z);
+  store_affine_bytes<BandCurve>(out64, P.X * zi, P.Y * zi);
+}
+extern "C" int hostemu_bls_sqrt(const uint32_t* a_mont, uint32_t* out_mont) {
+  Fp<BlsFr> a, r; memcpy(a.v, a_mont, 32);
+  bool ok = sqrt_ct<BlsFr>(&r, &a);
+  memcpy(out_mont, r.v, 32);
+  return ok;
+}

@@ -102,3 +102,32 @@ def test_proof_bytes_roundtrip_device_code(emu, suite):
         s2 = np.frombuffer(big.to_bytes(32, "little"), np.uint8).copy()
         emu.hostemu_wire_roundtrip(suite, p(out), p(c), p(s2), p(sig), p(cb), p(sb), p(ok))
         assert ok[0] == 0
+
+
+def test_bls_fr_sqrt_and_elligator2_device_code(emu):
+    """csrc/h2c.cuh on the host: the Pohlig-Hellman square root of BLS12-381 Fr against big-integer arithmetic, and the
+    inversion-free Elligator2 data_to_point against the oracle (incl. the upstream vector inputs)."""
+    import random
+    q = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
+    Rm = 1 << 256
+    rnd = random.Random(3)
+    nsq = 0
+    for i in range(300):
+        a = [0, 1, q - 1, 4, 5][i] if i < 5 else rnd.randrange(q)
+        A = (C.c_uint32 * 8)(*[((a * Rm % q) >> (32 * k)) & 0xFFFFFFFF for k in range(8)]); out = (C.c_uint32 * 8)()
+        ok = emu.hostemu_bls_sqrt(A, out)
+        is_sq = a == 0 or pow(a, (q - 1) // 2, q) == 1
+        assert bool(ok) == is_sq, a
+        if is_sq:
+            r = sum(int(out[k]) << (32 * k) for k in range(8)) * pow(Rm, -1, q) % q
+            assert r * r % q == a
+            nsq += 1
+    assert 100 < nsq < 200
+    datas = [b"", b"\x0a", b"sample"] + [bytes((i * 7 + j) & 0xFF for j in range(i % 90)) for i in range(120)]
+    pts_o, ok_o = O.data_to_point(O.BANDERSNATCH, datas)
+    assert ok_o.all()
+    for d, p in zip(datas, pts_o):
+        out = np.zeros(64, np.uint8)
+        buf = np.frombuffer(d, np.uint8).copy() if d else np.zeros(1, np.uint8)
+        emu.hostemu_band_h2c(buf.ctypes.data_as(C.c_void_p), len(d), out.ctypes.data_as(C.c_void_p))
+        assert np.array_equal(out, p), d

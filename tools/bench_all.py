@@ -35,6 +35,10 @@ for suite, name in (() if os.environ.get("MSM_ONLY") else ((0, "bandersnatch"), 
     t, okv = best(lambda: e.ietf_verify(suite, pk, inp, out, c, s)); r["ietf_verify"] = n / t; assert okv.all()
     t, (pr, bl) = best(lambda: e.pedersen_prove(suite, sk, inp, out)); r["pedersen_prove"] = n / t
     t, okp = best(lambda: e.pedersen_verify(suite, inp, out, pr)); r["pedersen_verify"] = n / t; assert okp.all()
+    pk_enc = e.point_encode(suite, pk); alphas_packed = vrfs.pack_var(alphas)
+    t, (sig, sok) = best(lambda: e.ietf_sign_wire(suite, sk, alphas_packed)); r["ietf_sign_wire"] = n / t; assert sok.all()
+    t, (okw, beta) = best(lambda: e.ietf_verify_wire(suite, pk_enc, alphas_packed, sig)); r["ietf_verify_wire"] = n / t; assert okw.all()
+    ow, bw = O.ietf_verify_wire(suite, pk_enc[sub], [alphas[i] for i in sub], sig[sub]); assert ow.all() and np.array_equal(bw, beta[sub])
     # oracle cross-check on a subsample
     assert np.array_equal(O.data_to_point(suite, [alphas[i] for i in sub])[0], inp[sub])
     co, so = O.ietf_prove(suite, sk[sub], inp[sub], out[sub]); assert np.array_equal(co, c[sub]) and np.array_equal(so, s[sub])
