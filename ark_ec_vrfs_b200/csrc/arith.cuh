@@ -136,6 +136,30 @@ template <class P> struct RedRows {
   }
 };
 
+// ---- pseudo-Mersenne fields p = 2^(32N-1) - c (2^255 - 19): values are PLAIN residues (the generated constants use the
+// representation factor 1, so one() = 1, to_mont/from_mont degenerate to a reduction / a copy), a product is the 2N-limb
+// schoolbook product (N^2 wide multiply-accumulates) followed by folding with 2^(32N) = 2c: N more multiply-accumulates
+// instead of the N^2 + N of a Montgomery reduction.  t < 2^(64N-1).
+template <class P>
+HD_INLINE void pm_fold(uint32_t* out, const uint32_t* t) {
+  constexpr int N = P::N;
+  typedef MontChains<N> C;
+  uint32_t v[N], u[N], r[N], addend[N];
+  for (int i = 0; i < N; i++) v[i] = t[i];
+  C::mul_row(u, t + N + 1, 2u * P::PM_C);         // odd limbs of the high half: u[j] sits at column j+1
+  C::mad_row(v, u[N - 1], t + N, 2u * P::PM_C);   // even limbs at columns 0,2,..; the carry out of column N-1 joins column N
+  C::merge(u, v);                                  // value = v[0] + (u[0..N-1] << 32)
+  r[0] = v[0];
+  for (int j = 1; j < N; j++) r[j] = u[j - 1];
+  const uint32_t top = (u[N - 1] << 1) | (r[N - 1] >> 31);   // bits at and above 2^(32N-1): at most a few dozen
+  r[N - 1] &= 0x7fffffffu;
+  addend[0] = top * P::PM_C;
+  for (int j = 1; j < N; j++) addend[j] = 0;
+  C::add(r, r, addend);                            // < 2^(32N-1) + 2^10
+  cond_sub_p<P>(r, 0u);
+  for (int i = 0; i < N; i++) out[i] = r[i];
+}
+
 // Montgomery product.  Requires a < p; b may be ANY N-limb value (used to reduce hash outputs).
 // p < 2^(32N-1): interleaved even/odd accumulators, 2N^2+N multiply-accumulates (IMAD.WIDE.U32).
 template <class P>
@@ -143,7 +167,11 @@ HD_INLINE void mont_mul_limbs(uint32_t* out, const uint32_t* a, const uint32_t* 
   constexpr int N = P::N;
   typedef MontChains<N> C;
   uint32_t mod[N];
-  if (!P::FULL) {
+  if (P::PM_C != 0) {
+    uint32_t t[2 * N];
+    C::mul_wide(t, a, b);
+    pm_fold<P>(out, t);
+  } else if (!P::FULL) {
     const uint32_t z = opaque_zero();
     for (int i = 0; i < N; i++) mod[i] = P::mod(i) ^ z;
     uint32_t u[N], v[N];
@@ -229,6 +257,7 @@ HD_INLINE void mont_sqr_limbs(uint32_t* out, const uint32_t* a) {
   typedef MontChains<N> C;
   if (P::FULL || !VRFS_DEDICATED_SQR) { mont_mul_limbs<P>(out, a, a); return; }
   uint32_t t[2 * N], mod[N], u[N], v[N];
+  if (P::PM_C != 0) { C::sqr_wide(t, a); pm_fold<P>(out, t); return; }
   const uint32_t z = opaque_zero();
   for (int i = 0; i < N; i++) mod[i] = P::mod(i) ^ z;
   C::sqr_wide(t, a);

@@ -194,6 +194,7 @@ def gen(N):
         L.append("#endif")
         L.append("  }")
     L += gen_sqr(N)
+    L += gen_mul_wide(N)
     L.append("};")
     return L
 
@@ -266,6 +267,65 @@ def gen_sqr(N):
     L.append(f"      unsigned __int128 nxt = 0;")
     L.append(f"      for (int i = 0; i < {N}; i++) {{ int j = c - i; if (j < 0 || j >= {N}) continue; uint64_t pr = (uint64_t)a[i] * a[j]; acc += (uint32_t)pr; nxt += pr >> 32; }}")
     L.append(f"      t[c] = (uint32_t)acc; acc = (acc >> 32) + nxt;")
+    L.append("    }")
+    L.append("#endif")
+    L.append("  }")
+    return L
+
+
+def mul_chains(N):
+    """Schoolbook 2N-limb product for the special-form fields (pseudo-Mersenne / Solinas reduction follows): row i adds
+    a_k * b_i at column k+i; products whose column is even go to the even-aligned accumulator e[], the others to o[]."""
+    chains = []
+    touched = {"e": set(), "o": set()}
+    for i in range(N):
+        for acc, par in (("e", 0), ("o", 1)):
+            ks = [k for k in range(N) if (k + i) % 2 == par]
+            first = ks[0] + i
+            top_hi = ks[-1] + i + 1
+            carry = (top_hi in touched[acc]) and top_hi + 1 < 2 * N
+            chains.append((acc, first, [f"a[{k}]" for k in ks], i, carry))
+            for k in ks:
+                touched[acc].add(k + i); touched[acc].add(k + i + 1)
+            if carry:
+                assert top_hi + 1 not in touched[acc]
+                touched[acc].add(top_hi + 1)
+    return chains
+
+
+def gen_mul_wide(N):
+    L = []
+    L.append("  // t[0..2N-1] = a * b (any N-limb values): N^2 wide products on two column-aligned accumulators")
+    L.append("  static HD_INLINE void mul_wide(uint32_t* t, const uint32_t* a, const uint32_t* b) {")
+    L.append("#ifdef __CUDA_ARCH__")
+    L.append(f"    uint32_t e[{2*N}], o[{2*N}];")
+    L.append(f"    for (int k = 0; k < {2*N}; k++) {{ e[k] = 0; o[k] = 0; }}")
+    for acc, first, mults, row, carry in mul_chains(N):
+        n = len(mults)
+        outs = [f"{acc}[{first + j}]" for j in range(2 * n)] + ([f"{acc}[{first + 2*n}]"] if carry else [])
+        no = len(outs)
+        ins = mults + [f"b[{row}]"]
+        lines = []
+        for j in range(n):
+            lo = "mad.lo.cc.u32" if j == 0 else "madc.lo.cc.u32"
+            hi = "madc.hi.cc.u32" if (j < n - 1 or carry) else "madc.hi.u32"
+            lines.append(f"{lo} %{2*j}, %{no+j}, %{no+n}, %{2*j}")
+            lines.append(f"{hi} %{2*j+1}, %{no+j}, %{no+n}, %{2*j+1}")
+        if carry:
+            lines.append(f"addc.u32 %{2*n}, %{2*n}, 0")
+        L.append(asm_block(lines, outs, ins))
+    lines = []
+    for c in range(1, 2 * N):
+        op = "add.cc.u32" if c == 1 else ("addc.cc.u32" if c < 2 * N - 1 else "addc.u32")
+        lines.append(f"{op} %{c-1}, %{c-1}, %{2*N-1+c-1}")
+    L.append(asm_block(lines, [f"e[{c}]" for c in range(1, 2 * N)], [f"o[{c}]" for c in range(1, 2 * N)]))
+    L.append(f"    for (int k = 0; k < {2*N}; k++) t[k] = e[k];")
+    L.append("#else")
+    L.append("    unsigned __int128 acc = 0;")
+    L.append(f"    for (int c = 0; c < {2*N}; c++) {{")
+    L.append("      unsigned __int128 nxt = 0;")
+    L.append(f"      for (int i = 0; i < {N}; i++) {{ int j = c - i; if (j < 0 || j >= {N}) continue; uint64_t pr = (uint64_t)a[i] * b[j]; acc += (uint32_t)pr; nxt += pr >> 32; }}")
+    L.append("      t[c] = (uint32_t)acc; acc = (acc >> 32) + nxt;")
     L.append("    }")
     L.append("#endif")
     L.append("  }")
