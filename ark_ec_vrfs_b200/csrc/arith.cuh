@@ -160,6 +160,40 @@ HD_INLINE void pm_fold(uint32_t* out, const uint32_t* t) {
   for (int i = 0; i < N; i++) out[i] = r[i];
 }
 
+// ---- NIST P-256: p = 2^256 - 2^224 + 2^192 + 2^96 - 1.  Plain residues; the 16-limb product is reduced with the FIPS 186
+// word identities (2^256 = 2^224 - 2^192 - 2^96 + 1) as signed column sums, then the small signed overflow k * 2^256 is folded
+// three times (|k| <= 4, then <= 1, then 0 - checked exhaustively on extremes and 2*10^5 random inputs in Python before
+// this was written) and one conditional subtraction.  No multiplier instruction at all.
+template <class P>
+HD_INLINE void p256_fold(uint32_t* out, const uint32_t* c) {
+  uint32_t r[8];
+  long long a;
+#define C64(i) ((long long)c[i])
+  a = C64(0) + C64(8) + C64(9) - C64(11) - C64(12) - C64(13) - C64(14);                          r[0] = (uint32_t)a; a >>= 32;
+  a += C64(1) + C64(9) + C64(10) - C64(12) - C64(13) - C64(14) - C64(15);                        r[1] = (uint32_t)a; a >>= 32;
+  a += C64(2) + C64(10) + C64(11) - C64(13) - C64(14) - C64(15);                                 r[2] = (uint32_t)a; a >>= 32;
+  a += C64(3) + 2 * (C64(11) + C64(12)) + C64(13) - C64(15) - C64(8) - C64(9);                   r[3] = (uint32_t)a; a >>= 32;
+  a += C64(4) + 2 * (C64(12) + C64(13)) + C64(14) - C64(9) - C64(10);                            r[4] = (uint32_t)a; a >>= 32;
+  a += C64(5) + 2 * (C64(13) + C64(14)) + C64(15) - C64(10) - C64(11);                           r[5] = (uint32_t)a; a >>= 32;
+  a += C64(6) + 3 * C64(14) + 2 * C64(15) + C64(13) - C64(8) - C64(9);                           r[6] = (uint32_t)a; a >>= 32;
+  a += C64(7) + 3 * C64(15) + C64(8) - C64(10) - C64(11) - C64(12) - C64(13);                    r[7] = (uint32_t)a; a >>= 32;
+#undef C64
+#pragma unroll
+  for (int pass = 0; pass < 3; pass++) {           // k * 2^256 = k * (2^224 - 2^192 - 2^96 + 1)
+    const long long k = a;
+    a = (long long)r[0] + k; r[0] = (uint32_t)a; a >>= 32;
+    a += r[1];               r[1] = (uint32_t)a; a >>= 32;
+    a += r[2];               r[2] = (uint32_t)a; a >>= 32;
+    a += (long long)r[3] - k; r[3] = (uint32_t)a; a >>= 32;
+    a += r[4];               r[4] = (uint32_t)a; a >>= 32;
+    a += r[5];               r[5] = (uint32_t)a; a >>= 32;
+    a += (long long)r[6] - k; r[6] = (uint32_t)a; a >>= 32;
+    a += (long long)r[7] + k; r[7] = (uint32_t)a; a >>= 32;
+  }
+  cond_sub_p<P>(r, 0u);
+  for (int i = 0; i < 8; i++) out[i] = r[i];
+}
+
 // Montgomery product.  Requires a < p; b may be ANY N-limb value (used to reduce hash outputs).
 // p < 2^(32N-1): interleaved even/odd accumulators, 2N^2+N multiply-accumulates (IMAD.WIDE.U32).
 template <class P>
@@ -171,6 +205,10 @@ HD_INLINE void mont_mul_limbs(uint32_t* out, const uint32_t* a, const uint32_t* 
     uint32_t t[2 * N];
     C::mul_wide(t, a, b);
     pm_fold<P>(out, t);
+  } else if (P::SOLINAS_P256) {
+    uint32_t t[2 * N];
+    C::mul_wide(t, a, b);
+    p256_fold<P>(out, t);
   } else if (!P::FULL) {
     const uint32_t z = opaque_zero();
     for (int i = 0; i < N; i++) mod[i] = P::mod(i) ^ z;
@@ -255,9 +293,10 @@ template <class P>
 HD_INLINE void mont_sqr_limbs(uint32_t* out, const uint32_t* a) {
   constexpr int N = P::N;
   typedef MontChains<N> C;
-  if (P::FULL || !VRFS_DEDICATED_SQR) { mont_mul_limbs<P>(out, a, a); return; }
+  if ((P::FULL && !P::SOLINAS_P256) || !VRFS_DEDICATED_SQR) { mont_mul_limbs<P>(out, a, a); return; }
   uint32_t t[2 * N], mod[N], u[N], v[N];
   if (P::PM_C != 0) { C::sqr_wide(t, a); pm_fold<P>(out, t); return; }
+  if (P::SOLINAS_P256) { C::mul_wide(t, a, a); p256_fold<P>(out, t); return; }   // a may use all 256 bits: sqr_wide needs the top bit clear
   const uint32_t z = opaque_zero();
   for (int i = 0; i < N; i++) mod[i] = P::mod(i) ^ z;
   C::sqr_wide(t, a);

@@ -75,7 +75,7 @@ def _fop(emu, f, o, a, b, n):
 @pytest.mark.parametrize("fi", range(len(FIELDS)))
 def test_montgomery_field_arithmetic(emu, fi):
     p, n = FIELDS[fi]
-    Rm = 1 if p == R.ED25519.p else 1 << (32 * n); Ri = pow(Rm, -1, p)      # 2^255-19 is kept in plain residues (arith.cuh pm_fold)
+    Rm = 1 if p in (R.ED25519.p, R.P256.p) else 1 << (32 * n); Ri = pow(Rm, -1, p)      # 2^255-19 and the P-256 prime are kept in plain residues (arith.cuh pm_fold / p256_fold)
     W = 1 << (32 * n)
     rnd = random.Random(fi)
     for t in range(200):
