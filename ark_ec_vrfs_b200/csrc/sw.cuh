@@ -75,4 +75,28 @@ template <class C> HD_NOINLINE void sw_add(SWPoint<C>* r, const SWPoint<C>* p, c
   r->X = X3; r->Y = Y3; r->Z = Z3;
 }
 
+// r = 16 p for a = -3: homogeneous -> Jacobian (X Z : Y Z^2 : Z), four Jacobian doublings (dbl-2001-b, 3M + 5S each, no
+// exceptional case on a prime-order curve), back to homogeneous (X Z : Y : Z^3): 38 products instead of the 56 of four complete
+// additions.  The identity (0:1:0) passes through as (0:0:0) and is restored at the end.
+template <class C> HD_NOINLINE void sw_dbl4_am3(SWPoint<C>* r, const SWPoint<C>* p) {
+  typedef typename C::F F;
+  F Z = p->Z, zz = sqr(Z), X = p->X * Z, Y = p->Y * zz;
+#pragma unroll 1
+  for (int i = 0; i < 4; i++) {
+    F delta = sqr(Z), gamma = sqr(Y), beta = X * gamma;
+    F t = (X - delta) * (X + delta), alpha = dbl(t) + t;
+    F b4 = dbl(dbl(beta));
+    F X3 = sqr(alpha) - dbl(b4);
+    F Z3 = sqr(Y + Z) - gamma - delta;
+    F g2 = sqr(gamma), g8 = dbl(dbl(dbl(g2)));
+    Y = alpha * (b4 - X3) - g8;
+    X = X3; Z = Z3;
+  }
+  bool inf = Z.is_zero();
+  F z2 = sqr(Z);
+  r->X = X * Z;
+  r->Y = select(inf, F::one(), Y);
+  r->Z = z2 * Z;
+}
+
 }  // namespace vrfs

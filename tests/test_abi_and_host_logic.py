@@ -107,7 +107,8 @@ def test_glv_split_and_lincomb(emu):
         assert (k1 + k2 * lam - k) % r == 0 and abs(k1) < (1 << 127) * 7 // 15 and abs(k2) < (1 << 127) * 7 // 15
     le = lambda x: x.to_bytes(32, "little")
     pt = lambda P: le(P[0]) + le(P[1])
-    for suite, cv in ((0, R.BANDERSNATCH), (1, R.ED25519)):
+    pt = lambda P: bytes(64) if P is None else le(P[0]) + le(P[1])          # short-Weierstrass identity = 64 zero bytes
+    for suite, cv in ((0, R.BANDERSNATCH), (1, R.ED25519), (2, R.P256)):
         r = cv.r
         P1 = cv.mul(rnd.randrange(r), cv.G); P2 = cv.mul(rnd.randrange(r), cv.G)
         for nv, nf in ((0, 1), (1, 0), (2, 0), (1, 1)):
