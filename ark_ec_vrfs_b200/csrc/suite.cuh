@@ -232,18 +232,58 @@ HD_INLINE void ietf_verify_finish_batched(uint32_t n, uint32_t first, uint32_t s
   }
 }
 
-// K projective points (X,Y,Z Montgomery limbs, 24 words each) -> affine Montgomery, ONE shared inversion
-template <class C, int K> HD_INLINE void to_affine_shared(typename C::F* ax, typename C::F* ay, const uint32_t* const* p) {
+// K projective points (X,Y,Z Montgomery limbs, 24 words each) -> affine Montgomery, ONE shared inversion.  A point with
+// Z = 0 (the short-Weierstrass identity) comes out as (0,0) and does not disturb the others.  `zinv` (optional): the inverse
+// of the product of the non-zero Z's, precomputed for many items at once by zinv_batched (one inversion per 8 items).
+template <class C, int K> HD_INLINE void to_affine_shared(typename C::F* ax, typename C::F* ay, const uint32_t* const* p, const uint32_t* zinv = nullptr) {
   typedef typename C::F F;
   F X[K], Y[K], Z[K], pre[K];
-  for (int k = 0; k < K; k++) for (int i = 0; i < 8; i++) { X[k].v[i] = p[k][i]; Y[k].v[i] = p[k][8 + i]; Z[k].v[i] = p[k][16 + i]; }
+  bool zero[K];
+  for (int k = 0; k < K; k++) {
+    for (int i = 0; i < 8; i++) { X[k].v[i] = p[k][i]; Y[k].v[i] = p[k][8 + i]; Z[k].v[i] = p[k][16 + i]; }
+    zero[k] = Z[k].is_zero();
+    Z[k] = select(zero[k], F::one(), Z[k]);
+  }
   pre[0] = Z[0];
   for (int k = 1; k < K; k++) pre[k] = pre[k - 1] * Z[k];
-  F acc = inv(pre[K - 1]);
+  F acc;
+  if (zinv) { for (int i = 0; i < 8; i++) acc.v[i] = zinv[i]; } else acc = inv(pre[K - 1]);
   for (int k = K - 1; k >= 0; k--) {
     F zi = k ? acc * pre[k - 1] : acc;
     if (k) acc = acc * Z[k];
+    zi = select(zero[k], F::zero(), zi);
     ax[k] = X[k] * zi; ay[k] = Y[k] * zi;
+  }
+}
+// zinv[i] = 1 / prod_j Z_j(i) over the NP projective points of item i (zero Z's skipped), for the K items
+// first, first + stride, ... of this thread with ONE field inversion (Montgomery's trick)
+template <class C, int NP, int K>
+HD_INLINE void zinv_batched(uint32_t n, uint32_t first, uint32_t stride, const uint32_t* const* pts, uint32_t* zinv) {
+  typedef typename C::F F;
+  F z[K], pre[K];
+  int cnt = 0;
+  for (int k = 0; k < K; k++) {
+    uint32_t i = first + (uint32_t)k * stride;
+    if (i >= n) break;
+    F t = F::one();
+    for (int j = 0; j < NP; j++) {
+      F Zj;
+      for (int w = 0; w < 8; w++) Zj.v[w] = pts[j][(size_t)24 * i + 16 + w];
+      Zj = select(Zj.is_zero(), F::one(), Zj);
+      t = j ? t * Zj : Zj;
+    }
+    z[k] = t;
+    pre[k] = k ? pre[k - 1] * t : t;
+    cnt = k + 1;
+  }
+  if (cnt == 0) return;
+  F acc = inv(pre[cnt - 1]);
+  for (int k = K - 1; k >= 0; k--) {
+    if (k >= cnt) continue;
+    uint32_t i = first + (uint32_t)k * stride;
+    F zi = k ? acc * pre[k - 1] : acc;
+    if (k) acc = acc * z[k];
+    for (int w = 0; w < 8; w++) zinv[(size_t)8 * i + w] = zi.v[w];
   }
 }
 template <class C> HD_INLINE void store_affine_bytes(uint8_t* out, const typename C::F& x, const typename C::F& y) {
@@ -261,11 +301,11 @@ template <class C> HD_INLINE void load_scalar_bytes_mod_r(uint32_t* k, const uin
 template <class S>
 HD_INLINE void ietf_prove_finish_item(uint8_t* out_c, uint8_t* out_s, const uint8_t* sk_bytes, const uint8_t* k_bytes, const uint8_t* input,
                                       const uint8_t* output, const uint32_t* y_xyz, const uint32_t* kg_xyz, const uint32_t* ki_xyz,
-                                      const uint8_t* ad, uint32_t adlen) {
+                                      const uint8_t* ad, uint32_t adlen, const uint32_t* zinv = nullptr) {
   typedef typename S::C C;
   typename C::F ax[3], ay[3];
   const uint32_t* pp[3] = {y_xyz, kg_xyz, ki_xyz};
-  to_affine_shared<C, 3>(ax, ay, pp);
+  to_affine_shared<C, 3>(ax, ay, pp, zinv);
   uint8_t enc[5][S::ENC_LEN];
   encode_point_mont<S>(enc[0], ax[0], ay[0]);
   encode_point_bytes<S>(enc[1], input);
@@ -308,11 +348,11 @@ template <class S> HD_INLINE void pedersen_prove_prep_item(uint8_t* out_b, uint8
 template <class S> HD_INLINE void pedersen_prove_finish_item(uint8_t* proof, const uint8_t* sk_bytes, const uint8_t* b_bytes, const uint8_t* k_bytes,
                                                              const uint8_t* kb_bytes, const uint8_t* input, const uint8_t* output,
                                                              const uint32_t* yb_xyz, const uint32_t* r_xyz, const uint32_t* ok_xyz,
-                                                             const uint8_t* ad, uint32_t adlen) {
+                                                             const uint8_t* ad, uint32_t adlen, const uint32_t* zinv = nullptr) {
   typedef typename S::C C;
   typename C::F ax[3], ay[3];
   const uint32_t* pp[3] = {yb_xyz, r_xyz, ok_xyz};
-  to_affine_shared<C, 3>(ax, ay, pp);
+  to_affine_shared<C, 3>(ax, ay, pp, zinv);
   uint8_t enc[5][S::ENC_LEN];
   encode_point_mont<S>(enc[0], ax[0], ay[0]);
   encode_point_bytes<S>(enc[1], input);

@@ -188,7 +188,7 @@ struct DevBuf {
   size_t cap = 0;
 };
 enum { BUF_IN0, BUF_IN1, BUF_IN2, BUF_IN3, BUF_IN4, BUF_AD, BUF_OFF, BUF_OUT0, BUF_OUT1, BUF_W0, BUF_W1, BUF_W2, BUF_W3, BUF_VALID, BUF_SLAB,
-       BUF_X0, BUF_X1, BUF_X2, BUF_X3, BUF_X4, BUF_COUNT };   // X*: wire-format staging (encoded keys, signatures, h2c data, flags)
+       BUF_X0, BUF_X1, BUF_X2, BUF_X3, BUF_X4, BUF_ZINV, BUF_COUNT };   // X*: wire-format staging (encoded keys, signatures, h2c data, flags)
 
 #define MAX_TIMED 64
 struct vrfs_ctx {
@@ -520,22 +520,30 @@ template <class S> __global__ void __launch_bounds__(ITEM_THREADS) k_nonce(uint3
 }
 template <class S> __global__ void __launch_bounds__(ITEM_THREADS) k_ietf_prove_finish(uint32_t n, const uint8_t* sk, const uint8_t* k, const uint8_t* input, const uint8_t* output,
                                                                                         const uint32_t* y, const uint32_t* kg, const uint32_t* ki, const uint8_t* ad, const uint64_t* ad_off,
-                                                                                        const uint8_t* valid, uint8_t* out_c, uint8_t* out_s) {
+                                                                                        const uint8_t* valid, const uint32_t* zinv, uint8_t* out_c, uint8_t* out_s) {
   ITEM_INDEX(n);
   VAR_SLICE(ad, ad_off, i, a, alen);
   uint8_t* oc = out_c + (size_t)32 * i; uint8_t* os = out_s + (size_t)32 * i;
   if (!valid[i]) { for (int j = 0; j < 32; j++) { oc[j] = 0; os[j] = 0; } return; }
   ietf_prove_finish_item<S>(oc, os, sk + (size_t)32 * i, k + (size_t)32 * i, input + (size_t)64 * i, output + (size_t)64 * i,
-                            y + (size_t)24 * i, kg + (size_t)24 * i, ki + (size_t)24 * i, a, alen);
+                            y + (size_t)24 * i, kg + (size_t)24 * i, ki + (size_t)24 * i, a, alen, zinv + (size_t)8 * i);
+}
+// one field inversion per ZINV_K items: zinv[i] = 1 / (product of the Z's of item i's NP projective points)
+#define ZINV_K 8
+template <class C, int NP> __global__ void __launch_bounds__(128) k_zinv(uint32_t n, const uint32_t* p0, const uint32_t* p1, const uint32_t* p2, uint32_t* zinv) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+  if (t >= n) return;
+  const uint32_t* pts[3] = {p0, p1, p2};
+  zinv_batched<C, NP, ZINV_K>(n, t, stride, pts, zinv);
 }
 // projective -> affine ABI bytes, one point per item (Secret::output, Public)
-template <class C> __global__ void __launch_bounds__(ITEM_THREADS) k_to_affine(uint32_t n, const uint32_t* xyz, const uint8_t* valid, uint8_t* out) {
+template <class C> __global__ void __launch_bounds__(ITEM_THREADS) k_to_affine(uint32_t n, const uint32_t* xyz, const uint8_t* valid, const uint32_t* zinv, uint8_t* out) {
   ITEM_INDEX(n);
   uint8_t* o = out + (size_t)64 * i;
   if (valid && !valid[i]) { for (int j = 0; j < 64; j++) o[j] = 0; return; }
   typename C::F ax[1], ay[1];
   const uint32_t* pp[1] = {xyz + (size_t)24 * i};
-  to_affine_shared<C, 1>(ax, ay, pp);
+  to_affine_shared<C, 1>(ax, ay, pp, zinv + (size_t)8 * i);
   store_affine_bytes<C>(o, ax[0], ay[0]);
 }
 // Secret::from_seed: sk = LE(H(seed)) mod r
@@ -578,7 +586,7 @@ template <class S> __global__ void __launch_bounds__(ITEM_THREADS) k_point_decod
   if (ok) store_affine_bytes<C>(o, x, y); else for (int j = 0; j < 64; j++) o[j] = 0;
 }
 // Suite::data_to_point (K6)
-template <class S> __global__ void __launch_bounds__(ITEM_THREADS) k_data_to_point(uint32_t n, const uint8_t* data, const uint64_t* off, uint8_t* out, uint8_t* out_ok) {
+template <class S> __global__ void __launch_bounds__(ITEM_THREADS) k_data_to_point(uint32_t n, const uint8_t* data, const uint64_t* off, uint32_t* out_xyz, uint8_t* out_ok) {
   ITEM_INDEX(n);
   typedef typename S::C C;
   VAR_SLICE(data, off, i, p, len);
@@ -586,11 +594,9 @@ template <class S> __global__ void __launch_bounds__(ITEM_THREADS) k_data_to_poi
   bool ok;
   if constexpr (C::HAS_GLV) { TEPoint<C> P; band_h2c_ell2(P, p, len); ok = true; X = P.X; Y = P.Y; Z = P.Z; }
   else { typename Grp<C>::Pt P; ok = h2c_tai<S>(P, p, len); X = P.X; Y = P.Y; Z = P.Z; }
-  uint8_t* o = out + (size_t)64 * i;
   out_ok[i] = ok;
-  if (!ok) { for (int j = 0; j < 64; j++) o[j] = 0; return; }
-  typename C::F zi = inv(Z);
-  store_affine_bytes<C>(o, X * zi, Y * zi);
+  if (!ok) { X = C::F::zero(); Y = C::F::one(); Z = C::F::one(); }
+  store_fp_xyz(out_xyz + (size_t)24 * i, X, Y, Z);      // projective: the inversion is shared by 8 items (k_zinv + k_to_affine)
 }
 template <class S> __global__ void __launch_bounds__(ITEM_THREADS) k_pedersen_prove_prep(uint32_t n, const uint8_t* sk, const uint8_t* input, const uint8_t* ad, const uint64_t* ad_off,
                                                                                           uint8_t* b, uint8_t* k, uint8_t* kb) {
@@ -600,13 +606,13 @@ template <class S> __global__ void __launch_bounds__(ITEM_THREADS) k_pedersen_pr
 }
 template <class S> __global__ void __launch_bounds__(ITEM_THREADS) k_pedersen_prove_finish(uint32_t n, const uint8_t* sk, const uint8_t* b, const uint8_t* k, const uint8_t* kb,
                                                                                             const uint8_t* input, const uint8_t* output, const uint32_t* yb, const uint32_t* r, const uint32_t* okp,
-                                                                                            const uint8_t* ad, const uint64_t* ad_off, const uint8_t* valid, uint8_t* proof, uint8_t* blinding) {
+                                                                                            const uint8_t* ad, const uint64_t* ad_off, const uint8_t* valid, const uint32_t* zinv, uint8_t* proof, uint8_t* blinding) {
   ITEM_INDEX(n);
   VAR_SLICE(ad, ad_off, i, a, alen);
   uint8_t* pr = proof + (size_t)256 * i; uint8_t* bl = blinding + (size_t)32 * i;
   if (!valid[i]) { for (int j = 0; j < 256; j++) pr[j] = 0; for (int j = 0; j < 32; j++) bl[j] = 0; return; }
   pedersen_prove_finish_item<S>(pr, sk + (size_t)32 * i, b + (size_t)32 * i, k + (size_t)32 * i, kb + (size_t)32 * i, input + (size_t)64 * i,
-                                output + (size_t)64 * i, yb + (size_t)24 * i, r + (size_t)24 * i, okp + (size_t)24 * i, a, alen);
+                                output + (size_t)64 * i, yb + (size_t)24 * i, r + (size_t)24 * i, okp + (size_t)24 * i, a, alen, zinv + (size_t)8 * i);
   for (int j = 0; j < 32; j++) bl[j] = b[(size_t)32 * i + j];
 }
 template <class S> __global__ void __launch_bounds__(ITEM_THREADS) k_pedersen_verify_prep(uint32_t n, const uint8_t* input, const uint8_t* output, const uint8_t* proof,
@@ -660,12 +666,36 @@ static vrfs_status fresh_valid(vrfs_ctx* ctx, size_t n, uint8_t** valid) {
   return VRFS_OK;
 }
 template <class S> static const void* fixtab(vrfs_ctx* ctx, int which) { return ctx->fixtab[S::ID][which]; }
+// batched inversion of the Z coordinates of NP projective results per item (k_zinv): returns the device array of n x 8 words
+template <class C, int NP> static vrfs_status launch_zinv(vrfs_ctx* ctx, size_t n, const void* p0, const void* p1, const void* p2, const uint32_t** out) {
+  void* z = nullptr;
+  ST(ensure(ctx, BUF_ZINV, n * 32, &z));
+  const size_t threads = (n + ZINV_K - 1) / ZINV_K;
+  k_zinv<C, NP><<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>((uint32_t)n, (const uint32_t*)p0, (const uint32_t*)p1, (const uint32_t*)p2, (uint32_t*)z);
+  LAUNCHED_AS(ctx, "zinv");
+  *out = (const uint32_t*)z;
+  return VRFS_OK;
+}
 #define SUITE_DISPATCH(suite, FN, ...)                                                         \
   switch (suite) {                                                                             \
     case VRFS_BANDERSNATCH_ELL2: return FN<BandSuite>(__VA_ARGS__);                            \
     case VRFS_ED25519_TAI: return FN<EdSuite>(__VA_ARGS__);                                    \
     default: return fail(ctx, VRFS_UNSUPPORTED, "suite %d is not implemented for %s", (int)suite, #FN); \
   }
+
+// Suite::data_to_point: hash-to-curve kernel (projective) + batched inversion + affine ABI bytes (zeros where no point was found)
+template <class S> static vrfs_status data_to_point_dev(vrfs_ctx* ctx, size_t n, const uint8_t* data, const uint64_t* off, uint8_t* out_pts, uint8_t* out_ok) {
+  typedef typename S::C C;
+  void* xyz = nullptr;
+  ST(ensure(ctx, BUF_W0, n * 96, &xyz));
+  k_data_to_point<S><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, data, off, (uint32_t*)xyz, out_ok);
+  LAUNCHED_AS(ctx, "data_to_point");
+  const uint32_t* zinv = nullptr;
+  ST((launch_zinv<C, 1>(ctx, n, xyz, nullptr, nullptr, &zinv)));
+  k_to_affine<C><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, (const uint32_t*)xyz, out_ok, zinv, out_pts);
+  LAUNCHED_AS(ctx, "to_affine");
+  return VRFS_OK;
+}
 
 // ---- ietf prove -----------------------------------------------------------------------------
 template <class S>
@@ -686,8 +716,10 @@ static vrfs_status ietf_prove_dev(vrfs_ctx* ctx, size_t n, const uint8_t* sk, co
   ST((launch_lincomb<C, 0, 1>(ctx, A)));
   A.var[0] = {input, 64, (const uint8_t*)k, 32, 0}; A.out_xyz = (uint32_t*)ki;
   ST((launch_lincomb<C, 1, 0>(ctx, A)));
+  const uint32_t* zinv = nullptr;
+  ST((launch_zinv<C, 3>(ctx, n, y, kg, ki, &zinv)));
   k_ietf_prove_finish<S><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, sk, (const uint8_t*)k, input, output, (const uint32_t*)y,
-                                                                           (const uint32_t*)kg, (const uint32_t*)ki, ad, ad_off, valid, out_c, out_s);
+                                                                           (const uint32_t*)kg, (const uint32_t*)ki, ad, ad_off, valid, zinv, out_c, out_s);
   LAUNCHED_AS(ctx, "ietf_prove_finish");
   return VRFS_OK;
 }
@@ -717,7 +749,9 @@ template <class S> static vrfs_status output_dev(vrfs_ctx* ctx, size_t n, const 
   LincombArgs A = {};
   A.n = (uint32_t)n; A.valid = valid; A.var[0] = {input, 64, sk, 32, 0}; A.out_xyz = (uint32_t*)o;
   ST((launch_lincomb<C, 1, 0>(ctx, A)));
-  k_to_affine<C><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, (const uint32_t*)o, valid, out);
+  const uint32_t* zinv = nullptr;
+  ST((launch_zinv<C, 1>(ctx, n, o, nullptr, nullptr, &zinv)));
+  k_to_affine<C><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, (const uint32_t*)o, valid, zinv, out);
   LAUNCHED_AS(ctx, "to_affine");
   return VRFS_OK;
 }
@@ -744,7 +778,9 @@ template <class S> static vrfs_status from_seed_dev(vrfs_ctx* ctx, size_t n, con
   LincombArgs A = {};
   A.n = (uint32_t)n; A.fix[0] = {out_sk, 32, 0, fixtab<S>(ctx, 0)}; A.out_xyz = (uint32_t*)o;
   ST((launch_lincomb<C, 0, 1>(ctx, A)));
-  k_to_affine<C><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, (const uint32_t*)o, nullptr, out_pk);
+  const uint32_t* zinv = nullptr;
+  ST((launch_zinv<C, 1>(ctx, n, o, nullptr, nullptr, &zinv)));
+  k_to_affine<C><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, (const uint32_t*)o, nullptr, zinv, out_pk);
   LAUNCHED_AS(ctx, "to_affine");
   return VRFS_OK;
 }
@@ -838,10 +874,8 @@ extern "C" vrfs_status vrfs_data_to_point_batch(vrfs_ctx* ctx, vrfs_suite suite,
   const uint8_t* d_d; const uint64_t* d_off; uint8_t *d_p, *d_ok;
   ST(stage_ad(ctx, n, data, data_off, &d_d, &d_off));
   ST(stage_out(ctx, BUF_OUT0, n * 64, &d_p)); ST(stage_out(ctx, BUF_OUT1, n, &d_ok));
-  if (suite == VRFS_BANDERSNATCH_ELL2) k_data_to_point<BandSuite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_d, d_off, d_p, d_ok);
-  else if (suite == VRFS_ED25519_TAI) k_data_to_point<EdSuite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_d, d_off, d_p, d_ok);
-  else k_data_to_point<P256Suite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_d, d_off, d_p, d_ok);
-  LAUNCHED_AS(ctx, "data_to_point");
+  ST(suite == VRFS_BANDERSNATCH_ELL2 ? data_to_point_dev<BandSuite>(ctx, n, d_d, d_off, d_p, d_ok)
+     : suite == VRFS_ED25519_TAI ? data_to_point_dev<EdSuite>(ctx, n, d_d, d_off, d_p, d_ok) : data_to_point_dev<P256Suite>(ctx, n, d_d, d_off, d_p, d_ok));
   ST(copy_out(ctx, out_pts, d_p, n * 64)); ST(copy_out(ctx, out_ok, d_ok, n));
   return finish_call(ctx);
 }
@@ -866,8 +900,10 @@ static vrfs_status pedersen_prove_dev(vrfs_ctx* ctx, size_t n, const uint8_t* sk
   ST((launch_lincomb<C, 0, 2>(ctx, A)));
   A.var[0] = {input, 64, k, 32, 0}; A.out_xyz = (uint32_t*)okp;
   ST((launch_lincomb<C, 1, 0>(ctx, A)));
+  const uint32_t* zinv = nullptr;
+  ST((launch_zinv<C, 3>(ctx, n, yb, r, okp, &zinv)));
   k_pedersen_prove_finish<S><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, sk, b, k, kb, input, output, (const uint32_t*)yb, (const uint32_t*)r,
-                                                                               (const uint32_t*)okp, ad, ad_off, valid, proof, blinding);
+                                                                               (const uint32_t*)okp, ad, ad_off, valid, zinv, proof, blinding);
   LAUNCHED_AS(ctx, "pedersen_prove_finish");
   return VRFS_OK;
 }
@@ -1018,8 +1054,7 @@ extern "C" vrfs_status vrfs_subgroup_check_batch(vrfs_ctx* ctx, vrfs_suite suite
 template <class S> static vrfs_status ietf_sign_wire_dev(vrfs_ctx* ctx, size_t n, const uint8_t* sk, const uint8_t* data, const uint64_t* data_off,
                                                          const uint8_t* ad, const uint64_t* ad_off, uint8_t* input, uint8_t* output, uint8_t* c, uint8_t* s,
                                                          uint8_t* h2c_ok, uint8_t* sig) {
-  k_data_to_point<S><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, data, data_off, input, h2c_ok);
-  LAUNCHED_AS(ctx, "data_to_point");
+  ST(data_to_point_dev<S>(ctx, n, data, data_off, input, h2c_ok));
   ST(output_dev<S>(ctx, n, sk, input, output));
   ST(ietf_prove_dev<S>(ctx, n, sk, input, output, ad, ad_off, c, s));
   k_wire_pack_sig<S><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, output, c, s, h2c_ok, sig);
@@ -1059,8 +1094,7 @@ template <class S> static vrfs_status ietf_verify_wire_dev(vrfs_ctx* ctx, size_t
   ST((decode_checked_launch<S>(ctx, n, pk_enc, S::ENC_LEN, pk, sig, SL, output, flags)));
   k_wire_parse_proof<S><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, sig, flags, c, s, flags + 2 * n);
   LAUNCHED_AS(ctx, "wire_parse_proof");
-  k_data_to_point<S><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, data, data_off, input, flags + 3 * n);
-  LAUNCHED_AS(ctx, "data_to_point");
+  ST(data_to_point_dev<S>(ctx, n, data, data_off, input, flags + 3 * n));
   ST(ietf_verify_dev<S>(ctx, n, pk, input, output, c, s, ad, ad_off, out_ok));
   if (out_hash) {
     k_point_to_hash<S><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, output, out_hash);
