@@ -209,7 +209,7 @@ def run_reference(a, rank, world):
     assert np.array_equal(got, w["expect"])
     v = n * a.steps / dt
     sample = f"2^{a.ref_logn} proofs per step (same generator as the GPU workload), {cores} pthreads"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (u64 on CPU)",
         "data": "synthetic", "config": {"workload": f"Bandersnatch IETF VRF batch verify, sample of 2^{a.ref_logn} per step on host CPU",
@@ -217,11 +217,34 @@ def run_reference(a, rank, world):
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                          "note": "CPU restatement of the reference algorithm (oracle/vrf_oracle.c), not the arkworks binary"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    })
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Everything any library prints on stdout (NCCL's version banner, ...) goes to stderr; the ONE JSON line is written to the
+    real stdout by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, line)
+    else:
+        os.write(_REAL_STDOUT, line)
 
 
 def main():
     a = parse()
+    quiet_stdout()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if a.impl == "reference":
         run_reference(a, rank, world)
@@ -362,7 +385,7 @@ def main():
                 out["ietf_verify_wire"] = wire_extra(eng, min(a.logn, 20))
             except Exception as ex:
                 out["ietf_verify_wire"] = {"error": repr(ex)}
-        print(json.dumps(out), flush=True)
+        emit(out)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
