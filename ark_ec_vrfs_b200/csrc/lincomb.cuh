@@ -145,6 +145,7 @@ struct LincombArgs {
   uint32_t* out_xyz;     // n x 3N limbs: X, Y, Z (Montgomery form)
   uint8_t* valid;        // n bytes, AND-ed with "all variable bases canonical and on the curve" (may be null)
   uint8_t* slab;         // per-thread table slabs
+  uint32_t* next_item;   // device work counter (items are handed out per warp)
 };
 
 // affine x||y, 32-byte little-endian canonical each -> Montgomery; false if not canonical / not on the curve.

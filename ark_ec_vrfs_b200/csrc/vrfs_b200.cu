@@ -39,13 +39,22 @@ __global__ void k_fixed_table(typename Grp<C>::FixEntry* out, int blinding) {
 // slab is per resident thread (L2-resident), not per item.
 template <class C, int NV, int NF>
 __global__ void __launch_bounds__(LINCOMB_THREADS, LINCOMB_MINBLOCKS) k_lincomb(LincombArgs A) {
-  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31u;
   typename Grp<C>::Entry* slab = reinterpret_cast<typename Grp<C>::Entry*>(A.slab + (size_t)tid * slab_bytes<C>(NV));
-  for (uint32_t item = tid; item < A.n; item += nthreads) {
-    typename Grp<C>::Pt acc;
-    bool ok = lincomb_item<C, NV, NF>(A, item, slab, acc);
-    Grp<C>::store_xyz(A.out_xyz + (size_t)item * 24, acc);
-    if (A.valid != nullptr && !ok) A.valid[item] = 0;
+  // items are handed out 32 at a time per warp from a device counter: no tail wave of idle warps behind the slowest SMs
+  for (;;) {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(A.next_item, 32u);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= A.n) break;
+    const uint32_t item = base + lane;
+    if (item < A.n) {
+      typename Grp<C>::Pt acc;
+      bool ok = lincomb_item<C, NV, NF>(A, item, slab, acc);
+      Grp<C>::store_xyz(A.out_xyz + (size_t)item * 24, acc);
+      if (A.valid != nullptr && !ok) A.valid[item] = 0;
+    }
+    __syncwarp();
   }
 }
 
@@ -348,8 +357,10 @@ static vrfs_status launch_lincomb(vrfs_ctx* ctx, LincombArgs A) {
   uint32_t need = (A.n + LINCOMB_THREADS - 1) / LINCOMB_THREADS;
   if (blocks > need) blocks = need;
   void* slab = nullptr;
-  ST(ensure(ctx, BUF_SLAB, (size_t)blocks * LINCOMB_THREADS * slab_bytes<C>(NV), &slab));
+  ST(ensure(ctx, BUF_SLAB, (size_t)blocks * LINCOMB_THREADS * slab_bytes<C>(NV) + 256, &slab));
   A.slab = (uint8_t*)slab;
+  A.next_item = reinterpret_cast<uint32_t*>((uint8_t*)slab + (size_t)blocks * LINCOMB_THREADS * slab_bytes<C>(NV));   // work counter behind the slabs
+  CU(cudaMemsetAsync(A.next_item, 0, sizeof(uint32_t), ctx->stream));
   k_lincomb<C, NV, NF><<<blocks, LINCOMB_THREADS, 0, ctx->stream>>>(A);
   LAUNCHED_AS(ctx, NV == 2 ? "lincomb<2,0>" : NV == 1 && NF == 1 ? "lincomb<1,1>" : NV == 1 ? "lincomb<1,0>" : NF == 2 ? "lincomb<0,2>" : NV == 1 && NF == 2 ? "lincomb<1,2>" : "lincomb<0,1>");
   return VRFS_OK;
