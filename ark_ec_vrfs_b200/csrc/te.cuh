@@ -74,28 +74,41 @@ template <class C> HD_NOINLINE void te_add(TEPoint<C>* r, const TEPoint<C>* p, c
 template <class C> HD_NOINLINE void te_add_cached(TEPoint<C>* r, const TEPoint<C>* p, const TECached<C>* q, bool negate) {
   typedef typename C::F F;
   F qX = cneg(q->X, negate), qdT = cneg(q->dT, negate);
-  F A = p->X * qX, B = p->Y * q->Y, Cc = p->T * qdT, D = p->Z * q->Z;
-  F E = (p->X + p->Y) * (qX + q->Y) - A - B;
+  F A, B, Cc, D, E, X3, Y3, T3, Z3;
+  mul2(A, B, p->X, qX, p->Y, q->Y);
+  mul2(Cc, D, p->T, qdT, p->Z, q->Z);
+  E = (p->X + p->Y) * (qX + q->Y) - A - B;
   F Fv = D - Cc, G = D + Cc, H = B - C::mul_a(A);
-  r->X = E * Fv; r->Y = G * H; r->T = E * H; r->Z = Fv * G;
+  mul2(X3, Y3, E, Fv, G, H);
+  mul2(T3, Z3, E, H, Fv, G);
+  r->X = X3; r->Y = Y3; r->T = T3; r->Z = Z3;
 }
 // r = p + q, q affine cached, optionally negated (8M)
 template <class C> HD_NOINLINE void te_madd(TEPoint<C>* r, const TEPoint<C>* p, const TEAffCached<C>* q, bool negate) {
   typedef typename C::F F;
   F qx = cneg(q->x, negate), qdt = cneg(q->dt, negate);
-  F A = p->X * qx, B = p->Y * q->y, Cc = p->T * qdt, D = p->Z;
-  F E = (p->X + p->Y) * (qx + q->y) - A - B;
+  F A, B, Cc, E, D = p->Z, X3, Y3, T3, Z3;
+  mul2(A, B, p->X, qx, p->Y, q->y);
+  mul2(Cc, E, p->T, qdt, p->X + p->Y, qx + q->y);
+  E = E - A - B;
   F Fv = D - Cc, G = D + Cc, H = B - C::mul_a(A);
-  r->X = E * Fv; r->Y = G * H; r->T = E * H; r->Z = Fv * G;
+  mul2(X3, Y3, E, Fv, G, H);
+  mul2(T3, Z3, E, H, Fv, G);
+  r->X = X3; r->Y = Y3; r->T = T3; r->Z = Z3;
 }
 // r = 2p (4S + 4M; T of the result is skipped when the next operation is another doubling)
 template <class C> HD_NOINLINE void te_dbl(TEPoint<C>* r, const TEPoint<C>* p, bool want_t) {
   typedef typename C::F F;
-  F A = sqr(p->X), B = sqr(p->Y), Cc = dbl(sqr(p->Z)), D = C::mul_a(A);
-  F E = sqr(p->X + p->Y) - A - B;
+  F A, B, Cc, E, X3, Y3, Z3;
+  sqr2(A, B, p->X, p->Y);
+  sqr2(Cc, E, p->Z, p->X + p->Y);
+  Cc = dbl(Cc);
+  F D = C::mul_a(A);
+  E = E - A - B;
   F G = D + B, Fv = G - Cc, H = D - B;
-  r->X = E * Fv; r->Y = G * H; r->Z = Fv * G;
-  if (want_t) r->T = E * H;
+  mul2(X3, Y3, E, Fv, G, H);
+  r->X = X3; r->Y = Y3;
+  if (want_t) { F T3; mul2(Z3, T3, Fv, G, E, H); r->Z = Z3; r->T = T3; } else r->Z = Fv * G;
 }
 template <class C> HD_INLINE void te_neg(TEPoint<C>& P) { P.X = neg(P.X); P.T = neg(P.T); }
 
