@@ -192,6 +192,10 @@ class Secret:
         """Input::new(data) -> output -> ietf prove -> serialised signatures point_encode(Output) || c || s; returns (sig, ok)"""
         return self.suite.engine.ietf_sign_wire(self.suite.suite_id, self.scalars, datas, ad)
 
+    def pedersen_sign(self, datas, ad=None):
+        """Input::new(data) -> output -> pedersen prove -> serialised Output || pedersen::Proof; returns (sig, blinding, ok)"""
+        return self.suite.engine.pedersen_sign_wire(self.suite.suite_id, self.scalars, datas, ad)
+
     def pedersen_prove(self, input, output, ad=None):
         """pedersen::Prover::prove -> (Proof, blinding)"""
         pr, bl = self.suite.engine.pedersen_prove(self.suite.suite_id, self.scalars, input.points, output.points, ad)
@@ -201,6 +205,11 @@ class Secret:
 def pedersen_verify(suite, input, output, ad, proof):
     """pedersen::Verifier::verify (needs no public key) -> uint8[n]"""
     return suite.engine.pedersen_verify(suite.suite_id, input.points, output.points, proof.raw, ad)
+
+
+def pedersen_verify_signatures(suite, datas, signatures, ad=None):
+    """serialised Output || pedersen::Proof + VRF input data -> ok flags (deserialise with validation, Input::new, verify)"""
+    return suite.engine.pedersen_verify_wire(suite.suite_id, datas, signatures, ad)
 
 
 def ring_commitment_msm(suite_or_engine, bases, scalar_columns):

@@ -1142,6 +1142,117 @@ extern "C" vrfs_status vrfs_ietf_verify_wire_batch(vrfs_ctx* ctx, vrfs_suite sui
   return finish_call(ctx);
 }
 
+// ---- pedersen wire form: point_encode(Output) || point_encode(pk_com) || point_encode(r) || point_encode(ok) || s || sb
+// (an `Output` followed by `pedersen::Proof`'s CanonicalSerialize, A.10)
+// one thread per encoded point (4 per item): j = 0 -> output_aff[item], j = 1..3 -> the ABI proof's three 64-byte points
+template <class S> __global__ void __launch_bounds__(ITEM_THREADS) k_ped_wire_points(uint32_t n, const uint8_t* sig, uint8_t* output, uint8_t* proof256, uint8_t* flags) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 4 * n) return;
+  constexpr uint32_t SL = 4 * S::ENC_LEN + 64;
+  const uint32_t j = t / n, i = t % n;
+  const uint8_t* e = sig + (size_t)SL * i + (size_t)S::ENC_LEN * j;
+  uint8_t tmp[S::ENC_LEN];
+  for (int k = 0; k < S::ENC_LEN; k++) tmp[k] = e[k];
+  uint8_t* dst = j == 0 ? output + (size_t)64 * i : proof256 + (size_t)256 * i + 64 * (j - 1);
+  flags[t] = (uint8_t)wire_decode_point_checked<S>(dst, tmp);
+}
+template <class S> __global__ void __launch_bounds__(ITEM_THREADS) k_ped_wire_scalars(uint32_t n, const uint8_t* sig, const uint8_t* flags4, uint8_t* proof256, uint8_t* valid) {
+  ITEM_INDEX(n);
+  constexpr uint32_t SL = 4 * S::ENC_LEN + 64;
+  const uint8_t* p = sig + (size_t)SL * i + 4 * S::ENC_LEN;
+  uint8_t* o = proof256 + (size_t)256 * i + 192;
+  bool ok = true;
+  for (int h = 0; h < 2; h++) {
+    for (int j = 0; j < 32; j++) o[32 * h + j] = S::SEC1 ? p[32 * h + 31 - j] : p[32 * h + j];
+    uint32_t raw[8];
+    load_le<8>(raw, o + 32 * h);
+    ok &= is_canonical<typename S::C::Fr>(raw);
+  }
+  valid[i] = (uint8_t)(ok && flags4[i] && flags4[n + i] && flags4[2 * n + i] && flags4[3 * n + i]);
+}
+template <class S> __global__ void __launch_bounds__(ITEM_THREADS) k_ped_wire_pack(uint32_t n, const uint8_t* output, const uint8_t* proof256, const uint8_t* ok, uint8_t* sig) {
+  ITEM_INDEX(n);
+  constexpr uint32_t SL = 4 * S::ENC_LEN + 64;
+  uint8_t* o = sig + (size_t)SL * i;
+  if (!ok[i]) { for (uint32_t j = 0; j < SL; j++) o[j] = 0; return; }
+  const uint8_t* pr = proof256 + (size_t)256 * i;
+  uint8_t tmp[SL];
+  encode_point_bytes<S>(tmp, output + (size_t)64 * i);
+  for (int j = 0; j < 3; j++) encode_point_bytes<S>(tmp + S::ENC_LEN * (j + 1), pr + 64 * j);
+  for (int h = 0; h < 2; h++) for (int j = 0; j < 32; j++) tmp[4 * S::ENC_LEN + 32 * h + j] = S::SEC1 ? pr[192 + 32 * h + 31 - j] : pr[192 + 32 * h + j];
+  for (uint32_t j = 0; j < SL; j++) o[j] = tmp[j];
+}
+extern "C" int vrfs_suite_pedersen_signature_len(vrfs_suite s) { return 4 * vrfs_suite_point_enc_len(s) + 64; }
+
+template <class S> static vrfs_status pedersen_sign_wire_dev(vrfs_ctx* ctx, size_t n, const uint8_t* sk, const uint8_t* data, const uint64_t* data_off, const uint8_t* ad,
+                                                             const uint64_t* ad_off, uint8_t* input, uint8_t* output, uint8_t* proof256, uint8_t* blinding, uint8_t* h2c_ok, uint8_t* sig) {
+  ST(data_to_point_dev<S>(ctx, n, data, data_off, input, h2c_ok));
+  ST(output_dev<S>(ctx, n, sk, input, output));
+  ST(pedersen_prove_dev<S>(ctx, n, sk, input, output, ad, ad_off, proof256, blinding));
+  k_ped_wire_pack<S><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, output, proof256, h2c_ok, sig);
+  LAUNCHED_AS(ctx, "ped_wire_pack");
+  return VRFS_OK;
+}
+extern "C" vrfs_status vrfs_pedersen_sign_wire_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* sk, const uint8_t* data, const uint64_t* data_off,
+                                                     const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_sig, uint8_t* out_blinding, uint8_t* out_ok) {
+  if (!ctx) return VRFS_BAD_ARG;
+  if (n == 0) return VRFS_OK;
+  if (!sk || !data_off || !out_sig || !out_blinding) return fail(ctx, VRFS_BAD_ARG, "null buffer");
+  if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
+  ST(begin_call(ctx, n));
+  const size_t sl = (size_t)vrfs_suite_pedersen_signature_len(suite);
+  const uint8_t *d_sk, *d_ad, *d_data; const uint64_t *d_off, *d_doff;
+  uint8_t *d_in, *d_out, *d_pr, *d_bl, *d_ok, *d_sig;
+  ST(stage_in(ctx, BUF_IN0, sk, n * 32, &d_sk));
+  ST(stage_ad(ctx, n, ad, ad_off, &d_ad, &d_off));
+  for (size_t i = 0; i < n; i++) if (data_off[i + 1] < data_off[i]) return fail(ctx, VRFS_BAD_ARG, "offsets must be non-decreasing");
+  if (data_off[n] > 0 && !data) return fail(ctx, VRFS_BAD_ARG, "null data buffer with non-empty offsets");
+  { const uint8_t* o; ST(stage_in(ctx, BUF_X2, data, (size_t)data_off[n], &d_data)); ST(stage_in(ctx, BUF_X3, data_off, (n + 1) * sizeof(uint64_t), &o)); d_doff = (const uint64_t*)o; }
+  ST(stage_out(ctx, BUF_IN1, n * 64, &d_in)); ST(stage_out(ctx, BUF_IN2, n * 64, &d_out)); ST(stage_out(ctx, BUF_OUT0, n * 256, &d_pr)); ST(stage_out(ctx, BUF_OUT1, n * 32, &d_bl));
+  ST(stage_out(ctx, BUF_X4, n, &d_ok)); ST(stage_out(ctx, BUF_X1, n * sl, &d_sig));
+  ST(suite == VRFS_BANDERSNATCH_ELL2 ? pedersen_sign_wire_dev<BandSuite>(ctx, n, d_sk, d_data, d_doff, d_ad, d_off, d_in, d_out, d_pr, d_bl, d_ok, d_sig)
+     : suite == VRFS_ED25519_TAI ? pedersen_sign_wire_dev<EdSuite>(ctx, n, d_sk, d_data, d_doff, d_ad, d_off, d_in, d_out, d_pr, d_bl, d_ok, d_sig)
+                                 : pedersen_sign_wire_dev<P256Suite>(ctx, n, d_sk, d_data, d_doff, d_ad, d_off, d_in, d_out, d_pr, d_bl, d_ok, d_sig));
+  ST(copy_out(ctx, out_sig, d_sig, n * sl)); ST(copy_out(ctx, out_blinding, d_bl, n * 32));
+  if (out_ok) ST(copy_out(ctx, out_ok, d_ok, n));
+  return finish_call(ctx);
+}
+template <class S> static vrfs_status pedersen_verify_wire_dev(vrfs_ctx* ctx, size_t n, const uint8_t* data, const uint64_t* data_off, const uint8_t* sig, const uint8_t* ad,
+                                                               const uint64_t* ad_off, uint8_t* input, uint8_t* output, uint8_t* proof256, uint8_t* flags /*6n*/, uint8_t* out_ok) {
+  k_ped_wire_points<S><<<item_blocks(4 * n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, sig, output, proof256, flags);
+  LAUNCHED_AS(ctx, "decode_checked");
+  k_ped_wire_scalars<S><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, sig, flags, proof256, flags + 4 * n);
+  LAUNCHED_AS(ctx, "ped_wire_scalars");
+  ST(data_to_point_dev<S>(ctx, n, data, data_off, input, flags + 5 * n));
+  ST(pedersen_verify_dev<S>(ctx, n, input, output, proof256, ad, ad_off, out_ok));
+  k_merge_flags<<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, flags + 4 * n, flags + 5 * n, out_ok, nullptr, 0u);
+  LAUNCHED_AS(ctx, "merge_flags");
+  return VRFS_OK;
+}
+extern "C" vrfs_status vrfs_pedersen_verify_wire_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* data, const uint64_t* data_off, const uint8_t* sig,
+                                                       const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_ok) {
+  if (!ctx) return VRFS_BAD_ARG;
+  if (n == 0) return VRFS_OK;
+  if (!data_off || !sig || !out_ok) return fail(ctx, VRFS_BAD_ARG, "null buffer");
+  if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
+  ST(begin_call(ctx, n));
+  const size_t sl = (size_t)vrfs_suite_pedersen_signature_len(suite);
+  const uint8_t *d_sig, *d_ad, *d_data; const uint64_t *d_off, *d_doff;
+  uint8_t *d_in, *d_out, *d_pr, *d_flags, *d_ok;
+  ST(stage_in(ctx, BUF_X1, sig, n * sl, &d_sig));
+  ST(stage_ad(ctx, n, ad, ad_off, &d_ad, &d_off));
+  for (size_t i = 0; i < n; i++) if (data_off[i + 1] < data_off[i]) return fail(ctx, VRFS_BAD_ARG, "offsets must be non-decreasing");
+  if (data_off[n] > 0 && !data) return fail(ctx, VRFS_BAD_ARG, "null data buffer with non-empty offsets");
+  { const uint8_t* o; ST(stage_in(ctx, BUF_X2, data, (size_t)data_off[n], &d_data)); ST(stage_in(ctx, BUF_X3, data_off, (n + 1) * sizeof(uint64_t), &o)); d_doff = (const uint64_t*)o; }
+  ST(stage_out(ctx, BUF_IN0, n * 64, &d_in)); ST(stage_out(ctx, BUF_IN1, n * 64, &d_out)); ST(stage_out(ctx, BUF_IN2, n * 256, &d_pr));
+  ST(stage_out(ctx, BUF_X4, 6 * n, &d_flags)); ST(stage_out(ctx, BUF_OUT0, n, &d_ok));
+  ST(suite == VRFS_BANDERSNATCH_ELL2 ? pedersen_verify_wire_dev<BandSuite>(ctx, n, d_data, d_doff, d_sig, d_ad, d_off, d_in, d_out, d_pr, d_flags, d_ok)
+     : suite == VRFS_ED25519_TAI ? pedersen_verify_wire_dev<EdSuite>(ctx, n, d_data, d_doff, d_sig, d_ad, d_off, d_in, d_out, d_pr, d_flags, d_ok)
+                                 : pedersen_verify_wire_dev<P256Suite>(ctx, n, d_data, d_doff, d_sig, d_ad, d_off, d_in, d_out, d_pr, d_flags, d_ok));
+  ST(copy_out(ctx, out_ok, d_ok, n));
+  return finish_call(ctx);
+}
+
 // =================================================================================================
 // ring commitment MSM (K12)
 // =================================================================================================

@@ -201,6 +201,22 @@ class Engine:
         self._call("vrfs_ietf_verify_wire_batch", suite, C.c_size_t(n), _p(pk_enc), _p(data), _p(doff), _p(sig), _p(adb), _p(off), _p(ok), _p(h))
         return (ok, h) if want_hash else ok
 
+    def pedersen_signature_len(self, suite):
+        return int(self._lib.vrfs_suite_pedersen_signature_len(suite))
+
+    def pedersen_sign_wire(self, suite, sk, datas, ad=None):
+        """Output || pedersen::Proof serialised (4 encoded points + 2 scalars); returns (sig, blinding, ok)"""
+        sk = _u8(sk, (-1, 32)); n = len(sk); data, doff = pack_var(datas); adb, off = pack_var(ad)
+        sig = np.zeros((n, self.pedersen_signature_len(suite)), np.uint8); bl = np.zeros((n, 32), np.uint8); ok = np.zeros(n, np.uint8)
+        self._call("vrfs_pedersen_sign_wire_batch", suite, C.c_size_t(n), _p(sk), _p(data), _p(doff), _p(adb), _p(off), _p(sig), _p(bl), _p(ok))
+        return sig, bl, ok
+
+    def pedersen_verify_wire(self, suite, datas, sig, ad=None):
+        sig = _u8(sig, (-1, self.pedersen_signature_len(suite))); n = len(sig); data, doff = pack_var(datas); adb, off = pack_var(ad)
+        ok = np.zeros(n, np.uint8)
+        self._call("vrfs_pedersen_verify_wire_batch", suite, C.c_size_t(n), _p(data), _p(doff), _p(sig), _p(adb), _p(off), _p(ok))
+        return ok
+
     # ---- pedersen
     def pedersen_prove(self, suite, sk, inp, outp, ad=None):
         sk = _u8(sk, (-1, 32)); n = len(sk); inp = _u8(inp, (n, 64)); outp = _u8(outp, (n, 64))

@@ -113,6 +113,15 @@ vrfs_status vrfs_ietf_verify_wire_batch(vrfs_ctx*, vrfs_suite, size_t n, const u
                                         const uint64_t* data_off, const uint8_t* sig /*n*sig_len*/, const uint8_t* ad,
                                         const uint64_t* ad_off, uint8_t* out_ok, uint8_t* out_hash);
 
+/* Pedersen on the wire: signature = point_encode(Output) || point_encode(pk_com) || point_encode(r) || point_encode(ok) || s || sb
+ * (an `Output` followed by `pedersen::Proof`'s CanonicalSerialize; Bandersnatch 192 B).  Deserialisation validates all four points
+ * (canonical, on curve, prime-order subgroup) and both scalars (canonical).  The blinding factor is returned to the prover only. */
+int vrfs_suite_pedersen_signature_len(vrfs_suite s);
+vrfs_status vrfs_pedersen_sign_wire_batch(vrfs_ctx*, vrfs_suite, size_t n, const uint8_t* sk, const uint8_t* data, const uint64_t* data_off,
+                                          const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_sig /*n*sig_len*/, uint8_t* out_blinding /*n*32*/, uint8_t* out_ok);
+vrfs_status vrfs_pedersen_verify_wire_batch(vrfs_ctx*, vrfs_suite, size_t n, const uint8_t* data, const uint64_t* data_off, const uint8_t* sig /*n*sig_len*/,
+                                            const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_ok);
+
 /* ring commitment MSM (ark-ec VariableBaseMSM::msm behind ring-proof's KZG commit):
  * n_columns scalar columns (column-major, n*32 bytes each) over one base vector of n affine G1 points.
  * out: n_columns * 96 bytes affine. */

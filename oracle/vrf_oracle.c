@@ -879,6 +879,51 @@ void oracle_ietf_verify_wire_batch(int suite, size_t n, const uint8_t *pk_enc, c
     parallel_for(n, nthreads, it_verify_wire, &x);
 }
 
+/* pedersen wire form: point_encode(Output) || point_encode(pk_com) || point_encode(r) || point_encode(ok) || s || sb
+ * (`Output` followed by `pedersen::Proof`'s CanonicalSerialize, A.10); the blinding factor stays with the prover. */
+int oracle_pedersen_signature_len(int suite) { const suite_t *S = get_suite(suite); return 4 * (S->sec1 ? 33 : 32) + 64; }
+static void it_ped_sign_wire(void *p, size_t i) {
+    bctx *x = p; const suite_t *S = x->S; const curve *C = S->C; size_t PL = S->sec1 ? 33 : 32, SL = 4 * PL + 64;
+    uint8_t *sig = x->o1 + SL * i; fe sk, bl; aff I, O; ped_proof pr;
+    load_scalar(C, &sk, x->a + 32 * i);
+    if (!data_to_point(S, &I, x->b + x->off[i], (size_t)(x->off[i + 1] - x->off[i]))) { memset(sig, 0, SL); memset(x->o3 + 32 * i, 0, 32); x->o2[i] = 0; return; }
+    aff_mul(C, &O, &sk, &I);
+    const uint8_t *ad = x->c ? x->c + ((const uint64_t *)x->d)[i] : (const uint8_t *)"";
+    size_t adlen = x->c ? (size_t)(((const uint64_t *)x->d)[i + 1] - ((const uint64_t *)x->d)[i]) : 0;
+    pedersen_prove_one(S, &sk, &I, &O, ad, adlen, &pr, &bl);
+    enc_point(S, &O, sig); enc_point(S, &pr.Yb, sig + PL); enc_point(S, &pr.R, sig + 2 * PL); enc_point(S, &pr.Ok, sig + 3 * PL);
+    enc_scalar(S, &pr.s, sig + 4 * PL); enc_scalar(S, &pr.sb, sig + 4 * PL + 32);
+    store_scalar(&bl, x->o3 + 32 * i);
+    x->o2[i] = 1;
+}
+void oracle_pedersen_sign_wire_batch(int suite, size_t n, const uint8_t *sk, const uint8_t *data, const uint64_t *data_off,
+                                     const uint8_t *ad, const uint64_t *ad_off, uint8_t *out_sig, uint8_t *out_blinding, uint8_t *out_ok, int nthreads) {
+    bctx x = {0}; x.S = get_suite(suite); x.a = sk; x.b = data; x.off = data_off; x.c = ad; x.d = (const uint8_t *)ad_off; x.o1 = out_sig; x.o2 = out_ok; x.o3 = out_blinding;
+    parallel_for(n, nthreads, it_ped_sign_wire, &x);
+}
+static int dec_scalar_canonical(const suite_t *S, fe *k_raw, const uint8_t *in) {
+    uint8_t le[32]; fe m;
+    for (int j = 0; j < 32; j++) le[j] = S->sec1 ? in[31 - j] : in[j];
+    if (!f_from_le_canonical(S->C->Fr, &m, le)) return 0;
+    f_to_raw(S->C->Fr, k_raw, &m); return 1;
+}
+static void it_ped_verify_wire(void *p, size_t i) {
+    bctx *x = p; const suite_t *S = x->S; size_t PL = S->sec1 ? 33 : 32, SL = 4 * PL + 64;
+    const uint8_t *sig = x->e + SL * i; aff I, O; ped_proof pr;
+    x->o1[i] = 0;
+    if (!dec_point_checked(S, &O, sig) || !dec_point_checked(S, &pr.Yb, sig + PL) || !dec_point_checked(S, &pr.R, sig + 2 * PL) || !dec_point_checked(S, &pr.Ok, sig + 3 * PL)) return;
+    if (!dec_scalar_canonical(S, &pr.s, sig + 4 * PL) || !dec_scalar_canonical(S, &pr.sb, sig + 4 * PL + 32)) return;
+    if (!data_to_point(S, &I, x->b + x->off[i], (size_t)(x->off[i + 1] - x->off[i]))) return;
+    const uint8_t *ad = x->c ? x->c + ((const uint64_t *)x->d)[i] : (const uint8_t *)"";
+    size_t adlen = x->c ? (size_t)(((const uint64_t *)x->d)[i + 1] - ((const uint64_t *)x->d)[i]) : 0;
+    x->o1[i] = (uint8_t)pedersen_verify_one(S, &I, &O, &pr, ad, adlen);
+}
+void oracle_pedersen_verify_wire_batch(int suite, size_t n, const uint8_t *data, const uint64_t *data_off, const uint8_t *sig,
+                                       const uint8_t *ad, const uint64_t *ad_off, uint8_t *out_ok, int nthreads) {
+    bctx x = {0}; x.S = get_suite(suite); x.b = data; x.off = data_off; x.e = sig; x.c = ad; x.d = (const uint8_t *)ad_off; x.o1 = out_ok;
+    parallel_for(n, nthreads, it_ped_verify_wire, &x);
+}
+
 /* ======================================================================================
  * BLS12-381 G1 MSM  (ark-ec VariableBaseMSM::msm -> msm_bigint: Pippenger with
  * c = 3 for n < 32, else ln(n) + 2; per-window bucket accumulation + running sum; windows

@@ -81,6 +81,11 @@ void oracle_ietf_sign_wire_batch(int suite, size_t n, const uint8_t *sk, const u
                                  const uint8_t *ad, const uint64_t *ad_off, uint8_t *out_sig, uint8_t *out_ok, int nthreads);
 void oracle_ietf_verify_wire_batch(int suite, size_t n, const uint8_t *pk_enc, const uint8_t *data, const uint64_t *data_off, const uint8_t *sig,
                                    const uint8_t *ad, const uint64_t *ad_off, uint8_t *out_ok, uint8_t *out_hash, int nthreads);
+int oracle_pedersen_signature_len(int suite);
+void oracle_pedersen_sign_wire_batch(int suite, size_t n, const uint8_t *sk, const uint8_t *data, const uint64_t *data_off,
+                                     const uint8_t *ad, const uint64_t *ad_off, uint8_t *out_sig, uint8_t *out_blinding, uint8_t *out_ok, int nthreads);
+void oracle_pedersen_verify_wire_batch(int suite, size_t n, const uint8_t *data, const uint64_t *data_off, const uint8_t *sig,
+                                       const uint8_t *ad, const uint64_t *ad_off, uint8_t *out_ok, int nthreads);
 /* ark-ec VariableBaseMSM::msm over BLS12-381 G1: n_columns scalar columns over one base vector.
  * bases n*96 B, scalars n_columns*n*32 B (column-major), out n_columns*96 B (identity = zeros). */
 void oracle_msm_g1(size_t n, const uint8_t *bases, const uint8_t *scalars, int n_columns, uint8_t *out, int nthreads);

@@ -25,7 +25,7 @@ def lib():
         if not os.path.exists(so) or (os.path.exists(src) and os.path.getmtime(so) < os.path.getmtime(src)):
             build()
         _lib = C.CDLL(so)
-        for f in ("oracle_hash_len", "oracle_point_enc_len", "oracle_challenge_len"):
+        for f in ("oracle_hash_len", "oracle_point_enc_len", "oracle_challenge_len", "oracle_ietf_signature_len", "oracle_pedersen_signature_len"):
             getattr(_lib, f).restype = C.c_int
     return _lib
 
@@ -179,3 +179,21 @@ def ietf_verify_wire(suite, pk_enc, datas, sig, ads=None, want_hash=True, nthrea
     ok = np.zeros(n, np.uint8); h = np.zeros((n, lib().oracle_hash_len(suite)), np.uint8) if want_hash else None
     lib().oracle_ietf_verify_wire_batch(suite, C.c_size_t(n), _p(pk_enc), _p(data), _p(off), _p(sig), _p(ad), _p(aoff), _p(ok), _p(h), nthreads)
     return (ok, h) if want_hash else ok
+
+
+def pedersen_signature_len(suite):
+    return int(lib().oracle_pedersen_signature_len(suite))
+
+
+def pedersen_sign_wire(suite, sk, datas, ads=None, nthreads=NTHREADS):
+    sk = _u8(sk, (-1, 32)); n = len(sk); data, off = pack_var(datas); ad, aoff = _ad(ads, n)
+    sig = np.zeros((n, pedersen_signature_len(suite)), np.uint8); bl = np.zeros((n, 32), np.uint8); ok = np.zeros(n, np.uint8)
+    lib().oracle_pedersen_sign_wire_batch(suite, C.c_size_t(n), _p(sk), _p(data), _p(off), _p(ad), _p(aoff), _p(sig), _p(bl), _p(ok), nthreads)
+    return sig, bl, ok
+
+
+def pedersen_verify_wire(suite, datas, sig, ads=None, nthreads=NTHREADS):
+    sig = _u8(sig, (-1, pedersen_signature_len(suite))); n = len(sig); data, off = pack_var(datas); ad, aoff = _ad(ads, n)
+    ok = np.zeros(n, np.uint8)
+    lib().oracle_pedersen_verify_wire_batch(suite, C.c_size_t(n), _p(data), _p(off), _p(sig), _p(ad), _p(aoff), _p(ok), nthreads)
+    return ok

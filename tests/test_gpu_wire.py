@@ -113,3 +113,34 @@ def test_wire_large_batch_roundtrip(eng):
     sub = np.arange(0, n, 997)                                          # oracle spot check
     ok_o, beta_o = O.ietf_verify_wire(O.BANDERSNATCH, pk_enc[sub], [datas[i] for i in sub], sig[sub], None)
     assert np.array_equal(ok_o, okv[sub]) and np.array_equal(beta_o, beta[sub])
+
+
+@pytest.mark.parametrize("suite", SUITES)
+def test_pedersen_sign_and_verify_wire(eng, suite):
+    n = 192
+    sk, pk = O.secret_from_seed(suite, [b"ped-wire-%d" % i for i in range(n)])
+    datas = [bytes((i * 5 + j) & 0xFF for j in range((i * 3) % 100)) for i in range(n)]
+    ads = [bytes((i + 2 * j) & 0xFF for j in range((i * 11) % 90)) for i in range(n)]
+    sig_o, bl_o, ok_o = O.pedersen_sign_wire(suite, sk, datas, ads)
+    sig, bl, ok = eng.pedersen_sign_wire(suite, sk, datas, ads)
+    assert ok_o.all() and np.array_equal(ok, ok_o) and np.array_equal(sig, sig_o) and np.array_equal(bl, bl_o)
+    L = eng.point_enc_len(suite)
+    sig = sig.copy(); datas = list(datas)
+    for i in range(0, n, 3):
+        kind = (i // 3) % 7
+        if kind < 4: sig[i, kind * L + 1 + (i % 20)] ^= 0x10          # one of the four encoded points
+        elif kind == 4: sig[i, 4 * L + (i % 31)] ^= 0x08               # s
+        elif kind == 5: sig[i, 4 * L + 32 + (i % 31)] ^= 0x08          # sb
+        else: datas[i] = datas[i] + b"!"                               # wrong input
+    exp = O.pedersen_verify_wire(suite, datas, sig, ads)
+    got = eng.pedersen_verify_wire(suite, datas, sig, ads)
+    assert np.array_equal(got, exp) and exp[1::3].all() and exp[2::3].all() and not exp[::3].all()
+    # upstream Pedersen vector 1 through the wire form
+    if suite == O.BANDERSNATCH:
+        g = json.load(open(os.path.join(GOLDEN, "bandersnatch_upstream.json")))
+        for v in g["pedersen"]:
+            skv = np.frombuffer(bytes.fromhex(v["sk"]), np.uint8); data = bytes.fromhex(v["salt"]) + bytes.fromhex(v["alpha"]); ad = bytes.fromhex(v["ad"])
+            s1, b1, k1 = eng.pedersen_sign_wire(suite, skv, [data], [ad])
+            assert k1[0] and b1[0].tobytes().hex() == v["blinding"]
+            assert s1[0].tobytes().hex() == v["gamma"] + v["proof_pk_com"] + v["proof_r"] + v["proof_ok"] + v["proof_s"] + v["proof_sb"]
+            assert eng.pedersen_verify_wire(suite, [data], s1, [ad])[0] == 1

@@ -83,6 +83,18 @@ def test_oracle_signature_bytes_match_upstream_and_rfc9381():
         assert okv[0]
 
 
+def test_oracle_pedersen_wire_matches_upstream():
+    g = json.load(open(os.path.join(GOLDEN, "bandersnatch_upstream.json")))
+    for v in g["pedersen"]:
+        sk = np.frombuffer(bytes.fromhex(v["sk"]), np.uint8); data = bytes.fromhex(v["salt"]) + bytes.fromhex(v["alpha"]); ad = bytes.fromhex(v["ad"])
+        sig, bl, ok = O.pedersen_sign_wire(O.BANDERSNATCH, sk, [data], [ad])
+        assert ok[0] and bl[0].tobytes().hex() == v["blinding"]
+        assert sig[0].tobytes().hex() == v["gamma"] + v["proof_pk_com"] + v["proof_r"] + v["proof_ok"] + v["proof_s"] + v["proof_sb"]
+        assert O.pedersen_verify_wire(O.BANDERSNATCH, [data], sig, [ad])[0] == 1
+        bad = sig.copy(); bad[0, 100] ^= 1
+        assert O.pedersen_verify_wire(O.BANDERSNATCH, [data], bad, [ad])[0] == 0
+
+
 @pytest.mark.parametrize("suite", [O.BANDERSNATCH, O.ED25519, O.P256])
 def test_proof_bytes_roundtrip_device_code(emu, suite):
     sk, pk = O.secret_from_seed(suite, [b"rt"])
