@@ -144,3 +144,33 @@ def test_pedersen_sign_and_verify_wire(eng, suite):
             assert k1[0] and b1[0].tobytes().hex() == v["blinding"]
             assert s1[0].tobytes().hex() == v["gamma"] + v["proof_pk_com"] + v["proof_r"] + v["proof_ok"] + v["proof_s"] + v["proof_sb"]
             assert eng.pedersen_verify_wire(suite, [data], s1, [ad])[0] == 1
+
+
+def test_wire_edge_cases(eng):
+    import ark_ec_vrfs_b200 as vrfs
+    s = O.BANDERSNATCH
+    # empty batches are accepted and return empty results
+    sig, ok = eng.ietf_sign_wire(s, np.zeros((0, 32), np.uint8), [])
+    assert sig.shape == (0, 96) and ok.shape == (0,)
+    okv, beta = eng.ietf_verify_wire(s, np.zeros((0, 32), np.uint8), [], np.zeros((0, 96), np.uint8))
+    assert okv.shape == (0,) and beta.shape == (0, 64)
+    assert eng.pedersen_verify_wire(s, [], np.zeros((0, 192), np.uint8)).shape == (0,)
+    # empty VRF input data, empty and long additional data in one batch
+    sk, pk = O.secret_from_seed(s, [b"e0", b"e1", b"e2"])
+    datas = [b"", b"x", b""]; ads = [b"", b"y" * 300, b"z"]
+    sig, ok = eng.ietf_sign_wire(s, sk, datas, ads)
+    sig_o, _ = O.ietf_sign_wire(s, sk, datas, ads)
+    assert ok.all() and np.array_equal(sig, sig_o)
+    assert eng.ietf_verify_wire(s, O.point_encode(s, pk), datas, sig, ads, want_hash=False).all()
+    # all-zero and all-ones keys / signatures are rejected item by item, never crash the call
+    junk = np.zeros((4, 96), np.uint8); junk[1] = 0xFF; junk[2, 31] = 0x80; junk[3, :32] = sig[0, :32]
+    keys = np.zeros((4, 32), np.uint8); keys[1] = 0xFF; keys[3] = O.point_encode(s, pk)[0]
+    got = eng.ietf_verify_wire(s, keys, [b"a"] * 4, junk, None, want_hash=False)
+    exp = O.ietf_verify_wire(s, keys, [b"a"] * 4, junk, None, want_hash=False)
+    assert np.array_equal(got, exp) and not got.any()
+    # decreasing offsets are a caller bug: status code, not a verdict
+    bad_off = (np.zeros(8, np.uint8), np.array([0, 4, 2, 8], np.uint64))
+    with pytest.raises(vrfs.VrfsError):
+        eng.ietf_sign_wire(s, sk, bad_off)
+    with pytest.raises(vrfs.VrfsError):
+        eng.ietf_verify_wire(s, O.point_encode(s, pk), bad_off, sig)
