@@ -1,0 +1,195 @@
+// vrfs_b200.hpp - header-only C++17 mirror of the reference's public API for the hot path, over the C ABI of
+// vrfs_b200.h.  The reference is Rust (`ark-ec-vrfs` = `ark-vrf` 0.1.0; the names below are the ones re-exported at
+// /root/reference/src/lib.rs:13-17: Suite, Secret, Public, Input, Output, ietf, pedersen, codec) and no Rust toolchain exists
+// in the build image, so this is the compiled-language host side: same names, same argument meaning, and the reference's
+// error behaviour mapped onto batches:
+//     Result<(), Error>   ->  std::vector<uint8_t>, 1 = Ok(()), 0 = Err(VerificationFailure | InvalidData)
+//     Option<Input>       ->  Input + ok flags
+// Every type holds a BATCH of n values in the ABI's layout (scalars 32 B LE, points affine x||y 64 B LE); every method is one
+// call into libvrfs_b200.so.  Whole-call failures (CUDA errors, bad arguments) throw vrfs::CallError - they are never turned
+// into a verdict.  There is no CPU implementation behind these classes.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "vrfs_b200.h"
+
+namespace vrfs {
+
+using Bytes = std::vector<uint8_t>;
+
+struct CallError : std::runtime_error {
+  vrfs_status status;
+  CallError(vrfs_status st, const std::string& msg) : std::runtime_error(msg), status(st) {}
+};
+
+// variable-length items (`ad`, VRF input data, seeds): concatenation + n+1 offsets
+struct Packed {
+  Bytes data;
+  std::vector<uint64_t> off;
+  Packed() : off(1, 0) {}
+  explicit Packed(const std::vector<Bytes>& items) : off(1, 0) {
+    for (const auto& b : items) { data.insert(data.end(), b.begin(), b.end()); off.push_back(data.size()); }
+  }
+  size_t size() const { return off.size() - 1; }
+  const uint8_t* ptr() const { return data.empty() ? reinterpret_cast<const uint8_t*>("") : data.data(); }
+};
+
+// one context on one GPU (RAII)
+class Engine {
+ public:
+  explicit Engine(int device = 0) {
+    vrfs_status st = vrfs_ctx_create(device, &ctx_);
+    if (st != VRFS_OK) {
+      std::string msg = ctx_ ? vrfs_last_error(ctx_) : "context allocation failed";
+      if (ctx_) vrfs_ctx_destroy(ctx_);
+      ctx_ = nullptr;
+      throw CallError(st, msg);
+    }
+  }
+  ~Engine() { if (ctx_) vrfs_ctx_destroy(ctx_); }
+  Engine(const Engine&) = delete;
+  Engine& operator=(const Engine&) = delete;
+  vrfs_ctx* ctx() const { return ctx_; }
+  void check(vrfs_status st) const { if (st != VRFS_OK) throw CallError(st, vrfs_last_error(ctx_)); }
+
+ private:
+  vrfs_ctx* ctx_ = nullptr;
+};
+
+// ark_vrf::Suite: one ciphersuite bound to one engine
+struct Suite {
+  vrfs_suite id;
+  Engine* engine;
+  static Suite bandersnatch(Engine& e) { return {VRFS_BANDERSNATCH_ELL2, &e}; }
+  static Suite ed25519(Engine& e) { return {VRFS_ED25519_TAI, &e}; }
+  static Suite secp256r1(Engine& e) { return {VRFS_P256_TAI, &e}; }
+  size_t challenge_len() const { return (size_t)vrfs_suite_challenge_len(id); }           // Suite::CHALLENGE_LEN
+  size_t hash_len() const { return (size_t)vrfs_suite_hash_len(id); }
+  size_t point_enc_len() const { return (size_t)vrfs_suite_point_enc_len(id); }
+  size_t ietf_signature_len() const { return (size_t)vrfs_suite_ietf_signature_len(id); }
+  size_t pedersen_signature_len() const { return (size_t)vrfs_suite_pedersen_signature_len(id); }
+};
+
+struct Points { Suite suite; Bytes xy; size_t size() const { return xy.size() / 64; } };   // n affine points
+
+struct Input : Points {
+  // Input::new(data) = Suite::data_to_point; ok[i] = 0 stands for None
+  static std::pair<Input, Bytes> new_(const Suite& s, const std::vector<Bytes>& datas) {
+    Packed d(datas); size_t n = d.size();
+    Input in{{s, Bytes(64 * n)}}; Bytes ok(n);
+    s.engine->check(vrfs_data_to_point_batch(s.engine->ctx(), s.id, n, d.ptr(), d.off.data(), in.xy.data(), ok.data()));
+    return {std::move(in), std::move(ok)};
+  }
+};
+
+struct Output : Points {
+  Bytes hash() const {                                   // Output::hash = Suite::point_to_hash
+    Bytes h(suite.hash_len() * size());
+    suite.engine->check(vrfs_point_to_hash_batch(suite.engine->ctx(), suite.id, size(), xy.data(), h.data()));
+    return h;
+  }
+  Bytes serialize_compressed() const {
+    Bytes e(suite.point_enc_len() * size());
+    suite.engine->check(vrfs_point_encode_batch(suite.engine->ctx(), suite.id, size(), xy.data(), e.data()));
+    return e;
+  }
+};
+
+namespace ietf {
+struct Proof { Bytes c, s; };                            // n x 32-byte little-endian scalars each
+}
+namespace pedersen {
+struct Proof { Bytes raw; };                             // n x 256: pk_com || r || ok (64 B affine each) || s || sb
+}
+
+struct Public : Points {
+  // ietf::Verifier::verify
+  Bytes verify(const Input& input, const Output& output, const std::vector<Bytes>& ad, const ietf::Proof& proof) const {
+    Packed a(ad); size_t n = size(); Bytes ok(n);
+    suite.engine->check(vrfs_ietf_verify_batch(suite.engine->ctx(), suite.id, n, xy.data(), input.xy.data(), output.xy.data(), proof.c.data(),
+                                               proof.s.data(), a.ptr(), a.off.data(), ok.data()));
+    return ok;
+  }
+  Bytes serialize_compressed() const {
+    Bytes e(suite.point_enc_len() * size());
+    suite.engine->check(vrfs_point_encode_batch(suite.engine->ctx(), suite.id, size(), xy.data(), e.data()));
+    return e;
+  }
+  // CanonicalDeserialize with validation: canonical, on curve, prime-order subgroup
+  static std::pair<Public, Bytes> deserialize_compressed(const Suite& s, const Bytes& enc) {
+    size_t n = enc.size() / s.point_enc_len();
+    Public p{{s, Bytes(64 * n)}}; Bytes ok(n);
+    s.engine->check(vrfs_point_decode_checked_batch(s.engine->ctx(), s.id, n, enc.data(), p.xy.data(), ok.data()));
+    return {std::move(p), std::move(ok)};
+  }
+  // serialised keys + VRF input data + serialised signatures (Output || ietf::Proof) -> ok flags and Output::hash
+  static std::pair<Bytes, Bytes> verify_signatures(const Suite& s, const Bytes& pk_enc, const std::vector<Bytes>& datas, const Bytes& sigs,
+                                                   const std::vector<Bytes>& ad) {
+    Packed d(datas), a(ad); size_t n = d.size(); Bytes ok(n), beta(n * s.hash_len());
+    s.engine->check(vrfs_ietf_verify_wire_batch(s.engine->ctx(), s.id, n, pk_enc.data(), d.ptr(), d.off.data(), sigs.data(), a.ptr(), a.off.data(),
+                                                ok.data(), beta.data()));
+    return {std::move(ok), std::move(beta)};
+  }
+};
+
+struct Secret {
+  Suite suite;
+  Bytes scalars;                                         // n x 32
+  Bytes public_points;                                   // n x 64
+  size_t size() const { return scalars.size() / 32; }
+  static Secret from_seed(const Suite& s, const std::vector<Bytes>& seeds) {
+    Packed d(seeds); size_t n = d.size();
+    Secret k{s, Bytes(32 * n), Bytes(64 * n)};
+    s.engine->check(vrfs_secret_from_seed_batch(s.engine->ctx(), s.id, n, d.ptr(), d.off.data(), k.scalars.data(), k.public_points.data()));
+    return k;
+  }
+  Public public_() const { return Public{{suite, public_points}}; }
+  Output output(const Input& input) const {              // Secret::output
+    Output o{{suite, Bytes(64 * size())}};
+    suite.engine->check(vrfs_output_batch(suite.engine->ctx(), suite.id, size(), scalars.data(), input.xy.data(), o.xy.data()));
+    return o;
+  }
+  ietf::Proof prove(const Input& input, const Output& output, const std::vector<Bytes>& ad) const {      // ietf::Prover::prove
+    Packed a(ad); size_t n = size(); ietf::Proof p{Bytes(32 * n), Bytes(32 * n)};
+    suite.engine->check(vrfs_ietf_prove_batch(suite.engine->ctx(), suite.id, n, scalars.data(), input.xy.data(), output.xy.data(), a.ptr(),
+                                              a.off.data(), p.c.data(), p.s.data()));
+    return p;
+  }
+  // pedersen::Prover::prove -> (Proof, blinding factors)
+  std::pair<pedersen::Proof, Bytes> pedersen_prove(const Input& input, const Output& output, const std::vector<Bytes>& ad) const {
+    Packed a(ad); size_t n = size(); pedersen::Proof p{Bytes(256 * n)}; Bytes bl(32 * n);
+    suite.engine->check(vrfs_pedersen_prove_batch(suite.engine->ctx(), suite.id, n, scalars.data(), input.xy.data(), output.xy.data(), a.ptr(),
+                                                  a.off.data(), p.raw.data(), bl.data()));
+    return {std::move(p), std::move(bl)};
+  }
+  // Input::new(data) -> output -> ietf prove -> serialised signatures point_encode(Output) || c || s
+  std::pair<Bytes, Bytes> sign(const std::vector<Bytes>& datas, const std::vector<Bytes>& ad) const {
+    Packed d(datas), a(ad); size_t n = size(); Bytes sig(n * suite.ietf_signature_len()), ok(n);
+    suite.engine->check(vrfs_ietf_sign_wire_batch(suite.engine->ctx(), suite.id, n, scalars.data(), d.ptr(), d.off.data(), a.ptr(), a.off.data(),
+                                                  sig.data(), ok.data()));
+    return {std::move(sig), std::move(ok)};
+  }
+};
+
+namespace pedersen {
+// pedersen::Verifier::verify (needs no public key)
+inline Bytes verify(const Suite& s, const Input& input, const Output& output, const std::vector<Bytes>& ad, const Proof& proof) {
+  Packed a(ad); size_t n = input.size(); Bytes ok(n);
+  s.engine->check(vrfs_pedersen_verify_batch(s.engine->ctx(), s.id, n, input.xy.data(), output.xy.data(), proof.raw.data(), a.ptr(), a.off.data(), ok.data()));
+  return ok;
+}
+}  // namespace pedersen
+
+// the three KZG commitments behind RingContext::verifier_key: one MSM per scalar column over the SRS bases (BLS12-381 G1)
+inline Bytes ring_commitment_msm(Engine& e, const Bytes& bases /*n*96*/, const Bytes& scalar_columns /*ncol*n*32*/, int n_columns) {
+  size_t n = bases.size() / 96; Bytes out(96 * (size_t)n_columns);
+  e.check(vrfs_msm_g1_bls12_381(e.ctx(), n, bases.data(), scalar_columns.data(), n_columns, out.data()));
+  return out;
+}
+
+}  // namespace vrfs

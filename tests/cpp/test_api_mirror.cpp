@@ -1,0 +1,89 @@
+// The reference's own round-trip tests (`prove_verify_works` of suite_tests! / ietf_suite_tests! / pedersen_suite_tests!,
+// SURVEY.md 4) replayed through the C++ mirror of its API (include/vrfs_b200.hpp), plus upstream Bandersnatch vector 1.
+// Built and run by tests/test_gpu_cpp_mirror.py on a GPU box; `--compile-only` use on CPU boxes is just the build.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "../../include/vrfs_b200.hpp"
+
+using namespace vrfs;
+
+static int failures = 0;
+#define CHECK(cond) do { if (!(cond)) { std::printf("FAIL %s:%d: %s\n", __FILE__, __LINE__, #cond); failures++; } } while (0)
+
+static Bytes bytes(const std::string& s) { return Bytes(s.begin(), s.end()); }
+static Bytes unhex(const std::string& h) {
+  Bytes o;
+  for (size_t i = 0; i + 1 < h.size(); i += 2) o.push_back((uint8_t)std::strtoul(h.substr(i, 2).c_str(), nullptr, 16));
+  return o;
+}
+static std::string hex(const uint8_t* p, size_t n) {
+  static const char* d = "0123456789abcdef"; std::string s;
+  for (size_t i = 0; i < n; i++) { s += d[p[i] >> 4]; s += d[p[i] & 15]; }
+  return s;
+}
+static bool all(const Bytes& v, uint8_t x) { for (auto b : v) if (b != x) return false; return !v.empty(); }
+
+static void prove_verify_works(const Suite& suite, const char* name) {
+  const size_t n = 48;
+  std::vector<Bytes> seeds, alphas, ad, ad2;
+  for (size_t i = 0; i < n; i++) { seeds.push_back(bytes("TEST_SEED-" + std::to_string(i))); alphas.push_back(bytes("foo-" + std::to_string(i))); ad.push_back(bytes("bar")); ad2.push_back(bytes("baz")); }
+  Secret secret = Secret::from_seed(suite, seeds);
+  Public pub = secret.public_();
+  auto [input, ok] = Input::new_(suite, alphas);
+  CHECK(all(ok, 1));
+  Output output = secret.output(input);
+  ietf::Proof proof = secret.prove(input, output, ad);
+  CHECK(all(pub.verify(input, output, ad, proof), 1));
+  CHECK(all(pub.verify(input, output, ad2, proof), 0));                         // Error::VerificationFailure
+  auto [ped, blinding] = secret.pedersen_prove(input, output, ad);
+  CHECK(all(pedersen::verify(suite, input, output, ad, ped), 1));
+  CHECK(all(pedersen::verify(suite, input, output, ad2, ped), 0));
+  CHECK(blinding.size() == 32 * n && output.hash().size() == suite.hash_len() * n);
+  // serialisation: keys round-trip with validation; signatures straight off the wire
+  auto [pub2, kok] = Public::deserialize_compressed(suite, pub.serialize_compressed());
+  CHECK(all(kok, 1) && pub2.xy == pub.xy);
+  auto [sig, sok] = secret.sign(alphas, ad);
+  CHECK(all(sok, 1) && sig.size() == n * suite.ietf_signature_len());
+  CHECK(std::memcmp(sig.data(), output.serialize_compressed().data(), suite.point_enc_len()) == 0);
+  auto [vok, beta] = Public::verify_signatures(suite, pub.serialize_compressed(), alphas, sig, ad);
+  CHECK(all(vok, 1) && beta == output.hash());
+  sig[suite.point_enc_len() + 3] ^= 1;                                           // corrupt item 0's challenge
+  auto [vok2, beta2] = Public::verify_signatures(suite, pub.serialize_compressed(), alphas, sig, ad);
+  CHECK(vok2[0] == 0 && vok2[1] == 1 && all(Bytes(beta2.begin(), beta2.begin() + suite.hash_len()), 0));
+  std::printf("%s: prove_verify_works %s\n", name, failures ? "FAILED" : "ok");
+}
+
+int main() {
+  try {
+    Engine eng(0);
+    prove_verify_works(Suite::bandersnatch(eng), "bandersnatch");
+    prove_verify_works(Suite::ed25519(eng), "ed25519");
+    prove_verify_works(Suite::secp256r1(eng), "secp256r1");
+    // upstream bandersnatch_sha-512_ell2_ietf vector 1 (tests/golden/bandersnatch_upstream.json): seed = [01], alpha = "", ad = ""
+    Suite s = Suite::bandersnatch(eng);
+    Secret k = Secret::from_seed(s, {Bytes{0x01}});
+    CHECK(hex(k.scalars.data(), 32) == "3d6406500d4009fdf2604546093665911e753f2213570a29521fd88bc30ede18");
+    CHECK(hex(k.public_().serialize_compressed().data(), 32) == "a1b1da71cc4682e159b7da23050d8b6261eb11a3247c89b07ef56ccd002fd38b");
+    auto [sig, ok] = k.sign({Bytes{}}, {Bytes{}});
+    CHECK(ok[0] == 1);
+    CHECK(hex(sig.data(), 96) == "e7aa5154103450f0a0525a36a441f827296ee489ef30ed8787cff8df1bef223f"
+                                 "439fd9495643314fa623f2581f4b3d7d6037394468084f4ad7d8031479d9d101"
+                                 "828bedd2ad95380b11f67a05ea0a76f0c3fef2bee9f043f4dffdddde09f55c01");
+    auto [vok, beta] = Public::verify_signatures(s, k.public_().serialize_compressed(), {Bytes{}}, sig, {Bytes{}});
+    CHECK(vok[0] == 1);
+    CHECK(hex(beta.data(), 64) == "fdeb377a4ffd7f95ebe48e5b43a88d069ce62188e49493500315ad55ee04d7442b93c4c91d5475370e9380496f4bc0b838c2483bce4e133c6f18b0adbb9e4722");
+    // a whole-call failure is an exception, not a verdict
+    bool threw = false;
+    try { vrfs_status st = vrfs_ietf_verify_batch(eng.ctx(), (vrfs_suite)9, 1, sig.data(), sig.data(), sig.data(), sig.data(), sig.data(), nullptr, nullptr, sig.data()); eng.check(st); }
+    catch (const CallError& e) { threw = e.status == VRFS_BAD_ARG; }
+    CHECK(threw);
+  } catch (const CallError& e) {
+    std::printf("CallError %d: %s\n", (int)e.status, e.what());
+    return 2;
+  }
+  std::printf(failures ? "FAILED (%d)\n" : "all ok\n", failures);
+  return failures ? 1 : 0;
+}
