@@ -37,14 +37,20 @@ struct MsmPlan {
 VRFS_HD inline MsmPlan msm_plan(uint32_t n, uint32_t ncol, int prepared) {
   MsmPlan p; p.n = n; p.ncol = ncol; p.prepared = prepared;
   int lg = 0; while ((1u << (lg + 1)) <= n) lg++;
-  if (prepared) p.c = lg <= 8 ? 8 : lg <= 10 ? 10 : lg <= 12 ? 12 : lg <= 14 ? 14 : 16;
+  // prepared mode: all windows of a column share one bucket set, so a short top window (255 mod c bits) piles n entries onto
+  // 2^(255 mod c) buckets; the window sizes below keep that remainder at >= 5 bits (c = 12 and 14 left 3 bits: oversized
+  // buckets cost 0.2-0.6 ms at 2^11..2^14)
+  if (prepared) p.c = lg <= 9 ? 8 : lg <= 11 ? 10 : lg <= 13 ? 13 : lg <= 14 ? 15 : 16;
   else p.c = lg <= 9 ? 7 : lg <= 11 ? 9 : lg <= 13 ? 11 : lg <= 15 ? 12 : 13;
   p.windows = (255 + p.c) / p.c;          // 255 scalar bits + the top carry of the signed recoding
   p.nb = 1 << (p.c - 1);
   p.seg_windows = prepared ? 1 : p.windows;
-  p.chunk = 16;
+  // small domains are latency-bound on chains of dependent additions: spread every stage over more threads
+  // (4 buckets per thread in the segment reduction below 2^13 buckets; >= 4 entries per thread in a bucket until the grid holds ~64 K threads)
+  p.chunk = p.nb <= 8192 ? 4 : 8;
   uint64_t avg = ((uint64_t)n * (prepared ? p.windows : 1)) / p.nb;      // expected entries per bucket for uniform digits
-  p.tpb = 1; while (p.tpb < 32 && avg / p.tpb > 24) p.tpb *= 2;
+  const uint64_t total_buckets = (uint64_t)ncol * (prepared ? 1 : p.windows) * p.nb;
+  p.tpb = 1; while (p.tpb < 32 && (avg / p.tpb > 24 || (total_buckets * p.tpb < 65536 && avg / p.tpb >= 4))) p.tpb *= 2;
   p.big = (uint32_t)(8 * (avg + 8));
   return p;
 }
@@ -90,6 +96,41 @@ HD_INLINE void msm_load_scalar(uint32_t* k, const uint8_t* p) {
   uint4 a = q[0], b = q[1];
   raw[0] = a.x; raw[1] = a.y; raw[2] = a.z; raw[3] = a.w; raw[4] = b.x; raw[5] = b.y; raw[6] = b.z; raw[7] = b.w;
   from_mont<BlsFr>(k, to_mont<BlsFr>(raw));     // reduce mod r like the reference's scalar decode
+}
+
+// 1/a in BLS12-381 Fq by the binary extended Euclid (at most 2*381 shift/subtract steps on 12-limb integers) instead of a
+// Fermat power (~480 dependent 12-limb products): the final projective -> affine step of an MSM runs on ONE thread per
+// column, so its latency is the whole call's tail (0.43 ms -> 0.16 ms).  Montgomery in, Montgomery out; 0 -> 0.
+HD_INLINE void fq381_shr1(uint32_t* a) { for (int i = 0; i < 11; i++) a[i] = (a[i] >> 1) | (a[i + 1] << 31); a[11] >>= 1; }
+HD_INLINE void fq381_halve_mod(uint32_t* x, const uint32_t* p) {            // x / 2 mod p, x < p
+  uint32_t t[12];
+  if (x[0] & 1u) { MontChains<12>::add(t, x, p); for (int i = 0; i < 12; i++) x[i] = t[i]; }   // < 2^382: no carry out
+  fq381_shr1(x);
+}
+HD_NOINLINE Fq381 fq381_inv(const Fq381& a) {
+  typedef MontChains<12> C;
+  if (a.is_zero()) return a;
+  uint32_t u[12], v[12], x1[12], x2[12], p[12], t[12];
+  for (int i = 0; i < 12; i++) { u[i] = a.v[i]; p[i] = BlsFq::mod(i); v[i] = p[i]; x1[i] = i == 0; x2[i] = 0; }
+  auto is_one = [](const uint32_t* z) { uint32_t o = z[0] ^ 1u; for (int i = 1; i < 12; i++) o |= z[i]; return o == 0; };
+  for (int guard = 0; guard < 2 * 384 && !is_one(u) && !is_one(v); guard++) {
+    while (!(u[0] & 1u)) { fq381_shr1(u); fq381_halve_mod(x1, p); }
+    while (!(v[0] & 1u)) { fq381_shr1(v); fq381_halve_mod(x2, p); }
+    if (C::sub(t, u, v) == 0) {                       // u >= v
+      for (int i = 0; i < 12; i++) u[i] = t[i];
+      if (C::sub(t, x1, x2)) C::add(t, t, p);
+      for (int i = 0; i < 12; i++) x1[i] = t[i];
+    } else {
+      C::sub(t, v, u);
+      for (int i = 0; i < 12; i++) v[i] = t[i];
+      if (C::sub(t, x2, x1)) C::add(t, t, p);
+      for (int i = 0; i < 12; i++) x2[i] = t[i];
+    }
+  }
+  Fq381 x;                                            // plain inverse of the integer a*R: (aR)^-1 = a^-1 R^-1
+  const uint32_t* r = is_one(u) ? x1 : x2;
+  for (int i = 0; i < 12; i++) x.v[i] = r[i];
+  return x * Fq381::r3();                             // a^-1 R^-1 * R^3 / R = a^-1 R
 }
 
 #ifdef __CUDACC__
@@ -300,7 +341,7 @@ __global__ void k_msm_final(MsmPlan p, const G1Pt* window_sums, uint8_t* out, in
     from_mont<BlsFq>(raw, acc.Z); store_le<12>(o + 96, raw);
   } else {
     uint8_t* o = out + (size_t)96 * col;
-    Fq381 zi = inv(acc.Z);                      // identity: Z = 0 -> zi = 0 -> zeros
+    Fq381 zi = fq381_inv(acc.Z);                // identity: Z = 0 -> zi = 0 -> zeros
     from_mont<BlsFq>(raw, acc.X * zi); store_le<12>(o, raw);
     from_mont<BlsFq>(raw, acc.Y * zi); store_le<12>(o + 48, raw);
   }
@@ -321,7 +362,7 @@ __global__ void k_g1_sum_partials(int n_parts, int ncol, const uint8_t* partials
   }
   uint32_t raw[12];
   uint8_t* o = out + (size_t)96 * col;
-  Fq381 zi = inv(acc.Z);
+  Fq381 zi = fq381_inv(acc.Z);
   from_mont<BlsFq>(raw, acc.X * zi); store_le<12>(o, raw);
   from_mont<BlsFq>(raw, acc.Y * zi); store_le<12>(o + 48, raw);
 }

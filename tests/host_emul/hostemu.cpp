@@ -172,3 +172,11 @@ extern "C" int hostemu_bls_sqrt(const uint32_t* a_mont, uint32_t* out_mont) {
   memcpy(out_mont, r.v, 32);
   return ok;
 }
+
+// BLS12-381 Fq inversion by binary extended Euclid (csrc/msm.cuh), Montgomery in / Montgomery out
+#include "../../ark_ec_vrfs_b200/csrc/msm.cuh"
+extern "C" void hostemu_fq381_inv(const uint32_t* a_mont, uint32_t* out_mont) {
+  Fq381 a; memcpy(a.v, a_mont, 48);
+  Fq381 r = fq381_inv(a);
+  memcpy(out_mont, r.v, 48);
+}

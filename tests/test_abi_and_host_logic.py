@@ -133,3 +133,15 @@ def test_host_emulated_ietf_verify_matches_oracle(emu, suite):
     p = lambda a: a.ctypes.data_as(C.c_void_p)
     emu.hostemu_ietf_verify(suite, C.c_size_t(n), p(w["pk"]), p(w["inp"]), p(w["out"]), p(w["c"]), p(w["s"]), p(ad), p(off), p(got))
     assert np.array_equal(got, w["expect"]) and 0 < got.sum() < n
+
+
+def test_fq381_binary_euclid_inverse(emu):
+    """csrc/msm.cuh fq381_inv (used on the MSM's final projective -> affine step) against big-integer arithmetic"""
+    p = R.BLS_FQ; Rm = 1 << 384
+    rnd = random.Random(21)
+    for t in range(300):
+        a = [0, 1, p - 1, 2, (p + 1) // 2][t] if t < 5 else rnd.randrange(p)
+        A = (C.c_uint32 * 12)(*[((a * Rm % p) >> (32 * i)) & 0xFFFFFFFF for i in range(12)]); out = (C.c_uint32 * 12)()
+        emu.hostemu_fq381_inv(A, out)
+        got = sum(int(out[i]) << (32 * i) for i in range(12))
+        assert got == (pow(a, -1, p) * Rm % p if a else 0), a
