@@ -62,6 +62,11 @@ template <class T> HD_INLINE void copy_words16(T* dst, const T* src_) {  // size
 }
 
 // ---- group adapters ---------------------------------------------------------------------------
+// Fixed-base window width.  16-bit signed windows halve the additions of every fixed-base multiplication (16 instead of 32) at
+// the price of a 50 MB table per base (L2/DRAM-resident, prefetched); 8-bit windows keep the tables at 400 KB.
+#ifndef VRFS_FIX_BITS
+#define VRFS_FIX_BITS 16
+#endif
 template <class C, bool TE = C::IS_TE> struct Grp;
 template <class C> struct Grp<C, true> {
   typedef TEPoint<C> Pt;
@@ -70,7 +75,7 @@ template <class C> struct Grp<C, true> {
   static constexpr int SPLIT = C::HAS_GLV ? 2 : 1;          // tables per variable base
   static constexpr int WINDOWS = C::HAS_GLV ? 32 : 64;      // radix-16 windows per (half-)scalar
   static constexpr int KB_LIMBS = C::HAS_GLV ? 4 : 8;
-  static constexpr int FIX_WINDOWS = 32;
+  static constexpr int FIX_WINDOWS = 256 / VRFS_FIX_BITS;
   static HD_INLINE void set_identity(Pt& P) { te_set_identity(P); }
   static HD_INLINE void from_affine(Pt& P, const typename C::F& x, const typename C::F& y) { te_from_affine<C>(P, x, y); }
   static HD_INLINE bool on_curve(const typename C::F& x, const typename C::F& y) { return te_on_curve<C>(x, y); }
@@ -97,7 +102,7 @@ template <> struct Grp<BandCurve, true> {
   typedef TE29Point Pt;
   typedef TE29Cached Entry;
   typedef TE29AffCached FixEntry;
-  static constexpr int SPLIT = 2, WINDOWS = 32, KB_LIMBS = 4, FIX_WINDOWS = 32;
+  static constexpr int SPLIT = 2, WINDOWS = 32, KB_LIMBS = 4, FIX_WINDOWS = 256 / VRFS_FIX_BITS;
   static HD_INLINE void set_identity(Pt& P) { te29_set_identity(P); }
   static HD_INLINE void from_affine(Pt& P, const C::F& x, const C::F& y) { P.X = f29_from_fp(x); P.Y = f29_from_fp(y); P.Z = f29_one(); P.T = f29_mul(P.X, P.Y); }
   static HD_INLINE bool on_curve(const C::F& x, const C::F& y) { return te_on_curve<C>(x, y); }
@@ -123,7 +128,7 @@ template <class C> struct Grp<C, false> {
   static constexpr int SPLIT = 1;
   static constexpr int WINDOWS = 65;       // 64 radix-16 digits + the carry of the bias addition (n ~ 2^256)
   static constexpr int KB_LIMBS = 9;
-  static constexpr int FIX_WINDOWS = 33;
+  static constexpr int FIX_WINDOWS = 256 / VRFS_FIX_BITS + 1;   // + the carry of the bias addition (n ~ 2^256)
   static HD_INLINE void set_identity(Pt& P) { sw_set_identity(P); }
   static HD_INLINE void from_affine(Pt& P, const typename C::F& x, const typename C::F& y) { sw_from_affine<C>(P, x, y); }
   static HD_INLINE bool on_curve(const typename C::F& x, const typename C::F& y) { return sw_on_curve<C>(x, y); }
@@ -141,7 +146,7 @@ template <class C> struct Grp<C, false> {
   static HD_INLINE void store_xyz(uint32_t* o, const Pt& P) { store_fp_xyz(o, P.X, P.Y, P.Z); }
 };
 static constexpr int TBL_ENTRIES = 9;     // 0*P .. 8*P
-static constexpr int FIX_ENTRIES = 129;   // 0 .. 128 times 256^w * B
+static constexpr int FIX_ENTRIES = (1 << (VRFS_FIX_BITS - 1)) + 1;   // 0 .. 2^(b-1) times 2^(b w) * B
 // bytes of per-thread table slab for NV variable bases
 template <class C> VRFS_HD constexpr size_t slab_bytes(int nv) { return (size_t)nv * Grp<C>::SPLIT * TBL_ENTRIES * sizeof(typename Grp<C>::Entry); }
 template <class C> VRFS_HD constexpr size_t fix_table_entries() { return (size_t)Grp<C>::FIX_WINDOWS * FIX_ENTRIES; }
@@ -267,19 +272,26 @@ HD_INLINE bool lincomb_item(const LincombArgs& A, uint32_t item, typename Grp<C>
     uint32_t k[9];
     load_scalar_mod_r<C>(k, A.fix[f].sc + (size_t)item * A.fix[f].sc_stride);
     k[8] = 0;
-    add_window_bias<9>(k, 0x80808080u, 8);
+    add_window_bias<9>(k, VRFS_FIX_BITS == 16 ? 0x80008000u : 0x80808080u, 8);
     const typename G::FixEntry* tbl = reinterpret_cast<const typename G::FixEntry*>(A.fix[f].table);
     bool neg = A.fix[f].negate != 0;
+    constexpr int TOPW = 256 / VRFS_FIX_BITS;     // index of the carry window (short-Weierstrass suites only)
+    auto digit = [&](int w) { return w == TOPW ? (int)k[8] : (VRFS_FIX_BITS == 16 ? digit16(k, w) : digit8(k, w)); };
+    if (VRFS_FIX_BITS == 16) {                    // the table is far larger than L1: start every window's record on its way to L2 now
+#pragma unroll 1
+      for (int w = 2; w < G::FIX_WINDOWS; w++) { int dn = digit(w); prefetch_l2(&tbl[(size_t)w * FIX_ENTRIES + (dn < 0 ? -dn : dn)], sizeof(typename G::FixEntry)); }
+      { int dn = digit(0); prefetch_l1(&tbl[(dn < 0 ? -dn : dn)], sizeof(typename G::FixEntry)); }
+    }
 #pragma unroll 1
     for (int w = 0; w < G::FIX_WINDOWS; w++) {
       if (w + 1 < G::FIX_WINDOWS) {   // next window's entry -> L1 while this addition runs
-        int dn = w + 1 == 32 ? (int)k[8] : digit8(k, w + 1);
-        prefetch_l1(&tbl[(w + 1) * FIX_ENTRIES + (dn < 0 ? -dn : dn)], sizeof(typename G::FixEntry));
+        int dn = digit(w + 1);
+        prefetch_l1(&tbl[(size_t)(w + 1) * FIX_ENTRIES + (dn < 0 ? -dn : dn)], sizeof(typename G::FixEntry));
       }
-      int d = w == 32 ? (int)k[8] : digit8(k, w);
+      int d = digit(w);
       int idx = d < 0 ? -d : d;
       typename G::FixEntry e;
-      copy_words16(&e, &tbl[w * FIX_ENTRIES + idx]);
+      copy_words16(&e, &tbl[(size_t)w * FIX_ENTRIES + idx]);
       G::add_fix(&acc, &e, (d < 0) != neg);
     }
   }
@@ -291,9 +303,9 @@ template <class C>
 HD_INLINE void fixed_table_entry(typename Grp<C>::FixEntry& out, const typename C::F& bx, const typename C::F& by, int w, int d) {
   typedef Grp<C> G;
   typename G::Pt P, R; G::from_affine(P, bx, by);
-  for (int i = 0; i < 8 * w; i++) G::dbl(&P);
+  for (int i = 0; i < VRFS_FIX_BITS * w; i++) G::dbl(&P);
   G::set_identity(R);
-  for (int bit = 7; bit >= 0; bit--) {
+  for (int bit = VRFS_FIX_BITS - 1; bit >= 0; bit--) {
     G::dbl(&R);
     if ((d >> bit) & 1) G::add(&R, &R, &P);
   }

@@ -82,5 +82,6 @@ template <int N> HD_INLINE void add_window_bias(uint32_t* k, uint32_t pattern, i
 }
 HD_INLINE int digit4(const uint32_t* kb, int w) { return (int)((kb[w >> 3] >> ((w & 7) * 4)) & 15u) - 8; }
 HD_INLINE int digit8(const uint32_t* kb, int w) { return (int)((kb[w >> 2] >> ((w & 3) * 8)) & 255u) - 128; }
+HD_INLINE int digit16(const uint32_t* kb, int w) { return (int)((kb[w >> 1] >> ((w & 1) * 16)) & 65535u) - 32768; }
 
 }  // namespace vrfs

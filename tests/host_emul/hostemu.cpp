@@ -46,8 +46,8 @@ template <class C> static const typename Grp<C>::FixEntry* fixed_table(bool blin
   auto& t = tabs[blinding];
   if (t.empty()) {
     t.resize(fix_table_entries<C>());
-    for (int w = 0; w < Grp<C>::FIX_WINDOWS; w++) for (int d = 0; d <= 128; d++)
-      fixed_table_entry<C>(t[w * 129 + d], blinding ? C::bx() : C::gx(), blinding ? C::by() : C::gy(), w, d);
+    for (int w = 0; w < Grp<C>::FIX_WINDOWS; w++) for (int d = 0; d < FIX_ENTRIES; d++)
+      fixed_table_entry<C>(t[(size_t)w * FIX_ENTRIES + d], blinding ? C::bx() : C::gx(), blinding ? C::by() : C::gy(), w, d);
   }
   return t.data();
 }
