@@ -432,6 +432,48 @@ HD_INLINE bool is_square(const Fp<P>& a) {
   return pow_const<P, ExpPM1H>(a) == Fp<P>::one();
 }
 
+// Jacobi symbol (a/p) of a field element by the binary algorithm (shift / compare / subtract on 8-limb integers, no
+// multiplier): 1, -1, or 0 for a = 0.  Works on the stored representation directly: the Montgomery factor 2^(32N) is a
+// square, so (aR/p) = (a/p).  ~20 K ALU instructions against ~110 K for an Euler-criterion power; the loop trip count is
+// data dependent (lanes of a warp finish within a few per cent of each other).
+template <class P>
+HD_NOINLINE int jacobi(const Fp<P>& x) {
+  constexpr int N = P::N;
+  typedef MontChains<N> C;
+  uint32_t a[N], n[N], t[N];
+  for (int i = 0; i < N; i++) { a[i] = x.v[i]; n[i] = P::mod(i); }
+  int sign = 1;
+  for (int guard = 0; guard < 64 * N + 8; guard++) {
+    uint32_t any = 0;
+    for (int i = 0; i < N; i++) any |= a[i];
+    if (!any) break;
+    // strip the factors of two: (2/n) = -1 iff n = 3, 5 (mod 8)
+    while (a[0] == 0) { for (int i = 0; i + 1 < N; i++) a[i] = a[i + 1]; a[N - 1] = 0; }      // 32 = even number of halvings
+#if defined(__CUDA_ARCH__)
+    const int tz = __ffs((int)a[0]) - 1;
+#else
+    const int tz = __builtin_ctz(a[0]);
+#endif
+    if (tz) {
+      for (int i = 0; i + 1 < N; i++) a[i] = (a[i] >> tz) | (a[i + 1] << (32 - tz));
+      a[N - 1] >>= tz;
+      const uint32_t n8 = n[0] & 7u;
+      if ((tz & 1) && (n8 == 3u || n8 == 5u)) sign = -sign;
+    }
+    // both odd now: make a >= n (quadratic reciprocity), then a -= n
+    if (C::sub(t, a, n)) {                               // a < n: swap roles, t = n - a
+      if ((a[0] & 3u) == 3u && (n[0] & 3u) == 3u) sign = -sign;
+      C::sub(t, n, a);
+      for (int i = 0; i < N; i++) { n[i] = a[i]; a[i] = t[i]; }
+    } else {
+      for (int i = 0; i < N; i++) a[i] = t[i];
+    }
+  }
+  uint32_t rest = n[0] ^ 1u;
+  for (int i = 1; i < N; i++) rest |= n[i];
+  return rest == 0 ? sign : 0;
+}
+
 // canonical value > (p-1)/2 ?   (arkworks TE "x is negative" flag)
 template <class P>
 HD_INLINE bool is_high(const Fp<P>& a) {

@@ -20,6 +20,7 @@ template <class P> static void field_op(int op, const uint32_t* a, const uint32_
     case 7: r = Fp<P>::zero(); r.v[0] = is_square(x); break;
     case 8: r = Fp<P>::zero(); r.v[0] = is_high(x) | (is_odd(x) << 1); break;
     case 9: r = sqr(x); break;                      // dedicated squaring path (SOS reduction)
+    case 10: r = Fp<P>::zero(); r.v[0] = (uint32_t)(jacobi(x) + 1); break;   // Jacobi symbol + 1
     default: r = Fp<P>::zero();
   }
   memcpy(out, r.v, 4 * P::N);

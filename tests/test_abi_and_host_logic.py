@@ -94,6 +94,10 @@ def test_montgomery_field_arithmetic(emu, fi):
         assert _fop(emu, fi, 5, a * Rm % p, 0, n) == pow(a, -1, p) * Rm % p
         assert _fop(emu, fi, 7, a * Rm % p, 0, n) == (1 if R.legendre(a, p) == 1 else 0)
         assert _fop(emu, fi, 8, a * Rm % p, 0, n) == (1 if a > (p - 1) // 2 else 0) | ((a & 1) << 1)
+    if n == 8 and p < (1 << 255):                       # binary Jacobi symbol (arith.cuh jacobi): subgroup checks use it on BLS12-381 Fr
+        for t in range(300):
+            a = [0, 1, p - 1, 2, 4][t] if t < 5 else (rnd.randrange(p) if t % 3 else rnd.randrange(1 << (8 * (t % 31) + 1)))
+            assert _fop(emu, fi, 10, a * Rm % p, 0, n) == {1: 2, -1: 0, 0: 1}[R.legendre(a, p)], a
 
 
 def test_glv_split_and_lincomb(emu):
