@@ -79,6 +79,48 @@ HD_NOINLINE void g1_dbl(G1Pt* r, const G1Pt* p) {
   X3 = dbl(t0 * (p->X * p->Y));
   r->X = X3; r->Y = Y3; r->Z = Z3;
 }
+// ---- bucket accumulation in XYZZ coordinates (x = X/ZZ, y = Y/ZZZ; ZZ = 0 is the identity) with AFFINE table records:
+// madd-2008-s costs 8M + 2S and ~7 field additions, against 12M and ~20 additions for the complete homogeneous formula.
+// The formula is not complete, so the three exceptional cases are tested explicitly (they only occur for an empty
+// accumulator, repeated bases and cancelling pairs - a warp almost never diverges on them).
+struct G1Xyzz { Fq381 X, Y, ZZ, ZZZ; };
+HD_INLINE void xyzz_set_identity(G1Xyzz& a) { a.X = Fq381::zero(); a.Y = Fq381::zero(); a.ZZ = Fq381::zero(); a.ZZZ = Fq381::zero(); }
+HD_NOINLINE void xyzz_madd(G1Xyzz* acc, const Fq381* x2, const Fq381* y2) {
+  if (acc->ZZ.is_zero()) { acc->X = *x2; acc->Y = *y2; acc->ZZ = Fq381::one(); acc->ZZZ = Fq381::one(); return; }
+  Fq381 U2 = *x2 * acc->ZZ, S2 = *y2 * acc->ZZZ;
+  Fq381 P = U2 - acc->X, R = S2 - acc->Y;
+  if (P.is_zero()) {
+    if (R.is_zero()) {                       // same point: affine doubling (mdbl-2008-s-1)
+      Fq381 U = dbl(*y2), V = sqr(U), W = U * V, S = *x2 * V, xx = sqr(*x2), M = dbl(xx) + xx;
+      Fq381 X3 = sqr(M) - dbl(S);
+      acc->Y = M * (S - X3) - W * *y2; acc->X = X3; acc->ZZ = V; acc->ZZZ = W;
+    } else {
+      xyzz_set_identity(*acc);               // P + (-P)
+    }
+    return;
+  }
+  Fq381 PP = sqr(P), PPP = P * PP, Q = acc->X * PP;
+  Fq381 X3 = sqr(R) - PPP - dbl(Q);
+  acc->Y = R * (Q - X3) - acc->Y * PPP;
+  acc->X = X3;
+  acc->ZZ = acc->ZZ * PP;
+  acc->ZZZ = acc->ZZZ * PPP;
+}
+// -> homogeneous projective (X ZZZ : Y ZZ : ZZ ZZZ); identity -> (0 : 1 : 0)
+HD_INLINE void xyzz_to_proj(G1Pt& r, const G1Xyzz& a) {
+  bool inf = a.ZZ.is_zero();
+  r.X = a.X * a.ZZZ;
+  r.Y = select(inf, Fq381::one(), a.Y * a.ZZ);
+  r.Z = a.ZZ * a.ZZZ;
+}
+// affine record (identity = all zero) -> (x, +-y); false for the identity
+HD_INLINE bool g1_load_aff_xy(Fq381& x, Fq381& y, const G1Aff* a, bool negate) {
+  G1Aff t;
+  copy_words16(&t, a);
+  x = t.x; y = cneg(t.y, negate);
+  return !(t.x.is_zero() & t.y.is_zero());
+}
+
 // signed radix-2^c digit w of the canonical scalar k (8 limbs): digits in [-2^(c-1), 2^(c-1)]
 HD_INLINE int msm_digit(const uint32_t* k, int w, int c, int& carry) {
   int bit = w * c;
@@ -145,16 +187,34 @@ __global__ void __launch_bounds__(128) k_msm_prep_bases(uint32_t n, const uint8_
   o.x = to_mont<BlsFq>(rx); o.y = to_mont<BlsFq>(ry);
   out[i] = o;
 }
-// prepared bases (the RingContext analogue: the SRS is fixed): Q[w*n + i] = 2^(c*w) * P_i, projective
-__global__ void __launch_bounds__(128) k_msm_prepare(uint32_t n, int c, int windows, const G1Aff* aff, G1Pt* Q) {
+// prepared bases (the RingContext analogue: the SRS is fixed): Q[w*n + i] = 2^(c*w) * P_i, AFFINE (96 B; identity = zeros).
+// One thread per base: the doubling chain leaves projective points, whose Z's are inverted together (Montgomery's trick, one
+// binary-Euclid inversion per base).
+#define MSM_MAX_WINDOWS 33
+__global__ void __launch_bounds__(128) k_msm_prepare(uint32_t n, int c, int windows, const G1Aff* aff, G1Aff* Q) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   G1Pt P;
   g1_load_aff(P, &aff[i], false);
-  copy_words16(&Q[i], &P);
-  for (int w = 1; w < windows; w++) {
-    for (int k = 0; k < c; k++) g1_dbl(&P, &P);
-    copy_words16(&Q[(size_t)w * n + i], &P);
+  Fq381 zs[MSM_MAX_WINDOWS], pre[MSM_MAX_WINDOWS];
+  unsigned long long infmask = 0;                                // windows whose point is the identity (Z = 0)
+  for (int w = 0; w < windows; w++) {
+    if (w) for (int k = 0; k < c; k++) g1_dbl(&P, &P);
+    G1Aff t; t.x = P.X; t.y = P.Y;                               // unnormalised for now
+    copy_words16(&Q[(size_t)w * n + i], &t);
+    const bool inf = P.Z.is_zero();
+    if (inf) infmask |= 1ull << w;
+    zs[w] = select(inf, Fq381::one(), P.Z);                      // an identity must not poison the product chain
+    pre[w] = w ? pre[w - 1] * zs[w] : zs[w];
+  }
+  Fq381 acc = fq381_inv(pre[windows - 1]);
+  for (int w = windows - 1; w >= 0; w--) {
+    Fq381 zi = w ? acc * pre[w - 1] : acc;
+    if (w) acc = acc * zs[w];
+    G1Aff t; copy_words16(&t, &Q[(size_t)w * n + i]);
+    t.x = t.x * zi; t.y = t.y * zi;
+    if ((infmask >> w) & 1ull) { t.x = Fq381::zero(); t.y = Fq381::zero(); }
+    copy_words16(&Q[(size_t)w * n + i], &t);
   }
 }
 // counts[seg*nb + (|d|-1)]++ ; seg = col*seg_windows + (prepared ? 0 : w)
@@ -210,9 +270,18 @@ __global__ void __launch_bounds__(128) k_msm_scatter(MsmPlan p, const uint8_t* s
     list[seg * seg_len + offsets[b] + pos] = idx | (d < 0 ? 0x80000000u : 0u);
   }
 }
-template <bool PREP> __device__ __forceinline__ void msm_load_entry(G1Pt& q, const void* bases, uint32_t e) {
-  if (PREP) g1_load_proj(q, reinterpret_cast<const G1Pt*>(bases) + (e & 0x7fffffffu), (e >> 31) != 0);
-  else g1_load_aff(q, reinterpret_cast<const G1Aff*>(bases) + (e & 0x7fffffffu), (e >> 31) != 0);
+// every table record is affine: the caller's bases (stateless) or the prepared 2^(c w) P_i
+__device__ __forceinline__ void msm_accumulate_entries(G1Pt& out, const void* bases, const uint32_t* l, uint32_t first, uint32_t cnt, uint32_t step) {
+  const G1Aff* tab = reinterpret_cast<const G1Aff*>(bases);
+  G1Xyzz acc; xyzz_set_identity(acc);
+  for (uint32_t j = first; j < cnt; j += step) {
+    const uint32_t e = l[j];
+    Fq381 x, y;
+    const bool finite = g1_load_aff_xy(x, y, tab + (e & 0x7fffffffu), (e >> 31) != 0);
+    if (j + step < cnt) prefetch_l1(tab + (l[j + step] & 0x7fffffffu), (unsigned)sizeof(G1Aff));   // a random 96-byte record of a table far larger than L2
+    if (finite) xyzz_madd(&acc, &x, &y);
+  }
+  xyzz_to_proj(out, acc);
 }
 // p.tpb threads per bucket (strided over its entries, shared-memory tree inside the group); buckets above p.big
 // entries are left to k_msm_accumulate_big
@@ -235,16 +304,7 @@ __global__ void __launch_bounds__(128, MSM_ACC_MINBLOCKS) k_msm_accumulate(MsmPl
     const size_t seg = b / p.nb;
     const size_t seg_len = (size_t)p.n * (p.prepared ? p.windows : 1);
     const uint32_t* l = list + seg * seg_len + offsets[b];
-    for (uint32_t j = lane; j < cnt; j += p.tpb) {
-      G1Pt q;
-      msm_load_entry<PREP>(q, bases, l[j]);
-      if (j + p.tpb < cnt) {     // the next entry is a random 96/144-byte record of a table far larger than L2: start its fetch now
-        const uint32_t e = l[j + p.tpb] & 0x7fffffffu;
-        prefetch_l1(PREP ? (const void*)(reinterpret_cast<const G1Pt*>(bases) + e) : (const void*)(reinterpret_cast<const G1Aff*>(bases) + e),
-                    PREP ? (unsigned)sizeof(G1Pt) : (unsigned)sizeof(G1Aff));
-      }
-      sw_add<G1Curve>(&acc, &acc, &q);
-    }
+    msm_accumulate_entries(acc, bases, l, lane, cnt, (uint32_t)p.tpb);
   }
   if (p.tpb > 1) {
     copy_words16(&sh[threadIdx.x], &acc);
@@ -269,12 +329,8 @@ __global__ void __launch_bounds__(MSM_BIG_THREADS) k_msm_accumulate_big(MsmPlan 
     const size_t seg_len = (size_t)p.n * (p.prepared ? p.windows : 1);
     const uint32_t* l = list + seg * seg_len + offsets[b];
     const uint32_t cnt = counts[b];
-    G1Pt acc; sw_set_identity(acc);
-    for (uint32_t j = threadIdx.x; j < cnt; j += MSM_BIG_THREADS) {
-      G1Pt q;
-      msm_load_entry<PREP>(q, bases, l[j]);
-      sw_add<G1Curve>(&acc, &acc, &q);
-    }
+    G1Pt acc;
+    msm_accumulate_entries(acc, bases, l, threadIdx.x, cnt, MSM_BIG_THREADS);
     copy_words16(&sh[threadIdx.x], &acc);
     __syncthreads();
     for (int stride = MSM_BIG_THREADS >> 1; stride > 0; stride >>= 1) {

@@ -1261,7 +1261,7 @@ struct vrfs_msm_bases {
   vrfs_ctx* ctx;
   size_t n;
   MsmPlan plan;
-  void* Q;          // windows * n projective points
+  void* Q;          // windows * n affine points (96 B each; identity = zeros)
 };
 // bases: G1Aff[n] (stateless) or the prepared table Q; scalars on the device
 static vrfs_status msm_dev(vrfs_ctx* ctx, MsmPlan p, const void* d_bases, const uint8_t* d_scalars, uint8_t* d_out, int out_mode) {
@@ -1341,7 +1341,7 @@ extern "C" vrfs_status vrfs_msm_g1_prepare(vrfs_ctx* ctx, size_t n, const uint8_
   vrfs_msm_bases* h = new (std::nothrow) vrfs_msm_bases();
   if (!h) return fail(ctx, VRFS_CUDA_ERROR, "out of host memory");
   h->ctx = ctx; h->n = n; h->plan = msm_plan((uint32_t)n, 1, 1); h->Q = nullptr;
-  cudaError_t e = cudaMalloc(&h->Q, (size_t)h->plan.windows * n * sizeof(G1Pt));
+  cudaError_t e = cudaMalloc(&h->Q, (size_t)h->plan.windows * n * sizeof(G1Aff));
   if (e != cudaSuccess) { delete h; return fail(ctx, VRFS_CUDA_ERROR, "cudaMalloc of the prepared table failed: %s", cudaGetErrorString(e)); }
   *out = h;
   const uint8_t* d_b; void* bases_m = nullptr;
@@ -1349,7 +1349,7 @@ extern "C" vrfs_status vrfs_msm_g1_prepare(vrfs_ctx* ctx, size_t n, const uint8_
   ST(ensure(ctx, BUF_W0, n * sizeof(G1Aff), &bases_m));
   k_msm_prep_bases<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((uint32_t)n, d_b, (G1Aff*)bases_m);
   LAUNCHED_AS(ctx, "msm_prep_bases");
-  k_msm_prepare<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((uint32_t)n, h->plan.c, h->plan.windows, (const G1Aff*)bases_m, (G1Pt*)h->Q);
+  k_msm_prepare<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((uint32_t)n, h->plan.c, h->plan.windows, (const G1Aff*)bases_m, (G1Aff*)h->Q);
   LAUNCHED_AS(ctx, "msm_prepare");
   return finish_call(ctx);
 }

@@ -53,6 +53,34 @@ def test_msm_edge_cases(eng):
     assert np.array_equal(eng.msm_g1(np.zeros((0, 96), np.uint8), np.zeros((0, 32), np.uint8), 1), np.zeros((1, 96), np.uint8))
 
 
+def test_msm_exceptional_additions_inside_a_bucket(eng):
+    """the bucket accumulator uses incomplete XYZZ mixed additions: P + P, P + (-P) and 0 + P inside one bucket must be
+    caught (repeated bases, negated bases and identity bases with equal scalars), stateless and prepared, all bucket widths"""
+    P_MOD = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
+    for n in (8, 300, 3000):
+        bases, sc = synth(n, 2, b"exc")
+        neg = bases.copy()
+        for i in range(n):
+            y = int.from_bytes(bases[i, 48:].tobytes(), "little")
+            neg[i, 48:] = np.frombuffer(((P_MOD - y) % P_MOD).to_bytes(48, "little"), np.uint8)
+        b = bases.copy()
+        b[1] = b[0]; b[2] = b[0]; b[3] = neg[0]                     # P, P, P, -P
+        b[5] = 0                                                     # identity base
+        b[n - 1] = neg[n - 2]                                        # a cancelling pair
+        s = sc.copy()
+        for col in range(2):
+            s[col * n + 1] = s[col * n]; s[col * n + 2] = s[col * n]; s[col * n + 3] = s[col * n]     # same digits -> same buckets
+            s[col * n + n - 1] = s[col * n + n - 2]
+        exp = O.msm_g1(b, s, 2)
+        assert np.array_equal(eng.msm_g1(b, s, 2), exp)
+        h = eng.msm_g1_prepare(b)
+        assert np.array_equal(h.msm(s, 2), exp)
+        h.release()
+        # everything cancels: the sum of k*P and k*(-P) over all bases is the identity
+        bb = np.concatenate([bases, neg]); ss = np.concatenate([sc[:n], sc[:n]])
+        assert not eng.msm_g1(bb, ss, 1).any()
+
+
 def test_msm_regression_golden(eng):
     """tests/golden/msm_g1_regression.json: big-endian hex x||y computed by the independent Python model"""
     with open(os.path.join(GOLDEN, "msm_g1_regression.json")) as f:
