@@ -174,3 +174,38 @@ def test_wire_edge_cases(eng):
         eng.ietf_sign_wire(s, sk, bad_off)
     with pytest.raises(vrfs.VrfsError):
         eng.ietf_verify_wire(s, O.point_encode(s, pk), bad_off, sig)
+
+
+def test_full_size_roundtrips(eng):
+    """BASELINE-size batches (2^20 IETF, 2^18 Pedersen) through size-independent properties: everything the signer produces
+    verifies, a flipped byte flips exactly that verdict, and a strided sample agrees with the oracle bit for bit."""
+    s = O.BANDERSNATCH
+    n = 1 << 20
+    sk256, pk256 = eng.secret_from_seed(s, [b"full-%d" % i for i in range(256)])
+    sk = np.tile(sk256, (n // 256, 1)); pk_enc = np.tile(eng.point_encode(s, pk256), (n // 256, 1))
+    datas = (np.arange(n, dtype=np.uint64).view(np.uint8).copy(), np.arange(n + 1, dtype=np.uint64) * 8)
+    sig, ok = eng.ietf_sign_wire(s, sk, datas)
+    assert ok.all()
+    flip = np.zeros(n, bool); flip[5::4099] = True
+    sig = sig.copy(); sig[flip, 33] ^= 0x40
+    okv, beta = eng.ietf_verify_wire(s, pk_enc, datas, sig)
+    assert np.array_equal(okv == 1, ~flip) and not beta[flip].any()
+    sub = np.arange(0, n, 16411)
+    sub_datas = [int(i).to_bytes(8, "little") for i in sub]
+    so, _ = O.ietf_sign_wire(s, sk[sub], sub_datas)
+    good = ~flip[sub]
+    assert np.array_equal(so[good], sig[sub][good])
+    ok_o, beta_o = O.ietf_verify_wire(s, pk_enc[sub], sub_datas, sig[sub])
+    assert np.array_equal(ok_o, okv[sub]) and np.array_equal(beta_o, beta[sub])
+    # Pedersen, 2^18
+    m = 1 << 18
+    datas_m = (datas[0][:8 * m], datas[1][:m + 1])
+    psig, bl, pok = eng.pedersen_sign_wire(s, sk[:m], datas_m)
+    assert pok.all()
+    pflip = np.zeros(m, bool); pflip[3::1031] = True
+    psig = psig.copy(); psig[pflip, 170] ^= 0x02
+    assert np.array_equal(eng.pedersen_verify_wire(s, datas_m, psig) == 1, ~pflip)
+    subm = np.arange(0, m, 8209)
+    po, bo, _ = O.pedersen_sign_wire(s, sk[subm], [int(i).to_bytes(8, "little") for i in subm])
+    gm = ~pflip[subm]
+    assert np.array_equal(po[gm], psig[subm][gm]) and np.array_equal(bo, bl[subm])
