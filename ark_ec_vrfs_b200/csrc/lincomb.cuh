@@ -151,7 +151,9 @@ static constexpr int FIX_ENTRIES = (1 << (VRFS_FIX_BITS - 1)) + 1;   // 0 .. 2^(
 template <class C> VRFS_HD constexpr size_t slab_bytes(int nv) { return (size_t)nv * Grp<C>::SPLIT * TBL_ENTRIES * sizeof(typename Grp<C>::Entry); }
 template <class C> VRFS_HD constexpr size_t fix_table_entries() { return (size_t)Grp<C>::FIX_WINDOWS * FIX_ENTRIES; }
 
-struct VarTerm { const uint8_t* pts; uint32_t pt_stride; const uint8_t* sc; uint32_t sc_stride; uint32_t negate; };
+// sc_bits: an upper bound on the scalars' bit length when the caller has one (a challenge of CHALLENGE_LEN = 16 bytes is < 2^128:
+// half of the windows of c*Y and c*O are empty), 0 = full width.  Only used by the suites without GLV.
+struct VarTerm { const uint8_t* pts; uint32_t pt_stride; const uint8_t* sc; uint32_t sc_stride; uint32_t negate; uint32_t sc_bits; };
 struct FixTerm { const uint8_t* sc; uint32_t sc_stride; uint32_t negate; const void* table; };
 struct LincombArgs {
   uint32_t n;
@@ -241,8 +243,16 @@ HD_INLINE bool lincomb_item(const LincombArgs& A, uint32_t item, typename Grp<C>
       }
     }
     for (int t = 0; t < NT; t++) add_window_bias<G::KB_LIMBS>(kb[t], 0x88888888u, G::KB_LIMBS > 8 ? 8 : G::KB_LIMBS);
+    // highest window that can hold a non-zero digit, per table (+1: the bias addition may carry one window up); warp-uniform
+    int topw[NT > 0 ? NT : 1], wstart = 0;
+#pragma unroll
+    for (int t = 0; t < NT; t++) {
+      const uint32_t bits = G::SPLIT == 1 ? A.var[t].sc_bits : 0u;
+      topw[t] = (bits != 0 && (int)(bits / 4 + 1) < G::WINDOWS - 1) ? (int)(bits / 4 + 1) : G::WINDOWS - 1;
+      wstart = topw[t] > wstart ? topw[t] : wstart;
+    }
 #pragma unroll 1
-    for (int w = G::WINDOWS - 1; w >= 0; w--) {
+    for (int w = wstart; w >= 0; w--) {
       // the table entries of this window do not depend on acc: pull them into L1 while the four doublings run
       // (the slab is L2/DRAM-resident; without this the loads below stall ~7 % of the kernel's issue slots)
 #pragma unroll
@@ -256,9 +266,10 @@ HD_INLINE bool lincomb_item(const LincombArgs& A, uint32_t item, typename Grp<C>
         }
 #endif
       }
-      if (w != G::WINDOWS - 1) G::dbl4(&acc);
+      if (w != wstart) G::dbl4(&acc);
 #pragma unroll
       for (int t = 0; t < NT; t++) {
+        if (w > topw[t]) continue;
         int d = (G::KB_LIMBS > 8 && w == 64) ? (int)kb[t][8] : digit4(kb[t], w);   // the top digit is the bias carry, unbiased
         int idx = d < 0 ? -d : d;
         typename G::Entry e;

@@ -382,13 +382,14 @@ static vrfs_status ietf_verify_dev(vrfs_ctx* ctx, size_t n, const uint8_t* pk, c
   A.n = (uint32_t)n;
   A.valid = (uint8_t*)valid;
   // U = s*G - c*Y
-  A.var[0] = {pk, 64, c, 32, 1};
+  const uint32_t cbits = S::CLEN < 32 ? 8u * S::CLEN : 0u;     // a CHALLENGE_LEN-byte challenge: half of its windows are empty
+  A.var[0] = {pk, 64, c, 32, 1, cbits};
   A.fix[0] = {s, 32, 0, ctx->fixtab[S::ID][0]};
   A.out_xyz = (uint32_t*)u;
   ST((launch_lincomb<C, 1, 1>(ctx, A)));
   // V = s*I - c*O
-  A.var[0] = {input, 64, s, 32, 0};
-  A.var[1] = {output, 64, c, 32, 1};
+  A.var[0] = {input, 64, s, 32, 0, 0};
+  A.var[1] = {output, 64, c, 32, 1, cbits};
   A.out_xyz = (uint32_t*)v;
   ST((launch_lincomb<C, 2, 0>(ctx, A)));
   k_ietf_verify_finish<S><<<(unsigned)((n + 128 * FINISH_K - 1) / (128 * FINISH_K)), 128, 0, ctx->stream>>>((uint32_t)n, pk, input, output, c, (const uint32_t*)u,
@@ -947,10 +948,11 @@ static vrfs_status pedersen_verify_dev(vrfs_ctx* ctx, size_t n, const uint8_t* i
   LincombArgs A = {};
   A.n = (uint32_t)n; A.valid = valid;
   // T1 = s*I - c*O
-  A.var[0] = {input, 64, proof + 192, 256, 0}; A.var[1] = {output, 64, (const uint8_t*)c, 32, 1}; A.out_xyz = (uint32_t*)t1;
+  const uint32_t cbits = S::CLEN < 32 ? 8u * S::CLEN : 0u;
+  A.var[0] = {input, 64, proof + 192, 256, 0, 0}; A.var[1] = {output, 64, (const uint8_t*)c, 32, 1, cbits}; A.out_xyz = (uint32_t*)t1;
   ST((launch_lincomb<C, 2, 0>(ctx, A)));
   // T2 = s*G + sb*B - c*Yb
-  A.var[0] = {proof, 256, (const uint8_t*)c, 32, 1};
+  A.var[0] = {proof, 256, (const uint8_t*)c, 32, 1, cbits};
   A.fix[0] = {proof + 192, 256, 0, fixtab<S>(ctx, 0)}; A.fix[1] = {proof + 224, 256, 0, fixtab<S>(ctx, 1)}; A.out_xyz = (uint32_t*)t2;
   ST((launch_lincomb<C, 1, 2>(ctx, A)));
   k_pedersen_verify_finish<C><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, proof, (const uint32_t*)t1, (const uint32_t*)t2, valid, out_ok);
