@@ -137,7 +137,8 @@ HD_INLINE void msm_load_scalar(uint32_t* k, const uint8_t* p) {
   const uint4* q = reinterpret_cast<const uint4*>(p);
   uint4 a = q[0], b = q[1];
   raw[0] = a.x; raw[1] = a.y; raw[2] = a.z; raw[3] = a.w; raw[4] = b.x; raw[5] = b.y; raw[6] = b.z; raw[7] = b.w;
-  from_mont<BlsFr>(k, to_mont<BlsFr>(raw));     // reduce mod r like the reference's scalar decode
+  if (is_canonical<BlsFr>(raw)) { for (int i = 0; i < 8; i++) k[i] = raw[i]; }      // the common case: nothing to reduce
+  else from_mont<BlsFr>(k, to_mont<BlsFr>(raw));  // reduce mod r like the reference's scalar decode
 }
 
 // 1/a in BLS12-381 Fq by the binary extended Euclid (at most 2*381 shift/subtract steps on 12-limb integers) instead of a
