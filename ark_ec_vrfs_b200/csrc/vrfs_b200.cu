@@ -197,7 +197,7 @@ struct DevBuf {
   size_t cap = 0;
 };
 enum { BUF_IN0, BUF_IN1, BUF_IN2, BUF_IN3, BUF_IN4, BUF_AD, BUF_OFF, BUF_OUT0, BUF_OUT1, BUF_W0, BUF_W1, BUF_W2, BUF_W3, BUF_VALID, BUF_SLAB,
-       BUF_X0, BUF_X1, BUF_X2, BUF_X3, BUF_X4, BUF_ZINV, BUF_COUNT };   // X*: wire-format staging (encoded keys, signatures, h2c data, flags)
+       BUF_X0, BUF_X1, BUF_X2, BUF_X3, BUF_X4, BUF_ZINV, BUF_SLAB2, BUF_COUNT };   // X*: wire-format staging (encoded keys, signatures, h2c data, flags)
 
 #define MAX_TIMED 64
 struct vrfs_ctx {
@@ -347,9 +347,12 @@ extern "C" int vrfs_suite_point_enc_len(vrfs_suite s) { return s == VRFS_P256_TA
 // =================================================================================================
 // lincomb launcher
 // =================================================================================================
+// `side` = true: enqueue on the context's second stream with its own slab, so that two independent linear combinations of a
+// small batch (U and V of a verify) run concurrently instead of back to back; the caller joins the streams.
 template <class C, int NV, int NF>
-static vrfs_status launch_lincomb(vrfs_ctx* ctx, LincombArgs A) {
+static vrfs_status launch_lincomb(vrfs_ctx* ctx, LincombArgs A, bool side = false) {
   if (A.n == 0) return VRFS_OK;
+  cudaStream_t stream = side ? ctx->copy_stream : ctx->stream;
   int per_sm = 0;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lincomb<C, NV, NF>, LINCOMB_THREADS, 0));
   if (per_sm < 1) per_sm = 1;
@@ -357,11 +360,11 @@ static vrfs_status launch_lincomb(vrfs_ctx* ctx, LincombArgs A) {
   uint32_t need = (A.n + LINCOMB_THREADS - 1) / LINCOMB_THREADS;
   if (blocks > need) blocks = need;
   void* slab = nullptr;
-  ST(ensure(ctx, BUF_SLAB, (size_t)blocks * LINCOMB_THREADS * slab_bytes<C>(NV) + 256, &slab));
+  ST(ensure(ctx, side ? BUF_SLAB2 : BUF_SLAB, (size_t)blocks * LINCOMB_THREADS * slab_bytes<C>(NV) + 256, &slab));
   A.slab = (uint8_t*)slab;
   A.next_item = reinterpret_cast<uint32_t*>((uint8_t*)slab + (size_t)blocks * LINCOMB_THREADS * slab_bytes<C>(NV));   // work counter behind the slabs
-  CU(cudaMemsetAsync(A.next_item, 0, sizeof(uint32_t), ctx->stream));
-  k_lincomb<C, NV, NF><<<blocks, LINCOMB_THREADS, 0, ctx->stream>>>(A);
+  CU(cudaMemsetAsync(A.next_item, 0, sizeof(uint32_t), stream));
+  k_lincomb<C, NV, NF><<<blocks, LINCOMB_THREADS, 0, stream>>>(A);
   LAUNCHED_AS(ctx, NV == 2 ? "lincomb<2,0>" : NV == 1 && NF == 1 ? "lincomb<1,1>" : NV == 1 ? "lincomb<1,0>" : NF == 2 ? "lincomb<0,2>" : NV == 1 && NF == 2 ? "lincomb<1,2>" : "lincomb<0,1>");
   return VRFS_OK;
 }
@@ -381,17 +384,28 @@ static vrfs_status ietf_verify_dev(vrfs_ctx* ctx, size_t n, const uint8_t* pk, c
   LincombArgs A = {};
   A.n = (uint32_t)n;
   A.valid = (uint8_t*)valid;
-  // U = s*G - c*Y
+  // Small batches leave most of the GPU idle and are bound by the latency of one thread's ~4 100 products: run U and V side by
+  // side on two streams (both grids fit at once).  Large batches fill the GPU either way and stay on one stream.
+  const bool split = n <= (size_t)ctx->sms * LINCOMB_THREADS;
   const uint32_t cbits = S::CLEN < 32 ? 8u * S::CLEN : 0u;     // a CHALLENGE_LEN-byte challenge: half of its windows are empty
+  // U = s*G - c*Y
   A.var[0] = {pk, 64, c, 32, 1, cbits};
   A.fix[0] = {s, 32, 0, ctx->fixtab[S::ID][0]};
   A.out_xyz = (uint32_t*)u;
-  ST((launch_lincomb<C, 1, 1>(ctx, A)));
+  if (split) {   // the side stream starts after everything already enqueued on the main stream (inputs, the memset of `valid`)
+    CU(cudaEventRecord(ctx->ev_chunk[2], ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_chunk[2], 0));
+  }
+  ST((launch_lincomb<C, 1, 1>(ctx, A, split)));
   // V = s*I - c*O
   A.var[0] = {input, 64, s, 32, 0, 0};
   A.var[1] = {output, 64, c, 32, 1, cbits};
   A.out_xyz = (uint32_t*)v;
   ST((launch_lincomb<C, 2, 0>(ctx, A)));
+  if (split) {
+    CU(cudaEventRecord(ctx->ev_chunk[3], ctx->copy_stream));
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[3], 0));
+  }
   k_ietf_verify_finish<S><<<(unsigned)((n + 128 * FINISH_K - 1) / (128 * FINISH_K)), 128, 0, ctx->stream>>>((uint32_t)n, pk, input, output, c, (const uint32_t*)u,
                                                                                 (const uint32_t*)v, ad, ad_off, (const uint8_t*)valid, out_ok);
   LAUNCHED_AS(ctx, "ietf_verify_finish");
