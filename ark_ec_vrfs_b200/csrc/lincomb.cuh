@@ -37,9 +37,6 @@ template <class F> HD_INLINE void store_fp_xyz(uint32_t* o, const F& X, const F&
   constexpr int Q = F::N / 4;
   for (int i = 0; i < Q; i++) { d[i] = sx[i]; d[Q + i] = sy[i]; d[2 * Q + i] = sz[i]; }
 }
-#ifndef VRFS_PREFETCH_L2_AHEAD
-#define VRFS_PREFETCH_L2_AHEAD 0
-#endif
 HD_INLINE void prefetch_l2(const void* p, unsigned bytes) {
 #ifdef __CUDA_ARCH__
   for (unsigned o = 0; o < bytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)p + o));
@@ -259,12 +256,6 @@ HD_INLINE bool lincomb_item(const LincombArgs& A, uint32_t item, typename Grp<C>
       for (int t = 0; t < NT; t++) {
         int d = (G::KB_LIMBS > 8 && w == 64) ? (int)kb[t][8] : digit4(kb[t], w);
         prefetch_l1(&slab[t * TBL_ENTRIES + (d < 0 ? -d : d)], sizeof(typename G::Entry));
-#if VRFS_PREFETCH_L2_AHEAD
-        if (w > 0) {   // next window's entries: DRAM -> L2 one whole window (4 doublings + the additions) ahead
-          int dn = digit4(kb[t], w - 1);
-          prefetch_l2(&slab[t * TBL_ENTRIES + (dn < 0 ? -dn : dn)], sizeof(typename G::Entry));
-        }
-#endif
       }
       if (w != wstart) G::dbl4(&acc);
 #pragma unroll
