@@ -4,6 +4,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <mutex>
 #include <new>
 
 #include "../../include/vrfs_b200.h"
@@ -211,6 +212,7 @@ struct vrfs_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t ev_chunk[4] = {nullptr, nullptr, nullptr, nullptr};
   char err[512] = {0};
+  std::recursive_mutex mu;            // entry points serialise per context ("internally synchronised")
   uint64_t launches = 0;
   DevBuf buf[BUF_COUNT];
   void* fixtab[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};   // [suite][G | blinding base]
@@ -253,6 +255,7 @@ static vrfs_status note_kernel(vrfs_ctx* ctx, const char* name) {
 }
 extern "C" vrfs_status vrfs_ctx_enable_kernel_timing(vrfs_ctx* ctx, int on) {
   if (!ctx) return VRFS_BAD_ARG;
+  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
   ctx->timing = on != 0;
   ctx->n_timed = 0;
   return VRFS_OK;
@@ -260,6 +263,7 @@ extern "C" vrfs_status vrfs_ctx_enable_kernel_timing(vrfs_ctx* ctx, int on) {
 // device time of every kernel of the most recent *_batch / *_batch_dev call (after a sync); returns the count
 extern "C" int vrfs_ctx_kernel_timings(vrfs_ctx* ctx, const char** names, float* ms, int cap) {
   if (!ctx || !ctx->timing) return 0;
+  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
   if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return 0;
   int n = ctx->n_timed < cap ? ctx->n_timed : cap;
   for (int i = 0; i < n; i++) {
@@ -334,6 +338,7 @@ extern "C" void vrfs_ctx_destroy(vrfs_ctx* ctx) {
 }
 extern "C" vrfs_status vrfs_ctx_sync(vrfs_ctx* ctx) {
   if (!ctx) return VRFS_BAD_ARG;
+  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
   CU(cudaStreamSynchronize(ctx->stream));
   return VRFS_OK;
 }
@@ -416,6 +421,7 @@ extern "C" vrfs_status vrfs_ietf_verify_batch_dev(vrfs_ctx* ctx, vrfs_suite suit
                                                   const uint8_t* output, const uint8_t* c, const uint8_t* s, const uint8_t* ad,
                                                   const uint64_t* ad_off, uint8_t* out_ok) {
   if (!ctx) return VRFS_BAD_ARG;
+  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
   if (n == 0) return VRFS_OK;
   if (!pk || !input || !output || !c || !s || !out_ok || (ad && !ad_off)) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if (n > 0x7fffffffu) return fail(ctx, VRFS_BAD_ARG, "batch too large (n < 2^31)");
@@ -454,6 +460,7 @@ extern "C" vrfs_status vrfs_ietf_verify_batch(vrfs_ctx* ctx, vrfs_suite suite, s
                                               const uint8_t* output, const uint8_t* c, const uint8_t* s, const uint8_t* ad,
                                               const uint64_t* ad_off, uint8_t* out_ok) {
   if (!ctx) return VRFS_BAD_ARG;
+  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
   if (n == 0) return VRFS_OK;
   if (!pk || !input || !output || !c || !s || !out_ok) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   CU(cudaSetDevice(ctx->device));
@@ -495,6 +502,7 @@ extern "C" vrfs_status vrfs_ietf_verify_batch(vrfs_ctx* ctx, vrfs_suite suite, s
 // =================================================================================================
 extern "C" vrfs_status vrfs_measure_mac32_peak(vrfs_ctx* ctx, int variant, double* out_mac_per_s, double* out_sm_mhz_est) {
   if (!ctx || !out_mac_per_s) return VRFS_BAD_ARG;
+  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
   CU(cudaSetDevice(ctx->device));
   const int threads = 256, blocks = ctx->sms * 8;
   void *out = nullptr, *cyc = nullptr;
@@ -752,6 +760,7 @@ static vrfs_status ietf_prove_dev(vrfs_ctx* ctx, size_t n, const uint8_t* sk, co
 extern "C" vrfs_status vrfs_ietf_prove_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* sk, const uint8_t* input, const uint8_t* output,
                                              const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_c, uint8_t* out_s) {
   if (!ctx) return VRFS_BAD_ARG;
+  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
   if (n == 0) return VRFS_OK;
   if (!sk || !input || !output || !out_c || !out_s) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
@@ -783,6 +792,7 @@ template <class S> static vrfs_status output_dev(vrfs_ctx* ctx, size_t n, const 
 }
 extern "C" vrfs_status vrfs_output_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* sk, const uint8_t* input, uint8_t* out_output) {
   if (!ctx) return VRFS_BAD_ARG;
+  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
   if (n == 0) return VRFS_OK;
   if (!sk || !input || !out_output) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
@@ -813,6 +823,7 @@ template <class S> static vrfs_status from_seed_dev(vrfs_ctx* ctx, size_t n, con
 extern "C" vrfs_status vrfs_secret_from_seed_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* seeds, const uint64_t* seed_off,
                                                    uint8_t* out_sk, uint8_t* out_pk) {
   if (!ctx) return VRFS_BAD_ARG;
+  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
   if (n == 0) return VRFS_OK;
   if (!seed_off || !out_sk) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
@@ -829,6 +840,7 @@ extern "C" vrfs_status vrfs_secret_from_seed_batch(vrfs_ctx* ctx, vrfs_suite sui
 }
 extern "C" vrfs_status vrfs_nonce_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* sk, const uint8_t* input, uint8_t* out_k) {
   if (!ctx) return VRFS_BAD_ARG;
+  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
   if (n == 0) return VRFS_OK;
   if (!sk || !input || !out_k) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
@@ -844,6 +856,7 @@ extern "C" vrfs_status vrfs_nonce_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t 
 }
 extern "C" vrfs_status vrfs_point_to_hash_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* pts, uint8_t* out_hash) {
   if (!ctx) return VRFS_BAD_ARG;
+  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
   if (n == 0) return VRFS_OK;
   if (!pts || !out_hash) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
@@ -860,6 +873,7 @@ extern "C" vrfs_status vrfs_point_to_hash_batch(vrfs_ctx* ctx, vrfs_suite suite,
 }
 extern "C" vrfs_status vrfs_point_encode_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* pts, uint8_t* out_enc) {
   if (!ctx) return VRFS_BAD_ARG;
+  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
   if (n == 0) return VRFS_OK;
   if (!pts || !out_enc) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
@@ -876,6 +890,7 @@ extern "C" vrfs_status vrfs_point_encode_batch(vrfs_ctx* ctx, vrfs_suite suite, 
 }
 extern "C" vrfs_status vrfs_point_decode_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* enc, uint8_t* out_pts, uint8_t* out_ok) {
   if (!ctx) return VRFS_BAD_ARG;
+  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
   if (n == 0) return VRFS_OK;
   if (!enc || !out_pts || !out_ok) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
@@ -893,6 +908,7 @@ extern "C" vrfs_status vrfs_point_decode_batch(vrfs_ctx* ctx, vrfs_suite suite, 
 extern "C" vrfs_status vrfs_data_to_point_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* data, const uint64_t* data_off,
                                                 uint8_t* out_pts, uint8_t* out_ok) {
   if (!ctx) return VRFS_BAD_ARG;
+  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
   if (n == 0) return VRFS_OK;
   if (!data_off || !out_pts || !out_ok) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
@@ -936,6 +952,7 @@ static vrfs_status pedersen_prove_dev(vrfs_ctx* ctx, size_t n, const uint8_t* sk
 extern "C" vrfs_status vrfs_pedersen_prove_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* sk, const uint8_t* input, const uint8_t* output,
                                                  const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_proof, uint8_t* out_blinding) {
   if (!ctx) return VRFS_BAD_ARG;
+  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
   if (n == 0) return VRFS_OK;
   if (!sk || !input || !output || !out_proof || !out_blinding) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
@@ -976,6 +993,7 @@ static vrfs_status pedersen_verify_dev(vrfs_ctx* ctx, size_t n, const uint8_t* i
 extern "C" vrfs_status vrfs_pedersen_verify_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* input, const uint8_t* output, const uint8_t* proof,
                                                   const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_ok) {
   if (!ctx) return VRFS_BAD_ARG;
+  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
   if (n == 0) return VRFS_OK;
   if (!input || !output || !proof || !out_ok) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
@@ -1048,6 +1066,7 @@ template <class S> static vrfs_status decode_checked_launch(vrfs_ctx* ctx, size_
 }
 extern "C" vrfs_status vrfs_point_decode_checked_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* enc, uint8_t* out_pts, uint8_t* out_ok) {
   if (!ctx) return VRFS_BAD_ARG;
+  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
   if (n == 0) return VRFS_OK;
   if (!enc || !out_pts || !out_ok) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
@@ -1063,6 +1082,7 @@ extern "C" vrfs_status vrfs_point_decode_checked_batch(vrfs_ctx* ctx, vrfs_suite
 }
 extern "C" vrfs_status vrfs_subgroup_check_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* pts, uint8_t* out_ok) {
   if (!ctx) return VRFS_BAD_ARG;
+  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
   if (n == 0) return VRFS_OK;
   if (!pts || !out_ok) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
@@ -1091,6 +1111,7 @@ template <class S> static vrfs_status ietf_sign_wire_dev(vrfs_ctx* ctx, size_t n
 extern "C" vrfs_status vrfs_ietf_sign_wire_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* sk, const uint8_t* data, const uint64_t* data_off,
                                                  const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_sig, uint8_t* out_ok) {
   if (!ctx) return VRFS_BAD_ARG;
+  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
   if (n == 0) return VRFS_OK;
   if (!sk || !data_off || !out_sig) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
@@ -1134,6 +1155,7 @@ template <class S> static vrfs_status ietf_verify_wire_dev(vrfs_ctx* ctx, size_t
 extern "C" vrfs_status vrfs_ietf_verify_wire_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* pk_enc, const uint8_t* data, const uint64_t* data_off,
                                                    const uint8_t* sig, const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_ok, uint8_t* out_hash) {
   if (!ctx) return VRFS_BAD_ARG;
+  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
   if (n == 0) return VRFS_OK;
   if (!pk_enc || !data_off || !sig || !out_ok) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
@@ -1212,6 +1234,7 @@ template <class S> static vrfs_status pedersen_sign_wire_dev(vrfs_ctx* ctx, size
 extern "C" vrfs_status vrfs_pedersen_sign_wire_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* sk, const uint8_t* data, const uint64_t* data_off,
                                                      const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_sig, uint8_t* out_blinding, uint8_t* out_ok) {
   if (!ctx) return VRFS_BAD_ARG;
+  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
   if (n == 0) return VRFS_OK;
   if (!sk || !data_off || !out_sig || !out_blinding) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
@@ -1248,6 +1271,7 @@ template <class S> static vrfs_status pedersen_verify_wire_dev(vrfs_ctx* ctx, si
 extern "C" vrfs_status vrfs_pedersen_verify_wire_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* data, const uint64_t* data_off, const uint8_t* sig,
                                                        const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_ok) {
   if (!ctx) return VRFS_BAD_ARG;
+  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
   if (n == 0) return VRFS_OK;
   if (!data_off || !sig || !out_ok) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
@@ -1321,6 +1345,7 @@ static vrfs_status msm_dev(vrfs_ctx* ctx, MsmPlan p, const void* d_bases, const 
 }
 static vrfs_status msm_host(vrfs_ctx* ctx, size_t n, const uint8_t* bases, const uint8_t* scalars, int ncol, uint8_t* out, int out_mode) {
   if (!ctx) return VRFS_BAD_ARG;
+  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
   if (ncol < 1 || ncol > 32) return fail(ctx, VRFS_BAD_ARG, "n_columns must be in 1..32");
   if (!out || (n && (!bases || !scalars))) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   const size_t ob = out_mode ? 144 : 96;
@@ -1350,6 +1375,7 @@ extern "C" vrfs_status vrfs_msm_g1_partial(vrfs_ctx* ctx, size_t n, const uint8_
 }
 extern "C" vrfs_status vrfs_msm_g1_prepare(vrfs_ctx* ctx, size_t n, const uint8_t* bases, vrfs_msm_bases** out) {
   if (!ctx || !out) return VRFS_BAD_ARG;
+  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
   *out = nullptr;
   if (n == 0 || !bases) return fail(ctx, VRFS_BAD_ARG, "empty base vector");
   if (n > (1u << 24)) return fail(ctx, VRFS_BAD_ARG, "prepared MSM size above 2^24 is not supported");
@@ -1371,6 +1397,7 @@ extern "C" vrfs_status vrfs_msm_g1_prepare(vrfs_ctx* ctx, size_t n, const uint8_
 }
 extern "C" void vrfs_msm_g1_release(vrfs_msm_bases* h) {
   if (!h) return;
+  std::lock_guard<std::recursive_mutex> lock_(h->ctx->mu);
   cudaSetDevice(h->ctx->device);
   cudaStreamSynchronize(h->ctx->stream);
   if (h->Q) cudaFree(h->Q);
@@ -1378,6 +1405,7 @@ extern "C" void vrfs_msm_g1_release(vrfs_msm_bases* h) {
 }
 extern "C" vrfs_status vrfs_msm_g1_prepared(vrfs_ctx* ctx, const vrfs_msm_bases* h, const uint8_t* scalars, int n_columns, uint8_t* out) {
   if (!ctx || !h || h->ctx != ctx) return VRFS_BAD_ARG;
+  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
   if (n_columns < 1 || n_columns > 32 || !scalars || !out) return fail(ctx, VRFS_BAD_ARG, "bad argument");
   ST(begin_call(ctx, h->n));
   const uint8_t* d_s; uint8_t* d_o;
@@ -1390,6 +1418,7 @@ extern "C" vrfs_status vrfs_msm_g1_prepared(vrfs_ctx* ctx, const vrfs_msm_bases*
 }
 extern "C" vrfs_status vrfs_g1_sum_partials(vrfs_ctx* ctx, int n_parts, int n_columns, const uint8_t* partials, uint8_t* out) {
   if (!ctx) return VRFS_BAD_ARG;
+  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
   if (n_parts < 1 || n_columns < 1 || n_columns > 32 || !partials || !out) return fail(ctx, VRFS_BAD_ARG, "bad argument");
   ST(begin_call(ctx, 1));
   const uint8_t* d_p; uint8_t* d_o;

@@ -25,8 +25,9 @@
  *   - `vrfs_*_batch`      : HOST buffers; copies in, runs, copies out, returns when done.
  *     `vrfs_*_batch_dev`  : DEVICE buffers (16-byte aligned) of the same layout, enqueued on the
  *                           context's stream; results are ready after `vrfs_ctx_sync`.
- *   - One context per GPU (one process per GPU under torch.distributed / NCCL); calls on one context
- *     must not overlap.
+ *   - One context per GPU (one process per GPU under torch.distributed / NCCL).  A context is internally synchronised:
+ *     concurrent calls on one context from several host threads serialise (per-context mutex); `*_batch_dev` calls
+ *     are asynchronous on the context's stream and must be followed by `vrfs_ctx_sync` before their buffers are reused.
  */
 #ifndef VRFS_B200_H
 #define VRFS_B200_H

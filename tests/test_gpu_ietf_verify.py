@@ -80,3 +80,30 @@ def test_ietf_verify_full_size_tiled(eng):
     got = eng.ietf_verify(O.BANDERSNATCH, w["pk"], w["inp"], w["out"], w["c"], w["s"], None)
     assert got.shape == (1 << 20,)
     assert np.array_equal(got, w["expect"])
+
+
+def test_concurrent_calls_on_one_context_serialise():
+    """include/vrfs_b200.h: a context is internally synchronised - host threads may share it (ctypes releases the GIL)."""
+    import threading
+    import ark_ec_vrfs_b200 as vrfs
+    eng = vrfs.Engine(0)
+    w = V.make_ietf_proofs(O.BANDERSNATCH, 2048, "ragged")
+    sk, pk, inp, out = V.make_keys_inputs(O.BANDERSNATCH, 512)
+    c_o, s_o = O.ietf_prove(O.BANDERSNATCH, sk, inp, out, None)
+    errs = []
+
+    def verifier():
+        for _ in range(6):
+            got = eng.ietf_verify(vrfs.BANDERSNATCH, w["pk"], w["inp"], w["out"], w["c"], w["s"], w["ads"])
+            if not np.array_equal(got, w["expect"]): errs.append("verify")
+
+    def prover():
+        for _ in range(6):
+            c, s = eng.ietf_prove(vrfs.BANDERSNATCH, sk, inp, out, None)
+            if not (np.array_equal(c, c_o) and np.array_equal(s, s_o)): errs.append("prove")
+
+    ts = [threading.Thread(target=f) for f in (verifier, prover, verifier, prover)]
+    for t in ts: t.start()
+    for t in ts: t.join()
+    eng.close()
+    assert not errs, errs
