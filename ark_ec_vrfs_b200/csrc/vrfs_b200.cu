@@ -668,12 +668,6 @@ template <class C> __global__ void __launch_bounds__(ITEM_THREADS) k_pedersen_ve
 // =================================================================================================
 // host-side plumbing shared by the entry points below
 // =================================================================================================
-struct Staged {   // device copies of a call's host inputs / device homes of its outputs
-  vrfs_ctx* ctx;
-  const uint8_t* in[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-  const uint8_t* var = nullptr; const uint64_t* off = nullptr;
-  uint8_t* out[2] = {nullptr, nullptr};
-};
 static vrfs_status stage_out(vrfs_ctx* ctx, int which, size_t bytes, uint8_t** dev) {
   void* d = nullptr;
   ST(ensure(ctx, which, bytes, &d));
@@ -1309,7 +1303,7 @@ static vrfs_status msm_dev(vrfs_ctx* ctx, MsmPlan p, const void* d_bases, const 
   const size_t n = p.n, ncol = p.ncol;
   const size_t segs = ncol * p.seg_windows, nbuckets = segs * p.nb, seg_len = n * (p.prepared ? p.windows : 1);
   const size_t per_seg = p.nb / p.chunk;
-  void *counts, *list, *buckets, *wsum;
+  void *counts = nullptr, *list = nullptr, *buckets = nullptr, *wsum = nullptr;
   ST(ensure(ctx, BUF_W1, (nbuckets * 4 + 16) * sizeof(uint32_t), &counts));
   uint32_t *offsets = (uint32_t*)counts + nbuckets, *cursors = offsets + nbuckets, *big_list = cursors + nbuckets, *big_count = big_list + nbuckets;
   ST(ensure(ctx, BUF_W2, segs * seg_len * sizeof(uint32_t), &list));
