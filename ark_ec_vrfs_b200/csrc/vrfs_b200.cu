@@ -442,6 +442,8 @@ static vrfs_status stage_in(vrfs_ctx* ctx, int which, const void* host, size_t b
   void* d = nullptr;
   ST(ensure(ctx, which, bytes, &d));
   if (bytes) CU(cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  // kernel timing: the first kernel's interval starts after the last input copy, not at the start of the call
+  if (ctx->timing && ctx->tev[0] && ctx->n_timed == 0) CU(cudaEventRecord(ctx->tev[0], ctx->stream));
   *dev = (const uint8_t*)d;
   return VRFS_OK;
 }

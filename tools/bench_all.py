@@ -17,33 +17,41 @@ n = 1 << a.logn
 e = vrfs.Engine(0)
 res = {"batch": n, "note": "host-buffer ABI calls (pageable numpy buffers), best of 3, includes H2D/D2H", "suites": {}}
 
+DEV = {}          # kernel-only items/s of the most recent best() call (sum of the call's kernel times, CUDA events)
+
+
 def best(f, reps=3):
     f(); ts = []
+    e.enable_kernel_timing(True)
     for _ in range(reps):
         t = time.perf_counter(); r = f(); ts.append(time.perf_counter() - t)
+    DEV["ms"] = sum(ms for _, ms in e.kernel_timings())
+    e.enable_kernel_timing(False)
     return min(ts), r
 
 sub = np.arange(0, n, n // 1024)
 for suite, name in (() if os.environ.get("MSM_ONLY") else ((0, "bandersnatch"), (1, "ed25519"), (2, "secp256r1"))):
     seeds = [b"bench-sk" + i.to_bytes(8, "little") for i in range(n)]
     alphas = [i.to_bytes(8, "little") + bytes(24) for i in range(n)]
-    r = {}
-    t, (sk, pk) = best(lambda: e.secret_from_seed(suite, seeds)); r["secret_from_seed+public"] = n / t
-    t, (inp, ok) = best(lambda: e.data_to_point(suite, alphas)); r["data_to_point"] = n / t; assert ok.all()
-    t, out = best(lambda: e.output(suite, sk, inp)); r["output"] = n / t
-    t, (c, s) = best(lambda: e.ietf_prove(suite, sk, inp, out)); r["ietf_prove"] = n / t
-    t, okv = best(lambda: e.ietf_verify(suite, pk, inp, out, c, s)); r["ietf_verify"] = n / t; assert okv.all()
-    t, (pr, bl) = best(lambda: e.pedersen_prove(suite, sk, inp, out)); r["pedersen_prove"] = n / t
-    t, okp = best(lambda: e.pedersen_verify(suite, inp, out, pr)); r["pedersen_verify"] = n / t; assert okp.all()
+    r = {}; dev = {}
+    t, (sk, pk) = best(lambda: e.secret_from_seed(suite, seeds)); r["secret_from_seed+public"] = n / t; dev["secret_from_seed+public"] = n / (DEV["ms"] * 1e-3);
+    t, (inp, ok) = best(lambda: e.data_to_point(suite, alphas)); r["data_to_point"] = n / t; dev["data_to_point"] = n / (DEV["ms"] * 1e-3); assert ok.all()
+    t, out = best(lambda: e.output(suite, sk, inp)); r["output"] = n / t; dev["output"] = n / (DEV["ms"] * 1e-3);
+    t, (c, s) = best(lambda: e.ietf_prove(suite, sk, inp, out)); r["ietf_prove"] = n / t; dev["ietf_prove"] = n / (DEV["ms"] * 1e-3);
+    t, okv = best(lambda: e.ietf_verify(suite, pk, inp, out, c, s)); r["ietf_verify"] = n / t; dev["ietf_verify"] = n / (DEV["ms"] * 1e-3); assert okv.all()
+    t, (pr, bl) = best(lambda: e.pedersen_prove(suite, sk, inp, out)); r["pedersen_prove"] = n / t; dev["pedersen_prove"] = n / (DEV["ms"] * 1e-3);
+    t, okp = best(lambda: e.pedersen_verify(suite, inp, out, pr)); r["pedersen_verify"] = n / t; dev["pedersen_verify"] = n / (DEV["ms"] * 1e-3); assert okp.all()
     pk_enc = e.point_encode(suite, pk); alphas_packed = vrfs.pack_var(alphas)
-    t, (sig, sok) = best(lambda: e.ietf_sign_wire(suite, sk, alphas_packed)); r["ietf_sign_wire"] = n / t; assert sok.all()
-    t, (okw, beta) = best(lambda: e.ietf_verify_wire(suite, pk_enc, alphas_packed, sig)); r["ietf_verify_wire"] = n / t; assert okw.all()
+    t, (sig, sok) = best(lambda: e.ietf_sign_wire(suite, sk, alphas_packed)); r["ietf_sign_wire"] = n / t; dev["ietf_sign_wire"] = n / (DEV["ms"] * 1e-3); assert sok.all()
+    t, (okw, beta) = best(lambda: e.ietf_verify_wire(suite, pk_enc, alphas_packed, sig)); r["ietf_verify_wire"] = n / t; dev["ietf_verify_wire"] = n / (DEV["ms"] * 1e-3); assert okw.all()
     ow, bw = O.ietf_verify_wire(suite, pk_enc[sub], [alphas[i] for i in sub], sig[sub]); assert ow.all() and np.array_equal(bw, beta[sub])
     # oracle cross-check on a subsample
     assert np.array_equal(O.data_to_point(suite, [alphas[i] for i in sub])[0], inp[sub])
     co, so = O.ietf_prove(suite, sk[sub], inp[sub], out[sub]); assert np.array_equal(co, c[sub]) and np.array_equal(so, s[sub])
     po, bo = O.pedersen_prove(suite, sk[sub], inp[sub], out[sub]); assert np.array_equal(po, pr[sub]) and np.array_equal(bo, bl[sub])
     res["suites"][name] = {k: round(v) for k, v in r.items()}
+    res.setdefault("suites_kernel_only", {})[name] = {k: round(v) for k, v in dev.items()}
+    print(name, "kernel-only", res["suites_kernel_only"][name], flush=True)
     print(name, res["suites"][name], flush=True)
 
 # ring commitment MSM: bases k_i * G (62-bit multiples, cheap on the oracle), 3 random columns
