@@ -1400,18 +1400,25 @@ extern "C" void vrfs_msm_g1_release(vrfs_msm_bases* h) {
   if (h->Q) cudaFree(h->Q);
   delete h;
 }
-extern "C" vrfs_status vrfs_msm_g1_prepared(vrfs_ctx* ctx, const vrfs_msm_bases* h, const uint8_t* scalars, int n_columns, uint8_t* out) {
+static vrfs_status msm_prepared_host(vrfs_ctx* ctx, const vrfs_msm_bases* h, const uint8_t* scalars, int n_columns, uint8_t* out, int out_mode) {
   if (!ctx || !h || h->ctx != ctx) return VRFS_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
   if (n_columns < 1 || n_columns > 32 || !scalars || !out) return fail(ctx, VRFS_BAD_ARG, "bad argument");
   ST(begin_call(ctx, h->n));
+  const size_t ob = out_mode ? 144 : 96;
   const uint8_t* d_s; uint8_t* d_o;
   ST(stage_in(ctx, BUF_IN1, scalars, h->n * 32 * (size_t)n_columns, &d_s));
-  ST(stage_out(ctx, BUF_OUT0, (size_t)96 * n_columns, &d_o));
+  ST(stage_out(ctx, BUF_OUT0, ob * n_columns, &d_o));
   MsmPlan p = msm_plan((uint32_t)h->n, (uint32_t)n_columns, 1);
-  ST(msm_dev(ctx, p, h->Q, d_s, d_o, 0));
-  ST(copy_out(ctx, out, d_o, (size_t)96 * n_columns));
+  ST(msm_dev(ctx, p, h->Q, d_s, d_o, out_mode));
+  ST(copy_out(ctx, out, d_o, ob * n_columns));
   return finish_call(ctx);
+}
+extern "C" vrfs_status vrfs_msm_g1_prepared(vrfs_ctx* ctx, const vrfs_msm_bases* h, const uint8_t* scalars, int n_columns, uint8_t* out) {
+  return msm_prepared_host(ctx, h, scalars, n_columns, out, 0);
+}
+extern "C" vrfs_status vrfs_msm_g1_prepared_partial(vrfs_ctx* ctx, const vrfs_msm_bases* h, const uint8_t* scalars, int n_columns, uint8_t* out_partial) {
+  return msm_prepared_host(ctx, h, scalars, n_columns, out_partial, 1);
 }
 extern "C" vrfs_status vrfs_g1_sum_partials(vrfs_ctx* ctx, int n_parts, int n_columns, const uint8_t* partials, uint8_t* out) {
   if (!ctx) return VRFS_BAD_ARG;

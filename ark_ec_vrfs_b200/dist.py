@@ -48,3 +48,25 @@ def msm_g1_sharded(engine, bases, scalars, n_columns, group=None, device=None):
     part = engine.msm_g1_partial(bases[lo:hi], sc, n_columns)
     parts = gather_bytes(part, group, device)
     return engine.g1_sum_partials(parts, n_columns)
+
+
+class ShardedPreparedBases:
+    """RingContext analogue on G GPUs: rank g prepares the SRS slice [g*n/G, (g+1)*n/G) once; every commitment is then one
+    prepared partial MSM per rank, an all-gather of 144 bytes per column per rank and G-1 point additions."""
+
+    def __init__(self, engine, bases, group=None, device=None):
+        import torch.distributed as dist
+        self.engine, self.group, self.device = engine, group, device
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.n = len(bases)
+        self.lo, self.hi = shard_range(self.n, self.rank, self.world)
+        self.handle = engine.msm_g1_prepare(bases[self.lo:self.hi])
+
+    def msm(self, scalars, n_columns=1):
+        sc = np.asarray(scalars, np.uint8).reshape(n_columns, self.n, 32)[:, self.lo:self.hi].reshape(-1, 32)
+        part = self.handle.msm_partial(sc, n_columns)
+        parts = gather_bytes(part, self.group, self.device)
+        return self.engine.g1_sum_partials(parts, n_columns)
+
+    def release(self):
+        self.handle.release()

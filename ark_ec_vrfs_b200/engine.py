@@ -40,6 +40,12 @@ class PreparedBases:
         self.engine._call("vrfs_msm_g1_prepared", self.handle, _p(scalars), int(n_columns), _p(out))
         return out
 
+    def msm_partial(self, scalars, n_columns=1):
+        """projective partial sums (n_columns, 144) over this handle's bases - one rank's share of a multi-GPU MSM"""
+        scalars = _u8(scalars, (n_columns * self.n, 32)); out = np.zeros((n_columns, 144), np.uint8)
+        self.engine._call("vrfs_msm_g1_prepared_partial", self.handle, _p(scalars), int(n_columns), _p(out))
+        return out
+
     def release(self):
         if self.handle:
             self.engine._lib.vrfs_msm_g1_release(self.handle)
