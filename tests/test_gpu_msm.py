@@ -146,3 +146,18 @@ def test_msm_prepared_equals_stateless_and_handles_skew(eng, logn):
         h.release()
     if logn <= 11:
         assert np.array_equal(full, O.msm_g1(bases, sc, 3))
+
+
+def test_prepared_partials_fold_to_the_full_commitment(eng):
+    """the multi-GPU form on one GPU: three point ranges, each with its own prepared SRS slice, partials folded"""
+    n, ncol = 3000, 3
+    bases, sc = synth(n, ncol, b"part")
+    cols = sc.reshape(ncol, n, 32)
+    cuts = [0, 1000, 1001, n]
+    parts = []
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        h = eng.msm_g1_prepare(bases[lo:hi])
+        parts.append(h.msm_partial(np.ascontiguousarray(cols[:, lo:hi]).reshape(-1, 32), ncol))
+        h.release()
+    got = eng.g1_sum_partials(np.stack(parts), ncol)
+    assert np.array_equal(got, O.msm_g1(bases, sc, ncol))
