@@ -18,6 +18,9 @@
 // the analogue of RingContext holding the SRS): segment = column, no Horner chain (255 dependent doublings ~ 2.5 ms).
 #pragma once
 #include "lincomb.cuh"
+#ifdef __CUDACC__
+#include <cooperative_groups.h>
+#endif
 
 namespace vrfs {
 
@@ -33,6 +36,7 @@ struct MsmPlan {
   int chunk;                     // buckets per thread in the segment reduction
   int tpb;                       // threads cooperating on one bucket in k_msm_accumulate (power of two <= 32)
   uint32_t big;                  // buckets with more entries than this go to k_msm_accumulate_big
+  int rc_h;                      // segment reduction: columns H of the R x H bucket matrix summed by k_msm_rc (0: nb <= 256, k_msm_wsum takes the buckets directly)
 };
 VRFS_HD inline MsmPlan msm_plan(uint32_t n, uint32_t ncol, int prepared) {
   MsmPlan p; p.n = n; p.ncol = ncol; p.prepared = prepared;
@@ -52,6 +56,8 @@ VRFS_HD inline MsmPlan msm_plan(uint32_t n, uint32_t ncol, int prepared) {
   const uint64_t total_buckets = (uint64_t)ncol * (prepared ? 1 : p.windows) * p.nb;
   p.tpb = 1; while (p.tpb < 32 && (avg / p.tpb > 24 || (total_buckets * p.tpb < 65536 && avg / p.tpb >= 4))) p.tpb *= 2;
   p.big = (uint32_t)(8 * (avg + 8));
+  p.rc_h = 0;
+  if (p.nb > 256) { int h = 0; while ((1 << (2 * h)) < p.nb) h++; p.rc_h = 1 << h; }   // H = 2^ceil(log2(nb)/2) <= 512
   return p;
 }
 #define MSM_BIG_THREADS 128
@@ -385,6 +391,220 @@ __global__ void __launch_bounds__(256) k_msm_window_sum(MsmPlan p, const G1Pt* p
     __syncthreads();
   }
   if (t == 0) copy_words16(&window_sums[seg], &sh[0]);
+}
+// =================================================================================================
+// Segment reduction, second generation (MSM_TAIL = 2, the default): everything after the bucket sums is a chain of
+// DEPENDENT point additions on very few points, and one thread needs ~11 us per complete addition (12 products of
+// 12 limbs on a multiplier pipe that retires one 64-bit product per ~6 cycles per warp).  Two changes against the
+// chunk / tree kernels above (kept behind MSM_TAIL = 1 for A/B):
+//  * lane-cooperative arithmetic: a complete addition is 6 independent products, a few additions, 6 more independent
+//    products.  A group of 8 lanes holds the operands replicated; lane g computes product g of each level and the six
+//    results are exchanged with shuffles: ~3 us per addition / doubling instead of ~11 (g1_coop_add, g1_coop_dbl).
+//  * sum_j j*B_j as (1) row and column sums of the R x H bucket matrix (j - 1 = hi*H + lo;
+//    sum j*B_j = H * sum_hi hi*Row_hi + sum_lo (lo+1)*Col_lo: two adds per bucket, depth log2 H, k_msm_rc) and
+//    (2) for the two short weighted sums the halving recursion  W(x) = W(y) + sum_u x_{2u+1},  y_u = 2 (x_{2u} + x_{2u+1})
+//    run by one cluster of 8 thread blocks (128 cooperating groups, one warp per SM sub-partition, k_msm_wsum): no
+//    multiplication by chunk offsets and no Horner chain.
+// =================================================================================================
+#ifndef MSM_TAIL
+#define MSM_TAIL 2
+#endif
+#define MSM_WSUM_CLUSTER 8
+#define MSM_WSUM_GROUPS (MSM_WSUM_CLUSTER * 16)          // 8 blocks x 4 warps x 4 groups of 8 lanes
+#define MSM_WSUM_MAXM 512                                  // longest weighted sum one cluster takes
+#define MSM_WSUM_HALF (MSM_WSUM_MAXM / 2 + 4)
+#define MSM_WSUM_SCRATCH (2 * MSM_WSUM_HALF + MSM_WSUM_GROUPS)   // points of scratch per weighted sum
+
+// scratch written by other SMs of the cluster: read through L2 (ld.global.cg), never a stale L1 line
+__device__ __forceinline__ void load_pt_cg(G1Pt* dst, const G1Pt* src_) {
+  const uint4* s = reinterpret_cast<const uint4*>(src_);
+  uint4* d = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (unsigned i = 0; i < sizeof(G1Pt) / 16; i++) d[i] = __ldcg(s + i);
+}
+__device__ __forceinline__ Fq381 fq_shfl(const Fq381& a, unsigned src_lane) {
+  Fq381 r;
+#pragma unroll
+  for (int i = 0; i < 12; i++) r.v[i] = __shfl_sync(0xffffffffu, a.v[i], src_lane);
+  return r;
+}
+// r = p + q (complete, the formula of sw_add with a = 0) computed by the 8 lanes of a group; p, q and r are replicated in every
+// lane of the group.  All 32 lanes of the warp must call it together.
+__device__ __noinline__ void g1_coop_add(G1Pt* r, const G1Pt* p, const G1Pt* q) {
+  const unsigned lane = threadIdx.x & 31u, g = lane & 7u, base = lane & ~7u;
+  Fq381 a, b;
+  {
+    // level 1, lane g: 0 X1*X2, 1 Y1*Y2, 2 Z1*Z2, 3 (X1+Y1)(X2+Y2), 4 (X1+Z1)(X2+Z2), 5 (Y1+Z1)(Y2+Z2)   (6, 7 repeat 0)
+    const bool fx = (g == 0) | (g == 3) | (g == 4) | (g >= 6), fy = (g == 1) | (g == 5);
+    const bool sy = (g == 3), sz = (g == 4) | (g == 5);
+    a = select(fx, p->X, select(fy, p->Y, p->Z)) + select(sy, p->Y, select(sz, p->Z, Fq381::zero()));
+    b = select(fx, q->X, select(fy, q->Y, q->Z)) + select(sy, q->Y, select(sz, q->Z, Fq381::zero()));
+  }
+  Fq381 t = a * b;
+  Fq381 t0 = fq_shfl(t, base), t1 = fq_shfl(t, base + 1), t2 = fq_shfl(t, base + 2);
+  Fq381 t3 = fq_shfl(t, base + 3) - (t0 + t1);            // X1Y2 + X2Y1
+  Fq381 t4 = fq_shfl(t, base + 4) - (t0 + t2);            // X1Z2 + X2Z1
+  Fq381 t5 = fq_shfl(t, base + 5) - (t1 + t2);            // Y1Z2 + Y2Z1
+  Fq381 Z3 = G1Curve::mul_b3(t2), X3 = t1 - Z3;
+  Z3 = t1 + Z3;
+  t1 = dbl(t0) + t0;
+  t4 = G1Curve::mul_b3(t4);
+  // level 2, lane g: 0 X3*Z3, 1 t1*t4, 2 t3*X3, 3 t5*t4, 4 t5*Z3, 5 t3*t1
+  a = select(g == 0, X3, select(g == 1, t1, select((g == 2) | (g == 5), t3, t5)));
+  b = select((g == 0) | (g == 4), Z3, select((g == 1) | (g == 3), t4, select(g == 2, X3, t1)));
+  t = a * b;
+  r->Y = fq_shfl(t, base) + fq_shfl(t, base + 1);
+  r->X = fq_shfl(t, base + 2) - fq_shfl(t, base + 3);
+  r->Z = fq_shfl(t, base + 4) + fq_shfl(t, base + 5);
+}
+// r = 2p (the formula of g1_dbl), same conventions
+__device__ __noinline__ void g1_coop_dbl(G1Pt* r, const G1Pt* p) {
+  const unsigned lane = threadIdx.x & 31u, g = lane & 7u, base = lane & ~7u;
+  // level 1, lane g: 0 Y*Y, 1 Y*Z, 2 Z*Z, 3 X*Y
+  Fq381 a = select(g == 2, p->Z, select(g == 3, p->X, p->Y));
+  Fq381 b = select((g == 1) | (g == 2), p->Z, p->Y);
+  Fq381 t = a * b;
+  Fq381 t0 = fq_shfl(t, base), t1 = fq_shfl(t, base + 1), t2 = G1Curve::mul_b3(fq_shfl(t, base + 2)), xy = fq_shfl(t, base + 3);
+  Fq381 Z3 = dbl(dbl(dbl(t0))), Y3 = t0 + t2;
+  t0 = t0 - (dbl(t2) + t2);
+  // level 2, lane g: 0 t2*Z3, 1 t1*Z3, 2 t0*Y3, 3 t0*xy
+  a = select(g == 0, t2, select(g == 1, t1, t0));
+  b = select((g == 0) | (g == 1), Z3, select(g == 2, Y3, xy));
+  t = a * b;
+  r->Y = fq_shfl(t, base + 2) + fq_shfl(t, base);
+  r->X = dbl(fq_shfl(t, base + 3));
+  r->Z = fq_shfl(t, base + 1);
+}
+
+// row and column sums of the bucket matrix of every segment: out[seg][hi] = sum_lo B[hi*H + lo] (hi < R = nb / H),
+// out[seg][R + lo] = sum_hi B[hi*H + lo].  One block per sum; the last five tree levels (<= 16 additions) are cooperative.
+__global__ void __launch_bounds__(128) k_msm_rc(MsmPlan p, const G1Pt* buckets, G1Pt* out) {
+  __shared__ uint4 sh_raw[128 * sizeof(G1Pt) / 16];
+  G1Pt* sh = reinterpret_cast<G1Pt*>(sh_raw);
+  const int H = p.rc_h, R = p.nb / H;
+  const uint32_t seg = blockIdx.y, o = blockIdx.x, t = threadIdx.x;
+  const G1Pt* B = buckets + (size_t)seg * p.nb;
+  const bool row = (int)o < R;
+  const int count = row ? H : R, stride = row ? 1 : H;
+  const G1Pt* first = row ? B + (size_t)o * H : B + (o - R);
+  G1Pt acc; sw_set_identity(acc);
+  if ((int)t < count) copy_words16(&acc, first + (size_t)t * stride);
+  for (int k = t + 128; k < count; k += 128) { G1Pt q; copy_words16(&q, first + (size_t)k * stride); sw_add<G1Curve>(&acc, &acc, &q); }
+  copy_words16(&sh[t], &acc);
+  __syncthreads();
+  int width = 128; while (width / 2 >= count) width /= 2;       // live entries of sh (power of two >= min(count, 128))
+  for (int s = width >> 1; s > 16; s >>= 1) {
+    if ((int)t < s) { G1Pt y; copy_words16(&y, &sh[t + s]); sw_add<G1Curve>(&acc, &acc, &y); copy_words16(&sh[t], &acc); }
+    __syncthreads();
+  }
+  const unsigned grp = t >> 3, g = t & 7u;                      // 16 groups of 8 lanes
+  for (int s = min(width >> 1, 16); s > 0; s >>= 1) {
+    if ((int)(grp & ~3u) < s) {                                 // warp-uniform: the warp holds a live group
+      G1Pt x, y, z;
+      copy_words16(&x, &sh[(int)grp < s ? grp : (unsigned)s]);            // idle groups of a live warp read what nobody writes
+      copy_words16(&y, &sh[(int)grp < s ? grp + s : (unsigned)s]);
+      g1_coop_add(&z, &x, &y);
+      __syncwarp();
+      if ((int)grp < s && g == 0) copy_words16(&sh[grp], &z);
+    }
+    __syncthreads();
+  }
+  if (t == 0) copy_words16(&out[(size_t)seg * (R + H) + o], &sh[0]);
+}
+
+// One cluster per weighted sum  W = sum_i (i + shift) * x_i, i < m <= MSM_WSUM_MAXM  (shift = 1: bucket values; shift = 0: the
+// row index of k_msm_rc), followed by `post` doublings.  With x'_{i+shift} = x_i:  W(x') = W(y) + sum_u x'_{2u+1},
+// y_u = 2 (x'_{2u} + x'_{2u+1}); every group keeps the sum of the odd elements it met, the groups' sums are tree-added at the end.
+__global__ void __cluster_dims__(MSM_WSUM_CLUSTER, 1, 1) __launch_bounds__(128) k_msm_wsum(MsmPlan p, const G1Pt* in, G1Pt* scratch, G1Pt* parts) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const uint32_t seg = blockIdx.z, part = blockIdx.y, nparts = gridDim.y;
+  const unsigned G = cluster.block_rank() * 16u + (threadIdx.x >> 3), g = threadIdx.x & 7u;
+  const G1Pt* x; int m, shift, post = 0;
+  if (p.rc_h) {
+    const int R = p.nb / p.rc_h;
+    x = in + (size_t)seg * (R + p.rc_h) + (part ? R : 0);
+    m = part ? p.rc_h : R; shift = part ? 1 : 0;
+    if (!part) while ((1 << post) < p.rc_h) post++;
+  } else { x = in + (size_t)seg * p.nb; m = p.nb; shift = 1; }
+  const size_t prob = (size_t)seg * nparts + part;
+  G1Pt* bufA = scratch + prob * MSM_WSUM_SCRATCH;
+  G1Pt* bufB = bufA + MSM_WSUM_HALF;
+  G1Pt* Hs = bufB + MSM_WSUM_HALF;
+  G1Pt T; sw_set_identity(T);
+  int len = m + shift, level = 0;
+  const G1Pt* src = x;
+  G1Pt* dst = bufA;
+  const int ntask0 = (len + 1) / 2;
+  while (len > 1) {
+    const int ntask = (len + 1) / 2;
+    for (int rd = 0; rd * MSM_WSUM_GROUPS < ntask; rd++) {
+      if ((int)((rd * MSM_WSUM_GROUPS + G) & ~3u) >= ntask) continue;      // warp-uniform: no live group in this warp
+      const int u = rd * MSM_WSUM_GROUPS + (int)G;
+      const bool valid = u < ntask;
+      G1Pt e0, e1, s;
+      sw_set_identity(e0); sw_set_identity(e1);
+      const int off = level == 0 ? shift : 0;
+      const int i0 = 2 * u - off, i1 = 2 * u + 1 - off;
+      if (valid && i0 >= 0 && i0 + off < len) load_pt_cg(&e0, src + i0);
+      if (valid && i1 + off < len) load_pt_cg(&e1, src + i1);
+      g1_coop_add(&s, &e0, &e1);
+      if (ntask > 1) g1_coop_dbl(&s, &s);
+      g1_coop_add(&T, &T, &e1);
+      __syncwarp();
+      if (valid && g == 0) copy_words16(dst + u, &s);
+    }
+    __threadfence();
+    cluster.sync();
+    src = dst; dst = (dst == bufA) ? bufB : bufA;
+    len = ntask; level++;
+  }
+  if (g == 0) copy_words16(&Hs[G], &T);
+  __threadfence();
+  cluster.sync();
+  int live = 1; while (live < ntask0 && live < MSM_WSUM_GROUPS) live <<= 1;   // groups that can hold a non-trivial sum
+  for (int s = live >> 1; s > 0; s >>= 1) {
+    if ((int)(G & ~3u) < s) {
+      G1Pt a, b, z;
+      load_pt_cg(&a, &Hs[(int)G < s ? G : (unsigned)s]);
+      load_pt_cg(&b, &Hs[(int)G < s ? G + s : (unsigned)s]);
+      g1_coop_add(&z, &a, &b);
+      __syncwarp();
+      if ((int)G < s && g == 0) copy_words16(&Hs[G], &z);
+    }
+    __threadfence();
+    cluster.sync();
+  }
+  if (G < 4) {                                                 // the first warp of the cluster; group 0 writes
+    G1Pt z; load_pt_cg(&z, &Hs[0]);
+    for (int k = 0; k < post; k++) g1_coop_dbl(&z, &z);
+    __syncwarp();
+    if (G == 0 && g == 0) copy_words16(&parts[prob], &z);
+  }
+}
+
+// one warp per column: segment value = sum of its parts, Horner over the windows (stateless mode), output as in k_msm_final
+__global__ void __launch_bounds__(32) k_msm_final2(MsmPlan p, int nparts, const G1Pt* parts, uint8_t* out, int out_mode) {
+  const uint32_t col = blockIdx.x;
+  const G1Pt* W = parts + (size_t)col * p.seg_windows * nparts;
+  G1Pt acc; sw_set_identity(acc);
+  for (int w = p.seg_windows - 1; w >= 0; w--) {
+    if (w != p.seg_windows - 1) for (int k = 0; k < p.c; k++) g1_coop_dbl(&acc, &acc);
+    for (int j = 0; j < nparts; j++) { G1Pt q; copy_words16(&q, &W[(size_t)w * nparts + j]); g1_coop_add(&acc, &acc, &q); }
+  }
+  if (threadIdx.x != 0) return;
+  uint32_t raw[12];
+  if (out_mode == 1) {
+    uint8_t* o = out + (size_t)144 * col;
+    from_mont<BlsFq>(raw, acc.X); store_le<12>(o, raw);
+    from_mont<BlsFq>(raw, acc.Y); store_le<12>(o + 48, raw);
+    from_mont<BlsFq>(raw, acc.Z); store_le<12>(o + 96, raw);
+  } else {
+    uint8_t* o = out + (size_t)96 * col;
+    Fq381 zi = fq381_inv(acc.Z);                // identity: Z = 0 -> zi = 0 -> zeros
+    from_mont<BlsFq>(raw, acc.X * zi); store_le<12>(o, raw);
+    from_mont<BlsFq>(raw, acc.Y * zi); store_le<12>(o + 48, raw);
+  }
 }
 // combine the segments of a column (Horner over windows when not prepared);
 // out_mode 0: affine LE canonical (96 B, identity = zeros); 1: projective X,Y,Z LE canonical (144 B)

@@ -25,7 +25,8 @@ def best(f, reps=3):
     e.enable_kernel_timing(True)
     for _ in range(reps):
         t = time.perf_counter(); r = f(); ts.append(time.perf_counter() - t)
-    DEV["ms"] = sum(ms for _, ms in e.kernel_timings())
+    DEV["kt"] = e.kernel_timings()          # (kernel, ms) of the timed calls, summed per kernel name
+    DEV["ms"] = sum(ms for _, ms in DEV["kt"])
     e.enable_kernel_timing(False)
     return min(ts), r
 
@@ -64,15 +65,13 @@ bases_all = O.g1_mul_gen(ks)
 for logn in range(10, a.msm_max_logn + 1):
     m = 1 << logn
     sc = rng.integers(0, 256, size=(3 * m, 32), dtype=np.uint8); sc[:, 31] &= 0x3F
-    e.enable_kernel_timing(True)
     t, outp = best(lambda: e.msm_g1(bases_all[:m], sc, 3))
-    kt = e.kernel_timings(); e.enable_kernel_timing(False)
+    kt = DEV["kt"]
     if logn <= 12:
         assert np.array_equal(outp, O.msm_g1(bases_all[:m], sc, 3))
     h = e.msm_g1_prepare(bases_all[:m])
-    e.enable_kernel_timing(True)
     tp, outp2 = best(lambda: h.msm(sc, 3))
-    ktp = e.kernel_timings(); e.enable_kernel_timing(False)
+    ktp = DEV["kt"]
     h.release()
     assert np.array_equal(outp, outp2)
     res["msm_g1_3col_ms"]["2^%d" % logn] = {"stateless_wall_ms": round(t * 1e3, 3), "stateless_kernels_ms": {a_: round(b_, 3) for a_, b_ in kt},
