@@ -38,14 +38,15 @@ struct MsmPlan {
   uint32_t big;                  // buckets with more entries than this go to k_msm_accumulate_big
   int rc_h;                      // segment reduction: columns H of the R x H bucket matrix summed by k_msm_rc (0: nb <= 256, k_msm_wsum takes the buckets directly)
 };
-VRFS_HD inline MsmPlan msm_plan(uint32_t n, uint32_t ncol, int prepared) {
+VRFS_HD inline MsmPlan msm_plan(uint32_t n, uint32_t ncol, int prepared, int c_override = 0) {
   MsmPlan p; p.n = n; p.ncol = ncol; p.prepared = prepared;
   int lg = 0; while ((1u << (lg + 1)) <= n) lg++;
   // prepared mode: all windows of a column share one bucket set, so a short top window (255 mod c bits) piles n entries onto
   // 2^(255 mod c) buckets; the window sizes below keep that remainder at >= 5 bits (c = 12 and 14 left 3 bits: oversized
   // buckets cost 0.2-0.6 ms at 2^11..2^14)
-  if (prepared) p.c = lg <= 9 ? 8 : lg <= 11 ? 10 : lg <= 13 ? 13 : lg <= 14 ? 15 : 16;
+  if (prepared) p.c = lg <= 9 ? 8 : lg <= 12 ? 10 : lg <= 14 ? 13 : lg <= 17 ? 15 : 16;      // tools/msm_sweep.py, profiles/r1o_msm_sweep.json
   else p.c = lg <= 9 ? 7 : lg <= 11 ? 9 : lg <= 13 ? 11 : lg <= 15 ? 12 : 13;
+  if (c_override >= 2 && c_override <= 18) p.c = c_override;      // tuning runs only (VRFS_MSM_C / VRFS_MSM_C_STATELESS)
   p.windows = (255 + p.c) / p.c;          // 255 scalar bits + the top carry of the signed recoding
   p.nb = 1 << (p.c - 1);
   p.seg_windows = prepared ? 1 : p.windows;
@@ -61,6 +62,10 @@ VRFS_HD inline MsmPlan msm_plan(uint32_t n, uint32_t ncol, int prepared) {
   return p;
 }
 #define MSM_BIG_THREADS 128
+#define MSM_SLICE 256u           // an oversized bucket is cut into slices of about this many entries, one block each
+#define MSM_MAX_SLICES 256u
+// capacity of the slice list: buckets above p.big = 8 (avg + 8) entries number < buckets / 8
+VRFS_HD inline size_t msm_big_capacity(size_t nbuckets, size_t total_entries) { return nbuckets / 8 + total_entries / MSM_SLICE + 64; }
 
 HD_INLINE void g1_load_aff(G1Pt& P, const G1Aff* a, bool negate) {
   uint4* d = reinterpret_cast<uint4*>(&P);
@@ -183,215 +188,6 @@ HD_NOINLINE Fq381 fq381_inv(const Fq381& a) {
 }
 
 #ifdef __CUDACC__
-__global__ void __launch_bounds__(128) k_msm_prep_bases(uint32_t n, const uint8_t* bases, G1Aff* out) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint4* q = reinterpret_cast<const uint4*>(bases + (size_t)96 * i);
-  uint32_t rx[12], ry[12];
-  for (int j = 0; j < 3; j++) { uint4 a = q[j]; rx[4 * j] = a.x; rx[4 * j + 1] = a.y; rx[4 * j + 2] = a.z; rx[4 * j + 3] = a.w; }
-  for (int j = 0; j < 3; j++) { uint4 a = q[3 + j]; ry[4 * j] = a.x; ry[4 * j + 1] = a.y; ry[4 * j + 2] = a.z; ry[4 * j + 3] = a.w; }
-  G1Aff o;
-  o.x = to_mont<BlsFq>(rx); o.y = to_mont<BlsFq>(ry);
-  out[i] = o;
-}
-// prepared bases (the RingContext analogue: the SRS is fixed): Q[w*n + i] = 2^(c*w) * P_i, AFFINE (96 B; identity = zeros).
-// One thread per base: the doubling chain leaves projective points, whose Z's are inverted together (Montgomery's trick, one
-// binary-Euclid inversion per base).
-#define MSM_MAX_WINDOWS 33
-__global__ void __launch_bounds__(128) k_msm_prepare(uint32_t n, int c, int windows, const G1Aff* aff, G1Aff* Q) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  G1Pt P;
-  g1_load_aff(P, &aff[i], false);
-  Fq381 zs[MSM_MAX_WINDOWS], pre[MSM_MAX_WINDOWS];
-  unsigned long long infmask = 0;                                // windows whose point is the identity (Z = 0)
-  for (int w = 0; w < windows; w++) {
-    if (w) for (int k = 0; k < c; k++) g1_dbl(&P, &P);
-    G1Aff t; t.x = P.X; t.y = P.Y;                               // unnormalised for now
-    copy_words16(&Q[(size_t)w * n + i], &t);
-    const bool inf = P.Z.is_zero();
-    if (inf) infmask |= 1ull << w;
-    zs[w] = select(inf, Fq381::one(), P.Z);                      // an identity must not poison the product chain
-    pre[w] = w ? pre[w - 1] * zs[w] : zs[w];
-  }
-  Fq381 acc = fq381_inv(pre[windows - 1]);
-  for (int w = windows - 1; w >= 0; w--) {
-    Fq381 zi = w ? acc * pre[w - 1] : acc;
-    if (w) acc = acc * zs[w];
-    G1Aff t; copy_words16(&t, &Q[(size_t)w * n + i]);
-    t.x = t.x * zi; t.y = t.y * zi;
-    if ((infmask >> w) & 1ull) { t.x = Fq381::zero(); t.y = Fq381::zero(); }
-    copy_words16(&Q[(size_t)w * n + i], &t);
-  }
-}
-// counts[seg*nb + (|d|-1)]++ ; seg = col*seg_windows + (prepared ? 0 : w)
-__global__ void __launch_bounds__(128) k_msm_histogram(MsmPlan p, const uint8_t* scalars, uint32_t* counts) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= p.n * p.ncol) return;
-  uint32_t col = t / p.n;
-  uint32_t k[8];
-  msm_load_scalar(k, scalars + (size_t)32 * t);
-  int carry = 0;
-  for (int w = 0; w < p.windows; w++) {
-    int d = msm_digit(k, w, p.c, carry);
-    size_t seg = (size_t)col * p.seg_windows + (p.prepared ? 0 : w);
-    if (d != 0) atomicAdd(&counts[seg * p.nb + (d < 0 ? -d : d) - 1], 1u);
-  }
-}
-// one block per segment: exclusive scan of nb counts -> offsets (relative to the segment); also lists the big buckets
-__global__ void __launch_bounds__(256) k_msm_scan(MsmPlan p, const uint32_t* counts, uint32_t* offsets, uint32_t* big_list, uint32_t* big_count) {
-  __shared__ uint32_t part[256];
-  const uint32_t seg = blockIdx.x;
-  const uint32_t* c = counts + (size_t)seg * p.nb;
-  uint32_t* o = offsets + (size_t)seg * p.nb;
-  const int per = (p.nb + 255) / 256;
-  const int lo = threadIdx.x * per, hi = min(lo + per, p.nb);
-  uint32_t s = 0;
-  for (int i = lo; i < hi; i++) s += c[i];
-  part[threadIdx.x] = s;
-  __syncthreads();
-  if (threadIdx.x == 0) { uint32_t run = 0; for (int i = 0; i < 256; i++) { uint32_t v = part[i]; part[i] = run; run += v; } }
-  __syncthreads();
-  uint32_t run = part[threadIdx.x];
-  for (int i = lo; i < hi; i++) {
-    o[i] = run; run += c[i];
-    if (c[i] > p.big) big_list[atomicAdd(big_count, 1u)] = seg * p.nb + i;
-  }
-}
-// list[seg*seg_len + offsets[bucket] + pos] = point index | sign << 31
-__global__ void __launch_bounds__(128) k_msm_scatter(MsmPlan p, const uint8_t* scalars, const uint32_t* offsets, uint32_t* cursors, uint32_t* list) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= p.n * p.ncol) return;
-  uint32_t col = t / p.n, i = t % p.n;
-  uint32_t k[8];
-  msm_load_scalar(k, scalars + (size_t)32 * t);
-  const size_t seg_len = (size_t)p.n * (p.prepared ? p.windows : 1);
-  int carry = 0;
-  for (int w = 0; w < p.windows; w++) {
-    int d = msm_digit(k, w, p.c, carry);
-    if (d == 0) continue;
-    size_t seg = (size_t)col * p.seg_windows + (p.prepared ? 0 : w);
-    size_t b = seg * p.nb + (d < 0 ? -d : d) - 1;
-    uint32_t pos = atomicAdd(&cursors[b], 1u);
-    uint32_t idx = p.prepared ? (uint32_t)w * p.n + i : i;
-    list[seg * seg_len + offsets[b] + pos] = idx | (d < 0 ? 0x80000000u : 0u);
-  }
-}
-// every table record is affine: the caller's bases (stateless) or the prepared 2^(c w) P_i
-__device__ __forceinline__ void msm_accumulate_entries(G1Pt& out, const void* bases, const uint32_t* l, uint32_t first, uint32_t cnt, uint32_t step) {
-  const G1Aff* tab = reinterpret_cast<const G1Aff*>(bases);
-  G1Xyzz acc; xyzz_set_identity(acc);
-  for (uint32_t j = first; j < cnt; j += step) {
-    const uint32_t e = l[j];
-    Fq381 x, y;
-    const bool finite = g1_load_aff_xy(x, y, tab + (e & 0x7fffffffu), (e >> 31) != 0);
-    if (j + step < cnt) prefetch_l1(tab + (l[j + step] & 0x7fffffffu), (unsigned)sizeof(G1Aff));   // a random 96-byte record of a table far larger than L2
-    if (finite) xyzz_madd(&acc, &x, &y);
-  }
-  xyzz_to_proj(out, acc);
-}
-// p.tpb threads per bucket (strided over its entries, shared-memory tree inside the group); buckets above p.big
-// entries are left to k_msm_accumulate_big
-#ifndef MSM_ACC_MINBLOCKS
-#define MSM_ACC_MINBLOCKS 4   // 128 registers: 16 warps/SM instead of 8 (measured 4.59 -> 4.17 ms at 2^17 x 3)
-#endif
-template <bool PREP>
-__global__ void __launch_bounds__(128, MSM_ACC_MINBLOCKS) k_msm_accumulate(MsmPlan p, const void* bases, const uint32_t* counts, const uint32_t* offsets,
-                                                         const uint32_t* list, G1Pt* buckets) {
-  __shared__ uint4 sh_raw[128 * sizeof(G1Pt) / 16];
-  G1Pt* sh = reinterpret_cast<G1Pt*>(sh_raw);
-  const size_t total = (size_t)p.ncol * p.seg_windows * p.nb;
-  const uint32_t lane = threadIdx.x % p.tpb;
-  const size_t b = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) / p.tpb;
-  const bool live = b < total;
-  uint32_t cnt = live ? counts[b] : 0u;
-  if (cnt > p.big) cnt = 0;                       // handled by the big path (which also writes the bucket)
-  G1Pt acc; sw_set_identity(acc);
-  if (cnt) {
-    const size_t seg = b / p.nb;
-    const size_t seg_len = (size_t)p.n * (p.prepared ? p.windows : 1);
-    const uint32_t* l = list + seg * seg_len + offsets[b];
-    msm_accumulate_entries(acc, bases, l, lane, cnt, (uint32_t)p.tpb);
-  }
-  if (p.tpb > 1) {
-    copy_words16(&sh[threadIdx.x], &acc);
-    __syncthreads();
-    for (int stride = p.tpb >> 1; stride > 0; stride >>= 1) {
-      if ((int)lane < stride) { G1Pt y; copy_words16(&y, &sh[threadIdx.x + stride]); sw_add<G1Curve>(&acc, &acc, &y); copy_words16(&sh[threadIdx.x], &acc); }
-      __syncthreads();
-    }
-  }
-  if (live && lane == 0 && counts[b] <= p.big) copy_words16(&buckets[b], &acc);
-}
-// one block per big bucket: strided partial sums + shared-memory tree
-template <bool PREP>
-__global__ void __launch_bounds__(MSM_BIG_THREADS) k_msm_accumulate_big(MsmPlan p, const void* bases, const uint32_t* counts, const uint32_t* offsets,
-                                                                         const uint32_t* list, const uint32_t* big_list, const uint32_t* big_count, G1Pt* buckets) {
-  __shared__ uint4 sh_raw[MSM_BIG_THREADS * sizeof(G1Pt) / 16];
-  G1Pt* sh = reinterpret_cast<G1Pt*>(sh_raw);
-  const uint32_t nbig = *big_count;
-  for (uint32_t bi = blockIdx.x; bi < nbig; bi += gridDim.x) {
-    const size_t b = big_list[bi];
-    const size_t seg = b / p.nb;
-    const size_t seg_len = (size_t)p.n * (p.prepared ? p.windows : 1);
-    const uint32_t* l = list + seg * seg_len + offsets[b];
-    const uint32_t cnt = counts[b];
-    G1Pt acc;
-    msm_accumulate_entries(acc, bases, l, threadIdx.x, cnt, MSM_BIG_THREADS);
-    copy_words16(&sh[threadIdx.x], &acc);
-    __syncthreads();
-    for (int stride = MSM_BIG_THREADS >> 1; stride > 0; stride >>= 1) {
-      if ((int)threadIdx.x < stride) { G1Pt x, y; copy_words16(&x, &sh[threadIdx.x]); copy_words16(&y, &sh[threadIdx.x + stride]); sw_add<G1Curve>(&x, &x, &y); copy_words16(&sh[threadIdx.x], &x); }
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) copy_words16(&buckets[b], &sh[0]);
-    __syncthreads();
-  }
-}
-// r = k * p for a small non-negative k (double-and-add, MSB first)
-__device__ __forceinline__ void g1_mul_small(G1Pt& r, const G1Pt& p, uint32_t k) {
-  sw_set_identity(r);
-  for (int bit = 31 - __clz(k | 1u); bit >= 0; bit--) {
-    g1_dbl(&r, &r);
-    if ((k >> bit) & 1u) sw_add<G1Curve>(&r, &r, &p);
-  }
-}
-// segment sum = sum_{j=1..nb} j * B_j in two stages.  Stage 1: one thread per chunk of p.chunk buckets (running sums),
-// partial[seg][t] = sum over its chunk of j * B_j.  Stage 2: one block per segment tree-sums the nb / chunk partials.
-__global__ void __launch_bounds__(128) k_msm_window_chunks(MsmPlan p, const G1Pt* buckets, G1Pt* partials) {
-  const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t per_seg = p.nb / p.chunk;
-  const size_t segs = (size_t)p.ncol * p.seg_windows;
-  if (g >= segs * per_seg) return;
-  const size_t seg = g / per_seg;
-  const uint32_t t = (uint32_t)(g % per_seg);
-  const G1Pt* B = buckets + seg * p.nb;
-  const int lo = t * p.chunk;              // bucket index j-1 in [lo, lo + chunk)
-  G1Pt run, tot; sw_set_identity(run); sw_set_identity(tot);
-  for (int j = lo + p.chunk - 1; j >= lo; j--) {
-    G1Pt q; copy_words16(&q, &B[j]);
-    sw_add<G1Curve>(&run, &run, &q);
-    sw_add<G1Curve>(&tot, &tot, &run);
-  }
-  // tot = sum (j - lo + 1) * B_j (bucket value j+1 at index j)  ->  add lo * run
-  if (lo > 0) { G1Pt m; g1_mul_small(m, run, (uint32_t)lo); sw_add<G1Curve>(&tot, &tot, &m); }
-  copy_words16(&partials[g], &tot);
-}
-__global__ void __launch_bounds__(256) k_msm_window_sum(MsmPlan p, const G1Pt* partials, G1Pt* window_sums) {
-  __shared__ uint4 sh_raw[256 * sizeof(G1Pt) / 16];
-  G1Pt* sh = reinterpret_cast<G1Pt*>(sh_raw);
-  const uint32_t seg = blockIdx.x, t = threadIdx.x, per_seg = p.nb / p.chunk;
-  const G1Pt* P = partials + (size_t)seg * per_seg;
-  G1Pt acc; sw_set_identity(acc);
-  for (uint32_t j = t; j < per_seg; j += 256) { G1Pt q; copy_words16(&q, &P[j]); sw_add<G1Curve>(&acc, &acc, &q); }
-  copy_words16(&sh[t], &acc);
-  __syncthreads();
-  for (int stride = 128; stride > 0; stride >>= 1) {
-    if ((int)t < stride) { G1Pt y; copy_words16(&y, &sh[t + stride]); sw_add<G1Curve>(&acc, &acc, &y); copy_words16(&sh[t], &acc); }
-    __syncthreads();
-  }
-  if (t == 0) copy_words16(&window_sums[seg], &sh[0]);
-}
 // =================================================================================================
 // Segment reduction, second generation (MSM_TAIL = 2, the default): everything after the bucket sums is a chain of
 // DEPENDENT point additions on very few points, and one thread needs ~11 us per complete addition (12 products of
@@ -476,6 +272,259 @@ __device__ __noinline__ void g1_coop_dbl(G1Pt* r, const G1Pt* p) {
   r->Z = fq_shfl(t, base + 1);
 }
 
+// sh[0] = sum of sh[0 .. width) (width a power of two <= blockDim.x = 128, entries already stored and the block synchronised):
+// one thread per addition while more than 16 remain, then groups of 8 lanes per addition
+__device__ __forceinline__ void block_tree_sum(G1Pt* sh, int width) {
+  const unsigned t = threadIdx.x;
+  for (int s = width >> 1; s > 16; s >>= 1) {
+    if ((int)t < s) { G1Pt x, y; copy_words16(&x, &sh[t]); copy_words16(&y, &sh[t + s]); sw_add<G1Curve>(&x, &x, &y); copy_words16(&sh[t], &x); }
+    __syncthreads();
+  }
+  const unsigned grp = t >> 3, g = t & 7u;                      // 16 groups of 8 lanes
+  for (int s = min(width >> 1, 16); s > 0; s >>= 1) {
+    if ((int)(grp & ~3u) < s) {                                 // warp-uniform: the warp holds a live group
+      G1Pt x, y, z;
+      copy_words16(&x, &sh[(int)grp < s ? grp : (unsigned)s]);            // idle groups of a live warp read what nobody writes
+      copy_words16(&y, &sh[(int)grp < s ? grp + s : (unsigned)s]);
+      g1_coop_add(&z, &x, &y);
+      __syncwarp();
+      if ((int)grp < s && g == 0) copy_words16(&sh[grp], &z);
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(128) k_msm_prep_bases(uint32_t n, const uint8_t* bases, G1Aff* out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint4* q = reinterpret_cast<const uint4*>(bases + (size_t)96 * i);
+  uint32_t rx[12], ry[12];
+  for (int j = 0; j < 3; j++) { uint4 a = q[j]; rx[4 * j] = a.x; rx[4 * j + 1] = a.y; rx[4 * j + 2] = a.z; rx[4 * j + 3] = a.w; }
+  for (int j = 0; j < 3; j++) { uint4 a = q[3 + j]; ry[4 * j] = a.x; ry[4 * j + 1] = a.y; ry[4 * j + 2] = a.z; ry[4 * j + 3] = a.w; }
+  G1Aff o;
+  o.x = to_mont<BlsFq>(rx); o.y = to_mont<BlsFq>(ry);
+  out[i] = o;
+}
+// prepared bases (the RingContext analogue: the SRS is fixed): Q[w*n + i] = 2^(c*w) * P_i, AFFINE (96 B; identity = zeros).
+// One thread per base: the doubling chain leaves projective points, whose Z's are inverted together (Montgomery's trick, one
+// binary-Euclid inversion per base).
+#define MSM_MAX_WINDOWS 33
+__global__ void __launch_bounds__(128) k_msm_prepare(uint32_t n, int c, int windows, const G1Aff* aff, G1Aff* Q) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  G1Pt P;
+  g1_load_aff(P, &aff[i], false);
+  Fq381 zs[MSM_MAX_WINDOWS], pre[MSM_MAX_WINDOWS];
+  unsigned long long infmask = 0;                                // windows whose point is the identity (Z = 0)
+  for (int w = 0; w < windows; w++) {
+    if (w) for (int k = 0; k < c; k++) g1_dbl(&P, &P);
+    G1Aff t; t.x = P.X; t.y = P.Y;                               // unnormalised for now
+    copy_words16(&Q[(size_t)w * n + i], &t);
+    const bool inf = P.Z.is_zero();
+    if (inf) infmask |= 1ull << w;
+    zs[w] = select(inf, Fq381::one(), P.Z);                      // an identity must not poison the product chain
+    pre[w] = w ? pre[w - 1] * zs[w] : zs[w];
+  }
+  Fq381 acc = fq381_inv(pre[windows - 1]);
+  for (int w = windows - 1; w >= 0; w--) {
+    Fq381 zi = w ? acc * pre[w - 1] : acc;
+    if (w) acc = acc * zs[w];
+    G1Aff t; copy_words16(&t, &Q[(size_t)w * n + i]);
+    t.x = t.x * zi; t.y = t.y * zi;
+    if ((infmask >> w) & 1ull) { t.x = Fq381::zero(); t.y = Fq381::zero(); }
+    copy_words16(&Q[(size_t)w * n + i], &t);
+  }
+}
+// counts[seg*nb + (|d|-1)]++ ; seg = col*seg_windows + (prepared ? 0 : w)
+__global__ void __launch_bounds__(128) k_msm_histogram(MsmPlan p, const uint8_t* scalars, uint32_t* counts) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= p.n * p.ncol) return;
+  uint32_t col = t / p.n;
+  uint32_t k[8];
+  msm_load_scalar(k, scalars + (size_t)32 * t);
+  int carry = 0;
+  for (int w = 0; w < p.windows; w++) {
+    int d = msm_digit(k, w, p.c, carry);
+    size_t seg = (size_t)col * p.seg_windows + (p.prepared ? 0 : w);
+    if (d != 0) atomicAdd(&counts[seg * p.nb + (d < 0 ? -d : d) - 1], 1u);
+  }
+}
+// one block per segment: exclusive scan of nb counts -> offsets (relative to the segment); also lists the big buckets
+__global__ void __launch_bounds__(256) k_msm_scan(MsmPlan p, const uint32_t* counts, uint32_t* offsets, uint32_t* big_list, uint32_t* big_count) {
+  __shared__ uint32_t part[256];
+  const uint32_t seg = blockIdx.x;
+  const uint32_t* c = counts + (size_t)seg * p.nb;
+  uint32_t* o = offsets + (size_t)seg * p.nb;
+  const int per = (p.nb + 255) / 256;
+  const int lo = threadIdx.x * per, hi = min(lo + per, p.nb);
+  uint32_t s = 0;
+  for (int i = lo; i < hi; i++) s += c[i];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) { uint32_t run = 0; for (int i = 0; i < 256; i++) { uint32_t v = part[i]; part[i] = run; run += v; } }
+  __syncthreads();
+  uint32_t run = part[threadIdx.x];
+  for (int i = lo; i < hi; i++) {
+    o[i] = run; run += c[i];
+    if (c[i] > p.big) {                                       // one work item per slice of ~MSM_SLICE entries
+      const uint32_t nsl = min((uint32_t)MSM_MAX_SLICES, (c[i] + MSM_SLICE - 1) / MSM_SLICE);
+      const uint32_t first = atomicAdd(big_count, nsl);
+      for (uint32_t sl = 0; sl < nsl; sl++) { big_list[2 * (first + sl)] = seg * p.nb + i; big_list[2 * (first + sl) + 1] = sl | (nsl << 16); }
+    }
+  }
+}
+// list[seg*seg_len + offsets[bucket] + pos] = point index | sign << 31
+__global__ void __launch_bounds__(128) k_msm_scatter(MsmPlan p, const uint8_t* scalars, const uint32_t* offsets, uint32_t* cursors, uint32_t* list) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= p.n * p.ncol) return;
+  uint32_t col = t / p.n, i = t % p.n;
+  uint32_t k[8];
+  msm_load_scalar(k, scalars + (size_t)32 * t);
+  const size_t seg_len = (size_t)p.n * (p.prepared ? p.windows : 1);
+  int carry = 0;
+  for (int w = 0; w < p.windows; w++) {
+    int d = msm_digit(k, w, p.c, carry);
+    if (d == 0) continue;
+    size_t seg = (size_t)col * p.seg_windows + (p.prepared ? 0 : w);
+    size_t b = seg * p.nb + (d < 0 ? -d : d) - 1;
+    uint32_t pos = atomicAdd(&cursors[b], 1u);
+    uint32_t idx = p.prepared ? (uint32_t)w * p.n + i : i;
+    list[seg * seg_len + offsets[b] + pos] = idx | (d < 0 ? 0x80000000u : 0u);
+  }
+}
+// every table record is affine: the caller's bases (stateless) or the prepared 2^(c w) P_i
+__device__ __forceinline__ void msm_accumulate_entries(G1Pt& out, const void* bases, const uint32_t* l, uint32_t first, uint32_t cnt, uint32_t step) {
+  const G1Aff* tab = reinterpret_cast<const G1Aff*>(bases);
+  G1Xyzz acc; xyzz_set_identity(acc);
+  for (uint32_t j = first; j < cnt; j += step) {
+    const uint32_t e = l[j];
+    Fq381 x, y;
+    const bool finite = g1_load_aff_xy(x, y, tab + (e & 0x7fffffffu), (e >> 31) != 0);
+    if (j + step < cnt) prefetch_l1(tab + (l[j + step] & 0x7fffffffu), (unsigned)sizeof(G1Aff));   // a random 96-byte record of a table far larger than L2
+    if (finite) xyzz_madd(&acc, &x, &y);
+  }
+  xyzz_to_proj(out, acc);
+}
+// p.tpb threads per bucket (strided over its entries, shared-memory tree inside the group); buckets above p.big
+// entries are left to k_msm_accumulate_big
+#ifndef MSM_ACC_MINBLOCKS
+#define MSM_ACC_MINBLOCKS 4   // 128 registers: 16 warps/SM instead of 8 (measured 4.59 -> 4.17 ms at 2^17 x 3)
+#endif
+template <bool PREP>
+__global__ void __launch_bounds__(128, MSM_ACC_MINBLOCKS) k_msm_accumulate(MsmPlan p, const void* bases, const uint32_t* counts, const uint32_t* offsets,
+                                                         const uint32_t* list, G1Pt* buckets) {
+  __shared__ uint4 sh_raw[128 * sizeof(G1Pt) / 16];
+  G1Pt* sh = reinterpret_cast<G1Pt*>(sh_raw);
+  const size_t total = (size_t)p.ncol * p.seg_windows * p.nb;
+  const uint32_t lane = threadIdx.x % p.tpb;
+  const size_t b = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) / p.tpb;
+  const bool live = b < total;
+  uint32_t cnt = live ? counts[b] : 0u;
+  if (cnt > p.big) cnt = 0;                       // handled by the big path (which also writes the bucket)
+  G1Pt acc; sw_set_identity(acc);
+  if (cnt) {
+    const size_t seg = b / p.nb;
+    const size_t seg_len = (size_t)p.n * (p.prepared ? p.windows : 1);
+    const uint32_t* l = list + seg * seg_len + offsets[b];
+    msm_accumulate_entries(acc, bases, l, lane, cnt, (uint32_t)p.tpb);
+  }
+  if (p.tpb > 1) {
+    copy_words16(&sh[threadIdx.x], &acc);
+    __syncthreads();
+    for (int stride = p.tpb >> 1; stride > 0; stride >>= 1) {
+      if ((int)lane < stride) { G1Pt y; copy_words16(&y, &sh[threadIdx.x + stride]); sw_add<G1Curve>(&acc, &acc, &y); copy_words16(&sh[threadIdx.x], &acc); }
+      __syncthreads();
+    }
+  }
+  if (live && lane == 0 && counts[b] <= p.big) copy_words16(&buckets[b], &acc);
+}
+// one block per slice of an oversized bucket: strided partial sums + shared-memory tree -> bigpart[slice];
+// k_msm_big_combine then adds the slices of each bucket.  (A ring's 0/1 selector column puts half the domain into ONE bucket:
+// a single block needed 4.8 ms for it at N = 2^17.)
+template <bool PREP>
+__global__ void __launch_bounds__(MSM_BIG_THREADS) k_msm_accumulate_big(MsmPlan p, const void* bases, const uint32_t* counts, const uint32_t* offsets,
+                                                                         const uint32_t* list, const uint32_t* big_list, const uint32_t* big_count, G1Pt* bigpart) {
+  __shared__ uint4 sh_raw[MSM_BIG_THREADS * sizeof(G1Pt) / 16];
+  G1Pt* sh = reinterpret_cast<G1Pt*>(sh_raw);
+  const uint32_t nbig = *big_count;
+  for (uint32_t bi = blockIdx.x; bi < nbig; bi += gridDim.x) {
+    const size_t b = big_list[2 * bi];
+    const uint32_t sl = big_list[2 * bi + 1] & 0xffffu, nsl = big_list[2 * bi + 1] >> 16;
+    const size_t seg = b / p.nb;
+    const size_t seg_len = (size_t)p.n * (p.prepared ? p.windows : 1);
+    const uint32_t cnt = counts[b];
+    const uint32_t lo = (uint32_t)(((uint64_t)cnt * sl) / nsl), hi = (uint32_t)(((uint64_t)cnt * (sl + 1)) / nsl);
+    const uint32_t* l = list + seg * seg_len + offsets[b] + lo;
+    G1Pt acc;
+    msm_accumulate_entries(acc, bases, l, threadIdx.x, hi - lo, MSM_BIG_THREADS);
+    copy_words16(&sh[threadIdx.x], &acc);
+    __syncthreads();
+    block_tree_sum(sh, MSM_BIG_THREADS);
+    if (threadIdx.x == 0) copy_words16(&bigpart[bi], &sh[0]);
+    __syncthreads();
+  }
+}
+__global__ void __launch_bounds__(MSM_BIG_THREADS) k_msm_big_combine(const uint32_t* big_list, const uint32_t* big_count, const G1Pt* bigpart, G1Pt* buckets) {
+  __shared__ uint4 sh_raw[MSM_BIG_THREADS * sizeof(G1Pt) / 16];
+  G1Pt* sh = reinterpret_cast<G1Pt*>(sh_raw);
+  const uint32_t nbig = *big_count;
+  for (uint32_t bi = blockIdx.x; bi < nbig; bi += gridDim.x) {
+    if ((big_list[2 * bi + 1] & 0xffffu) != 0) continue;        // block-uniform: only the first slice of a bucket leads
+    const uint32_t nsl = big_list[2 * bi + 1] >> 16;
+    G1Pt acc; sw_set_identity(acc);
+    for (uint32_t j = threadIdx.x; j < nsl; j += MSM_BIG_THREADS) { G1Pt q; copy_words16(&q, &bigpart[bi + j]); sw_add<G1Curve>(&acc, &acc, &q); }
+    copy_words16(&sh[threadIdx.x], &acc);
+    __syncthreads();
+    int width = MSM_BIG_THREADS; while (width / 2 >= (int)nsl) width /= 2;
+    block_tree_sum(sh, width);
+    if (threadIdx.x == 0) copy_words16(&buckets[big_list[2 * bi]], &sh[0]);
+    __syncthreads();
+  }
+}
+// r = k * p for a small non-negative k (double-and-add, MSB first)
+__device__ __forceinline__ void g1_mul_small(G1Pt& r, const G1Pt& p, uint32_t k) {
+  sw_set_identity(r);
+  for (int bit = 31 - __clz(k | 1u); bit >= 0; bit--) {
+    g1_dbl(&r, &r);
+    if ((k >> bit) & 1u) sw_add<G1Curve>(&r, &r, &p);
+  }
+}
+// segment sum = sum_{j=1..nb} j * B_j in two stages.  Stage 1: one thread per chunk of p.chunk buckets (running sums),
+// partial[seg][t] = sum over its chunk of j * B_j.  Stage 2: one block per segment tree-sums the nb / chunk partials.
+__global__ void __launch_bounds__(128) k_msm_window_chunks(MsmPlan p, const G1Pt* buckets, G1Pt* partials) {
+  const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t per_seg = p.nb / p.chunk;
+  const size_t segs = (size_t)p.ncol * p.seg_windows;
+  if (g >= segs * per_seg) return;
+  const size_t seg = g / per_seg;
+  const uint32_t t = (uint32_t)(g % per_seg);
+  const G1Pt* B = buckets + seg * p.nb;
+  const int lo = t * p.chunk;              // bucket index j-1 in [lo, lo + chunk)
+  G1Pt run, tot; sw_set_identity(run); sw_set_identity(tot);
+  for (int j = lo + p.chunk - 1; j >= lo; j--) {
+    G1Pt q; copy_words16(&q, &B[j]);
+    sw_add<G1Curve>(&run, &run, &q);
+    sw_add<G1Curve>(&tot, &tot, &run);
+  }
+  // tot = sum (j - lo + 1) * B_j (bucket value j+1 at index j)  ->  add lo * run
+  if (lo > 0) { G1Pt m; g1_mul_small(m, run, (uint32_t)lo); sw_add<G1Curve>(&tot, &tot, &m); }
+  copy_words16(&partials[g], &tot);
+}
+__global__ void __launch_bounds__(256) k_msm_window_sum(MsmPlan p, const G1Pt* partials, G1Pt* window_sums) {
+  __shared__ uint4 sh_raw[256 * sizeof(G1Pt) / 16];
+  G1Pt* sh = reinterpret_cast<G1Pt*>(sh_raw);
+  const uint32_t seg = blockIdx.x, t = threadIdx.x, per_seg = p.nb / p.chunk;
+  const G1Pt* P = partials + (size_t)seg * per_seg;
+  G1Pt acc; sw_set_identity(acc);
+  for (uint32_t j = t; j < per_seg; j += 256) { G1Pt q; copy_words16(&q, &P[j]); sw_add<G1Curve>(&acc, &acc, &q); }
+  copy_words16(&sh[t], &acc);
+  __syncthreads();
+  for (int stride = 128; stride > 0; stride >>= 1) {
+    if ((int)t < stride) { G1Pt y; copy_words16(&y, &sh[t + stride]); sw_add<G1Curve>(&acc, &acc, &y); copy_words16(&sh[t], &acc); }
+    __syncthreads();
+  }
+  if (t == 0) copy_words16(&window_sums[seg], &sh[0]);
+}
 // row and column sums of the bucket matrix of every segment: out[seg][hi] = sum_lo B[hi*H + lo] (hi < R = nb / H),
 // out[seg][R + lo] = sum_hi B[hi*H + lo].  One block per sum; the last five tree levels (<= 16 additions) are cooperative.
 __global__ void __launch_bounds__(128) k_msm_rc(MsmPlan p, const G1Pt* buckets, G1Pt* out) {
@@ -493,22 +542,7 @@ __global__ void __launch_bounds__(128) k_msm_rc(MsmPlan p, const G1Pt* buckets, 
   copy_words16(&sh[t], &acc);
   __syncthreads();
   int width = 128; while (width / 2 >= count) width /= 2;       // live entries of sh (power of two >= min(count, 128))
-  for (int s = width >> 1; s > 16; s >>= 1) {
-    if ((int)t < s) { G1Pt y; copy_words16(&y, &sh[t + s]); sw_add<G1Curve>(&acc, &acc, &y); copy_words16(&sh[t], &acc); }
-    __syncthreads();
-  }
-  const unsigned grp = t >> 3, g = t & 7u;                      // 16 groups of 8 lanes
-  for (int s = min(width >> 1, 16); s > 0; s >>= 1) {
-    if ((int)(grp & ~3u) < s) {                                 // warp-uniform: the warp holds a live group
-      G1Pt x, y, z;
-      copy_words16(&x, &sh[(int)grp < s ? grp : (unsigned)s]);            // idle groups of a live warp read what nobody writes
-      copy_words16(&y, &sh[(int)grp < s ? grp + s : (unsigned)s]);
-      g1_coop_add(&z, &x, &y);
-      __syncwarp();
-      if ((int)grp < s && g == 0) copy_words16(&sh[grp], &z);
-    }
-    __syncthreads();
-  }
+  block_tree_sum(sh, width);
   if (t == 0) copy_words16(&out[(size_t)seg * (R + H) + o], &sh[0]);
 }
 

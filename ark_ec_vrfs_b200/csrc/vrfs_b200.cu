@@ -4,6 +4,8 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdint.h>
+#include <stdlib.h>
 #include <mutex>
 #include <new>
 
@@ -1301,13 +1303,21 @@ struct vrfs_msm_bases {
   void* Q;          // windows * n affine points (96 B each; identity = zeros)
 };
 // bases: G1Aff[n] (stateless) or the prepared table Q; scalars on the device
+static int msm_c_override(int prepared) {
+  const char* e = getenv(prepared ? "VRFS_MSM_C" : "VRFS_MSM_C_STATELESS");
+  return e ? atoi(e) : 0;
+}
 static vrfs_status msm_dev(vrfs_ctx* ctx, MsmPlan p, const void* d_bases, const uint8_t* d_scalars, uint8_t* d_out, int out_mode) {
   const size_t n = p.n, ncol = p.ncol;
   const size_t segs = ncol * p.seg_windows, nbuckets = segs * p.nb, seg_len = n * (p.prepared ? p.windows : 1);
   const size_t per_seg = p.nb / p.chunk;
   void *counts = nullptr, *list = nullptr, *buckets = nullptr, *wsum = nullptr;
-  ST(ensure(ctx, BUF_W1, (nbuckets * 4 + 16) * sizeof(uint32_t), &counts));
-  uint32_t *offsets = (uint32_t*)counts + nbuckets, *cursors = offsets + nbuckets, *big_list = cursors + nbuckets, *big_count = big_list + nbuckets;
+  // counts | offsets | cursors | big_count (16 words) | slice list of the oversized buckets (2 words per slice) ; partial sums of the slices
+  const size_t bigcap = msm_big_capacity(nbuckets, segs * seg_len);
+  const size_t w1_words = nbuckets * 3 + 16 + 2 * bigcap;
+  ST(ensure(ctx, BUF_W1, w1_words * sizeof(uint32_t) + 16 + bigcap * sizeof(G1Pt), &counts));
+  uint32_t *offsets = (uint32_t*)counts + nbuckets, *cursors = offsets + nbuckets, *big_count = cursors + nbuckets, *big_list = big_count + 16;
+  G1Pt* bigpart = (G1Pt*)(((uintptr_t)((uint32_t*)counts + w1_words) + 15) & ~(uintptr_t)15);
   ST(ensure(ctx, BUF_W2, segs * seg_len * sizeof(uint32_t), &list));
   ST(ensure(ctx, BUF_W3, nbuckets * sizeof(G1Pt), &buckets));
 #if MSM_TAIL == 1
@@ -1321,7 +1331,7 @@ static vrfs_status msm_dev(vrfs_ctx* ctx, MsmPlan p, const void* d_bases, const 
   G1Pt* rc_out = (G1Pt*)wsum + segs * nparts;
   G1Pt* wscratch = rc_out + segs * rc_len;
 #endif
-  CU(cudaMemsetAsync(counts, 0, (nbuckets * 4 + 16) * sizeof(uint32_t), ctx->stream));
+  CU(cudaMemsetAsync(counts, 0, (nbuckets * 3 + 16) * sizeof(uint32_t), ctx->stream));
   const unsigned tsc = (unsigned)((n * ncol + 127) / 128);
   k_msm_histogram<<<tsc, 128, 0, ctx->stream>>>(p, d_scalars, (uint32_t*)counts);
   LAUNCHED_AS(ctx, "msm_histogram");
@@ -1334,13 +1344,15 @@ static vrfs_status msm_dev(vrfs_ctx* ctx, MsmPlan p, const void* d_bases, const 
   if (p.prepared) {
     k_msm_accumulate<true><<<ab, 128, 0, ctx->stream>>>(p, d_bases, (const uint32_t*)counts, offsets, (const uint32_t*)list, (G1Pt*)buckets);
     LAUNCHED_AS(ctx, "msm_accumulate");
-    k_msm_accumulate_big<true><<<bigb, MSM_BIG_THREADS, 0, ctx->stream>>>(p, d_bases, (const uint32_t*)counts, offsets, (const uint32_t*)list, big_list, big_count, (G1Pt*)buckets);
+    k_msm_accumulate_big<true><<<bigb, MSM_BIG_THREADS, 0, ctx->stream>>>(p, d_bases, (const uint32_t*)counts, offsets, (const uint32_t*)list, big_list, big_count, bigpart);
   } else {
     k_msm_accumulate<false><<<ab, 128, 0, ctx->stream>>>(p, d_bases, (const uint32_t*)counts, offsets, (const uint32_t*)list, (G1Pt*)buckets);
     LAUNCHED_AS(ctx, "msm_accumulate");
-    k_msm_accumulate_big<false><<<bigb, MSM_BIG_THREADS, 0, ctx->stream>>>(p, d_bases, (const uint32_t*)counts, offsets, (const uint32_t*)list, big_list, big_count, (G1Pt*)buckets);
+    k_msm_accumulate_big<false><<<bigb, MSM_BIG_THREADS, 0, ctx->stream>>>(p, d_bases, (const uint32_t*)counts, offsets, (const uint32_t*)list, big_list, big_count, bigpart);
   }
   LAUNCHED_AS(ctx, "msm_accumulate_big");
+  k_msm_big_combine<<<bigb, MSM_BIG_THREADS, 0, ctx->stream>>>(big_list, big_count, bigpart, (G1Pt*)buckets);
+  LAUNCHED_AS(ctx, "msm_big_combine");
 #if MSM_TAIL == 1
   k_msm_window_chunks<<<(unsigned)((segs * per_seg + 127) / 128), 128, 0, ctx->stream>>>(p, (const G1Pt*)buckets, partials);
   LAUNCHED_AS(ctx, "msm_window_chunks");
@@ -1380,7 +1392,7 @@ static vrfs_status msm_host(vrfs_ctx* ctx, size_t n, const uint8_t* bases, const
   ST(ensure(ctx, BUF_W0, n * sizeof(G1Aff), &bases_m));
   k_msm_prep_bases<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((uint32_t)n, d_b, (G1Aff*)bases_m);
   LAUNCHED_AS(ctx, "msm_prep_bases");
-  ST(msm_dev(ctx, msm_plan((uint32_t)n, (uint32_t)ncol, 0), bases_m, d_s, d_o, out_mode));
+  ST(msm_dev(ctx, msm_plan((uint32_t)n, (uint32_t)ncol, 0, msm_c_override(0)), bases_m, d_s, d_o, out_mode));
   ST(copy_out(ctx, out, d_o, ob * ncol));
   return finish_call(ctx);
 }
@@ -1399,7 +1411,7 @@ extern "C" vrfs_status vrfs_msm_g1_prepare(vrfs_ctx* ctx, size_t n, const uint8_
   ST(begin_call(ctx, n));
   vrfs_msm_bases* h = new (std::nothrow) vrfs_msm_bases();
   if (!h) return fail(ctx, VRFS_CUDA_ERROR, "out of host memory");
-  h->ctx = ctx; h->n = n; h->plan = msm_plan((uint32_t)n, 1, 1); h->Q = nullptr;
+  h->ctx = ctx; h->n = n; h->plan = msm_plan((uint32_t)n, 1, 1, msm_c_override(1)); h->Q = nullptr;
   cudaError_t e = cudaMalloc(&h->Q, (size_t)h->plan.windows * n * sizeof(G1Aff));
   if (e != cudaSuccess) { delete h; return fail(ctx, VRFS_CUDA_ERROR, "cudaMalloc of the prepared table failed: %s", cudaGetErrorString(e)); }
   *out = h;
@@ -1429,7 +1441,7 @@ static vrfs_status msm_prepared_host(vrfs_ctx* ctx, const vrfs_msm_bases* h, con
   const uint8_t* d_s; uint8_t* d_o;
   ST(stage_in(ctx, BUF_IN1, scalars, h->n * 32 * (size_t)n_columns, &d_s));
   ST(stage_out(ctx, BUF_OUT0, ob * n_columns, &d_o));
-  MsmPlan p = msm_plan((uint32_t)h->n, (uint32_t)n_columns, 1);
+  MsmPlan p = msm_plan((uint32_t)h->n, (uint32_t)n_columns, 1, msm_c_override(1));
   ST(msm_dev(ctx, p, h->Q, d_s, d_o, out_mode));
   ST(copy_out(ctx, out, d_o, ob * n_columns));
   return finish_call(ctx);

@@ -1,0 +1,38 @@
+#!/usr/bin/env python3
+"""Window-size sweep of the prepared 3-column MSM (tuning aid for msm_plan): device ms per (log2 n, c).
+  python tools/msm_sweep.py [lo hi]      # VRFS_MSM_C is set per run; results must agree across c"""
+import json, os, sys
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+import ark_ec_vrfs_b200 as vrfs
+import oracle_lib as O
+lo, hi = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (10, 17)
+e = vrfs.Engine(0)
+rng = np.random.default_rng(5)
+ks = np.zeros((2048, 32), np.uint8); ks[:, :8] = rng.integers(1, 2 ** 62, size=2048, dtype=np.uint64).view(np.uint8).reshape(2048, 8)
+base2k = O.g1_mul_gen(ks)
+res = {}
+for logn in range(lo, hi + 1):
+    n = 1 << logn
+    bases = np.tile(base2k, (max(1, n // 2048), 1))[:n]
+    sc = rng.integers(0, 256, size=(3 * n, 32), dtype=np.uint8); sc[:, 31] &= 0x3F
+    ref = None; row = {}
+    for c in [0] + list(range(max(8, logn - 3), min(18, logn + 5) + 1)):
+        if c: os.environ["VRFS_MSM_C"] = str(c)
+        else: os.environ.pop("VRFS_MSM_C", None)
+        h = e.msm_g1_prepare(bases)
+        best = None
+        for _ in range(4):
+            e.enable_kernel_timing(True); out = h.msm(sc, 3); kt = e.kernel_timings(); e.enable_kernel_timing(False)
+            ms = sum(v for _, v in kt)
+            if best is None or ms < best[0]: best = (ms, kt)
+        h.release()
+        if ref is None: ref = out
+        assert np.array_equal(ref, out), (logn, c)
+        row[c] = round(best[0], 3)
+        print("2^%d c=%d: %.3f ms" % (logn, c, best[0]), {a: round(b, 2) for a, b in best[1]}, flush=True)
+    res[logn] = row
+    print("2^%d best:" % logn, min(row, key=row.get), row, flush=True)
+os.environ.pop("VRFS_MSM_C", None)
+json.dump(res, open(os.path.join(ROOT, "gpurun_out", "msm_sweep.json"), "w"), indent=1)
