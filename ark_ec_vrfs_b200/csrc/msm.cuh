@@ -36,9 +36,10 @@ struct MsmPlan {
   int chunk;                     // buckets per thread in the segment reduction
   int tpb;                       // threads cooperating on one bucket in k_msm_accumulate (power of two <= 32)
   uint32_t big;                  // buckets with more entries than this go to k_msm_accumulate_big
+  int aff_rounds;                // bucket accumulation: pairwise rounds in affine coordinates before the XYZZ pass (0: XYZZ only)
   int rc_h;                      // segment reduction: columns H of the R x H bucket matrix summed by k_msm_rc (0: nb <= 256, k_msm_wsum takes the buckets directly)
 };
-VRFS_HD inline MsmPlan msm_plan(uint32_t n, uint32_t ncol, int prepared, int c_override = 0) {
+VRFS_HD inline MsmPlan msm_plan(uint32_t n, uint32_t ncol, int prepared, int c_override = 0, int aff_override = -1) {
   MsmPlan p; p.n = n; p.ncol = ncol; p.prepared = prepared;
   int lg = 0; while ((1u << (lg + 1)) <= n) lg++;
   // prepared mode: all windows of a column share one bucket set, so a short top window (255 mod c bits) piles n entries onto
@@ -57,6 +58,11 @@ VRFS_HD inline MsmPlan msm_plan(uint32_t n, uint32_t ncol, int prepared, int c_o
   const uint64_t total_buckets = (uint64_t)ncol * (prepared ? 1 : p.windows) * p.nb;
   p.tpb = 1; while (p.tpb < 32 && (avg / p.tpb > 24 || (total_buckets * p.tpb < 65536 && avg / p.tpb >= 4))) p.tpb *= 2;
   p.big = (uint32_t)(8 * (avg + 8));
+  // batched-affine rounds (k_msm_aff_round) are OFF unless VRFS_MSM_AFF asks for them: measured on B200 at N = 2^17 x 3 they
+  // take 3.48 ms against 3.30 ms of the XYZZ pass (round 0 alone 1.55 ms for half the additions) - see the note above the kernels
+  p.aff_rounds = 0;
+  if (aff_override >= 0 && prepared) p.aff_rounds = aff_override > 8 ? 8 : aff_override;      // tests / tuning (VRFS_MSM_AFF)
+  if ((uint64_t)n * p.windows >= (1u << 28)) p.aff_rounds = 0;                               // 29-bit slot indices in k_msm_aff_round
   p.rc_h = 0;
   if (p.nb > 256) { int h = 0; while ((1 << (2 * h)) < p.nb) h++; p.rc_h = 1 << h; }   // H = 2^ceil(log2(nb)/2) <= 512
   return p;
@@ -185,6 +191,112 @@ HD_NOINLINE Fq381 fq381_inv(const Fq381& a) {
   const uint32_t* r = is_one(u) ? x1 : x2;
   for (int i = 0; i < 12; i++) x.v[i] = r[i];
   return x * Fq381::r3();                             // a^-1 R^-1 * R^3 / R = a^-1 R
+}
+
+// 1/a in BLS12-381 Fq, second version: binary GCD on word-sized approximations (Pornin, "Optimized Binary GCD for Modular
+// Inversion", 2020), 32-bit flavour.  Each of the 26 outer rounds reads the top 32 and the low 30 bits of (a, b) into two
+// 62-bit words, runs 30 branch-free binary-GCD steps on them while recording the 2x2 update matrix (entries <= 2^30), and
+// applies the matrix once to the 12-limb a, b (exact division by 2^30) and to u, v (division by 2^30 mod p with one
+// Montgomery-style correction word).  ~1/4 of the instructions of fq381_inv and no data-dependent branch, so the 32 lanes of a
+// warp can invert 32 different values in lock-step.  Montgomery in, Montgomery out; 0 -> 0.  If the loop does not end in
+// (a, b) = (0, 1) - never observed; the round count follows the paper's 2*len - 1 bound - the result is recomputed by fq381_inv.
+HD_INLINE void bingcd_lin2(uint32_t* out13, const uint32_t* a, int32_t f, const uint32_t* b, int32_t g) {   // a*f + b*g, two's complement
+  long long cy = 0;
+  for (int i = 0; i < 12; i++) {
+    long long t = (long long)((unsigned long long)a[i] * (uint32_t)f) - (f < 0 ? (long long)((unsigned long long)a[i] << 32) : 0ll);
+    t += (long long)((unsigned long long)b[i] * (uint32_t)g) - (g < 0 ? (long long)((unsigned long long)b[i] << 32) : 0ll);
+    t += cy;
+    out13[i] = (uint32_t)t; cy = t >> 32;
+  }
+  out13[12] = (uint32_t)cy;
+}
+HD_INLINE bool fq381_inv_bingcd(Fq381& out, const Fq381& x) {        // false: the loop did not end in (0, 1) (x = 0, or never)
+  uint32_t a[12], b[12], u[12], v[12], pm[12];
+  for (int i = 0; i < 12; i++) { a[i] = x.v[i]; pm[i] = BlsFq::mod(i); b[i] = pm[i]; u[i] = i == 0; v[i] = 0; }
+  const uint32_t ninv30 = BlsFq::NINV & 0x3fffffffu;             // -p^-1 mod 2^30
+#pragma unroll 1
+  for (int round = 0; round < 26; round++) {
+    // bit length n of a | b, window position sp = max(n - 32, 30)
+    uint32_t topw = 0; int topi = 0;
+    for (int i = 0; i < 12; i++) { const uint32_t w = a[i] | b[i]; if (w) { topw = w; topi = i; } }
+#ifdef __CUDA_ARCH__
+    const int lz = __clz((int)topw);
+#else
+    const int lz = topw ? __builtin_clz(topw) : 32;
+#endif
+    int sp = 32 * topi + 32 - lz - 32; if (sp < 30) sp = 30;
+    const int q = sp >> 5, r = sp & 31;
+    uint32_t alo = 0, ahi = 0, blo = 0, bhi = 0;
+    for (int i = 0; i < 12; i++) { if (i == q) { alo = a[i]; blo = b[i]; } if (i == q + 1) { ahi = a[i]; bhi = b[i]; } }
+    const uint32_t atop = r ? (alo >> r) | (ahi << (32 - r)) : alo, btop = r ? (blo >> r) | (bhi << (32 - r)) : blo;
+    unsigned long long xa = (a[0] & 0x3fffffffu) | ((unsigned long long)atop << 30), xb = (b[0] & 0x3fffffffu) | ((unsigned long long)btop << 30);
+    // the matrix rows travel as F = f + g * 2^32 in two's complement: one 64-bit subtraction / doubling updates both entries
+    long long F0 = 1, F1 = 1ll << 32;
+    for (int j = 0; j < 30; j++) {
+      const bool odd = xa & 1u, sw = odd & (xa < xb);
+      const unsigned long long ta = sw ? xb : xa, tb = sw ? xa : xb;
+      const long long tF0 = sw ? F1 : F0, tF1 = sw ? F0 : F1;
+      xa = (ta - (odd ? tb : 0ull)) >> 1; xb = tb;
+      F0 = tF0 - (odd ? tF1 : 0ll);
+      F1 = (long long)((unsigned long long)tF1 << 1);
+    }
+    int32_t f0 = (int32_t)(uint32_t)F0, f1 = (int32_t)(uint32_t)F1;            // |f|, |g| <= 2^30
+    int32_t g0 = (int32_t)((F0 - (long long)f0) >> 32), g1 = (int32_t)((F1 - (long long)f1) >> 32);
+    uint32_t na[13], nb[13];
+    bingcd_lin2(na, a, f0, b, g0);
+    bingcd_lin2(nb, a, f1, b, g1);
+    const bool nega = na[12] >> 31, negb = nb[12] >> 31;
+    {                                                             // a = |na| >> 30, b = |nb| >> 30
+      uint32_t ca = nega, cb = negb;
+      const uint32_t ma = nega ? 0xffffffffu : 0u, mb = negb ? 0xffffffffu : 0u;
+      for (int i = 0; i < 13; i++) {
+        unsigned long long t = (unsigned long long)(na[i] ^ ma) + ca; na[i] = (uint32_t)t; ca = (uint32_t)(t >> 32);
+        t = (unsigned long long)(nb[i] ^ mb) + cb; nb[i] = (uint32_t)t; cb = (uint32_t)(t >> 32);
+      }
+      for (int i = 0; i < 12; i++) { a[i] = (na[i] >> 30) | (na[i + 1] << 2); b[i] = (nb[i] >> 30) | (nb[i + 1] << 2); }
+    }
+    if (nega) { f0 = -f0; g0 = -g0; }
+    if (negb) { f1 = -f1; g1 = -g1; }
+    // (u, v) <- (u f0 + v g0, u f1 + v g1) / 2^30 mod p
+    for (int which = 0; which < 2; which++) {
+      const int32_t f = which ? f1 : f0, g = which ? g1 : g0;
+      const uint32_t t0 = u[0] * (uint32_t)f + v[0] * (uint32_t)g;
+      const uint32_t qq = (t0 * ninv30) & 0x3fffffffu;
+      uint32_t t[13];
+      long long cy = 0;
+      for (int i = 0; i < 12; i++) {
+        long long w = (long long)((unsigned long long)u[i] * (uint32_t)f) - (f < 0 ? (long long)((unsigned long long)u[i] << 32) : 0ll);
+        w += (long long)((unsigned long long)v[i] * (uint32_t)g) - (g < 0 ? (long long)((unsigned long long)v[i] << 32) : 0ll);
+        w += cy;
+        // + p[i] * qq, added as an unsigned quantity: split so that the signed sum cannot overflow
+        const unsigned long long pq = (unsigned long long)pm[i] * qq;
+        w += (long long)(pq & 0xffffffffu);
+        t[i] = (uint32_t)w; cy = (w >> 32) + (long long)(pq >> 32);
+      }
+      t[12] = (uint32_t)cy;
+      uint32_t r12[12];
+      for (int i = 0; i < 12; i++) r12[i] = (t[i] >> 30) | (t[i + 1] << 2);      // in (-p, 2p), two's complement in 384 bits
+      const bool neg = t[12] >> 31;
+      uint32_t add[12], tmp[12];
+      for (int i = 0; i < 12; i++) add[i] = neg ? pm[i] : 0u;
+      MontChains<12>::add(r12, r12, add);                                          // now in [0, 2p)
+      const uint32_t borrow = MontChains<12>::sub(tmp, r12, pm);
+      for (int i = 0; i < 12; i++) r12[i] = borrow ? r12[i] : tmp[i];
+      if (which == 0) { for (int i = 0; i < 12; i++) na[i] = r12[i]; } else { for (int i = 0; i < 12; i++) nb[i] = r12[i]; }
+    }
+    for (int i = 0; i < 12; i++) { u[i] = na[i]; v[i] = nb[i]; }
+  }
+  uint32_t bad = b[0] ^ 1u;
+  for (int i = 0; i < 12; i++) bad |= a[i] | (i ? b[i] : 0u);
+  Fq381 r;                                                        // v = (xR)^-1 -> x^-1 R = v * R^3 / R
+  for (int i = 0; i < 12; i++) r.v[i] = v[i];
+  out = r * Fq381::r3();
+  return bad == 0;
+}
+HD_NOINLINE Fq381 fq381_inv_fast(const Fq381& x) {
+  Fq381 r;
+  if (fq381_inv_bingcd(r, x)) return r;
+  return fq381_inv(x);                                            // x = 0 (-> 0)
 }
 
 #ifdef __CUDACC__
@@ -325,7 +437,7 @@ __global__ void __launch_bounds__(128) k_msm_prepare(uint32_t n, int c, int wind
     zs[w] = select(inf, Fq381::one(), P.Z);                      // an identity must not poison the product chain
     pre[w] = w ? pre[w - 1] * zs[w] : zs[w];
   }
-  Fq381 acc = fq381_inv(pre[windows - 1]);
+  Fq381 acc = fq381_inv_fast(pre[windows - 1]);
   for (int w = windows - 1; w >= 0; w--) {
     Fq381 zi = w ? acc * pre[w - 1] : acc;
     if (w) acc = acc * zs[w];
@@ -438,6 +550,174 @@ __global__ void __launch_bounds__(128, MSM_ACC_MINBLOCKS) k_msm_accumulate(MsmPl
   }
   if (live && lane == 0 && counts[b] <= p.big) copy_words16(&buckets[b], &acc);
 }
+// ---- bucket accumulation, batched-affine rounds -------------------------------------------------------------------------------
+// An affine addition costs 1 inversion + 2M + 1S; with the inversions of many independent additions shared (Montgomery's trick,
+// 3M each) that is 5M + 1S = 6 products against the 10 of the XYZZ mixed addition.  The entries of every bucket are therefore
+// added PAIRWISE in rounds: round r maps the ceil(c / 2^r) points of a bucket to ceil(c / 2^(r+1)) (pairs added, an odd last
+// point copied), all buckets of all segments at once, so a round is one flat, perfectly balanced list of independent additions.
+// Layout: round r >= 1 keeps its points at pts[seg * cap_r + off_r[b] + j] with off_r the exclusive scan of ceil(c / 2^r) inside
+// the segment (k_msm_scan_rounds; cap_r = ceil(seg_len / 2^r) + nb bounds the segment).  A warp takes a tile of 32 x MSM_AFF_B
+// output slots (found by binary search in off_{r+1}); each lane chains the denominators of its MSM_AFF_B additions, inverts the
+// product with fq381_inv_fast - branch-free, so the 32 lanes invert 32 different values in lock-step - and unwinds.
+// Exceptional cases (identity operand, P + P, P - P) are classified per pair; their denominator is 2y or 1.
+// Buckets above p.big are left to the slice kernels; after p.aff_rounds rounds k_msm_accumulate_pts sums what is left in XYZZ.
+// MEASURED (B200, N = 2^17, 3 random columns, 6.7 M entries, MSM_AFF_B = 24, 5 rounds): rounds 1.55 / 0.70 / 0.53 / 0.40 / 0.30 ms
+// = 3.48 ms against 3.30 ms for the plain XYZZ pass, so the plan leaves them off (VRFS_MSM_AFF=r turns them on; the tests do).
+// Why 6 products do not beat 10 here: the inversion is ~48 K ALU instructions per warp and tile (~55 product-times of a 12-limb
+// multiplier that needs 1 833 cycles per warp and product), every operand is fetched twice (forward and backward pass), and the
+// short late rounds are bound by the latency of one tile (~0.3 ms) rather than by throughput.
+#ifndef MSM_AFF_B
+#define MSM_AFF_B 24
+#endif
+struct MsmAffArgs {
+  const uint32_t* counts;      // round-0 entries per bucket
+  const uint32_t* off_in;      // [segs * nb] exclusive offsets of the input round (relative to the segment)
+  const uint32_t* off_out;     // ... of the output round
+  const uint32_t* tot_out;     // [segs] slots of the output round
+  const uint32_t* list;        // round 0: sorted entries (point index | sign << 31)
+  const G1Aff* table;          // round 0: affine records
+  const G1Aff* pts_in;         // rounds >= 1
+  G1Aff* pts_out;
+  uint32_t* next_tile;         // device counter (zeroed by the host before every round)
+  size_t stride_in, stride_out;   // segment strides of the input (seg_len for round 0, cap_r after) and the output (cap_{r+1})
+  int r;                       // input round
+};
+VRFS_HD inline size_t msm_aff_cap(size_t seg_len, int nb, int r) { return ((seg_len + ((size_t)1 << r) - 1) >> r) + (size_t)nb; }
+HD_INLINE uint32_t msm_round_count(uint32_t c, int r, uint32_t big) { return c > big ? 0u : (c + ((1u << r) - 1u)) >> r; }
+
+// grid (segs, rounds): roff[(r-1) * nbuckets + seg * nb + i] = exclusive scan over the segment of ceil(c / 2^r), r = blockIdx.y + 1;
+// rtot[(r-1) * segs + seg] = its total
+__global__ void __launch_bounds__(256) k_msm_scan_rounds(MsmPlan p, const uint32_t* counts, uint32_t* roff, uint32_t* rtot) {
+  __shared__ uint32_t part[256];
+  const uint32_t seg = blockIdx.x, segs = gridDim.x;
+  const int r = blockIdx.y + 1;
+  const size_t nbuckets = (size_t)segs * p.nb;
+  const uint32_t* c = counts + (size_t)seg * p.nb;
+  uint32_t* o = roff + (size_t)(r - 1) * nbuckets + (size_t)seg * p.nb;
+  const int per = (p.nb + 255) / 256;
+  const int lo = threadIdx.x * per, hi = min(lo + per, p.nb);
+  uint32_t s = 0;
+  for (int i = lo; i < hi; i++) s += msm_round_count(c[i], r, p.big);
+  part[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) { uint32_t run = 0; for (int i = 0; i < 256; i++) { uint32_t v = part[i]; part[i] = run; run += v; } rtot[(size_t)(r - 1) * segs + seg] = run; }
+  __syncthreads();
+  uint32_t run = part[threadIdx.x];
+  for (int i = lo; i < hi; i++) { o[i] = run; run += msm_round_count(c[i], r, p.big); }
+}
+
+// kinds of a slot: 0 copy first, 1 copy second, 2 identity, 3 add, 4 double
+template <bool FIRST>
+__device__ __forceinline__ void msm_aff_load(const MsmAffArgs& A, size_t seg, uint32_t j, Fq381& x, Fq381& y) {
+  G1Aff t;
+  if (FIRST) {
+    const uint32_t e = A.list[seg * A.stride_in + j];
+    copy_words16(&t, A.table + (e & 0x7fffffffu));
+    x = t.x; y = cneg(t.y, (e >> 31) != 0);
+  } else {
+    copy_words16(&t, A.pts_in + seg * A.stride_in + j);
+    x = t.x; y = t.y;
+  }
+}
+template <bool FIRST>
+__global__ void __launch_bounds__(128, 4) k_msm_aff_round(MsmPlan p, MsmAffArgs A, uint32_t segs) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t tile_slots = 32u * MSM_AFF_B;
+  const uint32_t tiles_per_seg = (uint32_t)((A.stride_out + tile_slots - 1) / tile_slots);
+  Fq381 pre[MSM_AFF_B];
+  uint32_t meta[MSM_AFF_B];                        // input index of the first operand | kind << 29
+  for (;;) {
+    uint32_t tile = 0;
+    if (lane == 0) tile = atomicAdd(A.next_tile, 1u);
+    tile = __shfl_sync(0xffffffffu, tile, 0);
+    const uint32_t seg = tile / tiles_per_seg;
+    if (seg >= segs) break;
+    const uint32_t base_q = (tile % tiles_per_seg) * tile_slots, tot = A.tot_out[seg];
+    if (base_q >= tot) continue;
+    const uint32_t* oin = A.off_in + (size_t)seg * p.nb;
+    const uint32_t* oout = A.off_out + (size_t)seg * p.nb;
+    const uint32_t* cnt = A.counts + (size_t)seg * p.nb;
+    uint32_t b = 0;
+    {                                              // bucket of the lane's first slot: last b with oout[b] <= q
+      const uint32_t q = min(base_q + lane, tot - 1);
+      uint32_t lo = 0, hi = (uint32_t)p.nb;
+      while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (oout[mid] <= q) lo = mid; else hi = mid; }
+      b = lo;
+    }
+    Fq381 run;
+#pragma unroll 1
+    for (int k = 0; k < MSM_AFF_B; k++) {
+      const uint32_t q = base_q + (uint32_t)k * 32u + lane;
+      uint32_t kind = 2, j0 = 0;
+      Fq381 d = Fq381::one();
+      if (q < tot) {
+        while (b + 1 < (uint32_t)p.nb && oout[b + 1] <= q) b++;
+        const uint32_t i = q - oout[b], cin = msm_round_count(cnt[b], A.r, p.big);
+        j0 = oin[b] + 2 * i;
+        Fq381 x1, y1;
+        msm_aff_load<FIRST>(A, seg, j0, x1, y1);
+        kind = 0;
+        if (2 * i + 1 < cin) {
+          Fq381 x2, y2;
+          msm_aff_load<FIRST>(A, seg, j0 + 1, x2, y2);
+          const bool inf1 = x1.is_zero() & y1.is_zero(), inf2 = x2.is_zero() & y2.is_zero();
+          if (inf1) kind = 1;
+          else if (!inf2) {
+            d = x2 - x1;
+            if (!d.is_zero()) kind = 3;
+            else if (y1 == y2 && !y1.is_zero()) { kind = 4; d = dbl(y1); }
+            else { kind = 2; d = Fq381::one(); }
+          }
+        }
+      }
+      run = k ? run * d : d;
+      pre[k] = run;
+      meta[k] = j0 | (kind << 29);
+    }
+    Fq381 inv = fq381_inv_fast(run);
+#pragma unroll 1
+    for (int k = MSM_AFF_B - 1; k >= 0; k--) {
+      const uint32_t q = base_q + (uint32_t)k * 32u + lane;
+      const uint32_t kind = meta[k] >> 29, j0 = meta[k] & 0x1fffffffu;
+      Fq381 dinv = inv;
+      if (k) dinv = inv * pre[k - 1];
+      G1Aff out; out.x = Fq381::zero(); out.y = Fq381::zero();
+      if (kind >= 3) {
+        Fq381 x1, y1, x2, y2;
+        msm_aff_load<FIRST>(A, seg, j0, x1, y1);
+        Fq381 lam, d;
+        if (kind == 3) { msm_aff_load<FIRST>(A, seg, j0 + 1, x2, y2); d = x2 - x1; lam = (y2 - y1) * dinv; }
+        else { x2 = x1; d = dbl(y1); Fq381 xx = sqr(x1); lam = (dbl(xx) + xx) * dinv; }
+        if (k) inv = inv * d;
+        out.x = sqr(lam) - x1 - x2;
+        out.y = lam * (x1 - out.x) - y1;
+      } else if (kind != 2) {
+        msm_aff_load<FIRST>(A, seg, j0 + kind, out.x, out.y);
+      }
+      if (q < tot) copy_words16(A.pts_out + (size_t)seg * A.stride_out + q, &out);
+    }
+  }
+}
+// what the rounds left of every bucket (<= ceil(big / 2^R) points), summed in XYZZ -> projective bucket
+__global__ void __launch_bounds__(128, MSM_ACC_MINBLOCKS) k_msm_accumulate_pts(MsmPlan p, const uint32_t* counts, const uint32_t* off, const G1Aff* pts, size_t stride, G1Pt* buckets) {
+  const size_t total = (size_t)p.ncol * p.seg_windows * p.nb;
+  const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= total) return;
+  const uint32_t c0 = counts[b];
+  if (c0 > p.big) return;                          // written by k_msm_big_combine
+  const uint32_t cnt = msm_round_count(c0, p.aff_rounds, p.big);
+  const size_t seg = b / p.nb;
+  const G1Aff* l = pts + seg * stride + off[b];
+  G1Xyzz acc; xyzz_set_identity(acc);
+  for (uint32_t j = 0; j < cnt; j++) {
+    Fq381 x, y;
+    if (g1_load_aff_xy(x, y, l + j, false)) xyzz_madd(&acc, &x, &y);
+  }
+  G1Pt out;
+  xyzz_to_proj(out, acc);
+  copy_words16(&buckets[b], &out);
+}
+
 // one block per slice of an oversized bucket: strided partial sums + shared-memory tree -> bigpart[slice];
 // k_msm_big_combine then adds the slices of each bucket.  (A ring's 0/1 selector column puts half the domain into ONE bucket:
 // a single block needed 4.8 ms for it at N = 2^17.)
@@ -660,7 +940,7 @@ __global__ void k_msm_final(MsmPlan p, const G1Pt* window_sums, uint8_t* out, in
     from_mont<BlsFq>(raw, acc.Z); store_le<12>(o + 96, raw);
   } else {
     uint8_t* o = out + (size_t)96 * col;
-    Fq381 zi = fq381_inv(acc.Z);                // identity: Z = 0 -> zi = 0 -> zeros
+    Fq381 zi = fq381_inv_fast(acc.Z);                // identity: Z = 0 -> zi = 0 -> zeros
     from_mont<BlsFq>(raw, acc.X * zi); store_le<12>(o, raw);
     from_mont<BlsFq>(raw, acc.Y * zi); store_le<12>(o + 48, raw);
   }
@@ -681,7 +961,7 @@ __global__ void k_g1_sum_partials(int n_parts, int ncol, const uint8_t* partials
   }
   uint32_t raw[12];
   uint8_t* o = out + (size_t)96 * col;
-  Fq381 zi = fq381_inv(acc.Z);
+  Fq381 zi = fq381_inv_fast(acc.Z);
   from_mont<BlsFq>(raw, acc.X * zi); store_le<12>(o, raw);
   from_mont<BlsFq>(raw, acc.Y * zi); store_le<12>(o + 48, raw);
 }

@@ -6,6 +6,7 @@
 #include <string.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <algorithm>
 #include <mutex>
 #include <new>
 
@@ -1307,10 +1308,14 @@ static int msm_c_override(int prepared) {
   const char* e = getenv(prepared ? "VRFS_MSM_C" : "VRFS_MSM_C_STATELESS");
   return e ? atoi(e) : 0;
 }
+static int msm_aff_override() {
+  const char* e = getenv("VRFS_MSM_AFF");
+  return e ? atoi(e) : -1;
+}
 static vrfs_status msm_dev(vrfs_ctx* ctx, MsmPlan p, const void* d_bases, const uint8_t* d_scalars, uint8_t* d_out, int out_mode) {
   const size_t n = p.n, ncol = p.ncol;
   const size_t segs = ncol * p.seg_windows, nbuckets = segs * p.nb, seg_len = n * (p.prepared ? p.windows : 1);
-  const size_t per_seg = p.nb / p.chunk;
+  const size_t per_seg = p.nb / p.chunk; (void)per_seg;
   void *counts = nullptr, *list = nullptr, *buckets = nullptr, *wsum = nullptr;
   // counts | offsets | cursors | big_count (16 words) | slice list of the oversized buckets (2 words per slice) ; partial sums of the slices
   const size_t bigcap = msm_big_capacity(nbuckets, segs * seg_len);
@@ -1341,7 +1346,43 @@ static vrfs_status msm_dev(vrfs_ctx* ctx, MsmPlan p, const void* d_bases, const 
   LAUNCHED_AS(ctx, "msm_scatter");
   const unsigned ab = (unsigned)((nbuckets * p.tpb + 127) / 128);
   const unsigned bigb = (unsigned)(ctx->sms * 4);
-  if (p.prepared) {
+  if (p.aff_rounds) {
+    // batched-affine rounds (prepared mode, large domains): per-round offsets | totals | tile counters ; ping-pong point buffers
+    const int R = p.aff_rounds;
+    void *rbuf = nullptr, *ptsA = nullptr, *ptsB = nullptr;
+    ST(ensure(ctx, BUF_X2, ((size_t)R * nbuckets + (size_t)R * segs + 16) * sizeof(uint32_t), &rbuf));
+    ST(ensure(ctx, BUF_X0, segs * msm_aff_cap(seg_len, p.nb, 1) * sizeof(G1Aff), &ptsA));
+    ST(ensure(ctx, BUF_X1, segs * msm_aff_cap(seg_len, p.nb, 2) * sizeof(G1Aff), &ptsB));
+    uint32_t *roff = (uint32_t*)rbuf, *rtot = roff + (size_t)R * nbuckets, *tiles_ctr = rtot + (size_t)R * segs;
+    CU(cudaMemsetAsync(tiles_ctr, 0, 16 * sizeof(uint32_t), ctx->stream));
+    k_msm_scan_rounds<<<dim3((unsigned)segs, (unsigned)R), 256, 0, ctx->stream>>>(p, (const uint32_t*)counts, roff, rtot);
+    LAUNCHED_AS(ctx, "msm_scan_rounds");
+    for (int r = 0; r < R; r++) {
+      MsmAffArgs A;
+      A.counts = (const uint32_t*)counts;
+      A.off_in = r == 0 ? offsets : roff + (size_t)(r - 1) * nbuckets;
+      A.off_out = roff + (size_t)r * nbuckets;
+      A.tot_out = rtot + (size_t)r * segs;
+      A.list = (const uint32_t*)list; A.table = (const G1Aff*)d_bases;
+      A.pts_in = (const G1Aff*)((r & 1) ? ptsA : ptsB);
+      A.pts_out = (G1Aff*)(((r + 1) & 1) ? ptsA : ptsB);
+      A.next_tile = tiles_ctr + r;
+      A.stride_in = r == 0 ? seg_len : msm_aff_cap(seg_len, p.nb, r);
+      A.stride_out = msm_aff_cap(seg_len, p.nb, r + 1);
+      A.r = r;
+      const size_t tiles = segs * ((A.stride_out + 32 * MSM_AFF_B - 1) / (32 * MSM_AFF_B));
+      const unsigned blocks = (unsigned)std::min<size_t>((tiles + 3) / 4, (size_t)ctx->sms * 4);
+      if (r == 0) k_msm_aff_round<true><<<blocks, 128, 0, ctx->stream>>>(p, A, (uint32_t)segs);
+      else k_msm_aff_round<false><<<blocks, 128, 0, ctx->stream>>>(p, A, (uint32_t)segs);
+      static const char* const round_names[8] = {"msm_aff_round0", "msm_aff_round1", "msm_aff_round2", "msm_aff_round3", "msm_aff_round4", "msm_aff_round5", "msm_aff_round6", "msm_aff_round7"};
+      LAUNCHED_AS(ctx, round_names[r & 7]);
+    }
+    k_msm_accumulate_pts<<<(unsigned)((nbuckets + 127) / 128), 128, 0, ctx->stream>>>(p, (const uint32_t*)counts, roff + (size_t)(R - 1) * nbuckets,
+                                                                                     (const G1Aff*)((R & 1) ? ptsA : ptsB), msm_aff_cap(seg_len, p.nb, R), (G1Pt*)buckets);
+    LAUNCHED_AS(ctx, "msm_accumulate");
+    if (p.prepared) k_msm_accumulate_big<true><<<bigb, MSM_BIG_THREADS, 0, ctx->stream>>>(p, d_bases, (const uint32_t*)counts, offsets, (const uint32_t*)list, big_list, big_count, bigpart);
+    else k_msm_accumulate_big<false><<<bigb, MSM_BIG_THREADS, 0, ctx->stream>>>(p, d_bases, (const uint32_t*)counts, offsets, (const uint32_t*)list, big_list, big_count, bigpart);
+  } else if (p.prepared) {
     k_msm_accumulate<true><<<ab, 128, 0, ctx->stream>>>(p, d_bases, (const uint32_t*)counts, offsets, (const uint32_t*)list, (G1Pt*)buckets);
     LAUNCHED_AS(ctx, "msm_accumulate");
     k_msm_accumulate_big<true><<<bigb, MSM_BIG_THREADS, 0, ctx->stream>>>(p, d_bases, (const uint32_t*)counts, offsets, (const uint32_t*)list, big_list, big_count, bigpart);
@@ -1411,7 +1452,7 @@ extern "C" vrfs_status vrfs_msm_g1_prepare(vrfs_ctx* ctx, size_t n, const uint8_
   ST(begin_call(ctx, n));
   vrfs_msm_bases* h = new (std::nothrow) vrfs_msm_bases();
   if (!h) return fail(ctx, VRFS_CUDA_ERROR, "out of host memory");
-  h->ctx = ctx; h->n = n; h->plan = msm_plan((uint32_t)n, 1, 1, msm_c_override(1)); h->Q = nullptr;
+  h->ctx = ctx; h->n = n; h->plan = msm_plan((uint32_t)n, 1, 1, msm_c_override(1), msm_aff_override()); h->Q = nullptr;
   cudaError_t e = cudaMalloc(&h->Q, (size_t)h->plan.windows * n * sizeof(G1Aff));
   if (e != cudaSuccess) { delete h; return fail(ctx, VRFS_CUDA_ERROR, "cudaMalloc of the prepared table failed: %s", cudaGetErrorString(e)); }
   *out = h;
@@ -1441,7 +1482,7 @@ static vrfs_status msm_prepared_host(vrfs_ctx* ctx, const vrfs_msm_bases* h, con
   const uint8_t* d_s; uint8_t* d_o;
   ST(stage_in(ctx, BUF_IN1, scalars, h->n * 32 * (size_t)n_columns, &d_s));
   ST(stage_out(ctx, BUF_OUT0, ob * n_columns, &d_o));
-  MsmPlan p = msm_plan((uint32_t)h->n, (uint32_t)n_columns, 1, msm_c_override(1));
+  MsmPlan p = msm_plan((uint32_t)h->n, (uint32_t)n_columns, 1, msm_c_override(1), msm_aff_override());
   ST(msm_dev(ctx, p, h->Q, d_s, d_o, out_mode));
   ST(copy_out(ctx, out, d_o, ob * n_columns));
   return finish_call(ctx);

@@ -182,3 +182,11 @@ extern "C" void hostemu_fq381_inv(const uint32_t* a_mont, uint32_t* out_mont) {
   Fq381 r = fq381_inv(a);
   memcpy(out_mont, r.v, 48);
 }
+// the word-approximation binary GCD; returns 1 when its own loop finished (no fallback to fq381_inv was needed)
+extern "C" int hostemu_fq381_inv_fast(const uint32_t* a_mont, uint32_t* out_mont) {
+  Fq381 a, t; memcpy(a.v, a_mont, 48);
+  const bool finished = fq381_inv_bingcd(t, a);
+  Fq381 r = fq381_inv_fast(a);
+  memcpy(out_mont, r.v, 48);
+  return finished;
+}

@@ -139,6 +139,21 @@ def test_host_emulated_ietf_verify_matches_oracle(emu, suite):
     assert np.array_equal(got, w["expect"]) and 0 < got.sum() < n
 
 
+def test_fq381_word_approximation_gcd_inverse(emu):
+    """csrc/msm.cuh fq381_inv_fast (26 rounds of 30 binary-GCD steps on 62-bit approximations; the batched-affine rounds run it
+    in lock-step on 32 lanes) against big-integer arithmetic; its own loop must finish (no fallback) for every non-zero input"""
+    p = R.BLS_FQ; Rm = 1 << 384
+    rnd = random.Random(22)
+    special = [0, 1, p - 1, 2, (p + 1) // 2, 3, p - 2, 1 << 380, (1 << 380) - 1, (1 << 62) - 1, 1 << 62]
+    for t in range(1500):
+        a = special[t] if t < len(special) else (rnd.randrange(p) if t % 3 else rnd.randrange(1 << rnd.randrange(1, 381)))
+        A = (C.c_uint32 * 12)(*[((a * Rm % p) >> (32 * i)) & 0xFFFFFFFF for i in range(12)]); out = (C.c_uint32 * 12)()
+        finished = emu.hostemu_fq381_inv_fast(A, out)
+        got = sum(int(out[i]) << (32 * i) for i in range(12))
+        assert got == (pow(a, -1, p) * Rm % p if a else 0), a
+        assert finished == (1 if a else 0), a
+
+
 def test_fq381_binary_euclid_inverse(emu):
     """csrc/msm.cuh fq381_inv (used on the MSM's final projective -> affine step) against big-integer arithmetic"""
     p = R.BLS_FQ; Rm = 1 << 384
