@@ -565,7 +565,9 @@ __global__ void __launch_bounds__(128, MSM_ACC_MINBLOCKS) k_msm_accumulate(MsmPl
 // = 3.48 ms against 3.30 ms for the plain XYZZ pass, so the plan leaves them off (VRFS_MSM_AFF=r turns them on; the tests do).
 // Why 6 products do not beat 10 here: the inversion is ~48 K ALU instructions per warp and tile (~55 product-times of a 12-limb
 // multiplier that needs 1 833 cycles per warp and product), every operand is fetched twice (forward and backward pass), and the
-// short late rounds are bound by the latency of one tile (~0.3 ms) rather than by throughput.
+// short late rounds are bound by the latency of one tile (~0.3 ms) rather than by throughput.  Starting the resident blocks a
+// quarter tile period apart (so that inversions and multiplier passes of different warps overlap) made round 0 slower (1.91 ms):
+// the inversion does not hide behind the other warps' products.  Tiles of 16 instead of 24 additions per lane: 2.04 ms.
 #ifndef MSM_AFF_B
 #define MSM_AFF_B 24
 #endif
