@@ -217,3 +217,59 @@ def ring_commitment_msm(suite_or_engine, bases, scalar_columns):
     eng = suite_or_engine.engine if isinstance(suite_or_engine, Suite) else suite_or_engine
     cols = np.concatenate([np.asarray(c, np.uint8).reshape(-1, 32) for c in scalar_columns])
     return eng.msm_g1(bases, cols, len(scalar_columns))
+
+
+# ---- ring: the verifier-key part of `ring::RingContext` ------------------------------------------------------
+# [RECALL, unpinned] ring-proof's PiopParams: the domain keeps ZK_ROWS = 3 rows for blinding (capacity = N - 3), the fixed
+# columns hold `keyset_part_size = capacity - scalar_bitlen - 1` key slots (unused ones filled with the suite's padding point)
+# followed by the scalar_bitlen powers 2^j * H of the Pedersen blinding base; the selector is 1 on the key slots.  These numbers
+# are DEFAULTS of this mirror, passed to the engine as parameters; the engine itself hard-codes none of them.
+RING_ZK_ROWS = 3
+
+
+def g1_compress(points):
+    """ark-bls12-381's G1 `serialize_compressed` (the zcash format): 48 bytes big-endian x; bit 7 of byte 0 = compressed,
+    bit 6 = infinity, bit 5 = y is the lexicographically larger root.  points: (n, 96) affine LE, zeros = identity."""
+    P = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
+    pts = np.asarray(points, np.uint8).reshape(-1, 96); out = np.zeros((len(pts), 48), np.uint8)
+    for i, p in enumerate(pts):
+        if not p.any():
+            out[i, 0] = 0xC0
+            continue
+        x = int.from_bytes(p[:48].tobytes(), "little"); y = int.from_bytes(p[48:].tobytes(), "little")
+        b = bytearray(x.to_bytes(48, "big")); b[0] |= 0x80 | (0x20 if y > P - y else 0)
+        out[i] = np.frombuffer(bytes(b), np.uint8)
+    return out
+
+
+class RingContext:
+    """Holds the prepared SRS of one domain size and commits to rings of public keys: `RingContext::verifier_key(pks)` up to the
+    commitment (`RingCommitment` = cx, cy, selector).  srs_g1: (N, 96) affine G1 points, either the Lagrange basis [L_i(tau)]G1
+    over the radix-2 domain (lagrange=True, ring-proof's updatable `Ring`) or the monomial powers [tau^i]G1 (lagrange=False)."""
+
+    def __init__(self, suite, srs_g1, lagrange, padding, blinding_base_powers, keyset_part_size=None):
+        self.suite, self.engine, self.lagrange = suite, suite.engine, bool(lagrange)
+        srs_g1 = np.asarray(srs_g1, np.uint8).reshape(-1, 96)
+        self.domain_size = len(srs_g1)
+        assert self.domain_size & (self.domain_size - 1) == 0, "the SRS must cover a power-of-two domain"
+        self.tail = np.asarray(blinding_base_powers, np.uint8).reshape(-1, 64)
+        self.padding = np.asarray(padding, np.uint8).reshape(64)
+        self.keyset_part_size = (self.domain_size - RING_ZK_ROWS - len(self.tail) - 1) if keyset_part_size is None else int(keyset_part_size)
+        self.srs = self.engine.msm_g1_prepare(srs_g1)
+
+    def max_ring_size(self):
+        return self.keyset_part_size
+
+    def fixed_columns(self, public_keys):
+        return self.engine.ring_fixed_columns(self.domain_size, self.keyset_part_size, public_keys, self.padding, self.tail)
+
+    def verifier_key_commitment(self, public_keys):
+        """(3, 96) affine commitments cx, cy, selector"""
+        return self.srs.ring_commit(public_keys, self.keyset_part_size, self.padding, self.tail, self.lagrange)
+
+    def ring_commitment_bytes(self, public_keys):
+        """the 144-byte serialised RingCommitment: three compressed G1 points"""
+        return g1_compress(self.verifier_key_commitment(public_keys)).reshape(-1)
+
+    def release(self):
+        self.srs.release()

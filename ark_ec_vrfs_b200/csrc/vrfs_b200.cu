@@ -14,6 +14,7 @@
 #include "h2c.cuh"
 #include "wire.cuh"
 #include "msm.cuh"
+#include "ring.cuh"
 
 using namespace vrfs;
 
@@ -1492,6 +1493,92 @@ extern "C" vrfs_status vrfs_msm_g1_prepared(vrfs_ctx* ctx, const vrfs_msm_bases*
 }
 extern "C" vrfs_status vrfs_msm_g1_prepared_partial(vrfs_ctx* ctx, const vrfs_msm_bases* h, const uint8_t* scalars, int n_columns, uint8_t* out_partial) {
   return msm_prepared_host(ctx, h, scalars, n_columns, out_partial, 1);
+}
+// =================================================================================================
+// ring fixed columns + commitment (csrc/ring.cuh)
+// =================================================================================================
+// evaluations <-> coefficients over the size-2^logn domain, in/out canonical 32-byte LE on the device (may alias)
+static vrfs_status ntt_dev(vrfs_ctx* ctx, int logn, uint32_t ncol, int inverse, const uint8_t* d_in, uint8_t* d_out) {
+  const size_t n = (size_t)1 << logn, total = n * ncol;
+  void *work = nullptr, *tw = nullptr;
+  ST(ensure(ctx, BUF_X3, total * sizeof(Fr255), &work));
+  ST(ensure(ctx, BUF_X4, (n / 2 + 1) * sizeof(Fr255), &tw));
+  if (logn > 0) {
+    k_ntt_twiddles<<<(unsigned)((n / 2 + 127) / 128), 128, 0, ctx->stream>>>(logn, inverse, (Fr255*)tw);
+    LAUNCHED_AS(ctx, "ntt_twiddles");
+  }
+  k_ntt_load<<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(logn, ncol, d_in, (Fr255*)work);
+  LAUNCHED_AS(ctx, "ntt_load");
+  const int fused = logn < NTT_FUSED_LOG ? logn : NTT_FUSED_LOG;
+  if (fused > 0) {
+    k_ntt_fused<<<(unsigned)(total >> fused), 512, 0, ctx->stream>>>(logn, fused, (const Fr255*)tw, (Fr255*)work);
+    LAUNCHED_AS(ctx, "ntt_fused");
+  }
+  for (int s = fused + 1; s <= logn; s++) {
+    k_ntt_stage<<<(unsigned)((total / 2 + 255) / 256), 256, 0, ctx->stream>>>(logn, ncol, s, (const Fr255*)tw, (Fr255*)work);
+    LAUNCHED_AS(ctx, "ntt_stage");
+  }
+  k_ntt_store<<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(logn, ncol, inverse, (const Fr255*)work, d_out);
+  LAUNCHED_AS(ctx, "ntt_store");
+  return VRFS_OK;
+}
+extern "C" vrfs_status vrfs_fr_fft_batch(vrfs_ctx* ctx, int log_n, int n_columns, int inverse, const uint8_t* in, uint8_t* out) {
+  if (!ctx) return VRFS_BAD_ARG;
+  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
+  if (log_n < 0 || log_n > 26 || n_columns < 1 || n_columns > 32 || !in || !out) return fail(ctx, VRFS_BAD_ARG, "bad argument (0 <= log_n <= 26, 1 <= n_columns <= 32)");
+  const size_t bytes = ((size_t)n_columns << log_n) * 32;
+  ST(begin_call(ctx, (size_t)1 << log_n));
+  const uint8_t* d_i; uint8_t* d_o;
+  ST(stage_in(ctx, BUF_IN1, in, bytes, &d_i));
+  ST(stage_out(ctx, BUF_OUT1, bytes, &d_o));
+  ST(ntt_dev(ctx, log_n, (uint32_t)n_columns, inverse != 0, d_i, d_o));
+  ST(copy_out(ctx, out, d_o, bytes));
+  return finish_call(ctx);
+}
+static vrfs_status ring_columns_dev(vrfs_ctx* ctx, size_t n, size_t keyset_part, size_t n_keys, const uint8_t* keys, const uint8_t* padding,
+                                    size_t n_tail, const uint8_t* tail, uint8_t** d_cols) {
+  if (n == 0 || (n & (n - 1)) || n > (1u << 26)) return fail(ctx, VRFS_BAD_ARG, "domain size must be a power of two <= 2^26");
+  if (n_keys > keyset_part || keyset_part + n_tail > n) return fail(ctx, VRFS_BAD_ARG, "need n_keys <= keyset_part_size and keyset_part_size + n_tail <= domain size");
+  if ((n_keys && !keys) || (n_keys < keyset_part && !padding) || (n_tail && !tail)) return fail(ctx, VRFS_BAD_ARG, "null buffer");
+  const uint8_t *d_k = nullptr, *d_p = nullptr, *d_t = nullptr;
+  ST(stage_in(ctx, BUF_IN0, keys, n_keys * 64, &d_k));
+  ST(stage_in(ctx, BUF_IN2, padding, padding ? 64 : 0, &d_p));
+  ST(stage_in(ctx, BUF_IN3, tail, n_tail * 64, &d_t));
+  void* cols = nullptr;
+  ST(ensure(ctx, BUF_IN1, 3 * n * 32, &cols));
+  k_ring_columns<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((uint32_t)n, (uint32_t)keyset_part, (uint32_t)n_keys, d_k, d_p, (uint32_t)n_tail, d_t, (uint8_t*)cols);
+  LAUNCHED_AS(ctx, "ring_columns");
+  *d_cols = (uint8_t*)cols;
+  return VRFS_OK;
+}
+extern "C" vrfs_status vrfs_ring_fixed_columns(vrfs_ctx* ctx, size_t domain_size, size_t keyset_part_size, size_t n_keys, const uint8_t* keys,
+                                               const uint8_t* padding, size_t n_tail, const uint8_t* tail, uint8_t* out_columns) {
+  if (!ctx) return VRFS_BAD_ARG;
+  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
+  if (!out_columns) return fail(ctx, VRFS_BAD_ARG, "null buffer");
+  ST(begin_call(ctx, domain_size));
+  uint8_t* d_cols = nullptr;
+  ST(ring_columns_dev(ctx, domain_size, keyset_part_size, n_keys, keys, padding, n_tail, tail, &d_cols));
+  ST(copy_out(ctx, out_columns, d_cols, 3 * domain_size * 32));
+  return finish_call(ctx);
+}
+extern "C" vrfs_status vrfs_ring_commit(vrfs_ctx* ctx, const vrfs_msm_bases* srs, int srs_is_lagrange, size_t keyset_part_size, size_t n_keys,
+                                        const uint8_t* keys, const uint8_t* padding, size_t n_tail, const uint8_t* tail, uint8_t* out_commitment) {
+  if (!ctx || !srs || srs->ctx != ctx) return VRFS_BAD_ARG;
+  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
+  if (!out_commitment) return fail(ctx, VRFS_BAD_ARG, "null buffer");
+  const size_t n = srs->n;
+  ST(begin_call(ctx, n));
+  uint8_t *d_cols = nullptr, *d_o = nullptr;
+  ST(ring_columns_dev(ctx, n, keyset_part_size, n_keys, keys, padding, n_tail, tail, &d_cols));
+  if (!srs_is_lagrange) {                          // monomial SRS: commit to the interpolating polynomials
+    int logn = 0; while (((size_t)1 << logn) < n) logn++;
+    ST(ntt_dev(ctx, logn, 3, 1, d_cols, d_cols));
+  }
+  ST(stage_out(ctx, BUF_OUT0, 3 * 96, &d_o));
+  ST(msm_dev(ctx, msm_plan((uint32_t)n, 3, 1, msm_c_override(1), msm_aff_override()), srs->Q, d_cols, d_o, 0));
+  ST(copy_out(ctx, out_commitment, d_o, 3 * 96));
+  return finish_call(ctx);
 }
 extern "C" vrfs_status vrfs_g1_sum_partials(vrfs_ctx* ctx, int n_parts, int n_columns, const uint8_t* partials, uint8_t* out) {
   if (!ctx) return VRFS_BAD_ARG;

@@ -46,6 +46,13 @@ class PreparedBases:
         self.engine._call("vrfs_msm_g1_prepared_partial", self.handle, _p(scalars), int(n_columns), _p(out))
         return out
 
+    def ring_commit(self, keys, keyset_part_size, padding, tail, lagrange=True):
+        """(cx, cy, selector) commitments (3, 96) of the ring's fixed columns over this SRS (vrfs_ring_commit)"""
+        keys = _u8(keys, (-1, 64)); tail = _u8(tail, (-1, 64)); padding = _u8(padding, (64,)); out = np.zeros((3, 96), np.uint8)
+        self.engine._call("vrfs_ring_commit", self.handle, int(bool(lagrange)), C.c_size_t(keyset_part_size), C.c_size_t(len(keys)), _p(keys),
+                          _p(padding), C.c_size_t(len(tail)), _p(tail), _p(out))
+        return out
+
     def release(self):
         if self.handle:
             self.engine._lib.vrfs_msm_g1_release(self.handle)
@@ -261,6 +268,23 @@ class Engine:
     def g1_sum_partials(self, partials, n_columns=1):
         partials = _u8(partials, (-1, n_columns, 144)); out = np.zeros((n_columns, 96), np.uint8)
         self._call("vrfs_g1_sum_partials", int(len(partials)), int(n_columns), _p(partials), _p(out))
+        return out
+
+    # ---- ring fixed columns
+    def ring_fixed_columns(self, domain_size, keyset_part_size, keys, padding, tail):
+        """xs | ys | selector of the ring's fixed columns: (3, domain_size, 32) canonical LE values of BLS12-381 Fr"""
+        keys = _u8(keys, (-1, 64)); tail = _u8(tail, (-1, 64)); padding = _u8(padding, (64,))
+        out = np.zeros((3, domain_size, 32), np.uint8)
+        self._call("vrfs_ring_fixed_columns", C.c_size_t(domain_size), C.c_size_t(keyset_part_size), C.c_size_t(len(keys)), _p(keys), _p(padding),
+                   C.c_size_t(len(tail)), _p(tail), _p(out))
+        return out
+
+    def fr_fft(self, values, n_columns=1, inverse=False):
+        """Radix2EvaluationDomain::fft / ifft over BLS12-381 Fr on n_columns vectors of 2^k canonical LE values"""
+        values = _u8(values, (-1, 32)); n = len(values) // n_columns
+        assert n * n_columns == len(values) and n and not (n & (n - 1)), "column length must be a power of two"
+        out = np.zeros_like(values)
+        self._call("vrfs_fr_fft_batch", int(n.bit_length() - 1), int(n_columns), int(bool(inverse)), _p(values), _p(out))
         return out
 
     # ---- measurement

@@ -144,6 +144,30 @@ void vrfs_msm_g1_release(vrfs_msm_bases* bases);
 vrfs_status vrfs_msm_g1_partial(vrfs_ctx*, size_t n, const uint8_t* bases, const uint8_t* scalars, int n_columns, uint8_t* out_partial /*n_columns*144*/);
 vrfs_status vrfs_g1_sum_partials(vrfs_ctx*, int n_parts, int n_columns, const uint8_t* partials /*n_parts*n_columns*144*/, uint8_t* out /*n_columns*96*/);
 
+/* ---- ring fixed columns and their commitments -----------------------------------------------------------
+ * What `ring` -> RingContext::verifier_key / prover_key -> ring-proof `index` -> PiopParams::fixed_columns + FixedColumns::commit
+ * compute (named at /root/reference/src/lib.rs:13-17; the ring-proof crate itself is not available offline, so the row layout
+ * is given by the caller instead of being hard-coded):
+ *   row i of the domain (size N, a power of two):  keys[i]                      for i <  n_keys
+ *                                                  padding                      for n_keys <= i < keyset_part_size
+ *                                                  tail[i - keyset_part_size]   for the next n_tail rows (the powers 2^j * H)
+ *                                                  (0, 0)                       after that
+ *   columns: xs | ys | selector (1 on the first keyset_part_size rows), N canonical 32-byte LE values of BLS12-381 Fr each.
+ * Points are affine x || y (64 B) of the suite whose base field is BLS12-381 Fr (Bandersnatch). */
+vrfs_status vrfs_ring_fixed_columns(vrfs_ctx*, size_t domain_size, size_t keyset_part_size, size_t n_keys, const uint8_t* keys /*n_keys*64*/,
+                                    const uint8_t* padding /*64*/, size_t n_tail, const uint8_t* tail /*n_tail*64*/,
+                                    uint8_t* out_columns /*3*domain_size*32*/);
+/* The three KZG commitments (cx, cy, selector) of those columns over a prepared SRS of exactly domain_size G1 points
+ * (vrfs_msm_g1_prepare).  srs_is_lagrange != 0: the bases are [L_i(tau)]G1 over the domain (ring-proof's `Ring`, the updatable
+ * form) and the columns are committed as they are; 0: the bases are the monomial powers [tau^i]G1 (`index` / `FixedColumns::commit`)
+ * and the columns are interpolated first (inverse FFT below).  Both give the same three points.  out: 3 * 96 bytes affine. */
+vrfs_status vrfs_ring_commit(vrfs_ctx*, const vrfs_msm_bases* srs, int srs_is_lagrange, size_t keyset_part_size, size_t n_keys,
+                             const uint8_t* keys, const uint8_t* padding, size_t n_tail, const uint8_t* tail, uint8_t* out_commitment /*3*96*/);
+/* ark-poly Radix2EvaluationDomain::fft (inverse = 0: coefficients -> evaluations) / ::ifft (inverse != 0) over BLS12-381 Fr for
+ * n_columns vectors of 2^log_n canonical 32-byte LE values (values >= r are reduced); group_gen = TWO_ADIC_ROOT_OF_UNITY^(2^(32-log_n)).
+ * in and out may be the same buffer. */
+vrfs_status vrfs_fr_fft_batch(vrfs_ctx*, int log_n, int n_columns, int inverse, const uint8_t* in /*n_columns*2^log_n*32*/, uint8_t* out);
+
 /* measurement helper: runs the IMAD.WIDE.U32 issue-rate microbenchmark used as the integer-pipe roofline
  * denominator; returns multiply-accumulates (32x32+64) per second over the whole GPU. */
 vrfs_status vrfs_measure_mac32_peak(vrfs_ctx*, int variant, double* out_mac_per_s, double* out_sm_mhz_est);

@@ -1,0 +1,153 @@
+"""GPU tests of SURVEY.md 8f-2: the fixed columns of a ring, the radix-2 FFT over BLS12-381 Fr and the three KZG commitments
+(vrfs_ring_fixed_columns, vrfs_fr_fft_batch, vrfs_ring_commit; api.RingContext).  The ring-proof crate is not available offline,
+so these tests pin MATHEMATICS (the FFT against its definition over ark-ff's domain generator; Lagrange-basis and monomial SRS
+give the same commitment, equal to [sum_i col_i L_i(tau)] G computed with big integers) - the row layout itself is a parameter."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import vectors as V
+
+pytestmark = pytest.mark.gpu
+R_BLS = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
+ROOT = 10238227357739495823651030575849232062558860180284477541189508159991286009131   # ark-ff Fr::TWO_ADIC_ROOT_OF_UNITY = 7^((r-1)/2^32)
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import ark_ec_vrfs_b200 as vrfs
+    e = vrfs.Engine(0)
+    yield e
+    e.close()
+
+
+def le32(vals):
+    return np.frombuffer(b"".join(int(v).to_bytes(32, "little") for v in vals), np.uint8).reshape(-1, 32).copy()
+
+
+def ints(a):
+    return [int.from_bytes(r.tobytes(), "little") for r in np.asarray(a, np.uint8).reshape(-1, 32)]
+
+
+def domain_gen(logn):
+    assert pow(7, (R_BLS - 1) >> 32, R_BLS) == ROOT
+    return pow(ROOT, 1 << (32 - logn), R_BLS)
+
+
+def rand_fr(n, tag):
+    return [int.from_bytes(hashlib.sha512(tag + b"%d" % i).digest(), "little") % R_BLS for i in range(n)]
+
+
+@pytest.mark.parametrize("logn", [0, 1, 4, 7])
+def test_fft_matches_its_definition(eng, logn):
+    n = 1 << logn
+    w = domain_gen(logn)
+    cols = [rand_fr(n, b"fft%d-%d" % (logn, c)) for c in range(2)]
+    got = eng.fr_fft(le32(cols[0] + cols[1]), 2, inverse=False)
+    for c in range(2):
+        exp = [sum(cols[c][j] * pow(w, i * j, R_BLS) for j in range(n)) % R_BLS for i in range(n)]
+        assert ints(got[c * n:(c + 1) * n]) == exp
+    # ifft is the inverse map, natural order on both sides
+    assert ints(eng.fr_fft(got, 2, inverse=True)) == cols[0] + cols[1]
+
+
+@pytest.mark.parametrize("logn,ncol", [(10, 1), (11, 3), (13, 2), (17, 3)])
+def test_fft_round_trip_and_linearity(eng, logn, ncol):
+    n = 1 << logn
+    rng = np.random.default_rng(logn)
+    a = rng.integers(0, 256, size=(ncol * n, 32), dtype=np.uint8); a[:, 31] &= 0x3F
+    ev = eng.fr_fft(a, ncol)
+    assert np.array_equal(eng.fr_fft(ev, ncol, inverse=True), a)
+    # evaluation 0 is the sum of the coefficients; a constant polynomial evaluates to itself everywhere
+    for c in range(ncol):
+        assert ints(ev[c * n:c * n + 1])[0] == sum(ints(a[c * n:(c + 1) * n])) % R_BLS
+    const = np.zeros((n, 32), np.uint8); const[0] = a[0]
+    assert np.array_equal(eng.fr_fft(const, 1), np.tile(a[0], (n, 1)))
+    # values >= r are reduced on load
+    big = np.full((n, 32), 0xFF, np.uint8)
+    assert ints(eng.fr_fft(eng.fr_fft(big, 1), 1, inverse=True)) == [((1 << 256) - 1) % R_BLS] * n
+
+
+def test_ring_fixed_columns_layout(eng):
+    n, part = 64, 40
+    _, pk, inp, _ = V.make_keys_inputs(O.BANDERSNATCH, 20)
+    keys, tail, padding = pk[:7], inp[:10], pk[19]
+    cols = eng.ring_fixed_columns(n, part, keys, padding, tail)
+    assert cols.shape == (3, n, 32)
+    pts = np.concatenate([cols[0], cols[1]], axis=1)                  # row i = x || y
+    assert np.array_equal(pts[:7], keys)
+    assert np.array_equal(pts[7:part], np.tile(padding, (part - 7, 1)))
+    assert np.array_equal(pts[part:part + 10], tail)
+    assert not pts[part + 10:].any()
+    sel = ints(cols[2])
+    assert sel == [1] * part + [0] * (n - part)
+    # a full ring, no tail, no padding needed
+    cols = eng.ring_fixed_columns(16, 16, pk[:16], padding, np.zeros((0, 64), np.uint8))
+    assert np.array_equal(np.concatenate([cols[0], cols[1]], axis=1), pk[:16]) and ints(cols[2]) == [1] * 16
+    import ark_ec_vrfs_b200 as vrfs
+    with pytest.raises(vrfs.VrfsError):
+        eng.ring_fixed_columns(48, 40, keys, padding, tail)            # not a power of two
+    with pytest.raises(vrfs.VrfsError):
+        eng.ring_fixed_columns(64, 60, keys, padding, tail)            # tail does not fit
+
+
+def test_ring_commit_lagrange_equals_monomial_equals_direct(eng):
+    """test-only SRS with a public tau: [tau^i]G (monomial) and [L_i(tau)]G (Lagrange over the radix-2 domain)"""
+    import ark_ec_vrfs_b200 as vrfs
+    logn = 8; n = 1 << logn
+    tau = int.from_bytes(hashlib.sha512(b"vrfs-b200-bench-tau").digest(), "little") % R_BLS
+    w = domain_gen(logn)
+    mono = [pow(tau, i, R_BLS) for i in range(n)]
+    zn = (pow(tau, n, R_BLS) - 1) * pow(n, -1, R_BLS) % R_BLS
+    lag = [zn * pow(w, i, R_BLS) * pow((tau - pow(w, i, R_BLS)) % R_BLS, -1, R_BLS) % R_BLS for i in range(n)]
+    assert sum(lag) % R_BLS == 1
+    srs_mono, srs_lag = O.g1_mul_gen(le32(mono)), O.g1_mul_gen(le32(lag))
+    _, pk, inp, _ = V.make_keys_inputs(O.BANDERSNATCH, 150)
+    keys, tail, padding = pk[:100], inp[:50], pk[149]
+    part = n - 3 - len(tail) - 1
+    from ark_ec_vrfs_b200 import api
+    suite = api.Suite(vrfs.BANDERSNATCH, eng)
+    cols = eng.ring_fixed_columns(n, part, keys, padding, tail)
+    direct = O.g1_mul_gen(le32([sum(c * l for c, l in zip(ints(cols[k]), lag)) % R_BLS for k in range(3)]))
+    outs = []
+    for srs, is_lag in ((srs_lag, True), (srs_mono, False)):
+        h = eng.msm_g1_prepare(srs)
+        try:
+            outs.append(h.ring_commit(keys, part, padding, tail, lagrange=is_lag))
+            if is_lag:
+                assert np.array_equal(h.msm(cols.reshape(-1, 32), 3), outs[-1])
+        finally:
+            h.release()
+    assert np.array_equal(outs[0], direct) and np.array_equal(outs[1], direct)
+    # the API mirror: defaults of the row layout, serialised RingCommitment
+    ctx = api.RingContext(suite, srs_lag, True, padding, tail)
+    try:
+        assert ctx.keyset_part_size == part and np.array_equal(ctx.verifier_key_commitment(keys), direct)
+        blob = ctx.ring_commitment_bytes(keys)
+        assert blob.shape == (144,) and all(blob[48 * k] & 0x80 for k in range(3)) and not any(blob[48 * k] & 0x40 for k in range(3))
+        x0 = int.from_bytes(bytes([blob[0] & 0x1F]) + blob[1:48].tobytes(), "big")
+        assert x0 == int.from_bytes(direct[0, :48].tobytes(), "little")
+    finally:
+        ctx.release()
+
+
+def test_ring_commit_at_ring_size_2p10(eng):
+    """domain 2^11 (ring size 2^10): the one-call commitment equals the MSM of the columns it builds"""
+    n = 1 << 11
+    rng = np.random.default_rng(3)
+    ks = np.zeros((n, 32), np.uint8); ks[:, :8] = rng.integers(1, 2 ** 62, size=n, dtype=np.uint64).view(np.uint8).reshape(n, 8)
+    srs = O.g1_mul_gen(ks)
+    _, pk, inp, _ = V.make_keys_inputs(O.BANDERSNATCH, 1024)
+    tail = np.tile(inp[:23], (11, 1))                                   # 253 rows
+    part = n - 3 - len(tail) - 1
+    h = eng.msm_g1_prepare(srs)
+    try:
+        cols = eng.ring_fixed_columns(n, part, pk, pk[0], tail)
+        got = h.ring_commit(pk, part, pk[0], tail, lagrange=True)
+        assert np.array_equal(got, h.msm(cols.reshape(-1, 32), 3)) and got.any()
+        coef = eng.fr_fft(cols.reshape(-1, 32), 3, inverse=True)
+        assert np.array_equal(h.ring_commit(pk, part, pk[0], tail, lagrange=False), h.msm(coef, 3))
+    finally:
+        h.release()
