@@ -57,7 +57,7 @@ VRFS_HD inline MsmPlan msm_plan(uint32_t n, uint32_t ncol, int prepared, int c_o
   uint64_t avg = ((uint64_t)n * (prepared ? p.windows : 1)) / p.nb;      // expected entries per bucket for uniform digits
   const uint64_t total_buckets = (uint64_t)ncol * (prepared ? 1 : p.windows) * p.nb;
   p.tpb = 1; while (p.tpb < 32 && (avg / p.tpb > 24 || (total_buckets * p.tpb < 65536 && avg / p.tpb >= 4))) p.tpb *= 2;
-  p.big = (uint32_t)(8 * (avg + 8));
+  p.big = (uint32_t)(3 * avg + 64);     // far above any natural load (Poisson tail); a padded ring's repeated point (N/4..N/2 entries per window) must land here
   // batched-affine rounds (k_msm_aff_round) are OFF unless VRFS_MSM_AFF asks for them: measured on B200 at N = 2^17 x 3 they
   // take 3.48 ms against 3.30 ms of the XYZZ pass (round 0 alone 1.55 ms for half the additions) - see the note above the kernels
   p.aff_rounds = 0;
@@ -70,8 +70,8 @@ VRFS_HD inline MsmPlan msm_plan(uint32_t n, uint32_t ncol, int prepared, int c_o
 #define MSM_BIG_THREADS 128
 #define MSM_SLICE 256u           // an oversized bucket is cut into slices of about this many entries, one block each
 #define MSM_MAX_SLICES 256u
-// capacity of the slice list: buckets above p.big = 8 (avg + 8) entries number < buckets / 8
-VRFS_HD inline size_t msm_big_capacity(size_t nbuckets, size_t total_entries) { return nbuckets / 8 + total_entries / MSM_SLICE + 64; }
+// capacity of the slice list: buckets above p.big = 3 avg + 64 entries number < buckets / 3; every slice has >= MSM_SLICE entries but the last
+VRFS_HD inline size_t msm_big_capacity(size_t nbuckets, size_t total_entries) { return nbuckets / 2 + total_entries / MSM_SLICE + 64; }
 
 HD_INLINE void g1_load_aff(G1Pt& P, const G1Aff* a, bool negate) {
   uint4* d = reinterpret_cast<uint4*>(&P);
@@ -479,7 +479,10 @@ __global__ void __launch_bounds__(256) k_msm_scan(MsmPlan p, const uint32_t* cou
   for (int i = lo; i < hi; i++) {
     o[i] = run; run += c[i];
     if (c[i] > p.big) {                                       // one work item per slice of ~MSM_SLICE entries
-      const uint32_t nsl = min((uint32_t)MSM_MAX_SLICES, (c[i] + MSM_SLICE - 1) / MSM_SLICE);
+      // every slice ends in a block-wide tree of complete additions (~5 mixed additions' worth per thread), so long buckets get
+      // longer slices: 256 entries up to 4096, 1024 above (4096-entry slices measured worse: too few blocks for a lone long bucket)
+      const uint32_t slice = c[i] > 16u * MSM_SLICE ? 4u * MSM_SLICE : MSM_SLICE;
+      const uint32_t nsl = min((uint32_t)MSM_MAX_SLICES, (c[i] + slice - 1) / slice);
       const uint32_t first = atomicAdd(big_count, nsl);
       for (uint32_t sl = 0; sl < nsl; sl++) { big_list[2 * (first + sl)] = seg * p.nb + i; big_list[2 * (first + sl) + 1] = sl | (nsl << 16); }
     }

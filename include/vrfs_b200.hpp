@@ -192,4 +192,42 @@ inline Bytes ring_commitment_msm(Engine& e, const Bytes& bases /*n*96*/, const B
   return out;
 }
 
+
+// ring::RingContext up to the verifier key's commitment: holds the prepared SRS of one power-of-two domain
+// (Lagrange basis [L_i(tau)]G1 or monomial powers [tau^i]G1, 96-byte affine points) and the row layout of the fixed columns:
+// keys | padding up to keyset_part_size | tail (the powers 2^j * H of the blinding base) | zero rows; selector = 1 on the key slots.
+// [RECALL, unpinned: the ring-proof crate is not available offline] default keyset_part_size = N - 3 (ZK rows) - |tail| - 1.
+class RingContext {
+ public:
+  RingContext(Engine& e, const Bytes& srs_g1, bool lagrange, const Bytes& padding /*64*/, const Bytes& tail /*n_tail*64*/, size_t keyset_part_size = 0)
+      : e_(&e), lagrange_(lagrange), padding_(padding), tail_(tail), n_(srs_g1.size() / 96) {
+    part_ = keyset_part_size ? keyset_part_size : n_ - 3 - tail.size() / 64 - 1;
+    e.check(vrfs_msm_g1_prepare(e.ctx(), n_, srs_g1.data(), &srs_));
+  }
+  ~RingContext() { if (srs_) vrfs_msm_g1_release(srs_); }
+  RingContext(const RingContext&) = delete;
+  RingContext& operator=(const RingContext&) = delete;
+  size_t domain_size() const { return n_; }
+  size_t max_ring_size() const { return part_; }
+  // xs | ys | selector, 3 * N canonical 32-byte LE values
+  Bytes fixed_columns(const Bytes& public_keys /*n*64*/) const {
+    Bytes out(3 * n_ * 32);
+    e_->check(vrfs_ring_fixed_columns(e_->ctx(), n_, part_, public_keys.size() / 64, public_keys.data(), padding_.data(), tail_.size() / 64, tail_.data(), out.data()));
+    return out;
+  }
+  // cx | cy | selector, 3 * 96 bytes affine
+  Bytes verifier_key_commitment(const Bytes& public_keys) const {
+    Bytes out(3 * 96);
+    e_->check(vrfs_ring_commit(e_->ctx(), srs_, lagrange_ ? 1 : 0, part_, public_keys.size() / 64, public_keys.data(), padding_.data(), tail_.size() / 64, tail_.data(), out.data()));
+    return out;
+  }
+
+ private:
+  Engine* e_;
+  bool lagrange_;
+  Bytes padding_, tail_;
+  size_t n_, part_ = 0;
+  vrfs_msm_bases* srs_ = nullptr;
+};
+
 }  // namespace vrfs

@@ -75,6 +75,26 @@ int main() {
     auto [vok, beta] = Public::verify_signatures(s, k.public_().serialize_compressed(), {Bytes{}}, sig, {Bytes{}});
     CHECK(vok[0] == 1);
     CHECK(hex(beta.data(), 64) == "fdeb377a4ffd7f95ebe48e5b43a88d069ce62188e49493500315ad55ee04d7442b93c4c91d5475370e9380496f4bc0b838c2483bce4e133c6f18b0adbb9e4722");
+    // RingContext mirror: the one-call commitment equals the MSM of the columns it builds (SRS: multiples of one valid point -
+    // any G1 points serve for this identity; here N copies of the BLS12-381 G1 generator), and the FFT round-trips
+    {
+      const size_t N = 64, NK = 20;
+      Bytes g1 = unhex("bbc622db0af03afbef1a7af93fe8556c58ac1b173f3a4ea105b974974f8c68c30faca94f8c63952694d79731a7d3f117"
+                       "e1e7c5462923aa0ce48a88a244c73cd0edb3042ccb18db00f60ad0d595e0f5fce48a1d74ed309ea0f1a0aae381f4b308");
+      Bytes srs; for (size_t i = 0; i < N; i++) srs.insert(srs.end(), g1.begin(), g1.end());
+      std::vector<Bytes> seeds; for (size_t i = 0; i < NK + 6; i++) seeds.push_back(bytes("ring-" + std::to_string(i)));
+      Bytes pts = Secret::from_seed(s, seeds).public_points;
+      Bytes keys(pts.begin(), pts.begin() + 64 * NK), padding(pts.begin() + 64 * NK, pts.begin() + 64 * (NK + 1)), tail(pts.begin() + 64 * (NK + 1), pts.end());
+      RingContext rc(eng, srs, true, padding, tail);
+      CHECK(rc.max_ring_size() == N - 3 - 5 - 1);
+      Bytes cols = rc.fixed_columns(keys), com = rc.verifier_key_commitment(keys);
+      CHECK(std::memcmp(cols.data(), keys.data(), 32) == 0 && cols[2 * N * 32] == 1 && cols[(3 * N - 1) * 32] == 0);
+      CHECK(com == ring_commitment_msm(eng, srs, cols, 3));
+      Bytes ev(cols.size()), back(cols.size());
+      eng.check(vrfs_fr_fft_batch(eng.ctx(), 6, 3, 0, cols.data(), ev.data()));
+      eng.check(vrfs_fr_fft_batch(eng.ctx(), 6, 3, 1, ev.data(), back.data()));
+      CHECK(back == cols && ev != cols);
+    }
     // a whole-call failure is an exception, not a verdict
     bool threw = false;
     try { vrfs_status st = vrfs_ietf_verify_batch(eng.ctx(), (vrfs_suite)9, 1, sig.data(), sig.data(), sig.data(), sig.data(), sig.data(), nullptr, nullptr, sig.data()); eng.check(st); }
