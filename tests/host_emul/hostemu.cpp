@@ -190,3 +190,13 @@ extern "C" int hostemu_fq381_inv_fast(const uint32_t* a_mont, uint32_t* out_mont
   memcpy(out_mont, r.v, 48);
   return finished;
 }
+
+// generator of the radix-2 domain of size 2^logn over BLS12-381 Fr (csrc/ring.cuh), canonical limbs out
+#include "../../ark_ec_vrfs_b200/csrc/ring.cuh"
+extern "C" void hostemu_ntt_domain_gen(int logn, int inverse, uint32_t* out_canonical) {
+  Fr255 w = ntt_domain_gen(logn, inverse != 0);
+  from_mont<BlsFr>(out_canonical, w);
+}
+extern "C" void hostemu_ntt_inv_n(int logn, uint32_t* out_canonical) {
+  from_mont<BlsFr>(out_canonical, fr_pow_u32(ntt_const(2), (uint32_t)logn));
+}

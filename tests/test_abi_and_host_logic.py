@@ -164,3 +164,19 @@ def test_fq381_binary_euclid_inverse(emu):
         emu.hostemu_fq381_inv(A, out)
         got = sum(int(out[i]) << (32 * i) for i in range(12))
         assert got == (pow(a, -1, p) * Rm % p if a else 0), a
+
+
+def test_ntt_domain_generators_match_ark_ff(emu):
+    """csrc/ring.cuh: the FFT of vrfs_fr_fft_batch runs on Radix2EvaluationDomain's generator
+    TWO_ADIC_ROOT_OF_UNITY^(2^(32 - log n)) with TWO_ADIC_ROOT_OF_UNITY = 7^((r-1)/2^32) (ark-bls12-381 Fr), and scales by 1/n"""
+    r = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
+    root = pow(7, (r - 1) >> 32, r)
+    assert root == 10238227357739495823651030575849232062558860180284477541189508159991286009131
+    out = (C.c_uint32 * 8)()
+    val = lambda: sum(int(out[i]) << (32 * i) for i in range(8))
+    for logn in (0, 1, 5, 11, 17, 26, 32):
+        w = pow(root, 1 << (32 - logn), r)
+        emu.hostemu_ntt_domain_gen(logn, 0, out); assert val() == w
+        emu.hostemu_ntt_domain_gen(logn, 1, out); assert val() == pow(w, -1, r)
+        assert pow(w, 1 << logn, r) == 1 and (logn == 0 or pow(w, 1 << (logn - 1), r) == r - 1)
+        emu.hostemu_ntt_inv_n(logn, out); assert val() == pow(1 << logn, -1, r)
