@@ -39,7 +39,7 @@ struct MsmPlan {
   int aff_rounds;                // bucket accumulation: pairwise rounds in affine coordinates before the XYZZ pass (0: XYZZ only)
   int rc_h;                      // segment reduction: columns H of the R x H bucket matrix summed by k_msm_rc (0: nb <= 256, k_msm_wsum takes the buckets directly)
 };
-VRFS_HD inline MsmPlan msm_plan(uint32_t n, uint32_t ncol, int prepared, int c_override = 0, int aff_override = -1) {
+VRFS_HD inline MsmPlan msm_plan(uint32_t n, uint32_t ncol, int prepared, int c_override = 0, int aff_override = -1, int tpb_override = 0) {
   MsmPlan p; p.n = n; p.ncol = ncol; p.prepared = prepared;
   int lg = 0; while ((1u << (lg + 1)) <= n) lg++;
   // prepared mode: all windows of a column share one bucket set, so a short top window (255 mod c bits) piles n entries onto
@@ -52,11 +52,12 @@ VRFS_HD inline MsmPlan msm_plan(uint32_t n, uint32_t ncol, int prepared, int c_o
   p.nb = 1 << (p.c - 1);
   p.seg_windows = prepared ? 1 : p.windows;
   // small domains are latency-bound on chains of dependent additions: spread every stage over more threads
-  // (4 buckets per thread in the segment reduction below 2^13 buckets; >= 4 entries per thread in a bucket until the grid holds ~64 K threads)
+  // (>= 2 entries per thread in a bucket until the grid holds ~64 K threads: the in-bucket tree is cooperative and cheap)
   p.chunk = p.nb <= 8192 ? 4 : 8;
   uint64_t avg = ((uint64_t)n * (prepared ? p.windows : 1)) / p.nb;      // expected entries per bucket for uniform digits
   const uint64_t total_buckets = (uint64_t)ncol * (prepared ? 1 : p.windows) * p.nb;
-  p.tpb = 1; while (p.tpb < 32 && (avg / p.tpb > 24 || (total_buckets * p.tpb < 65536 && avg / p.tpb >= 4))) p.tpb *= 2;
+  p.tpb = 1; while (p.tpb < 32 && (avg / p.tpb > 24 || (total_buckets * p.tpb < 65536 && avg / p.tpb >= 2))) p.tpb *= 2;
+  if (tpb_override >= 1 && tpb_override <= 32 && !(tpb_override & (tpb_override - 1))) p.tpb = tpb_override;       // tuning (VRFS_MSM_TPB)
   p.big = (uint32_t)(3 * avg + 64);     // far above any natural load (Poisson tail); a padded ring's repeated point (N/4..N/2 entries per window) must land here
   // batched-affine rounds (k_msm_aff_round) are OFF unless VRFS_MSM_AFF asks for them: measured on B200 at N = 2^17 x 3 they
   // take 3.48 ms against 3.30 ms of the XYZZ pass (round 0 alone 1.55 ms for half the additions) - see the note above the kernels
@@ -544,12 +545,31 @@ __global__ void __launch_bounds__(128, MSM_ACC_MINBLOCKS) k_msm_accumulate(MsmPl
     msm_accumulate_entries(acc, bases, l, lane, cnt, (uint32_t)p.tpb);
   }
   if (p.tpb > 1) {
+    // tree over the tpb partial sums of every bucket of the block: the first level (64 additions per block) one thread per
+    // addition, the later ones (32, 16, ... additions per block) by the block's 16 cooperative groups of 8 lanes
     copy_words16(&sh[threadIdx.x], &acc);
     __syncthreads();
-    for (int stride = p.tpb >> 1; stride > 0; stride >>= 1) {
-      if ((int)lane < stride) { G1Pt y; copy_words16(&y, &sh[threadIdx.x + stride]); sw_add<G1Curve>(&acc, &acc, &y); copy_words16(&sh[threadIdx.x], &acc); }
+    int stride = p.tpb >> 1;
+    if ((int)lane < stride) { G1Pt y; copy_words16(&y, &sh[threadIdx.x + stride]); sw_add<G1Curve>(&acc, &acc, &y); copy_words16(&sh[threadIdx.x], &acc); }
+    __syncthreads();
+    const unsigned grp = threadIdx.x >> 3, g = threadIdx.x & 7u;
+    for (stride >>= 1; stride > 0; stride >>= 1) {
+      const int adds = (128 / p.tpb) * stride;                   // <= 32
+      for (int a0 = 0; a0 < adds; a0 += 16) {
+        if ((int)(a0 + (grp & ~3u)) < adds) {                    // warp-uniform: the warp holds a live group
+          const int a = a0 + (int)grp;
+          const bool on = a < adds;
+          const int slot = on ? (a / stride) * p.tpb + (a % stride) : stride;      // idle groups read what nobody writes at this level
+          G1Pt x, y, z;
+          copy_words16(&x, &sh[slot]); copy_words16(&y, &sh[on ? slot + stride : slot]);
+          g1_coop_add(&z, &x, &y);
+          __syncwarp();
+          if (on && g == 0) copy_words16(&sh[slot], &z);
+        }
+      }
       __syncthreads();
     }
+    if (lane == 0) copy_words16(&acc, &sh[threadIdx.x]);
   }
   if (live && lane == 0 && counts[b] <= p.big) copy_words16(&buckets[b], &acc);
 }

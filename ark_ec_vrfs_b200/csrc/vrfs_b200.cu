@@ -1309,6 +1309,10 @@ static int msm_c_override(int prepared) {
   const char* e = getenv(prepared ? "VRFS_MSM_C" : "VRFS_MSM_C_STATELESS");
   return e ? atoi(e) : 0;
 }
+static int msm_tpb_override() {
+  const char* e = getenv("VRFS_MSM_TPB");
+  return e ? atoi(e) : 0;
+}
 static int msm_aff_override() {
   const char* e = getenv("VRFS_MSM_AFF");
   return e ? atoi(e) : -1;
@@ -1453,7 +1457,7 @@ extern "C" vrfs_status vrfs_msm_g1_prepare(vrfs_ctx* ctx, size_t n, const uint8_
   ST(begin_call(ctx, n));
   vrfs_msm_bases* h = new (std::nothrow) vrfs_msm_bases();
   if (!h) return fail(ctx, VRFS_CUDA_ERROR, "out of host memory");
-  h->ctx = ctx; h->n = n; h->plan = msm_plan((uint32_t)n, 1, 1, msm_c_override(1), msm_aff_override()); h->Q = nullptr;
+  h->ctx = ctx; h->n = n; h->plan = msm_plan((uint32_t)n, 1, 1, msm_c_override(1), msm_aff_override(), msm_tpb_override()); h->Q = nullptr;
   cudaError_t e = cudaMalloc(&h->Q, (size_t)h->plan.windows * n * sizeof(G1Aff));
   if (e != cudaSuccess) { delete h; return fail(ctx, VRFS_CUDA_ERROR, "cudaMalloc of the prepared table failed: %s", cudaGetErrorString(e)); }
   *out = h;
@@ -1483,7 +1487,7 @@ static vrfs_status msm_prepared_host(vrfs_ctx* ctx, const vrfs_msm_bases* h, con
   const uint8_t* d_s; uint8_t* d_o;
   ST(stage_in(ctx, BUF_IN1, scalars, h->n * 32 * (size_t)n_columns, &d_s));
   ST(stage_out(ctx, BUF_OUT0, ob * n_columns, &d_o));
-  MsmPlan p = msm_plan((uint32_t)h->n, (uint32_t)n_columns, 1, msm_c_override(1), msm_aff_override());
+  MsmPlan p = msm_plan((uint32_t)h->n, (uint32_t)n_columns, 1, msm_c_override(1), msm_aff_override(), msm_tpb_override());
   ST(msm_dev(ctx, p, h->Q, d_s, d_o, out_mode));
   ST(copy_out(ctx, out, d_o, ob * n_columns));
   return finish_call(ctx);
@@ -1576,7 +1580,7 @@ extern "C" vrfs_status vrfs_ring_commit(vrfs_ctx* ctx, const vrfs_msm_bases* srs
     ST(ntt_dev(ctx, logn, 3, 1, d_cols, d_cols));
   }
   ST(stage_out(ctx, BUF_OUT0, 3 * 96, &d_o));
-  ST(msm_dev(ctx, msm_plan((uint32_t)n, 3, 1, msm_c_override(1), msm_aff_override()), srs->Q, d_cols, d_o, 0));
+  ST(msm_dev(ctx, msm_plan((uint32_t)n, 3, 1, msm_c_override(1), msm_aff_override(), msm_tpb_override()), srs->Q, d_cols, d_o, 0));
   ST(copy_out(ctx, out_commitment, d_o, 3 * 96));
   return finish_call(ctx);
 }

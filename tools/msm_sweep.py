@@ -18,7 +18,7 @@ for logn in range(lo, hi + 1):
     bases = np.tile(base2k, (max(1, n // 2048), 1))[:n]
     sc = rng.integers(0, 256, size=(3 * n, 32), dtype=np.uint8); sc[:, 31] &= 0x3F
     ref = None; row = {}
-    for c in [0] + list(range(max(8, logn - 3), min(18, logn + 5) + 1)):
+    for c in [0] + ([] if os.environ.get("SWEEP_AUTO_ONLY") else list(range(max(8, logn - 3), min(18, logn + 5) + 1))):
         if c: os.environ["VRFS_MSM_C"] = str(c)
         else: os.environ.pop("VRFS_MSM_C", None)
         h = e.msm_g1_prepare(bases)
