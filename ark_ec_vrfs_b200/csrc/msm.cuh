@@ -12,8 +12,8 @@
 //   k_msm_scatter         point indices (+ sign bit) grouped by bucket (counting sort)
 //   k_msm_accumulate      one thread per bucket: complete additions of its points
 //   k_msm_accumulate_big  one block per oversized bucket (top window / skewed scalar columns such as ring selectors)
-//   k_msm_window          one block per segment: chunked running sums  sum_j j*B_j, shared-memory tree
-//   k_msm_final           one thread per column: Horner over the windows (stateless mode only); partial or affine out
+//   k_msm_rc / k_msm_wsum segment value sum_j j*B_j: row / column sums of the bucket matrix, then a cluster-wide halving recursion
+//   k_msm_final2          one warp per column: Horner over the windows (stateless mode only); partial or affine out
 // Stateless mode (vrfs_msm_g1_bls12_381): segment = (column, window).  Prepared mode (vrfs_msm_g1_prepare + _prepared,
 // the analogue of RingContext holding the SRS): segment = column, no Horner chain (255 dependent doublings ~ 2.5 ms).
 #pragma once
@@ -33,7 +33,6 @@ struct MsmPlan {
   int c, windows, nb;            // window bits, digit windows per scalar, buckets per segment (2^(c-1))
   int prepared;                  // 1: bases pre-multiplied by 2^(c*w) -> ONE bucket segment per column, no Horner
   int seg_windows;               // segments per column: `windows` (stateless) or 1 (prepared)
-  int chunk;                     // buckets per thread in the segment reduction
   int tpb;                       // threads cooperating on one bucket in k_msm_accumulate (power of two <= 32)
   uint32_t big;                  // buckets with more entries than this go to k_msm_accumulate_big
   int aff_rounds;                // bucket accumulation: pairwise rounds in affine coordinates before the XYZZ pass (0: XYZZ only)
@@ -53,7 +52,6 @@ VRFS_HD inline MsmPlan msm_plan(uint32_t n, uint32_t ncol, int prepared, int c_o
   p.seg_windows = prepared ? 1 : p.windows;
   // small domains are latency-bound on chains of dependent additions: spread every stage over more threads
   // (>= 2 entries per thread in a bucket until the grid holds ~64 K threads: the in-bucket tree is cooperative and cheap)
-  p.chunk = p.nb <= 8192 ? 4 : 8;
   uint64_t avg = ((uint64_t)n * (prepared ? p.windows : 1)) / p.nb;      // expected entries per bucket for uniform digits
   const uint64_t total_buckets = (uint64_t)ncol * (prepared ? 1 : p.windows) * p.nb;
   p.tpb = 1; while (p.tpb < 32 && (avg / p.tpb > 24 || (total_buckets * p.tpb < 65536 && avg / p.tpb >= 2))) p.tpb *= 2;
@@ -302,10 +300,9 @@ HD_NOINLINE Fq381 fq381_inv_fast(const Fq381& x) {
 
 #ifdef __CUDACC__
 // =================================================================================================
-// Segment reduction, second generation (MSM_TAIL = 2, the default): everything after the bucket sums is a chain of
+// Segment reduction (second generation): everything after the bucket sums is a chain of
 // DEPENDENT point additions on very few points, and one thread needs ~11 us per complete addition (12 products of
-// 12 limbs on a multiplier pipe that retires one 64-bit product per ~6 cycles per warp).  Two changes against the
-// chunk / tree kernels above (kept behind MSM_TAIL = 1 for A/B):
+// 12 limbs on a multiplier pipe that retires one 64-bit product per ~6 cycles per warp).  Two ideas:
 //  * lane-cooperative arithmetic: a complete addition is 6 independent products, a few additions, 6 more independent
 //    products.  A group of 8 lanes holds the operands replicated; lane g computes product g of each level and the six
 //    results are exchanged with shuffles: ~3 us per addition / doubling instead of ~11 (g1_coop_add, g1_coop_dbl).
@@ -314,10 +311,9 @@ HD_NOINLINE Fq381 fq381_inv_fast(const Fq381& x) {
 //    (2) for the two short weighted sums the halving recursion  W(x) = W(y) + sum_u x_{2u+1},  y_u = 2 (x_{2u} + x_{2u+1})
 //    run by one cluster of 8 thread blocks (128 cooperating groups, one warp per SM sub-partition, k_msm_wsum): no
 //    multiplication by chunk offsets and no Horner chain.
+// (First generation - one thread per chunk of buckets with a double-and-add by the chunk offset, a block tree, a one-thread final -
+//  took 1.11 ms at 2^17 x 3 against 0.41 ms now; it is in the history before session 4.)
 // =================================================================================================
-#ifndef MSM_TAIL
-#define MSM_TAIL 2
-#endif
 #define MSM_WSUM_CLUSTER 8
 #define MSM_WSUM_GROUPS (MSM_WSUM_CLUSTER * 16)          // 8 blocks x 4 warps x 4 groups of 8 lanes
 #define MSM_WSUM_MAXM 512                                  // longest weighted sum one cluster takes
@@ -786,50 +782,6 @@ __global__ void __launch_bounds__(MSM_BIG_THREADS) k_msm_big_combine(const uint3
     __syncthreads();
   }
 }
-// r = k * p for a small non-negative k (double-and-add, MSB first)
-__device__ __forceinline__ void g1_mul_small(G1Pt& r, const G1Pt& p, uint32_t k) {
-  sw_set_identity(r);
-  for (int bit = 31 - __clz(k | 1u); bit >= 0; bit--) {
-    g1_dbl(&r, &r);
-    if ((k >> bit) & 1u) sw_add<G1Curve>(&r, &r, &p);
-  }
-}
-// segment sum = sum_{j=1..nb} j * B_j in two stages.  Stage 1: one thread per chunk of p.chunk buckets (running sums),
-// partial[seg][t] = sum over its chunk of j * B_j.  Stage 2: one block per segment tree-sums the nb / chunk partials.
-__global__ void __launch_bounds__(128) k_msm_window_chunks(MsmPlan p, const G1Pt* buckets, G1Pt* partials) {
-  const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t per_seg = p.nb / p.chunk;
-  const size_t segs = (size_t)p.ncol * p.seg_windows;
-  if (g >= segs * per_seg) return;
-  const size_t seg = g / per_seg;
-  const uint32_t t = (uint32_t)(g % per_seg);
-  const G1Pt* B = buckets + seg * p.nb;
-  const int lo = t * p.chunk;              // bucket index j-1 in [lo, lo + chunk)
-  G1Pt run, tot; sw_set_identity(run); sw_set_identity(tot);
-  for (int j = lo + p.chunk - 1; j >= lo; j--) {
-    G1Pt q; copy_words16(&q, &B[j]);
-    sw_add<G1Curve>(&run, &run, &q);
-    sw_add<G1Curve>(&tot, &tot, &run);
-  }
-  // tot = sum (j - lo + 1) * B_j (bucket value j+1 at index j)  ->  add lo * run
-  if (lo > 0) { G1Pt m; g1_mul_small(m, run, (uint32_t)lo); sw_add<G1Curve>(&tot, &tot, &m); }
-  copy_words16(&partials[g], &tot);
-}
-__global__ void __launch_bounds__(256) k_msm_window_sum(MsmPlan p, const G1Pt* partials, G1Pt* window_sums) {
-  __shared__ uint4 sh_raw[256 * sizeof(G1Pt) / 16];
-  G1Pt* sh = reinterpret_cast<G1Pt*>(sh_raw);
-  const uint32_t seg = blockIdx.x, t = threadIdx.x, per_seg = p.nb / p.chunk;
-  const G1Pt* P = partials + (size_t)seg * per_seg;
-  G1Pt acc; sw_set_identity(acc);
-  for (uint32_t j = t; j < per_seg; j += 256) { G1Pt q; copy_words16(&q, &P[j]); sw_add<G1Curve>(&acc, &acc, &q); }
-  copy_words16(&sh[t], &acc);
-  __syncthreads();
-  for (int stride = 128; stride > 0; stride >>= 1) {
-    if ((int)t < stride) { G1Pt y; copy_words16(&y, &sh[t + stride]); sw_add<G1Curve>(&acc, &acc, &y); copy_words16(&sh[t], &acc); }
-    __syncthreads();
-  }
-  if (t == 0) copy_words16(&window_sums[seg], &sh[0]);
-}
 // row and column sums of the bucket matrix of every segment: out[seg][hi] = sum_lo B[hi*H + lo] (hi < R = nb / H),
 // out[seg][R + lo] = sum_hi B[hi*H + lo].  One block per sum; the last five tree levels (<= 16 additions) are cooperative.
 __global__ void __launch_bounds__(128) k_msm_rc(MsmPlan p, const G1Pt* buckets, G1Pt* out) {
@@ -941,31 +893,6 @@ __global__ void __launch_bounds__(32) k_msm_final2(MsmPlan p, int nparts, const 
   } else {
     uint8_t* o = out + (size_t)96 * col;
     Fq381 zi = fq381_inv(acc.Z);                // identity: Z = 0 -> zi = 0 -> zeros
-    from_mont<BlsFq>(raw, acc.X * zi); store_le<12>(o, raw);
-    from_mont<BlsFq>(raw, acc.Y * zi); store_le<12>(o + 48, raw);
-  }
-}
-// combine the segments of a column (Horner over windows when not prepared);
-// out_mode 0: affine LE canonical (96 B, identity = zeros); 1: projective X,Y,Z LE canonical (144 B)
-__global__ void k_msm_final(MsmPlan p, const G1Pt* window_sums, uint8_t* out, int out_mode) {
-  uint32_t col = blockIdx.x * blockDim.x + threadIdx.x;
-  if (col >= p.ncol) return;
-  const G1Pt* W = window_sums + (size_t)col * p.seg_windows;
-  G1Pt acc = W[p.seg_windows - 1];
-  for (int w = p.seg_windows - 2; w >= 0; w--) {
-    for (int k = 0; k < p.c; k++) g1_dbl(&acc, &acc);
-    G1Pt q = W[w];
-    sw_add<G1Curve>(&acc, &acc, &q);
-  }
-  uint32_t raw[12];
-  if (out_mode == 1) {
-    uint8_t* o = out + (size_t)144 * col;
-    from_mont<BlsFq>(raw, acc.X); store_le<12>(o, raw);
-    from_mont<BlsFq>(raw, acc.Y); store_le<12>(o + 48, raw);
-    from_mont<BlsFq>(raw, acc.Z); store_le<12>(o + 96, raw);
-  } else {
-    uint8_t* o = out + (size_t)96 * col;
-    Fq381 zi = fq381_inv_fast(acc.Z);                // identity: Z = 0 -> zi = 0 -> zeros
     from_mont<BlsFq>(raw, acc.X * zi); store_le<12>(o, raw);
     from_mont<BlsFq>(raw, acc.Y * zi); store_le<12>(o + 48, raw);
   }

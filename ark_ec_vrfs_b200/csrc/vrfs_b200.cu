@@ -1320,7 +1320,6 @@ static int msm_aff_override() {
 static vrfs_status msm_dev(vrfs_ctx* ctx, MsmPlan p, const void* d_bases, const uint8_t* d_scalars, uint8_t* d_out, int out_mode) {
   const size_t n = p.n, ncol = p.ncol;
   const size_t segs = ncol * p.seg_windows, nbuckets = segs * p.nb, seg_len = n * (p.prepared ? p.windows : 1);
-  const size_t per_seg = p.nb / p.chunk; (void)per_seg;
   void *counts = nullptr, *list = nullptr, *buckets = nullptr, *wsum = nullptr;
   // counts | offsets | cursors | big_count (16 words) | slice list of the oversized buckets (2 words per slice) ; partial sums of the slices
   const size_t bigcap = msm_big_capacity(nbuckets, segs * seg_len);
@@ -1330,17 +1329,12 @@ static vrfs_status msm_dev(vrfs_ctx* ctx, MsmPlan p, const void* d_bases, const 
   G1Pt* bigpart = (G1Pt*)(((uintptr_t)((uint32_t*)counts + w1_words) + 15) & ~(uintptr_t)15);
   ST(ensure(ctx, BUF_W2, segs * seg_len * sizeof(uint32_t), &list));
   ST(ensure(ctx, BUF_W3, nbuckets * sizeof(G1Pt), &buckets));
-#if MSM_TAIL == 1
-  ST(ensure(ctx, BUF_SLAB, (segs + segs * per_seg) * sizeof(G1Pt), &wsum));
-  G1Pt* partials = (G1Pt*)wsum + segs;
-#else
   // parts[segs * nparts] | row and column sums [segs * (R + H)] | scratch of the weighted sums
   const unsigned nparts = p.rc_h ? 2u : 1u;
   const size_t rc_len = p.rc_h ? (size_t)(p.nb / p.rc_h + p.rc_h) : 0;
   ST(ensure(ctx, BUF_SLAB, (segs * nparts + segs * rc_len + segs * nparts * MSM_WSUM_SCRATCH) * sizeof(G1Pt), &wsum));
   G1Pt* rc_out = (G1Pt*)wsum + segs * nparts;
   G1Pt* wscratch = rc_out + segs * rc_len;
-#endif
   CU(cudaMemsetAsync(counts, 0, (nbuckets * 3 + 16) * sizeof(uint32_t), ctx->stream));
   const unsigned tsc = (unsigned)((n * ncol + 127) / 128);
   k_msm_histogram<<<tsc, 128, 0, ctx->stream>>>(p, d_scalars, (uint32_t*)counts);
@@ -1399,14 +1393,6 @@ static vrfs_status msm_dev(vrfs_ctx* ctx, MsmPlan p, const void* d_bases, const 
   LAUNCHED_AS(ctx, "msm_accumulate_big");
   k_msm_big_combine<<<bigb, MSM_BIG_THREADS, 0, ctx->stream>>>(big_list, big_count, bigpart, (G1Pt*)buckets);
   LAUNCHED_AS(ctx, "msm_big_combine");
-#if MSM_TAIL == 1
-  k_msm_window_chunks<<<(unsigned)((segs * per_seg + 127) / 128), 128, 0, ctx->stream>>>(p, (const G1Pt*)buckets, partials);
-  LAUNCHED_AS(ctx, "msm_window_chunks");
-  k_msm_window_sum<<<(unsigned)segs, 256, 0, ctx->stream>>>(p, partials, (G1Pt*)wsum);
-  LAUNCHED_AS(ctx, "msm_window_sum");
-  k_msm_final<<<1, 32, 0, ctx->stream>>>(p, (const G1Pt*)wsum, d_out, out_mode);
-  LAUNCHED_AS(ctx, "msm_final");
-#else
   if (p.rc_h) {
     k_msm_rc<<<dim3((unsigned)rc_len, (unsigned)segs), 128, 0, ctx->stream>>>(p, (const G1Pt*)buckets, rc_out);
     LAUNCHED_AS(ctx, "msm_rc");
@@ -1415,7 +1401,6 @@ static vrfs_status msm_dev(vrfs_ctx* ctx, MsmPlan p, const void* d_bases, const 
   LAUNCHED_AS(ctx, "msm_wsum");
   k_msm_final2<<<(unsigned)ncol, 32, 0, ctx->stream>>>(p, (int)nparts, (const G1Pt*)wsum, d_out, out_mode);
   LAUNCHED_AS(ctx, "msm_final");
-#endif
   return VRFS_OK;
 }
 static vrfs_status msm_host(vrfs_ctx* ctx, size_t n, const uint8_t* bases, const uint8_t* scalars, int ncol, uint8_t* out, int out_mode) {
