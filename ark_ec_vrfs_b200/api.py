@@ -256,6 +256,7 @@ class RingContext:
         self.padding = np.asarray(padding, np.uint8).reshape(64)
         self.keyset_part_size = (self.domain_size - RING_ZK_ROWS - len(self.tail) - 1) if keyset_part_size is None else int(keyset_part_size)
         self.srs = self.engine.msm_g1_prepare(srs_g1)
+        self._empty = None                                            # commitment of the ring of padding only (Lagrange SRS)
 
     def max_ring_size(self):
         return self.keyset_part_size
@@ -263,9 +264,27 @@ class RingContext:
     def fixed_columns(self, public_keys):
         return self.engine.ring_fixed_columns(self.domain_size, self.keyset_part_size, public_keys, self.padding, self.tail)
 
-    def verifier_key_commitment(self, public_keys):
-        """(3, 96) affine commitments cx, cy, selector"""
-        return self.srs.ring_commit(public_keys, self.keyset_part_size, self.padding, self.tail, self.lagrange)
+    def verifier_key_commitment(self, public_keys, incremental=None):
+        """(3, 96) affine commitments cx, cy, selector.  With a Lagrange-basis SRS the commitment of the all-padding ring is kept
+        and only sum (pk_i - padding) L_i over the real keys is computed per ring (incremental=False forces the full MSM)"""
+        keys = np.asarray(public_keys, np.uint8).reshape(-1, 64)
+        if incremental is None:
+            incremental = self.lagrange
+        if not incremental:
+            return self.srs.ring_commit(keys, self.keyset_part_size, self.padding, self.tail, self.lagrange)
+        assert self.lagrange, "the incremental form needs a Lagrange-basis SRS"
+        assert len(keys) <= self.keyset_part_size
+        if self._empty is None:
+            self._empty = self.srs.ring_commit(np.zeros((0, 64), np.uint8), self.keyset_part_size, self.padding, self.tail, True)
+        delta = self.srs.ring_commit_delta(keys, self.padding)
+        parts = np.zeros((2, 3, 144), np.uint8)                       # projective X | Y | Z; identity (0 : 1 : 0)
+        for k, pts in enumerate((self._empty, np.concatenate([delta, np.zeros((1, 96), np.uint8)]))):
+            for c in range(3):
+                if pts[c].any():
+                    parts[k, c, :96] = pts[c]; parts[k, c, 96] = 1
+                else:
+                    parts[k, c, 48] = 1
+        return self.engine.g1_sum_partials(parts, 3)
 
     def ring_commitment_bytes(self, public_keys):
         """the 144-byte serialised RingCommitment: three compressed G1 points"""

@@ -51,6 +51,25 @@ __global__ void k_ring_columns(uint32_t n, uint32_t keyset_part, uint32_t n_keys
   cx[0] = x0; cx[1] = x1; cy[0] = y0; cy[1] = y1;
   cs[0] = make_uint4(i < keyset_part ? 1u : 0u, 0, 0, 0); cs[1] = z;
 }
+// the homomorphic form (ring-proof's `Ring::append`): columns[0][i] = x_i - pad_x, columns[1][i] = y_i - pad_y (mod r) on the key rows,
+// zero elsewhere, so that  commit(ring) = commit(all-padding ring) + MSM(delta columns)  costs n_keys entries per window
+HD_INLINE Fr255 fr_load_reduced(const uint8_t* p) {            // canonical LE -> residue < r (values < 2^256 < 3 r)
+  Fr255 v;
+  load_le<8>(v.v, p);
+  cond_sub_p<BlsFr>(v.v, 0u); cond_sub_p<BlsFr>(v.v, 0u);
+  return v;
+}
+__global__ void k_ring_delta_columns(uint32_t n, uint32_t n_keys, const uint8_t* keys, const uint8_t* padding, uint8_t* columns) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr255 dx = Fr255::zero(), dy = Fr255::zero();
+  if (i < n_keys) {
+    dx = fr_load_reduced(keys + (size_t)64 * i) - fr_load_reduced(padding);
+    dy = fr_load_reduced(keys + (size_t)64 * i + 32) - fr_load_reduced(padding + 32);
+  }
+  store_le<8>(columns + (size_t)32 * i, dx.v);
+  store_le<8>(columns + (size_t)32 * ((size_t)n + i), dy.v);
+}
 // tw[j] = w^j, j < n/2 (Montgomery form)
 __global__ void k_ntt_twiddles(int logn, int inverse, Fr255* tw) {
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;

@@ -1569,6 +1569,25 @@ extern "C" vrfs_status vrfs_ring_commit(vrfs_ctx* ctx, const vrfs_msm_bases* srs
   ST(copy_out(ctx, out_commitment, d_o, 3 * 96));
   return finish_call(ctx);
 }
+extern "C" vrfs_status vrfs_ring_commit_delta(vrfs_ctx* ctx, const vrfs_msm_bases* srs_lagrange, size_t n_keys, const uint8_t* keys,
+                                              const uint8_t* padding, uint8_t* out_delta) {
+  if (!ctx || !srs_lagrange || srs_lagrange->ctx != ctx) return VRFS_BAD_ARG;
+  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
+  const size_t n = srs_lagrange->n;
+  if (!out_delta || !padding || (n_keys && !keys) || n_keys > n) return fail(ctx, VRFS_BAD_ARG, "bad argument (n_keys <= domain size, non-null buffers)");
+  ST(begin_call(ctx, n));
+  const uint8_t *d_k = nullptr, *d_p = nullptr; uint8_t* d_o = nullptr;
+  ST(stage_in(ctx, BUF_IN0, keys, n_keys * 64, &d_k));
+  ST(stage_in(ctx, BUF_IN2, padding, 64, &d_p));
+  void* cols = nullptr;
+  ST(ensure(ctx, BUF_IN1, 2 * n * 32, &cols));
+  k_ring_delta_columns<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((uint32_t)n, (uint32_t)n_keys, d_k, d_p, (uint8_t*)cols);
+  LAUNCHED_AS(ctx, "ring_delta_columns");
+  ST(stage_out(ctx, BUF_OUT0, 2 * 96, &d_o));
+  ST(msm_dev(ctx, msm_plan((uint32_t)n, 2, 1, msm_c_override(1), msm_aff_override(), msm_tpb_override()), srs_lagrange->Q, (const uint8_t*)cols, d_o, 0));
+  ST(copy_out(ctx, out_delta, d_o, 2 * 96));
+  return finish_call(ctx);
+}
 extern "C" vrfs_status vrfs_g1_sum_partials(vrfs_ctx* ctx, int n_parts, int n_columns, const uint8_t* partials, uint8_t* out) {
   if (!ctx) return VRFS_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lock_(ctx->mu);

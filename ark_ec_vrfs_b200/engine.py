@@ -53,6 +53,12 @@ class PreparedBases:
                           _p(padding), C.c_size_t(len(tail)), _p(tail), _p(out))
         return out
 
+    def ring_commit_delta(self, keys, padding):
+        """[sum (x_i - pad_x) L_i, sum (y_i - pad_y) L_i] over a Lagrange-basis SRS: (2, 96) (vrfs_ring_commit_delta)"""
+        keys = _u8(keys, (-1, 64)); padding = _u8(padding, (64,)); out = np.zeros((2, 96), np.uint8)
+        self.engine._call("vrfs_ring_commit_delta", self.handle, C.c_size_t(len(keys)), _p(keys), _p(padding), _p(out))
+        return out
+
     def release(self):
         if self.handle:
             self.engine._lib.vrfs_msm_g1_release(self.handle)

@@ -125,6 +125,11 @@ def test_ring_commit_lagrange_equals_monomial_equals_direct(eng):
     ctx = api.RingContext(suite, srs_lag, True, padding, tail)
     try:
         assert ctx.keyset_part_size == part and np.array_equal(ctx.verifier_key_commitment(keys), direct)
+        # the incremental form (all-padding commitment + delta over the real keys) gives the same points for every ring size
+        for nk in (0, 1, 100, part):
+            ks = np.tile(keys, (3, 1))[:nk]
+            assert np.array_equal(ctx.verifier_key_commitment(ks, incremental=True), ctx.verifier_key_commitment(ks, incremental=False)), nk
+        assert np.array_equal(ctx.verifier_key_commitment(np.tile(padding, (5, 1)), incremental=True), ctx.verifier_key_commitment(keys[:0], incremental=False))
         blob = ctx.ring_commitment_bytes(keys)
         assert blob.shape == (144,) and all(blob[48 * k] & 0x80 for k in range(3)) and not any(blob[48 * k] & 0x40 for k in range(3))
         x0 = int.from_bytes(bytes([blob[0] & 0x1F]) + blob[1:48].tobytes(), "big")

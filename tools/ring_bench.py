@@ -23,10 +23,12 @@ for logn in (11, 14, 17):
     part = n - 3 - len(tail) - 1
     h = e.msm_g1_prepare(srs)
     row = {}
-    for name, lag in (("lagrange", True), ("monomial", False)):
+    for name, lag in (("lagrange", True), ("monomial", False), ("lagrange_delta", None)):
         best = None
         for _ in range(4):
-            e.enable_kernel_timing(True); t = time.perf_counter(); out = h.ring_commit(keys, part, pk0[0], tail, lagrange=lag); wall = (time.perf_counter() - t) * 1e3
+            e.enable_kernel_timing(True); t = time.perf_counter()
+            out = h.ring_commit(keys, part, pk0[0], tail, lagrange=lag) if lag is not None else h.ring_commit_delta(keys, pk0[0])
+            wall = (time.perf_counter() - t) * 1e3
             kt = e.kernel_timings(); e.enable_kernel_timing(False)
             ms = sum(v for _, v in kt)
             if best is None or ms < best[0]: best = (ms, wall, kt)
