@@ -193,7 +193,7 @@ HD_NOINLINE Fq381 fq381_inv(const Fq381& a) {
 }
 
 // 1/a in BLS12-381 Fq, second version: binary GCD on word-sized approximations (Pornin, "Optimized Binary GCD for Modular
-// Inversion", 2020), 32-bit flavour.  Each of the 26 outer rounds reads the top 32 and the low 30 bits of (a, b) into two
+// Inversion", 2020), 32-bit flavour.  Each of the at most 26 outer rounds (the loop leaves as soon as a = 0, typically after 18-20) reads the top 32 and the low 30 bits of (a, b) into two
 // 62-bit words, runs 30 branch-free binary-GCD steps on them while recording the 2x2 update matrix (entries <= 2^30), and
 // applies the matrix once to the 12-limb a, b (exact division by 2^30) and to u, v (division by 2^30 mod p with one
 // Montgomery-style correction word).  ~1/4 of the instructions of fq381_inv and no data-dependent branch, so the 32 lanes of a
@@ -216,8 +216,9 @@ HD_INLINE bool fq381_inv_bingcd(Fq381& out, const Fq381& x) {        // false: t
 #pragma unroll 1
   for (int round = 0; round < 26; round++) {
     // bit length n of a | b, window position sp = max(n - 32, 30)
-    uint32_t topw = 0; int topi = 0;
-    for (int i = 0; i < 12; i++) { const uint32_t w = a[i] | b[i]; if (w) { topw = w; topi = i; } }
+    uint32_t topw = 0, anz = 0; int topi = 0;
+    for (int i = 0; i < 12; i++) { const uint32_t w = a[i] | b[i]; if (w) { topw = w; topi = i; } anz |= a[i]; }
+    if (anz == 0) break;                                          // a = 0: b = gcd and v is final (u, v carry no pending power of two)
 #ifdef __CUDA_ARCH__
     const int lz = __clz((int)topw);
 #else
@@ -459,20 +460,29 @@ __global__ void __launch_bounds__(128) k_msm_histogram(MsmPlan p, const uint8_t*
   }
 }
 // one block per segment: exclusive scan of nb counts -> offsets (relative to the segment); also lists the big buckets
-__global__ void __launch_bounds__(256) k_msm_scan(MsmPlan p, const uint32_t* counts, uint32_t* offsets, uint32_t* big_list, uint32_t* big_count) {
-  __shared__ uint32_t part[256];
+#define MSM_SCAN_THREADS 1024
+__global__ void __launch_bounds__(MSM_SCAN_THREADS) k_msm_scan(MsmPlan p, const uint32_t* counts, uint32_t* offsets, uint32_t* big_list, uint32_t* big_count) {
+  __shared__ uint32_t part[MSM_SCAN_THREADS];
   const uint32_t seg = blockIdx.x;
   const uint32_t* c = counts + (size_t)seg * p.nb;
   uint32_t* o = offsets + (size_t)seg * p.nb;
-  const int per = (p.nb + 255) / 256;
+  const int per = (p.nb + MSM_SCAN_THREADS - 1) / MSM_SCAN_THREADS;
   const int lo = threadIdx.x * per, hi = min(lo + per, p.nb);
   uint32_t s = 0;
   for (int i = lo; i < hi; i++) s += c[i];
-  part[threadIdx.x] = s;
+  // block-wide exclusive scan of the per-thread sums: warp scans by shuffle, then the 32 warp totals
+  const uint32_t lane_ = threadIdx.x & 31u, warp_ = threadIdx.x >> 5;
+  uint32_t incl = s;
+  for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if ((int)lane_ >= d) incl += v; }
+  if (lane_ == 31) part[warp_] = incl;
   __syncthreads();
-  if (threadIdx.x == 0) { uint32_t run = 0; for (int i = 0; i < 256; i++) { uint32_t v = part[i]; part[i] = run; run += v; } }
+  if (warp_ == 0) {
+    uint32_t w = part[lane_], wi = w;
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, wi, d); if ((int)lane_ >= d) wi += v; }
+    part[lane_] = wi - w;
+  }
   __syncthreads();
-  uint32_t run = part[threadIdx.x];
+  uint32_t run = part[warp_] + incl - s;
   for (int i = lo; i < hi; i++) {
     o[i] = run; run += c[i];
     if (c[i] > p.big) {                                       // one work item per slice of ~MSM_SLICE entries
@@ -892,7 +902,7 @@ __global__ void __launch_bounds__(32) k_msm_final2(MsmPlan p, int nparts, const 
     from_mont<BlsFq>(raw, acc.Z); store_le<12>(o + 96, raw);
   } else {
     uint8_t* o = out + (size_t)96 * col;
-    Fq381 zi = fq381_inv(acc.Z);                // identity: Z = 0 -> zi = 0 -> zeros
+    Fq381 zi = fq381_inv_fast(acc.Z);                // identity: Z = 0 -> zi = 0 -> zeros
     from_mont<BlsFq>(raw, acc.X * zi); store_le<12>(o, raw);
     from_mont<BlsFq>(raw, acc.Y * zi); store_le<12>(o + 48, raw);
   }

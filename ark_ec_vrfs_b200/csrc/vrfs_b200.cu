@@ -1339,7 +1339,7 @@ static vrfs_status msm_dev(vrfs_ctx* ctx, MsmPlan p, const void* d_bases, const 
   const unsigned tsc = (unsigned)((n * ncol + 127) / 128);
   k_msm_histogram<<<tsc, 128, 0, ctx->stream>>>(p, d_scalars, (uint32_t*)counts);
   LAUNCHED_AS(ctx, "msm_histogram");
-  k_msm_scan<<<(unsigned)segs, 256, 0, ctx->stream>>>(p, (const uint32_t*)counts, offsets, big_list, big_count);
+  k_msm_scan<<<(unsigned)segs, MSM_SCAN_THREADS, 0, ctx->stream>>>(p, (const uint32_t*)counts, offsets, big_list, big_count);
   LAUNCHED_AS(ctx, "msm_scan");
   k_msm_scatter<<<tsc, 128, 0, ctx->stream>>>(p, d_scalars, offsets, cursors, (uint32_t*)list);
   LAUNCHED_AS(ctx, "msm_scatter");
@@ -1586,6 +1586,33 @@ extern "C" vrfs_status vrfs_ring_commit_delta(vrfs_ctx* ctx, const vrfs_msm_base
   ST(stage_out(ctx, BUF_OUT0, 2 * 96, &d_o));
   ST(msm_dev(ctx, msm_plan((uint32_t)n, 2, 1, msm_c_override(1), msm_aff_override(), msm_tpb_override()), srs_lagrange->Q, (const uint8_t*)cols, d_o, 0));
   ST(copy_out(ctx, out_delta, d_o, 2 * 96));
+  return finish_call(ctx);
+}
+// self-test / measurement helper: 1/a in BLS12-381 Fq for n canonical 48-byte LE values (0 -> 0); ok[i] = 1 when the
+// word-approximation GCD finished on its own (no fallback to the binary Euclid) - the GPU tests require that for every a != 0
+__global__ void k_fq381_inv_batch(uint32_t n, const uint8_t* in, uint8_t* out, uint8_t* ok) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t raw[12];
+  load_le<12>(raw, in + (size_t)48 * i);
+  const Fq381 a = to_mont<BlsFq>(raw);
+  Fq381 t;
+  ok[i] = fq381_inv_bingcd(t, a) ? 1 : 0;
+  from_mont<BlsFq>(raw, fq381_inv_fast(a));
+  store_le<12>(out + (size_t)48 * i, raw);
+}
+extern "C" vrfs_status vrfs_fq381_inv_batch(vrfs_ctx* ctx, size_t n, const uint8_t* in, uint8_t* out, uint8_t* out_ok) {
+  if (!ctx) return VRFS_BAD_ARG;
+  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
+  if (n && (!in || !out || !out_ok)) return fail(ctx, VRFS_BAD_ARG, "null buffer");
+  if (n == 0) return VRFS_OK;
+  ST(begin_call(ctx, n));
+  const uint8_t* d_i; uint8_t *d_o, *d_k;
+  ST(stage_in(ctx, BUF_IN0, in, n * 48, &d_i));
+  ST(stage_out(ctx, BUF_OUT0, n * 48, &d_o)); ST(stage_out(ctx, BUF_OUT1, n, &d_k));
+  k_fq381_inv_batch<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((uint32_t)n, d_i, d_o, d_k);
+  LAUNCHED_AS(ctx, "fq381_inv_batch");
+  ST(copy_out(ctx, out, d_o, n * 48)); ST(copy_out(ctx, out_ok, d_k, n));
   return finish_call(ctx);
 }
 extern "C" vrfs_status vrfs_g1_sum_partials(vrfs_ctx* ctx, int n_parts, int n_columns, const uint8_t* partials, uint8_t* out) {

@@ -293,6 +293,12 @@ class Engine:
         self._call("vrfs_fr_fft_batch", int(n.bit_length() - 1), int(n_columns), int(bool(inverse)), _p(values), _p(out))
         return out
 
+    def fq381_inv(self, values):
+        """self-test helper: inverses in BLS12-381 Fq of (n, 48) canonical LE values -> (inverses, fast-path flags)"""
+        values = _u8(values, (-1, 48)); out = np.zeros_like(values); ok = np.zeros(len(values), np.uint8)
+        self._call("vrfs_fq381_inv_batch", C.c_size_t(len(values)), _p(values), _p(out), _p(ok))
+        return out, ok
+
     # ---- measurement
     def enable_kernel_timing(self, on=True):
         self._check(self._lib.vrfs_ctx_enable_kernel_timing(self._ctx, int(bool(on))))

@@ -123,7 +123,7 @@ def ncu_fmaheavy(kernel):
         return None
 
 
-def msm_extra(eng):
+def msm_extra(eng, peak_mac=None, hbm_peak=None):
     """second half of BASELINE's metric: ring KZG commitment MSM (3 columns, BLS12-381 G1) in ms, prepared SRS bases,
     for the domain sizes of ring sizes 2^10 and 2^16 (N = 2^11, 2^17).  Bases k_i*G are produced by the engine itself."""
     import numpy as np
@@ -151,10 +151,24 @@ def msm_extra(eng):
         eng.enable_kernel_timing(True)
         for _ in range(3):
             h.msm(sc, 3)
-        dev_ms = sum(ms for _, ms in eng.kernel_timings())
+        kt = dict(eng.kernel_timings())
+        dev_ms = sum(kt.values())
         eng.enable_kernel_timing(False)
         t0 = time.perf_counter(); h.msm(sc, 3); wall = (time.perf_counter() - t0) * 1e3
         out["2^%d" % logn] = {"device_ms": dev_ms, "e2e_ms": wall}
+        # roofline of the dominant MSM kernel (bucket accumulation): every non-zero signed digit is one XYZZ mixed addition
+        # = 10 products of 12 limbs = 10 x 300 MAC32, and one 96-byte table record + one 4-byte list entry of HBM traffic
+        c = 8 if logn <= 9 else 10 if logn <= 12 else 13 if logn <= 14 else 15 if logn <= 17 else 16     # msm_plan's window table
+        entries = 3 * n * ((255 + c) // c)
+        acc_ms = kt.get("msm_accumulate")
+        if acc_ms:
+            r = {"kernel": "k_msm_accumulate", "ms": acc_ms, "share_of_call": acc_ms / dev_ms, "mixed_additions": entries,
+                 "achieved_tmac32": entries * 3000 / (acc_ms * 1e-3) / 1e12, "hbm_gbps": entries * 100 / (acc_ms * 1e-3) / 1e9}
+            if peak_mac:
+                r["frac_of_mac32_peak"] = r["achieved_tmac32"] * 1e12 / peak_mac
+            if hbm_peak:
+                r["frac_of_hbm_peak"] = r["hbm_gbps"] / hbm_peak
+            out["2^%d" % logn]["roofline"] = r
         # the commitment of an actual ring: ring of N/2 distinct keys, the remaining key slots padded, 253-row tail of
         # blinding-base powers, Lagrange-basis SRS; one vrfs_ring_commit call from host keys (columns built on the device)
         try:
@@ -398,7 +412,7 @@ def main():
                                    "note": "CPU restatement of the reference algorithm (oracle/vrf_oracle.c), not the arkworks binary"}
         try:
             out["ring_kzg_msm_ms"] = {"what": "3-column commitment MSM over BLS12-381 G1, prepared SRS bases (vrfs_msm_g1_prepared), domain size N, 3 random columns; ring_commit_*: the fixed columns of a ring of N/2 keys built and committed in one call (vrfs_ring_commit); ring_commit_incremental: sum (pk_i - padding) L_i only, added to the kept commitment of the all-padding ring (vrfs_ring_commit_delta)",
-                                      **msm_extra(eng)}
+                                      **msm_extra(eng, peak_mac, hbm_peak)}
         except Exception as ex:   # never lose the headline line to the secondary measurement
             out["ring_kzg_msm_ms"] = {"error": repr(ex)}
         if world == 1:

@@ -174,6 +174,10 @@ vrfs_status vrfs_ring_commit_delta(vrfs_ctx*, const vrfs_msm_bases* srs_lagrange
  * in and out may be the same buffer. */
 vrfs_status vrfs_fr_fft_batch(vrfs_ctx*, int log_n, int n_columns, int inverse, const uint8_t* in /*n_columns*2^log_n*32*/, uint8_t* out);
 
+/* self-test / measurement helper: 1/a in BLS12-381 Fq (the inversion behind the MSM's affine output) for n canonical 48-byte LE
+ * values, 0 -> 0; out_ok[i] = 1 when the word-approximation GCD finished without falling back to the binary Euclid. */
+vrfs_status vrfs_fq381_inv_batch(vrfs_ctx*, size_t n, const uint8_t* in /*n*48*/, uint8_t* out /*n*48*/, uint8_t* out_ok /*n*/);
+
 /* measurement helper: runs the IMAD.WIDE.U32 issue-rate microbenchmark used as the integer-pipe roofline
  * denominator; returns multiply-accumulates (32x32+64) per second over the whole GPU. */
 vrfs_status vrfs_measure_mac32_peak(vrfs_ctx*, int variant, double* out_mac_per_s, double* out_sm_mhz_est);

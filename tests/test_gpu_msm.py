@@ -209,3 +209,16 @@ def test_msm_batched_affine_equals_xyzz_at_2p15(eng, monkeypatch):
         h = eng.msm_g1_prepare(bases)
         outs.append(h.msm(sc, 3)); h.release()
     assert np.array_equal(outs[0], outs[1]) and outs[0].any()
+
+
+def test_fq381_inverse_on_the_gpu(eng):
+    """fq381_inv_fast as compiled for the GPU: correct, and its word-approximation GCD finishes by itself (no fallback)"""
+    P_MOD = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
+    import random
+    rnd = random.Random(5)
+    vals = [0, 1, 2, P_MOD - 1, (P_MOD + 1) // 2, 1 << 380, (1 << 62) - 1] + [rnd.randrange(P_MOD) for _ in range(2000)] + [rnd.randrange(1 << rnd.randrange(1, 381)) for _ in range(500)]
+    a = np.frombuffer(b"".join(v.to_bytes(48, "little") for v in vals), np.uint8).reshape(-1, 48)
+    inv, ok = eng.fq381_inv(a)
+    got = [int.from_bytes(r.tobytes(), "little") for r in inv]
+    assert got == [pow(v, -1, P_MOD) if v else 0 for v in vals]
+    assert list(ok) == [1 if v else 0 for v in vals]
