@@ -222,6 +222,14 @@ class RingContext {
     return out;
   }
 
+  // Lagrange-basis SRS only: [sum (x_i - pad_x) L_i, sum (y_i - pad_y) L_i] (2 * 96 bytes) - the part of the commitment that depends on
+  // the keys; add it to verifier_key_commitment({}) (the ring of padding only, computed once) with vrfs_g1_sum_partials
+  Bytes verifier_key_commitment_delta(const Bytes& public_keys) const {
+    Bytes out(2 * 96);
+    e_->check(vrfs_ring_commit_delta(e_->ctx(), srs_, public_keys.size() / 64, public_keys.data(), padding_.data(), out.data()));
+    return out;
+  }
+
  private:
   Engine* e_;
   bool lagrange_;

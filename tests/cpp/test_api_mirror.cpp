@@ -90,6 +90,17 @@ int main() {
       Bytes cols = rc.fixed_columns(keys), com = rc.verifier_key_commitment(keys);
       CHECK(std::memcmp(cols.data(), keys.data(), 32) == 0 && cols[2 * N * 32] == 1 && cols[(3 * N - 1) * 32] == 0);
       CHECK(com == ring_commitment_msm(eng, srs, cols, 3));
+      {   // homomorphic form: commitment of the padding-only ring + delta over the keys = the full commitment
+        Bytes empty = rc.verifier_key_commitment(Bytes{}), delta = rc.verifier_key_commitment_delta(keys), parts(2 * 3 * 144, 0), sum(3 * 96);
+        for (int k = 0; k < 2; k++) for (int c = 0; c < 3; c++) {
+          uint8_t* d = parts.data() + (size_t)(k * 3 + c) * 144;
+          const uint8_t* src = k == 0 ? empty.data() + 96 * c : (c < 2 ? delta.data() + 96 * c : nullptr);
+          bool inf = true; if (src) for (int j = 0; j < 96; j++) inf = inf && src[j] == 0;
+          if (inf) d[48] = 1; else { std::memcpy(d, src, 96); d[96] = 1; }
+        }
+        eng.check(vrfs_g1_sum_partials(eng.ctx(), 2, 3, parts.data(), sum.data()));
+        CHECK(sum == com);
+      }
       Bytes ev(cols.size()), back(cols.size());
       eng.check(vrfs_fr_fft_batch(eng.ctx(), 6, 3, 0, cols.data(), ev.data()));
       eng.check(vrfs_fr_fft_batch(eng.ctx(), 6, 3, 1, ev.data(), back.data()));

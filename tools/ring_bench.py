@@ -38,4 +38,4 @@ for logn in (11, 14, 17):
     t = time.perf_counter(); e.fr_fft(cols, 3, inverse=True); row["ifft_3col_wall_ms"] = round((time.perf_counter() - t) * 1e3, 3)
     h.release()
     res["2^%d" % logn] = row
-json.dump(res, open(os.path.join(ROOT, "gpurun_out", "r1o_ring_bench.json"), "w"), indent=1)
+json.dump(res, open(os.path.join(ROOT, "gpurun_out", os.environ.get("RING_BENCH_OUT", "ring_bench.json")), "w"), indent=1)
