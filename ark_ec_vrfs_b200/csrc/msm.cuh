@@ -44,7 +44,8 @@ VRFS_HD inline MsmPlan msm_plan(uint32_t n, uint32_t ncol, int prepared, int c_o
   // prepared mode: all windows of a column share one bucket set, so a short top window (255 mod c bits) piles n entries onto
   // 2^(255 mod c) buckets; the window sizes below keep that remainder at >= 5 bits (c = 12 and 14 left 3 bits: oversized
   // buckets cost 0.2-0.6 ms at 2^11..2^14)
-  if (prepared) p.c = lg <= 9 ? 8 : lg <= 12 ? 10 : lg <= 14 ? 13 : lg <= 17 ? 15 : 16;      // tools/msm_sweep.py, profiles/r1o_msm_sweep.json
+  // tools/msm_sweep.py with scalars uniform below r (profiles/r1r_msm_sweep.json): c = 16 spends no window on the carry of bit 254
+  if (prepared) p.c = lg <= 9 ? 8 : lg <= 12 ? 10 : lg <= 16 ? 13 : 16;
   else p.c = lg <= 9 ? 7 : lg <= 11 ? 9 : lg <= 13 ? 11 : lg <= 15 ? 12 : 13;
   if (c_override >= 2 && c_override <= 18) p.c = c_override;      // tuning runs only (VRFS_MSM_C / VRFS_MSM_C_STATELESS)
   p.windows = (255 + p.c) / p.c;          // 255 scalar bits + the top carry of the signed recoding

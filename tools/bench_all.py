@@ -7,6 +7,8 @@ import argparse, hashlib, json, os, sys, time
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from _scalars import fr_uniform
 import ark_ec_vrfs_b200 as vrfs
 import oracle_lib as O
 
@@ -64,7 +66,7 @@ k = rng.integers(1, 2 ** 62, size=N, dtype=np.uint64); ks = np.zeros((N, 32), np
 bases_all = O.g1_mul_gen(ks)
 for logn in range(10, a.msm_max_logn + 1):
     m = 1 << logn
-    sc = rng.integers(0, 256, size=(3 * m, 32), dtype=np.uint8); sc[:, 31] &= 0x3F
+    sc = fr_uniform(rng, 3 * m)
     t, outp = best(lambda: e.msm_g1(bases_all[:m], sc, 3))
     kt = DEV["kt"]
     if logn <= 12:

@@ -7,6 +7,8 @@ import argparse, json, os, sys, time
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from _scalars import fr_uniform
 import torch
 import torch.distributed as dist
 import ark_ec_vrfs_b200 as vrfs
@@ -35,7 +37,7 @@ res = {}
 for logn in a.logn:
     n = 1 << logn
     bases = np.tile(small, (max(1, n // 2048), 1))[:n]
-    sc = rng.integers(0, 256, size=(3 * n, 32), dtype=np.uint8); sc[:, 31] &= 0x3F
+    sc = fr_uniform(rng, 3 * n)
     sh = vd.ShardedPreparedBases(eng, bases, device=dev)
     out = sh.msm(sc, 3)
     if world > 1:                                     # every rank must hold the same commitment

@@ -5,6 +5,8 @@ import os, sys
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from _scalars import fr_uniform
 import ark_ec_vrfs_b200 as vrfs
 import oracle_lib as O
 e = vrfs.Engine(0)
@@ -14,7 +16,7 @@ base2k = O.g1_mul_gen(ks)
 for logn in (11, 14, 17):
     n = 1 << logn
     bases = np.tile(base2k, (max(1, n // 2048), 1))[:n]
-    sc = rng.integers(0, 256, size=(3 * n, 32), dtype=np.uint8); sc[:, 31] &= 0x3F
+    sc = fr_uniform(rng, 3 * n)
     sel = sc.copy(); sel[2 * n:] = 0; sel[2 * n:2 * n + n // 2, 0] = 1
     h = e.msm_g1_prepare(bases)
     for name, s in (("random x3", sc), ("x, y, selector", sel)):

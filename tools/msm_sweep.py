@@ -5,6 +5,8 @@ import json, os, sys
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from _scalars import fr_uniform
 import ark_ec_vrfs_b200 as vrfs
 import oracle_lib as O
 lo, hi = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (10, 17)
@@ -16,7 +18,7 @@ res = {}
 for logn in range(lo, hi + 1):
     n = 1 << logn
     bases = np.tile(base2k, (max(1, n // 2048), 1))[:n]
-    sc = rng.integers(0, 256, size=(3 * n, 32), dtype=np.uint8); sc[:, 31] &= 0x3F
+    sc = fr_uniform(rng, 3 * n)
     ref = None; row = {}
     for c in [0] + ([] if os.environ.get("SWEEP_AUTO_ONLY") else list(range(max(8, logn - 3), min(18, logn + 5) + 1))):
         if c: os.environ["VRFS_MSM_C"] = str(c)
