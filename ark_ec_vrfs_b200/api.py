@@ -228,7 +228,8 @@ RING_ZK_ROWS = 3
 
 
 def g1_compress(points):
-    """ark-bls12-381's G1 `serialize_compressed` (the zcash format): 48 bytes big-endian x; bit 7 of byte 0 = compressed,
+    """host-side twin of Engine.g1_compress (kept as an independent cross-check for the tests):
+    ark-bls12-381's G1 `serialize_compressed` (the zcash format): 48 bytes big-endian x; bit 7 of byte 0 = compressed,
     bit 6 = infinity, bit 5 = y is the lexicographically larger root.  points: (n, 96) affine LE, zeros = identity."""
     P = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
     pts = np.asarray(points, np.uint8).reshape(-1, 96); out = np.zeros((len(pts), 48), np.uint8)
@@ -288,7 +289,7 @@ class RingContext:
 
     def ring_commitment_bytes(self, public_keys):
         """the 144-byte serialised RingCommitment: three compressed G1 points"""
-        return g1_compress(self.verifier_key_commitment(public_keys)).reshape(-1)
+        return self.engine.g1_compress(self.verifier_key_commitment(public_keys)).reshape(-1)
 
     def release(self):
         self.srs.release()

@@ -33,7 +33,76 @@ HD_INLINE Fr255 ntt_domain_gen(int logn, bool inverse) {
   return w;
 }
 
+// ---- BLS12-381 G1 on the wire: what ark-bls12-381's CanonicalSerialize / CanonicalDeserialize (compressed, validated) do to the
+// points of a RingCommitment and of an SRS.  [RECALL, unpinned beyond the generator vector] the crate uses the zcash encoding:
+// 48 bytes, big-endian x; bit 7 of byte 0 = compressed, bit 6 = infinity, bit 5 = y is the lexicographically larger root.
+struct ExpG1Sqrt { template <class P> static HD_INLINE uint32_t get(int i) { return G1WireConsts::sqrt_exp(i); } };
+// r = [|x|] p for the curve parameter x = -0xd201000000010000 (Hamming weight 6): MSB-first double-and-add, complete formulas
+HD_INLINE void g1_mul_xabs(G1Pt& r, const G1Pt& p) {
+  r = p;
+#pragma unroll 1
+  for (int bit = 62; bit >= 0; bit--) {
+    g1_dbl(&r, &r);
+    if ((G1WireConsts::X_ABS >> bit) & 1ull) sw_add<G1Curve>(&r, &r, &p);
+  }
+}
+// prime-order subgroup test for a finite point ON THE CURVE: phi(P) = (beta x, y) equals [-x^2] P exactly on G1
+// (Scott, eprint 2021/1130, sect. 6 - the test ark-bls12-381 uses; 126 doublings + 10 additions instead of a 255-bit multiplication)
+HD_INLINE bool g1_in_subgroup(const Fq381& x, const Fq381& y) {
+  G1Pt P, Q, Q2;
+  sw_from_affine(P, x, y);
+  g1_mul_xabs(Q, P);
+  g1_mul_xabs(Q2, Q);                            // [x^2] P
+  if (Q2.Z.is_zero()) return false;
+  Fq381 beta;
+  for (int i = 0; i < 12; i++) beta.v[i] = G1WireConsts::beta(i);
+  return (beta * x) * Q2.Z == Q2.X && y * Q2.Z == neg(Q2.Y);
+}
+// 96-byte affine LE (zeros = identity) -> 48-byte compressed
+HD_INLINE void g1_compress_one(uint8_t* out, const uint8_t* in) {
+  uint32_t rx[12], ry[12];
+  load_le<12>(rx, in); load_le<12>(ry, in + 48);
+  uint32_t any = 0;
+  for (int i = 0; i < 12; i++) any |= rx[i] | ry[i];
+  for (int i = 0; i < 12; i++) { const uint32_t w = rx[11 - i]; out[4 * i] = (uint8_t)(w >> 24); out[4 * i + 1] = (uint8_t)(w >> 16); out[4 * i + 2] = (uint8_t)(w >> 8); out[4 * i + 3] = (uint8_t)w; }
+  if (!any) { out[0] = 0xC0; return; }
+  const bool high = is_high(to_mont<BlsFq>(ry));
+  out[0] |= 0x80 | (high ? 0x20 : 0);
+}
+// 48-byte compressed -> 96-byte affine LE; false (and zeros) for a non-canonical / off-curve / out-of-subgroup encoding
+HD_INLINE bool g1_decompress_one(uint8_t* out, const uint8_t* in, bool check_subgroup) {
+  for (int i = 0; i < 96; i++) out[i] = 0;
+  const uint8_t b0 = in[0];
+  uint32_t rx[12];
+  for (int i = 0; i < 12; i++) {
+    const uint8_t* p = in + 4 * (11 - i);
+    rx[i] = ((uint32_t)(i == 11 ? (p[0] & 0x1F) : p[0]) << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3];
+  }
+  if (!(b0 & 0x80)) return false;                // only the compressed form travels here
+  uint32_t any = 0;
+  for (int i = 0; i < 12; i++) any |= rx[i];
+  if (b0 & 0x40) return !(b0 & 0x20) && any == 0;   // infinity: nothing else may be set
+  if (!is_canonical<BlsFq>(rx)) return false;
+  const Fq381 x = to_mont<BlsFq>(rx), rhs = sqr(x) * x + G1Curve::b();
+  Fq381 y = pow_const<BlsFq, ExpG1Sqrt>(rhs);
+  if (!(sqr(y) == rhs)) return false;            // x is not the abscissa of a point
+  if (is_high(y) != ((b0 & 0x20) != 0)) y = neg(y);
+  if (check_subgroup && !g1_in_subgroup(x, y)) return false;
+  uint32_t ry[12];
+  from_mont<BlsFq>(ry, y);
+  store_le<12>(out, rx); store_le<12>(out + 48, ry);
+  return true;
+}
+
 #ifdef __CUDACC__
+__global__ void k_g1_compress(uint32_t n, const uint8_t* in, uint8_t* out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) g1_compress_one(out + (size_t)48 * i, in + (size_t)96 * i);
+}
+__global__ void __launch_bounds__(128) k_g1_decompress(uint32_t n, const uint8_t* in, int check_subgroup, uint8_t* out, uint8_t* ok) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) ok[i] = g1_decompress_one(out + (size_t)96 * i, in + (size_t)48 * i, check_subgroup != 0) ? 1 : 0;
+}
 // columns[0] = xs, [1] = ys, [2] = selector; every value canonical 32-byte LE (points arrive as affine x || y, 64 B)
 __global__ void k_ring_columns(uint32_t n, uint32_t keyset_part, uint32_t n_keys, const uint8_t* keys, const uint8_t* padding,
                                uint32_t n_tail, const uint8_t* tail, uint8_t* columns) {

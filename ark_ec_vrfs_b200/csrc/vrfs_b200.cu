@@ -1588,6 +1588,34 @@ extern "C" vrfs_status vrfs_ring_commit_delta(vrfs_ctx* ctx, const vrfs_msm_base
   ST(copy_out(ctx, out_delta, d_o, 2 * 96));
   return finish_call(ctx);
 }
+extern "C" vrfs_status vrfs_g1_compress_batch(vrfs_ctx* ctx, size_t n, const uint8_t* points, uint8_t* out) {
+  if (!ctx) return VRFS_BAD_ARG;
+  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
+  if (n && (!points || !out)) return fail(ctx, VRFS_BAD_ARG, "null buffer");
+  if (n == 0) return VRFS_OK;
+  ST(begin_call(ctx, n));
+  const uint8_t* d_i; uint8_t* d_o;
+  ST(stage_in(ctx, BUF_IN0, points, n * 96, &d_i));
+  ST(stage_out(ctx, BUF_OUT0, n * 48, &d_o));
+  k_g1_compress<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((uint32_t)n, d_i, d_o);
+  LAUNCHED_AS(ctx, "g1_compress");
+  ST(copy_out(ctx, out, d_o, n * 48));
+  return finish_call(ctx);
+}
+extern "C" vrfs_status vrfs_g1_decompress_batch(vrfs_ctx* ctx, size_t n, const uint8_t* enc, int check_subgroup, uint8_t* out_points, uint8_t* out_ok) {
+  if (!ctx) return VRFS_BAD_ARG;
+  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
+  if (n && (!enc || !out_points || !out_ok)) return fail(ctx, VRFS_BAD_ARG, "null buffer");
+  if (n == 0) return VRFS_OK;
+  ST(begin_call(ctx, n));
+  const uint8_t* d_i; uint8_t *d_o, *d_k;
+  ST(stage_in(ctx, BUF_IN0, enc, n * 48, &d_i));
+  ST(stage_out(ctx, BUF_OUT0, n * 96, &d_o)); ST(stage_out(ctx, BUF_OUT1, n, &d_k));
+  k_g1_decompress<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((uint32_t)n, d_i, check_subgroup, d_o, d_k);
+  LAUNCHED_AS(ctx, "g1_decompress");
+  ST(copy_out(ctx, out_points, d_o, n * 96)); ST(copy_out(ctx, out_ok, d_k, n));
+  return finish_call(ctx);
+}
 // self-test / measurement helper: 1/a in BLS12-381 Fq for n canonical 48-byte LE values (0 -> 0); ok[i] = 1 when the
 // word-approximation GCD finished on its own (no fallback to the binary Euclid) - the GPU tests require that for every a != 0
 __global__ void k_fq381_inv_batch(uint32_t n, const uint8_t* in, uint8_t* out, uint8_t* ok) {

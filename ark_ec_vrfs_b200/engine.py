@@ -293,6 +293,18 @@ class Engine:
         self._call("vrfs_fr_fft_batch", int(n.bit_length() - 1), int(n_columns), int(bool(inverse)), _p(values), _p(out))
         return out
 
+    def g1_compress(self, points):
+        """(n, 96) affine LE G1 points (zeros = identity) -> (n, 48) ark-bls12-381 / zcash compressed encodings"""
+        points = _u8(points, (-1, 96)); out = np.zeros((len(points), 48), np.uint8)
+        self._call("vrfs_g1_compress_batch", C.c_size_t(len(points)), _p(points), _p(out))
+        return out
+
+    def g1_decompress(self, enc, check_subgroup=True):
+        """(n, 48) compressed encodings -> ((n, 96) affine LE points, ok flags); validated like CanonicalDeserialize"""
+        enc = _u8(enc, (-1, 48)); out = np.zeros((len(enc), 96), np.uint8); ok = np.zeros(len(enc), np.uint8)
+        self._call("vrfs_g1_decompress_batch", C.c_size_t(len(enc)), _p(enc), int(bool(check_subgroup)), _p(out), _p(ok))
+        return out, ok
+
     def fq381_inv(self, values):
         """self-test helper: inverses in BLS12-381 Fq of (n, 48) canonical LE values -> (inverses, fast-path flags)"""
         values = _u8(values, (-1, 48)); out = np.zeros_like(values); ok = np.zeros(len(values), np.uint8)

@@ -174,6 +174,14 @@ vrfs_status vrfs_ring_commit_delta(vrfs_ctx*, const vrfs_msm_bases* srs_lagrange
  * in and out may be the same buffer. */
 vrfs_status vrfs_fr_fft_batch(vrfs_ctx*, int log_n, int n_columns, int inverse, const uint8_t* in /*n_columns*2^log_n*32*/, uint8_t* out);
 
+/* BLS12-381 G1 on the wire (the points of a `RingCommitment`, an SRS file): ark-bls12-381's compressed CanonicalSerialize /
+ * validated CanonicalDeserialize, i.e. the zcash encoding - 48 bytes, big-endian x; bit 7 of byte 0 = compressed, bit 6 = infinity,
+ * bit 5 = y is the lexicographically larger root.  Points are 96-byte affine LE (zeros = identity) on the other side.
+ * decompress: out_ok[i] = 0 (and a zero point) for a missing compression flag, a non-canonical x, an x that is no abscissa, stray bits on
+ * an infinity encoding, or - when check_subgroup != 0 - a point outside the prime-order subgroup (endomorphism test). */
+vrfs_status vrfs_g1_compress_batch(vrfs_ctx*, size_t n, const uint8_t* points /*n*96*/, uint8_t* out /*n*48*/);
+vrfs_status vrfs_g1_decompress_batch(vrfs_ctx*, size_t n, const uint8_t* enc /*n*48*/, int check_subgroup, uint8_t* out_points /*n*96*/, uint8_t* out_ok /*n*/);
+
 /* self-test / measurement helper: 1/a in BLS12-381 Fq (the inversion behind the MSM's affine output) for n canonical 48-byte LE
  * values, 0 -> 0; out_ok[i] = 1 when the word-approximation GCD finished without falling back to the binary Euclid. */
 vrfs_status vrfs_fq381_inv_batch(vrfs_ctx*, size_t n, const uint8_t* in /*n*48*/, uint8_t* out /*n*48*/, uint8_t* out_ok /*n*/);

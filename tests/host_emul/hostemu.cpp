@@ -200,3 +200,7 @@ extern "C" void hostemu_ntt_domain_gen(int logn, int inverse, uint32_t* out_cano
 extern "C" void hostemu_ntt_inv_n(int logn, uint32_t* out_canonical) {
   from_mont<BlsFr>(out_canonical, fr_pow_u32(ntt_const(2), (uint32_t)logn));
 }
+
+// BLS12-381 G1 wire format (csrc/ring.cuh) on the host
+extern "C" void hostemu_g1_compress(const uint8_t* pt96, uint8_t* out48) { g1_compress_one(out48, pt96); }
+extern "C" int hostemu_g1_decompress(const uint8_t* in48, int check_subgroup, uint8_t* out96) { return g1_decompress_one(out96, in48, check_subgroup != 0); }

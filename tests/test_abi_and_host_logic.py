@@ -180,3 +180,52 @@ def test_ntt_domain_generators_match_ark_ff(emu):
         emu.hostemu_ntt_domain_gen(logn, 1, out); assert val() == pow(w, -1, r)
         assert pow(w, 1 << logn, r) == 1 and (logn == 0 or pow(w, 1 << (logn - 1), r) == r - 1)
         emu.hostemu_ntt_inv_n(logn, out); assert val() == pow(1 << logn, -1, r)
+
+
+def test_g1_wire_format_on_the_host(emu):
+    """csrc/ring.cuh g1_compress_one / g1_decompress_one (ark-bls12-381's zcash-format compressed G1): the generator's published
+    encoding, round trips with both y signs, the infinity encoding, rejection of non-canonical / off-curve / flag-less inputs, and
+    the endomorphism subgroup test against [r]P on points of the curve outside G1"""
+    p = R.BLS_FQ; r = R.BLS_FR; Cv = R.BLS12_381_G1
+    le96 = lambda P: (C.c_uint8 * 96)(*(P[0].to_bytes(48, "little") + P[1].to_bytes(48, "little")))
+    out48 = (C.c_uint8 * 48)(); out96 = (C.c_uint8 * 96)()
+    emu.hostemu_g1_compress(le96(Cv.G), out48)
+    assert bytes(out48).hex() == "97f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb"
+    rnd = random.Random(9)
+    for t in range(6):
+        P = Cv.mul(rnd.randrange(1, r), Cv.G)
+        for Q in (P, Cv.neg(P)):
+            emu.hostemu_g1_compress(le96(Q), out48)
+            enc = bytes(out48)
+            assert enc[0] & 0x80 and not enc[0] & 0x40 and bool(enc[0] & 0x20) == (Q[1] > p - Q[1])
+            assert int.from_bytes(bytes([enc[0] & 0x1F]) + enc[1:], "big") == Q[0]
+            assert emu.hostemu_g1_decompress(out48, 1, out96) == 1 and bytes(out96) == bytes(le96(Q))
+    # infinity
+    emu.hostemu_g1_compress((C.c_uint8 * 96)(), out48)
+    assert bytes(out48) == bytes([0xC0]) + bytes(47)
+    assert emu.hostemu_g1_decompress(out48, 1, out96) == 1 and not any(out96)
+    bad = bytearray(bytes(out48)); bad[47] = 1
+    assert emu.hostemu_g1_decompress((C.c_uint8 * 48)(*bad), 1, out96) == 0
+    # no compression flag / x >= p / x that is no abscissa
+    g = bytearray.fromhex("97f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb")
+    nf = bytearray(g); nf[0] &= 0x7F
+    assert emu.hostemu_g1_decompress((C.c_uint8 * 48)(*nf), 1, out96) == 0
+    big = bytearray((p + 1).to_bytes(48, "big")); big[0] |= 0x80
+    assert emu.hostemu_g1_decompress((C.c_uint8 * 48)(*big), 0, out96) == 0
+    x = 1
+    while pow((x ** 3 + 4) % p, (p - 1) // 2, p) == 1: x += 1
+    nx = bytearray(x.to_bytes(48, "big")); nx[0] |= 0x80
+    assert emu.hostemu_g1_decompress((C.c_uint8 * 48)(*nx), 0, out96) == 0
+    # points of E(Fq) outside the prime-order subgroup: accepted without the check, rejected with it
+    outside = 0
+    for x in range(1, 40):
+        rhs = (x ** 3 + 4) % p
+        y = pow(rhs, (p + 1) // 4, p)
+        if y * y % p != rhs: continue
+        in_g1 = Cv.is_identity(Cv.mul(r, (x, y)))
+        e = bytearray(x.to_bytes(48, "big")); e[0] |= 0x80 | (0x20 if y > p - y else 0)
+        buf = (C.c_uint8 * 48)(*e)
+        assert emu.hostemu_g1_decompress(buf, 0, out96) == 1 and bytes(out96) == bytes(le96((x, y)))
+        assert emu.hostemu_g1_decompress(buf, 1, out96) == (1 if in_g1 else 0)
+        outside += not in_g1
+    assert outside >= 5

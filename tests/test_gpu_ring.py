@@ -156,3 +156,44 @@ def test_ring_commit_at_ring_size_2p10(eng):
         assert np.array_equal(h.ring_commit(pk, part, pk[0], tail, lagrange=False), h.msm(coef, 3))
     finally:
         h.release()
+
+
+def test_g1_compress_decompress_on_the_gpu(eng):
+    """vrfs_g1_compress_batch / vrfs_g1_decompress_batch against the host-side twin (api.g1_compress), the published encoding of the
+    generator, round trips incl. the identity, and rejection of points outside the prime-order subgroup"""
+    from ark_ec_vrfs_b200 import api
+    P_MOD = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
+    rng = np.random.default_rng(12)
+    n = 1500
+    ks = rng.integers(0, 256, size=(n, 32), dtype=np.uint8); ks[:, 31] &= 0x3F; ks[0] = 0; ks[0, 0] = 1; ks[1] = 0       # G, identity
+    pts = O.g1_mul_gen(ks)
+    neg = pts.copy()
+    for i in range(2, 40):                                           # both y signs
+        y = int.from_bytes(pts[i, 48:].tobytes(), "little")
+        neg[i, 48:] = np.frombuffer(((P_MOD - y) % P_MOD).to_bytes(48, "little"), np.uint8)
+    allp = np.concatenate([pts, neg[2:40]])
+    enc = eng.g1_compress(allp)
+    assert np.array_equal(enc, api.g1_compress(allp))
+    assert enc[0].tobytes().hex() == "97f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb"
+    assert enc[1].tobytes() == bytes([0xC0]) + bytes(47)
+    back, ok = eng.g1_decompress(enc)
+    assert ok.all() and np.array_equal(back, allp)
+    # malformed encodings and points off the subgroup
+    bad = enc[:8].copy()
+    bad[2, 0] &= 0x7F                                                # compression flag missing
+    bad[3] = np.frombuffer((P_MOD + 5).to_bytes(48, "big"), np.uint8); bad[3, 0] |= 0x80      # x >= p
+    bad[1, 47] = 7                                                   # stray bits on the infinity encoding
+    x = 1; offs = []
+    while len(offs) < 4:                                             # curve points with small x are (almost always) outside G1
+        rhs = (x ** 3 + 4) % P_MOD; y = pow(rhs, (P_MOD + 1) // 4, P_MOD)
+        if y * y % P_MOD == rhs:
+            e = bytearray(x.to_bytes(48, "big")); e[0] |= 0x80 | (0x20 if y > P_MOD - y else 0); offs.append((bytes(e), x, y))
+        x += 1
+    for j, (e, _, _) in enumerate(offs):
+        bad[4 + j] = np.frombuffer(e, np.uint8)
+    out, ok = eng.g1_decompress(bad, check_subgroup=True)
+    assert list(ok) == [1, 0, 0, 0, 0, 0, 0, 0] and not out[1:].any()
+    out, ok = eng.g1_decompress(bad, check_subgroup=False)
+    assert list(ok) == [1, 0, 0, 0, 1, 1, 1, 1]
+    for j, (_, xx, yy) in enumerate(offs):
+        assert out[4 + j].tobytes() == xx.to_bytes(48, "little") + yy.to_bytes(48, "little")

@@ -36,6 +36,11 @@ for logn in (11, 14, 17):
         print("ring size 2^%d (domain 2^%d) %-9s kernels %.3f ms, wall %.3f ms" % (logn - 1, logn, name, best[0], best[1]), {a: round(b, 2) for a, b in best[2]}, flush=True)
     cols = e.ring_fixed_columns(n, part, keys, pk0[0], tail).reshape(-1, 32)
     t = time.perf_counter(); e.fr_fft(cols, 3, inverse=True); row["ifft_3col_wall_ms"] = round((time.perf_counter() - t) * 1e3, 3)
+    # SRS / commitment points on the wire: compress, decompress with and without the subgroup test (kernel ms)
+    enc = e.g1_compress(srs)
+    for name, f in (("g1_compress", lambda: e.g1_compress(srs)), ("g1_decompress_checked", lambda: e.g1_decompress(enc, True)), ("g1_decompress_unchecked", lambda: e.g1_decompress(enc, False))):
+        e.enable_kernel_timing(True); f(); row[name + "_kernel_ms"] = round(sum(v for _, v in e.kernel_timings()), 3); e.enable_kernel_timing(False)
+    print("   G1 wire, %d points: compress %.3f ms, decompress %.3f ms (with subgroup test) / %.3f ms (without)" % (n, row["g1_compress_kernel_ms"], row["g1_decompress_checked_kernel_ms"], row["g1_decompress_unchecked_kernel_ms"]), flush=True)
     h.release()
     res["2^%d" % logn] = row
 json.dump(res, open(os.path.join(ROOT, "gpurun_out", os.environ.get("RING_BENCH_OUT", "ring_bench.json")), "w"), indent=1)
