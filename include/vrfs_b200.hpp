@@ -193,6 +193,19 @@ inline Bytes ring_commitment_msm(Engine& e, const Bytes& bases /*n*96*/, const B
 }
 
 
+// ark-bls12-381's compressed G1 (de)serialisation (zcash format, 48 bytes) for commitments and SRS points; 96-byte affine LE otherwise
+inline Bytes g1_serialize_compressed(Engine& e, const Bytes& points /*n*96*/) {
+  size_t n = points.size() / 96; Bytes out(48 * n);
+  e.check(vrfs_g1_compress_batch(e.ctx(), n, points.data(), out.data()));
+  return out;
+}
+// -> (points, ok flags): ok[i] = 0 stands for the Err(_) of a validated deserialize_compressed
+inline std::pair<Bytes, Bytes> g1_deserialize_compressed(Engine& e, const Bytes& enc /*n*48*/, bool check_subgroup = true) {
+  size_t n = enc.size() / 48; Bytes pts(96 * n), ok(n);
+  e.check(vrfs_g1_decompress_batch(e.ctx(), n, enc.data(), check_subgroup ? 1 : 0, pts.data(), ok.data()));
+  return {pts, ok};
+}
+
 // ring::RingContext up to the verifier key's commitment: holds the prepared SRS of one power-of-two domain
 // (Lagrange basis [L_i(tau)]G1 or monomial powers [tau^i]G1, 96-byte affine points) and the row layout of the fixed columns:
 // keys | padding up to keyset_part_size | tail (the powers 2^j * H of the blinding base) | zero rows; selector = 1 on the key slots.
@@ -222,6 +235,8 @@ class RingContext {
     return out;
   }
 
+  // the serialised RingCommitment: three compressed G1 points (144 bytes)
+  Bytes ring_commitment_bytes(const Bytes& public_keys) const { return g1_serialize_compressed(*e_, verifier_key_commitment(public_keys)); }
   // Lagrange-basis SRS only: [sum (x_i - pad_x) L_i, sum (y_i - pad_y) L_i] (2 * 96 bytes) - the part of the commitment that depends on
   // the keys; add it to verifier_key_commitment({}) (the ring of padding only, computed once) with vrfs_g1_sum_partials
   Bytes verifier_key_commitment_delta(const Bytes& public_keys) const {

@@ -101,6 +101,13 @@ int main() {
         eng.check(vrfs_g1_sum_partials(eng.ctx(), 2, 3, parts.data(), sum.data()));
         CHECK(sum == com);
       }
+      {   // G1 on the wire: the generator's published compressed encoding, and a round trip of the commitment
+        Bytes genc = g1_serialize_compressed(eng, g1);
+        CHECK(hex(genc.data(), 48) == "97f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb");
+        Bytes blob = rc.ring_commitment_bytes(keys);
+        auto [pts, okf] = g1_deserialize_compressed(eng, blob);
+        CHECK(blob.size() == 144 && okf[0] == 1 && okf[1] == 1 && okf[2] == 1 && pts == com);
+      }
       Bytes ev(cols.size()), back(cols.size());
       eng.check(vrfs_fr_fft_batch(eng.ctx(), 6, 3, 0, cols.data(), ev.data()));
       eng.check(vrfs_fr_fft_batch(eng.ctx(), 6, 3, 1, ev.data(), back.data()));
