@@ -259,6 +259,15 @@ class RingContext:
         self.srs = self.engine.msm_g1_prepare(srs_g1)
         self._empty = None                                            # commitment of the ring of padding only (Lagrange SRS)
 
+    @classmethod
+    def from_compressed_srs(cls, suite, srs_bytes, lagrange, padding, blinding_base_powers, keyset_part_size=None, check_subgroup=True):
+        """the SRS as it is stored (48-byte compressed G1 points, ark-bls12-381 / zcash format): validated on the GPU
+        (canonical, on curve, prime-order subgroup) like `deserialize_compressed`; raises ValueError on the first bad point"""
+        pts, ok = suite.engine.g1_decompress(np.asarray(srs_bytes, np.uint8).reshape(-1, 48), check_subgroup)
+        if not ok.all():
+            raise ValueError("SRS point %d is not a valid compressed G1 point" % int(np.argmin(ok)))
+        return cls(suite, pts, lagrange, padding, blinding_base_powers, keyset_part_size)
+
     def max_ring_size(self):
         return self.keyset_part_size
 

@@ -136,6 +136,16 @@ def test_ring_commit_lagrange_equals_monomial_equals_direct(eng):
         assert x0 == int.from_bytes(direct[0, :48].tobytes(), "little")
     finally:
         ctx.release()
+    # the same context from the SRS as stored (compressed points, validated on the GPU); a corrupted point is refused
+    enc = eng.g1_compress(srs_lag)
+    ctx2 = api.RingContext.from_compressed_srs(suite, enc, True, padding, tail)
+    try:
+        assert np.array_equal(ctx2.verifier_key_commitment(keys), direct)
+    finally:
+        ctx2.release()
+    enc[5, 47] ^= 1
+    with pytest.raises(ValueError):
+        api.RingContext.from_compressed_srs(suite, enc, True, padding, tail)
 
 
 def test_ring_commit_at_ring_size_2p10(eng):
