@@ -207,3 +207,56 @@ def test_g1_compress_decompress_on_the_gpu(eng):
     assert list(ok) == [1, 0, 0, 0, 1, 1, 1, 1]
     for j, (_, xx, yy) in enumerate(offs):
         assert out[4 + j].tobytes() == xx.to_bytes(48, "little") + yy.to_bytes(48, "little")
+
+
+def test_ring_api_edge_cases_and_argument_checks(eng):
+    import ark_ec_vrfs_b200 as vrfs
+    _, pk, inp, _ = V.make_keys_inputs(O.BANDERSNATCH, 40)
+    rng = np.random.default_rng(8)
+    ks = np.zeros((64, 32), np.uint8); ks[:, :8] = rng.integers(1, 2 ** 62, size=64, dtype=np.uint64).view(np.uint8).reshape(64, 8)
+    srs = O.g1_mul_gen(ks)
+    none = np.zeros((0, 64), np.uint8)
+    h = eng.msm_g1_prepare(srs)
+    try:
+        # empty ring, no tail: only the selector column is non-trivial; keyset_part_size = 0: everything is the identity
+        got = h.ring_commit(none, 16, pk[0], none, lagrange=True)
+        cols = eng.ring_fixed_columns(64, 16, none, pk[0], none)
+        assert np.array_equal(got, O.msm_g1(srs, cols.reshape(-1, 32), 3)) and got.any()
+        assert not h.ring_commit(none, 0, pk[0], none, lagrange=True).any()
+        assert not h.ring_commit_delta(none, pk[0]).any()
+        # a full domain of keys (no padding, no tail), both SRS kinds against the oracle MSM of the columns / coefficients
+        keys = np.tile(pk, (2, 1))[:64]
+        cols = eng.ring_fixed_columns(64, 64, keys, pk[0], none).reshape(-1, 32)
+        assert np.array_equal(h.ring_commit(keys, 64, pk[0], none, lagrange=True), O.msm_g1(srs, cols, 3))
+        assert np.array_equal(h.ring_commit(keys, 64, pk[0], none, lagrange=False), O.msm_g1(srs, eng.fr_fft(cols, 3, inverse=True), 3))
+        with pytest.raises(vrfs.VrfsError):
+            h.ring_commit(keys, 63, pk[0], none)                 # more keys than key slots
+        with pytest.raises(vrfs.VrfsError):
+            h.ring_commit(keys[:3], 60, pk[0], inp[:5])          # tail does not fit
+    finally:
+        h.release()
+    h3 = eng.msm_g1_prepare(srs[:48])                            # an SRS that does not cover a power-of-two domain
+    try:
+        with pytest.raises(vrfs.VrfsError):
+            h3.ring_commit(none, 16, pk[0], none)
+    finally:
+        h3.release()
+    # empty batches are no-ops
+    assert eng.g1_compress(np.zeros((0, 96), np.uint8)).shape == (0, 48)
+    pts, ok = eng.g1_decompress(np.zeros((0, 48), np.uint8))
+    assert pts.shape == (0, 96) and ok.shape == (0,)
+    with pytest.raises((vrfs.VrfsError, AssertionError)):
+        eng.fr_fft(np.zeros((3, 32), np.uint8), 1)               # not a power of two
+
+
+def test_msm_32_columns_over_one_base(eng):
+    """the shape bench.py uses to derive an SRS: 32 one-scalar columns over a single prepared base"""
+    ks = np.zeros((1, 32), np.uint8); ks[0, 0] = 1
+    gen = O.g1_mul_gen(ks)
+    rng = np.random.default_rng(4)
+    sc = rng.integers(0, 256, size=(32, 32), dtype=np.uint8); sc[:, 31] &= 0x3F; sc[5] = 0
+    h = eng.msm_g1_prepare(gen)
+    try:
+        assert np.array_equal(h.msm(sc, 32), O.g1_mul_gen(sc))
+    finally:
+        h.release()
