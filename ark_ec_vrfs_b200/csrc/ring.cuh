@@ -107,19 +107,22 @@ __global__ void __launch_bounds__(128, G1_DEC_MINBLOCKS) k_g1_decompress(uint32_
   if (i < n) ok[i] = g1_decompress_one(out + (size_t)96 * i, in + (size_t)48 * i, check_subgroup != 0) ? 1 : 0;
 }
 // columns[0] = xs, [1] = ys, [2] = selector; every value canonical 32-byte LE (points arrive as affine x || y, 64 B)
-__global__ void k_ring_columns(uint32_t n, uint32_t keyset_part, uint32_t n_keys, const uint8_t* keys, const uint8_t* padding,
+// The kernel writes the n rows [row_lo, row_lo + n) of the domain (row_lo = 0 and n = domain size for the whole columns; a rank of
+// a multi-GPU commitment passes its slice); keys points at the key of row row_lo.
+__global__ void k_ring_columns(uint32_t n, uint32_t row_lo, uint32_t keyset_part, uint32_t n_keys, const uint8_t* keys, const uint8_t* padding,
                                uint32_t n_tail, const uint8_t* tail, uint8_t* columns) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const uint32_t i = row_lo + j;                 // row of the domain
   const uint8_t* src = nullptr;
-  if (i < n_keys) src = keys + (size_t)64 * i;
+  if (i < n_keys) src = keys + (size_t)64 * j;
   else if (i < keyset_part) src = padding;
   else if (i - keyset_part < n_tail) src = tail + (size_t)64 * (i - keyset_part);
   uint4 z = make_uint4(0, 0, 0, 0), x0 = z, x1 = z, y0 = z, y1 = z;
   if (src) { const uint4* s = reinterpret_cast<const uint4*>(src); x0 = s[0]; x1 = s[1]; y0 = s[2]; y1 = s[3]; }
-  uint4* cx = reinterpret_cast<uint4*>(columns + (size_t)32 * i);
-  uint4* cy = reinterpret_cast<uint4*>(columns + (size_t)32 * ((size_t)n + i));
-  uint4* cs = reinterpret_cast<uint4*>(columns + (size_t)32 * (2 * (size_t)n + i));
+  uint4* cx = reinterpret_cast<uint4*>(columns + (size_t)32 * j);
+  uint4* cy = reinterpret_cast<uint4*>(columns + (size_t)32 * ((size_t)n + j));
+  uint4* cs = reinterpret_cast<uint4*>(columns + (size_t)32 * (2 * (size_t)n + j));
   cx[0] = x0; cx[1] = x1; cy[0] = y0; cy[1] = y1;
   cs[0] = make_uint4(i < keyset_part ? 1u : 0u, 0, 0, 0); cs[1] = z;
 }

@@ -1524,18 +1524,21 @@ extern "C" vrfs_status vrfs_fr_fft_batch(vrfs_ctx* ctx, int log_n, int n_columns
   ST(copy_out(ctx, out, d_o, bytes));
   return finish_call(ctx);
 }
+// rows [row_lo, row_lo + n) of the columns; `keys` holds the keys of those rows only (rows row_lo .. min(n_keys, row_lo + n) - 1)
 static vrfs_status ring_columns_dev(vrfs_ctx* ctx, size_t n, size_t keyset_part, size_t n_keys, const uint8_t* keys, const uint8_t* padding,
-                                    size_t n_tail, const uint8_t* tail, uint8_t** d_cols) {
-  if (n == 0 || (n & (n - 1)) || n > (1u << 26)) return fail(ctx, VRFS_BAD_ARG, "domain size must be a power of two <= 2^26");
-  if (n_keys > keyset_part || keyset_part + n_tail > n) return fail(ctx, VRFS_BAD_ARG, "need n_keys <= keyset_part_size and keyset_part_size + n_tail <= domain size");
-  if ((n_keys && !keys) || (n_keys < keyset_part && !padding) || (n_tail && !tail)) return fail(ctx, VRFS_BAD_ARG, "null buffer");
+                                    size_t n_tail, const uint8_t* tail, uint8_t** d_cols, size_t row_lo = 0, bool whole_domain = true) {
+  if (whole_domain && (n == 0 || (n & (n - 1)) || n > (1u << 26))) return fail(ctx, VRFS_BAD_ARG, "domain size must be a power of two <= 2^26");
+  if (n == 0 || row_lo + n > (1u << 26)) return fail(ctx, VRFS_BAD_ARG, "empty or oversized row range");
+  if (n_keys > keyset_part || (whole_domain && keyset_part + n_tail > n)) return fail(ctx, VRFS_BAD_ARG, "need n_keys <= keyset_part_size and keyset_part_size + n_tail <= domain size");
+  const size_t keys_here = n_keys > row_lo ? std::min(n_keys - row_lo, n) : 0;
+  if ((keys_here && !keys) || (n_keys < keyset_part && !padding) || (n_tail && !tail)) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   const uint8_t *d_k = nullptr, *d_p = nullptr, *d_t = nullptr;
-  ST(stage_in(ctx, BUF_IN0, keys, n_keys * 64, &d_k));
+  ST(stage_in(ctx, BUF_IN0, keys, keys_here * 64, &d_k));
   ST(stage_in(ctx, BUF_IN2, padding, padding ? 64 : 0, &d_p));
   ST(stage_in(ctx, BUF_IN3, tail, n_tail * 64, &d_t));
   void* cols = nullptr;
   ST(ensure(ctx, BUF_IN1, 3 * n * 32, &cols));
-  k_ring_columns<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((uint32_t)n, (uint32_t)keyset_part, (uint32_t)n_keys, d_k, d_p, (uint32_t)n_tail, d_t, (uint8_t*)cols);
+  k_ring_columns<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((uint32_t)n, (uint32_t)row_lo, (uint32_t)keyset_part, (uint32_t)n_keys, d_k, d_p, (uint32_t)n_tail, d_t, (uint8_t*)cols);
   LAUNCHED_AS(ctx, "ring_columns");
   *d_cols = (uint8_t*)cols;
   return VRFS_OK;
@@ -1567,6 +1570,20 @@ extern "C" vrfs_status vrfs_ring_commit(vrfs_ctx* ctx, const vrfs_msm_bases* srs
   ST(stage_out(ctx, BUF_OUT0, 3 * 96, &d_o));
   ST(msm_dev(ctx, msm_plan((uint32_t)n, 3, 1, msm_c_override(1), msm_aff_override(), msm_tpb_override()), srs->Q, d_cols, d_o, 0));
   ST(copy_out(ctx, out_commitment, d_o, 3 * 96));
+  return finish_call(ctx);
+}
+extern "C" vrfs_status vrfs_ring_commit_rows_partial(vrfs_ctx* ctx, const vrfs_msm_bases* srs_rows, size_t row_lo, size_t keyset_part_size, size_t n_keys,
+                                                     const uint8_t* keys_rows, const uint8_t* padding, size_t n_tail, const uint8_t* tail, uint8_t* out_partial) {
+  if (!ctx || !srs_rows || srs_rows->ctx != ctx) return VRFS_BAD_ARG;
+  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
+  if (!out_partial) return fail(ctx, VRFS_BAD_ARG, "null buffer");
+  const size_t n = srs_rows->n;
+  ST(begin_call(ctx, n));
+  uint8_t *d_cols = nullptr, *d_o = nullptr;
+  ST(ring_columns_dev(ctx, n, keyset_part_size, n_keys, keys_rows, padding, n_tail, tail, &d_cols, row_lo, false));
+  ST(stage_out(ctx, BUF_OUT0, 3 * 144, &d_o));
+  ST(msm_dev(ctx, msm_plan((uint32_t)n, 3, 1, msm_c_override(1), msm_aff_override(), msm_tpb_override()), srs_rows->Q, d_cols, d_o, 1));
+  ST(copy_out(ctx, out_partial, d_o, 3 * 144));
   return finish_call(ctx);
 }
 extern "C" vrfs_status vrfs_ring_commit_delta(vrfs_ctx* ctx, const vrfs_msm_bases* srs_lagrange, size_t n_keys, const uint8_t* keys,

@@ -70,3 +70,38 @@ class ShardedPreparedBases:
 
     def release(self):
         self.handle.release()
+
+
+def ring_column_rows(lo, hi, keyset_part_size, keys, padding, tail):
+    """rows [lo, hi) of the ring's fixed columns (xs | ys | selector, the layout of vrfs_ring_fixed_columns) as (3, hi - lo, 32)
+    canonical LE values - the host-side statement of what k_ring_columns writes for a rank's slice (used by the tests)"""
+    keys = np.asarray(keys, np.uint8).reshape(-1, 64); tail = np.asarray(tail, np.uint8).reshape(-1, 64)
+    padding = np.asarray(padding, np.uint8).reshape(64)
+    rows = np.zeros((hi - lo, 64), np.uint8)
+    idx = np.arange(lo, hi)
+    k = idx < len(keys)
+    rows[k] = keys[idx[k]]
+    rows[(~k) & (idx < keyset_part_size)] = padding
+    t = (idx >= keyset_part_size) & (idx < keyset_part_size + len(tail))
+    rows[t] = tail[idx[t] - keyset_part_size]
+    sel = np.zeros((hi - lo, 32), np.uint8); sel[idx < keyset_part_size, 0] = 1
+    return np.stack([rows[:, :32], rows[:, 32:], sel])
+
+
+class ShardedRingContext:
+    """`RingContext` up to the verifier key's commitment on G GPUs with a Lagrange-basis SRS: rank g prepares the bases of the rows
+    [g*N/G, (g+1)*N/G), builds those rows of the fixed columns on its GPU (vrfs_ring_commit_rows_partial), and the commitment is one partial MSM per rank, an all-gather of
+    3 x 144 bytes per rank and G-1 point additions (every rank returns the same three points)."""
+
+    def __init__(self, engine, srs_lagrange, keyset_part_size, padding, tail, group=None, device=None):
+        self.bases = ShardedPreparedBases(engine, srs_lagrange, group, device)
+        self.keyset_part_size, self.padding, self.tail = int(keyset_part_size), padding, tail
+
+    def verifier_key_commitment(self, public_keys):
+        b = self.bases
+        keys = np.asarray(public_keys, np.uint8).reshape(-1, 64)
+        part = b.handle.ring_commit_rows_partial(b.lo, self.keyset_part_size, len(keys), keys[b.lo:b.hi], self.padding, self.tail)
+        return b.engine.g1_sum_partials(gather_bytes(part, b.group, b.device), 3)
+
+    def release(self):
+        self.bases.release()

@@ -53,6 +53,13 @@ class PreparedBases:
                           _p(padding), C.c_size_t(len(tail)), _p(tail), _p(out))
         return out
 
+    def ring_commit_rows_partial(self, row_lo, keyset_part_size, n_keys, keys_rows, padding, tail):
+        """this handle = the prepared Lagrange bases of rows [row_lo, row_lo + n): projective partial commitments (3, 144) of those rows"""
+        keys_rows = _u8(keys_rows, (-1, 64)); tail = _u8(tail, (-1, 64)); padding = _u8(padding, (64,)); out = np.zeros((3, 144), np.uint8)
+        self.engine._call("vrfs_ring_commit_rows_partial", self.handle, C.c_size_t(row_lo), C.c_size_t(keyset_part_size), C.c_size_t(n_keys), _p(keys_rows),
+                          _p(padding), C.c_size_t(len(tail)), _p(tail), _p(out))
+        return out
+
     def ring_commit_delta(self, keys, padding):
         """[sum (x_i - pad_x) L_i, sum (y_i - pad_y) L_i] over a Lagrange-basis SRS: (2, 96) (vrfs_ring_commit_delta)"""
         keys = _u8(keys, (-1, 64)); padding = _u8(padding, (64,)); out = np.zeros((2, 96), np.uint8)

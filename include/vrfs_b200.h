@@ -169,6 +169,13 @@ vrfs_status vrfs_ring_commit(vrfs_ctx*, const vrfs_msm_bases* srs, int srs_is_la
  * domain (a half-full ring: 2.2 instead of 3.9 ms at 2^17).  The caller adds the points (vrfs_g1_sum_partials with Z = 1). */
 vrfs_status vrfs_ring_commit_delta(vrfs_ctx*, const vrfs_msm_bases* srs_lagrange, size_t n_keys, const uint8_t* keys /*n_keys*64*/,
                                    const uint8_t* padding /*64*/, uint8_t* out_delta /*2*96*/);
+/* One rank's share of a multi-GPU ring commitment over a Lagrange-basis SRS: srs_rows holds the prepared bases of the rows
+ * [row_lo, row_lo + rows) of the domain, keys_rows the keys that fall into those rows (rows row_lo .. min(n_keys, row_lo + rows) - 1;
+ * n_keys is the ring size, as in vrfs_ring_commit).  The three projective partial sums (3 * 144 bytes) of all ranks are gathered
+ * and folded with vrfs_g1_sum_partials. */
+vrfs_status vrfs_ring_commit_rows_partial(vrfs_ctx*, const vrfs_msm_bases* srs_rows, size_t row_lo, size_t keyset_part_size, size_t n_keys,
+                                          const uint8_t* keys_rows, const uint8_t* padding, size_t n_tail, const uint8_t* tail,
+                                          uint8_t* out_partial /*3*144*/);
 /* ark-poly Radix2EvaluationDomain::fft (inverse = 0: coefficients -> evaluations) / ::ifft (inverse != 0) over BLS12-381 Fr for
  * n_columns vectors of 2^log_n canonical 32-byte LE values (values >= r are reduced); group_gen = TWO_ADIC_ROOT_OF_UNITY^(2^(32-log_n)).
  * in and out may be the same buffer. */

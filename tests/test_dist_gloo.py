@@ -65,3 +65,21 @@ def test_shard_ranges_partition(n, world):
     assert all(r[g][1] == r[g + 1][0] for g in range(world - 1))
     sizes = [hi - lo for lo, hi in r]
     assert max(sizes) - min(sizes) <= 1
+
+
+def test_ring_column_rows_partition_the_columns():
+    """dist.ring_column_rows: the row slices of all ranks concatenate to the full fixed columns (keys, padding, tail, zero rows;
+    selector on the key slots) for ragged splits"""
+    from ark_ec_vrfs_b200 import dist as D
+    rng = np.random.default_rng(2)
+    n, part = 64, 40
+    keys = rng.integers(0, 256, size=(7, 64), dtype=np.uint8); tail = rng.integers(0, 256, size=(10, 64), dtype=np.uint8)
+    padding = rng.integers(0, 256, size=64, dtype=np.uint8)
+    full = D.ring_column_rows(0, n, part, keys, padding, tail)
+    pts = np.concatenate([full[0], full[1]], axis=1)
+    assert np.array_equal(pts[:7], keys) and np.array_equal(pts[7:part], np.tile(padding, (part - 7, 1)))
+    assert np.array_equal(pts[part:part + 10], tail) and not pts[part + 10:].any()
+    assert full[2][:, 0].tolist() == [1] * part + [0] * (n - part) and not full[2][:, 1:].any()
+    for world in (1, 2, 3, 8):
+        parts = [D.ring_column_rows(*D.shard_range(n, g, world), part, keys, padding, tail) for g in range(world)]
+        assert np.array_equal(np.concatenate(parts, axis=1), full)

@@ -260,3 +260,33 @@ def test_msm_32_columns_over_one_base(eng):
         assert np.array_equal(h.msm(sc, 32), O.g1_mul_gen(sc))
     finally:
         h.release()
+
+
+def test_sharded_ring_context_on_one_rank(eng):
+    """dist.ShardedRingContext with world size 1 (gloo): host-built column rows + prepared partial MSM + fold = vrfs_ring_commit;
+    dist.ring_column_rows equals the device column builder"""
+    import torch.distributed as dist
+    from ark_ec_vrfs_b200 import dist as D
+    os_env = __import__("os").environ
+    os_env.setdefault("MASTER_ADDR", "127.0.0.1"); os_env.setdefault("MASTER_PORT", "29541")
+    created = not dist.is_initialized()
+    if created:
+        dist.init_process_group("gloo", rank=0, world_size=1)
+    try:
+        n = 256
+        rng = np.random.default_rng(6)
+        ks = np.zeros((n, 32), np.uint8); ks[:, :8] = rng.integers(1, 2 ** 62, size=n, dtype=np.uint64).view(np.uint8).reshape(n, 8)
+        srs = O.g1_mul_gen(ks)
+        _, pk, inp, _ = V.make_keys_inputs(O.BANDERSNATCH, 120)
+        keys, tail, padding = pk[:100], inp[:50], pk[119]
+        part = n - 3 - len(tail) - 1
+        assert np.array_equal(D.ring_column_rows(0, n, part, keys, padding, tail), eng.ring_fixed_columns(n, part, keys, padding, tail))
+        ctx = D.ShardedRingContext(eng, srs, part, padding, tail)
+        h = eng.msm_g1_prepare(srs)
+        try:
+            assert np.array_equal(ctx.verifier_key_commitment(keys), h.ring_commit(keys, part, padding, tail, lagrange=True))
+        finally:
+            ctx.release(); h.release()
+    finally:
+        if created:
+            dist.destroy_process_group()
