@@ -128,11 +128,18 @@ __global__ void k_ring_columns(uint32_t n, uint32_t row_lo, uint32_t keyset_part
 }
 // the homomorphic form (ring-proof's `Ring::append`): columns[0][i] = x_i - pad_x, columns[1][i] = y_i - pad_y (mod r) on the key rows,
 // zero elsewhere, so that  commit(ring) = commit(all-padding ring) + MSM(delta columns)  costs n_keys entries per window
-HD_INLINE Fr255 fr_load_reduced(const uint8_t* p) {            // canonical LE -> residue < r (values < 2^256 < 3 r)
+HD_INLINE Fr255 fr_load_reduced(const uint8_t* p) {            // 16-byte aligned canonical LE -> residue < r (values < 2^256 < 3 r)
   Fr255 v;
-  load_le<8>(v.v, p);
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  const uint4 lo4 = q[0], hi4 = q[1];
+  v.v[0] = lo4.x; v.v[1] = lo4.y; v.v[2] = lo4.z; v.v[3] = lo4.w; v.v[4] = hi4.x; v.v[5] = hi4.y; v.v[6] = hi4.z; v.v[7] = hi4.w;
   cond_sub_p<BlsFr>(v.v, 0u); cond_sub_p<BlsFr>(v.v, 0u);
   return v;
+}
+HD_INLINE void fr_store16(uint8_t* p, const Fr255& v) {         // 16-byte aligned
+  uint4* o = reinterpret_cast<uint4*>(p);
+  o[0] = make_uint4(v.v[0], v.v[1], v.v[2], v.v[3]);
+  o[1] = make_uint4(v.v[4], v.v[5], v.v[6], v.v[7]);
 }
 __global__ void k_ring_delta_columns(uint32_t n, uint32_t n_keys, const uint8_t* keys, const uint8_t* padding, uint8_t* columns) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -142,13 +149,15 @@ __global__ void k_ring_delta_columns(uint32_t n, uint32_t n_keys, const uint8_t*
     dx = fr_load_reduced(keys + (size_t)64 * i) - fr_load_reduced(padding);
     dy = fr_load_reduced(keys + (size_t)64 * i + 32) - fr_load_reduced(padding + 32);
   }
-  store_le<8>(columns + (size_t)32 * i, dx.v);
-  store_le<8>(columns + (size_t)32 * ((size_t)n + i), dy.v);
+  fr_store16(columns + (size_t)32 * i, dx);
+  fr_store16(columns + (size_t)32 * ((size_t)n + i), dy);
 }
-// tw[j] = w^j, j < n/2 (Montgomery form)
+// tw[j] = w^j, j < n/2 (Montgomery form);
+// tw[n/2] = 1/n (the scale of the inverse transform), computed once here instead of by every thread of k_ntt_store
 __global__ void k_ntt_twiddles(int logn, int inverse, Fr255* tw) {
-  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= (1u << logn) / 2u) return;
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x, half = (1u << logn) / 2u;
+  if (j == half) tw[half] = fr_pow_u32(ntt_const(2), (uint32_t)logn);
+  if (j >= half) return;
   tw[j] = fr_pow_u32(ntt_domain_gen(logn, inverse != 0), j);
 }
 // canonical LE -> Montgomery, bit-reversed position (values >= r are reduced, like ark-ff's from_le_bytes_mod_order)
@@ -157,8 +166,9 @@ __global__ void k_ntt_load(int logn, uint32_t ncol, const uint8_t* in, Fr255* wo
   const uint32_t n = 1u << logn;
   if (t >= (size_t)n * ncol) return;
   const uint32_t col = (uint32_t)(t >> logn), i = (uint32_t)(t & (n - 1));
-  uint32_t raw[8];
-  load_le<8>(raw, in + 32 * t);
+  const uint4* q = reinterpret_cast<const uint4*>(in + 32 * t);
+  const uint4 lo4 = q[0], hi4 = q[1];
+  const uint32_t raw[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
   const uint32_t rev = logn ? __brev(i) >> (32 - logn) : 0u;
   work[(size_t)col * n + rev] = to_mont<BlsFr>(raw);
 }
@@ -196,14 +206,16 @@ __global__ void __launch_bounds__(256) k_ntt_stage(int logn, uint32_t ncol, int 
   a[0] = x + y; a[half] = x - y;
 }
 // Montgomery -> canonical LE, scaled by 1/n for the inverse transform
-__global__ void k_ntt_store(int logn, uint32_t ncol, int inverse, const Fr255* work, uint8_t* out) {
+__global__ void k_ntt_store(int logn, uint32_t ncol, int inverse, const Fr255* work, const Fr255* tw, uint8_t* out) {
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= ((size_t)ncol << logn)) return;
   Fr255 v = work[t];
-  if (inverse) v = v * fr_pow_u32(ntt_const(2), (uint32_t)logn);
+  if (inverse) v = v * tw[(1u << logn) / 2u];
   uint32_t raw[8];
   from_mont<BlsFr>(raw, v);
-  store_le<8>(out + 32 * t, raw);
+  uint4* o = reinterpret_cast<uint4*>(out + 32 * t);            // device buffers are 256-byte aligned: two 16-byte stores per value
+  o[0] = make_uint4(raw[0], raw[1], raw[2], raw[3]);
+  o[1] = make_uint4(raw[4], raw[5], raw[6], raw[7]);
 }
 #endif  // __CUDACC__
 

@@ -1492,10 +1492,8 @@ static vrfs_status ntt_dev(vrfs_ctx* ctx, int logn, uint32_t ncol, int inverse, 
   void *work = nullptr, *tw = nullptr;
   ST(ensure(ctx, BUF_X3, total * sizeof(Fr255), &work));
   ST(ensure(ctx, BUF_X4, (n / 2 + 1) * sizeof(Fr255), &tw));
-  if (logn > 0) {
-    k_ntt_twiddles<<<(unsigned)((n / 2 + 127) / 128), 128, 0, ctx->stream>>>(logn, inverse, (Fr255*)tw);
-    LAUNCHED_AS(ctx, "ntt_twiddles");
-  }
+  k_ntt_twiddles<<<(unsigned)((n / 2 + 1 + 127) / 128), 128, 0, ctx->stream>>>(logn, inverse, (Fr255*)tw);   // n/2 twiddles + the 1/n scale
+  LAUNCHED_AS(ctx, "ntt_twiddles");
   k_ntt_load<<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(logn, ncol, d_in, (Fr255*)work);
   LAUNCHED_AS(ctx, "ntt_load");
   const int fused = logn < NTT_FUSED_LOG ? logn : NTT_FUSED_LOG;
@@ -1507,7 +1505,7 @@ static vrfs_status ntt_dev(vrfs_ctx* ctx, int logn, uint32_t ncol, int inverse, 
     k_ntt_stage<<<(unsigned)((total / 2 + 255) / 256), 256, 0, ctx->stream>>>(logn, ncol, s, (const Fr255*)tw, (Fr255*)work);
     LAUNCHED_AS(ctx, "ntt_stage");
   }
-  k_ntt_store<<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(logn, ncol, inverse, (const Fr255*)work, d_out);
+  k_ntt_store<<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(logn, ncol, inverse, (const Fr255*)work, (const Fr255*)tw, d_out);
   LAUNCHED_AS(ctx, "ntt_store");
   return VRFS_OK;
 }
