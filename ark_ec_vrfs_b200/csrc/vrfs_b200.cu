@@ -1566,7 +1566,9 @@ extern "C" vrfs_status vrfs_ring_commit(vrfs_ctx* ctx, const vrfs_msm_bases* srs
     ST(ntt_dev(ctx, logn, 3, 1, d_cols, d_cols));
   }
   ST(stage_out(ctx, BUF_OUT0, 3 * 96, &d_o));
-  ST(msm_dev(ctx, msm_plan((uint32_t)n, 3, 1, msm_c_override(1), msm_aff_override(), msm_tpb_override()), srs->Q, d_cols, d_o, 0));
+  MsmPlan plan = msm_plan((uint32_t)n, 3, 1, msm_c_override(1), msm_aff_override(), msm_tpb_override());
+  plan.warp_agg = srs_is_lagrange ? 1 : 0;       // evaluation-form columns repeat the padding point and hold a 0/1 selector
+  ST(msm_dev(ctx, plan, srs->Q, d_cols, d_o, 0));
   ST(copy_out(ctx, out_commitment, d_o, 3 * 96));
   return finish_call(ctx);
 }
@@ -1580,7 +1582,9 @@ extern "C" vrfs_status vrfs_ring_commit_rows_partial(vrfs_ctx* ctx, const vrfs_m
   uint8_t *d_cols = nullptr, *d_o = nullptr;
   ST(ring_columns_dev(ctx, n, keyset_part_size, n_keys, keys_rows, padding, n_tail, tail, &d_cols, row_lo, false));
   ST(stage_out(ctx, BUF_OUT0, 3 * 144, &d_o));
-  ST(msm_dev(ctx, msm_plan((uint32_t)n, 3, 1, msm_c_override(1), msm_aff_override(), msm_tpb_override()), srs_rows->Q, d_cols, d_o, 1));
+  MsmPlan plan = msm_plan((uint32_t)n, 3, 1, msm_c_override(1), msm_aff_override(), msm_tpb_override());
+  plan.warp_agg = 1;
+  ST(msm_dev(ctx, plan, srs_rows->Q, d_cols, d_o, 1));
   ST(copy_out(ctx, out_partial, d_o, 3 * 144));
   return finish_call(ctx);
 }
