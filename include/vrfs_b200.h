@@ -129,7 +129,7 @@ vrfs_status vrfs_pedersen_verify_wire_batch(vrfs_ctx*, vrfs_suite, size_t n, con
 vrfs_status vrfs_msm_g1_bls12_381(vrfs_ctx*, size_t n, const uint8_t* bases /*n*96*/, const uint8_t* scalars /*n_columns*n*32*/,
                                   int n_columns, uint8_t* out /*n_columns*96*/);
 /* Prepared bases: the counterpart of `RingContext` holding the SRS.  `prepare` stores 2^(c*w) * P_i for every window
- * once (device memory: ceil(256/c) * n * 144 bytes); `prepared` then computes n_columns commitments with one shared
+ * once (device memory: ceil(256/c) * n * 96 bytes, affine); `prepared` then computes n_columns commitments with one shared
  * bucket set per column and no Horner chain.  Results are identical to vrfs_msm_g1_bls12_381. */
 typedef struct vrfs_msm_bases vrfs_msm_bases;
 vrfs_status vrfs_msm_g1_prepare(vrfs_ctx*, size_t n, const uint8_t* bases /*n*96*/, vrfs_msm_bases** out);
