@@ -19,7 +19,7 @@ SYMBOLS = [
     "vrfs_pedersen_prove_batch", "vrfs_pedersen_verify_batch",
     "vrfs_suite_ietf_signature_len", "vrfs_point_decode_checked_batch", "vrfs_subgroup_check_batch", "vrfs_ietf_sign_wire_batch", "vrfs_ietf_verify_wire_batch",
     "vrfs_suite_pedersen_signature_len", "vrfs_pedersen_sign_wire_batch", "vrfs_pedersen_verify_wire_batch",
-    "vrfs_msm_g1_bls12_381", "vrfs_msm_g1_prepare", "vrfs_msm_g1_prepared", "vrfs_msm_g1_prepared_partial", "vrfs_msm_g1_release", "vrfs_msm_g1_partial", "vrfs_g1_sum_partials", "vrfs_measure_mac32_peak",
+    "vrfs_msm_g1_bls12_381", "vrfs_msm_g1_prepare", "vrfs_msm_g1_prepare_ex", "vrfs_msm_g1_prepared", "vrfs_msm_g1_prepared_partial", "vrfs_msm_g1_release", "vrfs_msm_g1_partial", "vrfs_g1_sum_partials", "vrfs_measure_mac32_peak",
     "vrfs_ring_fixed_columns", "vrfs_ring_commit", "vrfs_ring_commit_delta", "vrfs_ring_commit_rows_partial", "vrfs_fr_fft_batch", "vrfs_fq381_inv_batch", "vrfs_g1_compress_batch", "vrfs_g1_decompress_batch",
 ]
 

@@ -29,25 +29,9 @@
 
 namespace vrfs {
 
-// Modulus limbs: by default compile-time immediates (ptxas then emits IMAD.X + IMAD.HI.U32.X for the
-// reduction rows instead of one IMAD.WIDE.U32.X - the same number of multiplier passes, no registers
-// spent on the modulus).  VRFS_MOD_IN_REGS=1 XORs them with a zero loaded per lane from global memory,
-// which makes them ordinary vector registers and lets ptxas fuse the pairs; kept as a measured
-// alternative (see profiles/ and DESIGN.md "K1").
-#ifndef VRFS_MOD_IN_REGS
-#define VRFS_MOD_IN_REGS 0
-#endif
-#if defined(__CUDACC__) && VRFS_MOD_IN_REGS
-__device__ uint32_t g_opaque_zero[32];   // zero-initialised; indexed by lane so ptxas cannot prove the value warp-uniform
-#endif
-HD_INLINE uint32_t opaque_zero() {
-#if defined(__CUDA_ARCH__) && VRFS_MOD_IN_REGS
-  return g_opaque_zero[threadIdx.x & 31];
-#else
-  return 0;
-#endif
-}
-
+// Modulus limbs are compile-time immediates: ptxas emits IMAD.X + IMAD.HI.U32.X for the reduction rows instead of one
+// IMAD.WIDE.U32.X - the same number of multiplier passes, no registers spent on the modulus.  (Forcing them into registers
+// was measured and rejected in round 1: DESIGN.md "K1".)
 // Field parameter packs (generated: gen/field_consts.cuh) provide:
 //   static constexpr int N; static constexpr bool FULL (p >= 2^(32N-1)); static constexpr uint32_t NINV;
 //   HD_INLINE static uint32_t mod(i), one(i) [R mod p], r2(i), r3(i), pm2(i) [p-2], pm1h(i) [(p-1)/2]
@@ -210,8 +194,7 @@ HD_INLINE void mont_mul_limbs(uint32_t* out, const uint32_t* a, const uint32_t* 
     C::mul_wide(t, a, b);
     p256_fold<P>(out, t);
   } else if (!P::FULL) {
-    const uint32_t z = opaque_zero();
-    for (int i = 0; i < N; i++) mod[i] = P::mod(i) ^ z;
+    for (int i = 0; i < N; i++) mod[i] = P::mod(i);
     uint32_t u[N], v[N];
     // first row: v = a_even*b0 (cols 0..N-1), u = a_odd*b0 (cols 1..N)
     C::mul_row(v, a, b[0]);
@@ -295,10 +278,10 @@ HD_INLINE void mont_sqr_limbs(uint32_t* out, const uint32_t* a) {
   typedef MontChains<N> C;
   if ((P::FULL && !P::SOLINAS_P256) || !VRFS_DEDICATED_SQR) { mont_mul_limbs<P>(out, a, a); return; }
   uint32_t t[2 * N], mod[N], u[N], v[N];
-  if (P::PM_C != 0) { C::sqr_wide(t, a); pm_fold<P>(out, t); return; }
-  if (P::SOLINAS_P256) { C::mul_wide(t, a, a); p256_fold<P>(out, t); return; }   // a may use all 256 bits: sqr_wide needs the top bit clear
-  const uint32_t z = opaque_zero();
-  for (int i = 0; i < N; i++) mod[i] = P::mod(i) ^ z;
+  if constexpr (P::PM_C != 0) { C::sqr_wide(t, a); pm_fold<P>(out, t); return; }
+  else if constexpr (P::SOLINAS_P256) { C::mul_wide(t, a, a); p256_fold<P>(out, t); return; }   // a may use all 256 bits: sqr_wide needs the top bit clear
+  else {
+  for (int i = 0; i < N; i++) mod[i] = P::mod(i);
   C::sqr_wide(t, a);
   // reduce the low half: v = even-aligned window (column 0 = v[0]), u = odd-aligned; roles swap every step
   for (int i = 0; i < N; i++) { v[i] = t[i]; u[i] = 0; }
@@ -319,6 +302,7 @@ HD_INLINE void mont_sqr_limbs(uint32_t* out, const uint32_t* a) {
   C::add(v, v, t + N);          // + high half: < p + p^2/2^(32N) < 2p < 2^(32N)
   cond_sub_p<P>(v, 0u);
   for (int i = 0; i < N; i++) out[i] = v[i];
+  }
 }
 template <class P>
 HD_NOINLINE Fp<P> mont_sqr_call(Fp<P> a) {
@@ -337,44 +321,10 @@ HD_INLINE Fp<P> sqr(const Fp<P>& a) {
 #endif
 }
 
-// Two independent products / squares in one call, so that ptxas can interleave the two carry-chain streams (twice the ILP per
-// warp, half the call overhead); the twisted-Edwards formulas issue their products in independent pairs through mul2/sqr2.
-// Measured on B200 (A/B in one run): 10.709 vs 10.711 M verifies/s - no gain, so the default stays single calls; VRFS_MUL2=1
-// enables the paired form.
-#ifndef VRFS_MUL2
-#define VRFS_MUL2 0
-#endif
-template <class P> struct FpPair { Fp<P> a, b; };
-template <class P>
-HD_NOINLINE FpPair<P> mont_mul2_call(Fp<P> a, Fp<P> b, Fp<P> c, Fp<P> d) {
-  FpPair<P> r;
-  mont_mul_limbs<P>(r.a.v, a.v, b.v);
-  mont_mul_limbs<P>(r.b.v, c.v, d.v);
-  return r;
-}
-template <class P>
-HD_NOINLINE FpPair<P> mont_sqr2_call(Fp<P> a, Fp<P> c) {
-  FpPair<P> r;
-  mont_sqr_limbs<P>(r.a.v, a.v);
-  mont_sqr_limbs<P>(r.b.v, c.v);
-  return r;
-}
-template <class P> HD_INLINE void mul2(Fp<P>& r0, Fp<P>& r1, const Fp<P>& a, const Fp<P>& b, const Fp<P>& c, const Fp<P>& d) {
-#if VRFS_MUL2 && !VRFS_INLINE_MUL
-  FpPair<P> r = mont_mul2_call<P>(a, b, c, d);
-  r0 = r.a; r1 = r.b;
-#else
-  r0 = a * b; r1 = c * d;
-#endif
-}
-template <class P> HD_INLINE void sqr2(Fp<P>& r0, Fp<P>& r1, const Fp<P>& a, const Fp<P>& c) {
-#if VRFS_MUL2 && !VRFS_INLINE_MUL
-  FpPair<P> r = mont_sqr2_call<P>(a, c);
-  r0 = r.a; r1 = r.b;
-#else
-  r0 = sqr(a); r1 = sqr(c);
-#endif
-}
+// Two independent products / squares.  (A paired CALLED form that lets ptxas interleave the two carry chains was measured at
+// 10.709 vs 10.711 M verifies/s in round 1 - no gain - and removed; the formulas keep issuing their products in independent pairs.)
+template <class P> HD_INLINE void mul2(Fp<P>& r0, Fp<P>& r1, const Fp<P>& a, const Fp<P>& b, const Fp<P>& c, const Fp<P>& d) { r0 = a * b; r1 = c * d; }
+template <class P> HD_INLINE void sqr2(Fp<P>& r0, Fp<P>& r1, const Fp<P>& a, const Fp<P>& c) { r0 = sqr(a); r1 = sqr(c); }
 
 // canonical limbs (value < 2^(32N), not necessarily < p) -> Montgomery form, reduced
 template <class P>

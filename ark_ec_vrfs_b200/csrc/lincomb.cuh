@@ -16,7 +16,6 @@
 // one (secp256r1) through the Grp<C> adapter below.
 #pragma once
 #include "te.cuh"
-#include "te29.cuh"
 #include "sw.cuh"
 #include "scalar.cuh"
 
@@ -89,35 +88,6 @@ template <class C> struct Grp<C, true> {
   }
   static HD_INLINE void store_xyz(uint32_t* o, const Pt& P) { store_fp_xyz(o, P.X, P.Y, P.Z); }
 };
-// optional: Bandersnatch on the unsaturated 9x29-bit field (f29.cuh / te29.cuh); Fp<BlsFr> only at the boundary
-#ifndef VRFS_BAND_F29
-#define VRFS_BAND_F29 0   // measured SLOWER than the saturated path on B200 (IMAD.WIDE itself is half-rate): kept as an experiment
-#endif
-#if VRFS_BAND_F29
-template <> struct Grp<BandCurve, true> {
-  typedef BandCurve C;
-  typedef TE29Point Pt;
-  typedef TE29Cached Entry;
-  typedef TE29AffCached FixEntry;
-  static constexpr int SPLIT = 2, WINDOWS = 32, KB_LIMBS = 4, FIX_WINDOWS = 256 / VRFS_FIX_BITS;
-  static HD_INLINE void set_identity(Pt& P) { te29_set_identity(P); }
-  static HD_INLINE void from_affine(Pt& P, const C::F& x, const C::F& y) { P.X = f29_from_fp(x); P.Y = f29_from_fp(y); P.Z = f29_one(); P.T = f29_mul(P.X, P.Y); }
-  static HD_INLINE bool on_curve(const C::F& x, const C::F& y) { return te_on_curve<C>(x, y); }
-  static HD_INLINE void to_entry(Entry& e, const Pt& P) { te29_to_cached(e, P); }
-  static HD_INLINE void add_entry(Pt* acc, const Entry* e, bool negate) { te29_add_cached(acc, acc, e, negate); }
-  static HD_INLINE void add_fix(Pt* acc, const FixEntry* e, bool negate) { te29_madd(acc, acc, e, negate); }
-  static HD_INLINE void dbl4(Pt* acc) { te29_dbl(acc, acc, false); te29_dbl(acc, acc, false); te29_dbl(acc, acc, false); te29_dbl(acc, acc, true); }
-  static HD_INLINE void dbl(Pt* acc) { te29_dbl(acc, acc, true); }
-  static HD_INLINE void add(Pt* r, const Pt* p, const Pt* q) { Entry e; te29_to_cached(e, *q); te29_add_cached(r, p, &e, false); }
-  static HD_INLINE void endo(Pt* r, const Pt* p) { te29_endo(r, p); }
-  static HD_INLINE void to_fix(FixEntry& e, const Pt& P) {
-    C::F X = f29_to_fp(P.X), Y = f29_to_fp(P.Y), Z = f29_to_fp(P.Z);
-    C::F zi = inv(Z), x = X * zi, y = Y * zi;
-    e.x = f29_from_fp(x); e.y = f29_from_fp(y); e.dt = f29_from_fp(x * y * C::d()); e.pad = 0;
-  }
-  static HD_INLINE void store_xyz(uint32_t* o, const Pt& P) { store_fp_xyz(o, f29_to_fp(P.X), f29_to_fp(P.Y), f29_to_fp(P.Z)); }
-};
-#endif
 template <class C> struct Grp<C, false> {
   typedef SWPoint<C> Pt;
   typedef SWPoint<C> Entry;

@@ -35,11 +35,10 @@ struct MsmPlan {
   int seg_windows;               // segments per column: `windows` (stateless) or 1 (prepared)
   int tpb;                       // threads cooperating on one bucket in k_msm_accumulate (power of two <= 32)
   uint32_t big;                  // buckets with more entries than this go to k_msm_accumulate_big
-  int aff_rounds;                // bucket accumulation: pairwise rounds in affine coordinates before the XYZZ pass (0: XYZZ only)
   int warp_agg;                  // histogram / scatter: one atomic per group of lanes that hit the same bucket (set by callers that know their columns repeat values)
   int rc_h;                      // segment reduction: columns H of the R x H bucket matrix summed by k_msm_rc (0: nb <= 256, k_msm_wsum takes the buckets directly)
 };
-VRFS_HD inline MsmPlan msm_plan(uint32_t n, uint32_t ncol, int prepared, int c_override = 0, int aff_override = -1, int tpb_override = 0) {
+VRFS_HD inline MsmPlan msm_plan(uint32_t n, uint32_t ncol, int prepared, int c_override = 0, int tpb_override = 0) {
   MsmPlan p; p.n = n; p.ncol = ncol; p.prepared = prepared;
   int lg = 0; while ((1u << (lg + 1)) <= n) lg++;
   // prepared mode: all windows of a column share one bucket set, so a short top window (255 mod c bits) piles n entries onto
@@ -48,7 +47,7 @@ VRFS_HD inline MsmPlan msm_plan(uint32_t n, uint32_t ncol, int prepared, int c_o
   // tools/msm_sweep.py with scalars uniform below r (profiles/r1r_msm_sweep.json): c = 16 spends no window on the carry of bit 254
   if (prepared) p.c = lg <= 9 ? 8 : lg <= 12 ? 10 : lg <= 16 ? 13 : 16;
   else p.c = lg <= 9 ? 7 : lg <= 11 ? 9 : lg <= 13 ? 11 : lg <= 15 ? 12 : 13;
-  if (c_override >= 2 && c_override <= 18) p.c = c_override;      // tuning runs only (VRFS_MSM_C / VRFS_MSM_C_STATELESS)
+  if (c_override >= 2 && c_override <= 18) p.c = c_override;      // caller's window hint (vrfs_msm_g1_prepare_ex; tools/msm_sweep.py)
   p.windows = (255 + p.c) / p.c;          // 255 scalar bits + the top carry of the signed recoding
   p.nb = 1 << (p.c - 1);
   p.seg_windows = prepared ? 1 : p.windows;
@@ -57,13 +56,8 @@ VRFS_HD inline MsmPlan msm_plan(uint32_t n, uint32_t ncol, int prepared, int c_o
   uint64_t avg = ((uint64_t)n * (prepared ? p.windows : 1)) / p.nb;      // expected entries per bucket for uniform digits
   const uint64_t total_buckets = (uint64_t)ncol * (prepared ? 1 : p.windows) * p.nb;
   p.tpb = 1; while (p.tpb < 32 && (avg / p.tpb > 24 || (total_buckets * p.tpb < 65536 && avg / p.tpb >= 2))) p.tpb *= 2;
-  if (tpb_override >= 1 && tpb_override <= 32 && !(tpb_override & (tpb_override - 1))) p.tpb = tpb_override;       // tuning (VRFS_MSM_TPB)
+  if (tpb_override >= 1 && tpb_override <= 32 && !(tpb_override & (tpb_override - 1))) p.tpb = tpb_override;
   p.big = (uint32_t)(3 * avg + 64);     // far above any natural load (Poisson tail); a padded ring's repeated point (N/4..N/2 entries per window) must land here
-  // batched-affine rounds (k_msm_aff_round) are OFF unless VRFS_MSM_AFF asks for them: measured on B200 at N = 2^17 x 3 they
-  // take 3.48 ms against 3.30 ms of the XYZZ pass (round 0 alone 1.55 ms for half the additions) - see the note above the kernels
-  p.aff_rounds = 0;
-  if (aff_override >= 0 && prepared) p.aff_rounds = aff_override > 8 ? 8 : aff_override;      // tests / tuning (VRFS_MSM_AFF)
-  if ((uint64_t)n * p.windows >= (1u << 28)) p.aff_rounds = 0;                               // 29-bit slot indices in k_msm_aff_round
   p.warp_agg = 0;
   p.rc_h = 0;
   if (p.nb > 256) { int h = 0; while ((1 << (2 * h)) < p.nb) h++; p.rc_h = 1 << h; }   // H = 2^ceil(log2(nb)/2) <= 512
@@ -599,176 +593,6 @@ __global__ void __launch_bounds__(128, MSM_ACC_MINBLOCKS) k_msm_accumulate(MsmPl
   }
   if (live && lane == 0 && counts[b] <= p.big) copy_words16(&buckets[b], &acc);
 }
-// ---- bucket accumulation, batched-affine rounds -------------------------------------------------------------------------------
-// An affine addition costs 1 inversion + 2M + 1S; with the inversions of many independent additions shared (Montgomery's trick,
-// 3M each) that is 5M + 1S = 6 products against the 10 of the XYZZ mixed addition.  The entries of every bucket are therefore
-// added PAIRWISE in rounds: round r maps the ceil(c / 2^r) points of a bucket to ceil(c / 2^(r+1)) (pairs added, an odd last
-// point copied), all buckets of all segments at once, so a round is one flat, perfectly balanced list of independent additions.
-// Layout: round r >= 1 keeps its points at pts[seg * cap_r + off_r[b] + j] with off_r the exclusive scan of ceil(c / 2^r) inside
-// the segment (k_msm_scan_rounds; cap_r = ceil(seg_len / 2^r) + nb bounds the segment).  A warp takes a tile of 32 x MSM_AFF_B
-// output slots (found by binary search in off_{r+1}); each lane chains the denominators of its MSM_AFF_B additions, inverts the
-// product with fq381_inv_fast - branch-free, so the 32 lanes invert 32 different values in lock-step - and unwinds.
-// Exceptional cases (identity operand, P + P, P - P) are classified per pair; their denominator is 2y or 1.
-// Buckets above p.big are left to the slice kernels; after p.aff_rounds rounds k_msm_accumulate_pts sums what is left in XYZZ.
-// MEASURED (B200, N = 2^17, 3 random columns, 6.7 M entries, MSM_AFF_B = 24, 5 rounds): rounds 1.55 / 0.70 / 0.53 / 0.40 / 0.30 ms
-// = 3.48 ms against 3.30 ms for the plain XYZZ pass, so the plan leaves them off (VRFS_MSM_AFF=r turns them on; the tests do).
-// Why 6 products do not beat 10 here: the inversion is ~48 K ALU instructions per warp and tile (~55 product-times of a 12-limb
-// multiplier that needs 1 833 cycles per warp and product), every operand is fetched twice (forward and backward pass), and the
-// short late rounds are bound by the latency of one tile (~0.3 ms) rather than by throughput.  Starting the resident blocks a
-// quarter tile period apart (so that inversions and multiplier passes of different warps overlap) made round 0 slower (1.91 ms):
-// the inversion does not hide behind the other warps' products.  Tiles of 16 instead of 24 additions per lane: 2.04 ms.
-#ifndef MSM_AFF_B
-#define MSM_AFF_B 24
-#endif
-struct MsmAffArgs {
-  const uint32_t* counts;      // round-0 entries per bucket
-  const uint32_t* off_in;      // [segs * nb] exclusive offsets of the input round (relative to the segment)
-  const uint32_t* off_out;     // ... of the output round
-  const uint32_t* tot_out;     // [segs] slots of the output round
-  const uint32_t* list;        // round 0: sorted entries (point index | sign << 31)
-  const G1Aff* table;          // round 0: affine records
-  const G1Aff* pts_in;         // rounds >= 1
-  G1Aff* pts_out;
-  uint32_t* next_tile;         // device counter (zeroed by the host before every round)
-  size_t stride_in, stride_out;   // segment strides of the input (seg_len for round 0, cap_r after) and the output (cap_{r+1})
-  int r;                       // input round
-};
-VRFS_HD inline size_t msm_aff_cap(size_t seg_len, int nb, int r) { return ((seg_len + ((size_t)1 << r) - 1) >> r) + (size_t)nb; }
-HD_INLINE uint32_t msm_round_count(uint32_t c, int r, uint32_t big) { return c > big ? 0u : (c + ((1u << r) - 1u)) >> r; }
-
-// grid (segs, rounds): roff[(r-1) * nbuckets + seg * nb + i] = exclusive scan over the segment of ceil(c / 2^r), r = blockIdx.y + 1;
-// rtot[(r-1) * segs + seg] = its total
-__global__ void __launch_bounds__(256) k_msm_scan_rounds(MsmPlan p, const uint32_t* counts, uint32_t* roff, uint32_t* rtot) {
-  __shared__ uint32_t part[256];
-  const uint32_t seg = blockIdx.x, segs = gridDim.x;
-  const int r = blockIdx.y + 1;
-  const size_t nbuckets = (size_t)segs * p.nb;
-  const uint32_t* c = counts + (size_t)seg * p.nb;
-  uint32_t* o = roff + (size_t)(r - 1) * nbuckets + (size_t)seg * p.nb;
-  const int per = (p.nb + 255) / 256;
-  const int lo = threadIdx.x * per, hi = min(lo + per, p.nb);
-  uint32_t s = 0;
-  for (int i = lo; i < hi; i++) s += msm_round_count(c[i], r, p.big);
-  part[threadIdx.x] = s;
-  __syncthreads();
-  if (threadIdx.x == 0) { uint32_t run = 0; for (int i = 0; i < 256; i++) { uint32_t v = part[i]; part[i] = run; run += v; } rtot[(size_t)(r - 1) * segs + seg] = run; }
-  __syncthreads();
-  uint32_t run = part[threadIdx.x];
-  for (int i = lo; i < hi; i++) { o[i] = run; run += msm_round_count(c[i], r, p.big); }
-}
-
-// kinds of a slot: 0 copy first, 1 copy second, 2 identity, 3 add, 4 double
-template <bool FIRST>
-__device__ __forceinline__ void msm_aff_load(const MsmAffArgs& A, size_t seg, uint32_t j, Fq381& x, Fq381& y) {
-  G1Aff t;
-  if (FIRST) {
-    const uint32_t e = A.list[seg * A.stride_in + j];
-    copy_words16(&t, A.table + (e & 0x7fffffffu));
-    x = t.x; y = cneg(t.y, (e >> 31) != 0);
-  } else {
-    copy_words16(&t, A.pts_in + seg * A.stride_in + j);
-    x = t.x; y = t.y;
-  }
-}
-template <bool FIRST>
-__global__ void __launch_bounds__(128, 4) k_msm_aff_round(MsmPlan p, MsmAffArgs A, uint32_t segs) {
-  const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t tile_slots = 32u * MSM_AFF_B;
-  const uint32_t tiles_per_seg = (uint32_t)((A.stride_out + tile_slots - 1) / tile_slots);
-  Fq381 pre[MSM_AFF_B];
-  uint32_t meta[MSM_AFF_B];                        // input index of the first operand | kind << 29
-  for (;;) {
-    uint32_t tile = 0;
-    if (lane == 0) tile = atomicAdd(A.next_tile, 1u);
-    tile = __shfl_sync(0xffffffffu, tile, 0);
-    const uint32_t seg = tile / tiles_per_seg;
-    if (seg >= segs) break;
-    const uint32_t base_q = (tile % tiles_per_seg) * tile_slots, tot = A.tot_out[seg];
-    if (base_q >= tot) continue;
-    const uint32_t* oin = A.off_in + (size_t)seg * p.nb;
-    const uint32_t* oout = A.off_out + (size_t)seg * p.nb;
-    const uint32_t* cnt = A.counts + (size_t)seg * p.nb;
-    uint32_t b = 0;
-    {                                              // bucket of the lane's first slot: last b with oout[b] <= q
-      const uint32_t q = min(base_q + lane, tot - 1);
-      uint32_t lo = 0, hi = (uint32_t)p.nb;
-      while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (oout[mid] <= q) lo = mid; else hi = mid; }
-      b = lo;
-    }
-    Fq381 run;
-#pragma unroll 1
-    for (int k = 0; k < MSM_AFF_B; k++) {
-      const uint32_t q = base_q + (uint32_t)k * 32u + lane;
-      uint32_t kind = 2, j0 = 0;
-      Fq381 d = Fq381::one();
-      if (q < tot) {
-        while (b + 1 < (uint32_t)p.nb && oout[b + 1] <= q) b++;
-        const uint32_t i = q - oout[b], cin = msm_round_count(cnt[b], A.r, p.big);
-        j0 = oin[b] + 2 * i;
-        Fq381 x1, y1;
-        msm_aff_load<FIRST>(A, seg, j0, x1, y1);
-        kind = 0;
-        if (2 * i + 1 < cin) {
-          Fq381 x2, y2;
-          msm_aff_load<FIRST>(A, seg, j0 + 1, x2, y2);
-          const bool inf1 = x1.is_zero() & y1.is_zero(), inf2 = x2.is_zero() & y2.is_zero();
-          if (inf1) kind = 1;
-          else if (!inf2) {
-            d = x2 - x1;
-            if (!d.is_zero()) kind = 3;
-            else if (y1 == y2 && !y1.is_zero()) { kind = 4; d = dbl(y1); }
-            else { kind = 2; d = Fq381::one(); }
-          }
-        }
-      }
-      run = k ? run * d : d;
-      pre[k] = run;
-      meta[k] = j0 | (kind << 29);
-    }
-    Fq381 inv = fq381_inv_fast(run);
-#pragma unroll 1
-    for (int k = MSM_AFF_B - 1; k >= 0; k--) {
-      const uint32_t q = base_q + (uint32_t)k * 32u + lane;
-      const uint32_t kind = meta[k] >> 29, j0 = meta[k] & 0x1fffffffu;
-      Fq381 dinv = inv;
-      if (k) dinv = inv * pre[k - 1];
-      G1Aff out; out.x = Fq381::zero(); out.y = Fq381::zero();
-      if (kind >= 3) {
-        Fq381 x1, y1, x2, y2;
-        msm_aff_load<FIRST>(A, seg, j0, x1, y1);
-        Fq381 lam, d;
-        if (kind == 3) { msm_aff_load<FIRST>(A, seg, j0 + 1, x2, y2); d = x2 - x1; lam = (y2 - y1) * dinv; }
-        else { x2 = x1; d = dbl(y1); Fq381 xx = sqr(x1); lam = (dbl(xx) + xx) * dinv; }
-        if (k) inv = inv * d;
-        out.x = sqr(lam) - x1 - x2;
-        out.y = lam * (x1 - out.x) - y1;
-      } else if (kind != 2) {
-        msm_aff_load<FIRST>(A, seg, j0 + kind, out.x, out.y);
-      }
-      if (q < tot) copy_words16(A.pts_out + (size_t)seg * A.stride_out + q, &out);
-    }
-  }
-}
-// what the rounds left of every bucket (<= ceil(big / 2^R) points), summed in XYZZ -> projective bucket
-__global__ void __launch_bounds__(128, MSM_ACC_MINBLOCKS) k_msm_accumulate_pts(MsmPlan p, const uint32_t* counts, const uint32_t* off, const G1Aff* pts, size_t stride, G1Pt* buckets) {
-  const size_t total = (size_t)p.ncol * p.seg_windows * p.nb;
-  const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= total) return;
-  const uint32_t c0 = counts[b];
-  if (c0 > p.big) return;                          // written by k_msm_big_combine
-  const uint32_t cnt = msm_round_count(c0, p.aff_rounds, p.big);
-  const size_t seg = b / p.nb;
-  const G1Aff* l = pts + seg * stride + off[b];
-  G1Xyzz acc; xyzz_set_identity(acc);
-  for (uint32_t j = 0; j < cnt; j++) {
-    Fq381 x, y;
-    if (g1_load_aff_xy(x, y, l + j, false)) xyzz_madd(&acc, &x, &y);
-  }
-  G1Pt out;
-  xyzz_to_proj(out, acc);
-  copy_words16(&buckets[b], &out);
-}
-
 // one block per slice of an oversized bucket: strided partial sums + shared-memory tree -> bigpart[slice];
 // k_msm_big_combine then adds the slices of each bucket.  (A ring's 0/1 selector column puts half the domain into ONE bucket:
 // a single block needed 4.8 ms for it at N = 2^17.)

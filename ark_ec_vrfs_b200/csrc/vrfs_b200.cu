@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <mutex>
 #include <new>
+#include <vector>
 
 #include "../../include/vrfs_b200.h"
 #include "h2c.cuh"
@@ -149,18 +150,6 @@ __global__ void __launch_bounds__(256) k_mac_bench(uint32_t* out, int iters, uns
     uint32_t s = 0;
     for (int c = 0; c < 4; c++) { s ^= top[c]; for (int i = 0; i < 8; i++) s ^= acc[c][i]; }
     out[t] = s;
-  } else if (VARIANT == 7 || VARIANT == 8) {   // unsaturated 9x29 products (f29.cuh): 7 = mul chain, 8 = mul + sqr; 32 products per iteration
-    F29 a, b;
-    for (int i = 0; i < 9; i++) { a.v[i] = (int32_t)((t * 2654435761u + i * 40503u) & F29_MASK); b.v[i] = (int32_t)(((t ^ 0x5bd1e995u) * 2246822519u + i) & F29_MASK); }
-    a.v[8] &= 0xffff; b.v[8] &= 0xffff;
-#pragma unroll 1
-    for (int i = 0; i < iters; i++) {
-#pragma unroll 1
-      for (int r = 0; r < 16; r++) { a = f29_mul(a, b); b = VARIANT == 7 ? f29_mul(b, a) : f29_sqr(a); }
-    }
-    uint32_t s = 0;
-    for (int i = 0; i < 9; i++) s ^= (uint32_t)(a.v[i] ^ b.v[i]);
-    out[t] = s;
   } else if (VARIANT == 9) {   // DFMA: acc = fma(acc, y, x) with round-toward-zero, 8 independent chains (FP64 pipe)
     double a[8];
     for (int k = 0; k < 8; k++) a[k] = 1.0 + (double)((t + k) & 1023) * 1e-3;
@@ -220,6 +209,7 @@ struct vrfs_ctx {
   uint64_t launches = 0;
   DevBuf buf[BUF_COUNT];
   void* fixtab[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};   // [suite][G | blinding base]
+  std::vector<struct vrfs_msm_bases*> prepared;   // live prepared-base handles (freed / orphaned by vrfs_ctx_destroy)
 };
 
 static vrfs_status fail(vrfs_ctx* c, vrfs_status st, const char* fmt, ...) {
@@ -242,6 +232,7 @@ static vrfs_status fail(vrfs_ctx* c, vrfs_status st, const char* fmt, ...) {
 #define LAUNCHED_AS(ctx, name) do { (ctx)->launches++; CU(cudaGetLastError()); ST(note_kernel((ctx), (name))); } while (0)
 static vrfs_status note_kernel(vrfs_ctx* ctx, const char* name);
 static vrfs_status timing_begin(vrfs_ctx* ctx);
+static void orphan_prepared(vrfs_ctx* ctx);
 
 static vrfs_status timing_begin(vrfs_ctx* ctx) {
   ctx->n_timed = 0;
@@ -331,6 +322,7 @@ extern "C" void vrfs_ctx_destroy(vrfs_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  orphan_prepared(ctx);
   for (int i = 0; i < BUF_COUNT; i++) if (ctx->buf[i].p) cudaFree(ctx->buf[i].p);
   for (int s = 0; s < 3; s++) for (int b = 0; b < 2; b++) if (ctx->fixtab[s][b]) cudaFree(ctx->fixtab[s][b]);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -515,7 +507,7 @@ extern "C" vrfs_status vrfs_measure_mac32_peak(vrfs_ctx* ctx, int variant, doubl
   void *out = nullptr, *cyc = nullptr;
   ST(ensure(ctx, BUF_W0, (size_t)threads * blocks * 4, &out));
   ST(ensure(ctx, BUF_W1, 64, &cyc));
-  const bool field_mul = (variant == 2 || variant == 3 || variant == 7 || variant == 8);
+  const bool field_mul = (variant == 2 || variant == 3);
   int iters = field_mul ? 64 : 4096;
   double macs_per_thread_iter = field_mul ? 32.0 * 136.0 : 32.0;   // field products are counted as 136 MAC32 (the saturated 8-limb model) in every representation
   float ms = 0;
@@ -529,8 +521,6 @@ extern "C" vrfs_status vrfs_measure_mac32_peak(vrfs_ctx* ctx, int variant, doubl
       case 4: k_mac_bench<4><<<blocks, threads, 0, ctx->stream>>>((uint32_t*)out, iters, (unsigned long long*)cyc); break;
       case 5: k_mac_bench<5><<<blocks, threads, 0, ctx->stream>>>((uint32_t*)out, iters, (unsigned long long*)cyc); break;
       case 6: k_mac_bench<6><<<blocks, threads, 0, ctx->stream>>>((uint32_t*)out, iters, (unsigned long long*)cyc); break;
-      case 7: k_mac_bench<7><<<blocks, threads, 0, ctx->stream>>>((uint32_t*)out, iters, (unsigned long long*)cyc); break;
-      case 8: k_mac_bench<8><<<blocks, threads, 0, ctx->stream>>>((uint32_t*)out, iters, (unsigned long long*)cyc); break;
       case 9: k_mac_bench<9><<<blocks, threads, 0, ctx->stream>>>((uint32_t*)out, iters, (unsigned long long*)cyc); break;
       default: return fail(ctx, VRFS_BAD_ARG, "unknown variant %d", variant);
     }
@@ -1299,24 +1289,18 @@ extern "C" vrfs_status vrfs_pedersen_verify_wire_batch(vrfs_ctx* ctx, vrfs_suite
 // =================================================================================================
 // prepared bases (vrfs_msm_g1_prepare): the RingContext analogue - the SRS is fixed, so 2^(c w) P_i is computed once
 struct vrfs_msm_bases {
-  vrfs_ctx* ctx;
+  vrfs_ctx* ctx;    // nullptr once the context was destroyed first (the table is gone; release only frees this record)
   size_t n;
-  MsmPlan plan;
+  MsmPlan plan;     // the plan that sized and filled Q (window bits c, windows); per-call plans keep its c
+  int tpb_hint;     // 0 = automatic
   void* Q;          // windows * n affine points (96 B each; identity = zeros)
 };
+// the plan of one call on prepared bases: window size and count are the handle's (they fix the layout of Q), only the
+// column count (and with it the threads per bucket) is per call
+static MsmPlan plan_for(const vrfs_msm_bases* h, int n_columns) {
+  return msm_plan((uint32_t)h->n, (uint32_t)n_columns, 1, h->plan.c, h->tpb_hint);
+}
 // bases: G1Aff[n] (stateless) or the prepared table Q; scalars on the device
-static int msm_c_override(int prepared) {
-  const char* e = getenv(prepared ? "VRFS_MSM_C" : "VRFS_MSM_C_STATELESS");
-  return e ? atoi(e) : 0;
-}
-static int msm_tpb_override() {
-  const char* e = getenv("VRFS_MSM_TPB");
-  return e ? atoi(e) : 0;
-}
-static int msm_aff_override() {
-  const char* e = getenv("VRFS_MSM_AFF");
-  return e ? atoi(e) : -1;
-}
 static vrfs_status msm_dev(vrfs_ctx* ctx, MsmPlan p, const void* d_bases, const uint8_t* d_scalars, uint8_t* d_out, int out_mode) {
   const size_t n = p.n, ncol = p.ncol;
   const size_t segs = ncol * p.seg_windows, nbuckets = segs * p.nb, seg_len = n * (p.prepared ? p.windows : 1);
@@ -1345,43 +1329,7 @@ static vrfs_status msm_dev(vrfs_ctx* ctx, MsmPlan p, const void* d_bases, const 
   LAUNCHED_AS(ctx, "msm_scatter");
   const unsigned ab = (unsigned)((nbuckets * p.tpb + 127) / 128);
   const unsigned bigb = (unsigned)(ctx->sms * 4);
-  if (p.aff_rounds) {
-    // batched-affine rounds (prepared mode, large domains): per-round offsets | totals | tile counters ; ping-pong point buffers
-    const int R = p.aff_rounds;
-    void *rbuf = nullptr, *ptsA = nullptr, *ptsB = nullptr;
-    ST(ensure(ctx, BUF_X2, ((size_t)R * nbuckets + (size_t)R * segs + 16) * sizeof(uint32_t), &rbuf));
-    ST(ensure(ctx, BUF_X0, segs * msm_aff_cap(seg_len, p.nb, 1) * sizeof(G1Aff), &ptsA));
-    ST(ensure(ctx, BUF_X1, segs * msm_aff_cap(seg_len, p.nb, 2) * sizeof(G1Aff), &ptsB));
-    uint32_t *roff = (uint32_t*)rbuf, *rtot = roff + (size_t)R * nbuckets, *tiles_ctr = rtot + (size_t)R * segs;
-    CU(cudaMemsetAsync(tiles_ctr, 0, 16 * sizeof(uint32_t), ctx->stream));
-    k_msm_scan_rounds<<<dim3((unsigned)segs, (unsigned)R), 256, 0, ctx->stream>>>(p, (const uint32_t*)counts, roff, rtot);
-    LAUNCHED_AS(ctx, "msm_scan_rounds");
-    for (int r = 0; r < R; r++) {
-      MsmAffArgs A;
-      A.counts = (const uint32_t*)counts;
-      A.off_in = r == 0 ? offsets : roff + (size_t)(r - 1) * nbuckets;
-      A.off_out = roff + (size_t)r * nbuckets;
-      A.tot_out = rtot + (size_t)r * segs;
-      A.list = (const uint32_t*)list; A.table = (const G1Aff*)d_bases;
-      A.pts_in = (const G1Aff*)((r & 1) ? ptsA : ptsB);
-      A.pts_out = (G1Aff*)(((r + 1) & 1) ? ptsA : ptsB);
-      A.next_tile = tiles_ctr + r;
-      A.stride_in = r == 0 ? seg_len : msm_aff_cap(seg_len, p.nb, r);
-      A.stride_out = msm_aff_cap(seg_len, p.nb, r + 1);
-      A.r = r;
-      const size_t tiles = segs * ((A.stride_out + 32 * MSM_AFF_B - 1) / (32 * MSM_AFF_B));
-      const unsigned blocks = (unsigned)std::min<size_t>((tiles + 3) / 4, (size_t)ctx->sms * 4);
-      if (r == 0) k_msm_aff_round<true><<<blocks, 128, 0, ctx->stream>>>(p, A, (uint32_t)segs);
-      else k_msm_aff_round<false><<<blocks, 128, 0, ctx->stream>>>(p, A, (uint32_t)segs);
-      static const char* const round_names[8] = {"msm_aff_round0", "msm_aff_round1", "msm_aff_round2", "msm_aff_round3", "msm_aff_round4", "msm_aff_round5", "msm_aff_round6", "msm_aff_round7"};
-      LAUNCHED_AS(ctx, round_names[r & 7]);
-    }
-    k_msm_accumulate_pts<<<(unsigned)((nbuckets + 127) / 128), 128, 0, ctx->stream>>>(p, (const uint32_t*)counts, roff + (size_t)(R - 1) * nbuckets,
-                                                                                     (const G1Aff*)((R & 1) ? ptsA : ptsB), msm_aff_cap(seg_len, p.nb, R), (G1Pt*)buckets);
-    LAUNCHED_AS(ctx, "msm_accumulate");
-    if (p.prepared) k_msm_accumulate_big<true><<<bigb, MSM_BIG_THREADS, 0, ctx->stream>>>(p, d_bases, (const uint32_t*)counts, offsets, (const uint32_t*)list, big_list, big_count, bigpart);
-    else k_msm_accumulate_big<false><<<bigb, MSM_BIG_THREADS, 0, ctx->stream>>>(p, d_bases, (const uint32_t*)counts, offsets, (const uint32_t*)list, big_list, big_count, bigpart);
-  } else if (p.prepared) {
+  if (p.prepared) {
     k_msm_accumulate<true><<<ab, 128, 0, ctx->stream>>>(p, d_bases, (const uint32_t*)counts, offsets, (const uint32_t*)list, (G1Pt*)buckets);
     LAUNCHED_AS(ctx, "msm_accumulate");
     k_msm_accumulate_big<true><<<bigb, MSM_BIG_THREADS, 0, ctx->stream>>>(p, d_bases, (const uint32_t*)counts, offsets, (const uint32_t*)list, big_list, big_count, bigpart);
@@ -1423,7 +1371,7 @@ static vrfs_status msm_host(vrfs_ctx* ctx, size_t n, const uint8_t* bases, const
   ST(ensure(ctx, BUF_W0, n * sizeof(G1Aff), &bases_m));
   k_msm_prep_bases<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((uint32_t)n, d_b, (G1Aff*)bases_m);
   LAUNCHED_AS(ctx, "msm_prep_bases");
-  ST(msm_dev(ctx, msm_plan((uint32_t)n, (uint32_t)ncol, 0, msm_c_override(0)), bases_m, d_s, d_o, out_mode));
+  ST(msm_dev(ctx, msm_plan((uint32_t)n, (uint32_t)ncol, 0), bases_m, d_s, d_o, out_mode));
   ST(copy_out(ctx, out, d_o, ob * ncol));
   return finish_call(ctx);
 }
@@ -1433,35 +1381,67 @@ extern "C" vrfs_status vrfs_msm_g1_bls12_381(vrfs_ctx* ctx, size_t n, const uint
 extern "C" vrfs_status vrfs_msm_g1_partial(vrfs_ctx* ctx, size_t n, const uint8_t* bases, const uint8_t* scalars, int n_columns, uint8_t* out_partial) {
   return msm_host(ctx, n, bases, scalars, n_columns, out_partial, 1);
 }
-extern "C" vrfs_status vrfs_msm_g1_prepare(vrfs_ctx* ctx, size_t n, const uint8_t* bases, vrfs_msm_bases** out) {
+static vrfs_status msm_prepare_impl(vrfs_ctx* ctx, size_t n, const uint8_t* bases, int window_bits, int threads_per_bucket, vrfs_msm_bases** out) {
   if (!ctx || !out) return VRFS_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
   *out = nullptr;
   if (n == 0 || !bases) return fail(ctx, VRFS_BAD_ARG, "empty base vector");
   if (n > (1u << 24)) return fail(ctx, VRFS_BAD_ARG, "prepared MSM size above 2^24 is not supported");
+  if (window_bits != 0 && (window_bits < 2 || window_bits > 18)) return fail(ctx, VRFS_BAD_ARG, "window_bits must be 0 (automatic) or 2..18");
+  if (threads_per_bucket != 0 && (threads_per_bucket < 1 || threads_per_bucket > 32 || (threads_per_bucket & (threads_per_bucket - 1))))
+    return fail(ctx, VRFS_BAD_ARG, "threads_per_bucket must be 0 (automatic) or a power of two <= 32");
   ST(begin_call(ctx, n));
   vrfs_msm_bases* h = new (std::nothrow) vrfs_msm_bases();
   if (!h) return fail(ctx, VRFS_CUDA_ERROR, "out of host memory");
-  h->ctx = ctx; h->n = n; h->plan = msm_plan((uint32_t)n, 1, 1, msm_c_override(1), msm_aff_override(), msm_tpb_override()); h->Q = nullptr;
+  h->ctx = ctx; h->n = n; h->tpb_hint = threads_per_bucket; h->plan = msm_plan((uint32_t)n, 1, 1, window_bits, threads_per_bucket); h->Q = nullptr;
   cudaError_t e = cudaMalloc(&h->Q, (size_t)h->plan.windows * n * sizeof(G1Aff));
   if (e != cudaSuccess) { delete h; return fail(ctx, VRFS_CUDA_ERROR, "cudaMalloc of the prepared table failed: %s", cudaGetErrorString(e)); }
+  // a failure below must not leak the table (up to GBs) nor hand out a half-built handle
+  auto build = [&]() -> vrfs_status {
+    const uint8_t* d_b; void* bases_m = nullptr;
+    ST(stage_in(ctx, BUF_IN0, bases, n * 96, &d_b));
+    ST(ensure(ctx, BUF_W0, n * sizeof(G1Aff), &bases_m));
+    k_msm_prep_bases<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((uint32_t)n, d_b, (G1Aff*)bases_m);
+    LAUNCHED_AS(ctx, "msm_prep_bases");
+    k_msm_prepare<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((uint32_t)n, h->plan.c, h->plan.windows, (const G1Aff*)bases_m, (G1Aff*)h->Q);
+    LAUNCHED_AS(ctx, "msm_prepare");
+    return finish_call(ctx);
+  };
+  vrfs_status st = build();
+  if (st != VRFS_OK) { cudaStreamSynchronize(ctx->stream); cudaFree(h->Q); delete h; return st; }
+  ctx->prepared.push_back(h);
   *out = h;
-  const uint8_t* d_b; void* bases_m = nullptr;
-  ST(stage_in(ctx, BUF_IN0, bases, n * 96, &d_b));
-  ST(ensure(ctx, BUF_W0, n * sizeof(G1Aff), &bases_m));
-  k_msm_prep_bases<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((uint32_t)n, d_b, (G1Aff*)bases_m);
-  LAUNCHED_AS(ctx, "msm_prep_bases");
-  k_msm_prepare<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((uint32_t)n, h->plan.c, h->plan.windows, (const G1Aff*)bases_m, (G1Aff*)h->Q);
-  LAUNCHED_AS(ctx, "msm_prepare");
-  return finish_call(ctx);
+  return VRFS_OK;
 }
+extern "C" vrfs_status vrfs_msm_g1_prepare(vrfs_ctx* ctx, size_t n, const uint8_t* bases, vrfs_msm_bases** out) {
+  return msm_prepare_impl(ctx, n, bases, 0, 0, out);
+}
+extern "C" vrfs_status vrfs_msm_g1_prepare_ex(vrfs_ctx* ctx, size_t n, const uint8_t* bases, int window_bits, int threads_per_bucket, vrfs_msm_bases** out) {
+  return msm_prepare_impl(ctx, n, bases, window_bits, threads_per_bucket, out);
+}
+// Handles may be released before or after their context: vrfs_ctx_destroy frees the tables of the handles still alive and
+// orphans them (ctx = nullptr); releasing an orphan only frees the record.  (Registry guarded by a global mutex because an
+// orphan has no context mutex left to take.)
+static std::mutex g_handles_mu;
 extern "C" void vrfs_msm_g1_release(vrfs_msm_bases* h) {
   if (!h) return;
-  std::lock_guard<std::recursive_mutex> lock_(h->ctx->mu);
-  cudaSetDevice(h->ctx->device);
-  cudaStreamSynchronize(h->ctx->stream);
-  if (h->Q) cudaFree(h->Q);
+  vrfs_ctx* ctx;
+  { std::lock_guard<std::mutex> g(g_handles_mu); ctx = h->ctx; }
+  if (ctx) {
+    std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
+    std::lock_guard<std::mutex> g(g_handles_mu);
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (h->Q) cudaFree(h->Q);
+    auto& v = ctx->prepared;
+    v.erase(std::remove(v.begin(), v.end(), h), v.end());
+  }
   delete h;
+}
+static void orphan_prepared(vrfs_ctx* ctx) {      // called by vrfs_ctx_destroy (device set, stream synchronised)
+  std::lock_guard<std::mutex> g(g_handles_mu);
+  for (vrfs_msm_bases* h : ctx->prepared) { if (h->Q) cudaFree(h->Q); h->Q = nullptr; h->ctx = nullptr; }
+  ctx->prepared.clear();
 }
 static vrfs_status msm_prepared_host(vrfs_ctx* ctx, const vrfs_msm_bases* h, const uint8_t* scalars, int n_columns, uint8_t* out, int out_mode) {
   if (!ctx || !h || h->ctx != ctx) return VRFS_BAD_ARG;
@@ -1472,7 +1452,7 @@ static vrfs_status msm_prepared_host(vrfs_ctx* ctx, const vrfs_msm_bases* h, con
   const uint8_t* d_s; uint8_t* d_o;
   ST(stage_in(ctx, BUF_IN1, scalars, h->n * 32 * (size_t)n_columns, &d_s));
   ST(stage_out(ctx, BUF_OUT0, ob * n_columns, &d_o));
-  MsmPlan p = msm_plan((uint32_t)h->n, (uint32_t)n_columns, 1, msm_c_override(1), msm_aff_override(), msm_tpb_override());
+  MsmPlan p = plan_for(h, n_columns);
   ST(msm_dev(ctx, p, h->Q, d_s, d_o, out_mode));
   ST(copy_out(ctx, out, d_o, ob * n_columns));
   return finish_call(ctx);
@@ -1566,7 +1546,7 @@ extern "C" vrfs_status vrfs_ring_commit(vrfs_ctx* ctx, const vrfs_msm_bases* srs
     ST(ntt_dev(ctx, logn, 3, 1, d_cols, d_cols));
   }
   ST(stage_out(ctx, BUF_OUT0, 3 * 96, &d_o));
-  MsmPlan plan = msm_plan((uint32_t)n, 3, 1, msm_c_override(1), msm_aff_override(), msm_tpb_override());
+  MsmPlan plan = plan_for(srs, 3);
   plan.warp_agg = srs_is_lagrange ? 1 : 0;       // evaluation-form columns repeat the padding point and hold a 0/1 selector
   ST(msm_dev(ctx, plan, srs->Q, d_cols, d_o, 0));
   ST(copy_out(ctx, out_commitment, d_o, 3 * 96));
@@ -1582,7 +1562,7 @@ extern "C" vrfs_status vrfs_ring_commit_rows_partial(vrfs_ctx* ctx, const vrfs_m
   uint8_t *d_cols = nullptr, *d_o = nullptr;
   ST(ring_columns_dev(ctx, n, keyset_part_size, n_keys, keys_rows, padding, n_tail, tail, &d_cols, row_lo, false));
   ST(stage_out(ctx, BUF_OUT0, 3 * 144, &d_o));
-  MsmPlan plan = msm_plan((uint32_t)n, 3, 1, msm_c_override(1), msm_aff_override(), msm_tpb_override());
+  MsmPlan plan = plan_for(srs_rows, 3);
   plan.warp_agg = 1;
   ST(msm_dev(ctx, plan, srs_rows->Q, d_cols, d_o, 1));
   ST(copy_out(ctx, out_partial, d_o, 3 * 144));
@@ -1603,7 +1583,7 @@ extern "C" vrfs_status vrfs_ring_commit_delta(vrfs_ctx* ctx, const vrfs_msm_base
   k_ring_delta_columns<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((uint32_t)n, (uint32_t)n_keys, d_k, d_p, (uint8_t*)cols);
   LAUNCHED_AS(ctx, "ring_delta_columns");
   ST(stage_out(ctx, BUF_OUT0, 2 * 96, &d_o));
-  ST(msm_dev(ctx, msm_plan((uint32_t)n, 2, 1, msm_c_override(1), msm_aff_override(), msm_tpb_override()), srs_lagrange->Q, (const uint8_t*)cols, d_o, 0));
+  ST(msm_dev(ctx, plan_for(srs_lagrange, 2), srs_lagrange->Q, (const uint8_t*)cols, d_o, 0));
   ST(copy_out(ctx, out_delta, d_o, 2 * 96));
   return finish_call(ctx);
 }

@@ -70,6 +70,8 @@ class PreparedBases:
         if self.handle:
             self.engine._lib.vrfs_msm_g1_release(self.handle)
             self.handle = None
+            if self in self.engine._prepared:
+                self.engine._prepared.remove(self)
 
 
 class Engine:
@@ -77,6 +79,7 @@ class Engine:
 
     def __init__(self, device=0):
         self._lib = _lib.load()
+        self._prepared = []
         self._ctx = C.c_void_p()
         st = self._lib.vrfs_ctx_create(int(device), C.byref(self._ctx))
         if st != _lib.OK:
@@ -89,6 +92,8 @@ class Engine:
 
     def close(self):
         if getattr(self, "_ctx", None):
+            for p in list(self._prepared):          # outstanding prepared bases go with their context
+                p.release()
             self._lib.vrfs_ctx_destroy(self._ctx)
             self._ctx = None
 
@@ -265,12 +270,15 @@ class Engine:
         self._call("vrfs_msm_g1_bls12_381", C.c_size_t(n), _p(bases), _p(scalars), int(n_columns), _p(out))
         return out
 
-    def msm_g1_prepare(self, bases):
-        """RingContext analogue: returns a handle holding 2^(c w) * P_i on the device"""
+    def msm_g1_prepare(self, bases, window_bits=0, threads_per_bucket=0):
+        """RingContext analogue: returns a handle holding 2^(c w) * P_i on the device (window_bits / threads_per_bucket 0 = the
+        plan's own choice; anything else is a tuning hint, vrfs_msm_g1_prepare_ex)"""
         bases = _u8(bases, (-1, 96)); n = len(bases)
         h = C.c_void_p()
-        self._call("vrfs_msm_g1_prepare", C.c_size_t(n), _p(bases), C.byref(h))
-        return PreparedBases(self, h, n)
+        self._call("vrfs_msm_g1_prepare_ex", C.c_size_t(n), _p(bases), int(window_bits), int(threads_per_bucket), C.byref(h))
+        p = PreparedBases(self, h, n)
+        self._prepared.append(p)
+        return p
 
     def msm_g1_partial(self, bases, scalars, n_columns=1):
         bases = _u8(bases, (-1, 96)); n = len(bases); scalars = _u8(scalars, (n_columns * n, 32))

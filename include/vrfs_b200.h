@@ -133,10 +133,15 @@ vrfs_status vrfs_msm_g1_bls12_381(vrfs_ctx*, size_t n, const uint8_t* bases /*n*
  * bucket set per column and no Horner chain.  Results are identical to vrfs_msm_g1_bls12_381. */
 typedef struct vrfs_msm_bases vrfs_msm_bases;
 vrfs_status vrfs_msm_g1_prepare(vrfs_ctx*, size_t n, const uint8_t* bases /*n*96*/, vrfs_msm_bases** out);
+/* the same with tuning hints: window_bits (0 = automatic, else 2..18) and threads_per_bucket (0 = automatic, else a power of two
+ * <= 32).  The results never depend on them.  On failure *out stays NULL and nothing is leaked. */
+vrfs_status vrfs_msm_g1_prepare_ex(vrfs_ctx*, size_t n, const uint8_t* bases /*n*96*/, int window_bits, int threads_per_bucket, vrfs_msm_bases** out);
 vrfs_status vrfs_msm_g1_prepared(vrfs_ctx*, const vrfs_msm_bases* bases, const uint8_t* scalars /*n_columns*n*32*/, int n_columns, uint8_t* out /*n_columns*96*/);
 /* the same over this rank's point range, projective partial out (144 B per column) - the multi-GPU form: prepare each rank's
  * slice of the SRS once, all-gather the partials, fold them with vrfs_g1_sum_partials */
 vrfs_status vrfs_msm_g1_prepared_partial(vrfs_ctx*, const vrfs_msm_bases* bases, const uint8_t* scalars, int n_columns, uint8_t* out_partial /*n_columns*144*/);
+/* May be called before or after vrfs_ctx_destroy of the owning context (destroy frees the tables of handles still alive;
+ * releasing such a handle afterwards only frees its record). */
 void vrfs_msm_g1_release(vrfs_msm_bases* bases);
 /* multi-GPU MSM helper: this rank's partial sums over its point range, projective (X,Y,Z 48-byte LE
  * canonical each = 144 bytes per column), to be gathered (NCCL all-gather of 144*n_columns bytes) and

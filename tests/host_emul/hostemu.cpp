@@ -124,23 +124,6 @@ extern "C" void hostemu_glv(const uint32_t* k, uint32_t* out /*4+4+2*/) {
   memcpy(out, a.mag, 16); memcpy(out + 4, b.mag, 16); out[8] = a.neg; out[9] = b.neg;
 }
 
-// f29 unit tests: op 0 mul, 1 sqr, 2 from_fp->to_fp round trip of a Montgomery-256 value, 3 canonical limbs of a lazy value
-extern "C" void hostemu_f29(int op, const int32_t* a, const int32_t* b, int32_t* out) {
-  F29 x, y, r = f29_zero();
-  memcpy(x.v, a, 36); memcpy(y.v, b, 36);
-  if (op == 0) r = f29_mul(x, y);
-  else if (op == 1) r = f29_sqr(x);
-  else if (op == 3) { uint32_t l[9]; f29_canonical_limbs(l, x); memcpy(r.v, l, 36); }
-  memcpy(out, r.v, 36);
-}
-extern "C" void hostemu_f29_roundtrip(const uint32_t* fp_in, uint32_t* fp_out, int32_t* f29_out) {
-  Fp<BlsFr> x; memcpy(x.v, fp_in, 32);
-  F29 y = f29_from_fp(x);
-  memcpy(f29_out, y.v, 36);
-  Fp<BlsFr> z = f29_to_fp(y);
-  memcpy(fp_out, z.v, 32);
-}
-
 // wire formats (csrc/wire.cuh) on the host: checked point decode, proof parse, signature pack
 #include "../../ark_ec_vrfs_b200/csrc/wire.cuh"
 template <class S> static void wire_decode_checked(size_t n, const uint8_t* enc, uint8_t* out, uint8_t* ok) {

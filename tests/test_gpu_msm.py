@@ -163,15 +163,14 @@ def test_prepared_partials_fold_to_the_full_commitment(eng):
     assert np.array_equal(got, O.msm_g1(bases, sc, ncol))
 
 
-@pytest.mark.parametrize("rounds", [1, 3, 6])
-def test_msm_batched_affine_rounds_exceptional_and_skewed(eng, rounds, monkeypatch):
-    """the batched-affine pairwise rounds of the bucket accumulation (chosen by the plan for large prepared domains, forced here
-    at test sizes through VRFS_MSM_AFF): identity operands, P + P, P + (-P), odd bucket sizes, empty buckets, oversized buckets
-    and all-zero columns, against the oracle"""
-    monkeypatch.setenv("VRFS_MSM_AFF", str(rounds))
+@pytest.mark.parametrize("window_bits", [0, 6, 9])
+def test_msm_exceptional_and_skewed_inputs(eng, window_bits):
+    """the incomplete XYZZ mixed addition of the bucket accumulation handles its exceptional cases explicitly: identity operands,
+    P + P, P + (-P), odd bucket sizes, empty buckets, oversized buckets and all-zero columns, against the oracle - with the plan's
+    own window size and with two caller-chosen ones (vrfs_msm_g1_prepare_ex)"""
     P_MOD = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
     for n in (5, 300, 3000):
-        bases, sc = synth(n, 3, b"aff%d" % rounds)
+        bases, sc = synth(n, 3, b"exc%d" % window_bits)
         neg = bases.copy()
         for i in range(n):
             y = int.from_bytes(bases[i, 48:].tobytes(), "little")
@@ -188,27 +187,13 @@ def test_msm_batched_affine_rounds_exceptional_and_skewed(eng, rounds, monkeypat
             if n > 8: s[col * n + 7] = s[col * n + 6]
         s[2 * n:] = 0; s[2 * n: 2 * n + (2 * n) // 3, 0] = 1         # column 2: a 0/1 selector (one oversized bucket)
         exp = O.msm_g1(b, s, 3)
-        h = eng.msm_g1_prepare(b)
+        h = eng.msm_g1_prepare(b, window_bits=window_bits)
         try:
             assert np.array_equal(h.msm(s, 3), exp)
             assert not h.msm(np.zeros((n, 32), np.uint8), 1).any()
         finally:
             h.release()
-
-
-def test_msm_batched_affine_equals_xyzz_at_2p15(eng, monkeypatch):
-    n = 1 << 15
-    rng = np.random.default_rng(77)
-    ks = np.zeros((2048, 32), np.uint8); ks[:, :8] = rng.integers(1, 2 ** 62, size=2048, dtype=np.uint64).view(np.uint8).reshape(2048, 8)
-    bases = np.tile(O.g1_mul_gen(ks), (n // 2048, 1))            # every base 16 times: doublings inside the rounds
-    sc = rng.integers(0, 256, size=(3 * n, 32), dtype=np.uint8); sc[:, 31] &= 0x3F
-    sc[2 * n:] = 0; sc[2 * n: 2 * n + n // 2, 0] = 1
-    outs = []
-    for rounds in ("0", "4"):
-        monkeypatch.setenv("VRFS_MSM_AFF", rounds)
-        h = eng.msm_g1_prepare(bases)
-        outs.append(h.msm(sc, 3)); h.release()
-    assert np.array_equal(outs[0], outs[1]) and outs[0].any()
+        assert np.array_equal(eng.msm_g1(b, s, 3), exp)
 
 
 def test_fq381_inverse_on_the_gpu(eng):

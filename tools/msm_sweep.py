@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Window-size sweep of the prepared 3-column MSM (tuning aid for msm_plan): device ms per (log2 n, c).
-  python tools/msm_sweep.py [lo hi]      # VRFS_MSM_C is set per run; results must agree across c"""
+  python tools/msm_sweep.py [lo hi]      # window bits passed per run (vrfs_msm_g1_prepare_ex); results must agree across c"""
 import json, os, sys
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -21,9 +21,7 @@ for logn in range(lo, hi + 1):
     sc = fr_uniform(rng, 3 * n)
     ref = None; row = {}
     for c in [0] + ([] if os.environ.get("SWEEP_AUTO_ONLY") else list(range(max(8, logn - 3), min(18, logn + 5) + 1))):
-        if c: os.environ["VRFS_MSM_C"] = str(c)
-        else: os.environ.pop("VRFS_MSM_C", None)
-        h = e.msm_g1_prepare(bases)
+        h = e.msm_g1_prepare(bases, window_bits=c)
         best = None
         for _ in range(4):
             e.enable_kernel_timing(True); out = h.msm(sc, 3); kt = e.kernel_timings(); e.enable_kernel_timing(False)
@@ -36,5 +34,4 @@ for logn in range(lo, hi + 1):
         print("2^%d c=%d: %.3f ms" % (logn, c, best[0]), {a: round(b, 2) for a, b in best[1]}, flush=True)
     res[logn] = row
     print("2^%d best:" % logn, min(row, key=row.get), row, flush=True)
-os.environ.pop("VRFS_MSM_C", None)
 json.dump(res, open(os.path.join(ROOT, "gpurun_out", "msm_sweep.json"), "w"), indent=1)
