@@ -20,6 +20,10 @@ SYMBOLS = [
     "vrfs_suite_ietf_signature_len", "vrfs_point_decode_checked_batch", "vrfs_subgroup_check_batch", "vrfs_ietf_sign_wire_batch", "vrfs_ietf_verify_wire_batch",
     "vrfs_suite_pedersen_signature_len", "vrfs_pedersen_sign_wire_batch", "vrfs_pedersen_verify_wire_batch",
     "vrfs_msm_g1_bls12_381", "vrfs_msm_g1_prepare", "vrfs_msm_g1_prepare_ex", "vrfs_msm_g1_prepared", "vrfs_msm_g1_prepared_partial", "vrfs_msm_g1_release", "vrfs_msm_g1_partial", "vrfs_g1_sum_partials", "vrfs_measure_mac32_peak",
+    "vrfs_ctx_debug_read_staging", "vrfs_suite_pedersen_proof_len", "vrfs_pedersen_prove_compressed_batch", "vrfs_pedersen_verify_compressed_batch",
+    "vrfs_ctx_peer_export", "vrfs_ctx_peer_connect", "vrfs_ctx_peer_set_timeout_ms", "vrfs_ctx_peer_world", "vrfs_msm_g1_prepared_allgather", "vrfs_ring_commit_rows_allgather",
+    "vrfs_ctx_create_multi", "vrfs_mctx_destroy", "vrfs_mctx_device_count", "vrfs_mctx_device_ctx", "vrfs_mctx_last_error", "vrfs_mctx_launch_count",
+    "vrfs_multi_ietf_verify_batch", "vrfs_multi_msm_g1_prepare", "vrfs_multi_msm_g1_prepared", "vrfs_multi_ring_commit", "vrfs_multi_msm_g1_release",
     "vrfs_ring_fixed_columns", "vrfs_ring_commit", "vrfs_ring_commit_delta", "vrfs_ring_commit_rows_partial", "vrfs_fr_fft_batch", "vrfs_fq381_inv_batch", "vrfs_g1_compress_batch", "vrfs_g1_decompress_batch",
 ]
 
@@ -42,4 +46,7 @@ def load():
         _lib.vrfs_last_error.restype = C.c_char_p
         _lib.vrfs_ctx_stream.restype = C.c_void_p
         _lib.vrfs_ctx_launch_count.restype = C.c_uint64
+        _lib.vrfs_mctx_launch_count.restype = C.c_uint64
+        _lib.vrfs_mctx_last_error.restype = C.c_char_p
+        _lib.vrfs_mctx_device_ctx.restype = C.c_void_p
     return _lib

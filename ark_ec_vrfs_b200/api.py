@@ -6,7 +6,8 @@ ietf::Prover::prove / ietf::Verifier::verify,  pedersen::Prover::prove / pederse
 and the ring commitment built by RingContext::verifier_key.  Here every type holds a BATCH of n values
 (numpy uint8 arrays in the C ABI's layout) and every method is one call into libvrfs_b200.so; same names,
 same argument meaning, and the reference's error behaviour mapped onto arrays:
-   Result<(), Error>  ->  uint8[n], 1 = Ok(()), 0 = Err(VerificationFailure | InvalidData)
+   Result<(), Error>  ->  uint8[n], 1 = Ok(()), 0 = Err(_); with status=True also the variant per item
+                          (ITEM_OK / ITEM_VERIFICATION_FAILURE / ITEM_INVALID_DATA = Ok / Error::VerificationFailure / Error::InvalidData)
    Option<Input>      ->  (Input, uint8[n] ok)
 There is no CPU implementation behind these classes: constructing a Suite needs a CUDA device."""
 from dataclasses import dataclass
@@ -59,9 +60,9 @@ class Public:
     suite: Suite
     points: np.ndarray          # (n, 64)
 
-    def verify(self, input, output, ad, proof):
-        """ietf::Verifier::verify -> uint8[n]"""
-        return self.suite.engine.ietf_verify(self.suite.suite_id, self.points, input.points, output.points, proof.c, proof.s, ad)
+    def verify(self, input, output, ad, proof, status=False):
+        """ietf::Verifier::verify -> uint8[n] (status=True: (ok, Error variant per item))"""
+        return self.suite.engine.ietf_verify(self.suite.suite_id, self.points, input.points, output.points, proof.c, proof.s, ad, status=status)
 
     def encode(self):
         return self.suite.engine.point_encode(self.suite.suite_id, self.points)
@@ -75,10 +76,10 @@ class Public:
         return cls(suite, pts), ok
 
     @staticmethod
-    def verify_signatures(suite, pk_enc, datas, signatures, ad=None):
-        """serialised keys + VRF input data + serialised signatures (Output || ietf::Proof) -> (ok flags, Output::hash);
+    def verify_signatures(suite, pk_enc, datas, signatures, ad=None, status=False):
+        """serialised keys + VRF input data + serialised signatures (Output || ietf::Proof) -> (ok flags, Output::hash[, status]);
         one call: deserialise, Input::new, verify, hash"""
-        return suite.engine.ietf_verify_wire(suite.suite_id, pk_enc, datas, signatures, ad)
+        return suite.engine.ietf_verify_wire(suite.suite_id, pk_enc, datas, signatures, ad, status=status)
 
 
 @dataclass
@@ -196,20 +197,26 @@ class Secret:
         """Input::new(data) -> output -> pedersen prove -> serialised Output || pedersen::Proof; returns (sig, blinding, ok)"""
         return self.suite.engine.pedersen_sign_wire(self.suite.suite_id, self.scalars, datas, ad)
 
-    def pedersen_prove(self, input, output, ad=None):
-        """pedersen::Prover::prove -> (Proof, blinding)"""
+    def pedersen_prove(self, input, output, ad=None, serialized=False):
+        """pedersen::Prover::prove -> (Proof, blinding); serialized=True returns the proofs' CanonicalSerialize bytes instead
+        (3 encoded points + s + sb, 160 B each for Bandersnatch)"""
+        if serialized:
+            return self.suite.engine.pedersen_prove_compressed(self.suite.suite_id, self.scalars, input.points, output.points, ad)
         pr, bl = self.suite.engine.pedersen_prove(self.suite.suite_id, self.scalars, input.points, output.points, ad)
         return PedersenProof(pr), bl
 
 
-def pedersen_verify(suite, input, output, ad, proof):
-    """pedersen::Verifier::verify (needs no public key) -> uint8[n]"""
-    return suite.engine.pedersen_verify(suite.suite_id, input.points, output.points, proof.raw, ad)
+def pedersen_verify(suite, input, output, ad, proof, status=False):
+    """pedersen::Verifier::verify (needs no public key) -> uint8[n].  `proof`: a PedersenProof, or the serialised proofs
+    ((n, proof_len) bytes, 160 B each for Bandersnatch) which are deserialised with validation on the GPU first"""
+    if isinstance(proof, PedersenProof):
+        return suite.engine.pedersen_verify(suite.suite_id, input.points, output.points, proof.raw, ad, status=status)
+    return suite.engine.pedersen_verify_compressed(suite.suite_id, input.points, output.points, proof, ad, status=status)
 
 
-def pedersen_verify_signatures(suite, datas, signatures, ad=None):
+def pedersen_verify_signatures(suite, datas, signatures, ad=None, status=False):
     """serialised Output || pedersen::Proof + VRF input data -> ok flags (deserialise with validation, Input::new, verify)"""
-    return suite.engine.pedersen_verify_wire(suite.suite_id, datas, signatures, ad)
+    return suite.engine.pedersen_verify_wire(suite.suite_id, datas, signatures, ad, status=status)
 
 
 def ring_commitment_msm(suite_or_engine, bases, scalar_columns):

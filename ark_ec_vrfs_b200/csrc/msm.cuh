@@ -728,14 +728,85 @@ __global__ void __cluster_dims__(MSM_WSUM_CLUSTER, 1, 1) __launch_bounds__(128) 
   }
 }
 
-// one warp per column: segment value = sum of its parts, Horner over the windows (stateless mode), output as in k_msm_final
-__global__ void __launch_bounds__(32) k_msm_final2(MsmPlan p, int nparts, const G1Pt* parts, uint8_t* out, int out_mode) {
+// ---- multi-GPU exchange of the per-rank partial sums ("MSM splits by point range, with only a tiny NCCL/NVLink
+// reduction of partial bucket sums").  Every rank owns a MAILBOX in its device memory that the other ranks of the node have mapped
+// (in-process: peer access; across processes: CUDA IPC).  The final kernel of a rank's MSM stores its projective partial straight
+// into the peers' mailboxes over NVLink, raises a flag behind a system-scope fence, then - on the ranks that fold - waits for the
+// flags of all ranks in ITS OWN memory, adds the partials and normalises: the collective is part of the kernel that produced the
+// data, no NCCL call, no host hop (an all-gather of 144 B per column per rank).
+// Slots are double-buffered by call parity: a rank can only be one collective ahead of the slowest one (it needs that rank's
+// partial to finish), so parity e and e+2 never overlap.
+#define VRFS_MAX_PEERS 16
+#define VRFS_PEER_MAXCOL 32
+struct PeerBox {                                           // layout of one rank's mailbox
+  uint32_t slot[2][VRFS_MAX_PEERS][VRFS_PEER_MAXCOL][36];  // [parity][sender][column] X, Y, Z (Montgomery limbs, identical on every GPU)
+  unsigned long long flag[2][VRFS_MAX_PEERS][VRFS_PEER_MAXCOL];   // epoch of the last partial stored there
+};
+struct PeerArgs {
+  int rank, world, root;           // root < 0: every rank folds (all-gather); else only `root` does (gather)
+  unsigned long long epoch;        // this collective's number (> 0, the same on every rank)
+  unsigned long long timeout_ns;   // a rank that waits longer gives up (status word), so a lost peer cannot hang the GPU
+  PeerBox* box[VRFS_MAX_PEERS];    // every rank's mailbox as mapped here (box[rank] = this GPU's own)
+  unsigned int* timed_out;         // mapped pinned host word, set to 1 on a timeout
+};
+__device__ __forceinline__ unsigned long long peer_globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ unsigned long long peer_ld_acquire(const unsigned long long* p) {
+  unsigned long long v; asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void peer_st_release(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// one warp per column: segment value = sum of its parts, Horner over the windows (stateless mode).
+// out_mode 0: affine canonical bytes (96 B); 1: projective canonical bytes (144 B, the host-gathered multi-GPU form);
+//          2: publish the partial to the peers' mailboxes and (on folding ranks) fold all ranks' partials -> affine bytes (96 B)
+__global__ void __launch_bounds__(32) k_msm_final2(MsmPlan p, int nparts, const G1Pt* parts, uint8_t* out, int out_mode, PeerArgs peer) {
   const uint32_t col = blockIdx.x;
   const G1Pt* W = parts + (size_t)col * p.seg_windows * nparts;
   G1Pt acc; sw_set_identity(acc);
   for (int w = p.seg_windows - 1; w >= 0; w--) {
     if (w != p.seg_windows - 1) for (int k = 0; k < p.c; k++) g1_coop_dbl(&acc, &acc);
     for (int j = 0; j < nparts; j++) { G1Pt q; copy_words16(&q, &W[(size_t)w * nparts + j]); g1_coop_add(&acc, &acc, &q); }
+  }
+  if (out_mode == 2) {
+    const unsigned lane = threadIdx.x;
+    const int par = (int)(peer.epoch & 1ull);
+    // publish: lane r < world (or lane 0 -> root) stores the 36 words + the flag into rank r's mailbox
+    const bool sends = peer.root < 0 ? (int)lane < peer.world : lane == 0;
+    if (sends) {
+      const int dst = peer.root < 0 ? (int)lane : peer.root;
+      uint32_t* s = peer.box[dst]->slot[par][peer.rank][col];
+      uint4* d4 = reinterpret_cast<uint4*>(s);
+      const uint4 *sx = reinterpret_cast<const uint4*>(acc.X.v), *sy = reinterpret_cast<const uint4*>(acc.Y.v), *sz = reinterpret_cast<const uint4*>(acc.Z.v);
+      for (int i = 0; i < 3; i++) { d4[i] = sx[i]; d4[3 + i] = sy[i]; d4[6 + i] = sz[i]; }
+      __threadfence_system();
+      peer_st_release(&peer.box[dst]->flag[par][peer.rank][col], peer.epoch);
+    }
+    if (peer.root >= 0 && peer.root != peer.rank) return;
+    // fold: wait for every rank's flag in this GPU's own mailbox, then add (sender order is fixed, so every rank adds in the same order)
+    PeerBox* mine = peer.box[peer.rank];
+    bool late = false;
+    if ((int)lane < peer.world) {
+      const unsigned long long t0 = peer_globaltimer();
+      unsigned spins = 0;
+      while (peer_ld_acquire(&mine->flag[par][lane][col]) != peer.epoch) {
+        if ((++spins & 1023u) == 0 && peer_globaltimer() - t0 > peer.timeout_ns) { late = true; break; }
+      }
+    }
+    late = __any_sync(0xffffffffu, late);
+    if (late) {                                            // give up loudly: zeros out, host sees the status word
+      if (lane == 0) { *peer.timed_out = 1u; __threadfence_system(); for (int i = 0; i < 96; i++) out[(size_t)96 * col + i] = 0; }
+      return;
+    }
+    G1Pt sum; sw_set_identity(sum);
+    for (int r = 0; r < peer.world; r++) {
+      G1Pt q;
+      const uint4* s4 = reinterpret_cast<const uint4*>(mine->slot[par][r][col]);
+      uint4 *qx = reinterpret_cast<uint4*>(q.X.v), *qy = reinterpret_cast<uint4*>(q.Y.v), *qz = reinterpret_cast<uint4*>(q.Z.v);
+      for (int i = 0; i < 3; i++) { qx[i] = __ldcv(s4 + i); qy[i] = __ldcv(s4 + 3 + i); qz[i] = __ldcv(s4 + 6 + i); }   // written by another GPU: never from L1
+      g1_coop_add(&sum, &sum, &q);
+    }
+    acc = sum;
   }
   if (threadIdx.x != 0) return;
   uint32_t raw[12];

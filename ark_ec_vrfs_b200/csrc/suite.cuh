@@ -7,6 +7,9 @@
 
 namespace vrfs {
 
+// per-item Result<(), Error> of the verifiers (include/vrfs_b200.h: vrfs_item_status)
+enum { ITEM_OK = 0, ITEM_VERIFICATION_FAILURE = 1, ITEM_INVALID_DATA = 2 };
+
 struct BandSuite {
   typedef BandCurve C;
   typedef Sha512 H;
@@ -202,7 +205,7 @@ HD_INLINE bool ietf_verify_finish_item(const uint8_t* pk, const uint8_t* input, 
 template <class S, int K>
 HD_INLINE void ietf_verify_finish_batched(uint32_t n, uint32_t first, uint32_t stride, const uint8_t* pk, const uint8_t* input, const uint8_t* output,
                                           const uint8_t* c, const uint32_t* u_xyz, const uint32_t* v_xyz, const uint8_t* ad, const uint64_t* ad_off,
-                                          const uint8_t* valid, uint8_t* out_ok) {
+                                          const uint8_t* valid, uint8_t* out_ok, uint8_t* out_status = nullptr) {
   typedef typename S::C C;
   typedef typename C::F F;
   F z[K], pre[K];
@@ -228,7 +231,13 @@ HD_INLINE void ietf_verify_finish_batched(uint32_t n, uint32_t first, uint32_t s
                                               u_xyz + (size_t)24 * i, v_xyz + (size_t)24 * i, zinv, a, alen);
     // TE with Z = 0 cannot happen for on-curve inputs; guard anyway so a forged zero never verifies
     F t = zz_product<C>(u_xyz + (size_t)24 * i, v_xyz + (size_t)24 * i);
-    out_ok[i] = (uint8_t)(ok && valid[i] && !t.is_zero());
+    const bool good = ok && valid[i] && !t.is_zero();
+    out_ok[i] = (uint8_t)good;
+    if (out_status) {     // Result<(), Error>: values no typed Public / Input / Output can hold are InvalidData, the rest VerificationFailure
+      bool bad_input = !valid[i];
+      if (!C::IS_TE) bad_input |= bytes_all_zero(pk + (size_t)64 * i, 64) || bytes_all_zero(input + (size_t)64 * i, 64) || bytes_all_zero(output + (size_t)64 * i, 64);
+      out_status[i] = (uint8_t)(good ? ITEM_OK : bad_input ? ITEM_INVALID_DATA : ITEM_VERIFICATION_FAILURE);
+    }
   }
 }
 
@@ -385,8 +394,9 @@ template <class S> HD_INLINE bool pedersen_verify_prep_item(uint8_t* out_c, cons
   store_le<8>(out_c, c);
   return ok;
 }
-// is the projective point (X,Y,Z) equal to the affine point given as ABI bytes?  (also validates the affine point)
-template <class C> HD_INLINE bool proj_equals_affine_bytes(const uint32_t* xyz, const uint8_t* aff) {
+// is the projective point (X,Y,Z) equal to the affine point given as ABI bytes?  Also validates the affine point:
+// 0 = the bytes are no curve point (non-canonical / off the curve), 1 = a curve point different from (X:Y:Z), 2 = equal
+template <class C> HD_INLINE int proj_vs_affine_bytes(const uint32_t* xyz, const uint8_t* aff) {
   typedef typename C::F F;
   uint32_t rx[8], ry[8];
   load_le<8>(rx, aff); load_le<8>(ry, aff + 32);
@@ -394,7 +404,8 @@ template <class C> HD_INLINE bool proj_equals_affine_bytes(const uint32_t* xyz, 
   F x = to_mont<typename C::Fq>(rx), y = to_mont<typename C::Fq>(ry), X, Y, Z;
   ok &= Grp<C>::on_curve(x, y);
   for (int i = 0; i < 8; i++) { X.v[i] = xyz[i]; Y.v[i] = xyz[8 + i]; Z.v[i] = xyz[16 + i]; }
-  return ok & !Z.is_zero() & (x * Z == X) & (y * Z == Y);
+  if (!ok) return 0;
+  return (!Z.is_zero() & (x * Z == X) & (y * Z == Y)) ? 2 : 1;
 }
 
 }  // namespace vrfs

@@ -7,6 +7,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <algorithm>
+#include <memory>
 #include <mutex>
 #include <new>
 #include <vector>
@@ -69,10 +70,10 @@ __global__ void __launch_bounds__(LINCOMB_THREADS, LINCOMB_MINBLOCKS) k_lincomb(
 template <class S>
 __global__ void __launch_bounds__(128) k_ietf_verify_finish(uint32_t n, const uint8_t* pk, const uint8_t* input, const uint8_t* output,
                                                              const uint8_t* c, const uint32_t* u_xyz, const uint32_t* v_xyz,
-                                                             const uint8_t* ad, const uint64_t* ad_off, const uint8_t* valid, uint8_t* out_ok) {
+                                                             const uint8_t* ad, const uint64_t* ad_off, const uint8_t* valid, uint8_t* out_ok, uint8_t* out_status) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
   if (t >= n) return;
-  ietf_verify_finish_batched<S, FINISH_K>(n, t, stride, pk, input, output, c, u_xyz, v_xyz, ad, ad_off, valid, out_ok);
+  ietf_verify_finish_batched<S, FINISH_K>(n, t, stride, pk, input, output, c, u_xyz, v_xyz, ad, ad_off, valid, out_ok, out_status);
 }
 
 // integer-pipe roofline microbenchmarks: independent multiply-accumulate chains per thread
@@ -189,9 +190,10 @@ __global__ void __launch_bounds__(256) k_mac_bench(uint32_t* out, int iters, uns
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
+  size_t secret_bytes = 0;   // > 0: the running call put key material here (sk, nonces, blinding factors); zeroed before it returns
 };
 enum { BUF_IN0, BUF_IN1, BUF_IN2, BUF_IN3, BUF_IN4, BUF_AD, BUF_OFF, BUF_OUT0, BUF_OUT1, BUF_W0, BUF_W1, BUF_W2, BUF_W3, BUF_VALID, BUF_SLAB,
-       BUF_X0, BUF_X1, BUF_X2, BUF_X3, BUF_X4, BUF_ZINV, BUF_SLAB2, BUF_COUNT };   // X*: wire-format staging (encoded keys, signatures, h2c data, flags)
+       BUF_X0, BUF_X1, BUF_X2, BUF_X3, BUF_X4, BUF_X5, BUF_ZINV, BUF_SLAB2, BUF_COUNT };   // X*: wire-format staging (encoded keys, signatures, h2c data, flags)
 
 #define MAX_TIMED 64
 struct vrfs_ctx {
@@ -207,15 +209,48 @@ struct vrfs_ctx {
   char err[512] = {0};
   std::recursive_mutex mu;            // entry points serialise per context ("internally synchronised")
   uint64_t launches = 0;
+  int depth = 0;                      // nesting of entry points on this context (a host-buffer call runs its *_dev form inside)
+  bool failed = false;                // the running call hit an error: both streams are drained before it returns
   DevBuf buf[BUF_COUNT];
   void* fixtab[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};   // [suite][G | blinding base]
   std::vector<struct vrfs_msm_bases*> prepared;   // live prepared-base handles (freed / orphaned by vrfs_ctx_destroy)
+  // peer group of the multi-GPU MSM exchange (csrc/msm.cuh "multi-GPU exchange"): world = 0 until connected
+  struct {
+    int rank = 0, world = 0;
+    unsigned long long epoch = 0;
+    PeerBox* box[VRFS_MAX_PEERS] = {nullptr};      // box[rank] = this GPU's own mailbox (cudaMalloc); the others mapped
+    bool ipc[VRFS_MAX_PEERS] = {false};            // mapped through cudaIpcOpenMemHandle (to be closed), not a same-process pointer
+    unsigned int* timed_out = nullptr;             // mapped pinned host word written by a kernel that gave up waiting
+    unsigned long long timeout_ns = 2000000000ull;
+  } peer;
 };
 
 static vrfs_status fail(vrfs_ctx* c, vrfs_status st, const char* fmt, ...) {
-  if (c) { va_list ap; va_start(ap, fmt); vsnprintf(c->err, sizeof c->err, fmt, ap); va_end(ap); }
+  if (c) { va_list ap; va_start(ap, fmt); vsnprintf(c->err, sizeof c->err, fmt, ap); va_end(ap); c->failed = true; }
   return st;
 }
+// Every entry point holds one of these: the per-context lock plus the end-of-call hygiene of the OUTERMOST call -
+//  * device buffers that held key material (DevBuf::secret_bytes) are zeroed and the stream drained ("staging buffers
+//    holding sk are zeroed before release"; the buffers are pooled, so "release" is the end of the call);
+//  * after a failure both streams are drained, so that no copy is still reading the caller's host buffers when the error
+//    code reaches the caller.
+struct CallGuard {
+  vrfs_ctx* ctx;
+  explicit CallGuard(vrfs_ctx* c) : ctx(c) { ctx->mu.lock(); if (ctx->depth++ == 0) ctx->failed = false; }
+  ~CallGuard() {
+    if (--ctx->depth == 0) {
+      bool wiped = false;
+      for (int i = 0; i < BUF_COUNT; i++) {
+        DevBuf& b = ctx->buf[i];
+        if (b.secret_bytes && b.p) { cudaMemsetAsync(b.p, 0, b.secret_bytes < b.cap ? b.secret_bytes : b.cap, ctx->stream); wiped = true; }
+        b.secret_bytes = 0;
+      }
+      if (ctx->failed && ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+      if ((wiped || ctx->failed) && ctx->stream) cudaStreamSynchronize(ctx->stream);
+    }
+    ctx->mu.unlock();
+  }
+};
 #define CU(call)                                                                                                   \
   do {                                                                                                             \
     cudaError_t e_ = (call);                                                                                       \
@@ -233,6 +268,7 @@ static vrfs_status fail(vrfs_ctx* c, vrfs_status st, const char* fmt, ...) {
 static vrfs_status note_kernel(vrfs_ctx* ctx, const char* name);
 static vrfs_status timing_begin(vrfs_ctx* ctx);
 static void orphan_prepared(vrfs_ctx* ctx);
+static void peer_teardown(vrfs_ctx* ctx);
 
 static vrfs_status timing_begin(vrfs_ctx* ctx) {
   ctx->n_timed = 0;
@@ -250,7 +286,7 @@ static vrfs_status note_kernel(vrfs_ctx* ctx, const char* name) {
 }
 extern "C" vrfs_status vrfs_ctx_enable_kernel_timing(vrfs_ctx* ctx, int on) {
   if (!ctx) return VRFS_BAD_ARG;
-  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
+  CallGuard guard_(ctx);
   ctx->timing = on != 0;
   ctx->n_timed = 0;
   return VRFS_OK;
@@ -258,7 +294,7 @@ extern "C" vrfs_status vrfs_ctx_enable_kernel_timing(vrfs_ctx* ctx, int on) {
 // device time of every kernel of the most recent *_batch / *_batch_dev call (after a sync); returns the count
 extern "C" int vrfs_ctx_kernel_timings(vrfs_ctx* ctx, const char** names, float* ms, int cap) {
   if (!ctx || !ctx->timing) return 0;
-  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
+  CallGuard guard_(ctx);
   if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return 0;
   int n = ctx->n_timed < cap ? ctx->n_timed : cap;
   for (int i = 0; i < n; i++) {
@@ -272,7 +308,10 @@ static vrfs_status ensure(vrfs_ctx* ctx, int which, size_t bytes, void** out) {
   DevBuf& b = ctx->buf[which];
   if (bytes == 0) bytes = 16;
   if (b.cap < bytes) {
-    if (b.p) { CU(cudaStreamSynchronize(ctx->stream)); CU(cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
+    if (b.p) {
+      if (b.secret_bytes) CU(cudaMemsetAsync(b.p, 0, b.secret_bytes < b.cap ? b.secret_bytes : b.cap, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream)); CU(cudaFree(b.p)); b.p = nullptr; b.cap = 0;
+    }
     size_t cap = bytes + bytes / 8 + 256;
     CU(cudaMalloc(&b.p, cap));
     b.cap = cap;
@@ -282,18 +321,30 @@ static vrfs_status ensure(vrfs_ctx* ctx, int which, size_t bytes, void** out) {
 }
 static inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
 
-template <class C>
-static vrfs_status build_fixed_tables(vrfs_ctx* ctx, int suite) {
+// Fixed-base tables (G and the Pedersen blinding base B) are built the first time a suite needs them: 2 x 50 MB and ~30 ms of
+// k_fixed_table per suite that a caller of one suite should not pay three times at context creation.
+template <class S>
+static vrfs_status need_tables(vrfs_ctx* ctx) {
+  typedef typename S::C C;
+  if (ctx->fixtab[S::ID][1]) return VRFS_OK;
   const int n = (int)fix_table_entries<C>();
   for (int b = 0; b < 2; b++) {
-    CU(cudaMalloc(&ctx->fixtab[suite][b], sizeof(typename Grp<C>::FixEntry) * n));
-    k_fixed_table<C><<<(n + 63) / 64, 64, 0, ctx->stream>>>(reinterpret_cast<typename Grp<C>::FixEntry*>(ctx->fixtab[suite][b]), b);
-    LAUNCHED(ctx);
+    if (ctx->fixtab[S::ID][b]) continue;
+    void* t = nullptr;
+    CU(cudaMalloc(&t, sizeof(typename Grp<C>::FixEntry) * n));
+    k_fixed_table<C><<<(n + 63) / 64, 64, 0, ctx->stream>>>(reinterpret_cast<typename Grp<C>::FixEntry*>(t), b);
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { cudaFree(t); return fail(ctx, VRFS_CUDA_ERROR, "k_fixed_table launch failed: %s", cudaGetErrorString(e)); }
+    ST(note_kernel(ctx, "fixed_table"));
+    ctx->fixtab[S::ID][b] = t;
   }
   return VRFS_OK;
 }
 
-extern "C" int vrfs_abi_version(void) { return 1; }
+static_assert((int)ITEM_OK == (int)VRFS_ITEM_OK && (int)ITEM_VERIFICATION_FAILURE == (int)VRFS_ITEM_VERIFICATION_FAILURE &&
+              (int)ITEM_INVALID_DATA == (int)VRFS_ITEM_INVALID_DATA, "device-side status codes must match include/vrfs_b200.h");
+extern "C" int vrfs_abi_version(void) { return 2; }
 
 extern "C" vrfs_status vrfs_ctx_create(int device, vrfs_ctx** out) {
   if (!out) return VRFS_BAD_ARG;
@@ -312,17 +363,14 @@ extern "C" vrfs_status vrfs_ctx_create(int device, vrfs_ctx** out) {
   for (int i = 0; i < 4; i++) CU(cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming));
   CU(cudaEventCreate(&ctx->ev0));
   CU(cudaEventCreate(&ctx->ev1));
-  ST(build_fixed_tables<BandCurve>(ctx, VRFS_BANDERSNATCH_ELL2));
-  ST(build_fixed_tables<EdCurve>(ctx, VRFS_ED25519_TAI));
-  ST(build_fixed_tables<P256Curve>(ctx, VRFS_P256_TAI));
-  CU(cudaStreamSynchronize(ctx->stream));
-  return VRFS_OK;
+  return VRFS_OK;                      // fixed-base tables: built on first use per suite (need_tables)
 }
 extern "C" void vrfs_ctx_destroy(vrfs_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   orphan_prepared(ctx);
+  peer_teardown(ctx);
   for (int i = 0; i < BUF_COUNT; i++) if (ctx->buf[i].p) cudaFree(ctx->buf[i].p);
   for (int s = 0; s < 3; s++) for (int b = 0; b < 2; b++) if (ctx->fixtab[s][b]) cudaFree(ctx->fixtab[s][b]);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -334,8 +382,21 @@ extern "C" void vrfs_ctx_destroy(vrfs_ctx* ctx) {
 }
 extern "C" vrfs_status vrfs_ctx_sync(vrfs_ctx* ctx) {
   if (!ctx) return VRFS_BAD_ARG;
-  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
+  CallGuard guard_(ctx);
   CU(cudaStreamSynchronize(ctx->stream));
+  return VRFS_OK;
+}
+// test hook: bytes of an internal staging buffer (slot = position in the buffer pool; 0..4 are the input staging buffers in call
+// order, e.g. slot 0 holds `sk` during a prove call).  tests/ use it to check that key material is gone after a call returned.
+extern "C" vrfs_status vrfs_ctx_debug_read_staging(vrfs_ctx* ctx, int slot, size_t offset, uint8_t* out, size_t n) {
+  if (!ctx || !out) return VRFS_BAD_ARG;
+  CallGuard guard_(ctx);
+  if (slot < 0 || slot >= BUF_COUNT) return fail(ctx, VRFS_BAD_ARG, "no such staging buffer");
+  const DevBuf& b = ctx->buf[slot];
+  if (!b.p || offset + n > b.cap) return fail(ctx, VRFS_BAD_ARG, "range outside the staging buffer (capacity %zu)", b.cap);
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaMemcpy(out, (const uint8_t*)b.p + offset, n, cudaMemcpyDeviceToHost));
   return VRFS_OK;
 }
 extern "C" const char* vrfs_last_error(const vrfs_ctx* ctx) { return ctx ? ctx->err : "null context"; }
@@ -375,9 +436,10 @@ static vrfs_status launch_lincomb(vrfs_ctx* ctx, LincombArgs A, bool side = fals
 // =================================================================================================
 template <class S>
 static vrfs_status ietf_verify_dev(vrfs_ctx* ctx, size_t n, const uint8_t* pk, const uint8_t* input, const uint8_t* output, const uint8_t* c,
-                                   const uint8_t* s, const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_ok) {
+                                   const uint8_t* s, const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_ok, uint8_t* out_status = nullptr) {
   typedef typename S::C C;
   void *u = nullptr, *v = nullptr, *valid = nullptr;
+  ST(need_tables<S>(ctx));
   ST(ensure(ctx, BUF_W0, n * 96, &u));
   ST(ensure(ctx, BUF_W1, n * 96, &v));
   ST(ensure(ctx, BUF_VALID, n, &valid));
@@ -409,16 +471,16 @@ static vrfs_status ietf_verify_dev(vrfs_ctx* ctx, size_t n, const uint8_t* pk, c
     CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[3], 0));
   }
   k_ietf_verify_finish<S><<<(unsigned)((n + 128 * FINISH_K - 1) / (128 * FINISH_K)), 128, 0, ctx->stream>>>((uint32_t)n, pk, input, output, c, (const uint32_t*)u,
-                                                                                (const uint32_t*)v, ad, ad_off, (const uint8_t*)valid, out_ok);
+                                                                                (const uint32_t*)v, ad, ad_off, (const uint8_t*)valid, out_ok, out_status);
   LAUNCHED_AS(ctx, "ietf_verify_finish");
   return VRFS_OK;
 }
 
 extern "C" vrfs_status vrfs_ietf_verify_batch_dev(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* pk, const uint8_t* input,
                                                   const uint8_t* output, const uint8_t* c, const uint8_t* s, const uint8_t* ad,
-                                                  const uint64_t* ad_off, uint8_t* out_ok) {
+                                                  const uint64_t* ad_off, uint8_t* out_ok, uint8_t* out_status) {
   if (!ctx) return VRFS_BAD_ARG;
-  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
+  CallGuard guard_(ctx);
   if (n == 0) return VRFS_OK;
   if (!pk || !input || !output || !c || !s || !out_ok || (ad && !ad_off)) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if (n > 0x7fffffffu) return fail(ctx, VRFS_BAD_ARG, "batch too large (n < 2^31)");
@@ -426,9 +488,9 @@ extern "C" vrfs_status vrfs_ietf_verify_batch_dev(vrfs_ctx* ctx, vrfs_suite suit
   CU(cudaSetDevice(ctx->device));
   ST(timing_begin(ctx));
   switch (suite) {
-    case VRFS_BANDERSNATCH_ELL2: return ietf_verify_dev<BandSuite>(ctx, n, pk, input, output, c, s, ad, ad_off, out_ok);
-    case VRFS_ED25519_TAI: return ietf_verify_dev<EdSuite>(ctx, n, pk, input, output, c, s, ad, ad_off, out_ok);
-    case VRFS_P256_TAI: return ietf_verify_dev<P256Suite>(ctx, n, pk, input, output, c, s, ad, ad_off, out_ok);
+    case VRFS_BANDERSNATCH_ELL2: return ietf_verify_dev<BandSuite>(ctx, n, pk, input, output, c, s, ad, ad_off, out_ok, out_status);
+    case VRFS_ED25519_TAI: return ietf_verify_dev<EdSuite>(ctx, n, pk, input, output, c, s, ad, ad_off, out_ok, out_status);
+    case VRFS_P256_TAI: return ietf_verify_dev<P256Suite>(ctx, n, pk, input, output, c, s, ad, ad_off, out_ok, out_status);
     default: return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
   }
 }
@@ -447,31 +509,44 @@ static vrfs_status stage_ad(vrfs_ctx* ctx, size_t n, const uint8_t* ad, const ui
   *d_ad = nullptr; *d_off = nullptr;
   if (!ad_off) return VRFS_OK;
   for (size_t i = 0; i < n; i++) if (ad_off[i + 1] < ad_off[i]) return fail(ctx, VRFS_BAD_ARG, "offsets must be non-decreasing");
-  if (ad_off[n] > 0 && !ad) return fail(ctx, VRFS_BAD_ARG, "null data buffer with non-empty offsets");
-  const uint8_t* o = nullptr;
-  ST(stage_in(ctx, BUF_AD, ad, (size_t)ad_off[n], d_ad));
+  if (ad_off[n] > ad_off[0] && !ad) return fail(ctx, VRFS_BAD_ARG, "null data buffer with non-empty offsets");
+  // only the bytes these n items refer to travel (a shard of a larger batch passes ad_off + lo: absolute offsets into `ad`);
+  // the device pointer is biased so that the kernels keep indexing with the absolute offsets
+  const uint8_t *o = nullptr, *base = nullptr;
+  ST(stage_in(ctx, BUF_AD, ad ? ad + ad_off[0] : nullptr, (size_t)(ad_off[n] - ad_off[0]), &base));
+  *d_ad = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(base) - (uintptr_t)ad_off[0]);
   ST(stage_in(ctx, BUF_OFF, ad_off, (n + 1) * sizeof(uint64_t), &o));
   *d_off = (const uint64_t*)o;
   return VRFS_OK;
 }
+// variable-length items (h2c data): validated offsets + bytes -> device
+static vrfs_status stage_var(vrfs_ctx* ctx, int buf_data, int buf_off, size_t n, const uint8_t* data, const uint64_t* off, const uint8_t** d_data, const uint64_t** d_off) {
+  for (size_t i = 0; i < n; i++) if (off[i + 1] < off[i]) return fail(ctx, VRFS_BAD_ARG, "offsets must be non-decreasing");
+  if (off[n] > 0 && !data) return fail(ctx, VRFS_BAD_ARG, "null data buffer with non-empty offsets");
+  const uint8_t* o = nullptr;
+  ST(stage_in(ctx, buf_data, data, (size_t)off[n], d_data));
+  ST(stage_in(ctx, buf_off, off, (n + 1) * sizeof(uint64_t), &o));
+  *d_off = (const uint64_t*)o;
+  return VRFS_OK;
+}
 
-extern "C" vrfs_status vrfs_ietf_verify_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* pk, const uint8_t* input,
-                                              const uint8_t* output, const uint8_t* c, const uint8_t* s, const uint8_t* ad,
-                                              const uint64_t* ad_off, uint8_t* out_ok) {
-  if (!ctx) return VRFS_BAD_ARG;
-  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
-  if (n == 0) return VRFS_OK;
+// Host buffers, everything enqueued and nothing waited for (the multi-device context enqueues one of these per GPU before it
+// waits for any): the batch is cut into a first piece of one resident wave of the lincomb grid and the remainder, the H2D copies
+// run on their own stream, and the kernels of piece k wait only for piece k's copies - so all but the first ~20 MB of the
+// 256 B/item input transfer hides behind arithmetic (pinned host memory; pageable memory still works, the copies then
+// serialise inside the driver).
+static vrfs_status ietf_verify_host_enqueue(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* pk, const uint8_t* input, const uint8_t* output,
+                                            const uint8_t* c, const uint8_t* s, const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_ok, uint8_t* out_status) {
   if (!pk || !input || !output || !c || !s || !out_ok) return fail(ctx, VRFS_BAD_ARG, "null buffer");
+  if (n > 0x7fffffffu) return fail(ctx, VRFS_BAD_ARG, "batch too large (n < 2^31)");
+  if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
   CU(cudaSetDevice(ctx->device));
-  // Host buffers: the batch is cut into a first piece of one resident wave of the lincomb grid and the remainder, the
-  // H2D copies run on their own stream, and the kernels of piece k wait only for piece k's copies - so all but the
-  // first ~20 MB of the 256 B/item input transfer hides behind arithmetic (pinned host memory; pageable memory still
-  // works, the copies then serialise inside the driver).
   const uint8_t* d_ad;
   const uint64_t* d_off;
-  void *d_pk = nullptr, *d_in = nullptr, *d_out = nullptr, *d_c = nullptr, *d_s = nullptr, *d_ok = nullptr;
+  void *d_pk = nullptr, *d_in = nullptr, *d_out = nullptr, *d_c = nullptr, *d_s = nullptr, *d_ok = nullptr, *d_st = nullptr;
   ST(ensure(ctx, BUF_IN0, n * 64, &d_pk)); ST(ensure(ctx, BUF_IN1, n * 64, &d_in)); ST(ensure(ctx, BUF_IN2, n * 64, &d_out));
   ST(ensure(ctx, BUF_IN3, n * 32, &d_c)); ST(ensure(ctx, BUF_IN4, n * 32, &d_s)); ST(ensure(ctx, BUF_OUT0, n, &d_ok));
+  if (out_status) ST(ensure(ctx, BUF_OUT1, n, &d_st));
   ST(stage_ad(ctx, n, ad, ad_off, &d_ad, &d_off));
   const size_t wave = (size_t)ctx->sms * LINCOMB_MINBLOCKS * LINCOMB_THREADS;
   size_t cut[3] = {0, n > 3 * wave ? wave : n, n};
@@ -489,9 +564,20 @@ extern "C" vrfs_status vrfs_ietf_verify_batch(vrfs_ctx* ctx, vrfs_suite suite, s
     const size_t o = cut[k], m = cut[k + 1] - cut[k];
     CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[k], 0));
     ST(vrfs_ietf_verify_batch_dev(ctx, suite, m, (const uint8_t*)d_pk + o * 64, (const uint8_t*)d_in + o * 64, (const uint8_t*)d_out + o * 64,
-                                  (const uint8_t*)d_c + o * 32, (const uint8_t*)d_s + o * 32, d_ad, d_off ? d_off + o : nullptr, (uint8_t*)d_ok + o));
+                                  (const uint8_t*)d_c + o * 32, (const uint8_t*)d_s + o * 32, d_ad, d_off ? d_off + o : nullptr, (uint8_t*)d_ok + o,
+                                  d_st ? (uint8_t*)d_st + o : nullptr));
   }
   CU(cudaMemcpyAsync(out_ok, d_ok, n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (out_status) CU(cudaMemcpyAsync(out_status, d_st, n, cudaMemcpyDeviceToHost, ctx->stream));
+  return VRFS_OK;
+}
+extern "C" vrfs_status vrfs_ietf_verify_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* pk, const uint8_t* input,
+                                              const uint8_t* output, const uint8_t* c, const uint8_t* s, const uint8_t* ad,
+                                              const uint64_t* ad_off, uint8_t* out_ok, uint8_t* out_status) {
+  if (!ctx) return VRFS_BAD_ARG;
+  CallGuard guard_(ctx);
+  if (n == 0) return VRFS_OK;
+  ST(ietf_verify_host_enqueue(ctx, suite, n, pk, input, output, c, s, ad, ad_off, out_ok, out_status));
   CU(cudaStreamSynchronize(ctx->stream));
   return VRFS_OK;
 }
@@ -501,7 +587,7 @@ extern "C" vrfs_status vrfs_ietf_verify_batch(vrfs_ctx* ctx, vrfs_suite suite, s
 // =================================================================================================
 extern "C" vrfs_status vrfs_measure_mac32_peak(vrfs_ctx* ctx, int variant, double* out_mac_per_s, double* out_sm_mhz_est) {
   if (!ctx || !out_mac_per_s) return VRFS_BAD_ARG;
-  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
+  CallGuard guard_(ctx);
   CU(cudaSetDevice(ctx->device));
   const int threads = 256, blocks = ctx->sms * 8;
   void *out = nullptr, *cyc = nullptr;
@@ -654,11 +740,15 @@ template <class S> __global__ void __launch_bounds__(ITEM_THREADS) k_pedersen_ve
 }
 // Ok + c*O == s*I  and  R + c*Yb == s*G + sb*B, given T1 = s*I - c*O and T2 = s*G + sb*B - c*Yb (projective)
 template <class C> __global__ void __launch_bounds__(ITEM_THREADS) k_pedersen_verify_finish(uint32_t n, const uint8_t* proof, const uint32_t* t1, const uint32_t* t2,
-                                                                                             const uint8_t* valid, uint8_t* out_ok) {
+                                                                                             const uint8_t* valid, uint8_t* out_ok, uint8_t* out_status) {
   ITEM_INDEX(n);
   const uint8_t* pr = proof + (size_t)256 * i;
-  bool ok = proj_equals_affine_bytes<C>(t1 + (size_t)24 * i, pr + 128) & proj_equals_affine_bytes<C>(t2 + (size_t)24 * i, pr + 64);
-  out_ok[i] = (uint8_t)(ok && valid[i]);
+  const int e1 = proj_vs_affine_bytes<C>(t1 + (size_t)24 * i, pr + 128), e2 = proj_vs_affine_bytes<C>(t2 + (size_t)24 * i, pr + 64);
+  const bool good = e1 == 2 && e2 == 2 && valid[i];
+  out_ok[i] = (uint8_t)good;
+  // `valid` is cleared by the linear combinations for I, O, Yb that are no curve points and by the prep kernel for identities;
+  // R and Ok are validated here
+  if (out_status) out_status[i] = (uint8_t)(good ? ITEM_OK : (!valid[i] || e1 == 0 || e2 == 0) ? ITEM_INVALID_DATA : ITEM_VERIFICATION_FAILURE);
 }
 
 // =================================================================================================
@@ -690,7 +780,13 @@ static vrfs_status fresh_valid(vrfs_ctx* ctx, size_t n, uint8_t** valid) {
   *valid = (uint8_t*)v;
   return VRFS_OK;
 }
-template <class S> static const void* fixtab(vrfs_ctx* ctx, int which) { return ctx->fixtab[S::ID][which]; }
+template <class S> static const void* fixtab(vrfs_ctx* ctx, int which) { return ctx->fixtab[S::ID][which]; }   // after need_tables<S>
+// key material on the device: remembered per buffer, zeroed by the outermost CallGuard
+static void mark_secret(vrfs_ctx* ctx, int which, size_t bytes) { if (ctx->buf[which].secret_bytes < bytes) ctx->buf[which].secret_bytes = bytes; }
+static vrfs_status stage_secret(vrfs_ctx* ctx, int which, const void* host, size_t bytes, const uint8_t** dev) {
+  mark_secret(ctx, which, bytes);
+  return stage_in(ctx, which, host, bytes, dev);
+}
 // batched inversion of the Z coordinates of NP projective results per item (k_zinv): returns the device array of n x 8 words
 template <class C, int NP> static vrfs_status launch_zinv(vrfs_ctx* ctx, size_t n, const void* p0, const void* p1, const void* p2, const uint32_t** out) {
   void* z = nullptr;
@@ -729,7 +825,9 @@ static vrfs_status ietf_prove_dev(vrfs_ctx* ctx, size_t n, const uint8_t* sk, co
   typedef typename S::C C;
   void *k = nullptr, *y = nullptr, *kg = nullptr, *ki = nullptr;
   uint8_t* valid = nullptr;
+  ST(need_tables<S>(ctx));
   ST(ensure(ctx, BUF_W0, n * 32, &k)); ST(ensure(ctx, BUF_W1, n * 96, &y)); ST(ensure(ctx, BUF_W2, n * 96, &kg)); ST(ensure(ctx, BUF_W3, n * 96, &ki));
+  mark_secret(ctx, BUF_W0, n * 32);                      // the nonces k
   ST(fresh_valid(ctx, n, &valid));
   k_nonce<S><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, sk, input, (uint8_t*)k);
   LAUNCHED_AS(ctx, "nonce");
@@ -751,13 +849,13 @@ static vrfs_status ietf_prove_dev(vrfs_ctx* ctx, size_t n, const uint8_t* sk, co
 extern "C" vrfs_status vrfs_ietf_prove_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* sk, const uint8_t* input, const uint8_t* output,
                                              const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_c, uint8_t* out_s) {
   if (!ctx) return VRFS_BAD_ARG;
-  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
+  CallGuard guard_(ctx);
   if (n == 0) return VRFS_OK;
   if (!sk || !input || !output || !out_c || !out_s) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
   ST(begin_call(ctx, n));
   const uint8_t *d_sk, *d_in, *d_out, *d_ad; const uint64_t* d_off; uint8_t *d_c, *d_s;
-  ST(stage_in(ctx, BUF_IN0, sk, n * 32, &d_sk)); ST(stage_in(ctx, BUF_IN1, input, n * 64, &d_in)); ST(stage_in(ctx, BUF_IN2, output, n * 64, &d_out));
+  ST(stage_secret(ctx, BUF_IN0, sk, n * 32, &d_sk)); ST(stage_in(ctx, BUF_IN1, input, n * 64, &d_in)); ST(stage_in(ctx, BUF_IN2, output, n * 64, &d_out));
   ST(stage_ad(ctx, n, ad, ad_off, &d_ad, &d_off));
   ST(stage_out(ctx, BUF_OUT0, n * 32, &d_c)); ST(stage_out(ctx, BUF_OUT1, n * 32, &d_s));
   vrfs_status st = suite == VRFS_BANDERSNATCH_ELL2 ? ietf_prove_dev<BandSuite>(ctx, n, d_sk, d_in, d_out, d_ad, d_off, d_c, d_s)
@@ -783,13 +881,13 @@ template <class S> static vrfs_status output_dev(vrfs_ctx* ctx, size_t n, const 
 }
 extern "C" vrfs_status vrfs_output_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* sk, const uint8_t* input, uint8_t* out_output) {
   if (!ctx) return VRFS_BAD_ARG;
-  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
+  CallGuard guard_(ctx);
   if (n == 0) return VRFS_OK;
   if (!sk || !input || !out_output) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
   ST(begin_call(ctx, n));
   const uint8_t *d_sk, *d_in; uint8_t* d_o;
-  ST(stage_in(ctx, BUF_IN0, sk, n * 32, &d_sk)); ST(stage_in(ctx, BUF_IN1, input, n * 64, &d_in)); ST(stage_out(ctx, BUF_OUT0, n * 64, &d_o));
+  ST(stage_secret(ctx, BUF_IN0, sk, n * 32, &d_sk)); ST(stage_in(ctx, BUF_IN1, input, n * 64, &d_in)); ST(stage_out(ctx, BUF_OUT0, n * 64, &d_o));
   ST(suite == VRFS_BANDERSNATCH_ELL2 ? output_dev<BandSuite>(ctx, n, d_sk, d_in, d_o)
      : suite == VRFS_ED25519_TAI ? output_dev<EdSuite>(ctx, n, d_sk, d_in, d_o) : output_dev<P256Suite>(ctx, n, d_sk, d_in, d_o));
   ST(copy_out(ctx, out_output, d_o, n * 64));
@@ -800,6 +898,7 @@ template <class S> static vrfs_status from_seed_dev(vrfs_ctx* ctx, size_t n, con
   k_secret_from_seed<S><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, seeds, off, out_sk);
   LAUNCHED_AS(ctx, "secret_from_seed");
   if (!out_pk) return VRFS_OK;
+  ST(need_tables<S>(ctx));
   void* o = nullptr;
   ST(ensure(ctx, BUF_W0, n * 96, &o));
   LincombArgs A = {};
@@ -814,14 +913,16 @@ template <class S> static vrfs_status from_seed_dev(vrfs_ctx* ctx, size_t n, con
 extern "C" vrfs_status vrfs_secret_from_seed_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* seeds, const uint64_t* seed_off,
                                                    uint8_t* out_sk, uint8_t* out_pk) {
   if (!ctx) return VRFS_BAD_ARG;
-  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
+  CallGuard guard_(ctx);
   if (n == 0) return VRFS_OK;
   if (!seed_off || !out_sk) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
   ST(begin_call(ctx, n));
   const uint8_t* d_seeds; const uint64_t* d_off; uint8_t *d_sk, *d_pk = nullptr;
   ST(stage_ad(ctx, n, seeds, seed_off, &d_seeds, &d_off));
+  mark_secret(ctx, BUF_AD, (size_t)(seed_off[n] - seed_off[0]));
   ST(stage_out(ctx, BUF_OUT0, n * 32, &d_sk));
+  mark_secret(ctx, BUF_OUT0, n * 32);
   if (out_pk) ST(stage_out(ctx, BUF_OUT1, n * 64, &d_pk));
   ST(suite == VRFS_BANDERSNATCH_ELL2 ? from_seed_dev<BandSuite>(ctx, n, d_seeds, d_off, d_sk, d_pk)
      : suite == VRFS_ED25519_TAI ? from_seed_dev<EdSuite>(ctx, n, d_seeds, d_off, d_sk, d_pk) : from_seed_dev<P256Suite>(ctx, n, d_seeds, d_off, d_sk, d_pk));
@@ -831,13 +932,14 @@ extern "C" vrfs_status vrfs_secret_from_seed_batch(vrfs_ctx* ctx, vrfs_suite sui
 }
 extern "C" vrfs_status vrfs_nonce_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* sk, const uint8_t* input, uint8_t* out_k) {
   if (!ctx) return VRFS_BAD_ARG;
-  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
+  CallGuard guard_(ctx);
   if (n == 0) return VRFS_OK;
   if (!sk || !input || !out_k) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
   ST(begin_call(ctx, n));
   const uint8_t *d_sk, *d_in; uint8_t* d_k;
-  ST(stage_in(ctx, BUF_IN0, sk, n * 32, &d_sk)); ST(stage_in(ctx, BUF_IN1, input, n * 64, &d_in)); ST(stage_out(ctx, BUF_OUT0, n * 32, &d_k));
+  ST(stage_secret(ctx, BUF_IN0, sk, n * 32, &d_sk)); ST(stage_in(ctx, BUF_IN1, input, n * 64, &d_in)); ST(stage_out(ctx, BUF_OUT0, n * 32, &d_k));
+  mark_secret(ctx, BUF_OUT0, n * 32);
   if (suite == VRFS_BANDERSNATCH_ELL2) k_nonce<BandSuite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_sk, d_in, d_k);
   else if (suite == VRFS_ED25519_TAI) k_nonce<EdSuite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_sk, d_in, d_k);
   else k_nonce<P256Suite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_sk, d_in, d_k);
@@ -847,7 +949,7 @@ extern "C" vrfs_status vrfs_nonce_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t 
 }
 extern "C" vrfs_status vrfs_point_to_hash_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* pts, uint8_t* out_hash) {
   if (!ctx) return VRFS_BAD_ARG;
-  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
+  CallGuard guard_(ctx);
   if (n == 0) return VRFS_OK;
   if (!pts || !out_hash) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
@@ -864,7 +966,7 @@ extern "C" vrfs_status vrfs_point_to_hash_batch(vrfs_ctx* ctx, vrfs_suite suite,
 }
 extern "C" vrfs_status vrfs_point_encode_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* pts, uint8_t* out_enc) {
   if (!ctx) return VRFS_BAD_ARG;
-  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
+  CallGuard guard_(ctx);
   if (n == 0) return VRFS_OK;
   if (!pts || !out_enc) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
@@ -881,7 +983,7 @@ extern "C" vrfs_status vrfs_point_encode_batch(vrfs_ctx* ctx, vrfs_suite suite, 
 }
 extern "C" vrfs_status vrfs_point_decode_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* enc, uint8_t* out_pts, uint8_t* out_ok) {
   if (!ctx) return VRFS_BAD_ARG;
-  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
+  CallGuard guard_(ctx);
   if (n == 0) return VRFS_OK;
   if (!enc || !out_pts || !out_ok) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
@@ -899,7 +1001,7 @@ extern "C" vrfs_status vrfs_point_decode_batch(vrfs_ctx* ctx, vrfs_suite suite, 
 extern "C" vrfs_status vrfs_data_to_point_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* data, const uint64_t* data_off,
                                                 uint8_t* out_pts, uint8_t* out_ok) {
   if (!ctx) return VRFS_BAD_ARG;
-  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
+  CallGuard guard_(ctx);
   if (n == 0) return VRFS_OK;
   if (!data_off || !out_pts || !out_ok) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
@@ -920,7 +1022,9 @@ static vrfs_status pedersen_prove_dev(vrfs_ctx* ctx, size_t n, const uint8_t* sk
   typedef typename S::C C;
   void *sc = nullptr, *yb = nullptr, *r = nullptr, *okp = nullptr;
   uint8_t* valid = nullptr;
+  ST(need_tables<S>(ctx));
   ST(ensure(ctx, BUF_W0, n * 96, &sc)); ST(ensure(ctx, BUF_W1, n * 96, &yb)); ST(ensure(ctx, BUF_W2, n * 96, &r)); ST(ensure(ctx, BUF_W3, n * 96, &okp));
+  mark_secret(ctx, BUF_W0, n * 96);                      // blinding factor b and the nonces k, kb
   ST(fresh_valid(ctx, n, &valid));
   uint8_t *b = (uint8_t*)sc, *k = b + n * 32, *kb = k + n * 32;
   k_pedersen_prove_prep<S><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, sk, input, ad, ad_off, b, k, kb);
@@ -943,15 +1047,16 @@ static vrfs_status pedersen_prove_dev(vrfs_ctx* ctx, size_t n, const uint8_t* sk
 extern "C" vrfs_status vrfs_pedersen_prove_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* sk, const uint8_t* input, const uint8_t* output,
                                                  const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_proof, uint8_t* out_blinding) {
   if (!ctx) return VRFS_BAD_ARG;
-  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
+  CallGuard guard_(ctx);
   if (n == 0) return VRFS_OK;
   if (!sk || !input || !output || !out_proof || !out_blinding) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
   ST(begin_call(ctx, n));
   const uint8_t *d_sk, *d_in, *d_out, *d_ad; const uint64_t* d_off; uint8_t *d_pr, *d_bl;
-  ST(stage_in(ctx, BUF_IN0, sk, n * 32, &d_sk)); ST(stage_in(ctx, BUF_IN1, input, n * 64, &d_in)); ST(stage_in(ctx, BUF_IN2, output, n * 64, &d_out));
+  ST(stage_secret(ctx, BUF_IN0, sk, n * 32, &d_sk)); ST(stage_in(ctx, BUF_IN1, input, n * 64, &d_in)); ST(stage_in(ctx, BUF_IN2, output, n * 64, &d_out));
   ST(stage_ad(ctx, n, ad, ad_off, &d_ad, &d_off));
   ST(stage_out(ctx, BUF_OUT0, n * 256, &d_pr)); ST(stage_out(ctx, BUF_OUT1, n * 32, &d_bl));
+  mark_secret(ctx, BUF_OUT1, n * 32);
   ST(suite == VRFS_BANDERSNATCH_ELL2 ? pedersen_prove_dev<BandSuite>(ctx, n, d_sk, d_in, d_out, d_ad, d_off, d_pr, d_bl)
      : suite == VRFS_ED25519_TAI ? pedersen_prove_dev<EdSuite>(ctx, n, d_sk, d_in, d_out, d_ad, d_off, d_pr, d_bl) : pedersen_prove_dev<P256Suite>(ctx, n, d_sk, d_in, d_out, d_ad, d_off, d_pr, d_bl));
   ST(copy_out(ctx, out_proof, d_pr, n * 256)); ST(copy_out(ctx, out_blinding, d_bl, n * 32));
@@ -959,10 +1064,11 @@ extern "C" vrfs_status vrfs_pedersen_prove_batch(vrfs_ctx* ctx, vrfs_suite suite
 }
 template <class S>
 static vrfs_status pedersen_verify_dev(vrfs_ctx* ctx, size_t n, const uint8_t* input, const uint8_t* output, const uint8_t* proof, const uint8_t* ad,
-                                       const uint64_t* ad_off, uint8_t* out_ok) {
+                                       const uint64_t* ad_off, uint8_t* out_ok, uint8_t* out_status = nullptr) {
   typedef typename S::C C;
   void *c = nullptr, *t1 = nullptr, *t2 = nullptr;
   uint8_t* valid = nullptr;
+  ST(need_tables<S>(ctx));
   ST(ensure(ctx, BUF_W0, n * 32, &c)); ST(ensure(ctx, BUF_W1, n * 96, &t1)); ST(ensure(ctx, BUF_W2, n * 96, &t2));
   ST(fresh_valid(ctx, n, &valid));
   k_pedersen_verify_prep<S><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, input, output, proof, ad, ad_off, (uint8_t*)c, valid);
@@ -977,25 +1083,27 @@ static vrfs_status pedersen_verify_dev(vrfs_ctx* ctx, size_t n, const uint8_t* i
   A.var[0] = {proof, 256, (const uint8_t*)c, 32, 1, cbits};
   A.fix[0] = {proof + 192, 256, 0, fixtab<S>(ctx, 0)}; A.fix[1] = {proof + 224, 256, 0, fixtab<S>(ctx, 1)}; A.out_xyz = (uint32_t*)t2;
   ST((launch_lincomb<C, 1, 2>(ctx, A)));
-  k_pedersen_verify_finish<C><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, proof, (const uint32_t*)t1, (const uint32_t*)t2, valid, out_ok);
+  k_pedersen_verify_finish<C><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, proof, (const uint32_t*)t1, (const uint32_t*)t2, valid, out_ok, out_status);
   LAUNCHED_AS(ctx, "pedersen_verify_finish");
   return VRFS_OK;
 }
 extern "C" vrfs_status vrfs_pedersen_verify_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* input, const uint8_t* output, const uint8_t* proof,
-                                                  const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_ok) {
+                                                  const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_ok, uint8_t* out_status) {
   if (!ctx) return VRFS_BAD_ARG;
-  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
+  CallGuard guard_(ctx);
   if (n == 0) return VRFS_OK;
   if (!input || !output || !proof || !out_ok) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
   ST(begin_call(ctx, n));
-  const uint8_t *d_in, *d_out, *d_pr, *d_ad; const uint64_t* d_off; uint8_t* d_ok;
+  const uint8_t *d_in, *d_out, *d_pr, *d_ad; const uint64_t* d_off; uint8_t *d_ok, *d_st = nullptr;
   ST(stage_in(ctx, BUF_IN0, input, n * 64, &d_in)); ST(stage_in(ctx, BUF_IN1, output, n * 64, &d_out)); ST(stage_in(ctx, BUF_IN2, proof, n * 256, &d_pr));
   ST(stage_ad(ctx, n, ad, ad_off, &d_ad, &d_off));
   ST(stage_out(ctx, BUF_OUT0, n, &d_ok));
-  ST(suite == VRFS_BANDERSNATCH_ELL2 ? pedersen_verify_dev<BandSuite>(ctx, n, d_in, d_out, d_pr, d_ad, d_off, d_ok)
-     : suite == VRFS_ED25519_TAI ? pedersen_verify_dev<EdSuite>(ctx, n, d_in, d_out, d_pr, d_ad, d_off, d_ok) : pedersen_verify_dev<P256Suite>(ctx, n, d_in, d_out, d_pr, d_ad, d_off, d_ok));
+  if (out_status) ST(stage_out(ctx, BUF_OUT1, n, &d_st));
+  ST(suite == VRFS_BANDERSNATCH_ELL2 ? pedersen_verify_dev<BandSuite>(ctx, n, d_in, d_out, d_pr, d_ad, d_off, d_ok, d_st)
+     : suite == VRFS_ED25519_TAI ? pedersen_verify_dev<EdSuite>(ctx, n, d_in, d_out, d_pr, d_ad, d_off, d_ok, d_st) : pedersen_verify_dev<P256Suite>(ctx, n, d_in, d_out, d_pr, d_ad, d_off, d_ok, d_st));
   ST(copy_out(ctx, out_ok, d_ok, n));
+  if (out_status) ST(copy_out(ctx, out_status, d_st, n));
   return finish_call(ctx);
 }
 
@@ -1039,11 +1147,13 @@ template <class S> __global__ void __launch_bounds__(ITEM_THREADS) k_wire_pack_s
   wire_pack_signature<S>(tmp, output + (size_t)64 * i, c + (size_t)32 * i, s + (size_t)32 * i);
   for (int j = 0; j < SL; j++) o[j] = tmp[j];
 }
-// out_ok &= a & b; rejected items get a zero hash
-__global__ void k_merge_flags(uint32_t n, const uint8_t* a, const uint8_t* b, uint8_t* out_ok, uint8_t* hash, uint32_t hlen) {
+// out_ok &= a & b; rejected items get a zero hash; a failed deserialisation (a or b clear) is Error::InvalidData
+__global__ void k_merge_flags(uint32_t n, const uint8_t* a, const uint8_t* b, uint8_t* out_ok, uint8_t* hash, uint32_t hlen, uint8_t* status) {
   ITEM_INDEX(n);
-  uint8_t ok = out_ok[i] & a[i] & (b ? b[i] : 1);
+  const uint8_t wellformed = a[i] & (b ? b[i] : 1);
+  uint8_t ok = out_ok[i] & wellformed;
   out_ok[i] = ok;
+  if (status) status[i] = (uint8_t)(ok ? ITEM_OK : !wellformed ? ITEM_INVALID_DATA : status[i] == ITEM_OK ? ITEM_VERIFICATION_FAILURE : status[i]);
   if (hash && !ok) for (uint32_t j = 0; j < hlen; j++) hash[(size_t)hlen * i + j] = 0;
 }
 
@@ -1057,7 +1167,7 @@ template <class S> static vrfs_status decode_checked_launch(vrfs_ctx* ctx, size_
 }
 extern "C" vrfs_status vrfs_point_decode_checked_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* enc, uint8_t* out_pts, uint8_t* out_ok) {
   if (!ctx) return VRFS_BAD_ARG;
-  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
+  CallGuard guard_(ctx);
   if (n == 0) return VRFS_OK;
   if (!enc || !out_pts || !out_ok) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
@@ -1073,7 +1183,7 @@ extern "C" vrfs_status vrfs_point_decode_checked_batch(vrfs_ctx* ctx, vrfs_suite
 }
 extern "C" vrfs_status vrfs_subgroup_check_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* pts, uint8_t* out_ok) {
   if (!ctx) return VRFS_BAD_ARG;
-  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
+  CallGuard guard_(ctx);
   if (n == 0) return VRFS_OK;
   if (!pts || !out_ok) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
@@ -1102,7 +1212,7 @@ template <class S> static vrfs_status ietf_sign_wire_dev(vrfs_ctx* ctx, size_t n
 extern "C" vrfs_status vrfs_ietf_sign_wire_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* sk, const uint8_t* data, const uint64_t* data_off,
                                                  const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_sig, uint8_t* out_ok) {
   if (!ctx) return VRFS_BAD_ARG;
-  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
+  CallGuard guard_(ctx);
   if (n == 0) return VRFS_OK;
   if (!sk || !data_off || !out_sig) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
@@ -1110,11 +1220,9 @@ extern "C" vrfs_status vrfs_ietf_sign_wire_batch(vrfs_ctx* ctx, vrfs_suite suite
   const size_t sl = (size_t)vrfs_suite_ietf_signature_len(suite);
   const uint8_t *d_sk, *d_ad, *d_data; const uint64_t *d_off, *d_doff;
   uint8_t *d_in, *d_out, *d_c, *d_s, *d_ok, *d_sig;
-  ST(stage_in(ctx, BUF_IN0, sk, n * 32, &d_sk));
+  ST(stage_secret(ctx, BUF_IN0, sk, n * 32, &d_sk));
   ST(stage_ad(ctx, n, ad, ad_off, &d_ad, &d_off));
-  for (size_t i = 0; i < n; i++) if (data_off[i + 1] < data_off[i]) return fail(ctx, VRFS_BAD_ARG, "offsets must be non-decreasing");
-  if (data_off[n] > 0 && !data) return fail(ctx, VRFS_BAD_ARG, "null data buffer with non-empty offsets");
-  { const uint8_t* o; ST(stage_in(ctx, BUF_X2, data, (size_t)data_off[n], &d_data)); ST(stage_in(ctx, BUF_X3, data_off, (n + 1) * sizeof(uint64_t), &o)); d_doff = (const uint64_t*)o; }
+  ST(stage_var(ctx, BUF_X2, BUF_X3, n, data, data_off, &d_data, &d_doff));
   ST(stage_out(ctx, BUF_IN1, n * 64, &d_in)); ST(stage_out(ctx, BUF_IN2, n * 64, &d_out)); ST(stage_out(ctx, BUF_IN3, n * 32, &d_c)); ST(stage_out(ctx, BUF_IN4, n * 32, &d_s));
   ST(stage_out(ctx, BUF_X4, n, &d_ok)); ST(stage_out(ctx, BUF_X1, n * sl, &d_sig));
   ST(suite == VRFS_BANDERSNATCH_ELL2 ? ietf_sign_wire_dev<BandSuite>(ctx, n, d_sk, d_data, d_doff, d_ad, d_off, d_in, d_out, d_c, d_s, d_ok, d_sig)
@@ -1128,67 +1236,70 @@ extern "C" vrfs_status vrfs_ietf_sign_wire_batch(vrfs_ctx* ctx, vrfs_suite suite
 // serialised Public + data + signature -> verdict (+ Output::hash of accepted items)
 template <class S> static vrfs_status ietf_verify_wire_dev(vrfs_ctx* ctx, size_t n, const uint8_t* pk_enc, const uint8_t* data, const uint64_t* data_off, const uint8_t* sig,
                                                            const uint8_t* ad, const uint64_t* ad_off, uint8_t* pk, uint8_t* input, uint8_t* output, uint8_t* c, uint8_t* s,
-                                                           uint8_t* flags /*4n*/, uint8_t* out_ok, uint8_t* out_hash) {
+                                                           uint8_t* flags /*4n*/, uint8_t* out_ok, uint8_t* out_hash, uint8_t* out_status) {
   constexpr uint32_t SL = S::ENC_LEN + S::CLEN + 32;
   ST((decode_checked_launch<S>(ctx, n, pk_enc, S::ENC_LEN, pk, sig, SL, output, flags)));
   k_wire_parse_proof<S><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, sig, flags, c, s, flags + 2 * n);
   LAUNCHED_AS(ctx, "wire_parse_proof");
   ST(data_to_point_dev<S>(ctx, n, data, data_off, input, flags + 3 * n));
-  ST(ietf_verify_dev<S>(ctx, n, pk, input, output, c, s, ad, ad_off, out_ok));
+  ST(ietf_verify_dev<S>(ctx, n, pk, input, output, c, s, ad, ad_off, out_ok, out_status));
   if (out_hash) {
     k_point_to_hash<S><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, output, out_hash);
     LAUNCHED_AS(ctx, "point_to_hash");
   }
-  k_merge_flags<<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, flags + 2 * n, flags + 3 * n, out_ok, out_hash, (uint32_t)S::HLEN);
+  k_merge_flags<<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, flags + 2 * n, flags + 3 * n, out_ok, out_hash, (uint32_t)S::HLEN, out_status);
   LAUNCHED_AS(ctx, "merge_flags");
   return VRFS_OK;
 }
 extern "C" vrfs_status vrfs_ietf_verify_wire_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* pk_enc, const uint8_t* data, const uint64_t* data_off,
-                                                   const uint8_t* sig, const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_ok, uint8_t* out_hash) {
+                                                   const uint8_t* sig, const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_ok, uint8_t* out_hash, uint8_t* out_status) {
   if (!ctx) return VRFS_BAD_ARG;
-  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
+  CallGuard guard_(ctx);
   if (n == 0) return VRFS_OK;
   if (!pk_enc || !data_off || !sig || !out_ok) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
   ST(begin_call(ctx, n));
   const size_t sl = (size_t)vrfs_suite_ietf_signature_len(suite), el = (size_t)vrfs_suite_point_enc_len(suite), hl = (size_t)vrfs_suite_hash_len(suite);
   const uint8_t *d_pke, *d_sig, *d_ad, *d_data; const uint64_t *d_off, *d_doff;
-  uint8_t *d_pk, *d_in, *d_out, *d_c, *d_s, *d_flags, *d_ok, *d_hash = nullptr;
+  uint8_t *d_pk, *d_in, *d_out, *d_c, *d_s, *d_flags, *d_ok, *d_hash = nullptr, *d_st = nullptr;
   ST(stage_in(ctx, BUF_X0, pk_enc, n * el, &d_pke)); ST(stage_in(ctx, BUF_X1, sig, n * sl, &d_sig));
   ST(stage_ad(ctx, n, ad, ad_off, &d_ad, &d_off));
-  for (size_t i = 0; i < n; i++) if (data_off[i + 1] < data_off[i]) return fail(ctx, VRFS_BAD_ARG, "offsets must be non-decreasing");
-  if (data_off[n] > 0 && !data) return fail(ctx, VRFS_BAD_ARG, "null data buffer with non-empty offsets");
-  { const uint8_t* o; ST(stage_in(ctx, BUF_X2, data, (size_t)data_off[n], &d_data)); ST(stage_in(ctx, BUF_X3, data_off, (n + 1) * sizeof(uint64_t), &o)); d_doff = (const uint64_t*)o; }
+  ST(stage_var(ctx, BUF_X2, BUF_X3, n, data, data_off, &d_data, &d_doff));
   ST(stage_out(ctx, BUF_IN0, n * 64, &d_pk)); ST(stage_out(ctx, BUF_IN1, n * 64, &d_in)); ST(stage_out(ctx, BUF_IN2, n * 64, &d_out));
   ST(stage_out(ctx, BUF_IN3, n * 32, &d_c)); ST(stage_out(ctx, BUF_IN4, n * 32, &d_s)); ST(stage_out(ctx, BUF_X4, 4 * n, &d_flags));
   ST(stage_out(ctx, BUF_OUT0, n, &d_ok));
   if (out_hash) ST(stage_out(ctx, BUF_OUT1, n * hl, &d_hash));
-  ST(suite == VRFS_BANDERSNATCH_ELL2 ? ietf_verify_wire_dev<BandSuite>(ctx, n, d_pke, d_data, d_doff, d_sig, d_ad, d_off, d_pk, d_in, d_out, d_c, d_s, d_flags, d_ok, d_hash)
-     : suite == VRFS_ED25519_TAI ? ietf_verify_wire_dev<EdSuite>(ctx, n, d_pke, d_data, d_doff, d_sig, d_ad, d_off, d_pk, d_in, d_out, d_c, d_s, d_flags, d_ok, d_hash)
-                                 : ietf_verify_wire_dev<P256Suite>(ctx, n, d_pke, d_data, d_doff, d_sig, d_ad, d_off, d_pk, d_in, d_out, d_c, d_s, d_flags, d_ok, d_hash));
+  if (out_status) ST(stage_out(ctx, BUF_X5, n, &d_st));
+  ST(suite == VRFS_BANDERSNATCH_ELL2 ? ietf_verify_wire_dev<BandSuite>(ctx, n, d_pke, d_data, d_doff, d_sig, d_ad, d_off, d_pk, d_in, d_out, d_c, d_s, d_flags, d_ok, d_hash, d_st)
+     : suite == VRFS_ED25519_TAI ? ietf_verify_wire_dev<EdSuite>(ctx, n, d_pke, d_data, d_doff, d_sig, d_ad, d_off, d_pk, d_in, d_out, d_c, d_s, d_flags, d_ok, d_hash, d_st)
+                                 : ietf_verify_wire_dev<P256Suite>(ctx, n, d_pke, d_data, d_doff, d_sig, d_ad, d_off, d_pk, d_in, d_out, d_c, d_s, d_flags, d_ok, d_hash, d_st));
   ST(copy_out(ctx, out_ok, d_ok, n));
   if (out_hash) ST(copy_out(ctx, out_hash, d_hash, n * hl));
+  if (out_status) ST(copy_out(ctx, out_status, d_st, n));
   return finish_call(ctx);
 }
 
-// ---- pedersen wire form: point_encode(Output) || point_encode(pk_com) || point_encode(r) || point_encode(ok) || s || sb
-// (an `Output` followed by `pedersen::Proof`'s CanonicalSerialize, A.10)
-// one thread per encoded point (4 per item): j = 0 -> output_aff[item], j = 1..3 -> the ABI proof's three 64-byte points
-template <class S> __global__ void __launch_bounds__(ITEM_THREADS) k_ped_wire_points(uint32_t n, const uint8_t* sig, uint8_t* output, uint8_t* proof256, uint8_t* flags) {
+// ---- pedersen on the wire.  Two layouts share the kernels below (NP = encoded points per item):
+//   NP = 4  signature: point_encode(Output) || point_encode(pk_com) || point_encode(r) || point_encode(ok) || s || sb
+//           (an `Output` followed by `pedersen::Proof`'s CanonicalSerialize, A.10; Bandersnatch 192 B)
+//   NP = 3  the typed `pedersen::Proof` alone: pk_com || r || ok || s || sb (Bandersnatch 160 B)
+// one thread per encoded point: with NP = 4 point 0 goes to output_aff[item]; the proof's points go to the 256-byte ABI proof
+template <class S, int NP> __global__ void __launch_bounds__(ITEM_THREADS) k_ped_wire_points(uint32_t n, const uint8_t* sig, uint8_t* output, uint8_t* proof256, uint8_t* flags) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= 4 * n) return;
-  constexpr uint32_t SL = 4 * S::ENC_LEN + 64;
+  if (t >= NP * n) return;
+  constexpr uint32_t SL = NP * S::ENC_LEN + 64;
   const uint32_t j = t / n, i = t % n;
   const uint8_t* e = sig + (size_t)SL * i + (size_t)S::ENC_LEN * j;
   uint8_t tmp[S::ENC_LEN];
   for (int k = 0; k < S::ENC_LEN; k++) tmp[k] = e[k];
-  uint8_t* dst = j == 0 ? output + (size_t)64 * i : proof256 + (size_t)256 * i + 64 * (j - 1);
+  const uint32_t slot = NP == 4 ? j - 1 : j;
+  uint8_t* dst = (NP == 4 && j == 0) ? output + (size_t)64 * i : proof256 + (size_t)256 * i + 64 * slot;
   flags[t] = (uint8_t)wire_decode_point_checked<S>(dst, tmp);
 }
-template <class S> __global__ void __launch_bounds__(ITEM_THREADS) k_ped_wire_scalars(uint32_t n, const uint8_t* sig, const uint8_t* flags4, uint8_t* proof256, uint8_t* valid) {
+template <class S, int NP> __global__ void __launch_bounds__(ITEM_THREADS) k_ped_wire_scalars(uint32_t n, const uint8_t* sig, const uint8_t* flagsNP, uint8_t* proof256, uint8_t* valid) {
   ITEM_INDEX(n);
-  constexpr uint32_t SL = 4 * S::ENC_LEN + 64;
-  const uint8_t* p = sig + (size_t)SL * i + 4 * S::ENC_LEN;
+  constexpr uint32_t SL = NP * S::ENC_LEN + 64;
+  const uint8_t* p = sig + (size_t)SL * i + NP * S::ENC_LEN;
   uint8_t* o = proof256 + (size_t)256 * i + 192;
   bool ok = true;
   for (int h = 0; h < 2; h++) {
@@ -1197,35 +1308,37 @@ template <class S> __global__ void __launch_bounds__(ITEM_THREADS) k_ped_wire_sc
     load_le<8>(raw, o + 32 * h);
     ok &= is_canonical<typename S::C::Fr>(raw);
   }
-  valid[i] = (uint8_t)(ok && flags4[i] && flags4[n + i] && flags4[2 * n + i] && flags4[3 * n + i]);
+  for (int j = 0; j < NP; j++) ok &= flagsNP[(size_t)j * n + i] != 0;
+  valid[i] = (uint8_t)ok;
 }
-template <class S> __global__ void __launch_bounds__(ITEM_THREADS) k_ped_wire_pack(uint32_t n, const uint8_t* output, const uint8_t* proof256, const uint8_t* ok, uint8_t* sig) {
+template <class S, int NP> __global__ void __launch_bounds__(ITEM_THREADS) k_ped_wire_pack(uint32_t n, const uint8_t* output, const uint8_t* proof256, const uint8_t* ok, uint8_t* sig) {
   ITEM_INDEX(n);
-  constexpr uint32_t SL = 4 * S::ENC_LEN + 64;
+  constexpr uint32_t SL = NP * S::ENC_LEN + 64;
   uint8_t* o = sig + (size_t)SL * i;
-  if (!ok[i]) { for (uint32_t j = 0; j < SL; j++) o[j] = 0; return; }
+  if (ok && !ok[i]) { for (uint32_t j = 0; j < SL; j++) o[j] = 0; return; }
   const uint8_t* pr = proof256 + (size_t)256 * i;
   uint8_t tmp[SL];
-  encode_point_bytes<S>(tmp, output + (size_t)64 * i);
-  for (int j = 0; j < 3; j++) encode_point_bytes<S>(tmp + S::ENC_LEN * (j + 1), pr + 64 * j);
-  for (int h = 0; h < 2; h++) for (int j = 0; j < 32; j++) tmp[4 * S::ENC_LEN + 32 * h + j] = S::SEC1 ? pr[192 + 32 * h + 31 - j] : pr[192 + 32 * h + j];
+  if (NP == 4) encode_point_bytes<S>(tmp, output + (size_t)64 * i);
+  for (int j = 0; j < 3; j++) encode_point_bytes<S>(tmp + S::ENC_LEN * (j + NP - 3), pr + 64 * j);
+  for (int h = 0; h < 2; h++) for (int j = 0; j < 32; j++) tmp[NP * S::ENC_LEN + 32 * h + j] = S::SEC1 ? pr[192 + 32 * h + 31 - j] : pr[192 + 32 * h + j];
   for (uint32_t j = 0; j < SL; j++) o[j] = tmp[j];
 }
 extern "C" int vrfs_suite_pedersen_signature_len(vrfs_suite s) { return 4 * vrfs_suite_point_enc_len(s) + 64; }
+extern "C" int vrfs_suite_pedersen_proof_len(vrfs_suite s) { return 3 * vrfs_suite_point_enc_len(s) + 64; }
 
 template <class S> static vrfs_status pedersen_sign_wire_dev(vrfs_ctx* ctx, size_t n, const uint8_t* sk, const uint8_t* data, const uint64_t* data_off, const uint8_t* ad,
                                                              const uint64_t* ad_off, uint8_t* input, uint8_t* output, uint8_t* proof256, uint8_t* blinding, uint8_t* h2c_ok, uint8_t* sig) {
   ST(data_to_point_dev<S>(ctx, n, data, data_off, input, h2c_ok));
   ST(output_dev<S>(ctx, n, sk, input, output));
   ST(pedersen_prove_dev<S>(ctx, n, sk, input, output, ad, ad_off, proof256, blinding));
-  k_ped_wire_pack<S><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, output, proof256, h2c_ok, sig);
+  k_ped_wire_pack<S, 4><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, output, proof256, h2c_ok, sig);
   LAUNCHED_AS(ctx, "ped_wire_pack");
   return VRFS_OK;
 }
 extern "C" vrfs_status vrfs_pedersen_sign_wire_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* sk, const uint8_t* data, const uint64_t* data_off,
                                                      const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_sig, uint8_t* out_blinding, uint8_t* out_ok) {
   if (!ctx) return VRFS_BAD_ARG;
-  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
+  CallGuard guard_(ctx);
   if (n == 0) return VRFS_OK;
   if (!sk || !data_off || !out_sig || !out_blinding) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
@@ -1233,12 +1346,11 @@ extern "C" vrfs_status vrfs_pedersen_sign_wire_batch(vrfs_ctx* ctx, vrfs_suite s
   const size_t sl = (size_t)vrfs_suite_pedersen_signature_len(suite);
   const uint8_t *d_sk, *d_ad, *d_data; const uint64_t *d_off, *d_doff;
   uint8_t *d_in, *d_out, *d_pr, *d_bl, *d_ok, *d_sig;
-  ST(stage_in(ctx, BUF_IN0, sk, n * 32, &d_sk));
+  ST(stage_secret(ctx, BUF_IN0, sk, n * 32, &d_sk));
   ST(stage_ad(ctx, n, ad, ad_off, &d_ad, &d_off));
-  for (size_t i = 0; i < n; i++) if (data_off[i + 1] < data_off[i]) return fail(ctx, VRFS_BAD_ARG, "offsets must be non-decreasing");
-  if (data_off[n] > 0 && !data) return fail(ctx, VRFS_BAD_ARG, "null data buffer with non-empty offsets");
-  { const uint8_t* o; ST(stage_in(ctx, BUF_X2, data, (size_t)data_off[n], &d_data)); ST(stage_in(ctx, BUF_X3, data_off, (n + 1) * sizeof(uint64_t), &o)); d_doff = (const uint64_t*)o; }
+  ST(stage_var(ctx, BUF_X2, BUF_X3, n, data, data_off, &d_data, &d_doff));
   ST(stage_out(ctx, BUF_IN1, n * 64, &d_in)); ST(stage_out(ctx, BUF_IN2, n * 64, &d_out)); ST(stage_out(ctx, BUF_OUT0, n * 256, &d_pr)); ST(stage_out(ctx, BUF_OUT1, n * 32, &d_bl));
+  mark_secret(ctx, BUF_OUT1, n * 32);
   ST(stage_out(ctx, BUF_X4, n, &d_ok)); ST(stage_out(ctx, BUF_X1, n * sl, &d_sig));
   ST(suite == VRFS_BANDERSNATCH_ELL2 ? pedersen_sign_wire_dev<BandSuite>(ctx, n, d_sk, d_data, d_doff, d_ad, d_off, d_in, d_out, d_pr, d_bl, d_ok, d_sig)
      : suite == VRFS_ED25519_TAI ? pedersen_sign_wire_dev<EdSuite>(ctx, n, d_sk, d_data, d_doff, d_ad, d_off, d_in, d_out, d_pr, d_bl, d_ok, d_sig)
@@ -1247,40 +1359,96 @@ extern "C" vrfs_status vrfs_pedersen_sign_wire_batch(vrfs_ctx* ctx, vrfs_suite s
   if (out_ok) ST(copy_out(ctx, out_ok, d_ok, n));
   return finish_call(ctx);
 }
-template <class S> static vrfs_status pedersen_verify_wire_dev(vrfs_ctx* ctx, size_t n, const uint8_t* data, const uint64_t* data_off, const uint8_t* sig, const uint8_t* ad,
-                                                               const uint64_t* ad_off, uint8_t* input, uint8_t* output, uint8_t* proof256, uint8_t* flags /*6n*/, uint8_t* out_ok) {
-  k_ped_wire_points<S><<<item_blocks(4 * n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, sig, output, proof256, flags);
+// deserialise NP encoded points + 2 scalars per item, then pedersen::Verifier::verify.  NP = 4: input = Input::new(data) here
+// (h2c flags in flags[(NP+1)n ..]); NP = 3: input and output are the caller's typed values.
+template <class S, int NP> static vrfs_status pedersen_verify_wire_dev(vrfs_ctx* ctx, size_t n, const uint8_t* data, const uint64_t* data_off, const uint8_t* sig, const uint8_t* ad,
+                                                                       const uint64_t* ad_off, uint8_t* input, uint8_t* output, uint8_t* proof256, uint8_t* flags /*(NP+2)n*/,
+                                                                       uint8_t* out_ok, uint8_t* out_status) {
+  k_ped_wire_points<S, NP><<<item_blocks(NP * n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, sig, output, proof256, flags);
   LAUNCHED_AS(ctx, "decode_checked");
-  k_ped_wire_scalars<S><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, sig, flags, proof256, flags + 4 * n);
+  k_ped_wire_scalars<S, NP><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, sig, flags, proof256, flags + NP * n);
   LAUNCHED_AS(ctx, "ped_wire_scalars");
-  ST(data_to_point_dev<S>(ctx, n, data, data_off, input, flags + 5 * n));
-  ST(pedersen_verify_dev<S>(ctx, n, input, output, proof256, ad, ad_off, out_ok));
-  k_merge_flags<<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, flags + 4 * n, flags + 5 * n, out_ok, nullptr, 0u);
+  if (NP == 4) ST(data_to_point_dev<S>(ctx, n, data, data_off, input, flags + (NP + 1) * n));
+  ST(pedersen_verify_dev<S>(ctx, n, input, output, proof256, ad, ad_off, out_ok, out_status));
+  k_merge_flags<<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, flags + NP * n, NP == 4 ? flags + (NP + 1) * n : nullptr, out_ok, nullptr, 0u, out_status);
   LAUNCHED_AS(ctx, "merge_flags");
   return VRFS_OK;
 }
 extern "C" vrfs_status vrfs_pedersen_verify_wire_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* data, const uint64_t* data_off, const uint8_t* sig,
-                                                       const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_ok) {
+                                                       const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_ok, uint8_t* out_status) {
   if (!ctx) return VRFS_BAD_ARG;
-  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
+  CallGuard guard_(ctx);
   if (n == 0) return VRFS_OK;
   if (!data_off || !sig || !out_ok) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
   ST(begin_call(ctx, n));
   const size_t sl = (size_t)vrfs_suite_pedersen_signature_len(suite);
   const uint8_t *d_sig, *d_ad, *d_data; const uint64_t *d_off, *d_doff;
-  uint8_t *d_in, *d_out, *d_pr, *d_flags, *d_ok;
+  uint8_t *d_in, *d_out, *d_pr, *d_flags, *d_ok, *d_st = nullptr;
   ST(stage_in(ctx, BUF_X1, sig, n * sl, &d_sig));
   ST(stage_ad(ctx, n, ad, ad_off, &d_ad, &d_off));
-  for (size_t i = 0; i < n; i++) if (data_off[i + 1] < data_off[i]) return fail(ctx, VRFS_BAD_ARG, "offsets must be non-decreasing");
-  if (data_off[n] > 0 && !data) return fail(ctx, VRFS_BAD_ARG, "null data buffer with non-empty offsets");
-  { const uint8_t* o; ST(stage_in(ctx, BUF_X2, data, (size_t)data_off[n], &d_data)); ST(stage_in(ctx, BUF_X3, data_off, (n + 1) * sizeof(uint64_t), &o)); d_doff = (const uint64_t*)o; }
+  ST(stage_var(ctx, BUF_X2, BUF_X3, n, data, data_off, &d_data, &d_doff));
   ST(stage_out(ctx, BUF_IN0, n * 64, &d_in)); ST(stage_out(ctx, BUF_IN1, n * 64, &d_out)); ST(stage_out(ctx, BUF_IN2, n * 256, &d_pr));
   ST(stage_out(ctx, BUF_X4, 6 * n, &d_flags)); ST(stage_out(ctx, BUF_OUT0, n, &d_ok));
-  ST(suite == VRFS_BANDERSNATCH_ELL2 ? pedersen_verify_wire_dev<BandSuite>(ctx, n, d_data, d_doff, d_sig, d_ad, d_off, d_in, d_out, d_pr, d_flags, d_ok)
-     : suite == VRFS_ED25519_TAI ? pedersen_verify_wire_dev<EdSuite>(ctx, n, d_data, d_doff, d_sig, d_ad, d_off, d_in, d_out, d_pr, d_flags, d_ok)
-                                 : pedersen_verify_wire_dev<P256Suite>(ctx, n, d_data, d_doff, d_sig, d_ad, d_off, d_in, d_out, d_pr, d_flags, d_ok));
+  if (out_status) ST(stage_out(ctx, BUF_OUT1, n, &d_st));
+  ST(suite == VRFS_BANDERSNATCH_ELL2 ? (pedersen_verify_wire_dev<BandSuite, 4>(ctx, n, d_data, d_doff, d_sig, d_ad, d_off, d_in, d_out, d_pr, d_flags, d_ok, d_st))
+     : suite == VRFS_ED25519_TAI ? (pedersen_verify_wire_dev<EdSuite, 4>(ctx, n, d_data, d_doff, d_sig, d_ad, d_off, d_in, d_out, d_pr, d_flags, d_ok, d_st))
+                                 : (pedersen_verify_wire_dev<P256Suite, 4>(ctx, n, d_data, d_doff, d_sig, d_ad, d_off, d_in, d_out, d_pr, d_flags, d_ok, d_st)));
   ST(copy_out(ctx, out_ok, d_ok, n));
+  if (out_status) ST(copy_out(ctx, out_status, d_st, n));
+  return finish_call(ctx);
+}
+
+// ---- the typed pedersen::Proof in its serialised form (3 encoded points + 2 scalars: 160 B for Bandersnatch) ----
+template <class S> static vrfs_status pedersen_prove_compressed_dev(vrfs_ctx* ctx, size_t n, const uint8_t* sk, const uint8_t* input, const uint8_t* output, const uint8_t* ad,
+                                                                    const uint64_t* ad_off, uint8_t* proof256, uint8_t* blinding, uint8_t* out) {
+  ST(pedersen_prove_dev<S>(ctx, n, sk, input, output, ad, ad_off, proof256, blinding));
+  k_ped_wire_pack<S, 3><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, nullptr, proof256, nullptr, out);
+  LAUNCHED_AS(ctx, "ped_wire_pack");
+  return VRFS_OK;
+}
+extern "C" vrfs_status vrfs_pedersen_prove_compressed_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* sk, const uint8_t* input, const uint8_t* output,
+                                                            const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_proof, uint8_t* out_blinding) {
+  if (!ctx) return VRFS_BAD_ARG;
+  CallGuard guard_(ctx);
+  if (n == 0) return VRFS_OK;
+  if (!sk || !input || !output || !out_proof || !out_blinding) return fail(ctx, VRFS_BAD_ARG, "null buffer");
+  if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
+  ST(begin_call(ctx, n));
+  const size_t pl = (size_t)vrfs_suite_pedersen_proof_len(suite);
+  const uint8_t *d_sk, *d_in, *d_out, *d_ad; const uint64_t* d_off; uint8_t *d_pr, *d_bl, *d_enc;
+  ST(stage_secret(ctx, BUF_IN0, sk, n * 32, &d_sk)); ST(stage_in(ctx, BUF_IN1, input, n * 64, &d_in)); ST(stage_in(ctx, BUF_IN2, output, n * 64, &d_out));
+  ST(stage_ad(ctx, n, ad, ad_off, &d_ad, &d_off));
+  ST(stage_out(ctx, BUF_OUT0, n * 256, &d_pr)); ST(stage_out(ctx, BUF_OUT1, n * 32, &d_bl)); ST(stage_out(ctx, BUF_X1, n * pl, &d_enc));
+  mark_secret(ctx, BUF_OUT1, n * 32);
+  ST(suite == VRFS_BANDERSNATCH_ELL2 ? pedersen_prove_compressed_dev<BandSuite>(ctx, n, d_sk, d_in, d_out, d_ad, d_off, d_pr, d_bl, d_enc)
+     : suite == VRFS_ED25519_TAI ? pedersen_prove_compressed_dev<EdSuite>(ctx, n, d_sk, d_in, d_out, d_ad, d_off, d_pr, d_bl, d_enc)
+                                 : pedersen_prove_compressed_dev<P256Suite>(ctx, n, d_sk, d_in, d_out, d_ad, d_off, d_pr, d_bl, d_enc));
+  ST(copy_out(ctx, out_proof, d_enc, n * pl)); ST(copy_out(ctx, out_blinding, d_bl, n * 32));
+  return finish_call(ctx);
+}
+extern "C" vrfs_status vrfs_pedersen_verify_compressed_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* input, const uint8_t* output, const uint8_t* proof,
+                                                             const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_ok, uint8_t* out_status) {
+  if (!ctx) return VRFS_BAD_ARG;
+  CallGuard guard_(ctx);
+  if (n == 0) return VRFS_OK;
+  if (!input || !output || !proof || !out_ok) return fail(ctx, VRFS_BAD_ARG, "null buffer");
+  if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
+  ST(begin_call(ctx, n));
+  const size_t pl = (size_t)vrfs_suite_pedersen_proof_len(suite);
+  const uint8_t *d_enc, *d_ad, *d_in, *d_out; const uint64_t* d_off;
+  uint8_t *d_pr, *d_flags, *d_ok, *d_st = nullptr;
+  ST(stage_in(ctx, BUF_X1, proof, n * pl, &d_enc));
+  ST(stage_in(ctx, BUF_IN0, input, n * 64, &d_in)); ST(stage_in(ctx, BUF_IN1, output, n * 64, &d_out));
+  ST(stage_ad(ctx, n, ad, ad_off, &d_ad, &d_off));
+  ST(stage_out(ctx, BUF_IN2, n * 256, &d_pr)); ST(stage_out(ctx, BUF_X4, 5 * n, &d_flags)); ST(stage_out(ctx, BUF_OUT0, n, &d_ok));
+  if (out_status) ST(stage_out(ctx, BUF_OUT1, n, &d_st));
+  uint8_t *m_in = const_cast<uint8_t*>(d_in), *m_out = const_cast<uint8_t*>(d_out);
+  ST(suite == VRFS_BANDERSNATCH_ELL2 ? (pedersen_verify_wire_dev<BandSuite, 3>(ctx, n, nullptr, nullptr, d_enc, d_ad, d_off, m_in, m_out, d_pr, d_flags, d_ok, d_st))
+     : suite == VRFS_ED25519_TAI ? (pedersen_verify_wire_dev<EdSuite, 3>(ctx, n, nullptr, nullptr, d_enc, d_ad, d_off, m_in, m_out, d_pr, d_flags, d_ok, d_st))
+                                 : (pedersen_verify_wire_dev<P256Suite, 3>(ctx, n, nullptr, nullptr, d_enc, d_ad, d_off, m_in, m_out, d_pr, d_flags, d_ok, d_st)));
+  ST(copy_out(ctx, out_ok, d_ok, n));
+  if (out_status) ST(copy_out(ctx, out_status, d_st, n));
   return finish_call(ctx);
 }
 
@@ -1301,7 +1469,7 @@ static MsmPlan plan_for(const vrfs_msm_bases* h, int n_columns) {
   return msm_plan((uint32_t)h->n, (uint32_t)n_columns, 1, h->plan.c, h->tpb_hint);
 }
 // bases: G1Aff[n] (stateless) or the prepared table Q; scalars on the device
-static vrfs_status msm_dev(vrfs_ctx* ctx, MsmPlan p, const void* d_bases, const uint8_t* d_scalars, uint8_t* d_out, int out_mode) {
+static vrfs_status msm_dev(vrfs_ctx* ctx, MsmPlan p, const void* d_bases, const uint8_t* d_scalars, uint8_t* d_out, int out_mode, const PeerArgs* peer = nullptr) {
   const size_t n = p.n, ncol = p.ncol;
   const size_t segs = ncol * p.seg_windows, nbuckets = segs * p.nb, seg_len = n * (p.prepared ? p.windows : 1);
   void *counts = nullptr, *list = nullptr, *buckets = nullptr, *wsum = nullptr;
@@ -1347,13 +1515,15 @@ static vrfs_status msm_dev(vrfs_ctx* ctx, MsmPlan p, const void* d_bases, const 
   }
   k_msm_wsum<<<dim3(MSM_WSUM_CLUSTER, nparts, (unsigned)segs), 128, 0, ctx->stream>>>(p, p.rc_h ? (const G1Pt*)rc_out : (const G1Pt*)buckets, wscratch, (G1Pt*)wsum);
   LAUNCHED_AS(ctx, "msm_wsum");
-  k_msm_final2<<<(unsigned)ncol, 32, 0, ctx->stream>>>(p, (int)nparts, (const G1Pt*)wsum, d_out, out_mode);
+  PeerArgs pa = {};
+  if (out_mode == 2) { if (!peer) return fail(ctx, VRFS_BAD_ARG, "internal: peer exchange without a peer group"); pa = *peer; }
+  k_msm_final2<<<(unsigned)ncol, 32, 0, ctx->stream>>>(p, (int)nparts, (const G1Pt*)wsum, d_out, out_mode, pa);
   LAUNCHED_AS(ctx, "msm_final");
   return VRFS_OK;
 }
 static vrfs_status msm_host(vrfs_ctx* ctx, size_t n, const uint8_t* bases, const uint8_t* scalars, int ncol, uint8_t* out, int out_mode) {
   if (!ctx) return VRFS_BAD_ARG;
-  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
+  CallGuard guard_(ctx);
   if (ncol < 1 || ncol > 32) return fail(ctx, VRFS_BAD_ARG, "n_columns must be in 1..32");
   if (!out || (n && (!bases || !scalars))) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   const size_t ob = out_mode ? 144 : 96;
@@ -1383,7 +1553,7 @@ extern "C" vrfs_status vrfs_msm_g1_partial(vrfs_ctx* ctx, size_t n, const uint8_
 }
 static vrfs_status msm_prepare_impl(vrfs_ctx* ctx, size_t n, const uint8_t* bases, int window_bits, int threads_per_bucket, vrfs_msm_bases** out) {
   if (!ctx || !out) return VRFS_BAD_ARG;
-  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
+  CallGuard guard_(ctx);
   *out = nullptr;
   if (n == 0 || !bases) return fail(ctx, VRFS_BAD_ARG, "empty base vector");
   if (n > (1u << 24)) return fail(ctx, VRFS_BAD_ARG, "prepared MSM size above 2^24 is not supported");
@@ -1428,7 +1598,7 @@ extern "C" void vrfs_msm_g1_release(vrfs_msm_bases* h) {
   vrfs_ctx* ctx;
   { std::lock_guard<std::mutex> g(g_handles_mu); ctx = h->ctx; }
   if (ctx) {
-    std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
+    CallGuard guard_(ctx);
     std::lock_guard<std::mutex> g(g_handles_mu);
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
@@ -1445,7 +1615,7 @@ static void orphan_prepared(vrfs_ctx* ctx) {      // called by vrfs_ctx_destroy 
 }
 static vrfs_status msm_prepared_host(vrfs_ctx* ctx, const vrfs_msm_bases* h, const uint8_t* scalars, int n_columns, uint8_t* out, int out_mode) {
   if (!ctx || !h || h->ctx != ctx) return VRFS_BAD_ARG;
-  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
+  CallGuard guard_(ctx);
   if (n_columns < 1 || n_columns > 32 || !scalars || !out) return fail(ctx, VRFS_BAD_ARG, "bad argument");
   ST(begin_call(ctx, h->n));
   const size_t ob = out_mode ? 144 : 96;
@@ -1491,7 +1661,7 @@ static vrfs_status ntt_dev(vrfs_ctx* ctx, int logn, uint32_t ncol, int inverse, 
 }
 extern "C" vrfs_status vrfs_fr_fft_batch(vrfs_ctx* ctx, int log_n, int n_columns, int inverse, const uint8_t* in, uint8_t* out) {
   if (!ctx) return VRFS_BAD_ARG;
-  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
+  CallGuard guard_(ctx);
   if (log_n < 0 || log_n > 26 || n_columns < 1 || n_columns > 32 || !in || !out) return fail(ctx, VRFS_BAD_ARG, "bad argument (0 <= log_n <= 26, 1 <= n_columns <= 32)");
   const size_t bytes = ((size_t)n_columns << log_n) * 32;
   ST(begin_call(ctx, (size_t)1 << log_n));
@@ -1524,7 +1694,7 @@ static vrfs_status ring_columns_dev(vrfs_ctx* ctx, size_t n, size_t keyset_part,
 extern "C" vrfs_status vrfs_ring_fixed_columns(vrfs_ctx* ctx, size_t domain_size, size_t keyset_part_size, size_t n_keys, const uint8_t* keys,
                                                const uint8_t* padding, size_t n_tail, const uint8_t* tail, uint8_t* out_columns) {
   if (!ctx) return VRFS_BAD_ARG;
-  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
+  CallGuard guard_(ctx);
   if (!out_columns) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   ST(begin_call(ctx, domain_size));
   uint8_t* d_cols = nullptr;
@@ -1535,7 +1705,7 @@ extern "C" vrfs_status vrfs_ring_fixed_columns(vrfs_ctx* ctx, size_t domain_size
 extern "C" vrfs_status vrfs_ring_commit(vrfs_ctx* ctx, const vrfs_msm_bases* srs, int srs_is_lagrange, size_t keyset_part_size, size_t n_keys,
                                         const uint8_t* keys, const uint8_t* padding, size_t n_tail, const uint8_t* tail, uint8_t* out_commitment) {
   if (!ctx || !srs || srs->ctx != ctx) return VRFS_BAD_ARG;
-  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
+  CallGuard guard_(ctx);
   if (!out_commitment) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   const size_t n = srs->n;
   ST(begin_call(ctx, n));
@@ -1555,7 +1725,7 @@ extern "C" vrfs_status vrfs_ring_commit(vrfs_ctx* ctx, const vrfs_msm_bases* srs
 extern "C" vrfs_status vrfs_ring_commit_rows_partial(vrfs_ctx* ctx, const vrfs_msm_bases* srs_rows, size_t row_lo, size_t keyset_part_size, size_t n_keys,
                                                      const uint8_t* keys_rows, const uint8_t* padding, size_t n_tail, const uint8_t* tail, uint8_t* out_partial) {
   if (!ctx || !srs_rows || srs_rows->ctx != ctx) return VRFS_BAD_ARG;
-  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
+  CallGuard guard_(ctx);
   if (!out_partial) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   const size_t n = srs_rows->n;
   ST(begin_call(ctx, n));
@@ -1571,7 +1741,7 @@ extern "C" vrfs_status vrfs_ring_commit_rows_partial(vrfs_ctx* ctx, const vrfs_m
 extern "C" vrfs_status vrfs_ring_commit_delta(vrfs_ctx* ctx, const vrfs_msm_bases* srs_lagrange, size_t n_keys, const uint8_t* keys,
                                               const uint8_t* padding, uint8_t* out_delta) {
   if (!ctx || !srs_lagrange || srs_lagrange->ctx != ctx) return VRFS_BAD_ARG;
-  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
+  CallGuard guard_(ctx);
   const size_t n = srs_lagrange->n;
   if (!out_delta || !padding || (n_keys && !keys) || n_keys > n) return fail(ctx, VRFS_BAD_ARG, "bad argument (n_keys <= domain size, non-null buffers)");
   ST(begin_call(ctx, n));
@@ -1589,7 +1759,7 @@ extern "C" vrfs_status vrfs_ring_commit_delta(vrfs_ctx* ctx, const vrfs_msm_base
 }
 extern "C" vrfs_status vrfs_g1_compress_batch(vrfs_ctx* ctx, size_t n, const uint8_t* points, uint8_t* out) {
   if (!ctx) return VRFS_BAD_ARG;
-  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
+  CallGuard guard_(ctx);
   if (n && (!points || !out)) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if (n == 0) return VRFS_OK;
   ST(begin_call(ctx, n));
@@ -1603,7 +1773,7 @@ extern "C" vrfs_status vrfs_g1_compress_batch(vrfs_ctx* ctx, size_t n, const uin
 }
 extern "C" vrfs_status vrfs_g1_decompress_batch(vrfs_ctx* ctx, size_t n, const uint8_t* enc, int check_subgroup, uint8_t* out_points, uint8_t* out_ok) {
   if (!ctx) return VRFS_BAD_ARG;
-  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
+  CallGuard guard_(ctx);
   if (n && (!enc || !out_points || !out_ok)) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if (n == 0) return VRFS_OK;
   ST(begin_call(ctx, n));
@@ -1630,7 +1800,7 @@ __global__ void k_fq381_inv_batch(uint32_t n, const uint8_t* in, uint8_t* out, u
 }
 extern "C" vrfs_status vrfs_fq381_inv_batch(vrfs_ctx* ctx, size_t n, const uint8_t* in, uint8_t* out, uint8_t* out_ok) {
   if (!ctx) return VRFS_BAD_ARG;
-  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
+  CallGuard guard_(ctx);
   if (n && (!in || !out || !out_ok)) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if (n == 0) return VRFS_OK;
   ST(begin_call(ctx, n));
@@ -1644,7 +1814,7 @@ extern "C" vrfs_status vrfs_fq381_inv_batch(vrfs_ctx* ctx, size_t n, const uint8
 }
 extern "C" vrfs_status vrfs_g1_sum_partials(vrfs_ctx* ctx, int n_parts, int n_columns, const uint8_t* partials, uint8_t* out) {
   if (!ctx) return VRFS_BAD_ARG;
-  std::lock_guard<std::recursive_mutex> lock_(ctx->mu);
+  CallGuard guard_(ctx);
   if (n_parts < 1 || n_columns < 1 || n_columns > 32 || !partials || !out) return fail(ctx, VRFS_BAD_ARG, "bad argument");
   ST(begin_call(ctx, 1));
   const uint8_t* d_p; uint8_t* d_o;
@@ -1655,3 +1825,5 @@ extern "C" vrfs_status vrfs_g1_sum_partials(vrfs_ctx* ctx, int n_parts, int n_co
   ST(copy_out(ctx, out, d_o, (size_t)96 * n_columns));
   return finish_call(ctx);
 }
+
+#include "multi_gpu.cuh"

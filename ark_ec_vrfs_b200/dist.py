@@ -2,8 +2,12 @@
 
 VRF batches are independent items: rank g takes the contiguous index range [g*n/G, (g+1)*n/G) and there is
 NO data-path collective.  The MSM splits by point range; each rank produces one projective partial per
-column (144 bytes) and the only exchange is an all-gather of those bytes (NCCL on GPU boxes, gloo in the
-CPU tests), folded by `Engine.g1_sum_partials`."""
+column (144 bytes).  On GPU boxes the partials are exchanged INSIDE the MSM's last kernel: `connect_peers`
+all-gathers the ranks' 64-byte CUDA IPC mailbox handles once (host side, torch.distributed), after which
+`ShardedPreparedBases.msm` / `ShardedRingContext.verifier_key_commitment` are single C-ABI calls whose final
+kernel stores the partial into every peer's device memory over NVLink, waits for the peers' flags and folds
+(vrfs_msm_g1_prepared_allgather / vrfs_ring_commit_rows_allgather).  Without a peer group (the gloo CPU
+tests, or GPUs without peer access) the partials go through a host all-gather and `Engine.g1_sum_partials`."""
 import numpy as np
 
 
@@ -38,6 +42,26 @@ def gather_bytes(local: np.ndarray, group=None, device=None):
     return np.stack([o.cpu().numpy() for o in outs])
 
 
+def connect_peers(engine, group=None):
+    """one-time setup of the device-side exchange: every rank exports its mailbox, the handles are all-gathered over
+    torch.distributed (host objects), every rank maps its peers.  Returns True when the peer group is up; False (and the
+    callers below fall back to the host all-gather) when the GPUs cannot map each other."""
+    import torch.distributed as dist
+    from ._lib import VrfsError
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    h = engine.peer_export(rank, world)
+    handles = [None] * world
+    dist.all_gather_object(handles, h.tobytes(), group=group)
+    ok = True
+    try:
+        engine.peer_connect(np.frombuffer(b"".join(handles), np.uint8))
+    except VrfsError:
+        ok = False
+    flags = [None] * world
+    dist.all_gather_object(flags, ok, group=group)          # all or nothing: a collective needs every rank
+    return all(flags)
+
+
 def msm_g1_sharded(engine, bases, scalars, n_columns, group=None, device=None):
     """each rank passes the FULL inputs; computes its point range; all ranks return the same affine result"""
     import torch.distributed as dist
@@ -61,9 +85,23 @@ class ShardedPreparedBases:
         self.n = len(bases)
         self.lo, self.hi = shard_range(self.n, self.rank, self.world)
         self.handle = engine.msm_g1_prepare(bases[self.lo:self.hi])
+        self.device_exchange = engine.peer_world == self.world      # connect_peers was called for this group
+
+    def local_scalars(self, scalars, n_columns=1):
+        """this rank's slice of column-major scalars (what a caller that already shards its data would hold)"""
+        return np.ascontiguousarray(np.asarray(scalars, np.uint8).reshape(n_columns, self.n, 32)[:, self.lo:self.hi]).reshape(-1, 32)
+
+    def msm_local(self, local_scalars, n_columns=1):
+        """COLLECTIVE: the full commitments from each rank's own slice of the scalars"""
+        if self.device_exchange:
+            return self.handle.msm_allgather(local_scalars, n_columns)
+        part = self.handle.msm_partial(local_scalars, n_columns)
+        return self.engine.g1_sum_partials(gather_bytes(part, self.group, self.device), n_columns)
 
     def msm(self, scalars, n_columns=1):
-        sc = np.asarray(scalars, np.uint8).reshape(n_columns, self.n, 32)[:, self.lo:self.hi].reshape(-1, 32)
+        sc = self.local_scalars(scalars, n_columns)
+        if self.device_exchange:
+            return self.handle.msm_allgather(sc, n_columns)
         part = self.handle.msm_partial(sc, n_columns)
         parts = gather_bytes(part, self.group, self.device)
         return self.engine.g1_sum_partials(parts, n_columns)
@@ -100,6 +138,8 @@ class ShardedRingContext:
     def verifier_key_commitment(self, public_keys):
         b = self.bases
         keys = np.asarray(public_keys, np.uint8).reshape(-1, 64)
+        if b.device_exchange:
+            return b.handle.ring_commit_rows_allgather(b.lo, self.keyset_part_size, len(keys), keys[b.lo:b.hi], self.padding, self.tail)
         part = b.handle.ring_commit_rows_partial(b.lo, self.keyset_part_size, len(keys), keys[b.lo:b.hi], self.padding, self.tail)
         return b.engine.g1_sum_partials(gather_bytes(part, b.group, b.device), 3)
 

@@ -19,15 +19,26 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
-def pack_var(items):
-    """list of bytes -> (uint8 data, uint64 offsets[n+1]); `items` may already be such a pair, or None."""
+ITEM_OK, ITEM_VERIFICATION_FAILURE, ITEM_INVALID_DATA = 0, 1, 2      # vrfs_item_status: Ok(()) / Error::VerificationFailure / Error::InvalidData
+
+
+def pack_var(items, n=None):
+    """list of bytes -> (uint8 data, uint64 offsets[n+1]); `items` may already be such a pair, or None.
+    n: the batch size the C side will read offsets for - a shorter list would make it read past the arrays, so it is an error here."""
     if items is None:
         return None, None
     if isinstance(items, tuple):
-        return items
-    off = np.zeros(len(items) + 1, dtype=np.uint64)
-    off[1:] = np.cumsum([len(b) for b in items], dtype=np.uint64)
-    data = np.frombuffer(b"".join(items), dtype=np.uint8).copy() if off[-1] else np.zeros(16, dtype=np.uint8)
+        data, off = items
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        data = np.ascontiguousarray(data if data is not None else np.zeros(16, np.uint8), dtype=np.uint8).reshape(-1)
+    else:
+        off = np.zeros(len(items) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(b) for b in items], dtype=np.uint64)
+        data = np.frombuffer(b"".join(items), dtype=np.uint8).copy() if off[-1] else np.zeros(16, dtype=np.uint8)
+    if n is not None and len(off) - 1 != n:
+        raise ValueError(f"{len(off) - 1} variable-length items for a batch of {n}")
+    if len(off) and int(off[-1]) > data.size:
+        raise ValueError("offsets run past the data buffer")
     return data, off
 
 
@@ -57,6 +68,20 @@ class PreparedBases:
         """this handle = the prepared Lagrange bases of rows [row_lo, row_lo + n): projective partial commitments (3, 144) of those rows"""
         keys_rows = _u8(keys_rows, (-1, 64)); tail = _u8(tail, (-1, 64)); padding = _u8(padding, (64,)); out = np.zeros((3, 144), np.uint8)
         self.engine._call("vrfs_ring_commit_rows_partial", self.handle, C.c_size_t(row_lo), C.c_size_t(keyset_part_size), C.c_size_t(n_keys), _p(keys_rows),
+                          _p(padding), C.c_size_t(len(tail)), _p(tail), _p(out))
+        return out
+
+    def msm_allgather(self, scalars, n_columns=1):
+        """COLLECTIVE over the engine's peer group: this rank's scalars over its slice of the SRS -> the full commitments
+        (n_columns, 96) on every rank; the partials travel GPU to GPU inside the MSM's last kernel (vrfs_msm_g1_prepared_allgather)"""
+        scalars = _u8(scalars, (n_columns * self.n, 32)); out = np.zeros((n_columns, 96), np.uint8)
+        self.engine._call("vrfs_msm_g1_prepared_allgather", self.handle, _p(scalars), int(n_columns), _p(out))
+        return out
+
+    def ring_commit_rows_allgather(self, row_lo, keyset_part_size, n_keys, keys_rows, padding, tail):
+        """COLLECTIVE: the ring commitment (3, 96) with the domain's rows split over the ranks (vrfs_ring_commit_rows_allgather)"""
+        keys_rows = _u8(keys_rows, (-1, 64)); tail = _u8(tail, (-1, 64)); padding = _u8(padding, (64,)); out = np.zeros((3, 96), np.uint8)
+        self.engine._call("vrfs_ring_commit_rows_allgather", self.handle, C.c_size_t(row_lo), C.c_size_t(keyset_part_size), C.c_size_t(n_keys), _p(keys_rows),
                           _p(padding), C.c_size_t(len(tail)), _p(tail), _p(out))
         return out
 
@@ -124,24 +149,49 @@ class Engine:
     def stream(self):
         return self._lib.vrfs_ctx_stream(self._ctx)
 
+    # ---- peer group (one process per GPU): device-side exchange of MSM partials over NVLink
+    def peer_export(self, rank, world):
+        """allocate this rank's mailbox; returns its 64-byte CUDA IPC handle (to be all-gathered by the caller)"""
+        h = np.zeros(64, np.uint8)
+        self._call("vrfs_ctx_peer_export", int(rank), int(world), _p(h))
+        return h
+
+    def peer_connect(self, handles):
+        handles = _u8(handles, (-1, 64))
+        self._call("vrfs_ctx_peer_connect", _p(handles))
+
+    def peer_set_timeout_ms(self, ms):
+        self._call("vrfs_ctx_peer_set_timeout_ms", C.c_uint(int(ms)))
+
+    @property
+    def peer_world(self):
+        return int(self._lib.vrfs_ctx_peer_world(self._ctx))
+
     # ---- ietf
-    def ietf_verify(self, suite, pk, inp, outp, c, s, ad=None):
+    def ietf_verify(self, suite, pk, inp, outp, c, s, ad=None, status=False):
+        """ietf::Verifier::verify -> ok flags; status=True: (ok, vrfs_item_status per item)"""
         pk = _u8(pk, (-1, 64)); n = len(pk)
         inp = _u8(inp, (n, 64)); outp = _u8(outp, (n, 64)); c = _u8(c, (n, 32)); s = _u8(s, (n, 32))
-        adb, off = pack_var(ad)
-        ok = np.zeros(n, np.uint8)
-        self._check(self._lib.vrfs_ietf_verify_batch(self._ctx, suite, C.c_size_t(n), _p(pk), _p(inp), _p(outp), _p(c), _p(s), _p(adb), _p(off), _p(ok)))
-        return ok
+        adb, off = pack_var(ad, n)
+        ok = np.zeros(n, np.uint8); st = np.zeros(n, np.uint8) if status else None
+        self._check(self._lib.vrfs_ietf_verify_batch(self._ctx, suite, C.c_size_t(n), _p(pk), _p(inp), _p(outp), _p(c), _p(s), _p(adb), _p(off), _p(ok), _p(st)))
+        return (ok, st) if status else ok
 
-    def ietf_verify_dev(self, suite, n, d_pk, d_inp, d_outp, d_c, d_s, d_ok, d_ad=None, d_off=None):
+    def ietf_verify_dev(self, suite, n, d_pk, d_inp, d_outp, d_c, d_s, d_ok, d_ad=None, d_off=None, d_status=None):
         """device pointers (ints); enqueues on the context stream, returns immediately"""
         v = lambda x: C.c_void_p(x) if x else None
-        self._check(self._lib.vrfs_ietf_verify_batch_dev(self._ctx, suite, C.c_size_t(n), v(d_pk), v(d_inp), v(d_outp), v(d_c), v(d_s), v(d_ad), v(d_off), v(d_ok)))
+        self._check(self._lib.vrfs_ietf_verify_batch_dev(self._ctx, suite, C.c_size_t(n), v(d_pk), v(d_inp), v(d_outp), v(d_c), v(d_s), v(d_ad), v(d_off), v(d_ok), v(d_status)))
 
-    def ietf_verify_host_ptrs(self, suite, n, pk, inp, outp, c, s, ok, ad=None, off=None):
+    def ietf_verify_host_ptrs(self, suite, n, pk, inp, outp, c, s, ok, ad=None, off=None, status=None):
         """raw host pointers (ints), e.g. of pinned torch tensors; synchronous"""
         v = lambda x: C.c_void_p(x) if x else None
-        self._check(self._lib.vrfs_ietf_verify_batch(self._ctx, suite, C.c_size_t(n), v(pk), v(inp), v(outp), v(c), v(s), v(ad), v(off), v(ok)))
+        self._check(self._lib.vrfs_ietf_verify_batch(self._ctx, suite, C.c_size_t(n), v(pk), v(inp), v(outp), v(c), v(s), v(ad), v(off), v(ok), v(status)))
+
+    def debug_read_staging(self, slot, nbytes, offset=0):
+        """test hook (vrfs_ctx_debug_read_staging): bytes of an internal staging buffer after a call returned"""
+        out = np.zeros(nbytes, np.uint8)
+        self._call("vrfs_ctx_debug_read_staging", int(slot), C.c_size_t(offset), _p(out), C.c_size_t(nbytes))
+        return out
 
     # ---- keys, inputs, outputs (Secret / Public / Input / Output of the reference API)
     def _call(self, fn, *args):
@@ -158,6 +208,8 @@ class Engine:
 
     def secret_from_seed(self, suite, seeds, want_pk=True):
         data, off = pack_var(seeds); n = len(off) - 1
+        if data is None:
+            raise ValueError("seeds are required")
         sk = np.zeros((n, 32), np.uint8); pk = np.zeros((n, 64), np.uint8) if want_pk else None
         self._call("vrfs_secret_from_seed_batch", suite, C.c_size_t(n), _p(data), _p(off), _p(sk), _p(pk))
         return (sk, pk) if want_pk else sk
@@ -196,7 +248,7 @@ class Engine:
 
     def ietf_prove(self, suite, sk, inp, outp, ad=None):
         sk = _u8(sk, (-1, 32)); n = len(sk); inp = _u8(inp, (n, 64)); outp = _u8(outp, (n, 64))
-        adb, off = pack_var(ad)
+        adb, off = pack_var(ad, n)
         c = np.zeros((n, 32), np.uint8); s = np.zeros((n, 32), np.uint8)
         self._call("vrfs_ietf_prove_batch", suite, C.c_size_t(n), _p(sk), _p(inp), _p(outp), _p(adb), _p(off), _p(c), _p(s))
         return c, s
@@ -219,49 +271,71 @@ class Engine:
 
     def ietf_sign_wire(self, suite, sk, datas, ad=None):
         """signature_i = point_encode(Output) || c || s for Input::new(datas[i]); returns (sig (n, sig_len), ok)."""
-        sk = _u8(sk, (-1, 32)); n = len(sk); data, doff = pack_var(datas); adb, off = pack_var(ad)
+        sk = _u8(sk, (-1, 32)); n = len(sk); data, doff = pack_var(datas, n); adb, off = pack_var(ad, n)
         sig = np.zeros((n, self.ietf_signature_len(suite)), np.uint8); ok = np.zeros(n, np.uint8)
         self._call("vrfs_ietf_sign_wire_batch", suite, C.c_size_t(n), _p(sk), _p(data), _p(doff), _p(adb), _p(off), _p(sig), _p(ok))
         return sig, ok
 
-    def ietf_verify_wire(self, suite, pk_enc, datas, sig, ad=None, want_hash=True):
-        """serialised public keys + VRF input data + signatures -> (ok, beta) with beta = Output::hash of accepted items."""
+    def ietf_verify_wire(self, suite, pk_enc, datas, sig, ad=None, want_hash=True, status=False):
+        """serialised public keys + VRF input data + signatures -> (ok, beta) with beta = Output::hash of accepted items
+        (status=True appends the per-item vrfs_item_status)."""
         pk_enc = _u8(pk_enc, (-1, self.point_enc_len(suite))); n = len(pk_enc)
-        sig = _u8(sig, (n, self.ietf_signature_len(suite))); data, doff = pack_var(datas); adb, off = pack_var(ad)
+        sig = _u8(sig, (n, self.ietf_signature_len(suite))); data, doff = pack_var(datas, n); adb, off = pack_var(ad, n)
         ok = np.zeros(n, np.uint8); h = np.zeros((n, self.hash_len(suite)), np.uint8) if want_hash else None
-        self._call("vrfs_ietf_verify_wire_batch", suite, C.c_size_t(n), _p(pk_enc), _p(data), _p(doff), _p(sig), _p(adb), _p(off), _p(ok), _p(h))
-        return (ok, h) if want_hash else ok
+        st = np.zeros(n, np.uint8) if status else None
+        self._call("vrfs_ietf_verify_wire_batch", suite, C.c_size_t(n), _p(pk_enc), _p(data), _p(doff), _p(sig), _p(adb), _p(off), _p(ok), _p(h), _p(st))
+        res = (ok, h) if want_hash else (ok,)
+        res = res + (st,) if status else res
+        return res if len(res) > 1 else res[0]
 
     def pedersen_signature_len(self, suite):
         return int(self._lib.vrfs_suite_pedersen_signature_len(suite))
 
     def pedersen_sign_wire(self, suite, sk, datas, ad=None):
         """Output || pedersen::Proof serialised (4 encoded points + 2 scalars); returns (sig, blinding, ok)"""
-        sk = _u8(sk, (-1, 32)); n = len(sk); data, doff = pack_var(datas); adb, off = pack_var(ad)
+        sk = _u8(sk, (-1, 32)); n = len(sk); data, doff = pack_var(datas, n); adb, off = pack_var(ad, n)
         sig = np.zeros((n, self.pedersen_signature_len(suite)), np.uint8); bl = np.zeros((n, 32), np.uint8); ok = np.zeros(n, np.uint8)
         self._call("vrfs_pedersen_sign_wire_batch", suite, C.c_size_t(n), _p(sk), _p(data), _p(doff), _p(adb), _p(off), _p(sig), _p(bl), _p(ok))
         return sig, bl, ok
 
-    def pedersen_verify_wire(self, suite, datas, sig, ad=None):
-        sig = _u8(sig, (-1, self.pedersen_signature_len(suite))); n = len(sig); data, doff = pack_var(datas); adb, off = pack_var(ad)
-        ok = np.zeros(n, np.uint8)
-        self._call("vrfs_pedersen_verify_wire_batch", suite, C.c_size_t(n), _p(data), _p(doff), _p(sig), _p(adb), _p(off), _p(ok))
-        return ok
+    def pedersen_verify_wire(self, suite, datas, sig, ad=None, status=False):
+        sig = _u8(sig, (-1, self.pedersen_signature_len(suite))); n = len(sig); data, doff = pack_var(datas, n); adb, off = pack_var(ad, n)
+        ok = np.zeros(n, np.uint8); st = np.zeros(n, np.uint8) if status else None
+        self._call("vrfs_pedersen_verify_wire_batch", suite, C.c_size_t(n), _p(data), _p(doff), _p(sig), _p(adb), _p(off), _p(ok), _p(st))
+        return (ok, st) if status else ok
 
     # ---- pedersen
     def pedersen_prove(self, suite, sk, inp, outp, ad=None):
         sk = _u8(sk, (-1, 32)); n = len(sk); inp = _u8(inp, (n, 64)); outp = _u8(outp, (n, 64))
-        adb, off = pack_var(ad)
+        adb, off = pack_var(ad, n)
         proof = np.zeros((n, 256), np.uint8); bl = np.zeros((n, 32), np.uint8)
         self._call("vrfs_pedersen_prove_batch", suite, C.c_size_t(n), _p(sk), _p(inp), _p(outp), _p(adb), _p(off), _p(proof), _p(bl))
         return proof, bl
 
-    def pedersen_verify(self, suite, inp, outp, proof, ad=None):
+    def pedersen_verify(self, suite, inp, outp, proof, ad=None, status=False):
         inp = _u8(inp, (-1, 64)); n = len(inp); outp = _u8(outp, (n, 64)); proof = _u8(proof, (n, 256))
-        adb, off = pack_var(ad)
-        ok = np.zeros(n, np.uint8)
-        self._call("vrfs_pedersen_verify_batch", suite, C.c_size_t(n), _p(inp), _p(outp), _p(proof), _p(adb), _p(off), _p(ok))
-        return ok
+        adb, off = pack_var(ad, n)
+        ok = np.zeros(n, np.uint8); st = np.zeros(n, np.uint8) if status else None
+        self._call("vrfs_pedersen_verify_batch", suite, C.c_size_t(n), _p(inp), _p(outp), _p(proof), _p(adb), _p(off), _p(ok), _p(st))
+        return (ok, st) if status else ok
+
+    def pedersen_proof_len(self, suite):
+        return int(self._lib.vrfs_suite_pedersen_proof_len(suite))
+
+    def pedersen_prove_compressed(self, suite, sk, inp, outp, ad=None):
+        """pedersen::Prover::prove with the proof in its serialised form (3 encoded points + s + sb; 160 B for Bandersnatch)"""
+        sk = _u8(sk, (-1, 32)); n = len(sk); inp = _u8(inp, (n, 64)); outp = _u8(outp, (n, 64))
+        adb, off = pack_var(ad, n)
+        proof = np.zeros((n, self.pedersen_proof_len(suite)), np.uint8); bl = np.zeros((n, 32), np.uint8)
+        self._call("vrfs_pedersen_prove_compressed_batch", suite, C.c_size_t(n), _p(sk), _p(inp), _p(outp), _p(adb), _p(off), _p(proof), _p(bl))
+        return proof, bl
+
+    def pedersen_verify_compressed(self, suite, inp, outp, proof, ad=None, status=False):
+        inp = _u8(inp, (-1, 64)); n = len(inp); outp = _u8(outp, (n, 64)); proof = _u8(proof, (n, self.pedersen_proof_len(suite)))
+        adb, off = pack_var(ad, n)
+        ok = np.zeros(n, np.uint8); st = np.zeros(n, np.uint8) if status else None
+        self._call("vrfs_pedersen_verify_compressed_batch", suite, C.c_size_t(n), _p(inp), _p(outp), _p(proof), _p(adb), _p(off), _p(ok), _p(st))
+        return (ok, st) if status else ok
 
     # ---- ring commitment MSM (BLS12-381 G1)
     def msm_g1(self, bases, scalars, n_columns=1):
@@ -340,3 +414,90 @@ class Engine:
         macs = C.c_double(); mhz = C.c_double()
         self._check(self._lib.vrfs_measure_mac32_peak(self._ctx, int(variant), C.byref(macs), C.byref(mhz)))
         return macs.value, mhz.value
+
+
+class MultiPreparedBases:
+    def __init__(self, mengine, handle, n):
+        self.mengine, self.handle, self.n = mengine, handle, n
+
+    def msm(self, scalars, n_columns=1):
+        scalars = _u8(scalars, (n_columns * self.n, 32)); out = np.zeros((n_columns, 96), np.uint8)
+        self.mengine._call("vrfs_multi_msm_g1_prepared", self.handle, _p(scalars), int(n_columns), _p(out))
+        return out
+
+    def ring_commit(self, keys, keyset_part_size, padding, tail):
+        keys = _u8(keys, (-1, 64)); tail = _u8(tail, (-1, 64)); padding = _u8(padding, (64,)); out = np.zeros((3, 96), np.uint8)
+        self.mengine._call("vrfs_multi_ring_commit", self.handle, C.c_size_t(keyset_part_size), C.c_size_t(len(keys)), _p(keys), _p(padding),
+                           C.c_size_t(len(tail)), _p(tail), _p(out))
+        return out
+
+    def release(self):
+        if self.handle:
+            self.mengine._lib.vrfs_multi_msm_g1_release(self.handle)
+            self.handle = None
+
+
+class MultiEngine:
+    """One caller, several GPUs of one node (vrfs_ctx_create_multi): verify batches are sharded by index range, the commitment
+    MSM by point range with the partials exchanged device to device."""
+
+    def __init__(self, devices):
+        self._lib = _lib.load()
+        self._m = C.c_void_p()
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        st = self._lib.vrfs_ctx_create_multi(devs, len(devices), C.byref(self._m))
+        if st != _lib.OK:
+            msg = self._lib.vrfs_mctx_last_error(self._m).decode() if self._m else "context allocation failed"
+            if self._m:
+                self._lib.vrfs_mctx_destroy(self._m)
+                self._m = None
+            raise _lib.VrfsError(st, msg)
+        self.devices = list(devices)
+        self._prepared = []
+
+    def _call(self, fn, *args):
+        st = getattr(self._lib, fn)(self._m, *args)
+        if st != _lib.OK:
+            raise _lib.VrfsError(st, self._lib.vrfs_mctx_last_error(self._m).decode())
+
+    @property
+    def launch_count(self):
+        return int(self._lib.vrfs_mctx_launch_count(self._m))
+
+    def ietf_verify(self, suite, pk, inp, outp, c, s, ad=None, status=False):
+        pk = _u8(pk, (-1, 64)); n = len(pk)
+        inp = _u8(inp, (n, 64)); outp = _u8(outp, (n, 64)); c = _u8(c, (n, 32)); s = _u8(s, (n, 32))
+        adb, off = pack_var(ad, n)
+        ok = np.zeros(n, np.uint8); st = np.zeros(n, np.uint8) if status else None
+        self._call("vrfs_multi_ietf_verify_batch", suite, C.c_size_t(n), _p(pk), _p(inp), _p(outp), _p(c), _p(s), _p(adb), _p(off), _p(ok), _p(st))
+        return (ok, st) if status else ok
+
+    def ietf_verify_host_ptrs(self, suite, n, pk, inp, outp, c, s, ok, ad=None, off=None, status=None):
+        v = lambda x: C.c_void_p(x) if x else None
+        self._call("vrfs_multi_ietf_verify_batch", suite, C.c_size_t(n), v(pk), v(inp), v(outp), v(c), v(s), v(ad), v(off), v(ok), v(status))
+
+    def msm_g1_prepare(self, bases):
+        bases = _u8(bases, (-1, 96)); h = C.c_void_p()
+        self._call("vrfs_multi_msm_g1_prepare", C.c_size_t(len(bases)), _p(bases), C.byref(h))
+        p = MultiPreparedBases(self, h, len(bases))
+        self._prepared.append(p)
+        return p
+
+    def close(self):
+        if getattr(self, "_m", None):
+            for p in self._prepared:
+                p.release()
+            self._lib.vrfs_mctx_destroy(self._m)
+            self._m = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

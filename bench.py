@@ -1,20 +1,28 @@
 #!/usr/bin/env python3
-"""bench.py - headline benchmark: Bandersnatch IETF VRF batch verify (BASELINE.json configs[1]).
+"""bench.py - headline benchmark: Bandersnatch IETF VRF batch verify (BASELINE.json configs[1]) plus, in the same driver-run
+line, every other BASELINE config and the multi-GPU commitment MSM.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--logn 20]
 
 A step = one pass of `ietf::Verifier::verify` over one batch of 2^logn synthetic proofs per GPU.
-  value : verifies/s, whole job, inputs resident in HBM (vrfs_ietf_verify_batch_dev), CUDA-event timed on
-          the engine's stream, max over ranks.
-  e2e   : the same through the host-buffer C ABI call (vrfs_ietf_verify_batch) from pinned host memory,
-          H2D + D2H inside the timed region.
+Workload: 2^logn DISTINCT items per GPU - sk_i = Secret::from_seed("vrfs-b200-bench-sk" || u64le(i)),
+alpha_i = u64le(i) || 24 x 0x00, proofs produced by the engine's own prover and cross-checked against the CPU oracle on a
+2^12 subsample (prover output AND verdicts); 1/64 of the items corrupted (bit flip in c, s or O, position i mod 3).
+  value : verifies/s, whole job, inputs resident in HBM (vrfs_ietf_verify_batch_dev), CUDA-event timed on the engine's
+          stream, max over ranks.
+  e2e   : the same through the host-buffer C ABI call (vrfs_ietf_verify_batch) from pinned host memory, H2D + D2H inside.
   roofline : integer-pipe (32x32+64 multiply-accumulate) roofline of the dominant kernel, plus its HBM view.
-  cpu_baseline : the CPU oracle (restatement of the reference algorithm, NOT the arkworks binary - the mounted
-          reference is a deprecation stub and no Rust toolchain exists) on a bounded sample, all host threads.
---impl reference times that same CPU oracle as the reference arm.
-Only the workload generator, the cpu_baseline leg and --impl reference touch oracle/ (tests/oracle_lib.py).
+  cpu_baseline : the CPU oracle (restatement of the reference algorithm, NOT the arkworks binary - the mounted reference is a
+          deprecation stub and no Rust toolchain exists) on a bounded sample, all host threads.
+  configs : with_ad32 (the headline with 32-byte additional data), strong_scaling (ONE 2^logn batch over the N GPUs),
+          ietf_prove (Ed25519, secp256r1; BASELINE configs[2]), pedersen (Bandersnatch prove + verify; configs[3]),
+          ring_kzg_msm_ms (3-column commitment MSM for the domains 2^11..2^17; configs[4]) - at N > 1 the point-range-split
+          form whose partial sums are exchanged by the MSM's last kernel over NVLink (no NCCL on the data path).
+--impl reference times the CPU oracle as the reference arm.
+Only the cross-checks, the cpu_baseline leg and --impl reference touch oracle/ (tests/oracle_lib.py).
 """
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -22,6 +30,7 @@ import subprocess
 import sys
 import threading
 import time
+import traceback
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -29,10 +38,29 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "bandersnatch_ietf_vrf_verifies_per_sec"
 UNIT = "verifies/s"
-# algorithmic work per item (DESIGN.md "Roofline model"): field multiplications x 136 MAC32
-MULS = {"lincomb<2,0>": 2110, "lincomb<1,1>": 1820, "ietf_verify_finish": 275}
-MAC_PER_MUL = 136
-BYTES_PER_ITEM = {"lincomb<2,0>": 64 + 64 + 32 + 32 + 96, "lincomb<1,1>": 64 + 32 + 32 + 96, "ietf_verify_finish": 3 * 64 + 32 + 2 * 96 + 2}
+MAC_PER_MUL = 136          # one 8-limb Montgomery product = 2 n^2 + n multiply-accumulates
+R_BLS = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
+SUITE_NAMES = {0: "Bandersnatch_SHA-512_ELL2", 1: "Ed25519_SHA-512_TAI", 2: "secp256r1_SHA-256_TAI"}
+
+
+def kernel_muls(suite, kernel):
+    """algorithmic field products per item of one kernel (DESIGN.md "Roofline model"): squarings count as products, additions and
+    multiplications by small constants are free.  What the engine executes, not the reference's double-and-add."""
+    if suite == 0:       # Bandersnatch: GLV halves, 32 radix-16 windows -> 124 shared doublings (8), cached adds (9), 2 tables of 7 adds + endo
+        dbl, add, madd, tab, windows, split = 8, 9, 8, 7 * 9 + 5, 32, 2
+        doublings = 124
+    elif suite == 1:     # Ed25519: 64 radix-16 windows -> 252 doublings
+        dbl, add, madd, tab, windows, split = 8, 9, 8, 7 * 9, 64, 1
+        doublings = 252
+    else:                # secp256r1: 65 windows, dbl4 = 38 products, complete additions of 12
+        dbl, add, madd, tab, windows, split = 9.5, 12, 12, 7 * 12, 65, 1
+        doublings = 256
+    var = lambda nv: doublings * dbl + nv * split * (windows * add + tab)
+    fix = lambda nf: nf * 16 * madd
+    inv = 270
+    table = {"lincomb<2,0>": var(2), "lincomb<1,1>": var(1) + fix(1), "lincomb<1,0>": var(1), "lincomb<0,1>": fix(1), "lincomb<0,2>": fix(2),
+             "lincomb<1,2>": var(1) + fix(2), "ietf_verify_finish": inv / 8 + 3 * 3 + 8, "zinv": inv / 8 + 9}
+    return table.get(kernel)
 
 
 def parse():
@@ -45,6 +73,7 @@ def parse():
     ap.add_argument("--ref-logn", type=int, default=14, help="log2 of the reference arm's per-step sample")
     ap.add_argument("--cpu-sample-logn", type=int, default=18)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--headline-only", action="store_true", help="skip the secondary configs (profiling runs)")
     return ap.parse_args()
 
 
@@ -107,34 +136,162 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
 
 
-def ncu_traffic(kernel, n):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/traffic.json), scaled per item"""
+def ncu_record(kernel, key, n):
+    """figures of the committed ncu capture of the dominant kernel (profiles/traffic.json); byte counts scaled to n items"""
     try:
         d = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        return d["dram_bytes_per_launch"][kernel] / d["items_per_launch"] * n
+        v = d[key][kernel]
+        return v / d["items_per_launch"] * n if key == "dram_bytes_per_launch" else v
     except Exception:
         return None
 
 
-def ncu_fmaheavy(kernel):
-    try:
-        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["fmaheavy_pipe_active_pct"][kernel]
-    except Exception:
-        return None
-
-
-def msm_extra(eng, peak_mac=None, hbm_peak=None):
-    """second half of BASELINE's metric: ring KZG commitment MSM (3 columns, BLS12-381 G1) in ms, prepared SRS bases,
-    for the domain sizes of ring sizes 2^10 and 2^16 (N = 2^11, 2^17)."""
-    import hashlib
+# ---------------------------------------------------------------------------------------------------------------------------
+# workload generation (on the GPU, by the engine's own prover; the oracle only cross-checks a subsample)
+# ---------------------------------------------------------------------------------------------------------------------------
+def packed_counter(prefix, base, n, pad=0):
+    """n items prefix || u64le(base + i) || pad zero bytes, as (data, offsets) for the engine"""
     import numpy as np
-    out = {}
-    # synthetic inputs of SURVEY.md 8(d): a test-only SRS [tau^j]G1 with the PUBLIC tau = LE(SHA-512("vrfs-b200-bench-tau")) mod r and
-    # scalars LE(SHA-512("vrfs-b200-bench-msm" || u64le(j))) mod r.  The bases are produced by the engine itself (one prepared base
-    # G1, 32 one-scalar columns per call), the scalars on the host.
-    R_BLS = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
+    L = len(prefix) + 8 + pad
+    d = np.zeros((n, L), np.uint8)
+    if prefix:
+        d[:, :len(prefix)] = np.frombuffer(prefix, np.uint8)
+    d[:, len(prefix):len(prefix) + 8] = np.arange(base, base + n, dtype=np.uint64).view(np.uint8).reshape(n, 8)
+    return d.reshape(-1), np.arange(n + 1, dtype=np.uint64) * L
+
+
+def ad32(base, n):
+    import numpy as np
+    raw = b"".join(hashlib.sha256((base + i).to_bytes(8, "little")).digest() for i in range(n))
+    return np.frombuffer(raw, np.uint8).copy(), np.arange(n + 1, dtype=np.uint64) * 32
+
+
+def slice_var(v, idx):
+    data, off = v
+    return [data[int(off[i]):int(off[i + 1])].tobytes() for i in idx]
+
+
+def make_keys(eng, suite, base, n):
+    seeds = packed_counter(b"vrfs-b200-bench-sk", base, n)
+    alphas = packed_counter(b"", base, n, pad=24)
+    sk, pk = eng.secret_from_seed(suite, seeds)
+    inp, ok = eng.data_to_point(suite, alphas)
+    assert ok.all()
+    out = eng.output(suite, sk, inp)
+    return dict(seeds=seeds, alphas=alphas, sk=sk, pk=pk, inp=inp, out=out)
+
+
+def make_verify_workload(eng, suite, base, n, with_ad, oracle_threads):
+    """2^logn distinct proofs by the GPU prover; 1/64 corrupted; prover output and verdicts oracle-checked on a 2^12 subsample"""
+    import numpy as np
+    import oracle_lib as O
+    w = make_keys(eng, suite, base, n)
+    w["ads"] = ad32(base, n) if with_ad else None
+    c, s = eng.ietf_prove(suite, w["sk"], w["inp"], w["out"], w["ads"])
+    expect = np.ones(n, np.uint8)
+    bad = np.arange(0, n, 64)
+    out = w["out"].copy()
+    for kind, arr in ((0, c), (1, s), (2, out)):
+        rows = bad[bad % 3 == kind]
+        arr[rows, (rows // 64) % 16] ^= 1 << 3
+    w["out_good"] = w["out"]; w["out"] = out
+    expect[bad] = 0
+    w["c"], w["s"], w["expect"] = c, s, expect
+    sub = np.arange(0, n, max(1, n // 4096))
+    adsub = slice_var(w["ads"], sub) if with_ad else None
+    sk_o, pk_o = O.secret_from_seed(suite, slice_var(w["seeds"], sub), nthreads=oracle_threads)
+    inp_o, _ = O.data_to_point(suite, slice_var(w["alphas"], sub), nthreads=oracle_threads)
+    assert np.array_equal(sk_o, w["sk"][sub]) and np.array_equal(pk_o, w["pk"][sub]) and np.array_equal(inp_o, w["inp"][sub]), "keys / inputs differ from the oracle"
+    c_o, s_o = O.ietf_prove(suite, sk_o, inp_o, w["out_good"][sub], adsub, nthreads=oracle_threads)
+    good = expect[sub] == 1
+    assert np.array_equal(c_o[good], c[sub][good]) and np.array_equal(s_o[good], s[sub][good]), "GPU prover differs from the oracle"
+    v_o = O.ietf_verify(suite, w["pk"][sub], w["inp"][sub], out[sub], c[sub], s[sub], adsub, nthreads=oracle_threads)
+    assert np.array_equal(v_o, expect[sub]), "expected verdicts differ from the oracle"
+    w["oracle_checked_items"] = int(len(sub))
+    return w
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# secondary configs (host-buffer calls; every rank runs them on its own 2^logn items, rank 0 aggregates)
+# ---------------------------------------------------------------------------------------------------------------------------
+def timed_host_call(eng, fn, steps):
+    """(seconds per call by wall clock, {kernel: ms} of one call by CUDA events on the engine's stream)"""
+    fn()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    wall = (time.perf_counter() - t0) / steps
+    eng.enable_kernel_timing(True)
+    fn()
+    kt = {}
+    for name, ms in eng.kernel_timings():
+        kt[name] = kt.get(name, 0.0) + ms
+    eng.enable_kernel_timing(False)
+    return wall, kt
+
+
+def roofline_of(kt, suite, n, peak_mac):
+    dom = max(kt, key=kt.get)
+    muls = kernel_muls(suite, dom)
+    r = {"kernel": dom, "kernel_ms": {k: round(v, 3) for k, v in kt.items()}, "share_of_device_time": kt[dom] / sum(kt.values())}
+    if muls:
+        ach = n * muls * MAC_PER_MUL / (kt[dom] * 1e-3)
+        r.update({"field_muls_per_item": muls, "achieved_tmac32": ach / 1e12, "frac_of_mac32_peak": ach / peak_mac if peak_mac else None})
+    return r
+
+
+def config_ietf_prove(eng, suite, base, n, steps, peak_mac, oracle_threads):
+    """BASELINE configs[2]: batch IETF prove with deterministic nonces; inputs in host memory, c and s back to host"""
+    import numpy as np
+    import oracle_lib as O
+    w = make_keys(eng, suite, base, n)
+    res = {}
+    fn = lambda: eng.ietf_prove(suite, w["sk"], w["inp"], w["out"], None)
+    wall, kt = timed_host_call(eng, fn, steps)
+    c, s = fn()
+    sub = np.arange(0, n, max(1, n // 1024))
+    c_o, s_o = O.ietf_prove(suite, w["sk"][sub], w["inp"][sub], w["out"][sub], None, nthreads=oracle_threads)
+    assert np.array_equal(c_o, c[sub]) and np.array_equal(s_o, s[sub]), "prove differs from the oracle"
+    assert eng.ietf_verify(suite, w["pk"], w["inp"], w["out"], c, s).all()
+    dev_ms = sum(kt.values())
+    res = {"items": n, "e2e_per_s": n / wall, "device_per_s": n / (dev_ms * 1e-3), "e2e_ms": wall * 1e3, "device_ms": dev_ms,
+           "h2d_bytes": n * 160, "d2h_bytes": n * 64, "oracle_checked_items": int(len(sub)), "roofline": roofline_of(kt, suite, n, peak_mac)}
+    return res
+
+
+def config_pedersen(eng, base, n, steps, peak_mac, oracle_threads):
+    """BASELINE configs[3]: Pedersen prove + verify over Bandersnatch"""
+    import numpy as np
+    import oracle_lib as O
+    suite = 0
+    w = make_keys(eng, suite, base, n)
+    fnp = lambda: eng.pedersen_prove(suite, w["sk"], w["inp"], w["out"], None)
+    wall_p, kt_p = timed_host_call(eng, fnp, steps)
+    proof, bl = fnp()
+    sub = np.arange(0, n, max(1, n // 1024))
+    p_o, b_o = O.pedersen_prove(suite, w["sk"][sub], w["inp"][sub], w["out"][sub], None, nthreads=oracle_threads)
+    assert np.array_equal(p_o, proof[sub]) and np.array_equal(b_o, bl[sub]), "pedersen prove differs from the oracle"
+    bad = np.arange(0, n, 64)
+    proof[bad, 192 + (bad // 64) % 30] ^= 4
+    fnv = lambda: eng.pedersen_verify(suite, w["inp"], w["out"], proof, None)
+    wall_v, kt_v = timed_host_call(eng, fnv, steps)
+    ok = fnv()
+    expect = np.ones(n, np.uint8); expect[bad] = 0
+    assert np.array_equal(ok, expect), "pedersen verdicts"
+    assert np.array_equal(O.pedersen_verify(suite, w["inp"][sub], w["out"][sub], proof[sub], None, nthreads=oracle_threads), expect[sub])
+    dp, dv = sum(kt_p.values()), sum(kt_v.values())
+    return {"items": n,
+            "prove": {"e2e_per_s": n / wall_p, "device_per_s": n / (dp * 1e-3), "e2e_ms": wall_p * 1e3, "device_ms": dp, "h2d_bytes": n * 160, "d2h_bytes": n * 288,
+                      "roofline": roofline_of(kt_p, suite, n, peak_mac)},
+            "verify": {"e2e_per_s": n / wall_v, "device_per_s": n / (dv * 1e-3), "e2e_ms": wall_v * 1e3, "device_ms": dv, "h2d_bytes": n * 384, "d2h_bytes": n,
+                       "invalid_fraction": 1 / 64, "roofline": roofline_of(kt_v, suite, n, peak_mac)},
+            "oracle_checked_items": int(len(sub))}
+
+
+def bench_srs(eng, nmax):
+    """test-only SRS [tau^j]G1 with the PUBLIC tau = LE(SHA-512("vrfs-b200-bench-tau")) mod r, produced by the engine"""
+    import numpy as np
     tau = int.from_bytes(hashlib.sha512(b"vrfs-b200-bench-tau").digest(), "little") % R_BLS
-    nmax = 1 << 17
     pw = np.zeros((nmax, 32), np.uint8); t = 1
     for j in range(nmax):
         pw[j] = np.frombuffer(t.to_bytes(32, "little"), np.uint8); t = t * tau % R_BLS
@@ -145,65 +302,88 @@ def msm_extra(eng, peak_mac=None, hbm_peak=None):
     h1 = eng.msm_g1_prepare(gen)
     srs = np.concatenate([h1.msm(pw[i:i + 32], 32) for i in range(0, nmax, 32)])
     h1.release()
-    for logn in (11, 17):
+    return srs
+
+
+def bench_scalars(m):
+    """uniform field elements (what ring columns and polynomial coefficients look like), deterministic"""
+    import numpy as np
+    rng = np.random.default_rng(20261017)
+    raw = rng.integers(0, 256, size=(m, 40), dtype=np.uint8)
+    return np.frombuffer(b"".join((int.from_bytes(r.tobytes(), "little") % R_BLS).to_bytes(32, "little") for r in raw), np.uint8).reshape(m, 32).copy()
+
+
+def msm_window(logn):
+    return 8 if logn <= 9 else 10 if logn <= 12 else 13 if logn <= 16 else 16      # msm_plan's prepared-mode table (csrc/msm.cuh)
+
+
+def config_msm(eng, rank, world, peak_mac, hbm_peak, sizes, steps=5):
+    """BASELINE configs[4]: 3-column KZG commitment MSM over BLS12-381 G1, prepared SRS, for every domain size; plus the commitment
+    of an actual ring (fixed columns built on the device).  world > 1: the SRS is split by point range over the ranks and the
+    partials are exchanged by the MSM's last kernel over NVLink (vrfs_msm_g1_prepared_allgather / vrfs_ring_commit_rows_allgather);
+    every rank checks the collective result against its own single-GPU computation."""
+    import numpy as np
+    import ark_ec_vrfs_b200 as vrfs
+    from ark_ec_vrfs_b200 import dist as D
+    nmax = 1 << max(sizes)
+    srs = bench_srs(eng, nmax)
+    pool = bench_scalars(3 * nmax).reshape(3, nmax, 32)
+    _, allkeys = eng.secret_from_seed(vrfs.BANDERSNATCH, packed_counter(b"bench-ring-key-", 0, nmax // 2 + 254))
+    out = {}
+    device_exchange = world > 1 and eng.peer_world == world      # main() connected the peer group (a collective of its own)
+    out["exchange"] = ("device-side: partials stored into the peers' mailboxes by k_msm_final2 over NVLink (CUDA IPC), flags + fold in the same kernel"
+                       if device_exchange else ("single GPU" if world == 1 else "host all-gather fallback (no peer access)"))
+    for logn in sizes:
         n = 1 << logn
-        bases = srs[:n]
-        sc = np.frombuffer(b"".join((int.from_bytes(hashlib.sha512(b"vrfs-b200-bench-msm" + j.to_bytes(8, "little")).digest(), "little") % R_BLS).to_bytes(32, "little")
-                                    for j in range(3 * n)), np.uint8).reshape(3 * n, 32)
-        h = eng.msm_g1_prepare(bases)
-        eng.enable_kernel_timing(True)
-        for _ in range(3):
-            h.msm(sc, 3)
-        kt = dict(eng.kernel_timings())
-        dev_ms = sum(kt.values())
-        eng.enable_kernel_timing(False)
-        t0 = time.perf_counter(); h.msm(sc, 3); wall = (time.perf_counter() - t0) * 1e3
-        out["2^%d" % logn] = {"device_ms": dev_ms, "e2e_ms": wall}
-        # roofline of the dominant MSM kernel (bucket accumulation): every non-zero signed digit is one XYZZ mixed addition
-        # = 10 products of 12 limbs = 10 x 300 MAC32, and one 96-byte table record + one 4-byte list entry of HBM traffic
-        c = 8 if logn <= 9 else 10 if logn <= 12 else 13 if logn <= 16 else 16     # msm_plan's window table
+        sc = np.ascontiguousarray(pool[:, :n]).reshape(-1, 32)
+        h = eng.msm_g1_prepare(srs[:n])
+        ref = h.msm(sc, 3)
+        wall1, kt1 = timed_host_call(eng, lambda: h.msm(sc, 3), steps)
+        r = {"single_gpu": {"device_ms": sum(kt1.values()), "e2e_ms": wall1 * 1e3, "kernel_ms": {k: round(v, 4) for k, v in kt1.items()}}}
+        c = msm_window(logn)
         entries = 3 * n * ((255 + c) // c)
-        acc_ms = kt.get("msm_accumulate")
+        acc_ms = kt1.get("msm_accumulate")
         if acc_ms:
-            r = {"kernel": "k_msm_accumulate", "ms": acc_ms, "share_of_call": acc_ms / dev_ms, "mixed_additions": entries,
-                 "achieved_tmac32": entries * 3000 / (acc_ms * 1e-3) / 1e12, "hbm_gbps": entries * 100 / (acc_ms * 1e-3) / 1e9}
+            # every non-zero signed digit is one XYZZ mixed addition = 10 products of 12 limbs = 10 x 300 MAC32, one 96-byte table record + 4-byte list entry
+            rl = {"kernel": "k_msm_accumulate", "ms": acc_ms, "share_of_call": acc_ms / sum(kt1.values()), "mixed_additions": entries,
+                  "achieved_tmac32": entries * 3000 / (acc_ms * 1e-3) / 1e12, "hbm_gbps": entries * 100 / (acc_ms * 1e-3) / 1e9}
             if peak_mac:
-                r["frac_of_mac32_peak"] = r["achieved_tmac32"] * 1e12 / peak_mac
+                rl["frac_of_mac32_peak"] = rl["achieved_tmac32"] * 1e12 / peak_mac
+                r["single_gpu"]["whole_call_frac_of_mac32_peak"] = entries * 3000 / (sum(kt1.values()) * 1e-3) / peak_mac
             if hbm_peak:
-                r["frac_of_hbm_peak"] = r["hbm_gbps"] / hbm_peak
-            out["2^%d" % logn]["roofline"] = r
-        # the commitment of an actual ring: ring of N/2 distinct keys, the remaining key slots padded, 253-row tail of
-        # blinding-base powers, Lagrange-basis SRS; one vrfs_ring_commit call from host keys (columns built on the device)
-        try:
-            import ark_ec_vrfs_b200 as vrfs
-            _, keys = eng.secret_from_seed(vrfs.BANDERSNATCH, [b"bench-ring-key-%d" % i for i in range(n // 2 + 254)])
-            tail, padding, keys = keys[n // 2 + 1:], keys[n // 2], keys[:n // 2]
-            part = n - 3 - len(tail) - 1
-            eng.enable_kernel_timing(True)
-            for _ in range(3):
-                h.ring_commit(keys, part, padding, tail, lagrange=True)
-            ring_dev = sum(ms for _, ms in eng.kernel_timings())
-            eng.enable_kernel_timing(False)
-            t0 = time.perf_counter(); h.ring_commit(keys, part, padding, tail, lagrange=True); ring_wall = (time.perf_counter() - t0) * 1e3
-            eng.enable_kernel_timing(True)
-            for _ in range(3):
-                h.ring_commit_delta(keys, padding)
-            delta_dev = sum(ms for _, ms in eng.kernel_timings())
-            eng.enable_kernel_timing(False)
-            out["2^%d" % logn].update({"ring_commit_device_ms": ring_dev, "ring_commit_e2e_ms": ring_wall, "ring_commit_incremental_device_ms": delta_dev})
-        except Exception as ex:                                   # noqa: BLE001 - the headline line must still print
-            out["2^%d" % logn]["ring_commit_error"] = repr(ex)
+                rl["frac_of_hbm_peak"] = rl["hbm_gbps"] / hbm_peak
+            r["single_gpu"]["roofline"] = rl
+        # the commitment of an actual ring (SURVEY 8f-2): N/2 distinct keys, the remaining key slots padded, 253-row tail, Lagrange-basis SRS
+        tail, padding, keys = allkeys[n // 2 + 1:n // 2 + 254], allkeys[n // 2], allkeys[:n // 2]
+        part = n - 3 - len(tail) - 1
+        ring_ref = h.ring_commit(keys, part, padding, tail, lagrange=True)
+        wr, ktr = timed_host_call(eng, lambda: h.ring_commit(keys, part, padding, tail, lagrange=True), steps)
+        r["single_gpu"]["ring_commit_device_ms"] = sum(ktr.values()); r["single_gpu"]["ring_commit_e2e_ms"] = wr * 1e3
+        wd, ktd = timed_host_call(eng, lambda: h.ring_commit_delta(keys, padding), steps)
+        r["single_gpu"]["ring_commit_incremental_device_ms"] = sum(ktd.values())
         h.release()
+        if world > 1:
+            sh = D.ShardedPreparedBases(eng, srs[:n])
+            loc = sh.local_scalars(sc, 3)
+            got = sh.msm_local(loc, 3)
+            assert np.array_equal(got, ref), "sharded MSM differs from the single-GPU result at 2^%d" % logn
+            wall, kt = timed_host_call(eng, lambda: sh.msm_local(loc, 3), steps)
+            rc = D.ShardedRingContext(eng, srs[:n], part, padding, tail)
+            assert np.array_equal(rc.verifier_key_commitment(keys), ring_ref), "sharded ring commitment differs at 2^%d" % logn
+            wallr, ktrr = timed_host_call(eng, lambda: rc.verifier_key_commitment(keys), steps)
+            r["sharded"] = {"device_ms": sum(kt.values()), "e2e_ms": wall * 1e3, "ring_commit_device_ms": sum(ktrr.values()), "ring_commit_e2e_ms": wallr * 1e3,
+                            "kernel_ms": {k: round(v, 4) for k, v in kt.items()}, "points_per_rank": n // world}
+            rc.release(); sh.release()
+        out["2^%d" % logn] = r
     return out
 
 
-def wire_extra(eng, logn):
+def config_wire(eng, n):
     """verification straight off the wire - serialised 32-byte keys, 8-byte VRF input data and 96-byte signatures
-    (Output || c || s) in HOST memory -> verdicts + Output::hash, one C-ABI call per batch (deserialisation with subgroup checks,
-    Elligator2 hash-to-curve, verify, hash).  Signatures are produced by the engine's own signer (bit-exact vs the oracle in tests)."""
+    (Output || c || s) in HOST memory -> verdicts + Output::hash, one C-ABI call (deserialisation with subgroup checks, Elligator2,
+    verify, hash).  Signatures by the engine's own signer (bit-exact vs the oracle in tests)."""
     import numpy as np
     import ark_ec_vrfs_b200 as vrfs
-    n = 1 << logn
     sk256, pk256 = eng.secret_from_seed(vrfs.BANDERSNATCH, [b"bench-wire-%d" % i for i in range(256)])
     sk = np.tile(sk256, (n // 256, 1)); pk_enc = np.tile(eng.point_encode(vrfs.BANDERSNATCH, pk256), (n // 256, 1))
     datas = (np.arange(n, dtype=np.uint64).view(np.uint8).copy(), np.arange(n + 1, dtype=np.uint64) * 8)
@@ -215,27 +395,20 @@ def wire_extra(eng, logn):
         t0 = time.perf_counter(); okv, beta = eng.ietf_verify_wire(vrfs.BANDERSNATCH, pk_enc, datas, sig); dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
     assert int(okv.sum()) == n - n // 64
-    return {"what": "Bandersnatch: serialised keys + input data + 96-byte signatures (host) -> verdicts + 64-byte VRF outputs, 2^%d items, 1/64 corrupted" % logn,
+    return {"what": "Bandersnatch: serialised keys + input data + 96-byte signatures (host) -> verdicts + 64-byte VRF outputs, %d items, 1/64 corrupted" % n,
             "verifies_per_s": n / best, "bytes_in_per_item": 32 + 8 + 96, "bytes_out_per_item": 65}
 
 
-def make_workload(logn):
-    import numpy as np
-    import oracle_lib as O
-    import vectors as V
-    base_n = min(1 << logn, 4096)
-    base = V.make_ietf_proofs(O.BANDERSNATCH, base_n, "empty")
-    return V.tile(base, (1 << logn) // base_n), base
-
-
+# ---------------------------------------------------------------------------------------------------------------------------
 def run_reference(a, rank, world):
     """reference arm: the CPU oracle's ietf verify, all host threads, bounded sample per step (rank 0 only)"""
     if rank != 0:
         return
     import numpy as np
     import oracle_lib as O
-    w, _ = make_workload(a.ref_logn)
+    import vectors as V
     n = 1 << a.ref_logn
+    w = V.make_ietf_proofs(O.BANDERSNATCH, n, "empty")
     cores = os.cpu_count() or 1
     for _ in range(a.warmup):
         O.ietf_verify(O.BANDERSNATCH, w["pk"], w["inp"], w["out"], w["c"], w["s"], None, nthreads=cores)
@@ -245,7 +418,7 @@ def run_reference(a, rank, world):
     dt = time.perf_counter() - t0
     assert np.array_equal(got, w["expect"])
     v = n * a.steps / dt
-    sample = f"2^{a.ref_logn} proofs per step (same generator as the GPU workload), {cores} pthreads"
+    sample = f"2^{a.ref_logn} distinct proofs per step (oracle-generated, same suite / ad as the GPU workload), {cores} pthreads"
     emit({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (u64 on CPU)",
@@ -299,7 +472,10 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     eng = vrfs.Engine(local)
     n = 1 << a.logn
-    w, base = make_workload(a.logn)
+    cores = os.cpu_count() or 1
+    oracle_threads = max(1, cores // world)
+    base = rank * n                                  # every rank proves and verifies its own index range: all items of the job are distinct
+    w = make_verify_workload(eng, vrfs.BANDERSNATCH, base, n, False, oracle_threads)
     names = ("pk", "inp", "out", "c", "s")
     host = {k: torch.from_numpy(w[k]).pin_memory() for k in names}
     dev = {k: host[k].cuda(non_blocking=False) for k in names}
@@ -314,13 +490,29 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_dev():
-        eng.ietf_verify_dev(vrfs.BANDERSNATCH, n, dev["pk"].data_ptr(), dev["inp"].data_ptr(), dev["out"].data_ptr(),
-                            dev["c"].data_ptr(), dev["s"].data_ptr(), d_ok.data_ptr())
+    def gather(obj):
+        """every rank's object on rank 0 (None elsewhere); ALWAYS called by all ranks, whatever happened inside a section"""
+        if world == 1:
+            return [obj]
+        objs = [None] * world
+        dist.all_gather_object(objs, obj)
+        return objs
 
-    def step_host():
-        eng.ietf_verify_host_ptrs(vrfs.BANDERSNATCH, n, host["pk"].data_ptr(), host["inp"].data_ptr(), host["out"].data_ptr(),
-                                  host["c"].data_ptr(), host["s"].data_ptr(), h_ok.data_ptr())
+    def section(fn):
+        """run a per-rank measurement; a failure on any rank becomes an error entry instead of a hang or a lost headline"""
+        try:
+            r = fn()
+        except Exception as ex:   # noqa: BLE001
+            r = {"error": repr(ex), "trace": traceback.format_exc(limit=3)}
+        return gather(r)
+
+    def step_dev(d=dev, ad=None, off=None):
+        eng.ietf_verify_dev(vrfs.BANDERSNATCH, n, d["pk"].data_ptr(), d["inp"].data_ptr(), d["out"].data_ptr(),
+                            d["c"].data_ptr(), d["s"].data_ptr(), d_ok.data_ptr(), ad, off)
+
+    def step_host(h=host, m=n, ad=None, off=None):
+        eng.ietf_verify_host_ptrs(vrfs.BANDERSNATCH, m, h["pk"].data_ptr(), h["inp"].data_ptr(), h["out"].data_ptr(),
+                                  h["c"].data_ptr(), h["s"].data_ptr(), h_ok.data_ptr(), ad, off)
 
     # ---- integer-pipe peak, measured live (the roofline denominator of this path): the best sustained rate of any
     # 32x32->64-bit multiply(-accumulate) instruction form, each with data-dependent operands
@@ -332,7 +524,7 @@ def main():
     for _ in range(max(a.warmup, 3)):
         step_dev()
     eng.sync()
-    assert np.array_equal(d_ok.cpu().numpy(), expect), "GPU verdicts differ from the oracle"
+    assert np.array_equal(d_ok.cpu().numpy(), expect), "GPU verdicts differ from the expected ones"
     eng.enable_kernel_timing(True)
     ktimes = {}
     sampler = ClockSampler(local); sampler.start()
@@ -364,28 +556,115 @@ def main():
     e2e_s = time.perf_counter() - t0
     assert np.array_equal(h_ok.numpy(), expect)
 
-    t = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    # ---- strong scaling: ONE batch of 2^logn items over the N GPUs (rank g takes the g-th index range), host buffers, max over ranks
+    lo, hi = (n * rank) // world, (n * (rank + 1)) // world
+    hs = {k: host[k][lo:hi] for k in names}
+    for _ in range(2):
+        step_host(hs, hi - lo)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        step_host(hs, hi - lo)
+    torch.cuda.synchronize()
+    strong_s = time.perf_counter() - t0
+    assert np.array_equal(h_ok.numpy()[:hi - lo], expect[lo:hi])
+
+    t = torch.tensor([ms_total, e2e_s * 1e3, strong_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms = float(t[0]), float(t[1])
+    ms_total, e2e_ms, strong_ms = float(t[0]), float(t[1]), float(t[2])
     value = n * world * a.steps / (ms_total * 1e-3)
     e2e_value = n * world * a.steps / (e2e_ms * 1e-3)
+
+    # ---- secondary configs (all ranks; results gathered on rank 0)
+    extras = {}
+    if world > 1 and not a.headline_only:
+        # the peer group of the MSM exchange: one host-side all-gather of the 64-byte mailbox handles.  Generous timeout: the ranks
+        # reach the collective MSM calls seconds apart (their CPU-side preparation differs); a lost peer still cannot hang a GPU.
+        from ark_ec_vrfs_b200 import dist as D
+        if D.connect_peers(eng):
+            eng.peer_set_timeout_ms(30000)
+    if not a.headline_only:
+        ksteps = max(2, min(a.steps, 5))
+
+        def with_ad():
+            wa = make_verify_workload(eng, vrfs.BANDERSNATCH, base, n, True, oracle_threads)
+            ha = {k: torch.from_numpy(wa[k]).pin_memory() for k in names}
+            da = {k: ha[k].cuda() for k in names}
+            adh, offh = torch.from_numpy(wa["ads"][0]).pin_memory(), torch.from_numpy(wa["ads"][1].view(np.int64)).pin_memory()
+            add, offd = adh.cuda(), offh.cuda()
+            for _ in range(2):
+                step_dev(da, add.data_ptr(), offd.data_ptr())
+            eng.sync()
+            assert np.array_equal(d_ok.cpu().numpy(), wa["expect"])
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(stream):
+                e0.record(stream)
+                for _ in range(ksteps):
+                    step_dev(da, add.data_ptr(), offd.data_ptr())
+                e1.record(stream)
+            eng.sync()
+            dms = e0.elapsed_time(e1) / ksteps
+            step_host(ha, n, adh.data_ptr(), offh.data_ptr())
+            t0 = time.perf_counter()
+            for _ in range(ksteps):
+                step_host(ha, n, adh.data_ptr(), offh.data_ptr())
+            wall = (time.perf_counter() - t0) / ksteps
+            assert np.array_equal(h_ok.numpy(), wa["expect"])
+            return {"device_ms": dms, "e2e_ms": wall * 1e3, "oracle_checked_items": wa["oracle_checked_items"]}
+
+        extras["with_ad32"] = section(with_ad)
+        extras["ietf_prove_ed25519"] = section(lambda: config_ietf_prove(eng, vrfs.ED25519, base, n, ksteps, peak_mac, oracle_threads))
+        extras["ietf_prove_secp256r1"] = section(lambda: config_ietf_prove(eng, vrfs.P256, base, n, ksteps, peak_mac, oracle_threads))
+        extras["pedersen_bandersnatch"] = section(lambda: config_pedersen(eng, base, n, ksteps, peak_mac, oracle_threads))
+        hbm_peak_, _ = measured_peaks()
+        extras["ring_kzg_msm_ms"] = section(lambda: config_msm(eng, rank, world, peak_mac, hbm_peak_, list(range(11, 18))))
+        if world == 1:
+            extras["ietf_verify_wire"] = section(lambda: config_wire(eng, min(n, 1 << 20)))
+
+    # ---- one caller, all GPUs (vrfs_ctx_create_multi): rank 0 drives every device of the job with ONE host call per step while the
+    # other ranks idle at the barrier
+    multi = None
+    if world > 1 and not a.headline_only:
+        barrier()
+        if rank == 0:
+            try:
+                with vrfs.MultiEngine(list(range(world))) as me:
+                    for _ in range(2):
+                        me.ietf_verify_host_ptrs(vrfs.BANDERSNATCH, n, host["pk"].data_ptr(), host["inp"].data_ptr(), host["out"].data_ptr(),
+                                                 host["c"].data_ptr(), host["s"].data_ptr(), h_ok.data_ptr())
+                    t0 = time.perf_counter()
+                    for _ in range(a.steps):
+                        me.ietf_verify_host_ptrs(vrfs.BANDERSNATCH, n, host["pk"].data_ptr(), host["inp"].data_ptr(), host["out"].data_ptr(),
+                                                 host["c"].data_ptr(), host["s"].data_ptr(), h_ok.data_ptr())
+                    dt = (time.perf_counter() - t0) / a.steps
+                    assert np.array_equal(h_ok.numpy(), expect)
+                    multi = {"what": "vrfs_multi_ietf_verify_batch: one process, one call per step, 2^%d host items sharded over %d GPUs" % (a.logn, world),
+                             "verifies_per_s": n / dt, "ms_per_step": dt * 1e3}
+            except Exception as ex:   # noqa: BLE001
+                multi = {"error": repr(ex)}
+        barrier()
 
     if rank == 0:
         kavg = {k: sum(v) / len(v) for k, v in ktimes.items()}
         dom = max(kavg, key=kavg.get)
         dom_s = kavg[dom] * 1e-3
-        achieved = n * MULS.get(dom, 0) * MAC_PER_MUL / dom_s
+        muls = kernel_muls(0, dom) or 0
+        achieved = n * muls * MAC_PER_MUL / dom_s
         hbm_peak, hbm_src = measured_peaks()
-        hbm_ach = n * BYTES_PER_ITEM.get(dom, 0) / dom_s / 1e9
+        bytes_per_item = {"lincomb<2,0>": 64 + 64 + 32 + 32 + 96, "lincomb<1,1>": 64 + 32 + 32 + 96, "ietf_verify_finish": 3 * 64 + 32 + 2 * 96 + 2}.get(dom, 0)
+        hbm_ach = n * bytes_per_item / dom_s / 1e9
         total_k = sum(kavg.values())
+        traffic = ncu_record(dom, "dram_bytes_per_launch", n)
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32 limbs (256-bit Montgomery, integer)", "data": "synthetic",
-            "config": {"workload": f"Bandersnatch IETF VRF batch verify, 2^{a.logn} proofs per GPU (BASELINE configs[1])",
+            "config": {"workload": f"Bandersnatch IETF VRF batch verify, 2^{a.logn} distinct proofs per GPU (BASELINE configs[1])",
                        "suite": "Bandersnatch_SHA-512_ELL2", "ad": "empty", "batch_per_gpu": n, "invalid_fraction": float(1 - expect.mean()),
-                       "distinct_items": int(len(base["expect"])), "l2": "inputs (256 B/item = %.0f MB) exceed the 126 MB L2; no flush needed" % (n * 256 / 1e6),
+                       "distinct_items": int(n * world), "generator": "engine prover on the GPU (Secret::from_seed, Input::new, Secret::output, ietf prove); keys, inputs, proofs and verdicts oracle-checked on a 2^12 subsample per rank",
+                       "oracle_checked_items_per_rank": w["oracle_checked_items"],
+                       "l2": "inputs (256 B/item = %.0f MB) exceed the 126 MB L2; no flush needed" % (n * 256 / 1e6),
                        "parallelism": f"batch sharded by index range over {world} GPU(s), no collective"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 256, "d2h_bytes_per_step": n, "ms_per_step": e2e_ms / a.steps},
             "gpu_launches": int(launches),
@@ -394,16 +673,20 @@ def main():
                          "achieved": achieved / 1e12, "peak": peak_mac / 1e12, "unit": "TMAC32/s", "frac": achieved / peak_mac,
                          "peak_source": "measured live: max over 64-bit-product instruction microbenchmarks (vrfs_measure_mac32_peak)",
                          "peak_probe_tmac32": {k: v / 1e12 for k, v in peak_probe.items()},
-                         "algorithmic_per_item": {"field_muls": MULS.get(dom), "mac32_per_mul": MAC_PER_MUL},
+                         "algorithmic_per_item": {"field_muls": muls, "mac32_per_mul": MAC_PER_MUL},
                          "kernel_ms": kavg, "kernel_share": {k: v / total_k for k, v in kavg.items()},
-                         "traffic": ncu_traffic(dom, n), "traffic_unit": "bytes/launch (dram read+write, ncu; window-table slab spills past L2)",
-                         "fmaheavy_pipe_active_pct_ncu": ncu_fmaheavy(dom),
+                         "traffic": traffic,
+                         "traffic_unit": "bytes/launch (dram read+write of the dominant kernel, ncu --set full capture under profiles/)",
+                         "fmaheavy_pipe_active_pct_ncu": ncu_record(dom, "fmaheavy_pipe_active_pct", n),
                          "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak, "peak_source": hbm_src,
-                                 "bytes_per_item": BYTES_PER_ITEM.get(dom)}},
+                                 "bytes_per_item": bytes_per_item}},
+            "strong_scaling": {"what": f"ONE batch of 2^{a.logn} host items over {world} GPU(s): rank g verifies the g-th index range, H2D/D2H inside, max over ranks",
+                               "value": n * a.steps / (strong_ms * 1e-3), "unit": UNIT, "ms_per_step": strong_ms / a.steps, "items_per_gpu": n // world},
         }
+        if multi:
+            out["one_caller_multi_gpu"] = multi
         if world == 1 and not a.no_cpu_baseline:
             import oracle_lib as O
-            cores = os.cpu_count() or 1
             m = min(n, 1 << a.cpu_sample_logn)
             t0 = time.perf_counter()
             got = O.ietf_verify(O.BANDERSNATCH, w["pk"][:m], w["inp"][:m], w["out"][:m], w["c"][:m], w["s"][:m], None, nthreads=cores)
@@ -412,16 +695,70 @@ def main():
             out["cpu_baseline"] = {"value": m / dt, "unit": UNIT, "cores": cores, "kind": "port",
                                    "sample": f"first 2^{a.cpu_sample_logn} proofs of the same workload, {cores} pthreads, {dt:.1f} s",
                                    "note": "CPU restatement of the reference algorithm (oracle/vrf_oracle.c), not the arkworks binary"}
-        if world == 1:                                # secondary measurements run on the single-GPU line only
-            try:
-                out["ring_kzg_msm_ms"] = {"what": "3-column commitment MSM over BLS12-381 G1, prepared SRS bases (vrfs_msm_g1_prepared), domain size N, 3 random columns; ring_commit_*: the fixed columns of a ring of N/2 keys built and committed in one call (vrfs_ring_commit); ring_commit_incremental: sum (pk_i - padding) L_i only, added to the kept commitment of the all-padding ring (vrfs_ring_commit_delta)",
-                                          **msm_extra(eng, peak_mac, hbm_peak)}
-            except Exception as ex:   # never lose the headline line to the secondary measurement
-                out["ring_kzg_msm_ms"] = {"error": repr(ex)}
-            try:
-                out["ietf_verify_wire"] = wire_extra(eng, min(a.logn, 20))
-            except Exception as ex:
-                out["ietf_verify_wire"] = {"error": repr(ex)}
+        # ---- aggregate the per-rank sections: rates add up over ranks, times take the slowest rank
+        def agg(rs, path, how):
+            vals = []
+            for r in rs:
+                x = r
+                for k in path:
+                    x = x.get(k) if isinstance(x, dict) else None
+                if x is None:
+                    return None
+                vals.append(x)
+            return sum(vals) if how == "sum" else max(vals)
+
+        def errors(rs):
+            e = [r["error"] for r in rs if isinstance(r, dict) and "error" in r]
+            return e or None
+
+        if "with_ad32" in extras:
+            rs = extras["with_ad32"]
+            if errors(rs):
+                out["with_ad32"] = {"error": errors(rs)}
+            else:
+                dms, ems = agg(rs, ["device_ms"], "max"), agg(rs, ["e2e_ms"], "max")
+                out["with_ad32"] = {"what": "the headline with 32-byte additional data per item (SHA-256(u64le(i))), distinct proofs made with that ad",
+                                    "value": n * world / (dms * 1e-3), "e2e": n * world / (ems * 1e-3), "unit": UNIT, "device_ms_per_step": dms, "e2e_ms_per_step": ems}
+        for key, label in (("ietf_prove_ed25519", "Ed25519_SHA-512_TAI"), ("ietf_prove_secp256r1", "secp256r1 (RFC 9381 suite 0x01)")):
+            if key in extras:
+                rs = extras[key]
+                if errors(rs):
+                    out[key] = {"error": errors(rs)}
+                else:
+                    out[key] = {"what": f"BASELINE configs[2]: {label} IETF prove of 2^{a.logn} items per GPU with deterministic nonces, host buffers in and out",
+                                "unit": "proves/s", "e2e": agg(rs, ["e2e_per_s"], "sum"), "device": agg(rs, ["device_per_s"], "sum"),
+                                "e2e_ms_per_step": agg(rs, ["e2e_ms"], "max"), "device_ms_per_step": agg(rs, ["device_ms"], "max"),
+                                "h2d_bytes_per_step": rs[0]["h2d_bytes"], "d2h_bytes_per_step": rs[0]["d2h_bytes"],
+                                "oracle_checked_items_per_rank": rs[0]["oracle_checked_items"], "roofline": rs[0]["roofline"]}
+        if "pedersen_bandersnatch" in extras:
+            rs = extras["pedersen_bandersnatch"]
+            if errors(rs):
+                out["pedersen_bandersnatch"] = {"error": errors(rs)}
+            else:
+                o = {"what": f"BASELINE configs[3]: Pedersen VRF prove and verify of 2^{a.logn} items per GPU over Bandersnatch, host buffers in and out",
+                     "oracle_checked_items_per_rank": rs[0]["oracle_checked_items"]}
+                for leg, unit in (("prove", "proves/s"), ("verify", "verifies/s")):
+                    o[leg] = {"unit": unit, "e2e": agg(rs, [leg, "e2e_per_s"], "sum"), "device": agg(rs, [leg, "device_per_s"], "sum"),
+                              "e2e_ms_per_step": agg(rs, [leg, "e2e_ms"], "max"), "device_ms_per_step": agg(rs, [leg, "device_ms"], "max"),
+                              "h2d_bytes_per_step": rs[0][leg]["h2d_bytes"], "d2h_bytes_per_step": rs[0][leg]["d2h_bytes"], "roofline": rs[0][leg]["roofline"]}
+                out["pedersen_bandersnatch"] = o
+        if "ring_kzg_msm_ms" in extras:
+            rs = extras["ring_kzg_msm_ms"]
+            if errors(rs):
+                out["ring_kzg_msm_ms"] = {"error": errors(rs)}
+            else:
+                o = {"what": "BASELINE configs[4]: 3-column commitment MSM over BLS12-381 G1 with a prepared SRS, domain size N (ring size N/2), uniform field elements; ring_commit: the fixed columns of a ring of N/2 keys built on the device and committed in one call over a Lagrange-basis SRS; single_gpu = every rank alone, sharded = the SRS split by point range over all ranks (times: slowest rank)",
+                     "exchange": rs[0]["exchange"], "n_gpus": world}
+                for key in [k for k in rs[0] if k.startswith("2^")]:
+                    e = {"single_gpu": rs[0][key]["single_gpu"]}
+                    if "sharded" in rs[0][key]:
+                        e["sharded"] = {f: agg(rs, [key, "sharded", f], "max") for f in ("device_ms", "e2e_ms", "ring_commit_device_ms", "ring_commit_e2e_ms")}
+                        e["sharded"]["points_per_rank"] = rs[0][key]["sharded"]["points_per_rank"]
+                        e["sharded"]["kernel_ms_rank0"] = rs[0][key]["sharded"]["kernel_ms"]
+                    o[key] = e
+                out["ring_kzg_msm_ms"] = o
+        if "ietf_verify_wire" in extras:
+            out["ietf_verify_wire"] = extras["ietf_verify_wire"][0]
         emit(out)
     eng.close()
     if world > 1:

@@ -19,6 +19,8 @@
  *   - variable-length data (`ad`, h2c `data`, seeds): one concatenated byte buffer + n+1 offsets
  *     (uint64).  A NULL `ad` means every item has empty additional data.
  *   - BLS12-381 G1 points: affine x || y, 48 bytes little-endian each; identity = 96 zero bytes.
+ *   - Secrets: device staging buffers that held `Secret` scalars, nonces or blinding factors are zeroed before the call
+ *     returns (the buffers are pooled, so that is their "release"); the library keeps no pinned host copies.
  *   - The caller owns every buffer; nothing is retained after return.  No exceptions, no aborts:
  *     every failure is a status code; `vrfs_last_error` gives text.  There is NO CPU fallback: without
  *     a CUDA device every call fails with VRFS_CUDA_ERROR.
@@ -41,15 +43,28 @@ typedef struct vrfs_ctx vrfs_ctx;
 typedef enum { VRFS_OK = 0, VRFS_INVALID_DATA = 1, VRFS_CUDA_ERROR = 2, VRFS_BAD_ARG = 3, VRFS_UNSUPPORTED = 4 } vrfs_status;
 /* `suites::{bandersnatch, ed25519, secp256r1}` (lib.rs:13-17) */
 typedef enum { VRFS_BANDERSNATCH_ELL2 = 0, VRFS_ED25519_TAI = 1, VRFS_P256_TAI = 2 } vrfs_suite;
+/* Per-item result of the verifiers: the reference's `Result<(), Error>` with `Error::{VerificationFailure, InvalidData}`
+ * (/root/reference/src/lib.rs:13-17, `Error`).  Every verify entry point takes an optional `out_status` array (may be NULL)
+ * next to `out_ok`:
+ *   VRFS_ITEM_OK                    Ok(())                       (out_ok = 1)
+ *   VRFS_ITEM_VERIFICATION_FAILURE  well-formed values whose proof does not check
+ *   VRFS_ITEM_INVALID_DATA          a value no typed Public / Input / Output / Proof can hold: non-canonical coordinates or
+ *                                   scalars, off the curve, the un-encodable short-Weierstrass identity; on the wire entry
+ *                                   points also: outside the prime-order subgroup, s >= r, no input point found */
+typedef enum { VRFS_ITEM_OK = 0, VRFS_ITEM_VERIFICATION_FAILURE = 1, VRFS_ITEM_INVALID_DATA = 2 } vrfs_item_status;
 
 int vrfs_abi_version(void);
-/* device = CUDA ordinal.  Builds the fixed-base tables for G and the Pedersen blinding base B. */
+/* device = CUDA ordinal.  The fixed-base tables for G and the Pedersen blinding base B (2 x 50 MB per suite) are built the
+ * first time a suite is used, not here. */
 vrfs_status vrfs_ctx_create(int device, vrfs_ctx** out);
 void vrfs_ctx_destroy(vrfs_ctx* ctx);
 vrfs_status vrfs_ctx_sync(vrfs_ctx* ctx);
 const char* vrfs_last_error(const vrfs_ctx* ctx);
 /* the CUDA stream (cudaStream_t) the context enqueues on; lets a caller order its own work after it */
 void* vrfs_ctx_stream(vrfs_ctx* ctx);
+/* test hook: n bytes at `offset` of internal staging buffer `slot` (0..4 = the input staging buffers in argument order, e.g.
+ * slot 0 held `sk` during a prove call); lets tests check that key material is zeroed once a call has returned */
+vrfs_status vrfs_ctx_debug_read_staging(vrfs_ctx* ctx, int slot, size_t offset, uint8_t* out, size_t n);
 /* number of kernel launches issued by this context so far (bench.py's `gpu_launches`) */
 uint64_t vrfs_ctx_launch_count(const vrfs_ctx* ctx);
 /* per-kernel device times (CUDA events on the context's stream) of the most recent batch call; used by
@@ -83,16 +98,25 @@ vrfs_status vrfs_ietf_prove_batch(vrfs_ctx*, vrfs_suite, size_t n, const uint8_t
 /* ietf::Verifier::verify (A.9) - the headline metric.  out_ok[i] = 1 iff the proof verifies (Ok(())),
  * 0 for Error::VerificationFailure / Error::InvalidData. */
 vrfs_status vrfs_ietf_verify_batch(vrfs_ctx*, vrfs_suite, size_t n, const uint8_t* pk, const uint8_t* input, const uint8_t* output,
-                                   const uint8_t* c, const uint8_t* s, const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_ok);
+                                   const uint8_t* c, const uint8_t* s, const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_ok,
+                                   uint8_t* out_status /* n x vrfs_item_status, may be NULL */);
 vrfs_status vrfs_ietf_verify_batch_dev(vrfs_ctx*, vrfs_suite, size_t n, const uint8_t* d_pk, const uint8_t* d_input,
                                        const uint8_t* d_output, const uint8_t* d_c, const uint8_t* d_s, const uint8_t* d_ad,
-                                       const uint64_t* d_ad_off, uint8_t* d_out_ok);
+                                       const uint64_t* d_ad_off, uint8_t* d_out_ok, uint8_t* d_out_status /* may be NULL */);
 
 /* pedersen::Prover::prove / Verifier::verify (A.10).  proof = pk_com || r || ok (3 x 64-byte affine) || s || sb (2 x 32 bytes) = 256 bytes. */
 vrfs_status vrfs_pedersen_prove_batch(vrfs_ctx*, vrfs_suite, size_t n, const uint8_t* sk, const uint8_t* input, const uint8_t* output,
                                       const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_proof /*n*256*/, uint8_t* out_blinding /*n*32*/);
 vrfs_status vrfs_pedersen_verify_batch(vrfs_ctx*, vrfs_suite, size_t n, const uint8_t* input, const uint8_t* output, const uint8_t* proof,
-                                       const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_ok);
+                                       const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_ok, uint8_t* out_status /* may be NULL */);
+/* The same with the typed `pedersen::Proof` in its serialised form (its CanonicalSerialize, A.10): point_encode(pk_com) ||
+ * point_encode(r) || point_encode(ok) || s || sb in codec byte order - 3 * enc_len + 64 bytes (Bandersnatch: 160 B, the size
+ * SURVEY 8b specifies).  verify deserialises like the reference (canonical, on curve, prime-order subgroup, s and sb < r). */
+int vrfs_suite_pedersen_proof_len(vrfs_suite s);
+vrfs_status vrfs_pedersen_prove_compressed_batch(vrfs_ctx*, vrfs_suite, size_t n, const uint8_t* sk, const uint8_t* input, const uint8_t* output,
+                                                 const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_proof /*n*proof_len*/, uint8_t* out_blinding /*n*32*/);
+vrfs_status vrfs_pedersen_verify_compressed_batch(vrfs_ctx*, vrfs_suite, size_t n, const uint8_t* input, const uint8_t* output, const uint8_t* proof /*n*proof_len*/,
+                                                  const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_ok, uint8_t* out_status /* may be NULL */);
 
 /* Wire formats: the serialised forms `CanonicalSerialize/Deserialize` (Compress::Yes, Validate::Yes)
  * give `Public`, `Output` and `ietf::Proof` (names at /root/reference/src/lib.rs:13-17), so that keys and signatures
@@ -112,7 +136,7 @@ vrfs_status vrfs_ietf_sign_wire_batch(vrfs_ctx*, vrfs_suite, size_t n, const uin
  * Output::hash of the accepted items (zero for rejected ones), n*hash_len. */
 vrfs_status vrfs_ietf_verify_wire_batch(vrfs_ctx*, vrfs_suite, size_t n, const uint8_t* pk_enc /*n*enc_len*/, const uint8_t* data,
                                         const uint64_t* data_off, const uint8_t* sig /*n*sig_len*/, const uint8_t* ad,
-                                        const uint64_t* ad_off, uint8_t* out_ok, uint8_t* out_hash);
+                                        const uint64_t* ad_off, uint8_t* out_ok, uint8_t* out_hash, uint8_t* out_status /* may be NULL */);
 
 /* Pedersen on the wire: signature = point_encode(Output) || point_encode(pk_com) || point_encode(r) || point_encode(ok) || s || sb
  * (an `Output` followed by `pedersen::Proof`'s CanonicalSerialize; Bandersnatch 192 B).  Deserialisation validates all four points
@@ -121,7 +145,7 @@ int vrfs_suite_pedersen_signature_len(vrfs_suite s);
 vrfs_status vrfs_pedersen_sign_wire_batch(vrfs_ctx*, vrfs_suite, size_t n, const uint8_t* sk, const uint8_t* data, const uint64_t* data_off,
                                           const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_sig /*n*sig_len*/, uint8_t* out_blinding /*n*32*/, uint8_t* out_ok);
 vrfs_status vrfs_pedersen_verify_wire_batch(vrfs_ctx*, vrfs_suite, size_t n, const uint8_t* data, const uint64_t* data_off, const uint8_t* sig /*n*sig_len*/,
-                                            const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_ok);
+                                            const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_ok, uint8_t* out_status /* may be NULL */);
 
 /* ring commitment MSM (ark-ec VariableBaseMSM::msm behind ring-proof's KZG commit):
  * n_columns scalar columns (column-major, n*32 bytes each) over one base vector of n affine G1 points.
@@ -148,6 +172,49 @@ void vrfs_msm_g1_release(vrfs_msm_bases* bases);
  * folded with vrfs_g1_sum_partials on any rank. */
 vrfs_status vrfs_msm_g1_partial(vrfs_ctx*, size_t n, const uint8_t* bases, const uint8_t* scalars, int n_columns, uint8_t* out_partial /*n_columns*144*/);
 vrfs_status vrfs_g1_sum_partials(vrfs_ctx*, int n_parts, int n_columns, const uint8_t* partials /*n_parts*n_columns*144*/, uint8_t* out /*n_columns*96*/);
+
+/* ---- several GPUs of one node -----------------------------------------------------------------------------
+ * VRF batches are independent items: they shard by index range and never communicate.  The commitment MSM splits by point
+ * range; each GPU reduces its range to one projective partial per column (144 B) and the partials are exchanged by the MSM's
+ * last kernel itself: it stores them into the peers' device memory over NVLink (peer access / CUDA IPC), raises a flag behind a
+ * system-scope fence, waits for the other ranks' flags in its own memory, adds and normalises.  No NCCL call, no host hop.
+ *
+ * (1) one process per GPU (torch.distributed / torchrun; the shape bench.py runs in): every rank creates an ordinary context,
+ *     calls vrfs_ctx_peer_export, all-gathers the 64-byte handles over its own control plane (host side, once), calls
+ *     vrfs_ctx_peer_connect.  The *_allgather entry points are COLLECTIVE: every rank of the group must call them in the same
+ *     order; every rank receives the full result.  A rank that waits longer than the timeout (default 2 s) for a peer fails with
+ *     VRFS_CUDA_ERROR instead of hanging. */
+#define VRFS_PEER_HANDLE_BYTES 64
+vrfs_status vrfs_ctx_peer_export(vrfs_ctx*, int rank, int world /* <= 16 */, uint8_t* out_handle /*64*/);
+vrfs_status vrfs_ctx_peer_connect(vrfs_ctx*, const uint8_t* handles /*world*64, rank order*/);
+vrfs_status vrfs_ctx_peer_set_timeout_ms(vrfs_ctx*, unsigned int ms);
+int vrfs_ctx_peer_world(const vrfs_ctx*);   /* 0 = not connected */
+/* this rank's scalars (n_columns x its n bases, column-major) over its prepared slice of the SRS -> the full commitments */
+vrfs_status vrfs_msm_g1_prepared_allgather(vrfs_ctx*, const vrfs_msm_bases* bases, const uint8_t* scalars, int n_columns, uint8_t* out /*n_columns*96*/);
+/* the ring commitment with the domain's rows split over the ranks: arguments as vrfs_ring_commit_rows_partial, full result out */
+vrfs_status vrfs_ring_commit_rows_allgather(vrfs_ctx*, const vrfs_msm_bases* srs_rows, size_t row_lo, size_t keyset_part_size, size_t n_keys,
+                                            const uint8_t* keys_rows, const uint8_t* padding, size_t n_tail, const uint8_t* tail,
+                                            uint8_t* out_commitment /*3*96*/);
+/* (2) one caller, several GPUs - the `vrfs_ctx_create(const int* devices, int n_devices, ..)` of SURVEY.md 8b.  The multi-device
+ *     context owns one context per device (vrfs_mctx_device_ctx gives them for the per-device entry points), enables peer access
+ *     between them, shards verify batches by index range and runs the MSM exchange with device 0 as the folding rank.  Host
+ *     buffers should be pinned, otherwise the per-device copies serialise in the driver. */
+typedef struct vrfs_mctx vrfs_mctx;
+typedef struct vrfs_multi_bases vrfs_multi_bases;
+vrfs_status vrfs_ctx_create_multi(const int* devices, int n_devices, vrfs_mctx** out);   /* *out is set even on failure: read the error, then destroy */
+void vrfs_mctx_destroy(vrfs_mctx*);
+int vrfs_mctx_device_count(const vrfs_mctx*);
+vrfs_ctx* vrfs_mctx_device_ctx(vrfs_mctx*, int i);
+const char* vrfs_mctx_last_error(const vrfs_mctx*);
+uint64_t vrfs_mctx_launch_count(const vrfs_mctx*);
+vrfs_status vrfs_multi_ietf_verify_batch(vrfs_mctx*, vrfs_suite, size_t n, const uint8_t* pk, const uint8_t* input, const uint8_t* output,
+                                         const uint8_t* c, const uint8_t* s, const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_ok,
+                                         uint8_t* out_status /* may be NULL */);
+vrfs_status vrfs_multi_msm_g1_prepare(vrfs_mctx*, size_t n, const uint8_t* bases /*n*96*/, vrfs_multi_bases** out);
+vrfs_status vrfs_multi_msm_g1_prepared(vrfs_mctx*, const vrfs_multi_bases*, const uint8_t* scalars /*n_columns*n*32*/, int n_columns, uint8_t* out /*n_columns*96*/);
+vrfs_status vrfs_multi_ring_commit(vrfs_mctx*, const vrfs_multi_bases* srs_lagrange, size_t keyset_part_size, size_t n_keys, const uint8_t* keys,
+                                   const uint8_t* padding, size_t n_tail, const uint8_t* tail, uint8_t* out_commitment /*3*96*/);
+void vrfs_multi_msm_g1_release(vrfs_multi_bases*);
 
 /* ---- ring fixed columns and their commitments -----------------------------------------------------------
  * What `ring` -> RingContext::verifier_key / prover_key -> ring-proof `index` -> PiopParams::fixed_columns + FixedColumns::commit

@@ -3,7 +3,8 @@
 // /root/reference/src/lib.rs:13-17: Suite, Secret, Public, Input, Output, ietf, pedersen, codec) and no Rust toolchain exists
 // in the build image, so this is the compiled-language host side: same names, same argument meaning, and the reference's
 // error behaviour mapped onto batches:
-//     Result<(), Error>   ->  std::vector<uint8_t>, 1 = Ok(()), 0 = Err(VerificationFailure | InvalidData)
+//     Result<(), Error>   ->  std::vector<uint8_t> ok flags (1 = Ok(())) plus, on request, one vrfs::Error per item
+//                             (Error::None / VerificationFailure / InvalidData - the variant the crate would return)
 //     Option<Input>       ->  Input + ok flags
 // Every type holds a BATCH of n values in the ABI's layout (scalars 32 B LE, points affine x||y 64 B LE); every method is one
 // call into libvrfs_b200.so.  Whole-call failures (CUDA errors, bad arguments) throw vrfs::CallError - they are never turned
@@ -21,6 +22,11 @@
 namespace vrfs {
 
 using Bytes = std::vector<uint8_t>;
+// ark_vrf::Error per item (vrfs_item_status of the C ABI); None stands for Ok(())
+enum class Error : uint8_t { None = VRFS_ITEM_OK, VerificationFailure = VRFS_ITEM_VERIFICATION_FAILURE, InvalidData = VRFS_ITEM_INVALID_DATA };
+using Errors = std::vector<Error>;
+static_assert(sizeof(Error) == 1, "Errors is handed to the C ABI as a byte array");
+inline uint8_t* status_ptr(Errors* e, size_t n) { if (!e) return nullptr; e->assign(n, Error::None); return reinterpret_cast<uint8_t*>(e->data()); }
 
 struct CallError : std::runtime_error {
   vrfs_status status;
@@ -73,6 +79,7 @@ struct Suite {
   size_t point_enc_len() const { return (size_t)vrfs_suite_point_enc_len(id); }
   size_t ietf_signature_len() const { return (size_t)vrfs_suite_ietf_signature_len(id); }
   size_t pedersen_signature_len() const { return (size_t)vrfs_suite_pedersen_signature_len(id); }
+  size_t pedersen_proof_len() const { return (size_t)vrfs_suite_pedersen_proof_len(id); }
 };
 
 struct Points { Suite suite; Bytes xy; size_t size() const { return xy.size() / 64; } };   // n affine points
@@ -105,14 +112,15 @@ struct Proof { Bytes c, s; };                            // n x 32-byte little-e
 }
 namespace pedersen {
 struct Proof { Bytes raw; };                             // n x 256: pk_com || r || ok (64 B affine each) || s || sb
+struct SerializedProof { Bytes bytes; };                 // n x Suite::pedersen_proof_len(): the proof's CanonicalSerialize (160 B for Bandersnatch)
 }
 
 struct Public : Points {
   // ietf::Verifier::verify
-  Bytes verify(const Input& input, const Output& output, const std::vector<Bytes>& ad, const ietf::Proof& proof) const {
+  Bytes verify(const Input& input, const Output& output, const std::vector<Bytes>& ad, const ietf::Proof& proof, Errors* errors = nullptr) const {
     Packed a(ad); size_t n = size(); Bytes ok(n);
     suite.engine->check(vrfs_ietf_verify_batch(suite.engine->ctx(), suite.id, n, xy.data(), input.xy.data(), output.xy.data(), proof.c.data(),
-                                               proof.s.data(), a.ptr(), a.off.data(), ok.data()));
+                                               proof.s.data(), a.ptr(), a.off.data(), ok.data(), status_ptr(errors, n)));
     return ok;
   }
   Bytes serialize_compressed() const {
@@ -129,10 +137,10 @@ struct Public : Points {
   }
   // serialised keys + VRF input data + serialised signatures (Output || ietf::Proof) -> ok flags and Output::hash
   static std::pair<Bytes, Bytes> verify_signatures(const Suite& s, const Bytes& pk_enc, const std::vector<Bytes>& datas, const Bytes& sigs,
-                                                   const std::vector<Bytes>& ad) {
+                                                   const std::vector<Bytes>& ad, Errors* errors = nullptr) {
     Packed d(datas), a(ad); size_t n = d.size(); Bytes ok(n), beta(n * s.hash_len());
     s.engine->check(vrfs_ietf_verify_wire_batch(s.engine->ctx(), s.id, n, pk_enc.data(), d.ptr(), d.off.data(), sigs.data(), a.ptr(), a.off.data(),
-                                                ok.data(), beta.data()));
+                                                ok.data(), beta.data(), status_ptr(errors, n)));
     return {std::move(ok), std::move(beta)};
   }
 };
@@ -167,6 +175,13 @@ struct Secret {
                                                   a.off.data(), p.raw.data(), bl.data()));
     return {std::move(p), std::move(bl)};
   }
+  // the same with the proof already in its serialised (wire) form
+  std::pair<pedersen::SerializedProof, Bytes> pedersen_prove_serialized(const Input& input, const Output& output, const std::vector<Bytes>& ad) const {
+    Packed a(ad); size_t n = size(); pedersen::SerializedProof p{Bytes(suite.pedersen_proof_len() * n)}; Bytes bl(32 * n);
+    suite.engine->check(vrfs_pedersen_prove_compressed_batch(suite.engine->ctx(), suite.id, n, scalars.data(), input.xy.data(), output.xy.data(), a.ptr(),
+                                                             a.off.data(), p.bytes.data(), bl.data()));
+    return {std::move(p), std::move(bl)};
+  }
   // Input::new(data) -> output -> ietf prove -> serialised signatures point_encode(Output) || c || s
   std::pair<Bytes, Bytes> sign(const std::vector<Bytes>& datas, const std::vector<Bytes>& ad) const {
     Packed d(datas), a(ad); size_t n = size(); Bytes sig(n * suite.ietf_signature_len()), ok(n);
@@ -178,9 +193,17 @@ struct Secret {
 
 namespace pedersen {
 // pedersen::Verifier::verify (needs no public key)
-inline Bytes verify(const Suite& s, const Input& input, const Output& output, const std::vector<Bytes>& ad, const Proof& proof) {
+inline Bytes verify(const Suite& s, const Input& input, const Output& output, const std::vector<Bytes>& ad, const Proof& proof, Errors* errors = nullptr) {
   Packed a(ad); size_t n = input.size(); Bytes ok(n);
-  s.engine->check(vrfs_pedersen_verify_batch(s.engine->ctx(), s.id, n, input.xy.data(), output.xy.data(), proof.raw.data(), a.ptr(), a.off.data(), ok.data()));
+  s.engine->check(vrfs_pedersen_verify_batch(s.engine->ctx(), s.id, n, input.xy.data(), output.xy.data(), proof.raw.data(), a.ptr(), a.off.data(), ok.data(),
+                                             status_ptr(errors, n)));
+  return ok;
+}
+// Proof::deserialize_compressed (validated) + verify
+inline Bytes verify(const Suite& s, const Input& input, const Output& output, const std::vector<Bytes>& ad, const SerializedProof& proof, Errors* errors = nullptr) {
+  Packed a(ad); size_t n = input.size(); Bytes ok(n);
+  s.engine->check(vrfs_pedersen_verify_compressed_batch(s.engine->ctx(), s.id, n, input.xy.data(), output.xy.data(), proof.bytes.data(), a.ptr(), a.off.data(),
+                                                        ok.data(), status_ptr(errors, n)));
   return ok;
 }
 }  // namespace pedersen

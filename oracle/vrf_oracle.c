@@ -694,7 +694,12 @@ static void parallel_for(size_t n, int nthreads, item_fn fn, void *ctx) {
 
 typedef struct {
     const suite_t *S; const uint8_t *a, *b, *c, *d, *e, *ad; const uint64_t *off; uint8_t *o1, *o2, *o3;
+    uint8_t *st;   /* optional per-item Result<(), Error>: 0 Ok, 1 Error::VerificationFailure, 2 Error::InvalidData */
 } bctx;
+#define ST_OK 0
+#define ST_VERIFICATION_FAILURE 1
+#define ST_INVALID_DATA 2
+#define SET_ST(x, i, v) do { if ((x)->st) (x)->st[i] = (uint8_t)(v); } while (0)
 #define AD_PTR(x, i) ((x)->ad && (x)->off ? (x)->ad + (x)->off[i] : (const uint8_t *)"")
 #define AD_LEN(x, i) ((x)->ad && (x)->off ? (size_t)((x)->off[(i) + 1] - (x)->off[i]) : (size_t)0)
 
@@ -768,11 +773,19 @@ static void it_ietf_verify(void *p, size_t i) {
     int ok = load_point(C, &Y, x->a + 64 * i) & load_point(C, &I, x->b + 64 * i) & load_point(C, &O, x->c + 64 * i);
     ok = ok && aff_on_curve(C, &Y) && aff_on_curve(C, &I) && aff_on_curve(C, &O);   /* typed Public/Input/Output are on-curve by construction */
     load_scalar(C, &c, x->d + 32 * i); load_scalar(C, &s, x->e + 32 * i);
-    x->o1[i] = (uint8_t)(ok && ietf_verify_one(x->S, &Y, &I, &O, &c, &s, AD_PTR(x, i), AD_LEN(x, i)));
+    /* values that no typed Public / Input / Output can hold (non-canonical, off the curve, the un-encodable short-Weierstrass
+     * identity) are what deserialisation rejects with Error::InvalidData; a proof that does not check is VerificationFailure */
+    if (ok && !C->is_te && (Y.inf || I.inf || O.inf)) ok = 0;
+    if (!ok) { x->o1[i] = 0; SET_ST(x, i, ST_INVALID_DATA); return; }
+    const int good = ietf_verify_one(x->S, &Y, &I, &O, &c, &s, AD_PTR(x, i), AD_LEN(x, i));
+    x->o1[i] = (uint8_t)good; SET_ST(x, i, good ? ST_OK : ST_VERIFICATION_FAILURE);
+}
+void oracle_ietf_verify_status_batch(int suite, size_t n, const uint8_t *pk, const uint8_t *input, const uint8_t *output, const uint8_t *c, const uint8_t *s, const uint8_t *ad, const uint64_t *ad_off, uint8_t *out_ok, uint8_t *out_status, int nthreads) {
+    bctx x = {0}; x.S = get_suite(suite); x.a = pk; x.b = input; x.c = output; x.d = c; x.e = s; x.ad = ad; x.off = ad_off; x.o1 = out_ok; x.st = out_status;
+    parallel_for(n, nthreads, it_ietf_verify, &x);
 }
 void oracle_ietf_verify_batch(int suite, size_t n, const uint8_t *pk, const uint8_t *input, const uint8_t *output, const uint8_t *c, const uint8_t *s, const uint8_t *ad, const uint64_t *ad_off, uint8_t *out_ok, int nthreads) {
-    bctx x = {0}; x.S = get_suite(suite); x.a = pk; x.b = input; x.c = output; x.d = c; x.e = s; x.ad = ad; x.off = ad_off; x.o1 = out_ok;
-    parallel_for(n, nthreads, it_ietf_verify, &x);
+    oracle_ietf_verify_status_batch(suite, n, pk, input, output, c, s, ad, ad_off, out_ok, NULL, nthreads);
 }
 static void it_ped_prove(void *p, size_t i) {
     bctx *x = p; const curve *C = x->S->C; fe sk, bl; aff I, O; ped_proof pr;
@@ -790,11 +803,17 @@ static void it_ped_verify(void *p, size_t i) {
     int ok = load_point(C, &I, x->a + 64 * i) & load_point(C, &O, x->b + 64 * i) & load_point(C, &pr.Yb, pb) & load_point(C, &pr.R, pb + 64) & load_point(C, &pr.Ok, pb + 128);
     ok = ok && aff_on_curve(C, &I) && aff_on_curve(C, &O) && aff_on_curve(C, &pr.Yb) && aff_on_curve(C, &pr.R) && aff_on_curve(C, &pr.Ok);
     load_scalar(C, &pr.s, pb + 192); load_scalar(C, &pr.sb, pb + 224);
-    x->o1[i] = (uint8_t)(ok && pedersen_verify_one(x->S, &I, &O, &pr, AD_PTR(x, i), AD_LEN(x, i)));
+    if (ok && !C->is_te && (I.inf || O.inf || pr.Yb.inf || pr.R.inf || pr.Ok.inf)) ok = 0;
+    if (!ok) { x->o1[i] = 0; SET_ST(x, i, ST_INVALID_DATA); return; }
+    const int good = pedersen_verify_one(x->S, &I, &O, &pr, AD_PTR(x, i), AD_LEN(x, i));
+    x->o1[i] = (uint8_t)good; SET_ST(x, i, good ? ST_OK : ST_VERIFICATION_FAILURE);
+}
+void oracle_pedersen_verify_status_batch(int suite, size_t n, const uint8_t *input, const uint8_t *output, const uint8_t *proof, const uint8_t *ad, const uint64_t *ad_off, uint8_t *out_ok, uint8_t *out_status, int nthreads) {
+    bctx x = {0}; x.S = get_suite(suite); x.a = input; x.b = output; x.c = proof; x.ad = ad; x.off = ad_off; x.o1 = out_ok; x.st = out_status;
+    parallel_for(n, nthreads, it_ped_verify, &x);
 }
 void oracle_pedersen_verify_batch(int suite, size_t n, const uint8_t *input, const uint8_t *output, const uint8_t *proof, const uint8_t *ad, const uint64_t *ad_off, uint8_t *out_ok, int nthreads) {
-    bctx x = {0}; x.S = get_suite(suite); x.a = input; x.b = output; x.c = proof; x.ad = ad; x.off = ad_off; x.o1 = out_ok;
-    parallel_for(n, nthreads, it_ped_verify, &x);
+    oracle_pedersen_verify_status_batch(suite, n, input, output, proof, ad, ad_off, out_ok, NULL, nthreads);
 }
 
 /* ======================================================================================
@@ -857,6 +876,7 @@ static void it_verify_wire(void *p, size_t i) {
     bctx *x = p; const suite_t *S = x->S; const curve *C = S->C; size_t PL = S->sec1 ? 33 : 32, SL = PL + (size_t)S->clen + 32;
     const uint8_t *sig = x->e + SL * i; aff Y, I, O; fe c, s, m;
     x->o1[i] = 0; if (x->o2) memset(x->o2 + (size_t)(S->is512 ? 64 : 32) * i, 0, S->is512 ? 64 : 32);
+    SET_ST(x, i, ST_INVALID_DATA);                                                       /* every early return below is a failed deserialisation */
     if (!dec_point_checked(S, &Y, x->a + PL * i)) return;                                /* Public::deserialize_compressed */
     if (!dec_point_checked(S, &O, sig)) return;                                          /* Output */
     if (!C->is_te && (Y.inf || O.inf)) return;
@@ -869,14 +889,19 @@ static void it_verify_wire(void *p, size_t i) {
     if (!data_to_point(S, &I, x->b + x->off[i], (size_t)(x->off[i + 1] - x->off[i]))) return;   /* Input::new */
     const uint8_t *ad = x->c ? x->c + ((const uint64_t *)x->d)[i] : (const uint8_t *)"";
     size_t adlen = x->c ? (size_t)(((const uint64_t *)x->d)[i + 1] - ((const uint64_t *)x->d)[i]) : 0;
-    if (!ietf_verify_one(S, &Y, &I, &O, &c, &s, ad, adlen)) return;
+    if (!ietf_verify_one(S, &Y, &I, &O, &c, &s, ad, adlen)) { SET_ST(x, i, ST_VERIFICATION_FAILURE); return; }
+    SET_ST(x, i, ST_OK);
     x->o1[i] = 1; if (x->o2) suite_point_to_hash(S, &O, x->o2 + (size_t)(S->is512 ? 64 : 32) * i);
 }
 /* Public::deserialize + Input::new(data) + Output/Proof::deserialize + ietf::Verifier::verify (+ Output::hash for accepted items) */
+void oracle_ietf_verify_wire_status_batch(int suite, size_t n, const uint8_t *pk_enc, const uint8_t *data, const uint64_t *data_off, const uint8_t *sig,
+                                          const uint8_t *ad, const uint64_t *ad_off, uint8_t *out_ok, uint8_t *out_hash, uint8_t *out_status, int nthreads) {
+    bctx x = {0}; x.S = get_suite(suite); x.a = pk_enc; x.b = data; x.off = data_off; x.e = sig; x.c = ad; x.d = (const uint8_t *)ad_off; x.o1 = out_ok; x.o2 = out_hash; x.st = out_status;
+    parallel_for(n, nthreads, it_verify_wire, &x);
+}
 void oracle_ietf_verify_wire_batch(int suite, size_t n, const uint8_t *pk_enc, const uint8_t *data, const uint64_t *data_off, const uint8_t *sig,
                                    const uint8_t *ad, const uint64_t *ad_off, uint8_t *out_ok, uint8_t *out_hash, int nthreads) {
-    bctx x = {0}; x.S = get_suite(suite); x.a = pk_enc; x.b = data; x.off = data_off; x.e = sig; x.c = ad; x.d = (const uint8_t *)ad_off; x.o1 = out_ok; x.o2 = out_hash;
-    parallel_for(n, nthreads, it_verify_wire, &x);
+    oracle_ietf_verify_wire_status_batch(suite, n, pk_enc, data, data_off, sig, ad, ad_off, out_ok, out_hash, NULL, nthreads);
 }
 
 /* pedersen wire form: point_encode(Output) || point_encode(pk_com) || point_encode(r) || point_encode(ok) || s || sb
@@ -910,18 +935,24 @@ static int dec_scalar_canonical(const suite_t *S, fe *k_raw, const uint8_t *in) 
 static void it_ped_verify_wire(void *p, size_t i) {
     bctx *x = p; const suite_t *S = x->S; size_t PL = S->sec1 ? 33 : 32, SL = 4 * PL + 64;
     const uint8_t *sig = x->e + SL * i; aff I, O; ped_proof pr;
-    x->o1[i] = 0;
+    x->o1[i] = 0; SET_ST(x, i, ST_INVALID_DATA);
     if (!dec_point_checked(S, &O, sig) || !dec_point_checked(S, &pr.Yb, sig + PL) || !dec_point_checked(S, &pr.R, sig + 2 * PL) || !dec_point_checked(S, &pr.Ok, sig + 3 * PL)) return;
     if (!dec_scalar_canonical(S, &pr.s, sig + 4 * PL) || !dec_scalar_canonical(S, &pr.sb, sig + 4 * PL + 32)) return;
     if (!data_to_point(S, &I, x->b + x->off[i], (size_t)(x->off[i + 1] - x->off[i]))) return;
     const uint8_t *ad = x->c ? x->c + ((const uint64_t *)x->d)[i] : (const uint8_t *)"";
     size_t adlen = x->c ? (size_t)(((const uint64_t *)x->d)[i + 1] - ((const uint64_t *)x->d)[i]) : 0;
+    if (!S->C->is_te && (I.inf || O.inf || pr.Yb.inf || pr.R.inf || pr.Ok.inf)) return;
     x->o1[i] = (uint8_t)pedersen_verify_one(S, &I, &O, &pr, ad, adlen);
+    SET_ST(x, i, x->o1[i] ? ST_OK : ST_VERIFICATION_FAILURE);
+}
+void oracle_pedersen_verify_wire_status_batch(int suite, size_t n, const uint8_t *data, const uint64_t *data_off, const uint8_t *sig,
+                                              const uint8_t *ad, const uint64_t *ad_off, uint8_t *out_ok, uint8_t *out_status, int nthreads) {
+    bctx x = {0}; x.S = get_suite(suite); x.b = data; x.off = data_off; x.e = sig; x.c = ad; x.d = (const uint8_t *)ad_off; x.o1 = out_ok; x.st = out_status;
+    parallel_for(n, nthreads, it_ped_verify_wire, &x);
 }
 void oracle_pedersen_verify_wire_batch(int suite, size_t n, const uint8_t *data, const uint64_t *data_off, const uint8_t *sig,
                                        const uint8_t *ad, const uint64_t *ad_off, uint8_t *out_ok, int nthreads) {
-    bctx x = {0}; x.S = get_suite(suite); x.b = data; x.off = data_off; x.e = sig; x.c = ad; x.d = (const uint8_t *)ad_off; x.o1 = out_ok;
-    parallel_for(n, nthreads, it_ped_verify_wire, &x);
+    oracle_pedersen_verify_wire_status_batch(suite, n, data, data_off, sig, ad, ad_off, out_ok, NULL, nthreads);
 }
 
 /* ======================================================================================

@@ -86,6 +86,19 @@ void oracle_pedersen_sign_wire_batch(int suite, size_t n, const uint8_t *sk, con
                                      const uint8_t *ad, const uint64_t *ad_off, uint8_t *out_sig, uint8_t *out_blinding, uint8_t *out_ok, int nthreads);
 void oracle_pedersen_verify_wire_batch(int suite, size_t n, const uint8_t *data, const uint64_t *data_off, const uint8_t *sig,
                                        const uint8_t *ad, const uint64_t *ad_off, uint8_t *out_ok, int nthreads);
+/* the same verifiers reporting which `Error` variant the reference's Result<(), Error> carries (lib.rs:13-17 `Error`):
+ * out_status[i] = 0 Ok(()), 1 Error::VerificationFailure (well-formed values, the proof does not check), 2 Error::InvalidData
+ * (a value no typed Public / Input / Output / Proof can hold: non-canonical, off the curve, outside the prime-order subgroup on
+ * the wire entry points, the un-encodable short-Weierstrass identity, no input point found). */
+void oracle_ietf_verify_status_batch(int suite, size_t n, const uint8_t *pk, const uint8_t *input, const uint8_t *output,
+                                     const uint8_t *c, const uint8_t *s, const uint8_t *ad, const uint64_t *ad_off,
+                                     uint8_t *out_ok, uint8_t *out_status, int nthreads);
+void oracle_pedersen_verify_status_batch(int suite, size_t n, const uint8_t *input, const uint8_t *output, const uint8_t *proof,
+                                         const uint8_t *ad, const uint64_t *ad_off, uint8_t *out_ok, uint8_t *out_status, int nthreads);
+void oracle_ietf_verify_wire_status_batch(int suite, size_t n, const uint8_t *pk_enc, const uint8_t *data, const uint64_t *data_off, const uint8_t *sig,
+                                          const uint8_t *ad, const uint64_t *ad_off, uint8_t *out_ok, uint8_t *out_hash, uint8_t *out_status, int nthreads);
+void oracle_pedersen_verify_wire_status_batch(int suite, size_t n, const uint8_t *data, const uint64_t *data_off, const uint8_t *sig,
+                                              const uint8_t *ad, const uint64_t *ad_off, uint8_t *out_ok, uint8_t *out_status, int nthreads);
 /* ark-ec VariableBaseMSM::msm over BLS12-381 G1: n_columns scalar columns over one base vector.
  * bases n*96 B, scalars n_columns*n*32 B (column-major), out n_columns*96 B (identity = zeros). */
 void oracle_msm_g1(size_t n, const uint8_t *bases, const uint8_t *scalars, int n_columns, uint8_t *out, int nthreads);

@@ -37,10 +37,26 @@ static void prove_verify_works(const Suite& suite, const char* name) {
   Output output = secret.output(input);
   ietf::Proof proof = secret.prove(input, output, ad);
   CHECK(all(pub.verify(input, output, ad, proof), 1));
-  CHECK(all(pub.verify(input, output, ad2, proof), 0));                         // Error::VerificationFailure
+  Errors errs;
+  CHECK(all(pub.verify(input, output, ad2, proof, &errs), 0));                  // Error::VerificationFailure
+  for (auto e : errs) CHECK(e == Error::VerificationFailure);
+  {   // a value no typed Input can hold (off the curve) is Error::InvalidData, and only that item
+    Input bad = input; bad.xy[5] ^= 0x10;
+    Bytes okb = pub.verify(bad, output, ad, proof, &errs);
+    CHECK(okb[0] == 0 && errs[0] == Error::InvalidData && okb[1] == 1 && errs[1] == Error::None);
+  }
   auto [ped, blinding] = secret.pedersen_prove(input, output, ad);
   CHECK(all(pedersen::verify(suite, input, output, ad, ped), 1));
-  CHECK(all(pedersen::verify(suite, input, output, ad2, ped), 0));
+  CHECK(all(pedersen::verify(suite, input, output, ad2, ped, &errs), 0));
+  for (auto e : errs) CHECK(e == Error::VerificationFailure);
+  {   // the serialised proof (160 B for the 32-byte codecs): same blinding, verifies, and a flipped byte of `s` fails only its item
+    auto [sp, bl2] = secret.pedersen_prove_serialized(input, output, ad);
+    CHECK(bl2 == blinding && sp.bytes.size() == n * suite.pedersen_proof_len());
+    CHECK(all(pedersen::verify(suite, input, output, ad, sp), 1));
+    sp.bytes[3 * suite.point_enc_len() + 7] ^= 1;
+    Bytes okp = pedersen::verify(suite, input, output, ad, sp, &errs);
+    CHECK(okp[0] == 0 && okp[1] == 1 && errs[0] != Error::None && errs[1] == Error::None);
+  }
   CHECK(blinding.size() == 32 * n && output.hash().size() == suite.hash_len() * n);
   // serialisation: keys round-trip with validation; signatures straight off the wire
   auto [pub2, kok] = Public::deserialize_compressed(suite, pub.serialize_compressed());
@@ -115,7 +131,7 @@ int main() {
     }
     // a whole-call failure is an exception, not a verdict
     bool threw = false;
-    try { vrfs_status st = vrfs_ietf_verify_batch(eng.ctx(), (vrfs_suite)9, 1, sig.data(), sig.data(), sig.data(), sig.data(), sig.data(), nullptr, nullptr, sig.data()); eng.check(st); }
+    try { vrfs_status st = vrfs_ietf_verify_batch(eng.ctx(), (vrfs_suite)9, 1, sig.data(), sig.data(), sig.data(), sig.data(), sig.data(), nullptr, nullptr, sig.data(), nullptr); eng.check(st); }
     catch (const CallError& e) { threw = e.status == VRFS_BAD_ARG; }
     CHECK(threw);
   } catch (const CallError& e) {

@@ -118,11 +118,12 @@ def ietf_prove(suite, sk, inp, outp, ads=None, nthreads=NTHREADS):
     return c, s
 
 
-def ietf_verify(suite, pk, inp, outp, c, s, ads=None, nthreads=NTHREADS):
+def ietf_verify(suite, pk, inp, outp, c, s, ads=None, nthreads=NTHREADS, status=False):
+    """status=True: (ok, per-item Result<(), Error>: 0 Ok / 1 VerificationFailure / 2 InvalidData)"""
     pk = _u8(pk, (-1, 64)); inp = _u8(inp, (-1, 64)); outp = _u8(outp, (-1, 64)); c = _u8(c, (-1, 32)); s = _u8(s, (-1, 32)); n = len(pk)
-    ad, off = _ad(ads, n); ok = np.zeros(n, np.uint8)
-    lib().oracle_ietf_verify_batch(suite, C.c_size_t(n), _p(pk), _p(inp), _p(outp), _p(c), _p(s), _p(ad), _p(off), _p(ok), nthreads)
-    return ok
+    ad, off = _ad(ads, n); ok = np.zeros(n, np.uint8); st = np.zeros(n, np.uint8) if status else None
+    lib().oracle_ietf_verify_status_batch(suite, C.c_size_t(n), _p(pk), _p(inp), _p(outp), _p(c), _p(s), _p(ad), _p(off), _p(ok), _p(st), nthreads)
+    return (ok, st) if status else ok
 
 
 def pedersen_prove(suite, sk, inp, outp, ads=None, nthreads=NTHREADS):
@@ -132,11 +133,11 @@ def pedersen_prove(suite, sk, inp, outp, ads=None, nthreads=NTHREADS):
     return proof, bl
 
 
-def pedersen_verify(suite, inp, outp, proof, ads=None, nthreads=NTHREADS):
+def pedersen_verify(suite, inp, outp, proof, ads=None, nthreads=NTHREADS, status=False):
     inp = _u8(inp, (-1, 64)); outp = _u8(outp, (-1, 64)); proof = _u8(proof, (-1, 256)); n = len(inp)
-    ad, off = _ad(ads, n); ok = np.zeros(n, np.uint8)
-    lib().oracle_pedersen_verify_batch(suite, C.c_size_t(n), _p(inp), _p(outp), _p(proof), _p(ad), _p(off), _p(ok), nthreads)
-    return ok
+    ad, off = _ad(ads, n); ok = np.zeros(n, np.uint8); st = np.zeros(n, np.uint8) if status else None
+    lib().oracle_pedersen_verify_status_batch(suite, C.c_size_t(n), _p(inp), _p(outp), _p(proof), _p(ad), _p(off), _p(ok), _p(st), nthreads)
+    return (ok, st) if status else ok
 
 
 def msm_g1(bases, scalars, n_columns=1, nthreads=NTHREADS):
@@ -173,12 +174,15 @@ def ietf_sign_wire(suite, sk, datas, ads=None, nthreads=NTHREADS):
     return sig, ok
 
 
-def ietf_verify_wire(suite, pk_enc, datas, sig, ads=None, want_hash=True, nthreads=NTHREADS):
+def ietf_verify_wire(suite, pk_enc, datas, sig, ads=None, want_hash=True, nthreads=NTHREADS, status=False):
     L = lib().oracle_point_enc_len(suite); pk_enc = _u8(pk_enc, (-1, L)); n = len(pk_enc)
     sig = _u8(sig, (n, ietf_signature_len(suite))); data, off = pack_var(datas); ad, aoff = _ad(ads, n)
     ok = np.zeros(n, np.uint8); h = np.zeros((n, lib().oracle_hash_len(suite)), np.uint8) if want_hash else None
-    lib().oracle_ietf_verify_wire_batch(suite, C.c_size_t(n), _p(pk_enc), _p(data), _p(off), _p(sig), _p(ad), _p(aoff), _p(ok), _p(h), nthreads)
-    return (ok, h) if want_hash else ok
+    st = np.zeros(n, np.uint8) if status else None
+    lib().oracle_ietf_verify_wire_status_batch(suite, C.c_size_t(n), _p(pk_enc), _p(data), _p(off), _p(sig), _p(ad), _p(aoff), _p(ok), _p(h), _p(st), nthreads)
+    res = (ok, h) if want_hash else (ok,)
+    res = res + (st,) if status else res
+    return res if len(res) > 1 else res[0]
 
 
 def pedersen_signature_len(suite):
@@ -192,8 +196,8 @@ def pedersen_sign_wire(suite, sk, datas, ads=None, nthreads=NTHREADS):
     return sig, bl, ok
 
 
-def pedersen_verify_wire(suite, datas, sig, ads=None, nthreads=NTHREADS):
+def pedersen_verify_wire(suite, datas, sig, ads=None, nthreads=NTHREADS, status=False):
     sig = _u8(sig, (-1, pedersen_signature_len(suite))); n = len(sig); data, off = pack_var(datas); ad, aoff = _ad(ads, n)
-    ok = np.zeros(n, np.uint8)
-    lib().oracle_pedersen_verify_wire_batch(suite, C.c_size_t(n), _p(data), _p(off), _p(sig), _p(ad), _p(aoff), _p(ok), nthreads)
-    return ok
+    ok = np.zeros(n, np.uint8); st = np.zeros(n, np.uint8) if status else None
+    lib().oracle_pedersen_verify_wire_status_batch(suite, C.c_size_t(n), _p(data), _p(off), _p(sig), _p(ad), _p(aoff), _p(ok), _p(st), nthreads)
+    return (ok, st) if status else ok

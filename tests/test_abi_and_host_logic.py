@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol(lib):
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for s in declared:
         assert hasattr(lib, s), s
-    assert lib.vrfs_abi_version() == 1
+    assert lib.vrfs_abi_version() == 2
     assert [lib.vrfs_suite_challenge_len(i) for i in range(3)] == [32, 16, 16]
     assert [lib.vrfs_suite_hash_len(i) for i in range(3)] == [64, 64, 32]
     assert [lib.vrfs_suite_point_enc_len(i) for i in range(3)] == [32, 32, 33]
