@@ -47,7 +47,7 @@ VRFS_HD inline MsmPlan msm_plan(uint32_t n, uint32_t ncol, int prepared, int c_o
   // tools/msm_sweep.py with scalars uniform below r (profiles/r1r_msm_sweep.json): c = 16 spends no window on the carry of bit 254
   if (prepared) p.c = lg <= 9 ? 8 : lg <= 12 ? 10 : lg <= 16 ? 13 : 16;
   else p.c = lg <= 9 ? 7 : lg <= 11 ? 9 : lg <= 13 ? 11 : lg <= 15 ? 12 : 13;
-  if (c_override >= 2 && c_override <= 18) p.c = c_override;      // caller's window hint (vrfs_msm_g1_prepare_ex; tools/msm_sweep.py)
+  if (c_override >= 8 && c_override <= 18) p.c = c_override;      // caller's window hint (vrfs_msm_g1_prepare_ex; tools/msm_sweep.py)
   p.windows = (255 + p.c) / p.c;          // 255 scalar bits + the top carry of the signed recoding
   p.nb = 1 << (p.c - 1);
   p.seg_windows = prepared ? 1 : p.windows;

@@ -277,7 +277,10 @@ extern "C" vrfs_status vrfs_multi_msm_g1_prepared(vrfs_mctx* m, const vrfs_multi
   if (n_columns < 1 || n_columns > VRFS_PEER_MAXCOL || !scalars || !out) return mfail(m, VRFS_BAD_ARG, "bad argument");
   std::vector<std::unique_ptr<CallGuard>> guards;
   for (int g = 0; g < m->n; g++) guards.emplace_back(new CallGuard(m->dev[g]));
-  for (int g = 0; g < m->n; g++) {
+  // The folding device (0) is enqueued LAST: its final kernel spins until the other devices' partials arrive, and with peer access
+  // enabled a cudaMalloc on ANY device has to update the page tables of its peers - it would block behind that spinning kernel
+  // until the exchange timed out.  Enqueued last, device 0 only ever waits for work that is already in flight.
+  for (int g = m->n - 1; g >= 0; g--) {
     vrfs_ctx* ctx = m->dev[g];
     const size_t lo = h->lo[g], cnt = h->lo[g + 1] - lo;
     PeerArgs pa;
@@ -306,7 +309,7 @@ extern "C" vrfs_status vrfs_multi_ring_commit(vrfs_mctx* m, const vrfs_multi_bas
   if (n_keys > keyset_part_size || keyset_part_size + n_tail > h->n) return mfail(m, VRFS_BAD_ARG, "need n_keys <= keyset_part_size and keyset_part_size + n_tail <= domain size");
   std::vector<std::unique_ptr<CallGuard>> guards;
   for (int g = 0; g < m->n; g++) guards.emplace_back(new CallGuard(m->dev[g]));
-  for (int g = 0; g < m->n; g++) {
+  for (int g = m->n - 1; g >= 0; g--) {                  // the folding device last (see vrfs_multi_msm_g1_prepared)
     vrfs_ctx* ctx = m->dev[g];
     const size_t lo = h->lo[g], cnt = h->lo[g + 1] - lo;
     PeerArgs pa;

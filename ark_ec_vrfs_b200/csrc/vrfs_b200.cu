@@ -1557,13 +1557,15 @@ static vrfs_status msm_prepare_impl(vrfs_ctx* ctx, size_t n, const uint8_t* base
   *out = nullptr;
   if (n == 0 || !bases) return fail(ctx, VRFS_BAD_ARG, "empty base vector");
   if (n > (1u << 24)) return fail(ctx, VRFS_BAD_ARG, "prepared MSM size above 2^24 is not supported");
-  if (window_bits != 0 && (window_bits < 2 || window_bits > 18)) return fail(ctx, VRFS_BAD_ARG, "window_bits must be 0 (automatic) or 2..18");
+  // ceil(256 / c) windows must fit k_msm_prepare's per-thread arrays (MSM_MAX_WINDOWS)
+  if (window_bits != 0 && (window_bits < 8 || window_bits > 18)) return fail(ctx, VRFS_BAD_ARG, "window_bits must be 0 (automatic) or 8..18");
   if (threads_per_bucket != 0 && (threads_per_bucket < 1 || threads_per_bucket > 32 || (threads_per_bucket & (threads_per_bucket - 1))))
     return fail(ctx, VRFS_BAD_ARG, "threads_per_bucket must be 0 (automatic) or a power of two <= 32");
   ST(begin_call(ctx, n));
   vrfs_msm_bases* h = new (std::nothrow) vrfs_msm_bases();
   if (!h) return fail(ctx, VRFS_CUDA_ERROR, "out of host memory");
   h->ctx = ctx; h->n = n; h->tpb_hint = threads_per_bucket; h->plan = msm_plan((uint32_t)n, 1, 1, window_bits, threads_per_bucket); h->Q = nullptr;
+  if (h->plan.windows > MSM_MAX_WINDOWS) { delete h; return fail(ctx, VRFS_BAD_ARG, "internal: %d windows exceed MSM_MAX_WINDOWS", h->plan.windows); }
   cudaError_t e = cudaMalloc(&h->Q, (size_t)h->plan.windows * n * sizeof(G1Aff));
   if (e != cudaSuccess) { delete h; return fail(ctx, VRFS_CUDA_ERROR, "cudaMalloc of the prepared table failed: %s", cudaGetErrorString(e)); }
   // a failure below must not leak the table (up to GBs) nor hand out a half-built handle

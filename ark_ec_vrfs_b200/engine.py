@@ -246,10 +246,12 @@ class Engine:
         self._call("vrfs_nonce_batch", suite, C.c_size_t(n), _p(sk), _p(inp), _p(out))
         return out
 
-    def ietf_prove(self, suite, sk, inp, outp, ad=None):
+    def ietf_prove(self, suite, sk, inp, outp, ad=None, out=None):
+        """ietf::Prover::prove -> (c, s); out = (c, s) arrays to fill (e.g. views of pinned memory) instead of fresh ones"""
         sk = _u8(sk, (-1, 32)); n = len(sk); inp = _u8(inp, (n, 64)); outp = _u8(outp, (n, 64))
         adb, off = pack_var(ad, n)
-        c = np.zeros((n, 32), np.uint8); s = np.zeros((n, 32), np.uint8)
+        c, s = out if out is not None else (np.zeros((n, 32), np.uint8), np.zeros((n, 32), np.uint8))
+        assert c.shape == (n, 32) and s.shape == (n, 32) and c.dtype == np.uint8 and s.dtype == np.uint8 and c.flags.c_contiguous and s.flags.c_contiguous
         self._call("vrfs_ietf_prove_batch", suite, C.c_size_t(n), _p(sk), _p(inp), _p(outp), _p(adb), _p(off), _p(c), _p(s))
         return c, s
 
@@ -305,10 +307,11 @@ class Engine:
         return (ok, st) if status else ok
 
     # ---- pedersen
-    def pedersen_prove(self, suite, sk, inp, outp, ad=None):
+    def pedersen_prove(self, suite, sk, inp, outp, ad=None, out=None):
         sk = _u8(sk, (-1, 32)); n = len(sk); inp = _u8(inp, (n, 64)); outp = _u8(outp, (n, 64))
         adb, off = pack_var(ad, n)
-        proof = np.zeros((n, 256), np.uint8); bl = np.zeros((n, 32), np.uint8)
+        proof, bl = out if out is not None else (np.zeros((n, 256), np.uint8), np.zeros((n, 32), np.uint8))
+        assert proof.shape == (n, 256) and bl.shape == (n, 32) and proof.dtype == np.uint8 and bl.dtype == np.uint8 and proof.flags.c_contiguous and bl.flags.c_contiguous
         self._call("vrfs_pedersen_prove_batch", suite, C.c_size_t(n), _p(sk), _p(inp), _p(outp), _p(adb), _p(off), _p(proof), _p(bl))
         return proof, bl
 

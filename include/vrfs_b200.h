@@ -157,7 +157,7 @@ vrfs_status vrfs_msm_g1_bls12_381(vrfs_ctx*, size_t n, const uint8_t* bases /*n*
  * bucket set per column and no Horner chain.  Results are identical to vrfs_msm_g1_bls12_381. */
 typedef struct vrfs_msm_bases vrfs_msm_bases;
 vrfs_status vrfs_msm_g1_prepare(vrfs_ctx*, size_t n, const uint8_t* bases /*n*96*/, vrfs_msm_bases** out);
-/* the same with tuning hints: window_bits (0 = automatic, else 2..18) and threads_per_bucket (0 = automatic, else a power of two
+/* the same with tuning hints: window_bits (0 = automatic, else 8..18) and threads_per_bucket (0 = automatic, else a power of two
  * <= 32).  The results never depend on them.  On failure *out stays NULL and nothing is leaked. */
 vrfs_status vrfs_msm_g1_prepare_ex(vrfs_ctx*, size_t n, const uint8_t* bases /*n*96*/, int window_bits, int threads_per_bucket, vrfs_msm_bases** out);
 vrfs_status vrfs_msm_g1_prepared(vrfs_ctx*, const vrfs_msm_bases* bases, const uint8_t* scalars /*n_columns*n*32*/, int n_columns, uint8_t* out /*n_columns*96*/);
