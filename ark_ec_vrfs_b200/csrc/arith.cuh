@@ -272,17 +272,14 @@ HD_INLINE Fp<P> operator*(const Fp<P>& a, const Fp<P>& b) {
 #ifndef VRFS_DEDICATED_SQR
 #define VRFS_DEDICATED_SQR 1
 #endif
+// Montgomery reduction of a 2N-limb value t < p * 2^(32N) (a reduction-only pass of the even/odd accumulator pair over the low
+// half, then + high half): N^2 + N multiply-accumulates.  Plain Montgomery fields with p < 2^(32N-1) only.
 template <class P>
-HD_INLINE void mont_sqr_limbs(uint32_t* out, const uint32_t* a) {
+HD_INLINE void mont_reduce_wide(uint32_t* out, const uint32_t* t) {
   constexpr int N = P::N;
   typedef MontChains<N> C;
-  if ((P::FULL && !P::SOLINAS_P256) || !VRFS_DEDICATED_SQR) { mont_mul_limbs<P>(out, a, a); return; }
-  uint32_t t[2 * N], mod[N], u[N], v[N];
-  if constexpr (P::PM_C != 0) { C::sqr_wide(t, a); pm_fold<P>(out, t); return; }
-  else if constexpr (P::SOLINAS_P256) { C::mul_wide(t, a, a); p256_fold<P>(out, t); return; }   // a may use all 256 bits: sqr_wide needs the top bit clear
-  else {
+  uint32_t mod[N], u[N], v[N];
   for (int i = 0; i < N; i++) mod[i] = P::mod(i);
-  C::sqr_wide(t, a);
   // reduce the low half: v = even-aligned window (column 0 = v[0]), u = odd-aligned; roles swap every step
   for (int i = 0; i < N; i++) { v[i] = t[i]; u[i] = 0; }
 #pragma unroll
@@ -302,6 +299,18 @@ HD_INLINE void mont_sqr_limbs(uint32_t* out, const uint32_t* a) {
   C::add(v, v, t + N);          // + high half: < p + p^2/2^(32N) < 2p < 2^(32N)
   cond_sub_p<P>(v, 0u);
   for (int i = 0; i < N; i++) out[i] = v[i];
+}
+template <class P>
+HD_INLINE void mont_sqr_limbs(uint32_t* out, const uint32_t* a) {
+  constexpr int N = P::N;
+  typedef MontChains<N> C;
+  if ((P::FULL && !P::SOLINAS_P256) || !VRFS_DEDICATED_SQR) { mont_mul_limbs<P>(out, a, a); return; }
+  uint32_t t[2 * N];
+  if constexpr (P::PM_C != 0) { C::sqr_wide(t, a); pm_fold<P>(out, t); return; }
+  else if constexpr (P::SOLINAS_P256) { C::mul_wide(t, a, a); p256_fold<P>(out, t); return; }   // a may use all 256 bits: sqr_wide needs the top bit clear
+  else {
+    C::sqr_wide(t, a);
+    mont_reduce_wide<P>(out, t);
   }
 }
 template <class P>

@@ -98,7 +98,15 @@ HD_NOINLINE void g1_dbl(G1Pt* r, const G1Pt* p) {
 // accumulator, repeated bases and cancelling pairs - a warp almost never diverges on them).
 struct G1Xyzz { Fq381 X, Y, ZZ, ZZZ; };
 HD_INLINE void xyzz_set_identity(G1Xyzz& a) { a.X = Fq381::zero(); a.Y = Fq381::zero(); a.ZZ = Fq381::zero(); a.ZZZ = Fq381::zero(); }
-HD_NOINLINE void xyzz_madd(G1Xyzz* acc, const Fq381* x2, const Fq381* y2) {
+#ifndef MSM_MADD_INLINE
+#define MSM_MADD_INLINE 0
+#endif
+#if MSM_MADD_INLINE
+HD_INLINE
+#else
+HD_NOINLINE
+#endif
+void xyzz_madd(G1Xyzz* acc, const Fq381* x2, const Fq381* y2) {
   if (acc->ZZ.is_zero()) { acc->X = *x2; acc->Y = *y2; acc->ZZ = Fq381::one(); acc->ZZZ = Fq381::one(); return; }
   Fq381 U2 = *x2 * acc->ZZ, S2 = *y2 * acc->ZZZ;
   Fq381 P = U2 - acc->X, R = S2 - acc->Y;
