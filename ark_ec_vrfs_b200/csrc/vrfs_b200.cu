@@ -418,6 +418,9 @@ static vrfs_status launch_lincomb(vrfs_ctx* ctx, LincombArgs A, bool side = fals
   int per_sm = 0;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lincomb<C, NV, NF>, LINCOMB_THREADS, 0));
   if (per_sm < 1) per_sm = 1;
+#ifdef LINCOMB_MAXBLOCKS
+  if (per_sm > LINCOMB_MAXBLOCKS) per_sm = LINCOMB_MAXBLOCKS;       // tuning builds: resident threads per SM (the slab scales with them)
+#endif
   uint32_t blocks = (uint32_t)(ctx->sms * per_sm);
   uint32_t need = (A.n + LINCOMB_THREADS - 1) / LINCOMB_THREADS;
   if (blocks > need) blocks = need;
