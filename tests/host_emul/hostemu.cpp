@@ -187,3 +187,34 @@ extern "C" void hostemu_ntt_inv_n(int logn, uint32_t* out_canonical) {
 // BLS12-381 G1 wire format (csrc/ring.cuh) on the host
 extern "C" void hostemu_g1_compress(const uint8_t* pt96, uint8_t* out48) { g1_compress_one(out48, pt96); }
 extern "C" int hostemu_g1_decompress(const uint8_t* in48, int check_subgroup, uint8_t* out96) { return g1_decompress_one(out96, in48, check_subgroup != 0); }
+
+// BLS12-381 pairing (csrc/pairing.cuh) on the host: tower operations and the whole product check, ABI bytes in and out
+#include "../../ark_ec_vrfs_b200/csrc/pairing.cuh"
+static Fq12 f12_from_bytes(const uint8_t* b) {
+  Fq381 c[12]; uint32_t raw[12];
+  for (int k = 0; k < 12; k++) { load_le<12>(raw, b + 48 * k); c[k] = to_mont<BlsFq>(raw); }
+  return Fq12{Fq6{Fq2{c[0], c[1]}, Fq2{c[2], c[3]}, Fq2{c[4], c[5]}}, Fq6{Fq2{c[6], c[7]}, Fq2{c[8], c[9]}, Fq2{c[10], c[11]}}};
+}
+// op: 0 mul, 1 sqr, 2 inv, 3 frobenius q, 4 frobenius q^2, 5 cyclotomic squaring, 6 a * (b.c0.c0 + b.c0.c1 v + b.c1.c1 v w) sparse, 7 conj, 8 a^x, 9 final exponentiation
+extern "C" void hostemu_f12_op(int op, const uint8_t* a576, const uint8_t* b576, uint8_t* out576) {
+  Fq12 a = f12_from_bytes(a576), b = f12_from_bytes(b576), r = f12_one();
+  switch (op) {
+    case 0: r = f12_mul(a, b); break;
+    case 1: r = f12_sqr(a); break;
+    case 2: r = f12_inv(a); break;
+    case 3: r = f12_frob<1>(a); break;
+    case 4: r = f12_frob<2>(a); break;
+    case 5: r = f12_cyclotomic_sqr(a); break;
+    case 6: r = f12_mul_by_014(a, b.c0.c0, b.c0.c1, b.c1.c1); break;
+    case 7: r = f12_conj(a); break;
+    case 8: r = f12_exp_by_x(a); break;
+    case 9: r = final_exponentiation(a); break;
+  }
+  f12_store(out576, r);
+}
+extern "C" int hostemu_pairing_product(int n, const uint8_t* g1, const uint8_t* g2, unsigned negate, uint8_t* out_gt576) {
+  Fq12 e = f12_one();
+  int verdict = pairing_product_check_bytes(n, g1, g2, negate, &e);
+  if (out_gt576) f12_store(out_gt576, e);
+  return verdict;
+}
