@@ -17,6 +17,7 @@
 #include "wire.cuh"
 #include "msm.cuh"
 #include "ring.cuh"
+#include "pairing.cuh"
 
 using namespace vrfs;
 
@@ -1832,3 +1833,4 @@ extern "C" vrfs_status vrfs_g1_sum_partials(vrfs_ctx* ctx, int n_parts, int n_co
 }
 
 #include "multi_gpu.cuh"
+#include "kzg.cuh"

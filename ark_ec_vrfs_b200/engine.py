@@ -403,6 +403,24 @@ class Engine:
         self._call("vrfs_fq381_inv_batch", C.c_size_t(len(values)), _p(values), _p(out), _p(ok))
         return out, ok
 
+    # ---- BLS12-381 pairing / batched KZG opening check
+    def pairing_products(self, g1, g2, n_pairs=1, negate_masks=None, want_gt=False):
+        """n products of n_pairs pairings each: verdicts (1 = product is one, 0 = not, 2 = malformed point) [and GT values (n, 576)]"""
+        g1 = _u8(g1, (-1, n_pairs * 96)); n = len(g1); g2 = _u8(g2, (n, n_pairs * 192))
+        neg = None if negate_masks is None else np.ascontiguousarray(negate_masks, dtype=np.uint32).reshape(n)
+        ok = np.zeros(n, np.uint8); gt = np.zeros((n, 576), np.uint8) if want_gt else None
+        self._call("vrfs_pairing_product_batch", C.c_size_t(n), int(n_pairs), _p(g1), _p(g2), _p(neg), _p(ok), _p(gt))
+        return (ok, gt) if want_gt else ok
+
+    def kzg_batch_verify(self, commitments, zs, vs, proofs, rs, g2, tau_g2, check_points=1):
+        """1 accepted / 0 rejected / 2 malformed point for k openings aggregated with the coefficients rs (vrfs_kzg_batch_verify)"""
+        commitments = _u8(commitments, (-1, 96)); k = len(commitments)
+        proofs = _u8(proofs, (k, 96)); zs = _u8(zs, (k, 32)); vs = _u8(vs, (k, 32)); rs = _u8(rs, (k, 32))
+        g2 = _u8(g2, (192,)); tau_g2 = _u8(tau_g2, (192,))
+        ok = np.zeros(1, np.uint8)
+        self._call("vrfs_kzg_batch_verify", C.c_size_t(k), _p(commitments), _p(zs), _p(vs), _p(proofs), _p(rs), _p(g2), _p(tau_g2), int(check_points), _p(ok))
+        return int(ok[0])
+
     # ---- measurement
     def enable_kernel_timing(self, on=True):
         self._check(self._lib.vrfs_ctx_enable_kernel_timing(self._ctx, int(bool(on))))

@@ -409,6 +409,49 @@ def config_msm(eng, rank, world, peak_mac, hbm_peak, sizes, steps=5):
     return out
 
 
+def config_kzg(eng, sizes, steps=3):
+    """BASELINE configs[4], second half ("plus batched ring-proof verify"): k KZG openings checked at once - the 2-column MSM over
+    2k + 1 points and the product of two BLS12-381 pairings a ring-proof verifier ends in (transcript coefficients as inputs).
+    Honest openings under the bench's public tau; every size must accept, and reject with one forged value."""
+    import numpy as np
+    tau = int.from_bytes(hashlib.sha512(b"vrfs-b200-bench-tau").digest(), "little") % R_BLS
+    kmax = 1 << max(sizes)
+    rng = np.random.default_rng(4242)
+    def fr(m):
+        raw = rng.integers(0, 256, size=(m, 40), dtype=np.uint8)
+        return [int.from_bytes(r.tobytes(), "little") % R_BLS for r in raw]
+    pt, z, r = fr(kmax), fr(kmax), fr(kmax)                  # p_i(tau), z_i, r_i; the polynomial is p_i(X) = pt_i + a_i (X - tau) with a_i = z_i + 1
+    v = [(p + (zz + 1) * (zz - tau)) % R_BLS for p, zz in zip(pt, z)]
+    w = [(zz + 1) % R_BLS for zz in z]                       # (p(tau) - p(z)) / (tau - z) = a_i
+    sc = lambda xs: np.frombuffer(b"".join(x.to_bytes(32, "little") for x in xs), np.uint8).reshape(-1, 32).copy()
+    gen = np.zeros((1, 96), np.uint8)
+    gx = 0x17f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb
+    gy = 0x08b3f481e3aaa0f1a09e30ed741d8ae4fcf5e095d5d00af600db18cb2c04b3edd03cc744a2888ae40caa232946c5e7e1
+    gen[0, :48] = np.frombuffer(gx.to_bytes(48, "little"), np.uint8); gen[0, 48:] = np.frombuffer(gy.to_bytes(48, "little"), np.uint8)
+    h1 = eng.msm_g1_prepare(gen)
+    mults = lambda s: np.concatenate([h1.msm(s[i:i + 32], 32) for i in range(0, len(s), 32)])
+    C, W = mults(sc(pt)), mults(sc(w))
+    h1.release()
+    # the verifier key's [tau] G2: one scalar multiplication on the host (affine big-integer arithmetic, not timed)
+    from oracle import pairing_ref as PR
+    g2 = np.frombuffer(PR.g2_to_bytes(PR.G2_GEN), np.uint8); tau_g2 = np.frombuffer(PR.g2_to_bytes(PR.g2_mul(tau, PR.G2_GEN)), np.uint8)
+    Z, V, Rr = sc(z), sc(v), sc(r)
+    out = {}
+    for logk in sizes:
+        k = 1 << logk
+        args = (C[:k], Z[:k], V[:k], W[:k], Rr[:k], g2, tau_g2)
+        assert eng.kzg_batch_verify(*args, check_points=0) == 1, "honest openings rejected at 2^%d" % logk
+        bad = V[:k].copy(); bad[k // 3, 1] ^= 4
+        assert eng.kzg_batch_verify(C[:k], Z[:k], bad, W[:k], Rr[:k], g2, tau_g2, check_points=0) == 0, "forged opening accepted at 2^%d" % logk
+        wall, kt = timed_host_call(eng, lambda: eng.kzg_batch_verify(*args, check_points=0), steps)
+        wall2, kt2 = timed_host_call(eng, lambda: eng.kzg_batch_verify(*args, check_points=2), steps)
+        msm_ms = sum(ms for name, ms in kt.items() if name.startswith("msm_"))
+        out["2^%d" % logk] = {"device_ms": sum(kt.values()), "e2e_ms": wall * 1e3, "msm_ms": msm_ms, "pairing_ms": kt.get("kzg_pairing"),
+                              "with_subgroup_checks_device_ms": sum(kt2.values()), "g1_validate_ms": kt2.get("g1_validate"),
+                              "openings_per_s": k / (sum(kt.values()) * 1e-3)}
+    return out
+
+
 def config_wire(eng, n):
     """verification straight off the wire - serialised 32-byte keys, 8-byte VRF input data and 96-byte signatures
     (Output || c || s) in HOST memory -> verdicts + Output::hash, one C-ABI call (deserialisation with subgroup checks, Elligator2,
@@ -652,6 +695,7 @@ def main():
         hbm_peak_, _ = measured_peaks()
         extras["ring_kzg_msm_ms"] = section(lambda: config_msm(eng, rank, world, peak_mac, hbm_peak_, list(range(11, 18))))
         if world == 1:
+            extras["kzg_batch_verify_ms"] = section(lambda: config_kzg(eng, list(range(10, 17))))
             extras["ietf_verify_wire"] = section(lambda: config_wire(eng, min(n, 1 << 20)))
 
     # ---- one caller, all GPUs (vrfs_ctx_create_multi): rank 0 drives every device of the job with ONE host call per step while the
@@ -793,6 +837,9 @@ def main():
                         e["sharded"]["kernel_ms_rank0"] = rs[0][key]["sharded"]["kernel_ms"]
                     o[key] = e
                 out["ring_kzg_msm_ms"] = o
+        if "kzg_batch_verify_ms" in extras:
+            out["kzg_batch_verify_ms"] = {"what": "BASELINE configs[4] 'plus batched ring-proof verify' (SURVEY 8f-3): k KZG openings (commitment, point, value, proof, transcript coefficient) checked at once = one 2-column MSM over 2k+1 G1 points + one product of two BLS12-381 pairings; every size accepts honest openings and rejects one forged value",
+                                          **extras["kzg_batch_verify_ms"][0]}
         if "ietf_verify_wire" in extras:
             out["ietf_verify_wire"] = extras["ietf_verify_wire"][0]
         emit(out)

@@ -261,6 +261,28 @@ vrfs_status vrfs_fr_fft_batch(vrfs_ctx*, int log_n, int n_columns, int inverse, 
 vrfs_status vrfs_g1_compress_batch(vrfs_ctx*, size_t n, const uint8_t* points /*n*96*/, uint8_t* out /*n*48*/);
 vrfs_status vrfs_g1_decompress_batch(vrfs_ctx*, size_t n, const uint8_t* enc /*n*48*/, int check_subgroup, uint8_t* out_points /*n*96*/, uint8_t* out_ok /*n*/);
 
+/* ---- BLS12-381 pairing and the batched KZG opening check -------------------------------------------------
+ * What `ring` -> ring-proof's verifier reduces to after its PIOP identities (ark-ec `Bls12::multi_miller_loop` +
+ * `final_exponentiation`, reached through the re-exports at /root/reference/src/lib.rs:13-17).  The ring-proof crate is not
+ * available offline, so its transcript is NOT restated: the aggregation coefficients r_i are inputs, like the ring's row layout.
+ * G2 points: affine x.c0 || x.c1 || y.c0 || y.c1, 48 bytes little-endian each (192 B; zeros = identity).  GT values: the 12 F_q
+ * coefficients of the tower F_q12 -> F_q6 -> F_q2 in order (c0.c0.c0, c0.c0.c1, c0.c1.c0, ...), 48 bytes LE each (576 B); the
+ * engine's final exponent is 3 (q^12 - 1)/r (the usual x-chain), i.e. its GT values are cubes of the textbook ones.
+ *
+ * n independent products  prod_{j < n_pairs} e(+-P_ij, Q_ij)  (n_pairs <= 4; bit j of negate_masks[i] negates P_ij; NULL = none):
+ * out_ok[i] = 1 if the product is one, 0 if not, 2 if a point is non-canonical or off its curve; out_gt (may be NULL) gets the
+ * product's value.  Points are NOT subgroup-checked here. */
+vrfs_status vrfs_pairing_product_batch(vrfs_ctx*, size_t n, int n_pairs, const uint8_t* g1 /*n*n_pairs*96*/, const uint8_t* g2 /*n*n_pairs*192*/,
+                                       const uint32_t* negate_masks /*n*/, uint8_t* out_ok /*n*/, uint8_t* out_gt /*n*576*/);
+/* k KZG openings (commitment C_i, point z_i, value v_i, proof W_i; scalars 32-byte LE, reduced mod r) checked at once against the
+ * verifier key (G2, [tau]G2) with aggregation coefficients r_i:  e(sum r_i (C_i - [v_i]G1 + [z_i]W_i), G2) = e(sum r_i W_i, [tau]G2).
+ * One 2-column MSM over 2k+1 points + one product of two pairings.  check_points: 0 = C_i, W_i are typed values (already
+ * validated), 1 = canonical + on the curve, 2 = also in the prime-order subgroup (what CanonicalDeserialize validates).
+ * *out_ok = 1 accepted, 0 rejected, 2 malformed point. */
+vrfs_status vrfs_kzg_batch_verify(vrfs_ctx*, size_t k, const uint8_t* commitments /*k*96*/, const uint8_t* points_z /*k*32*/, const uint8_t* values_v /*k*32*/,
+                                  const uint8_t* proofs /*k*96*/, const uint8_t* coeffs_r /*k*32*/, const uint8_t* g2 /*192*/, const uint8_t* tau_g2 /*192*/,
+                                  int check_points, uint8_t* out_ok /*1*/);
+
 /* self-test / measurement helper: 1/a in BLS12-381 Fq (the inversion behind the MSM's affine output) for n canonical 48-byte LE
  * values, 0 -> 0; out_ok[i] = 1 when the word-approximation GCD finished without falling back to the binary Euclid. */
 vrfs_status vrfs_fq381_inv_batch(vrfs_ctx*, size_t n, const uint8_t* in /*n*48*/, uint8_t* out /*n*48*/, uint8_t* out_ok /*n*/);
