@@ -227,8 +227,27 @@ HD_INLINE bool sec1_decode_point(typename C::F& x, typename C::F& y, const uint8
   if (is_odd(y) != (bool)(in[0] & 1)) y = neg(y);
   return true;
 }
+// arkworks codec on a short-Weierstrass curve [RECALL]: 32-byte LE x, then a flag byte whose bit 7 selects the larger root and whose
+// bit 6 marks the identity (rejected here: no typed Public / Input / Output holds it)
+template <class C>
+HD_INLINE bool arksw_decode_point(typename C::F& x, typename C::F& y, const uint8_t* in) {
+  typedef typename C::F F;
+  const uint32_t flags = in[32] >> 6;
+  if (flags & 1u) return false;
+  uint32_t raw[8];
+  load_le<8>(raw, in);
+  if (!is_canonical<typename C::Fq>(raw)) return false;
+  x = to_mont<typename C::Fq>(raw);
+  F rhs = (sqr(x) + C::mul_a(F::one())) * x + C::b();
+  if (rhs.is_zero()) y = F::zero();
+  else if (!sqrt_ct<typename C::Fq>(&y, &rhs)) return false;
+  if (is_high(y) != (bool)(flags >> 1)) y = neg(y);
+  return true;
+}
 template <class S> HD_INLINE bool decode_point(typename S::C::F& x, typename S::C::F& y, const uint8_t* in) {
-  if constexpr (S::SEC1) return sec1_decode_point<typename S::C>(x, y, in); else return ark_decode_point<typename S::C>(x, y, in);
+  if constexpr (S::SEC1) return sec1_decode_point<typename S::C>(x, y, in);
+  else if constexpr (S::ARK_SW) return arksw_decode_point<typename S::C>(x, y, in);
+  else return ark_decode_point<typename S::C>(x, y, in);
 }
 
 // hash_to_curve_tai_rfc_9381 (A.5): first ctr whose hash decodes to a point whose cofactor multiple is not

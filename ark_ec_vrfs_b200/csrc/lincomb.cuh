@@ -102,7 +102,10 @@ template <class C> struct Grp<C, false> {
   static HD_INLINE void to_entry(Entry& e, const Pt& P) { e = P; }
   static HD_INLINE void add_entry(Pt* acc, const Entry* e, bool negate) { Entry q = *e; sw_cneg(q, negate); sw_add<C>(acc, acc, &q); }
   static HD_INLINE void add_fix(Pt* acc, const FixEntry* e, bool negate) { add_entry(acc, e, negate); }
-  static HD_INLINE void dbl4(Pt* acc) { sw_dbl4_am3<C>(acc, acc); }            // Grp<C,false> is only instantiated for secp256r1 (a = -3)
+  static HD_INLINE void dbl4(Pt* acc) {
+    if constexpr (C::A_IS_M3) sw_dbl4_am3<C>(acc, acc);                          // secp256r1
+    else { for (int i = 0; i < 4; i++) sw_add<C>(acc, acc, acc); }               // general a (bandersnatch_sw): the complete addition doubles
+  }
   static HD_INLINE void dbl(Pt* acc) { sw_add<C>(acc, acc, acc); }
   static HD_INLINE void add(Pt* r, const Pt* p, const Pt* q) { sw_add<C>(r, p, q); }
   static HD_INLINE void to_fix(FixEntry& e, const Pt& P) {            // normalise to Z = 1 (identity stays (0:1:0))

@@ -14,7 +14,7 @@ struct BandSuite {
   typedef BandCurve C;
   typedef Sha512 H;
   static constexpr int CLEN = 32, HLEN = 64, ID_LEN = 25, ENC_LEN = 32;
-  static constexpr bool SEC1 = false, RFC6979 = false;
+  static constexpr bool SEC1 = false, RFC6979 = false, ARK_SW = false;
   static constexpr int ID = 0;
   static HD_INLINE uint8_t id(int i) { constexpr char s[] = "Bandersnatch_SHA-512_ELL2"; return (uint8_t)s[i]; }
 };
@@ -22,7 +22,7 @@ struct EdSuite {
   typedef EdCurve C;
   typedef Sha512 H;
   static constexpr int CLEN = 16, HLEN = 64, ID_LEN = 19, ENC_LEN = 32;
-  static constexpr bool SEC1 = false, RFC6979 = false;
+  static constexpr bool SEC1 = false, RFC6979 = false, ARK_SW = false;
   static constexpr int ID = 1;
   static HD_INLINE uint8_t id(int i) { constexpr char s[] = "Ed25519_SHA-512_TAI"; return (uint8_t)s[i]; }
 };
@@ -30,9 +30,35 @@ struct P256Suite {          // RFC 9381 ECVRF-P256-SHA256-TAI, suite string 0x01
   typedef P256Curve C;
   typedef Sha256 H;
   static constexpr int CLEN = 16, HLEN = 32, ID_LEN = 1, ENC_LEN = 33;
-  static constexpr bool SEC1 = true, RFC6979 = true;
+  static constexpr bool SEC1 = true, RFC6979 = true, ARK_SW = false;
   static constexpr int ID = 2;
   static HD_INLINE uint8_t id(int) { return 0x01; }
+};
+
+// SURVEY 8(f)4 suites ([RECALL] suite strings, CHALLENGE_LEN, TAI, arkworks codec; blinding bases are placeholders - unpinned)
+struct BandSwSuite {        // arkworks codec on a short-Weierstrass curve: 32-byte LE x + a flag byte (ARK_SW)
+  typedef BandSwCurve C;
+  typedef Sha512 H;
+  static constexpr int CLEN = 32, HLEN = 64, ID_LEN = 27, ENC_LEN = 33;
+  static constexpr bool SEC1 = false, RFC6979 = false, ARK_SW = true;
+  static constexpr int ID = 3;
+  static HD_INLINE uint8_t id(int i) { constexpr char s[] = "Bandersnatch_SW_SHA-512_TAI"; return (uint8_t)s[i]; }
+};
+struct JubSuite {
+  typedef JubCurve C;
+  typedef Sha512 H;
+  static constexpr int CLEN = 32, HLEN = 64, ID_LEN = 18, ENC_LEN = 32;
+  static constexpr bool SEC1 = false, RFC6979 = false, ARK_SW = false;
+  static constexpr int ID = 4;
+  static HD_INLINE uint8_t id(int i) { constexpr char s[] = "JubJub_SHA-512_TAI"; return (uint8_t)s[i]; }
+};
+struct BjjSuite {
+  typedef BjjCurve C;
+  typedef Sha512 H;
+  static constexpr int CLEN = 32, HLEN = 64, ID_LEN = 22, ENC_LEN = 32;
+  static constexpr bool SEC1 = false, RFC6979 = false, ARK_SW = false;
+  static constexpr int ID = 5;
+  static HD_INLINE uint8_t id(int i) { constexpr char s[] = "BabyJubJub_SHA-512_TAI"; return (uint8_t)s[i]; }
 };
 
 template <class S> HD_INLINE void put_suite_id(typename S::H& h) { for (int i = 0; i < S::ID_LEN; i++) h.put(S::id(i)); }
@@ -44,6 +70,12 @@ template <class S> HD_INLINE void encode_point(uint8_t* out, const uint32_t* x, 
   if (S::SEC1) {
     out[0] = (uint8_t)(2u | (y[0] & 1u));
     store_be<8>(out + 1, x);
+  } else if (S::ARK_SW) {     // arkworks short-Weierstrass compressed form: x LE, then the flag byte (bit 7: y > (p-1)/2)
+    uint32_t h[8], t[8];
+    for (int i = 0; i < 8; i++) h[i] = S::C::Fq::pm1h(i);
+    const bool high = MontChains<8>::sub(t, h, y) != 0;
+    store_le<8>(out, x);
+    out[S::ENC_LEN - 1] = high ? 0x80 : 0x00;
   } else {
     uint32_t h[8], t[8];
     for (int i = 0; i < 8; i++) h[i] = S::C::Fq::pm1h(i);

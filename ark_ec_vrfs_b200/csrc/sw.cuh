@@ -18,8 +18,27 @@ struct P256Curve {
   typedef Fp<Fq> F;
   static constexpr bool IS_TE = false;
   static constexpr bool HAS_GLV = false;
+  static constexpr bool A_IS_M3 = true;
   static constexpr int COF_LOG2 = 0;
   static HD_INLINE F mul_a(const F& x) { return neg(dbl(x) + x); }                        // a = -3
+  static HD_INLINE F mul_b3(const F& x) { return x * fconst<Fq, K::B3>(); }
+  static HD_INLINE F b() { return fconst<Fq, K::B>(); }
+  static HD_INLINE F gx() { return fconst<Fq, K::GX>(); }
+  static HD_INLINE F gy() { return fconst<Fq, K::GY>(); }
+  static HD_INLINE F bx() { return fconst<Fq, K::BX>(); }
+  static HD_INLINE F by() { return fconst<Fq, K::BY>(); }
+};
+// Bandersnatch in short-Weierstrass form (ark-ed-on-bls12-381-bandersnatch SWConfig): general a, cofactor 4
+struct BandSwCurve {
+  typedef BlsFr Fq;
+  typedef BandFr Fr;
+  typedef BandSwConsts K;
+  typedef Fp<Fq> F;
+  static constexpr bool IS_TE = false;
+  static constexpr bool HAS_GLV = false;
+  static constexpr bool A_IS_M3 = false;
+  static constexpr int COF_LOG2 = 2;
+  static HD_INLINE F mul_a(const F& x) { return x * fconst<Fq, K::A>(); }
   static HD_INLINE F mul_b3(const F& x) { return x * fconst<Fq, K::B3>(); }
   static HD_INLINE F b() { return fconst<Fq, K::B>(); }
   static HD_INLINE F gx() { return fconst<Fq, K::GX>(); }

@@ -42,6 +42,39 @@ struct EdCurve {
   static HD_INLINE F by() { return fconst<Fq, K::BY>(); }
 };
 
+// Jubjub (a = -1 over BLS12-381 Fr) and Baby-Jubjub (a = 1 over BN254 Fr); both have a square `a` and a non-square
+// `d`, so the unified hwcd formulas are complete on the whole curve
+struct JubCurve {
+  typedef BlsFr Fq;
+  typedef JubFr Fr;
+  typedef JubConsts K;
+  typedef Fp<Fq> F;
+  static constexpr int COF_LOG2 = 3;
+  static constexpr bool IS_TE = true;
+  static constexpr bool HAS_GLV = false;
+  static HD_INLINE F mul_a(const F& x) { return neg(x); }
+  static HD_INLINE F d() { return fconst<Fq, K::D>(); }
+  static HD_INLINE F gx() { return fconst<Fq, K::GX>(); }
+  static HD_INLINE F gy() { return fconst<Fq, K::GY>(); }
+  static HD_INLINE F bx() { return fconst<Fq, K::BX>(); }
+  static HD_INLINE F by() { return fconst<Fq, K::BY>(); }
+};
+struct BjjCurve {
+  typedef Bn254Fr Fq;
+  typedef BjjFr Fr;
+  typedef BjjConsts K;
+  typedef Fp<Fq> F;
+  static constexpr int COF_LOG2 = 3;
+  static constexpr bool IS_TE = true;
+  static constexpr bool HAS_GLV = false;
+  static HD_INLINE F mul_a(const F& x) { return x; }
+  static HD_INLINE F d() { return fconst<Fq, K::D>(); }
+  static HD_INLINE F gx() { return fconst<Fq, K::GX>(); }
+  static HD_INLINE F gy() { return fconst<Fq, K::GY>(); }
+  static HD_INLINE F bx() { return fconst<Fq, K::BX>(); }
+  static HD_INLINE F by() { return fconst<Fq, K::BY>(); }
+};
+
 template <class C> struct TEPoint { typename C::F X, Y, Z, T; };
 // table entry forms: "cached" = (X, Y, Z, d*T); "affine cached" = (x, y, d*x*y) with Z = 1
 template <class C> struct TECached { typename C::F X, Y, Z, dT; };

@@ -213,7 +213,7 @@ struct vrfs_ctx {
   int depth = 0;                      // nesting of entry points on this context (a host-buffer call runs its *_dev form inside)
   bool failed = false;                // the running call hit an error: both streams are drained before it returns
   DevBuf buf[BUF_COUNT];
-  void* fixtab[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};   // [suite][G | blinding base]
+  void* fixtab[VRFS_SUITE_COUNT][2] = {};   // [suite][G | blinding base], built on first use
   std::vector<struct vrfs_msm_bases*> prepared;   // live prepared-base handles (freed / orphaned by vrfs_ctx_destroy)
   // peer group of the multi-GPU MSM exchange (csrc/msm.cuh "multi-GPU exchange"): world = 0 until connected
   struct {
@@ -373,7 +373,7 @@ extern "C" void vrfs_ctx_destroy(vrfs_ctx* ctx) {
   orphan_prepared(ctx);
   peer_teardown(ctx);
   for (int i = 0; i < BUF_COUNT; i++) if (ctx->buf[i].p) cudaFree(ctx->buf[i].p);
-  for (int s = 0; s < 3; s++) for (int b = 0; b < 2; b++) if (ctx->fixtab[s][b]) cudaFree(ctx->fixtab[s][b]);
+  for (int s = 0; s < VRFS_SUITE_COUNT; s++) for (int b = 0; b < 2; b++) if (ctx->fixtab[s][b]) cudaFree(ctx->fixtab[s][b]);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   for (int i = 0; i < 4; i++) if (ctx->ev_chunk[i]) cudaEventDestroy(ctx->ev_chunk[i]);
@@ -403,9 +403,32 @@ extern "C" vrfs_status vrfs_ctx_debug_read_staging(vrfs_ctx* ctx, int slot, size
 extern "C" const char* vrfs_last_error(const vrfs_ctx* ctx) { return ctx ? ctx->err : "null context"; }
 extern "C" void* vrfs_ctx_stream(vrfs_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 extern "C" uint64_t vrfs_ctx_launch_count(const vrfs_ctx* ctx) { return ctx ? ctx->launches : 0; }
-extern "C" int vrfs_suite_challenge_len(vrfs_suite s) { return s == VRFS_BANDERSNATCH_ELL2 ? 32 : 16; }
-extern "C" int vrfs_suite_hash_len(vrfs_suite s) { return s == VRFS_P256_TAI ? 32 : 64; }
-extern "C" int vrfs_suite_point_enc_len(vrfs_suite s) { return s == VRFS_P256_TAI ? 33 : 32; }
+// the suite behind a vrfs_suite value, handed to a generic lambda as a value of its tag type
+template <class F> static vrfs_status with_suite(vrfs_ctx* ctx, vrfs_suite s, F&& f) {
+  switch (s) {
+    case VRFS_BANDERSNATCH_ELL2: return f(BandSuite{});
+    case VRFS_ED25519_TAI: return f(EdSuite{});
+    case VRFS_P256_TAI: return f(P256Suite{});
+    case VRFS_BANDERSNATCH_SW_TAI: return f(BandSwSuite{});
+    case VRFS_JUBJUB_TAI: return f(JubSuite{});
+    case VRFS_BABYJUBJUB_TAI: return f(BjjSuite{});
+    default: return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)s);
+  }
+}
+template <class F> static int suite_const(vrfs_suite s, F&& f) {
+  switch (s) {
+    case VRFS_BANDERSNATCH_ELL2: return f(BandSuite{});
+    case VRFS_ED25519_TAI: return f(EdSuite{});
+    case VRFS_P256_TAI: return f(P256Suite{});
+    case VRFS_BANDERSNATCH_SW_TAI: return f(BandSwSuite{});
+    case VRFS_JUBJUB_TAI: return f(JubSuite{});
+    case VRFS_BABYJUBJUB_TAI: return f(BjjSuite{});
+    default: return 0;
+  }
+}
+extern "C" int vrfs_suite_challenge_len(vrfs_suite s) { return suite_const(s, [](auto S_) { return (int)decltype(S_)::CLEN; }); }
+extern "C" int vrfs_suite_hash_len(vrfs_suite s) { return suite_const(s, [](auto S_) { return (int)decltype(S_)::HLEN; }); }
+extern "C" int vrfs_suite_point_enc_len(vrfs_suite s) { return suite_const(s, [](auto S_) { return (int)decltype(S_)::ENC_LEN; }); }
 
 // =================================================================================================
 // lincomb launcher
@@ -491,12 +514,7 @@ extern "C" vrfs_status vrfs_ietf_verify_batch_dev(vrfs_ctx* ctx, vrfs_suite suit
   if (!aligned16(pk) || !aligned16(input) || !aligned16(output) || !aligned16(c) || !aligned16(s)) return fail(ctx, VRFS_BAD_ARG, "device buffers must be 16-byte aligned");
   CU(cudaSetDevice(ctx->device));
   ST(timing_begin(ctx));
-  switch (suite) {
-    case VRFS_BANDERSNATCH_ELL2: return ietf_verify_dev<BandSuite>(ctx, n, pk, input, output, c, s, ad, ad_off, out_ok, out_status);
-    case VRFS_ED25519_TAI: return ietf_verify_dev<EdSuite>(ctx, n, pk, input, output, c, s, ad, ad_off, out_ok, out_status);
-    case VRFS_P256_TAI: return ietf_verify_dev<P256Suite>(ctx, n, pk, input, output, c, s, ad, ad_off, out_ok, out_status);
-    default: return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
-  }
+  return with_suite(ctx, suite, [&](auto S_) { typedef decltype(S_) S; return ietf_verify_dev<S>(ctx, n, pk, input, output, c, s, ad, ad_off, out_ok, out_status); });
 }
 
 // host -> device staging of one input; returns the device pointer
@@ -543,7 +561,7 @@ static vrfs_status ietf_verify_host_enqueue(vrfs_ctx* ctx, vrfs_suite suite, siz
                                             const uint8_t* c, const uint8_t* s, const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_ok, uint8_t* out_status) {
   if (!pk || !input || !output || !c || !s || !out_ok) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if (n > 0x7fffffffu) return fail(ctx, VRFS_BAD_ARG, "batch too large (n < 2^31)");
-  if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
+  if ((unsigned)suite >= VRFS_SUITE_COUNT) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
   CU(cudaSetDevice(ctx->device));
   const uint8_t* d_ad;
   const uint64_t* d_off;
@@ -801,13 +819,6 @@ template <class C, int NP> static vrfs_status launch_zinv(vrfs_ctx* ctx, size_t 
   *out = (const uint32_t*)z;
   return VRFS_OK;
 }
-#define SUITE_DISPATCH(suite, FN, ...)                                                         \
-  switch (suite) {                                                                             \
-    case VRFS_BANDERSNATCH_ELL2: return FN<BandSuite>(__VA_ARGS__);                            \
-    case VRFS_ED25519_TAI: return FN<EdSuite>(__VA_ARGS__);                                    \
-    default: return fail(ctx, VRFS_UNSUPPORTED, "suite %d is not implemented for %s", (int)suite, #FN); \
-  }
-
 // Suite::data_to_point: hash-to-curve kernel (projective) + batched inversion + affine ABI bytes (zeros where no point was found)
 template <class S> static vrfs_status data_to_point_dev(vrfs_ctx* ctx, size_t n, const uint8_t* data, const uint64_t* off, uint8_t* out_pts, uint8_t* out_ok) {
   typedef typename S::C C;
@@ -856,14 +867,13 @@ extern "C" vrfs_status vrfs_ietf_prove_batch(vrfs_ctx* ctx, vrfs_suite suite, si
   CallGuard guard_(ctx);
   if (n == 0) return VRFS_OK;
   if (!sk || !input || !output || !out_c || !out_s) return fail(ctx, VRFS_BAD_ARG, "null buffer");
-  if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
+  if ((unsigned)suite >= VRFS_SUITE_COUNT) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
   ST(begin_call(ctx, n));
   const uint8_t *d_sk, *d_in, *d_out, *d_ad; const uint64_t* d_off; uint8_t *d_c, *d_s;
   ST(stage_secret(ctx, BUF_IN0, sk, n * 32, &d_sk)); ST(stage_in(ctx, BUF_IN1, input, n * 64, &d_in)); ST(stage_in(ctx, BUF_IN2, output, n * 64, &d_out));
   ST(stage_ad(ctx, n, ad, ad_off, &d_ad, &d_off));
   ST(stage_out(ctx, BUF_OUT0, n * 32, &d_c)); ST(stage_out(ctx, BUF_OUT1, n * 32, &d_s));
-  vrfs_status st = suite == VRFS_BANDERSNATCH_ELL2 ? ietf_prove_dev<BandSuite>(ctx, n, d_sk, d_in, d_out, d_ad, d_off, d_c, d_s)
-     : suite == VRFS_ED25519_TAI ? ietf_prove_dev<EdSuite>(ctx, n, d_sk, d_in, d_out, d_ad, d_off, d_c, d_s) : ietf_prove_dev<P256Suite>(ctx, n, d_sk, d_in, d_out, d_ad, d_off, d_c, d_s);
+  vrfs_status st = with_suite(ctx, suite, [&](auto S_) { typedef decltype(S_) S; return ietf_prove_dev<S>(ctx, n, d_sk, d_in, d_out, d_ad, d_off, d_c, d_s); });
   ST(st);
   ST(copy_out(ctx, out_c, d_c, n * 32)); ST(copy_out(ctx, out_s, d_s, n * 32));
   return finish_call(ctx);
@@ -888,12 +898,11 @@ extern "C" vrfs_status vrfs_output_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t
   CallGuard guard_(ctx);
   if (n == 0) return VRFS_OK;
   if (!sk || !input || !out_output) return fail(ctx, VRFS_BAD_ARG, "null buffer");
-  if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
+  if ((unsigned)suite >= VRFS_SUITE_COUNT) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
   ST(begin_call(ctx, n));
   const uint8_t *d_sk, *d_in; uint8_t* d_o;
   ST(stage_secret(ctx, BUF_IN0, sk, n * 32, &d_sk)); ST(stage_in(ctx, BUF_IN1, input, n * 64, &d_in)); ST(stage_out(ctx, BUF_OUT0, n * 64, &d_o));
-  ST(suite == VRFS_BANDERSNATCH_ELL2 ? output_dev<BandSuite>(ctx, n, d_sk, d_in, d_o)
-     : suite == VRFS_ED25519_TAI ? output_dev<EdSuite>(ctx, n, d_sk, d_in, d_o) : output_dev<P256Suite>(ctx, n, d_sk, d_in, d_o));
+  ST(with_suite(ctx, suite, [&](auto S_) { typedef decltype(S_) S; return output_dev<S>(ctx, n, d_sk, d_in, d_o); }));
   ST(copy_out(ctx, out_output, d_o, n * 64));
   return finish_call(ctx);
 }
@@ -920,7 +929,7 @@ extern "C" vrfs_status vrfs_secret_from_seed_batch(vrfs_ctx* ctx, vrfs_suite sui
   CallGuard guard_(ctx);
   if (n == 0) return VRFS_OK;
   if (!seed_off || !out_sk) return fail(ctx, VRFS_BAD_ARG, "null buffer");
-  if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
+  if ((unsigned)suite >= VRFS_SUITE_COUNT) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
   ST(begin_call(ctx, n));
   const uint8_t* d_seeds; const uint64_t* d_off; uint8_t *d_sk, *d_pk = nullptr;
   ST(stage_ad(ctx, n, seeds, seed_off, &d_seeds, &d_off));
@@ -928,8 +937,7 @@ extern "C" vrfs_status vrfs_secret_from_seed_batch(vrfs_ctx* ctx, vrfs_suite sui
   ST(stage_out(ctx, BUF_OUT0, n * 32, &d_sk));
   mark_secret(ctx, BUF_OUT0, n * 32);
   if (out_pk) ST(stage_out(ctx, BUF_OUT1, n * 64, &d_pk));
-  ST(suite == VRFS_BANDERSNATCH_ELL2 ? from_seed_dev<BandSuite>(ctx, n, d_seeds, d_off, d_sk, d_pk)
-     : suite == VRFS_ED25519_TAI ? from_seed_dev<EdSuite>(ctx, n, d_seeds, d_off, d_sk, d_pk) : from_seed_dev<P256Suite>(ctx, n, d_seeds, d_off, d_sk, d_pk));
+  ST(with_suite(ctx, suite, [&](auto S_) { typedef decltype(S_) S; return from_seed_dev<S>(ctx, n, d_seeds, d_off, d_sk, d_pk); }));
   ST(copy_out(ctx, out_sk, d_sk, n * 32));
   if (out_pk) ST(copy_out(ctx, out_pk, d_pk, n * 64));
   return finish_call(ctx);
@@ -939,14 +947,12 @@ extern "C" vrfs_status vrfs_nonce_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t 
   CallGuard guard_(ctx);
   if (n == 0) return VRFS_OK;
   if (!sk || !input || !out_k) return fail(ctx, VRFS_BAD_ARG, "null buffer");
-  if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
+  if ((unsigned)suite >= VRFS_SUITE_COUNT) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
   ST(begin_call(ctx, n));
   const uint8_t *d_sk, *d_in; uint8_t* d_k;
   ST(stage_secret(ctx, BUF_IN0, sk, n * 32, &d_sk)); ST(stage_in(ctx, BUF_IN1, input, n * 64, &d_in)); ST(stage_out(ctx, BUF_OUT0, n * 32, &d_k));
   mark_secret(ctx, BUF_OUT0, n * 32);
-  if (suite == VRFS_BANDERSNATCH_ELL2) k_nonce<BandSuite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_sk, d_in, d_k);
-  else if (suite == VRFS_ED25519_TAI) k_nonce<EdSuite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_sk, d_in, d_k);
-  else k_nonce<P256Suite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_sk, d_in, d_k);
+  ST(with_suite(ctx, suite, [&](auto S_) { typedef decltype(S_) S; k_nonce<S><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_sk, d_in, d_k); return VRFS_OK; }));
   LAUNCHED_AS(ctx, "nonce");
   ST(copy_out(ctx, out_k, d_k, n * 32));
   return finish_call(ctx);
@@ -956,14 +962,12 @@ extern "C" vrfs_status vrfs_point_to_hash_batch(vrfs_ctx* ctx, vrfs_suite suite,
   CallGuard guard_(ctx);
   if (n == 0) return VRFS_OK;
   if (!pts || !out_hash) return fail(ctx, VRFS_BAD_ARG, "null buffer");
-  if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
+  if ((unsigned)suite >= VRFS_SUITE_COUNT) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
   ST(begin_call(ctx, n));
   const uint8_t* d_p; uint8_t* d_h;
   const size_t hl = (size_t)vrfs_suite_hash_len(suite);
   ST(stage_in(ctx, BUF_IN0, pts, n * 64, &d_p)); ST(stage_out(ctx, BUF_OUT0, n * hl, &d_h));
-  if (suite == VRFS_BANDERSNATCH_ELL2) k_point_to_hash<BandSuite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_p, d_h);
-  else if (suite == VRFS_ED25519_TAI) k_point_to_hash<EdSuite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_p, d_h);
-  else k_point_to_hash<P256Suite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_p, d_h);
+  ST(with_suite(ctx, suite, [&](auto S_) { typedef decltype(S_) S; k_point_to_hash<S><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_p, d_h); return VRFS_OK; }));
   LAUNCHED_AS(ctx, "point_to_hash");
   ST(copy_out(ctx, out_hash, d_h, n * hl));
   return finish_call(ctx);
@@ -973,14 +977,12 @@ extern "C" vrfs_status vrfs_point_encode_batch(vrfs_ctx* ctx, vrfs_suite suite, 
   CallGuard guard_(ctx);
   if (n == 0) return VRFS_OK;
   if (!pts || !out_enc) return fail(ctx, VRFS_BAD_ARG, "null buffer");
-  if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
+  if ((unsigned)suite >= VRFS_SUITE_COUNT) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
   ST(begin_call(ctx, n));
   const uint8_t* d_p; uint8_t* d_e;
   const size_t el = (size_t)vrfs_suite_point_enc_len(suite);
   ST(stage_in(ctx, BUF_IN0, pts, n * 64, &d_p)); ST(stage_out(ctx, BUF_OUT0, n * el, &d_e));
-  if (suite == VRFS_BANDERSNATCH_ELL2) k_point_encode<BandSuite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_p, d_e);
-  else if (suite == VRFS_ED25519_TAI) k_point_encode<EdSuite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_p, d_e);
-  else k_point_encode<P256Suite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_p, d_e);
+  ST(with_suite(ctx, suite, [&](auto S_) { typedef decltype(S_) S; k_point_encode<S><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_p, d_e); return VRFS_OK; }));
   LAUNCHED_AS(ctx, "point_encode");
   ST(copy_out(ctx, out_enc, d_e, n * el));
   return finish_call(ctx);
@@ -990,14 +992,12 @@ extern "C" vrfs_status vrfs_point_decode_batch(vrfs_ctx* ctx, vrfs_suite suite, 
   CallGuard guard_(ctx);
   if (n == 0) return VRFS_OK;
   if (!enc || !out_pts || !out_ok) return fail(ctx, VRFS_BAD_ARG, "null buffer");
-  if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
+  if ((unsigned)suite >= VRFS_SUITE_COUNT) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
   ST(begin_call(ctx, n));
   const uint8_t* d_e; uint8_t *d_p, *d_ok;
   const size_t el = (size_t)vrfs_suite_point_enc_len(suite);
   ST(stage_in(ctx, BUF_IN0, enc, n * el, &d_e)); ST(stage_out(ctx, BUF_OUT0, n * 64, &d_p)); ST(stage_out(ctx, BUF_OUT1, n, &d_ok));
-  if (suite == VRFS_BANDERSNATCH_ELL2) k_point_decode<BandSuite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_e, d_p, d_ok);
-  else if (suite == VRFS_ED25519_TAI) k_point_decode<EdSuite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_e, d_p, d_ok);
-  else k_point_decode<P256Suite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_e, d_p, d_ok);
+  ST(with_suite(ctx, suite, [&](auto S_) { typedef decltype(S_) S; k_point_decode<S><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_e, d_p, d_ok); return VRFS_OK; }));
   LAUNCHED_AS(ctx, "point_decode");
   ST(copy_out(ctx, out_pts, d_p, n * 64)); ST(copy_out(ctx, out_ok, d_ok, n));
   return finish_call(ctx);
@@ -1008,13 +1008,12 @@ extern "C" vrfs_status vrfs_data_to_point_batch(vrfs_ctx* ctx, vrfs_suite suite,
   CallGuard guard_(ctx);
   if (n == 0) return VRFS_OK;
   if (!data_off || !out_pts || !out_ok) return fail(ctx, VRFS_BAD_ARG, "null buffer");
-  if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
+  if ((unsigned)suite >= VRFS_SUITE_COUNT) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
   ST(begin_call(ctx, n));
   const uint8_t* d_d; const uint64_t* d_off; uint8_t *d_p, *d_ok;
   ST(stage_ad(ctx, n, data, data_off, &d_d, &d_off));
   ST(stage_out(ctx, BUF_OUT0, n * 64, &d_p)); ST(stage_out(ctx, BUF_OUT1, n, &d_ok));
-  ST(suite == VRFS_BANDERSNATCH_ELL2 ? data_to_point_dev<BandSuite>(ctx, n, d_d, d_off, d_p, d_ok)
-     : suite == VRFS_ED25519_TAI ? data_to_point_dev<EdSuite>(ctx, n, d_d, d_off, d_p, d_ok) : data_to_point_dev<P256Suite>(ctx, n, d_d, d_off, d_p, d_ok));
+  ST(with_suite(ctx, suite, [&](auto S_) { typedef decltype(S_) S; return data_to_point_dev<S>(ctx, n, d_d, d_off, d_p, d_ok); }));
   ST(copy_out(ctx, out_pts, d_p, n * 64)); ST(copy_out(ctx, out_ok, d_ok, n));
   return finish_call(ctx);
 }
@@ -1054,15 +1053,14 @@ extern "C" vrfs_status vrfs_pedersen_prove_batch(vrfs_ctx* ctx, vrfs_suite suite
   CallGuard guard_(ctx);
   if (n == 0) return VRFS_OK;
   if (!sk || !input || !output || !out_proof || !out_blinding) return fail(ctx, VRFS_BAD_ARG, "null buffer");
-  if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
+  if ((unsigned)suite >= VRFS_SUITE_COUNT) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
   ST(begin_call(ctx, n));
   const uint8_t *d_sk, *d_in, *d_out, *d_ad; const uint64_t* d_off; uint8_t *d_pr, *d_bl;
   ST(stage_secret(ctx, BUF_IN0, sk, n * 32, &d_sk)); ST(stage_in(ctx, BUF_IN1, input, n * 64, &d_in)); ST(stage_in(ctx, BUF_IN2, output, n * 64, &d_out));
   ST(stage_ad(ctx, n, ad, ad_off, &d_ad, &d_off));
   ST(stage_out(ctx, BUF_OUT0, n * 256, &d_pr)); ST(stage_out(ctx, BUF_OUT1, n * 32, &d_bl));
   mark_secret(ctx, BUF_OUT1, n * 32);
-  ST(suite == VRFS_BANDERSNATCH_ELL2 ? pedersen_prove_dev<BandSuite>(ctx, n, d_sk, d_in, d_out, d_ad, d_off, d_pr, d_bl)
-     : suite == VRFS_ED25519_TAI ? pedersen_prove_dev<EdSuite>(ctx, n, d_sk, d_in, d_out, d_ad, d_off, d_pr, d_bl) : pedersen_prove_dev<P256Suite>(ctx, n, d_sk, d_in, d_out, d_ad, d_off, d_pr, d_bl));
+  ST(with_suite(ctx, suite, [&](auto S_) { typedef decltype(S_) S; return pedersen_prove_dev<S>(ctx, n, d_sk, d_in, d_out, d_ad, d_off, d_pr, d_bl); }));
   ST(copy_out(ctx, out_proof, d_pr, n * 256)); ST(copy_out(ctx, out_blinding, d_bl, n * 32));
   return finish_call(ctx);
 }
@@ -1097,15 +1095,14 @@ extern "C" vrfs_status vrfs_pedersen_verify_batch(vrfs_ctx* ctx, vrfs_suite suit
   CallGuard guard_(ctx);
   if (n == 0) return VRFS_OK;
   if (!input || !output || !proof || !out_ok) return fail(ctx, VRFS_BAD_ARG, "null buffer");
-  if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
+  if ((unsigned)suite >= VRFS_SUITE_COUNT) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
   ST(begin_call(ctx, n));
   const uint8_t *d_in, *d_out, *d_pr, *d_ad; const uint64_t* d_off; uint8_t *d_ok, *d_st = nullptr;
   ST(stage_in(ctx, BUF_IN0, input, n * 64, &d_in)); ST(stage_in(ctx, BUF_IN1, output, n * 64, &d_out)); ST(stage_in(ctx, BUF_IN2, proof, n * 256, &d_pr));
   ST(stage_ad(ctx, n, ad, ad_off, &d_ad, &d_off));
   ST(stage_out(ctx, BUF_OUT0, n, &d_ok));
   if (out_status) ST(stage_out(ctx, BUF_OUT1, n, &d_st));
-  ST(suite == VRFS_BANDERSNATCH_ELL2 ? pedersen_verify_dev<BandSuite>(ctx, n, d_in, d_out, d_pr, d_ad, d_off, d_ok, d_st)
-     : suite == VRFS_ED25519_TAI ? pedersen_verify_dev<EdSuite>(ctx, n, d_in, d_out, d_pr, d_ad, d_off, d_ok, d_st) : pedersen_verify_dev<P256Suite>(ctx, n, d_in, d_out, d_pr, d_ad, d_off, d_ok, d_st));
+  ST(with_suite(ctx, suite, [&](auto S_) { typedef decltype(S_) S; return pedersen_verify_dev<S>(ctx, n, d_in, d_out, d_pr, d_ad, d_off, d_ok, d_st); }));
   ST(copy_out(ctx, out_ok, d_ok, n));
   if (out_status) ST(copy_out(ctx, out_status, d_st, n));
   return finish_call(ctx);
@@ -1174,14 +1171,12 @@ extern "C" vrfs_status vrfs_point_decode_checked_batch(vrfs_ctx* ctx, vrfs_suite
   CallGuard guard_(ctx);
   if (n == 0) return VRFS_OK;
   if (!enc || !out_pts || !out_ok) return fail(ctx, VRFS_BAD_ARG, "null buffer");
-  if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
+  if ((unsigned)suite >= VRFS_SUITE_COUNT) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
   ST(begin_call(ctx, n));
   const uint32_t el = (uint32_t)vrfs_suite_point_enc_len(suite);
   const uint8_t* d_e; uint8_t *d_p, *d_ok;
   ST(stage_in(ctx, BUF_X0, enc, n * el, &d_e)); ST(stage_out(ctx, BUF_OUT0, n * 64, &d_p)); ST(stage_out(ctx, BUF_OUT1, n, &d_ok));
-  ST(suite == VRFS_BANDERSNATCH_ELL2 ? decode_checked_launch<BandSuite>(ctx, n, d_e, el, d_p, nullptr, 0, nullptr, d_ok)
-     : suite == VRFS_ED25519_TAI ? decode_checked_launch<EdSuite>(ctx, n, d_e, el, d_p, nullptr, 0, nullptr, d_ok)
-                                 : decode_checked_launch<P256Suite>(ctx, n, d_e, el, d_p, nullptr, 0, nullptr, d_ok));
+  ST(with_suite(ctx, suite, [&](auto S_) { typedef decltype(S_) S; return decode_checked_launch<S>(ctx, n, d_e, el, d_p, nullptr, 0, nullptr, d_ok); }));
   ST(copy_out(ctx, out_pts, d_p, n * 64)); ST(copy_out(ctx, out_ok, d_ok, n));
   return finish_call(ctx);
 }
@@ -1190,13 +1185,11 @@ extern "C" vrfs_status vrfs_subgroup_check_batch(vrfs_ctx* ctx, vrfs_suite suite
   CallGuard guard_(ctx);
   if (n == 0) return VRFS_OK;
   if (!pts || !out_ok) return fail(ctx, VRFS_BAD_ARG, "null buffer");
-  if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
+  if ((unsigned)suite >= VRFS_SUITE_COUNT) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
   ST(begin_call(ctx, n));
   const uint8_t* d_p; uint8_t* d_ok;
   ST(stage_in(ctx, BUF_IN0, pts, n * 64, &d_p)); ST(stage_out(ctx, BUF_OUT0, n, &d_ok));
-  if (suite == VRFS_BANDERSNATCH_ELL2) k_subgroup_check<BandSuite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_p, d_ok);
-  else if (suite == VRFS_ED25519_TAI) k_subgroup_check<EdSuite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_p, d_ok);
-  else k_subgroup_check<P256Suite><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_p, d_ok);
+  ST(with_suite(ctx, suite, [&](auto S_) { typedef decltype(S_) S; k_subgroup_check<S><<<item_blocks(n), ITEM_THREADS, 0, ctx->stream>>>((uint32_t)n, d_p, d_ok); return VRFS_OK; }));
   LAUNCHED_AS(ctx, "subgroup_check");
   ST(copy_out(ctx, out_ok, d_ok, n));
   return finish_call(ctx);
@@ -1219,7 +1212,7 @@ extern "C" vrfs_status vrfs_ietf_sign_wire_batch(vrfs_ctx* ctx, vrfs_suite suite
   CallGuard guard_(ctx);
   if (n == 0) return VRFS_OK;
   if (!sk || !data_off || !out_sig) return fail(ctx, VRFS_BAD_ARG, "null buffer");
-  if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
+  if ((unsigned)suite >= VRFS_SUITE_COUNT) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
   ST(begin_call(ctx, n));
   const size_t sl = (size_t)vrfs_suite_ietf_signature_len(suite);
   const uint8_t *d_sk, *d_ad, *d_data; const uint64_t *d_off, *d_doff;
@@ -1229,9 +1222,7 @@ extern "C" vrfs_status vrfs_ietf_sign_wire_batch(vrfs_ctx* ctx, vrfs_suite suite
   ST(stage_var(ctx, BUF_X2, BUF_X3, n, data, data_off, &d_data, &d_doff));
   ST(stage_out(ctx, BUF_IN1, n * 64, &d_in)); ST(stage_out(ctx, BUF_IN2, n * 64, &d_out)); ST(stage_out(ctx, BUF_IN3, n * 32, &d_c)); ST(stage_out(ctx, BUF_IN4, n * 32, &d_s));
   ST(stage_out(ctx, BUF_X4, n, &d_ok)); ST(stage_out(ctx, BUF_X1, n * sl, &d_sig));
-  ST(suite == VRFS_BANDERSNATCH_ELL2 ? ietf_sign_wire_dev<BandSuite>(ctx, n, d_sk, d_data, d_doff, d_ad, d_off, d_in, d_out, d_c, d_s, d_ok, d_sig)
-     : suite == VRFS_ED25519_TAI ? ietf_sign_wire_dev<EdSuite>(ctx, n, d_sk, d_data, d_doff, d_ad, d_off, d_in, d_out, d_c, d_s, d_ok, d_sig)
-                                 : ietf_sign_wire_dev<P256Suite>(ctx, n, d_sk, d_data, d_doff, d_ad, d_off, d_in, d_out, d_c, d_s, d_ok, d_sig));
+  ST(with_suite(ctx, suite, [&](auto S_) { typedef decltype(S_) S; return ietf_sign_wire_dev<S>(ctx, n, d_sk, d_data, d_doff, d_ad, d_off, d_in, d_out, d_c, d_s, d_ok, d_sig); }));
   ST(copy_out(ctx, out_sig, d_sig, n * sl));
   if (out_ok) ST(copy_out(ctx, out_ok, d_ok, n));
   return finish_call(ctx);
@@ -1261,7 +1252,7 @@ extern "C" vrfs_status vrfs_ietf_verify_wire_batch(vrfs_ctx* ctx, vrfs_suite sui
   CallGuard guard_(ctx);
   if (n == 0) return VRFS_OK;
   if (!pk_enc || !data_off || !sig || !out_ok) return fail(ctx, VRFS_BAD_ARG, "null buffer");
-  if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
+  if ((unsigned)suite >= VRFS_SUITE_COUNT) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
   ST(begin_call(ctx, n));
   const size_t sl = (size_t)vrfs_suite_ietf_signature_len(suite), el = (size_t)vrfs_suite_point_enc_len(suite), hl = (size_t)vrfs_suite_hash_len(suite);
   const uint8_t *d_pke, *d_sig, *d_ad, *d_data; const uint64_t *d_off, *d_doff;
@@ -1274,9 +1265,7 @@ extern "C" vrfs_status vrfs_ietf_verify_wire_batch(vrfs_ctx* ctx, vrfs_suite sui
   ST(stage_out(ctx, BUF_OUT0, n, &d_ok));
   if (out_hash) ST(stage_out(ctx, BUF_OUT1, n * hl, &d_hash));
   if (out_status) ST(stage_out(ctx, BUF_X5, n, &d_st));
-  ST(suite == VRFS_BANDERSNATCH_ELL2 ? ietf_verify_wire_dev<BandSuite>(ctx, n, d_pke, d_data, d_doff, d_sig, d_ad, d_off, d_pk, d_in, d_out, d_c, d_s, d_flags, d_ok, d_hash, d_st)
-     : suite == VRFS_ED25519_TAI ? ietf_verify_wire_dev<EdSuite>(ctx, n, d_pke, d_data, d_doff, d_sig, d_ad, d_off, d_pk, d_in, d_out, d_c, d_s, d_flags, d_ok, d_hash, d_st)
-                                 : ietf_verify_wire_dev<P256Suite>(ctx, n, d_pke, d_data, d_doff, d_sig, d_ad, d_off, d_pk, d_in, d_out, d_c, d_s, d_flags, d_ok, d_hash, d_st));
+  ST(with_suite(ctx, suite, [&](auto S_) { typedef decltype(S_) S; return ietf_verify_wire_dev<S>(ctx, n, d_pke, d_data, d_doff, d_sig, d_ad, d_off, d_pk, d_in, d_out, d_c, d_s, d_flags, d_ok, d_hash, d_st); }));
   ST(copy_out(ctx, out_ok, d_ok, n));
   if (out_hash) ST(copy_out(ctx, out_hash, d_hash, n * hl));
   if (out_status) ST(copy_out(ctx, out_status, d_st, n));
@@ -1345,7 +1334,7 @@ extern "C" vrfs_status vrfs_pedersen_sign_wire_batch(vrfs_ctx* ctx, vrfs_suite s
   CallGuard guard_(ctx);
   if (n == 0) return VRFS_OK;
   if (!sk || !data_off || !out_sig || !out_blinding) return fail(ctx, VRFS_BAD_ARG, "null buffer");
-  if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
+  if ((unsigned)suite >= VRFS_SUITE_COUNT) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
   ST(begin_call(ctx, n));
   const size_t sl = (size_t)vrfs_suite_pedersen_signature_len(suite);
   const uint8_t *d_sk, *d_ad, *d_data; const uint64_t *d_off, *d_doff;
@@ -1356,9 +1345,7 @@ extern "C" vrfs_status vrfs_pedersen_sign_wire_batch(vrfs_ctx* ctx, vrfs_suite s
   ST(stage_out(ctx, BUF_IN1, n * 64, &d_in)); ST(stage_out(ctx, BUF_IN2, n * 64, &d_out)); ST(stage_out(ctx, BUF_OUT0, n * 256, &d_pr)); ST(stage_out(ctx, BUF_OUT1, n * 32, &d_bl));
   mark_secret(ctx, BUF_OUT1, n * 32);
   ST(stage_out(ctx, BUF_X4, n, &d_ok)); ST(stage_out(ctx, BUF_X1, n * sl, &d_sig));
-  ST(suite == VRFS_BANDERSNATCH_ELL2 ? pedersen_sign_wire_dev<BandSuite>(ctx, n, d_sk, d_data, d_doff, d_ad, d_off, d_in, d_out, d_pr, d_bl, d_ok, d_sig)
-     : suite == VRFS_ED25519_TAI ? pedersen_sign_wire_dev<EdSuite>(ctx, n, d_sk, d_data, d_doff, d_ad, d_off, d_in, d_out, d_pr, d_bl, d_ok, d_sig)
-                                 : pedersen_sign_wire_dev<P256Suite>(ctx, n, d_sk, d_data, d_doff, d_ad, d_off, d_in, d_out, d_pr, d_bl, d_ok, d_sig));
+  ST(with_suite(ctx, suite, [&](auto S_) { typedef decltype(S_) S; return pedersen_sign_wire_dev<S>(ctx, n, d_sk, d_data, d_doff, d_ad, d_off, d_in, d_out, d_pr, d_bl, d_ok, d_sig); }));
   ST(copy_out(ctx, out_sig, d_sig, n * sl)); ST(copy_out(ctx, out_blinding, d_bl, n * 32));
   if (out_ok) ST(copy_out(ctx, out_ok, d_ok, n));
   return finish_call(ctx);
@@ -1384,7 +1371,7 @@ extern "C" vrfs_status vrfs_pedersen_verify_wire_batch(vrfs_ctx* ctx, vrfs_suite
   CallGuard guard_(ctx);
   if (n == 0) return VRFS_OK;
   if (!data_off || !sig || !out_ok) return fail(ctx, VRFS_BAD_ARG, "null buffer");
-  if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
+  if ((unsigned)suite >= VRFS_SUITE_COUNT) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
   ST(begin_call(ctx, n));
   const size_t sl = (size_t)vrfs_suite_pedersen_signature_len(suite);
   const uint8_t *d_sig, *d_ad, *d_data; const uint64_t *d_off, *d_doff;
@@ -1395,9 +1382,7 @@ extern "C" vrfs_status vrfs_pedersen_verify_wire_batch(vrfs_ctx* ctx, vrfs_suite
   ST(stage_out(ctx, BUF_IN0, n * 64, &d_in)); ST(stage_out(ctx, BUF_IN1, n * 64, &d_out)); ST(stage_out(ctx, BUF_IN2, n * 256, &d_pr));
   ST(stage_out(ctx, BUF_X4, 6 * n, &d_flags)); ST(stage_out(ctx, BUF_OUT0, n, &d_ok));
   if (out_status) ST(stage_out(ctx, BUF_OUT1, n, &d_st));
-  ST(suite == VRFS_BANDERSNATCH_ELL2 ? (pedersen_verify_wire_dev<BandSuite, 4>(ctx, n, d_data, d_doff, d_sig, d_ad, d_off, d_in, d_out, d_pr, d_flags, d_ok, d_st))
-     : suite == VRFS_ED25519_TAI ? (pedersen_verify_wire_dev<EdSuite, 4>(ctx, n, d_data, d_doff, d_sig, d_ad, d_off, d_in, d_out, d_pr, d_flags, d_ok, d_st))
-                                 : (pedersen_verify_wire_dev<P256Suite, 4>(ctx, n, d_data, d_doff, d_sig, d_ad, d_off, d_in, d_out, d_pr, d_flags, d_ok, d_st)));
+  ST(with_suite(ctx, suite, [&](auto S_) { typedef decltype(S_) S; return (pedersen_verify_wire_dev<S, 4>(ctx, n, d_data, d_doff, d_sig, d_ad, d_off, d_in, d_out, d_pr, d_flags, d_ok, d_st)); }));
   ST(copy_out(ctx, out_ok, d_ok, n));
   if (out_status) ST(copy_out(ctx, out_status, d_st, n));
   return finish_call(ctx);
@@ -1417,7 +1402,7 @@ extern "C" vrfs_status vrfs_pedersen_prove_compressed_batch(vrfs_ctx* ctx, vrfs_
   CallGuard guard_(ctx);
   if (n == 0) return VRFS_OK;
   if (!sk || !input || !output || !out_proof || !out_blinding) return fail(ctx, VRFS_BAD_ARG, "null buffer");
-  if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
+  if ((unsigned)suite >= VRFS_SUITE_COUNT) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
   ST(begin_call(ctx, n));
   const size_t pl = (size_t)vrfs_suite_pedersen_proof_len(suite);
   const uint8_t *d_sk, *d_in, *d_out, *d_ad; const uint64_t* d_off; uint8_t *d_pr, *d_bl, *d_enc;
@@ -1425,9 +1410,7 @@ extern "C" vrfs_status vrfs_pedersen_prove_compressed_batch(vrfs_ctx* ctx, vrfs_
   ST(stage_ad(ctx, n, ad, ad_off, &d_ad, &d_off));
   ST(stage_out(ctx, BUF_OUT0, n * 256, &d_pr)); ST(stage_out(ctx, BUF_OUT1, n * 32, &d_bl)); ST(stage_out(ctx, BUF_X1, n * pl, &d_enc));
   mark_secret(ctx, BUF_OUT1, n * 32);
-  ST(suite == VRFS_BANDERSNATCH_ELL2 ? pedersen_prove_compressed_dev<BandSuite>(ctx, n, d_sk, d_in, d_out, d_ad, d_off, d_pr, d_bl, d_enc)
-     : suite == VRFS_ED25519_TAI ? pedersen_prove_compressed_dev<EdSuite>(ctx, n, d_sk, d_in, d_out, d_ad, d_off, d_pr, d_bl, d_enc)
-                                 : pedersen_prove_compressed_dev<P256Suite>(ctx, n, d_sk, d_in, d_out, d_ad, d_off, d_pr, d_bl, d_enc));
+  ST(with_suite(ctx, suite, [&](auto S_) { typedef decltype(S_) S; return pedersen_prove_compressed_dev<S>(ctx, n, d_sk, d_in, d_out, d_ad, d_off, d_pr, d_bl, d_enc); }));
   ST(copy_out(ctx, out_proof, d_enc, n * pl)); ST(copy_out(ctx, out_blinding, d_bl, n * 32));
   return finish_call(ctx);
 }
@@ -1437,7 +1420,7 @@ extern "C" vrfs_status vrfs_pedersen_verify_compressed_batch(vrfs_ctx* ctx, vrfs
   CallGuard guard_(ctx);
   if (n == 0) return VRFS_OK;
   if (!input || !output || !proof || !out_ok) return fail(ctx, VRFS_BAD_ARG, "null buffer");
-  if ((unsigned)suite > VRFS_P256_TAI) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
+  if ((unsigned)suite >= VRFS_SUITE_COUNT) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
   ST(begin_call(ctx, n));
   const size_t pl = (size_t)vrfs_suite_pedersen_proof_len(suite);
   const uint8_t *d_enc, *d_ad, *d_in, *d_out; const uint64_t* d_off;
@@ -1448,9 +1431,7 @@ extern "C" vrfs_status vrfs_pedersen_verify_compressed_batch(vrfs_ctx* ctx, vrfs
   ST(stage_out(ctx, BUF_IN2, n * 256, &d_pr)); ST(stage_out(ctx, BUF_X4, 5 * n, &d_flags)); ST(stage_out(ctx, BUF_OUT0, n, &d_ok));
   if (out_status) ST(stage_out(ctx, BUF_OUT1, n, &d_st));
   uint8_t *m_in = const_cast<uint8_t*>(d_in), *m_out = const_cast<uint8_t*>(d_out);
-  ST(suite == VRFS_BANDERSNATCH_ELL2 ? (pedersen_verify_wire_dev<BandSuite, 3>(ctx, n, nullptr, nullptr, d_enc, d_ad, d_off, m_in, m_out, d_pr, d_flags, d_ok, d_st))
-     : suite == VRFS_ED25519_TAI ? (pedersen_verify_wire_dev<EdSuite, 3>(ctx, n, nullptr, nullptr, d_enc, d_ad, d_off, m_in, m_out, d_pr, d_flags, d_ok, d_st))
-                                 : (pedersen_verify_wire_dev<P256Suite, 3>(ctx, n, nullptr, nullptr, d_enc, d_ad, d_off, m_in, m_out, d_pr, d_flags, d_ok, d_st)));
+  ST(with_suite(ctx, suite, [&](auto S_) { typedef decltype(S_) S; return (pedersen_verify_wire_dev<S, 3>(ctx, n, nullptr, nullptr, d_enc, d_ad, d_off, m_in, m_out, d_pr, d_flags, d_ok, d_st)); }));
   ST(copy_out(ctx, out_ok, d_ok, n));
   if (out_status) ST(copy_out(ctx, out_status, d_st, n));
   return finish_call(ctx);

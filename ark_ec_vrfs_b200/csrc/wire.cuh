@@ -45,6 +45,25 @@ template <> struct SubgroupCheck<EdCurve> {
     return R.X.is_zero() && R.Y == R.Z && !R.Y.is_zero();
   }
 };
+// [r]P == O by double-and-add over the public bits of r (warp-uniform branches), for the curves added by SURVEY 8(f)4
+template <class C> struct SubgroupCheckMulR {
+  static HD_INLINE bool run(const typename C::F& x, const typename C::F& y) {
+    typedef Grp<C> G;
+    typename G::Pt P, Rr;
+    G::from_affine(P, x, y);
+    G::set_identity(Rr);
+#pragma unroll 1
+    for (int i = 255; i >= 0; i--) {
+      G::dbl(&Rr);
+      if ((C::Fr::mod(i >> 5) >> (i & 31)) & 1u) G::add(&Rr, &Rr, &P);
+    }
+    if constexpr (C::IS_TE) return Rr.X.is_zero() && Rr.Y == Rr.Z && !Rr.Y.is_zero();
+    else return Rr.Z.is_zero();
+  }
+};
+template <> struct SubgroupCheck<JubCurve> : SubgroupCheckMulR<JubCurve> {};
+template <> struct SubgroupCheck<BjjCurve> : SubgroupCheckMulR<BjjCurve> {};
+template <> struct SubgroupCheck<BandSwCurve> : SubgroupCheckMulR<BandSwCurve> {};
 template <> struct SubgroupCheck<P256Curve> {           // cofactor 1
   static HD_INLINE bool run(const P256Curve::F&, const P256Curve::F&) { return true; }
 };

@@ -6,8 +6,9 @@ import numpy as np
 
 from . import _lib
 
-BANDERSNATCH, ED25519, P256 = 0, 1, 2
-SUITE_NAMES = {0: "Bandersnatch_SHA-512_ELL2", 1: "Ed25519_SHA-512_TAI", 2: "secp256r1 (RFC 9381 suite 0x01)"}
+BANDERSNATCH, ED25519, P256, BANDERSNATCH_SW, JUBJUB, BABYJUBJUB = 0, 1, 2, 3, 4, 5
+SUITE_NAMES = {0: "Bandersnatch_SHA-512_ELL2", 1: "Ed25519_SHA-512_TAI", 2: "secp256r1 (RFC 9381 suite 0x01)",
+               3: "Bandersnatch_SW_SHA-512_TAI", 4: "JubJub_SHA-512_TAI", 5: "BabyJubJub_SHA-512_TAI"}
 
 
 def _u8(a, shape):

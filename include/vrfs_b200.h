@@ -41,8 +41,13 @@ extern "C" {
 
 typedef struct vrfs_ctx vrfs_ctx;
 typedef enum { VRFS_OK = 0, VRFS_INVALID_DATA = 1, VRFS_CUDA_ERROR = 2, VRFS_BAD_ARG = 3, VRFS_UNSUPPORTED = 4 } vrfs_status;
-/* `suites::{bandersnatch, ed25519, secp256r1}` (lib.rs:13-17) */
-typedef enum { VRFS_BANDERSNATCH_ELL2 = 0, VRFS_ED25519_TAI = 1, VRFS_P256_TAI = 2 } vrfs_suite;
+/* `suites::{bandersnatch, ed25519, secp256r1}` (lib.rs:13-17) and, per SURVEY 8(f)4, the remaining suites of the crate:
+ * bandersnatch_sw ("Bandersnatch_SW_SHA-512_TAI", the short-Weierstrass form; encoded points are arkworks' 33-byte x || flags),
+ * jubjub ("JubJub_SHA-512_TAI") and baby-jubjub ("BabyJubJub_SHA-512_TAI").  The last three are PARITY UNPINNED: curve constants are
+ * checked numerically, suite strings / CHALLENGE_LEN = 32 are recalled, and their Pedersen blinding bases are placeholders
+ * (data_to_point of a fixed label) until the crate's constants are available. */
+typedef enum { VRFS_BANDERSNATCH_ELL2 = 0, VRFS_ED25519_TAI = 1, VRFS_P256_TAI = 2, VRFS_BANDERSNATCH_SW_TAI = 3, VRFS_JUBJUB_TAI = 4,
+               VRFS_BABYJUBJUB_TAI = 5, VRFS_SUITE_COUNT = 6 } vrfs_suite;
 /* Per-item result of the verifiers: the reference's `Result<(), Error>` with `Error::{VerificationFailure, InvalidData}`
  * (/root/reference/src/lib.rs:13-17, `Error`).  Every verify entry point takes an optional `out_status` array (may be NULL)
  * next to `out_ok`:

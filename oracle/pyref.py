@@ -219,7 +219,7 @@ class Suite:
 
     @property
     def pt_len(self) -> int:
-        return 33 if self.codec == "sec1" else 32
+        return 33 if (self.codec == "sec1" or self.curve.kind == "sw") else 32
 
 
 SUITE_BANDERSNATCH = Suite(
@@ -235,6 +235,47 @@ SUITE_P256 = Suite(
     "secp256r1", b"\x01", 16, "sha256", "sec1", "tai", "rfc6979", P256,
     (55516455597544811540149985232155473070193196202193483189274003004283034832642,
      48580550536742846740990228707183741745344724157532839324866819111997786854582))
+
+
+# ---- the remaining suites of `ark_vrf::suites` (bandersnatch_sw, jubjub, baby-jubjub).  Curve constants are those of
+# ark-ed-on-bls12-381-bandersnatch (SWConfig), ark-ed-on-bls12-381 and ark-ed-on-bn254, recalled and CHECKED numerically (on the
+# curve, generator of prime order r, cofactor).  The suite strings, CHALLENGE_LEN = 32, TAI hash-to-curve and the arkworks codec are
+# [RECALL]; the Pedersen blinding bases of these suites are NOT recalled: the placeholders below are
+# data_to_point(b"vrfs-b200 blinding base " || SUITE_ID) and must be replaced by the crate's constants.  PARITY UNPINNED.
+BANDERSNATCH_SW = SWCurve(
+    "bandersnatch_sw", BLS_FR,
+    10773120815616481058602537765553212789256758185246796157495669123169359657269,
+    29569587568322301171008055308580903175558631321415017492731745847794083609535,
+    BANDERSNATCH.r, 4,
+    (30900340493481298850216505686589334086208278925799850409469406976849338430199,
+     12663882780877899054958035777720958383845500985908634476792678820121468453298))
+JUBJUB = TECurve(
+    "jubjub", BLS_FR, (-1) % BLS_FR, 19257038036680949359750312669786877991949435402254120286184196891950884077233,
+    0x0e7db4ea6533afa906673b0101343b00a6682093ccc81082d0970e5ed6f72cb7, 8,
+    (8076246640662884909881801758704306714034609987455869804520522091855516602923,
+     13262374693698910701929044844600465831413122818447359594527400194675274060458))
+BN254_FR = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+BABYJUBJUB = TECurve(
+    "babyjubjub", BN254_FR, 1, 9706598848417545097372247223557719406784115219466060233080913168975159366771,
+    2736030358979909402780800718157159386076813972158567259200215660948447373041, 8,
+    (19698561148652590122159747500897617769866003486955115824547446575314762165298,
+     19298250018296453272277890825869354524455968081175474282777126169995084727839))
+
+
+def _placeholder_blinding_base(suite_id: bytes, curve):
+    S0 = Suite("tmp", suite_id, 32, "sha512", "ark", "tai", "rfc8032", curve, (0, 0))
+    return h2c_tai(S0, b"vrfs-b200 blinding base " + suite_id)
+
+
+def _late_suites():
+    out = {}
+    for idx, (name, sid, curve) in {3: ("bandersnatch_sw", b"Bandersnatch_SW_SHA-512_TAI", BANDERSNATCH_SW),
+                                    4: ("jubjub", b"JubJub_SHA-512_TAI", JUBJUB),
+                                    5: ("babyjubjub", b"BabyJubJub_SHA-512_TAI", BABYJUBJUB)}.items():
+        out[idx] = Suite(name, sid, 32, "sha512", "ark", "tai", "rfc8032", curve, _placeholder_blinding_base(sid, curve))
+    return out
+
+
 SUITES = {0: SUITE_BANDERSNATCH, 1: SUITE_ED25519, 2: SUITE_P256}
 
 
@@ -254,6 +295,12 @@ def enc_pt(S: Suite, P) -> bytes:
     if S.codec == "sec1":
         assert P is not None
         return bytes([2 + (P[1] & 1)]) + P[0].to_bytes(32, "big")
+    if S.curve.kind == "sw":
+        # arkworks short-Weierstrass compressed form [RECALL]: x little-endian over ceil((bits + 2 flag bits)/8) = 33 bytes, the top two
+        # bits of the last byte are the flags: bit 7 = y is the larger root (y > (p-1)/2), bit 6 = point at infinity
+        if P is None:
+            return bytes(32) + b"\x40"
+        return P[0].to_bytes(32, "little") + bytes([0x80 if P[1] > (S.curve.p - 1) // 2 else 0])
     p = S.curve.p
     e = bytearray(P[1].to_bytes(32, "little"))
     if P[0] > (p - 1) // 2:
@@ -275,6 +322,23 @@ def dec_pt(S: Suite, b: bytes):
         if y is None:
             return None
         if (y & 1) != (b[0] & 1):
+            y = (p - y) % p
+        return (x, y)
+    if C.kind == "sw":
+        if len(b) < 33:
+            return None
+        flags = b[32] >> 6
+        if flags == 3:
+            return None                               # both flags: SWFlags::from_u8 gives None
+        x = int.from_bytes(b[:32], "little")
+        if x >= p:
+            return None
+        if flags == 1:
+            return None                               # the identity: no typed Public / Input / Output holds it
+        y = sqrt_mod((x * x * x + C.a * x + C.b) % p, p)
+        if y is None:
+            return None
+        if (y > (p - 1) // 2) != bool(flags & 2):
             y = (p - y) % p
         return (x, y)
     b = bytearray(b[:32])
@@ -352,8 +416,8 @@ def h2c_tai(S: Suite, data: bytes, return_ctr: bool = False):
     C = S.curve
     for ctr in range(256):
         hs = S.H(S.suite_id + b"\x01" + data + bytes([ctr]) + b"\x00")
-        P = dec_pt(S, b"\x02" + hs) if S.codec == "sec1" else dec_pt(S, hs[:32])
-        if P is None:
+        P = dec_pt(S, b"\x02" + hs) if S.codec == "sec1" else dec_pt(S, hs[:S.pt_len])
+        if P is None or P == "inf":
             continue
         P = C.mul(C.h, P)
         if C.is_identity(P):
@@ -541,3 +605,7 @@ def glv_decompose(k: int, r: int, lam: int, basis=None):
     k2 = -c1 * b1 - c2 * b2
     assert (k1 + k2 * lam - k) % r == 0
     return k1, k2
+
+
+SUITES.update(_late_suites())
+SUITE_BANDERSNATCH_SW, SUITE_JUBJUB, SUITE_BABYJUBJUB = SUITES[3], SUITES[4], SUITES[5]

@@ -392,12 +392,15 @@ static int aff_eq(const curve *C, const aff *A, const aff *B) {
 /* ======================================================================================
  * Global parameter tables (hex literals generated into curve_consts.h)
  * ====================================================================================== */
-static fctx F_BLSFR, F_BANDR, F_25519, F_EDL, F_P256, F_P256N, F_BLSFQ;
-static curve C_BAND, C_ED, C_P256, C_G1;
+static fctx F_BLSFR, F_BANDR, F_25519, F_EDL, F_P256, F_P256N, F_BLSFQ, F_JUBR, F_BN254R, F_BJJR;
+static curve C_BAND, C_ED, C_P256, C_G1, C_BSW, C_JUB, C_BJJ;
 typedef struct {
     const curve *C; const uint8_t *suite_id; size_t suite_id_len; int clen, is512, sec1, ell2, rfc6979; aff B;
 } suite_t;
-static suite_t SUITES[3];
+#define N_SUITES 6
+static suite_t SUITES[N_SUITES];
+/* encoded point length: 32 B for the arkworks twisted-Edwards form; 33 B for SEC1 and for the arkworks short-Weierstrass form */
+static size_t pt_len(const suite_t *S) { return (S->sec1 || !S->C->is_te) ? 33 : 32; }
 static fe ELL2_JK, ELL2_KSQI, ELL2_K, ELL2_Z;   /* J/K, 1/K^2, K, Z=5 (A.5) */
 static pthread_once_t init_once = PTHREAD_ONCE_INIT;
 
@@ -438,6 +441,26 @@ static void init_all(void) {
     set_aff_hex(&F_25519, &SUITES[1].B, HEX_ED_BX, HEX_ED_BY);
     set_aff_hex(&F_P256, &SUITES[2].B, HEX_P256_BX, HEX_P256_BY);
 
+    /* bandersnatch_sw, jubjub, baby-jubjub - constants checked in oracle/pyref.py; suite strings [RECALL];
+     * blinding bases are placeholders (pyref._placeholder_blinding_base).  PARITY UNPINNED. */
+    fctx_init(&F_JUBR, 4, HEX_JUB_R); fctx_init(&F_BN254R, 4, HEX_BN254_FR); fctx_init(&F_BJJR, 4, HEX_BJJ_R);
+    memset(&C_BSW, 0, sizeof C_BSW); C_BSW.F = &F_BLSFR; C_BSW.Fr = &F_BANDR; C_BSW.cof_log2 = 2;
+    hex_to_fe(&t, HEX_BSW_A); f_from_raw(&F_BLSFR, &C_BSW.a, &t); hex_to_fe(&t, HEX_BSW_B); f_from_raw(&F_BLSFR, &C_BSW.d_or_b, &t);
+    set_aff_hex(&F_BLSFR, &C_BSW.G, HEX_BSW_GX, HEX_BSW_GY);
+    memset(&C_JUB, 0, sizeof C_JUB); C_JUB.is_te = 1; C_JUB.F = &F_BLSFR; C_JUB.Fr = &F_JUBR; C_JUB.cof_log2 = 3;
+    f_neg(&F_BLSFR, &C_JUB.a, &F_BLSFR.one); hex_to_fe(&t, HEX_JUB_D); f_from_raw(&F_BLSFR, &C_JUB.d_or_b, &t);
+    set_aff_hex(&F_BLSFR, &C_JUB.G, HEX_JUB_GX, HEX_JUB_GY);
+    memset(&C_BJJ, 0, sizeof C_BJJ); C_BJJ.is_te = 1; C_BJJ.F = &F_BN254R; C_BJJ.Fr = &F_BJJR; C_BJJ.cof_log2 = 3;
+    C_BJJ.a = F_BN254R.one; hex_to_fe(&t, HEX_BJJ_D); f_from_raw(&F_BN254R, &C_BJJ.d_or_b, &t);
+    set_aff_hex(&F_BN254R, &C_BJJ.G, HEX_BJJ_GX, HEX_BJJ_GY);
+    static const uint8_t id_bsw[] = "Bandersnatch_SW_SHA-512_TAI", id_jub[] = "JubJub_SHA-512_TAI", id_bjj[] = "BabyJubJub_SHA-512_TAI";
+    SUITES[3].C = &C_BSW; SUITES[3].suite_id = id_bsw; SUITES[3].suite_id_len = 27; SUITES[3].clen = 32; SUITES[3].is512 = 1;
+    SUITES[4].C = &C_JUB; SUITES[4].suite_id = id_jub; SUITES[4].suite_id_len = 18; SUITES[4].clen = 32; SUITES[4].is512 = 1;
+    SUITES[5].C = &C_BJJ; SUITES[5].suite_id = id_bjj; SUITES[5].suite_id_len = 22; SUITES[5].clen = 32; SUITES[5].is512 = 1;
+    set_aff_hex(&F_BLSFR, &SUITES[3].B, HEX_BSW_BX, HEX_BSW_BY);
+    set_aff_hex(&F_BLSFR, &SUITES[4].B, HEX_JUB_BX, HEX_JUB_BY);
+    set_aff_hex(&F_BN254R, &SUITES[5].B, HEX_BJJ_BX, HEX_BJJ_BY);
+
     fe A_, B_, bi;
     hex_to_fe(&t, HEX_BAND_MONT_A); f_from_raw(&F_BLSFR, &A_, &t);
     hex_to_fe(&t, HEX_BAND_MONT_B); f_from_raw(&F_BLSFR, &B_, &t);
@@ -446,7 +469,7 @@ static void init_all(void) {
 }
 static const suite_t *get_suite(int id) { pthread_once(&init_once, init_all); return &SUITES[id]; }
 int oracle_hash_len(int suite) { return get_suite(suite)->is512 ? 64 : 32; }
-int oracle_point_enc_len(int suite) { return get_suite(suite)->sec1 ? 33 : 32; }
+int oracle_point_enc_len(int suite) { return (int)pt_len(get_suite(suite)); }
 int oracle_challenge_len(int suite) { return get_suite(suite)->clen; }
 
 /* ======================================================================================
@@ -472,6 +495,10 @@ static void store_scalar(fe *k, uint8_t *b) { for (int i = 0; i < 4; i++) for (i
 static size_t enc_point(const suite_t *S, const aff *A, uint8_t *out) {
     const fctx *F = S->C->F;
     if (S->sec1) { out[0] = (uint8_t)(2 + f_is_odd(F, &A->y)); f_to_be32(F, &A->x, out + 1); return 33; }
+    if (!S->C->is_te) {   /* arkworks short-Weierstrass compressed form [RECALL]: x LE (32 B) + flag byte: bit 7 = y > (p-1)/2, bit 6 = infinity */
+        if (A->inf) { memset(out, 0, 33); out[32] = 0x40; return 33; }
+        f_to_le(F, &A->x, out); out[32] = f_is_high(F, &A->y) ? 0x80 : 0x00; return 33;
+    }
     f_to_le(F, &A->y, out); if (f_is_high(F, &A->x)) out[31] |= 0x80; return 32;
 }
 static size_t enc_scalar(const suite_t *S, const fe *k_raw, uint8_t *out) {
@@ -488,6 +515,16 @@ static int dec_point(const suite_t *S, aff *A, const uint8_t *in) {   /* on-curv
         fe rhs, t; f_sqr(F, &rhs, &A->x); f_mul(F, &rhs, &rhs, &A->x); f_mul(F, &t, &C->a, &A->x); f_add(F, &rhs, &rhs, &t); f_add(F, &rhs, &rhs, &C->d_or_b);
         if (!f_sqrt(F, &A->y, &rhs)) return 0;
         if (f_is_odd(F, &A->y) != (in[0] & 1)) f_neg(F, &A->y, &A->y);
+        return 1;
+    }
+    if (!C->is_te) {
+        int flags = in[32] >> 6;
+        if (flags == 3) return 0;
+        if (!f_from_le_canonical(F, &A->x, in)) return 0;
+        if (flags == 1) return 0;                   /* the identity: no typed Public / Input / Output holds it */
+        fe rhs, t; f_sqr(F, &rhs, &A->x); f_mul(F, &rhs, &rhs, &A->x); f_mul(F, &t, &C->a, &A->x); f_add(F, &rhs, &rhs, &t); f_add(F, &rhs, &rhs, &C->d_or_b);
+        if (!f_sqrt(F, &A->y, &rhs)) return 0;
+        if (f_is_high(F, &A->y) != ((flags >> 1) & 1)) f_neg(F, &A->y, &A->y);
         return 1;
     }
     uint8_t b[32]; memcpy(b, in, 32); int sign = b[31] >> 7; b[31] &= 0x7f;
@@ -714,7 +751,7 @@ void oracle_secret_from_seed_batch(int suite, size_t n, const uint8_t *seeds, co
     bctx x = {0}; x.S = get_suite(suite); x.a = seeds; x.off = seed_off; x.o1 = out_sk; x.o2 = out_pk; parallel_for(n, nthreads, it_from_seed, &x);
 }
 static void it_enc(void *p, size_t i) {
-    bctx *x = p; aff A; size_t L = x->S->sec1 ? 33 : 32;
+    bctx *x = p; aff A; size_t L = pt_len(x->S);
     if (!load_point(x->S->C, &A, x->a + 64 * i) || (!x->S->C->is_te && A.inf)) { memset(x->o1 + L * i, 0, L); return; }
     enc_point(x->S, &A, x->o1 + L * i);
 }
@@ -722,7 +759,7 @@ void oracle_point_encode_batch(int suite, size_t n, const uint8_t *pts, uint8_t 
     bctx x = {0}; x.S = get_suite(suite); x.a = pts; x.o1 = out_enc; parallel_for(n, nthreads, it_enc, &x);
 }
 static void it_dec(void *p, size_t i) {
-    bctx *x = p; aff A; size_t L = x->S->sec1 ? 33 : 32; int ok = dec_point(x->S, &A, x->a + L * i);
+    bctx *x = p; aff A; size_t L = pt_len(x->S); int ok = dec_point(x->S, &A, x->a + L * i);
     x->o2[i] = (uint8_t)ok; if (ok) store_point(x->S->C, &A, x->o1 + 64 * i); else memset(x->o1 + 64 * i, 0, 64);
 }
 void oracle_point_decode_batch(int suite, size_t n, const uint8_t *enc, uint8_t *out_pts, uint8_t *out_ok, int nthreads) {
@@ -825,9 +862,10 @@ void oracle_pedersen_verify_batch(int suite, size_t n, const uint8_t *input, con
  * signature = point_encode(Output) || c || s   (Bandersnatch 96 B; secp256r1 81 B = RFC 9381 pi_string)
  * ====================================================================================== */
 static int in_prime_subgroup(const curve *C, const aff *A) {
-    if (!C->is_te) return 1;                       /* cofactor 1 */
+    if (C->cof_log2 == 0) return 1;                /* cofactor 1 */
     const fctx *F = C->F; proj p, r; pt_from_aff(C, &p, A);
     pt_mul(C, &r, C->Fr->p.v, C->Fr->n, &p);
+    if (!C->is_te) return pt_is_identity(C, &r);   /* short Weierstrass with a cofactor (bandersnatch_sw) */
     /* ark-ec twisted_edwards::Projective::is_zero: x == 0 && y == z && y != 0 && t == 0 */
     return f_is_zero(F, &r.X) && f_eq(F, &r.Y, &r.Z) && !f_is_zero(F, &r.Y) && f_is_zero(F, &r.T);
 }
@@ -842,20 +880,20 @@ void oracle_subgroup_check_batch(int suite, size_t n, const uint8_t *pts, uint8_
     bctx x = {0}; x.S = get_suite(suite); x.a = pts; x.o1 = out_ok; parallel_for(n, nthreads, it_subgroup, &x);
 }
 static void it_dec_checked(void *p, size_t i) {
-    bctx *x = p; aff A; size_t L = x->S->sec1 ? 33 : 32; int ok = dec_point_checked(x->S, &A, x->a + L * i);
+    bctx *x = p; aff A; size_t L = pt_len(x->S); int ok = dec_point_checked(x->S, &A, x->a + L * i);
     x->o2[i] = (uint8_t)ok; if (ok) store_point(x->S->C, &A, x->o1 + 64 * i); else memset(x->o1 + 64 * i, 0, 64);
 }
 void oracle_point_decode_checked_batch(int suite, size_t n, const uint8_t *enc, uint8_t *out_pts, uint8_t *out_ok, int nthreads) {
     bctx x = {0}; x.S = get_suite(suite); x.a = enc; x.o1 = out_pts; x.o2 = out_ok; parallel_for(n, nthreads, it_dec_checked, &x);
 }
-int oracle_ietf_signature_len(int suite) { const suite_t *S = get_suite(suite); return (S->sec1 ? 33 : 32) + S->clen + 32; }
+int oracle_ietf_signature_len(int suite) { const suite_t *S = get_suite(suite); return pt_len(S) + S->clen + 32; }
 /* c (canonical raw) -> CHALLENGE_LEN bytes in codec order */
 static void enc_challenge(const suite_t *S, const fe *c_raw, uint8_t *out) {
     uint8_t t[32]; fe k = *c_raw; store_scalar(&k, t);
     if (S->sec1) for (int i = 0; i < S->clen; i++) out[i] = t[S->clen - 1 - i]; else memcpy(out, t, (size_t)S->clen);
 }
 static void it_sign_wire(void *p, size_t i) {
-    bctx *x = p; const suite_t *S = x->S; const curve *C = S->C; size_t PL = S->sec1 ? 33 : 32, SL = PL + (size_t)S->clen + 32;
+    bctx *x = p; const suite_t *S = x->S; const curve *C = S->C; size_t PL = pt_len(S), SL = PL + (size_t)S->clen + 32;
     uint8_t *sig = x->o1 + SL * i; fe sk, c, s; aff I, O;
     load_scalar(C, &sk, x->a + 32 * i);
     if (!data_to_point(S, &I, x->b + x->off[i], (size_t)(x->off[i + 1] - x->off[i]))) { memset(sig, 0, SL); x->o2[i] = 0; return; }
@@ -873,7 +911,7 @@ void oracle_ietf_sign_wire_batch(int suite, size_t n, const uint8_t *sk, const u
     parallel_for(n, nthreads, it_sign_wire, &x);
 }
 static void it_verify_wire(void *p, size_t i) {
-    bctx *x = p; const suite_t *S = x->S; const curve *C = S->C; size_t PL = S->sec1 ? 33 : 32, SL = PL + (size_t)S->clen + 32;
+    bctx *x = p; const suite_t *S = x->S; const curve *C = S->C; size_t PL = pt_len(S), SL = PL + (size_t)S->clen + 32;
     const uint8_t *sig = x->e + SL * i; aff Y, I, O; fe c, s, m;
     x->o1[i] = 0; if (x->o2) memset(x->o2 + (size_t)(S->is512 ? 64 : 32) * i, 0, S->is512 ? 64 : 32);
     SET_ST(x, i, ST_INVALID_DATA);                                                       /* every early return below is a failed deserialisation */
@@ -906,9 +944,9 @@ void oracle_ietf_verify_wire_batch(int suite, size_t n, const uint8_t *pk_enc, c
 
 /* pedersen wire form: point_encode(Output) || point_encode(pk_com) || point_encode(r) || point_encode(ok) || s || sb
  * (`Output` followed by `pedersen::Proof`'s CanonicalSerialize, A.10); the blinding factor stays with the prover. */
-int oracle_pedersen_signature_len(int suite) { const suite_t *S = get_suite(suite); return 4 * (S->sec1 ? 33 : 32) + 64; }
+int oracle_pedersen_signature_len(int suite) { const suite_t *S = get_suite(suite); return 4 * pt_len(S) + 64; }
 static void it_ped_sign_wire(void *p, size_t i) {
-    bctx *x = p; const suite_t *S = x->S; const curve *C = S->C; size_t PL = S->sec1 ? 33 : 32, SL = 4 * PL + 64;
+    bctx *x = p; const suite_t *S = x->S; const curve *C = S->C; size_t PL = pt_len(S), SL = 4 * PL + 64;
     uint8_t *sig = x->o1 + SL * i; fe sk, bl; aff I, O; ped_proof pr;
     load_scalar(C, &sk, x->a + 32 * i);
     if (!data_to_point(S, &I, x->b + x->off[i], (size_t)(x->off[i + 1] - x->off[i]))) { memset(sig, 0, SL); memset(x->o3 + 32 * i, 0, 32); x->o2[i] = 0; return; }
@@ -933,7 +971,7 @@ static int dec_scalar_canonical(const suite_t *S, fe *k_raw, const uint8_t *in) 
     f_to_raw(S->C->Fr, k_raw, &m); return 1;
 }
 static void it_ped_verify_wire(void *p, size_t i) {
-    bctx *x = p; const suite_t *S = x->S; size_t PL = S->sec1 ? 33 : 32, SL = 4 * PL + 64;
+    bctx *x = p; const suite_t *S = x->S; size_t PL = pt_len(S), SL = 4 * PL + 64;
     const uint8_t *sig = x->e + SL * i; aff I, O; ped_proof pr;
     x->o1[i] = 0; SET_ST(x, i, ST_INVALID_DATA);
     if (!dec_point_checked(S, &O, sig) || !dec_point_checked(S, &pr.Yb, sig + PL) || !dec_point_checked(S, &pr.R, sig + 2 * PL) || !dec_point_checked(S, &pr.Ok, sig + 3 * PL)) return;

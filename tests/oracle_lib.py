@@ -10,7 +10,7 @@ ORACLE_DIR = os.path.join(ROOT, "oracle")
 _lib = None
 NTHREADS = max(1, os.cpu_count() or 1)
 
-BANDERSNATCH, ED25519, P256 = 0, 1, 2
+BANDERSNATCH, ED25519, P256, BANDERSNATCH_SW, JUBJUB, BABYJUBJUB = 0, 1, 2, 3, 4, 5
 
 
 def build():

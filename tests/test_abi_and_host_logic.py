@@ -31,9 +31,9 @@ def test_library_exports_every_declared_symbol(lib):
     for s in declared:
         assert hasattr(lib, s), s
     assert lib.vrfs_abi_version() == 2
-    assert [lib.vrfs_suite_challenge_len(i) for i in range(3)] == [32, 16, 16]
-    assert [lib.vrfs_suite_hash_len(i) for i in range(3)] == [64, 64, 32]
-    assert [lib.vrfs_suite_point_enc_len(i) for i in range(3)] == [32, 32, 33]
+    assert [lib.vrfs_suite_challenge_len(i) for i in range(7)] == [32, 16, 16, 32, 32, 32, 0]
+    assert [lib.vrfs_suite_hash_len(i) for i in range(7)] == [64, 64, 32, 64, 64, 64, 0]
+    assert [lib.vrfs_suite_point_enc_len(i) for i in range(7)] == [32, 32, 33, 33, 32, 32, 0]
 
 
 def test_no_cpu_fallback_without_gpu(lib):

@@ -7,7 +7,7 @@ import pytest
 import oracle_lib as O
 import vectors as V
 
-SUITES = [O.BANDERSNATCH, O.ED25519, O.P256]
+SUITES = [O.BANDERSNATCH, O.ED25519, O.P256, O.BANDERSNATCH_SW, O.JUBJUB, O.BABYJUBJUB]
 
 
 @pytest.fixture(scope="module")

@@ -21,7 +21,7 @@ def eng():
     e.close()
 
 
-@pytest.mark.parametrize("suite", [O.BANDERSNATCH, O.ED25519, O.P256])
+@pytest.mark.parametrize("suite", [O.BANDERSNATCH, O.ED25519, O.P256, O.BANDERSNATCH_SW, O.JUBJUB, O.BABYJUBJUB])
 @pytest.mark.parametrize("ad_kind", ["empty", "fixed32", "ragged"])
 def test_ietf_verify_matches_oracle(eng, suite, ad_kind):
     n = 600

@@ -11,7 +11,7 @@ import vectors as V
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
-TE_SUITES = [O.BANDERSNATCH, O.ED25519, O.P256]
+TE_SUITES = [O.BANDERSNATCH, O.ED25519, O.P256, O.BANDERSNATCH_SW, O.JUBJUB, O.BABYJUBJUB]      # every suite of the crate (the last three)
 
 
 @pytest.fixture(scope="module")
