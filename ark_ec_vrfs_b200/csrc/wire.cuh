@@ -5,6 +5,11 @@
 //            ark-ec's default `mul_bigint(r).is_zero()`; any test deciding the same predicate gives the same verdict.
 //   proof  : c = CHALLENGE_LEN bytes in codec byte order (reduced mod r), s = 32 bytes, rejected when >= r   (A.9)
 //   signature = point_encode(Output) || c || s      (Bandersnatch 96 B, Ed25519 80 B, secp256r1 81 B = RFC 9381 pi_string)
+// secp256r1 caveat (parity unpinned): what is implemented for that suite is the CODEC's form - SEC1 points and
+// big-endian scalars, i.e. RFC 9381's pi_string, pinned by the RFC's Examples 10-11.  Whether the crate's derived
+// CanonicalSerialize of `Public` / `Output` / `pedersen::Proof` uses this or arkworks' native short-Weierstrass form (33-byte
+// little-endian x || flags, little-endian s - the form the engine implements for bandersnatch_sw, `ARK_SW`) cannot be settled
+// without the crate; a caller that needs the latter for secp256r1 must re-encode.  Bandersnatch and Ed25519 are unaffected.
 #pragma once
 #include "h2c.cuh"
 

@@ -130,7 +130,10 @@ vrfs_status vrfs_pedersen_verify_compressed_batch(vrfs_ctx*, vrfs_suite, size_t 
  *                   prime-order subgroup (the reference: ark-ec `mul_bigint(r).is_zero()`; here a 2-descent for
  *                   Bandersnatch, [L]P for Ed25519, nothing for cofactor-1 secp256r1 - same predicate)
  *   proof         : c (CHALLENGE_LEN bytes, codec byte order, reduced mod r) || s (32 bytes, rejected when >= r)
- *   signature     : point_encode(Output) || proof   (Bandersnatch 96 B, Ed25519 80 B, secp256r1 81 B = RFC 9381 pi_string) */
+ *   signature     : point_encode(Output) || proof   (Bandersnatch 96 B, Ed25519 80 B, secp256r1 81 B = RFC 9381 pi_string)
+ * secp256r1: the wire form is the CODEC's (SEC1 points, big-endian scalars = RFC 9381 pi_string, pinned by the RFC's examples), not
+ * necessarily the crate's derived CanonicalSerialize (possibly arkworks' 33-byte little-endian x || flags with little-endian
+ * scalars) - unpinned without the crate; see csrc/wire.cuh. */
 int vrfs_suite_ietf_signature_len(vrfs_suite s);
 vrfs_status vrfs_point_decode_checked_batch(vrfs_ctx*, vrfs_suite, size_t n, const uint8_t* enc, uint8_t* out_pts /*n*64*/, uint8_t* out_ok);
 vrfs_status vrfs_subgroup_check_batch(vrfs_ctx*, vrfs_suite, size_t n, const uint8_t* pts /*n*64*/, uint8_t* out_ok);

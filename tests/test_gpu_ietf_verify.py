@@ -107,3 +107,36 @@ def test_concurrent_calls_on_one_context_serialise():
     for t in ts: t.join()
     eng.close()
     assert not errs, errs
+
+
+@pytest.mark.parametrize("suite", [O.BANDERSNATCH, O.ED25519])
+def test_raw_verify_on_small_order_and_out_of_subgroup_points(eng, suite):
+    """The typed values of the reference are prime-order-subgroup points (arkworks validates on deserialisation), and the raw ABI
+    documents that as its contract (include/vrfs_b200.h); the wire entry points enforce it.  This test pins what the raw entry
+    point does when the contract is broken anyway - torsion points and subgroup points shifted by torsion as key, input or
+    output: the verdicts are the oracle's (all rejected: every point enters the challenge hash, so no such item can carry a
+    proof that checks), and the status is never Ok."""
+    from oracle import pyref as R
+    S = R.SUITES[suite]; C = S.curve
+    n = 64
+    w = V.make_ietf_proofs(suite, n, "fixed32", corrupt=False)
+    pk, inp, out, c, s = (w[k].copy() for k in ("pk", "inp", "out", "c", "s"))
+    pt = lambda P: np.frombuffer(P[0].to_bytes(32, "little") + P[1].to_bytes(32, "little"), np.uint8)
+    # torsion points of the curve: (0, 1) identity, (0, -1) of order 2, and for Ed25519 a point of order 8
+    tors = [(0, 1), (0, C.p - 1)]
+    if suite == O.ED25519:
+        y = 2707385501144840649318225287225658788936804267575313519463743609750303402022      # y of a point of order 8 (RFC 7748 / ed25519 small-order list)
+        P8 = R.dec_pt(S, y.to_bytes(32, "little"))
+        if P8 is not None and C.is_identity(C.mul(8, P8)) and not C.is_identity(C.mul(4, P8)):
+            tors.append(P8)
+    k = 0
+    for T in tors:
+        for arr in (pk, inp, out):
+            arr[k] = pt(T); k += 1                                          # a torsion point in place of the value
+            P = (int.from_bytes(arr[k, :32].tobytes(), "little"), int.from_bytes(arr[k, 32:].tobytes(), "little"))
+            arr[k] = pt(C.add(P, T)); k += 1                                # the honest value shifted by the torsion point
+    exp, st_o = O.ietf_verify(suite, pk, inp, out, c, s, w["ads"], status=True)
+    got, st = eng.ietf_verify(suite, pk, inp, out, c, s, w["ads"], status=True)
+    assert np.array_equal(got, exp) and np.array_equal(st, st_o)
+    touched = [i for i in range(k) if not (i % 2 == 1 and tors[i // 6] == (0, 1))]   # shifting by the identity changes nothing
+    assert not got[touched].any() and got[k:].all() and (st[touched] != 0).all()
