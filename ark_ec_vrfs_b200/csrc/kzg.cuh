@@ -6,6 +6,9 @@
 //       accept  <=>  e(L, G2) e(-R, [tau] G2) = 1
 //   = one 2-column MSM over the 2k + 1 bases [C | W | G1] (csrc/msm.cuh) + one product of two pairings (csrc/pairing.cuh).
 #pragma once
+#ifndef VRFS_PAIRING_LANES_MAX_N
+#define VRFS_PAIRING_LANES_MAX_N 4096      // measured cross-over with the one-thread kernel (tools/pairing_bench.py): 4096 products 20 ms vs 27.5 ms
+#endif
 
 // one thread per product of `pairs` pairings (tests, small batches, and the reference point for the cooperative kernel)
 __global__ void __launch_bounds__(32) k_pairing_products(uint32_t n, int pairs, const uint8_t* g1, const uint8_t* g2, const uint32_t* negate,
@@ -74,15 +77,13 @@ __global__ void __launch_bounds__(128) k_g1_validate(uint32_t n, const uint8_t* 
   if (ok && level >= 2 && !p.inf) ok = g1_in_subgroup(p.x, p.y);
   if (!ok) atomicAdd(bad_count, 1u);
 }
-// the final product of two pairings of the KZG check: verdict 1 / 0, or 2 when the MSM inputs were malformed
-__global__ void __launch_bounds__(32) k_kzg_pairing(const uint8_t* lr /*2*96*/, const uint8_t* g2s /*2*192*/, const uint32_t* bad_count, uint8_t* out_verdict) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  if (*bad_count) { *out_verdict = 2; return; }
-  *out_verdict = (uint8_t)pairing_product_check_bytes(2, lr, g2s, 2u);
-}
-
-static vrfs_status kzg_pairing_launch(vrfs_ctx* ctx, const uint8_t* d_lr, const uint8_t* d_g2s, const uint32_t* d_bad, uint8_t* d_verdict) {
-  k_kzg_pairing<<<1, 32, 0, ctx->stream>>>(d_lr, d_g2s, d_bad, d_verdict);
+// the final product of two pairings of the KZG check, e(L, G2) e(-R, [tau] G2): verdict 1 / 0, or 2 when the MSM inputs were
+// malformed.  One warp runs the lane programs of csrc/pairing_coop.cuh (1.x ms; the one-thread form took 27 ms).
+static vrfs_status kzg_pairing_launch(vrfs_ctx* ctx, const uint8_t* d_lr, const uint8_t* d_g2s, const uint32_t* d_bad, uint32_t* d_negmask, uint8_t* d_verdict) {
+  static_assert(PairingProg::NPAIRS == 2, "the KZG check is a product of two pairings");
+  static const uint32_t two = 2u;                    // negate the second G1 point
+  CU(cudaMemcpyAsync(d_negmask, &two, 4, cudaMemcpyHostToDevice, ctx->stream));
+  k_pairing_products_lanes<<<1, PairingProg::LANES, 0, ctx->stream>>>(1u, d_lr, d_g2s, d_negmask, d_bad, d_verdict, nullptr);
   LAUNCHED_AS(ctx, "kzg_pairing");
   return VRFS_OK;
 }
@@ -99,8 +100,15 @@ extern "C" vrfs_status vrfs_pairing_product_batch(vrfs_ctx* ctx, size_t n, int n
   if (negate_masks) ST(stage_in(ctx, BUF_IN2, negate_masks, n * 4, &d_neg));
   ST(stage_out(ctx, BUF_OUT0, n, &d_ok));
   if (out_gt) ST(stage_out(ctx, BUF_OUT1, n * 576, &d_gt));
-  k_pairing_products<<<(unsigned)((n + 31) / 32), 32, 0, ctx->stream>>>((uint32_t)n, n_pairs, d_g1, d_g2, (const uint32_t*)d_neg, d_ok, d_gt);
-  LAUNCHED_AS(ctx, "pairing_products");
+  // few products of two pairings: one WARP per product (csrc/pairing_coop.cuh, ~20x lower latency); large batches keep the
+  // one-thread-per-product form, whose throughput is higher once every multiplier pipe has its own products
+  if (n_pairs == PairingProg::NPAIRS && n <= VRFS_PAIRING_LANES_MAX_N) {
+    k_pairing_products_lanes<<<(unsigned)n, PairingProg::LANES, 0, ctx->stream>>>((uint32_t)n, d_g1, d_g2, (const uint32_t*)d_neg, nullptr, d_ok, d_gt);
+    LAUNCHED_AS(ctx, "pairing_products_lanes");
+  } else {
+    k_pairing_products<<<(unsigned)((n + 31) / 32), 32, 0, ctx->stream>>>((uint32_t)n, n_pairs, d_g1, d_g2, (const uint32_t*)d_neg, d_ok, d_gt);
+    LAUNCHED_AS(ctx, "pairing_products");
+  }
   ST(copy_out(ctx, out_ok, d_ok, n));
   if (out_gt) ST(copy_out(ctx, out_gt, d_gt, n * 576));
   return finish_call(ctx);
@@ -146,7 +154,7 @@ extern "C" vrfs_status vrfs_kzg_batch_verify(vrfs_ctx* ctx, size_t k, const uint
   k_msm_prep_bases<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((uint32_t)n, (const uint8_t*)d_bases, (G1Aff*)d_aff);
   LAUNCHED_AS(ctx, "msm_prep_bases");
   ST(msm_dev(ctx, msm_plan((uint32_t)n, 2, 0), d_aff, (const uint8_t*)d_scal, d_lr, 0));
-  ST(kzg_pairing_launch(ctx, d_lr, (const uint8_t*)d_g2s, (const uint32_t*)d_misc, d_ok));
+  ST(kzg_pairing_launch(ctx, d_lr, (const uint8_t*)d_g2s, (const uint32_t*)d_misc, (uint32_t*)d_misc + 8, d_ok));
   ST(copy_out(ctx, out_ok, d_ok, 1));
   return finish_call(ctx);
 }

@@ -17,7 +17,7 @@
 #include "wire.cuh"
 #include "msm.cuh"
 #include "ring.cuh"
-#include "pairing.cuh"
+#include "pairing_coop.cuh"
 
 using namespace vrfs;
 

@@ -189,7 +189,7 @@ extern "C" void hostemu_g1_compress(const uint8_t* pt96, uint8_t* out48) { g1_co
 extern "C" int hostemu_g1_decompress(const uint8_t* in48, int check_subgroup, uint8_t* out96) { return g1_decompress_one(out96, in48, check_subgroup != 0); }
 
 // BLS12-381 pairing (csrc/pairing.cuh) on the host: tower operations and the whole product check, ABI bytes in and out
-#include "../../ark_ec_vrfs_b200/csrc/pairing.cuh"
+#include "../../ark_ec_vrfs_b200/csrc/pairing_coop.cuh"
 static Fq12 f12_from_bytes(const uint8_t* b) {
   Fq381 c[12]; uint32_t raw[12];
   for (int k = 0; k < 12; k++) { load_le<12>(raw, b + 48 * k); c[k] = to_mont<BlsFq>(raw); }
@@ -211,6 +211,13 @@ extern "C" void hostemu_f12_op(int op, const uint8_t* a576, const uint8_t* b576,
     case 9: r = final_exponentiation(a); break;
   }
   f12_store(out576, r);
+}
+// the warp-cooperative form (csrc/pairing_coop.cuh): the interpreter of the generated lane programs, all lanes played in turn
+extern "C" int hostemu_pairing_product_lanes(const uint8_t* g1, const uint8_t* g2, unsigned negate, uint8_t* out_gt576) {
+  Fq12 e = f12_one();
+  int verdict = pairing_product_check_lanes_host(g1, g2, negate, &e);
+  if (out_gt576) f12_store(out_gt576, e);
+  return verdict;
 }
 extern "C" int hostemu_pairing_product(int n, const uint8_t* g1, const uint8_t* g2, unsigned negate, uint8_t* out_gt576) {
   Fq12 e = f12_one();

@@ -50,6 +50,34 @@ def test_pairing_values_and_bilinearity(eng):
     assert eng.pairing_products(u8(three), u8(q * 3), 3, negate_masks=[0]).tolist() == [0]
 
 
+def test_two_pairing_products_one_warp_per_product(eng):
+    """n_pairs = 2 and a small batch runs the lane programs of csrc/pairing_coop.cuh (one warp per product): GT values against the
+    oracle, identity pairs, malformed points, and bit-equality with the one-thread-per-product kernel (taken by large batches)"""
+    rnd = random.Random(22)
+    g1s, g2s, masks, want_ok, want_gt = [], [], [], [], []
+    for i in range(6):
+        a, b, c, d = (rnd.randrange(1, P.R) for _ in range(4))
+        p1, q1, p2, q2 = P.g1_mul(a, P.G1_GEN), P.g2_mul(b, P.G2_GEN), P.g1_mul(c, P.G1_GEN), P.g2_mul(d, P.G2_GEN)
+        if i == 3: p2 = P.g1_mul(a * b * pow(d, -1, P.R) % P.R, P.G1_GEN)       # e(p1, q1) e(-p2, q2) = 1
+        if i == 4: p1 = None                                                     # identity: that pair contributes 1
+        m = 2 if i in (1, 3) else 0
+        g1s.append(P.g1_to_bytes(p1) + P.g1_to_bytes(p2)); g2s.append(P.g2_to_bytes(q1) + P.g2_to_bytes(q2)); masks.append(m)
+        e1 = P.pairing(p1, q1) if p1 is not None else P.F12_ONE
+        e2 = P.pairing(P.g1_neg(p2) if m else p2, q2)
+        gt = P.gt_cubed(P.f12_mul(e1, e2))
+        want_gt.append(P.f12_to_bytes(gt)); want_ok.append(1 if gt == P.F12_ONE else 0)
+    bad = bytearray(g1s[0]); bad[100] ^= 1
+    g1s.append(bytes(bad)); g2s.append(g2s[0]); masks.append(0); want_ok.append(2); want_gt.append(P.f12_to_bytes(P.F12_ONE))
+    ok, gt = eng.pairing_products(u8(b"".join(g1s)), u8(b"".join(g2s)), 2, negate_masks=masks, want_gt=True)
+    assert ok.tolist() == want_ok and want_ok[3] == 1
+    assert [g.tobytes() for g in gt] == want_gt
+    # the same products tiled into a batch large enough for the one-thread kernel
+    reps = 1300 // len(g1s) + 1
+    ok2, gt2 = eng.pairing_products(u8(b"".join(g1s) * reps), u8(b"".join(g2s) * reps), 2, negate_masks=masks * reps, want_gt=True)
+    assert ok2.tolist() == want_ok * reps
+    assert all(gt2[j].tobytes() == want_gt[j % len(g1s)] for j in range(len(ok2)))
+
+
 def test_pairing_rejects_malformed_points(eng):
     q = P.g2_to_bytes(P.g2_mul(7, P.G2_GEN)); g = P.g1_to_bytes(P.G1_GEN)
     bad1 = bytearray(g); bad1[3] ^= 1

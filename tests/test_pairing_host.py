@@ -83,6 +83,35 @@ def test_pairing_matches_oracle_and_is_bilinear(emu):
         assert emu.hostemu_pairing_product(3, g1b(p) + g1b(P.g1_mul(b, P.G1_GEN)) + g1b(s), g2b(q) * 3, 4, None) == 1
 
 
+def test_lane_programs_match_oracle(emu):
+    """the warp-cooperative form (csrc/pairing_coop.cuh + the tables of tools/gen_pairing_prog.py), all lanes played on the host"""
+    rnd = random.Random(16)
+    emu.hostemu_pairing_product_lanes.restype = C.c_int
+    out, out1 = C.create_string_buffer(576), C.create_string_buffer(576)
+    for trial in range(3):
+        a, b, c, d = (rnd.randrange(1, P.R) for _ in range(4))
+        p1, q1, p2, q2 = P.g1_mul(a, P.G1_GEN), P.g2_mul(b, P.G2_GEN), P.g1_mul(c, P.G1_GEN), P.g2_mul(d, P.G2_GEN)
+        g1, g2 = g1b(p1) + g1b(p2), g2b(q1) + g2b(q2)
+        assert emu.hostemu_pairing_product_lanes(g1, g2, trial, out) == 0
+        e2 = P.pairing(P.g1_neg(p2) if trial & 2 else p2, q2)
+        e1 = P.pairing(P.g1_neg(p1) if trial & 1 else p1, q1)
+        assert P.f12_from_bytes(out.raw) == P.gt_cubed(P.f12_mul(e1, e2))
+        assert emu.hostemu_pairing_product(2, g1, g2, trial, out1) == 0 and out1.raw == out.raw
+        ab = P.g1_mul(a * b, P.G1_GEN)
+        assert emu.hostemu_pairing_product_lanes(g1b(p1) + g1b(ab), g2b(q1) + g2b(P.G2_GEN), 2, out) == 1
+        assert P.f12_from_bytes(out.raw) == P.F12_ONE
+    # an identity in the product and malformed points fall back to / agree with the one-thread form
+    assert emu.hostemu_pairing_product_lanes(bytes(96) + g1b(p2), g2b(q1) + g2b(q2), 0, out) == 0
+    assert P.f12_from_bytes(out.raw) == P.gt_cubed(P.pairing(p2, q2))
+    bad = bytearray(g1b(p1) + g1b(p2)); bad[99] ^= 1
+    assert emu.hostemu_pairing_product_lanes(bytes(bad), g2b(q1) + g2b(q2), 0, None) == 2
+
+
+def test_lane_program_generator_self_check():
+    """the generator's own model run of the emitted tables (twin and oracle equality) passes, and the committed tables are current"""
+    subprocess.run(["python", os.path.join(ROOT, "tools", "gen_pairing_prog.py"), "--check"], check=True, capture_output=True)
+
+
 def test_pairing_identity_and_malformed_inputs(emu):
     q = P.g2_mul(7, P.G2_GEN)
     out = C.create_string_buffer(576)
