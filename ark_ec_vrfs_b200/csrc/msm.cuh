@@ -12,7 +12,7 @@
 //   k_msm_scatter         point indices (+ sign bit) grouped by bucket (counting sort)
 //   k_msm_accumulate      one thread per bucket: complete additions of its points
 //   k_msm_accumulate_big  one block per oversized bucket (top window / skewed scalar columns such as ring selectors)
-//   k_msm_rc / k_msm_wsum segment value sum_j j*B_j: row / column sums of the bucket matrix, then a cluster-wide halving recursion
+//   k_msm_rc / k_msm_wbits segment value sum_j j*B_j: row / column sums of the bucket matrix, then the two short weighted sums bit by bit
 //   k_msm_final2          one warp per column: Horner over the windows (stateless mode only); partial or affine out
 // Stateless mode (vrfs_msm_g1_bls12_381): segment = (column, window).  Prepared mode (vrfs_msm_g1_prepare + _prepared,
 // the analogue of RingContext holding the SRS): segment = column, no Horner chain (255 dependent doublings ~ 2.5 ms).
@@ -36,7 +36,7 @@ struct MsmPlan {
   int tpb;                       // threads cooperating on one bucket in k_msm_accumulate (power of two <= 32)
   uint32_t big;                  // buckets with more entries than this go to k_msm_accumulate_big
   int warp_agg;                  // histogram / scatter: one atomic per group of lanes that hit the same bucket (set by callers that know their columns repeat values)
-  int rc_h;                      // segment reduction: columns H of the R x H bucket matrix summed by k_msm_rc (0: nb <= 256, k_msm_wsum takes the buckets directly)
+  int rc_h;                      // segment reduction: columns H of the R x H bucket matrix summed by k_msm_rc (0: nb <= 256, k_msm_wbits takes the buckets directly)
 };
 VRFS_HD inline MsmPlan msm_plan(uint32_t n, uint32_t ncol, int prepared, int c_override = 0, int tpb_override = 0) {
   MsmPlan p; p.n = n; p.ncol = ncol; p.prepared = prepared;
@@ -97,6 +97,32 @@ HD_NOINLINE void g1_dbl(G1Pt* r, const G1Pt* p) {
 // The formula is not complete, so the three exceptional cases are tested explicitly (they only occur for an empty
 // accumulator, repeated bases and cancelling pairs - a warp almost never diverges on them).
 struct G1Xyzz { Fq381 X, Y, ZZ, ZZZ; };
+// a b - c d with ONE Montgomery reduction: the two 24-limb products are added as a b + c (q - d) < 2 q^2 < q 2^384 / 5 and reduced
+// together (2 x 144 + 156 multiply-accumulates instead of 2 x 300).  VRFS_MSM_FUSED_RED=0 keeps the two separate products.
+#ifndef VRFS_MSM_FUSED_RED
+#define VRFS_MSM_FUSED_RED 1
+#endif
+HD_NOINLINE Fq381 fq381_mul_sub2(const Fq381& a, const Fq381& b, const Fq381& c, const Fq381& d) {
+#if VRFS_MSM_FUSED_RED
+  typedef MontChains<12> C;
+  uint32_t t[24], t2[24], nd[12], pm[12];
+  for (int i = 0; i < 12; i++) pm[i] = BlsFq::mod(i);
+  C::sub(nd, pm, d.v);                                  // q - d in [1, q]: the reduction takes any value below q 2^384
+  C::mul_wide(t, a.v, b.v);
+  C::mul_wide(t2, c.v, nd);
+  const uint32_t cy = C::add(t, t, t2);                 // 24-limb sum: low halves, then high halves with the carry
+  uint32_t one[12];
+  for (int i = 0; i < 12; i++) one[i] = 0;
+  one[0] = cy;
+  C::add(t + 12, t + 12, t2 + 12);
+  C::add(t + 12, t + 12, one);
+  Fq381 r;
+  mont_reduce_wide<BlsFq>(r.v, t);
+  return r;
+#else
+  return a * b - c * d;
+#endif
+}
 HD_INLINE void xyzz_set_identity(G1Xyzz& a) { a.X = Fq381::zero(); a.Y = Fq381::zero(); a.ZZ = Fq381::zero(); a.ZZZ = Fq381::zero(); }
 // (called, not inlined: with the accumulator's address taken it lives in local memory - 928 B of stack in k_msm_accumulate - but
 //  inlining it and/or raising the register cap to 168 was measured at 3.07 / 3.07 / 3.14 / 3.16 ms for the 2^17 x 3 accumulate:
@@ -117,7 +143,7 @@ HD_NOINLINE void xyzz_madd(G1Xyzz* acc, const Fq381* x2, const Fq381* y2) {
   }
   Fq381 PP = sqr(P), PPP = P * PP, Q = acc->X * PP;
   Fq381 X3 = sqr(R) - PPP - dbl(Q);
-  acc->Y = R * (Q - X3) - acc->Y * PPP;
+  acc->Y = fq381_mul_sub2(R, Q - X3, acc->Y, PPP);
   acc->X = X3;
   acc->ZZ = acc->ZZ * PP;
   acc->ZZZ = acc->ZZZ * PPP;
@@ -309,24 +335,111 @@ HD_NOINLINE Fq381 fq381_inv_fast(const Fq381& x) {
 //    results are exchanged with shuffles: ~3 us per addition / doubling instead of ~11 (g1_coop_add, g1_coop_dbl).
 //  * sum_j j*B_j as (1) row and column sums of the R x H bucket matrix (j - 1 = hi*H + lo;
 //    sum j*B_j = H * sum_hi hi*Row_hi + sum_lo (lo+1)*Col_lo: two adds per bucket, depth log2 H, k_msm_rc) and
-//    (2) for the two short weighted sums the halving recursion  W(x) = W(y) + sum_u x_{2u+1},  y_u = 2 (x_{2u} + x_{2u+1})
-//    run by one cluster of 8 thread blocks (128 cooperating groups, one warp per SM sub-partition, k_msm_wsum): no
-//    multiplication by chunk offsets and no Horner chain.
+//    (2) the two short weighted sums by the bits of their weights (k_msm_wbits, round 2: one block per bit gathers the points
+//    whose weight has that bit, doubles the sum bit-many times; round 1 ran a halving recursion on an 8-block cluster, 2.5 x
+//    slower at these sizes): no multiplication by chunk offsets and no Horner chain.
 // (First generation - one thread per chunk of buckets with a double-and-add by the chunk offset, a block tree, a one-thread final -
 //  took 1.11 ms at 2^17 x 3 against 0.41 ms now; it is in the history before session 4.)
 // =================================================================================================
-#define MSM_WSUM_CLUSTER 8
-#define MSM_WSUM_GROUPS (MSM_WSUM_CLUSTER * 16)          // 8 blocks x 4 warps x 4 groups of 8 lanes
-#define MSM_WSUM_MAXM 512                                  // longest weighted sum one cluster takes
-#define MSM_WSUM_HALF (MSM_WSUM_MAXM / 2 + 4)
-#define MSM_WSUM_SCRATCH (2 * MSM_WSUM_HALF + MSM_WSUM_GROUPS)   // points of scratch per weighted sum
-
-// scratch written by other SMs of the cluster: read through L2 (ld.global.cg), never a stale L1 line
-__device__ __forceinline__ void load_pt_cg(G1Pt* dst, const G1Pt* src_) {
-  const uint4* s = reinterpret_cast<const uint4*>(src_);
-  uint4* d = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-  for (unsigned i = 0; i < sizeof(G1Pt) / 16; i++) d[i] = __ldcg(s + i);
+// 1/x in F_q by FOUR lanes: the word-approximation GCD of fq381_inv_bingcd with its four 12-limb updates of a round
+// (a, b <- exact quotients; u, v <- quotients mod q) spread over the lanes of a group - lane r of a group holds ONE of a, b, u, v -
+// and run through one uniform code path (a lane-dependent code path would be serialised by the warp): every lane forms
+// X f + Y g + qq q over 13 limbs (qq = 0 for a and b), shifts by 30 bits, then one masked fix-up (|.| for a, b; + q when negative
+// for u, v), one conditional - q, and one conditional negation mod q of u / v by the sign its a / b partner found.  The 30-step
+// inner loop on the 62-bit approximations is computed by all lanes alike.  ~750 instructions per round and lane instead of
+// ~1000 on one thread (measured: k_msm_final2 0.065 -> 0.055 ms; the 30-step inner loop is most of a round either way).
+// Every lane of the warp must call it; x is the same in the four lanes of a group; all lanes of a group return 1/x (0 -> 0;
+// the fallback for a loop that did not end in (0, 1) - never observed - is the one-thread routine).
+__device__ __noinline__ Fq381 fq381_inv_coop4(const Fq381& x) {
+  const unsigned lane = threadIdx.x & 31u, role = lane & 3u, base = lane & ~3u;
+  const bool is_ab = role < 2u, second = (role & 1u) != 0;     // roles: 0 a, 1 b, 2 u, 3 v
+  uint32_t V[12], pm[12];
+  for (int i = 0; i < 12; i++) {
+    pm[i] = BlsFq::mod(i);
+    V[i] = role == 0 ? x.v[i] : role == 1 ? pm[i] : role == 2 ? (i == 0 ? 1u : 0u) : 0u;
+  }
+  const uint32_t ninv30 = BlsFq::NINV & 0x3fffffffu;
+#pragma unroll 1
+  for (int round = 0; round < 26; round++) {
+    uint32_t O[12];                                            // the partner's value: a <-> b, u <-> v
+    for (int i = 0; i < 12; i++) O[i] = __shfl_xor_sync(0xffffffffu, V[i], 1);
+    const uint32_t* X = second ? O : V;                        // (X, Y) = (a, b) or (u, v)
+    const uint32_t* Y = second ? V : O;
+    uint32_t topw = 0, anz = 0; int topi = 0;
+    for (int i = 0; i < 12; i++) { const uint32_t w = X[i] | Y[i]; if (w) { topw = w; topi = i; } anz |= X[i]; }
+    anz = __shfl_sync(0xffffffffu, anz, base);                 // a of this group
+    if (!__any_sync(0xffffffffu, anz != 0)) break;             // every group of the warp is done (a finished group idles correctly: a stays 0, b and v stay)
+    const int lz = __clz((int)topw);
+    int sp = 32 * topi + 32 - lz - 32; if (sp < 30) sp = 30;
+    const int q = sp >> 5, r = sp & 31;
+    uint32_t alo = 0, ahi = 0, blo = 0, bhi = 0;
+    for (int i = 0; i < 12; i++) { if (i == q) { alo = X[i]; blo = Y[i]; } if (i == q + 1) { ahi = X[i]; bhi = Y[i]; } }
+    const uint32_t atop = r ? (alo >> r) | (ahi << (32 - r)) : alo, btop = r ? (blo >> r) | (bhi << (32 - r)) : blo;
+    unsigned long long xa = (X[0] & 0x3fffffffu) | ((unsigned long long)atop << 30), xb = (Y[0] & 0x3fffffffu) | ((unsigned long long)btop << 30);
+    xa = __shfl_sync(0xffffffffu, xa, base); xb = __shfl_sync(0xffffffffu, xb, base);        // the (a, b) approximations, for all four lanes
+    long long F0 = 1, F1 = 1ll << 32;
+    for (int j = 0; j < 30; j++) {
+      const bool odd = xa & 1u, sw = odd & (xa < xb);
+      const unsigned long long ta = sw ? xb : xa, tb = sw ? xa : xb;
+      const long long tF0 = sw ? F1 : F0, tF1 = sw ? F0 : F1;
+      xa = (ta - (odd ? tb : 0ull)) >> 1; xb = tb;
+      F0 = tF0 - (odd ? tF1 : 0ll);
+      F1 = (long long)((unsigned long long)tF1 << 1);
+    }
+    const long long Fm = second ? F1 : F0;                     // this lane's row of the matrix
+    const int32_t f = (int32_t)(uint32_t)Fm;
+    const int32_t g = (int32_t)((Fm - (long long)f) >> 32);
+    // t = X f + Y g + qq q (13 limbs, two's complement); qq makes the low 30 bits vanish for u, v (they do by themselves for a, b)
+    const uint32_t t0 = X[0] * (uint32_t)f + Y[0] * (uint32_t)g;
+    const uint32_t qq = is_ab ? 0u : ((t0 * ninv30) & 0x3fffffffu);
+    uint32_t t[13];
+    long long cy = 0;
+    for (int i = 0; i < 12; i++) {
+      long long w = (long long)((unsigned long long)X[i] * (uint32_t)f) - (f < 0 ? (long long)((unsigned long long)X[i] << 32) : 0ll);
+      w += (long long)((unsigned long long)Y[i] * (uint32_t)g) - (g < 0 ? (long long)((unsigned long long)Y[i] << 32) : 0ll);
+      w += cy;
+      const unsigned long long pq = (unsigned long long)pm[i] * qq;
+      w += (long long)(pq & 0xffffffffu);
+      t[i] = (uint32_t)w; cy = (w >> 32) + (long long)(pq >> 32);
+    }
+    t[12] = (uint32_t)cy;
+    uint32_t r12[12];
+    for (int i = 0; i < 12; i++) r12[i] = (t[i] >> 30) | (t[i + 1] << 2);      // a, b: exact, |.| < 2^383; u, v: in (-q, 2q)
+    const bool negv = (t[12] >> 31) != 0;
+    {  // a, b: |r|;  u, v: r + q when negative
+      const uint32_t xm = (is_ab && negv) ? 0xffffffffu : 0u;
+      uint32_t add[12];
+      for (int i = 0; i < 12; i++) add[i] = (!is_ab && negv) ? pm[i] : 0u;
+      if (is_ab && negv) add[0] = 1u;
+      for (int i = 0; i < 12; i++) r12[i] ^= xm;
+      MontChains<12>::add(r12, r12, add);
+    }
+    {  // u, v: - q when >= q
+      uint32_t tmp[12];
+      const uint32_t borrow = MontChains<12>::sub(tmp, r12, pm);
+      const bool take = !is_ab && borrow == 0;
+      for (int i = 0; i < 12; i++) r12[i] = take ? tmp[i] : r12[i];
+    }
+    {  // the sign a / b lost goes to u / v:  u <- -u mod q  (lane r + 2 follows lane r)
+      const bool flip = __shfl_xor_sync(0xffffffffu, (int)negv, 2) != 0 && !is_ab;
+      uint32_t tmp[12], nz = 0;
+      MontChains<12>::sub(tmp, pm, r12);
+      for (int i = 0; i < 12; i++) nz |= r12[i];
+      for (int i = 0; i < 12; i++) r12[i] = (flip && nz) ? tmp[i] : r12[i];
+    }
+    for (int i = 0; i < 12; i++) V[i] = r12[i];
+  }
+  // (a, b) must have ended in (0, 1); v = (x R)^-1
+  uint32_t bad = 0;
+  if (role == 0) for (int i = 0; i < 12; i++) bad |= V[i];
+  if (role == 1) { bad = V[0] ^ 1u; for (int i = 1; i < 12; i++) bad |= V[i]; }
+  bad |= __shfl_xor_sync(0xffffffffu, bad, 1);
+  bad = __shfl_sync(0xffffffffu, bad, base);
+  Fq381 res;
+  for (int i = 0; i < 12; i++) res.v[i] = __shfl_sync(0xffffffffu, V[i], base + 3);
+  res = res * Fq381::r3();
+  if (__any_sync(0xffffffffu, bad != 0)) { if (bad) res = fq381_inv(x); }   // x = 0 (-> 0), or the never-observed unfinished loop
+  return res;
 }
 __device__ __forceinline__ Fq381 fq_shfl(const Fq381& a, unsigned src_lane) {
   Fq381 r;
@@ -660,14 +773,43 @@ __global__ void __launch_bounds__(128) k_msm_rc(MsmPlan p, const G1Pt* buckets, 
   if (t == 0) copy_words16(&out[(size_t)seg * (R + H) + o], &sh[0]);
 }
 
-// One cluster per weighted sum  W = sum_i (i + shift) * x_i, i < m <= MSM_WSUM_MAXM  (shift = 1: bucket values; shift = 0: the
-// row index of k_msm_rc), followed by `post` doublings.  With x'_{i+shift} = x_i:  W(x') = W(y) + sum_u x'_{2u+1},
-// y_u = 2 (x'_{2u} + x'_{2u+1}); every group keeps the sum of the odd elements it met, the groups' sums are tree-added at the end.
-__global__ void __cluster_dims__(MSM_WSUM_CLUSTER, 1, 1) __launch_bounds__(128) k_msm_wsum(MsmPlan p, const G1Pt* in, G1Pt* scratch, G1Pt* parts) {
-  namespace cg = cooperative_groups;
-  cg::cluster_group cluster = cg::this_cluster();
-  const uint32_t seg = blockIdx.z, part = blockIdx.y, nparts = gridDim.y;
-  const unsigned G = cluster.block_rank() * 16u + (threadIdx.x >> 3), g = threadIdx.x & 7u;
+// The weighted sums  W = sum_i (i + shift) * x_i, i < m <= 512  (shift = 1: bucket values / column sums; shift = 0: the row index
+// of k_msm_rc, followed by `post` = log2 H doublings) by the BITS of the weights:
+//   W = sum_b 2^b S_b,   S_b = sum of the x_i whose weight has bit b set.
+// One block per (bit, part, segment): its 32 cooperating groups pick up the <= m/2 selected points (one coop addition per 32
+// points), a 5-level tree in shared memory gives S_b, and the first warp doubles it b (+ post) times; k_msm_final2 adds the
+// msm_wbits(p) results of every part.  No cluster barriers and no chain longer than log2(nb) doublings: 0.04 ms where the
+// halving recursion W(x) = W(y) + sum_u x_{2u+1}, y_u = 2 (x_{2u} + x_{2u+1}) run by an 8-block cluster (round 1; in the history) took
+// 0.10 ms (m = 16 / 32 at N = 2^11), and 0.08 instead of 0.17 ms at N = 2^17.
+#define MSM_WBITS 10                                       // weights <= 512 < 2^10
+VRFS_HD inline int msm_wbits(const MsmPlan& p) {           // bits of the largest weight of a plan's weighted sums
+  const int wmax = p.rc_h ? p.rc_h : p.nb;                 // columns / buckets carry weights 1 .. H (or nb); rows 0 .. R - 1 < H
+  int b = 0; while ((1 << b) <= wmax) b++;
+  return b;
+}
+// stateless mode: the parts of every (column, window) segment are added by their own warp before the Horner chain of k_msm_final2
+__global__ void __launch_bounds__(32) k_msm_sum_parts(int nparts, const G1Pt* parts, G1Pt* out) {
+  const G1Pt* W = parts + (size_t)blockIdx.x * nparts;
+  const unsigned grp = threadIdx.x >> 3;
+  G1Pt sum; sw_set_identity(sum);
+  for (int j0 = 0; j0 < nparts; j0 += 4) {
+    const int j = j0 + (int)grp;
+    G1Pt q; sw_set_identity(q);
+    if (j < nparts) copy_words16(&q, &W[j]);
+    if (j0 == 0) sum = q; else g1_coop_add(&sum, &sum, &q);
+  }
+  for (int s = 2; s > 0; s >>= 1) {
+    G1Pt other;
+    other.X = fq_shfl(sum.X, (threadIdx.x + 8u * s) & 31u); other.Y = fq_shfl(sum.Y, (threadIdx.x + 8u * s) & 31u); other.Z = fq_shfl(sum.Z, (threadIdx.x + 8u * s) & 31u);
+    g1_coop_add(&sum, &sum, &other);
+  }
+  if (threadIdx.x == 0) copy_words16(&out[blockIdx.x], &sum);
+}
+__global__ void __launch_bounds__(256) k_msm_wbits(MsmPlan p, const G1Pt* in, G1Pt* parts) {
+  __shared__ uint4 sh_raw[32 * sizeof(G1Pt) / 16];
+  G1Pt* sh = reinterpret_cast<G1Pt*>(sh_raw);
+  const uint32_t b = blockIdx.x, part = blockIdx.y, nparts = gridDim.y, seg = blockIdx.z;
+  const unsigned G = threadIdx.x >> 3, g = threadIdx.x & 7u;
   const G1Pt* x; int m, shift, post = 0;
   if (p.rc_h) {
     const int R = p.nb / p.rc_h;
@@ -675,59 +817,45 @@ __global__ void __cluster_dims__(MSM_WSUM_CLUSTER, 1, 1) __launch_bounds__(128) 
     m = part ? p.rc_h : R; shift = part ? 1 : 0;
     if (!part) while ((1 << post) < p.rc_h) post++;
   } else { x = in + (size_t)seg * p.nb; m = p.nb; shift = 1; }
-  const size_t prob = (size_t)seg * nparts + part;
-  G1Pt* bufA = scratch + prob * MSM_WSUM_SCRATCH;
-  G1Pt* bufB = bufA + MSM_WSUM_HALF;
-  G1Pt* Hs = bufB + MSM_WSUM_HALF;
-  G1Pt T; sw_set_identity(T);
-  int len = m + shift, level = 0;
-  const G1Pt* src = x;
-  G1Pt* dst = bufA;
-  const int ntask0 = (len + 1) / 2;
-  while (len > 1) {
-    const int ntask = (len + 1) / 2;
-    for (int rd = 0; rd * MSM_WSUM_GROUPS < ntask; rd++) {
-      if ((int)((rd * MSM_WSUM_GROUPS + G) & ~3u) >= ntask) continue;      // warp-uniform: no live group in this warp
-      const int u = rd * MSM_WSUM_GROUPS + (int)G;
-      const bool valid = u < ntask;
-      G1Pt e0, e1, s;
-      sw_set_identity(e0); sw_set_identity(e1);
-      const int off = level == 0 ? shift : 0;
-      const int i0 = 2 * u - off, i1 = 2 * u + 1 - off;
-      if (valid && i0 >= 0 && i0 + off < len) load_pt_cg(&e0, src + i0);
-      if (valid && i1 + off < len) load_pt_cg(&e1, src + i1);
-      g1_coop_add(&s, &e0, &e1);
-      if (ntask > 1) g1_coop_dbl(&s, &s);
-      g1_coop_add(&T, &T, &e1);
-      __syncwarp();
-      if (valid && g == 0) copy_words16(dst + u, &s);
-    }
-    __threadfence();
-    cluster.sync();
-    src = dst; dst = (dst == bufA) ? bufB : bufA;
-    len = ntask; level++;
+  G1Pt* out = parts + ((size_t)seg * nparts + part) * gridDim.x + b;           // gridDim.x = msm_wbits(p) bits per part
+  // the k-th weight with bit b set is w_k = (k >> b) << (b + 1) | 1 << b | (k & (2^b - 1)); weights run over [shift, m + shift)
+  const int top = m + shift;                               // exclusive
+  int K = 0;
+  {
+    const int full = top >> (b + 1), rem = top & ((1 << (b + 1)) - 1);
+    K = full * (1 << b) + (rem > (1 << b) ? rem - (1 << b) : 0);
   }
-  if (g == 0) copy_words16(&Hs[G], &T);
-  __threadfence();
-  cluster.sync();
-  int live = 1; while (live < ntask0 && live < MSM_WSUM_GROUPS) live <<= 1;   // groups that can hold a non-trivial sum
+  G1Pt acc; sw_set_identity(acc);
+  if (K == 0) { if (threadIdx.x == 0) copy_words16(out, &acc); return; }
+  for (int r = 0; r * 32 < K; r++) {
+    const int k = r * 32 + (int)G;
+    G1Pt e; sw_set_identity(e);
+    if (k < K) {
+      const int w = ((k >> b) << (b + 1)) | (1 << b) | (k & ((1 << b) - 1));
+      copy_words16(&e, x + (w - shift));
+    }
+    if (r == 0) acc = e;
+    else if ((r * 32 + (int)(G & ~3u)) < K) g1_coop_add(&acc, &acc, &e);      // warp-uniform: some group of this warp has a point
+  }
+  if (g == 0) copy_words16(&sh[G], &acc);
+  __syncthreads();
+  int live = 1; while (live < K && live < 32) live <<= 1;
   for (int s = live >> 1; s > 0; s >>= 1) {
     if ((int)(G & ~3u) < s) {
-      G1Pt a, b, z;
-      load_pt_cg(&a, &Hs[(int)G < s ? G : (unsigned)s]);
-      load_pt_cg(&b, &Hs[(int)G < s ? G + s : (unsigned)s]);
-      g1_coop_add(&z, &a, &b);
+      G1Pt a2, b2, z;
+      copy_words16(&a2, &sh[(int)G < s ? G : (unsigned)s]);
+      copy_words16(&b2, &sh[(int)G < s ? G + s : (unsigned)s]);
+      g1_coop_add(&z, &a2, &b2);
       __syncwarp();
-      if ((int)G < s && g == 0) copy_words16(&Hs[G], &z);
+      if ((int)G < s && g == 0) copy_words16(&sh[G], &z);
     }
-    __threadfence();
-    cluster.sync();
+    __syncthreads();
   }
-  if (G < 4) {                                                 // the first warp of the cluster; group 0 writes
-    G1Pt z; load_pt_cg(&z, &Hs[0]);
-    for (int k = 0; k < post; k++) g1_coop_dbl(&z, &z);
+  if (G < 4) {                                             // the first warp; every group computes the same
+    G1Pt z; copy_words16(&z, &sh[0]);
+    for (int k = 0; k < (int)b + post; k++) g1_coop_dbl(&z, &z);
     __syncwarp();
-    if (G == 0 && g == 0) copy_words16(&parts[prob], &z);
+    if (G == 0 && g == 0) copy_words16(out, &z);
   }
 }
 
@@ -767,9 +895,25 @@ __global__ void __launch_bounds__(32) k_msm_final2(MsmPlan p, int nparts, const 
   const uint32_t col = blockIdx.x;
   const G1Pt* W = parts + (size_t)col * p.seg_windows * nparts;
   G1Pt acc; sw_set_identity(acc);
+  const unsigned grp = threadIdx.x >> 3;                  // the warp's four groups of eight lanes add the parts of a window side by side
   for (int w = p.seg_windows - 1; w >= 0; w--) {
     if (w != p.seg_windows - 1) for (int k = 0; k < p.c; k++) g1_coop_dbl(&acc, &acc);
-    for (int j = 0; j < nparts; j++) { G1Pt q; copy_words16(&q, &W[(size_t)w * nparts + j]); g1_coop_add(&acc, &acc, &q); }
+    if (nparts == 1) { G1Pt q; copy_words16(&q, &W[w]); g1_coop_add(&acc, &acc, &q); continue; }      // stateless: summed by k_msm_sum_parts
+    G1Pt part_sum; sw_set_identity(part_sum);
+    for (int j0 = 0; j0 < nparts; j0 += 4) {
+      const int j = j0 + (int)grp;
+      G1Pt q; sw_set_identity(q);
+      if (j < nparts) copy_words16(&q, &W[(size_t)w * nparts + j]);
+      if (j0 == 0) part_sum = q; else g1_coop_add(&part_sum, &part_sum, &q);
+    }
+    // fold the four groups' sums: lanes 8..31 hand theirs down (two shuffle-exchange levels)
+    for (int s = 2; s > 0; s >>= 1) {
+      G1Pt other;
+      other.X = fq_shfl(part_sum.X, (threadIdx.x + 8u * s) & 31u); other.Y = fq_shfl(part_sum.Y, (threadIdx.x + 8u * s) & 31u); other.Z = fq_shfl(part_sum.Z, (threadIdx.x + 8u * s) & 31u);
+      g1_coop_add(&part_sum, &part_sum, &other);
+    }
+    // every group now holds the same total (the additions commute; all four computed a rotation of the same sum)
+    g1_coop_add(&acc, &acc, &part_sum);
   }
   if (out_mode == 2) {
     const unsigned lane = threadIdx.x;
@@ -811,18 +955,18 @@ __global__ void __launch_bounds__(32) k_msm_final2(MsmPlan p, int nparts, const 
     }
     acc = sum;
   }
-  if (threadIdx.x != 0) return;
   uint32_t raw[12];
   if (out_mode == 1) {
+    if (threadIdx.x != 0) return;
     uint8_t* o = out + (size_t)144 * col;
     from_mont<BlsFq>(raw, acc.X); store_le<12>(o, raw);
     from_mont<BlsFq>(raw, acc.Y); store_le<12>(o + 48, raw);
     from_mont<BlsFq>(raw, acc.Z); store_le<12>(o + 96, raw);
   } else {
     uint8_t* o = out + (size_t)96 * col;
-    Fq381 zi = fq381_inv_fast(acc.Z);                // identity: Z = 0 -> zi = 0 -> zeros
-    from_mont<BlsFq>(raw, acc.X * zi); store_le<12>(o, raw);
-    from_mont<BlsFq>(raw, acc.Y * zi); store_le<12>(o + 48, raw);
+    const Fq381 zi = fq381_inv_coop4(acc.Z);         // the whole warp (acc is replicated in every lane); identity: Z = 0 -> zi = 0 -> zeros
+    if (threadIdx.x == 0) { from_mont<BlsFq>(raw, acc.X * zi); store_le<12>(o, raw); }
+    if (threadIdx.x == 1) { from_mont<BlsFq>(raw, acc.Y * zi); store_le<12>(o + 48, raw); }
   }
 }
 // fold partial sums of several ranks: partials[part][col] projective LE canonical -> affine out

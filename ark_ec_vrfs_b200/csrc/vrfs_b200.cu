@@ -1469,9 +1469,10 @@ static vrfs_status msm_dev(vrfs_ctx* ctx, MsmPlan p, const void* d_bases, const 
   // parts[segs * nparts] | row and column sums [segs * (R + H)] | scratch of the weighted sums
   const unsigned nparts = p.rc_h ? 2u : 1u;
   const size_t rc_len = p.rc_h ? (size_t)(p.nb / p.rc_h + p.rc_h) : 0;
-  ST(ensure(ctx, BUF_SLAB, (segs * nparts + segs * rc_len + segs * nparts * MSM_WSUM_SCRATCH) * sizeof(G1Pt), &wsum));
-  G1Pt* rc_out = (G1Pt*)wsum + segs * nparts;
-  G1Pt* wscratch = rc_out + segs * rc_len;
+  const unsigned wb = (unsigned)msm_wbits(p);                       // results per weighted sum (one per bit of the weights)
+  ST(ensure(ctx, BUF_SLAB, (segs * nparts * wb + segs * rc_len + segs) * sizeof(G1Pt), &wsum));
+  G1Pt* rc_out = (G1Pt*)wsum + segs * nparts * wb;
+  G1Pt* seg_sums = rc_out + segs * rc_len;
   CU(cudaMemsetAsync(counts, 0, (nbuckets * 3 + 16) * sizeof(uint32_t), ctx->stream));
   const unsigned tsc = (unsigned)((n * ncol + 127) / 128);
   k_msm_histogram<<<tsc, 128, 0, ctx->stream>>>(p, d_scalars, (uint32_t*)counts);
@@ -1498,11 +1499,18 @@ static vrfs_status msm_dev(vrfs_ctx* ctx, MsmPlan p, const void* d_bases, const 
     k_msm_rc<<<dim3((unsigned)rc_len, (unsigned)segs), 128, 0, ctx->stream>>>(p, (const G1Pt*)buckets, rc_out);
     LAUNCHED_AS(ctx, "msm_rc");
   }
-  k_msm_wsum<<<dim3(MSM_WSUM_CLUSTER, nparts, (unsigned)segs), 128, 0, ctx->stream>>>(p, p.rc_h ? (const G1Pt*)rc_out : (const G1Pt*)buckets, wscratch, (G1Pt*)wsum);
+  k_msm_wbits<<<dim3(wb, nparts, (unsigned)segs), 256, 0, ctx->stream>>>(p, p.rc_h ? (const G1Pt*)rc_out : (const G1Pt*)buckets, (G1Pt*)wsum);
   LAUNCHED_AS(ctx, "msm_wsum");
+  int final_parts = (int)(nparts * wb);
+  const G1Pt* final_in = (const G1Pt*)wsum;
+  if (!p.prepared) {                                                // 20 windows per column: add their parts side by side, not inside the Horner chain
+    k_msm_sum_parts<<<(unsigned)segs, 32, 0, ctx->stream>>>(final_parts, (const G1Pt*)wsum, seg_sums);
+    LAUNCHED_AS(ctx, "msm_sum_parts");
+    final_parts = 1; final_in = seg_sums;
+  }
   PeerArgs pa = {};
   if (out_mode == 2) { if (!peer) return fail(ctx, VRFS_BAD_ARG, "internal: peer exchange without a peer group"); pa = *peer; }
-  k_msm_final2<<<(unsigned)ncol, 32, 0, ctx->stream>>>(p, (int)nparts, (const G1Pt*)wsum, d_out, out_mode, pa);
+  k_msm_final2<<<(unsigned)ncol, 32, 0, ctx->stream>>>(p, final_parts, final_in, d_out, out_mode, pa);
   LAUNCHED_AS(ctx, "msm_final");
   return VRFS_OK;
 }
@@ -1776,13 +1784,23 @@ extern "C" vrfs_status vrfs_g1_decompress_batch(vrfs_ctx* ctx, size_t n, const u
 // word-approximation GCD finished on its own (no fallback to the binary Euclid) - the GPU tests require that for every a != 0
 __global__ void k_fq381_inv_batch(uint32_t n, const uint8_t* in, uint8_t* out, uint8_t* ok) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
   uint32_t raw[12];
-  load_le<12>(raw, in + (size_t)48 * i);
+  for (int k = 0; k < 12; k++) raw[k] = k == 0;
+  if (i < n) load_le<12>(raw, in + (size_t)48 * i);
   const Fq381 a = to_mont<BlsFq>(raw);
   Fq381 t;
-  ok[i] = fq381_inv_bingcd(t, a) ? 1 : 0;
-  from_mont<BlsFq>(raw, fq381_inv_fast(a));
+  const bool finished = fq381_inv_bingcd(t, a);
+  const Fq381 one_thread = fq381_inv_fast(a);
+  // the four-lane form (fq381_inv_coop4) must give the same element: the lanes of a group take their four values in turn
+  Fq381 four_lane = one_thread;
+  for (unsigned turn = 0; turn < 4; turn++) {
+    const Fq381 x = fq_shfl(a, (threadIdx.x & 28u) + turn);
+    const Fq381 r = fq381_inv_coop4(x);
+    if ((threadIdx.x & 3u) == turn) four_lane = r;
+  }
+  if (i >= n) return;
+  ok[i] = (finished && four_lane == one_thread) ? 1 : 0;
+  from_mont<BlsFq>(raw, four_lane);
   store_le<12>(out + (size_t)48 * i, raw);
 }
 extern "C" vrfs_status vrfs_fq381_inv_batch(vrfs_ctx* ctx, size_t n, const uint8_t* in, uint8_t* out, uint8_t* out_ok) {

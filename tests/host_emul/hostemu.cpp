@@ -174,6 +174,13 @@ extern "C" int hostemu_fq381_inv_fast(const uint32_t* a_mont, uint32_t* out_mont
   return finished;
 }
 
+// a b - c d with one reduction (csrc/msm.cuh fq381_mul_sub2, the Y coordinate of the bucket addition); Montgomery limbs in and out
+extern "C" void hostemu_fq381_mul_sub2(const uint32_t* a, const uint32_t* b, const uint32_t* c, const uint32_t* d, uint32_t* out_mont) {
+  Fq381 A, B, Cc, D; memcpy(A.v, a, 48); memcpy(B.v, b, 48); memcpy(Cc.v, c, 48); memcpy(D.v, d, 48);
+  Fq381 r = fq381_mul_sub2(A, B, Cc, D);
+  memcpy(out_mont, r.v, 48);
+}
+
 // generator of the radix-2 domain of size 2^logn over BLS12-381 Fr (csrc/ring.cuh), canonical limbs out
 #include "../../ark_ec_vrfs_b200/csrc/ring.cuh"
 extern "C" void hostemu_ntt_domain_gen(int logn, int inverse, uint32_t* out_canonical) {

@@ -154,6 +154,19 @@ def test_fq381_word_approximation_gcd_inverse(emu):
         assert finished == (1 if a else 0), a
 
 
+def test_fq381_fused_product_difference(emu):
+    """csrc/msm.cuh fq381_mul_sub2: a b - c d through ONE Montgomery reduction of a b + c (q - d), extremes included"""
+    p = R.BLS_FQ; Rm = 1 << 384
+    rnd = random.Random(23)
+    lim = lambda x: (C.c_uint32 * 12)(*[((x * Rm % p) >> (32 * i)) & 0xFFFFFFFF for i in range(12)])
+    ext = [0, 1, p - 1, p - 2, (p - 1) // 2]
+    for t in range(600):
+        a, b, c, d = ([ext[(t >> (2 * k)) % 5] for k in range(4)] if t < 200 else [rnd.randrange(p) for _ in range(4)])
+        out = (C.c_uint32 * 12)()
+        emu.hostemu_fq381_mul_sub2(lim(a), lim(b), lim(c), lim(d), out)
+        assert sum(int(out[i]) << (32 * i) for i in range(12)) == (a * b - c * d) * Rm % p, (a, b, c, d)
+
+
 def test_fq381_binary_euclid_inverse(emu):
     """csrc/msm.cuh fq381_inv (used on the MSM's final projective -> affine step) against big-integer arithmetic"""
     p = R.BLS_FQ; Rm = 1 << 384
