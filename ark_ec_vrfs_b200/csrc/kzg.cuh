@@ -153,7 +153,7 @@ extern "C" vrfs_status vrfs_kzg_batch_verify(vrfs_ctx* ctx, size_t k, const uint
   LAUNCHED_AS(ctx, "kzg_sum");
   k_msm_prep_bases<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((uint32_t)n, (const uint8_t*)d_bases, (G1Aff*)d_aff);
   LAUNCHED_AS(ctx, "msm_prep_bases");
-  ST(msm_dev(ctx, msm_plan((uint32_t)n, 2, 0), d_aff, (const uint8_t*)d_scal, d_lr, 0));
+  ST(msm_stateless_dev(ctx, n, 2, d_aff, (const uint8_t*)d_scal, d_lr, 0));
   ST(kzg_pairing_launch(ctx, d_lr, (const uint8_t*)d_g2s, (const uint32_t*)d_misc, (uint32_t*)d_misc + 8, d_ok));
   ST(copy_out(ctx, out_ok, d_ok, 1));
   return finish_call(ctx);

@@ -18,6 +18,7 @@
 // the analogue of RingContext holding the SRS): segment = column, no Horner chain (255 dependent doublings ~ 2.5 ms).
 #pragma once
 #include "lincomb.cuh"
+#include "gen/ntt_consts.cuh"
 #ifdef __CUDACC__
 #include <cooperative_groups.h>
 #endif
@@ -38,7 +39,7 @@ struct MsmPlan {
   int warp_agg;                  // histogram / scatter: one atomic per group of lanes that hit the same bucket (set by callers that know their columns repeat values)
   int rc_h;                      // segment reduction: columns H of the R x H bucket matrix summed by k_msm_rc (0: nb <= 256, k_msm_wbits takes the buckets directly)
 };
-VRFS_HD inline MsmPlan msm_plan(uint32_t n, uint32_t ncol, int prepared, int c_override = 0, int tpb_override = 0) {
+VRFS_HD inline MsmPlan msm_plan(uint32_t n, uint32_t ncol, int prepared, int c_override = 0, int tpb_override = 0, int scalar_bits = 255) {
   MsmPlan p; p.n = n; p.ncol = ncol; p.prepared = prepared;
   int lg = 0; while ((1u << (lg + 1)) <= n) lg++;
   // prepared mode: all windows of a column share one bucket set, so a short top window (255 mod c bits) piles n entries onto
@@ -46,9 +47,11 @@ VRFS_HD inline MsmPlan msm_plan(uint32_t n, uint32_t ncol, int prepared, int c_o
   // buckets cost 0.2-0.6 ms at 2^11..2^14)
   // tools/msm_sweep.py with scalars uniform below r (profiles/r1r_msm_sweep.json): c = 16 spends no window on the carry of bit 254
   if (prepared) p.c = lg <= 9 ? 8 : lg <= 12 ? 10 : lg <= 16 ? 13 : 16;
-  else p.c = lg <= 9 ? 7 : lg <= 11 ? 9 : lg <= 13 ? 11 : lg <= 15 ? 12 : 13;
-  if (c_override >= 8 && c_override <= 18) p.c = c_override;      // caller's window hint (vrfs_msm_g1_prepare_ex; tools/msm_sweep.py)
-  p.windows = (255 + p.c) / p.c;          // 255 scalar bits + the top carry of the signed recoding
+  // stateless mode (n counts the 2 x bases of the GLV halves, 128-bit scalars): tools/msm_sweep_stateless.py.  The top window must
+  // not be a few bits wide (c = 9, 12 leave 2 / 8 bits: its buckets collect 8 x the average load); c = 8 spends it on the carry alone
+  else p.c = lg <= 13 ? 8 : lg <= 14 ? 10 : lg <= 16 ? 11 : 13;
+  if (c_override >= 7 && c_override <= 18) p.c = c_override;      // caller's window hint (vrfs_msm_g1_prepare_ex; tools/msm_sweep.py)
+  p.windows = (scalar_bits + p.c) / p.c;  // scalar bits (255; 128 for the GLV halves of the stateless mode) + the top carry of the signed recoding
   p.nb = 1 << (p.c - 1);
   p.seg_windows = prepared ? 1 : p.windows;
   // small domains are latency-bound on chains of dependent additions: spread every stage over more threads
@@ -181,6 +184,42 @@ HD_INLINE void msm_load_scalar(uint32_t* k, const uint8_t* p) {
   raw[0] = a.x; raw[1] = a.y; raw[2] = a.z; raw[3] = a.w; raw[4] = b.x; raw[5] = b.y; raw[6] = b.z; raw[7] = b.w;
   if (is_canonical<BlsFr>(raw)) { for (int i = 0; i < 8; i++) k[i] = raw[i]; }      // the common case: nothing to reduce
   else from_mont<BlsFr>(k, to_mont<BlsFr>(raw));  // reduce mod r like the reference's scalar decode
+}
+
+// ---- GLV for the stateless mode: phi(x, y) = (beta x, y) is multiplication by -z^2 on G1 (z the curve parameter; the constant of
+// g1_in_subgroup), and r = z^4 - z^2 + 1, so every scalar below r is  k = k1 + q z^2  with k1 < z^2 < 2^128 and q < 2^128:
+//     k P = k1 P + q (-phi(P)) = k1 (x, y) + q (beta x, -y).
+// The stateless MSM (the literal `VariableBaseMSM::msm` signature) runs over the 2n bases [P_i | -phi(P_i)] with these 128-bit
+// halves: as many bucket additions as before, but half the windows - half the bucket sets to reduce and a Horner chain of 128
+// instead of 255 dependent doublings (0.47 of the call's ~1.5 ms at N = 2^11).  The division by z^2 is a multiplication by
+// floor(2^256 / z^2) and at most one correction (checked on 10^5 random scalars when the constants were derived; the host tests
+// check k = k1 + q z^2 and the bounds on this very code).
+HD_INLINE void g1_glv_split(uint32_t* k1 /*4*/, uint32_t* q /*4*/, const uint32_t* k /*8, canonical < r*/) {
+  constexpr uint32_t Z2[4] = {0x00000000u, 0x00000001u, 0x0001a402u, 0xac45a401u};                    // z^2
+  constexpr uint32_t M[5] = {0xf6cfee2eu, 0x63f6e522u, 0xe01faaddu, 0x7c6becf1u, 0x00000001u};        // floor(2^256 / z^2)
+  uint32_t prod[13];
+  for (int i = 0; i < 13; i++) prod[i] = 0;
+  for (int i = 0; i < 8; i++) {
+    uint64_t c = 0;
+    for (int j = 0; j < 5; j++) { const uint64_t t = (uint64_t)k[i] * M[j] + prod[i + j] + c; prod[i + j] = (uint32_t)t; c = t >> 32; }
+    prod[i + 5] = (uint32_t)c;
+  }
+  uint32_t qe[4] = {prod[8], prod[9], prod[10], prod[11]};      // floor(k M / 2^256) in {q - 1, q}; q < 2^128
+  uint32_t qz[8];
+  for (int i = 0; i < 8; i++) qz[i] = 0;
+  for (int i = 0; i < 4; i++) {
+    uint64_t c = 0;
+    for (int j = 0; j < 4; j++) { const uint64_t t = (uint64_t)qe[i] * Z2[j] + qz[i + j] + c; qz[i + j] = (uint32_t)t; c = t >> 32; }
+    qz[i + 4] = (uint32_t)c;
+  }
+  uint32_t rem[5];                                              // k - qe z^2 < 2 z^2 < 2^129
+  { uint64_t b = 0; for (int i = 0; i < 5; i++) { const uint64_t t = (uint64_t)k[i] - qz[i] - b; rem[i] = (uint32_t)t; b = (t >> 32) & 1u; } }
+  uint32_t sub[5];
+  uint64_t b = 0;
+  for (int i = 0; i < 5; i++) { const uint64_t t = (uint64_t)rem[i] - (i < 4 ? Z2[i] : 0u) - b; sub[i] = (uint32_t)t; b = (t >> 32) & 1u; }
+  const bool fix = b == 0;                                      // rem >= z^2: one more z^2 fits
+  uint64_t c = fix ? 1u : 0u;
+  for (int i = 0; i < 4; i++) { k1[i] = fix ? sub[i] : rem[i]; const uint64_t t = (uint64_t)qe[i] + c; q[i] = (uint32_t)t; c = t >> 32; }
 }
 
 // 1/a in BLS12-381 Fq by the binary extended Euclid (at most 2*381 shift/subtract steps on 12-limb integers) instead of a
@@ -527,6 +566,27 @@ __global__ void __launch_bounds__(128) k_msm_prep_bases(uint32_t n, const uint8_
   G1Aff o;
   o.x = to_mont<BlsFq>(rx); o.y = to_mont<BlsFq>(ry);
   out[i] = o;
+}
+// stateless mode: bases2 = [P_i | -phi(P_i)], scalars2[col] = [k1_i | q_i] as 32-byte values (see g1_glv_split)
+__global__ void __launch_bounds__(128) k_msm_glv_split(uint32_t n, uint32_t ncol, const G1Aff* aff, const uint8_t* scalars, G1Aff* bases2, uint8_t* scalars2) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * ncol) return;
+  const uint32_t col = t / n, i = t % n;
+  uint32_t k[8], k1[4], q[4];
+  msm_load_scalar(k, scalars + (size_t)32 * t);
+  g1_glv_split(k1, q, k);
+  uint4* o1 = reinterpret_cast<uint4*>(scalars2 + (size_t)32 * ((size_t)col * 2 * n + i));
+  uint4* o2 = reinterpret_cast<uint4*>(scalars2 + (size_t)32 * ((size_t)col * 2 * n + n + i));
+  o1[0] = make_uint4(k1[0], k1[1], k1[2], k1[3]); o1[1] = make_uint4(0, 0, 0, 0);
+  o2[0] = make_uint4(q[0], q[1], q[2], q[3]); o2[1] = make_uint4(0, 0, 0, 0);
+  if (col == 0) {
+    G1Aff a; copy_words16(&a, &aff[i]);
+    copy_words16(&bases2[i], &a);
+    Fq381 beta;
+    for (int j = 0; j < 12; j++) beta.v[j] = G1WireConsts::beta(j);
+    a.x = a.x * beta; a.y = neg(a.y);                          // the identity (0, 0) stays (0, 0)
+    copy_words16(&bases2[n + i], &a);
+  }
 }
 // prepared bases (the RingContext analogue: the SRS is fixed): Q[w*n + i] = 2^(c*w) * P_i, AFFINE (96 B; identity = zeros).
 // One thread per base: the doubling chain leaves projective points, whose Z's are inverted together (Montgomery's trick, one

@@ -31,6 +31,9 @@ using namespace vrfs;
 #ifndef LINCOMB_MINBLOCKS
 #define LINCOMB_MINBLOCKS 2
 #endif
+#ifndef VRFS_SPLIT_ITEMS_PER_SM
+#define VRFS_SPLIT_ITEMS_PER_SM 256      // a verify batch of up to this many items per SM runs its two linear combinations on two streams
+#endif
 
 // one fixed-base table (K8): thread (w, d) computes (d * 256^w) * B in affine cached form
 template <class C>
@@ -477,7 +480,7 @@ static vrfs_status ietf_verify_dev(vrfs_ctx* ctx, size_t n, const uint8_t* pk, c
   // Small batches leave most of the GPU idle and are bound by the latency of one thread's ~4 100 products: run U and V side by
   // side on two streams (both grids fit at once).  Large batches fill the GPU either way and stay on one stream.
   // (overlapping the two launches of a LARGE batch the same way was measured at +0.3 %: not worth losing per-kernel timing)
-  const bool split = n <= (size_t)ctx->sms * LINCOMB_THREADS;
+  const bool split = n <= (size_t)ctx->sms * VRFS_SPLIT_ITEMS_PER_SM;
   const uint32_t cbits = S::CLEN < 32 ? 8u * S::CLEN : 0u;     // a CHALLENGE_LEN-byte challenge: half of its windows are empty
   // U = s*G - c*Y
   A.var[0] = {pk, 64, c, 32, 1, cbits};
@@ -1514,7 +1517,16 @@ static vrfs_status msm_dev(vrfs_ctx* ctx, MsmPlan p, const void* d_bases, const 
   LAUNCHED_AS(ctx, "msm_final");
   return VRFS_OK;
 }
-static vrfs_status msm_host(vrfs_ctx* ctx, size_t n, const uint8_t* bases, const uint8_t* scalars, int ncol, uint8_t* out, int out_mode) {
+// the stateless MSM over Montgomery affine bases on the device: GLV halves over [P | -phi(P)] (msm.cuh), then the bucket pipeline
+static vrfs_status msm_stateless_dev(vrfs_ctx* ctx, size_t n, int ncol, const void* d_aff, const uint8_t* d_scalars, uint8_t* d_out, int out_mode, int window_bits = 0) {
+  void *bases2 = nullptr, *scalars2 = nullptr;
+  ST(ensure(ctx, BUF_X4, 2 * n * sizeof(G1Aff), &bases2));
+  ST(ensure(ctx, BUF_X5, 2 * n * 32 * (size_t)ncol, &scalars2));
+  k_msm_glv_split<<<(unsigned)((n * ncol + 127) / 128), 128, 0, ctx->stream>>>((uint32_t)n, (uint32_t)ncol, (const G1Aff*)d_aff, d_scalars, (G1Aff*)bases2, (uint8_t*)scalars2);
+  LAUNCHED_AS(ctx, "msm_glv_split");
+  return msm_dev(ctx, msm_plan((uint32_t)(2 * n), (uint32_t)ncol, 0, window_bits, 0, 128), bases2, (const uint8_t*)scalars2, d_out, out_mode);
+}
+static vrfs_status msm_host(vrfs_ctx* ctx, size_t n, const uint8_t* bases, const uint8_t* scalars, int ncol, uint8_t* out, int out_mode, int window_bits = 0) {
   if (!ctx) return VRFS_BAD_ARG;
   CallGuard guard_(ctx);
   if (ncol < 1 || ncol > 32) return fail(ctx, VRFS_BAD_ARG, "n_columns must be in 1..32");
@@ -1534,12 +1546,16 @@ static vrfs_status msm_host(vrfs_ctx* ctx, size_t n, const uint8_t* bases, const
   ST(ensure(ctx, BUF_W0, n * sizeof(G1Aff), &bases_m));
   k_msm_prep_bases<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((uint32_t)n, d_b, (G1Aff*)bases_m);
   LAUNCHED_AS(ctx, "msm_prep_bases");
-  ST(msm_dev(ctx, msm_plan((uint32_t)n, (uint32_t)ncol, 0), bases_m, d_s, d_o, out_mode));
+  ST(msm_stateless_dev(ctx, n, ncol, bases_m, d_s, d_o, out_mode, window_bits));
   ST(copy_out(ctx, out, d_o, ob * ncol));
   return finish_call(ctx);
 }
 extern "C" vrfs_status vrfs_msm_g1_bls12_381(vrfs_ctx* ctx, size_t n, const uint8_t* bases, const uint8_t* scalars, int n_columns, uint8_t* out) {
   return msm_host(ctx, n, bases, scalars, n_columns, out, 0);
+}
+extern "C" vrfs_status vrfs_msm_g1_bls12_381_ex(vrfs_ctx* ctx, size_t n, const uint8_t* bases, const uint8_t* scalars, int n_columns, int window_bits, uint8_t* out) {
+  if (ctx && window_bits != 0 && (window_bits < 7 || window_bits > 16)) return fail(ctx, VRFS_BAD_ARG, "window_bits must be 0 (automatic) or 7..16");
+  return msm_host(ctx, n, bases, scalars, n_columns, out, 0, window_bits);
 }
 extern "C" vrfs_status vrfs_msm_g1_partial(vrfs_ctx* ctx, size_t n, const uint8_t* bases, const uint8_t* scalars, int n_columns, uint8_t* out_partial) {
   return msm_host(ctx, n, bases, scalars, n_columns, out_partial, 1);

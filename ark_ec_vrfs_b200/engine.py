@@ -342,10 +342,11 @@ class Engine:
         return (ok, st) if status else ok
 
     # ---- ring commitment MSM (BLS12-381 G1)
-    def msm_g1(self, bases, scalars, n_columns=1):
+    def msm_g1(self, bases, scalars, n_columns=1, window_bits=0):
         bases = _u8(bases, (-1, 96)); n = len(bases); scalars = _u8(scalars, (n_columns * n, 32))
         out = np.zeros((n_columns, 96), np.uint8)
-        self._call("vrfs_msm_g1_bls12_381", C.c_size_t(n), _p(bases), _p(scalars), int(n_columns), _p(out))
+        if window_bits: self._call("vrfs_msm_g1_bls12_381_ex", C.c_size_t(n), _p(bases), _p(scalars), int(n_columns), int(window_bits), _p(out))
+        else: self._call("vrfs_msm_g1_bls12_381", C.c_size_t(n), _p(bases), _p(scalars), int(n_columns), _p(out))
         return out
 
     def msm_g1_prepare(self, bases, window_bits=0, threads_per_bucket=0):

@@ -160,6 +160,9 @@ vrfs_status vrfs_pedersen_verify_wire_batch(vrfs_ctx*, vrfs_suite, size_t n, con
  * out: n_columns * 96 bytes affine. */
 vrfs_status vrfs_msm_g1_bls12_381(vrfs_ctx*, size_t n, const uint8_t* bases /*n*96*/, const uint8_t* scalars /*n_columns*n*32*/,
                                   int n_columns, uint8_t* out /*n_columns*96*/);
+/* the same with a tuning hint: window_bits (0 = automatic, else 7..16).  The result never depends on it. */
+vrfs_status vrfs_msm_g1_bls12_381_ex(vrfs_ctx*, size_t n, const uint8_t* bases /*n*96*/, const uint8_t* scalars /*n_columns*n*32*/, int n_columns, int window_bits,
+                                     uint8_t* out /*n_columns*96*/);
 /* Prepared bases: the counterpart of `RingContext` holding the SRS.  `prepare` stores 2^(c*w) * P_i for every window
  * once (device memory: ceil(256/c) * n * 96 bytes, affine); `prepared` then computes n_columns commitments with one shared
  * bucket set per column and no Horner chain.  Results are identical to vrfs_msm_g1_bls12_381. */

@@ -174,6 +174,8 @@ extern "C" int hostemu_fq381_inv_fast(const uint32_t* a_mont, uint32_t* out_mont
   return finished;
 }
 
+// k = k1 + q z^2 (csrc/msm.cuh g1_glv_split, the stateless MSM's scalar halves); canonical limbs in and out
+extern "C" void hostemu_g1_glv_split(const uint32_t* k8, uint32_t* k1_4, uint32_t* q_4) { g1_glv_split(k1_4, q_4, k8); }
 // a b - c d with one reduction (csrc/msm.cuh fq381_mul_sub2, the Y coordinate of the bucket addition); Montgomery limbs in and out
 extern "C" void hostemu_fq381_mul_sub2(const uint32_t* a, const uint32_t* b, const uint32_t* c, const uint32_t* d, uint32_t* out_mont) {
   Fq381 A, B, Cc, D; memcpy(A.v, a, 48); memcpy(B.v, b, 48); memcpy(Cc.v, c, 48); memcpy(D.v, d, 48);

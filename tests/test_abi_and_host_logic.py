@@ -154,6 +154,22 @@ def test_fq381_word_approximation_gcd_inverse(emu):
         assert finished == (1 if a else 0), a
 
 
+def test_g1_glv_split_of_msm_scalars(emu):
+    """csrc/msm.cuh g1_glv_split: k = k1 + q z^2 with both halves below z^2 < 2^128 (z the BLS12-381 curve parameter), extremes included"""
+    z2 = 0xd201000000010000 ** 2
+    r = R.BLS_FR
+    assert r == z2 * z2 - z2 + 1
+    rnd = random.Random(24)
+    ext = [0, 1, z2 - 1, z2, z2 + 1, r - 1, r - z2, 2 * z2 - 1, (z2 - 1) * z2, (z2 - 1) * z2 + z2 - 1]
+    for t in range(3000):
+        k = ext[t] if t < len(ext) else rnd.randrange(r) if t % 4 else rnd.randrange(z2) * z2 + rnd.choice([0, 1, z2 - 1, z2 - 2])
+        k %= r
+        K = (C.c_uint32 * 8)(*[(k >> (32 * i)) & 0xFFFFFFFF for i in range(8)]); k1 = (C.c_uint32 * 4)(); q = (C.c_uint32 * 4)()
+        emu.hostemu_g1_glv_split(K, k1, q)
+        a = sum(int(k1[i]) << (32 * i) for i in range(4)); b = sum(int(q[i]) << (32 * i) for i in range(4))
+        assert a == k % z2 and b == k // z2, hex(k)
+
+
 def test_fq381_fused_product_difference(emu):
     """csrc/msm.cuh fq381_mul_sub2: a b - c d through ONE Montgomery reduction of a b + c (q - d), extremes included"""
     p = R.BLS_FQ; Rm = 1 << 384
