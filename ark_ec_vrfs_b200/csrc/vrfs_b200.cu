@@ -1809,13 +1809,15 @@ __global__ void k_fq381_inv_batch(uint32_t n, const uint8_t* in, uint8_t* out, u
   const Fq381 one_thread = fq381_inv_fast(a);
   // the four-lane form (fq381_inv_coop4) must give the same element: the lanes of a group take their four values in turn
   Fq381 four_lane = one_thread;
+  bool four_lane_finished = false;
   for (unsigned turn = 0; turn < 4; turn++) {
     const Fq381 x = fq_shfl(a, (threadIdx.x & 28u) + turn);
-    const Fq381 r = fq381_inv_coop4(x);
-    if ((threadIdx.x & 3u) == turn) four_lane = r;
+    bool fb = false;
+    const Fq381 r = fq381_inv_coop4(x, &fb);
+    if ((threadIdx.x & 3u) == turn) { four_lane = r; four_lane_finished = !fb; }
   }
   if (i >= n) return;
-  ok[i] = (finished && four_lane == one_thread) ? 1 : 0;
+  ok[i] = (finished && four_lane_finished && four_lane == one_thread) ? 1 : 0;
   from_mont<BlsFq>(raw, four_lane);
   store_le<12>(out + (size_t)48 * i, raw);
 }
