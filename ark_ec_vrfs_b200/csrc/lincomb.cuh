@@ -76,10 +76,12 @@ template <class C> struct Grp<C, true> {
   static HD_INLINE void from_affine(Pt& P, const typename C::F& x, const typename C::F& y) { te_from_affine<C>(P, x, y); }
   static HD_INLINE bool on_curve(const typename C::F& x, const typename C::F& y) { return te_on_curve<C>(x, y); }
   static HD_INLINE void to_entry(Entry& e, const Pt& P) { te_to_cached(e, P); }
-  static HD_INLINE void add_entry(Pt* acc, const Entry* e, bool negate) { te_add_cached<C>(acc, acc, e, negate); }
-  static HD_INLINE void add_fix(Pt* acc, const FixEntry* e, bool negate) { te_madd<C>(acc, acc, e, negate); }
+  // want_t = false: the T coordinate of the sum is left undefined (the caller follows with a doubling, or stores X, Y, Z)
+  static HD_INLINE void add_entry(Pt* acc, const Entry* e, bool negate, bool want_t = true) { te_add_cached<C>(acc, acc, e, negate, want_t); }
+  static HD_INLINE void add_fix(Pt* acc, const FixEntry* e, bool negate, bool want_t = true) { te_madd<C>(acc, acc, e, negate, want_t); }
   static HD_INLINE void dbl4(Pt* acc) { te_dbl<C>(acc, acc, false); te_dbl<C>(acc, acc, false); te_dbl<C>(acc, acc, false); te_dbl<C>(acc, acc, true); }
   static HD_INLINE void dbl(Pt* acc) { te_dbl<C>(acc, acc, true); }
+  static HD_INLINE void dbl_entry(Pt* r, const Entry* e) { Pt p; p.X = e->X; p.Y = e->Y; p.Z = e->Z; p.T = e->Z; te_dbl<C>(r, &p, true); }   // the doubling does not read T
   static HD_INLINE void add(Pt* r, const Pt* p, const Pt* q) { te_add<C>(r, p, q); }
   static HD_INLINE void endo(Pt* r, const Pt* p) { band_endo(reinterpret_cast<TEPoint<BandCurve>*>(r), reinterpret_cast<const TEPoint<BandCurve>*>(p)); }
   static HD_INLINE void to_fix(FixEntry& e, const Pt& P) {
@@ -100,13 +102,14 @@ template <class C> struct Grp<C, false> {
   static HD_INLINE void from_affine(Pt& P, const typename C::F& x, const typename C::F& y) { sw_from_affine<C>(P, x, y); }
   static HD_INLINE bool on_curve(const typename C::F& x, const typename C::F& y) { return sw_on_curve<C>(x, y); }
   static HD_INLINE void to_entry(Entry& e, const Pt& P) { e = P; }
-  static HD_INLINE void add_entry(Pt* acc, const Entry* e, bool negate) { Entry q = *e; sw_cneg(q, negate); sw_add<C>(acc, acc, &q); }
-  static HD_INLINE void add_fix(Pt* acc, const FixEntry* e, bool negate) { add_entry(acc, e, negate); }
+  static HD_INLINE void add_entry(Pt* acc, const Entry* e, bool negate, bool = true) { Entry q = *e; sw_cneg(q, negate); sw_add<C>(acc, acc, &q); }
+  static HD_INLINE void add_fix(Pt* acc, const FixEntry* e, bool negate, bool = true) { add_entry(acc, e, negate); }
   static HD_INLINE void dbl4(Pt* acc) {
     if constexpr (C::A_IS_M3) sw_dbl4_am3<C>(acc, acc);                          // secp256r1
     else { for (int i = 0; i < 4; i++) sw_add<C>(acc, acc, acc); }               // general a (bandersnatch_sw): the complete addition doubles
   }
   static HD_INLINE void dbl(Pt* acc) { sw_add<C>(acc, acc, acc); }
+  static HD_INLINE void dbl_entry(Pt* r, const Entry* e) { *r = *e; sw_add<C>(r, r, r); }
   static HD_INLINE void add(Pt* r, const Pt* p, const Pt* q) { sw_add<C>(r, p, q); }
   static HD_INLINE void to_fix(FixEntry& e, const Pt& P) {            // normalise to Z = 1 (identity stays (0:1:0))
     bool inf = P.Z.is_zero();
@@ -115,6 +118,12 @@ template <class C> struct Grp<C, false> {
   }
   static HD_INLINE void store_xyz(uint32_t* o, const Pt& P) { store_fp_xyz(o, P.X, P.Y, P.Z); }
 };
+#ifndef VRFS_SKIP_T
+#define VRFS_SKIP_T 1                     // do not compute the T coordinate of sums nobody reads (one product per window)
+#endif
+#ifndef VRFS_TABLE_DOUBLINGS
+#define VRFS_TABLE_DOUBLINGS 1
+#endif
 static constexpr int TBL_ENTRIES = 9;     // 0*P .. 8*P
 static constexpr int FIX_ENTRIES = (1 << (VRFS_FIX_BITS - 1)) + 1;   // 0 .. 2^(b-1) times 2^(b w) * B
 // bytes of per-thread table slab for NV variable bases
@@ -161,7 +170,8 @@ template <class C> HD_INLINE void load_scalar_mod_r(uint32_t* k, const uint8_t* 
   from_mont<typename C::Fr>(k, m);
 }
 
-// table of j*B, j = 0..8; B in projective/extended coordinates
+// table of j*B, j = 0..8; B in projective/extended coordinates.  Twisted Edwards: the even multiples are doublings of the entry
+// j/2 read back from the slab (4S + 4M instead of the 9M of an addition: 2P, 4P, 6P, 8P), the odd ones add B to the point just made.
 template <class C> HD_INLINE void build_table(typename Grp<C>::Entry* tbl, const typename Grp<C>::Pt& B) {
   typedef Grp<C> G;
   typename G::Pt cur; G::set_identity(cur);
@@ -172,7 +182,12 @@ template <class C> HD_INLINE void build_table(typename Grp<C>::Entry* tbl, const
   cur = B;
 #pragma unroll 1
   for (int j = 2; j <= 8; j++) {
-    G::add_entry(&cur, &cb, false);
+    if (C::IS_TE && VRFS_TABLE_DOUBLINGS && (j & 1) == 0) {
+      copy_words16(&e, &tbl[j >> 1]);
+      G::dbl_entry(&cur, &e);
+    } else {
+      G::add_entry(&cur, &cb, false);
+    }
     G::to_entry(e, cur); copy_words16(&tbl[j], &e);
   }
 }
@@ -238,7 +253,9 @@ HD_INLINE bool lincomb_item(const LincombArgs& A, uint32_t item, typename Grp<C>
         int idx = d < 0 ? -d : d;
         typename G::Entry e;
         copy_words16(&e, &slab[t * TBL_ENTRIES + idx]);
-        G::add_entry(&acc, &e, (d < 0) != kneg[t]);
+        // the last addition of a window is followed by the next window's doublings (which do not read T) or, after the last
+        // window, by nothing but the fixed-base additions: its T is only computed when somebody reads it
+        G::add_entry(&acc, &e, (d < 0) != kneg[t], VRFS_SKIP_T ? (t != NT - 1 || (w == 0 && NF > 0)) : true);
       }
     }
   }
@@ -267,7 +284,7 @@ HD_INLINE bool lincomb_item(const LincombArgs& A, uint32_t item, typename Grp<C>
       int idx = d < 0 ? -d : d;
       typename G::FixEntry e;
       copy_words16(&e, &tbl[(size_t)w * FIX_ENTRIES + idx]);
-      G::add_fix(&acc, &e, (d < 0) != neg);
+      G::add_fix(&acc, &e, (d < 0) != neg, VRFS_SKIP_T ? (f != NF - 1 || w != G::FIX_WINDOWS - 1) : true);
     }
   }
   return ok;

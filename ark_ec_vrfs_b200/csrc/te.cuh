@@ -104,30 +104,31 @@ template <class C> HD_NOINLINE void te_add(TEPoint<C>* r, const TEPoint<C>* p, c
   r->X = E * Fv; r->Y = G * H; r->T = E * H; r->Z = Fv * G;
 }
 // r = p + q, q cached, optionally negated (9M)
-template <class C> HD_NOINLINE void te_add_cached(TEPoint<C>* r, const TEPoint<C>* p, const TECached<C>* q, bool negate) {
+// (want_t = false: T of the result is not computed - the next operation is a doubling, which does not read it, or the end)
+template <class C> HD_NOINLINE void te_add_cached(TEPoint<C>* r, const TEPoint<C>* p, const TECached<C>* q, bool negate, bool want_t = true) {
   typedef typename C::F F;
   F qX = cneg(q->X, negate), qdT = cneg(q->dT, negate);
-  F A, B, Cc, D, E, X3, Y3, T3, Z3;
+  F A, B, Cc, D, E, X3, Y3, Z3;
   mul2(A, B, p->X, qX, p->Y, q->Y);
   mul2(Cc, D, p->T, qdT, p->Z, q->Z);
   E = (p->X + p->Y) * (qX + q->Y) - A - B;
   F Fv = D - Cc, G = D + Cc, H = B - C::mul_a(A);
   mul2(X3, Y3, E, Fv, G, H);
-  mul2(T3, Z3, E, H, Fv, G);
-  r->X = X3; r->Y = Y3; r->T = T3; r->Z = Z3;
+  r->X = X3; r->Y = Y3;
+  if (want_t) { F T3; mul2(T3, Z3, E, H, Fv, G); r->T = T3; r->Z = Z3; } else r->Z = Fv * G;
 }
 // r = p + q, q affine cached, optionally negated (8M)
-template <class C> HD_NOINLINE void te_madd(TEPoint<C>* r, const TEPoint<C>* p, const TEAffCached<C>* q, bool negate) {
+template <class C> HD_NOINLINE void te_madd(TEPoint<C>* r, const TEPoint<C>* p, const TEAffCached<C>* q, bool negate, bool want_t = true) {
   typedef typename C::F F;
   F qx = cneg(q->x, negate), qdt = cneg(q->dt, negate);
-  F A, B, Cc, E, D = p->Z, X3, Y3, T3, Z3;
+  F A, B, Cc, E, D = p->Z, X3, Y3, Z3;
   mul2(A, B, p->X, qx, p->Y, q->y);
   mul2(Cc, E, p->T, qdt, p->X + p->Y, qx + q->y);
   E = E - A - B;
   F Fv = D - Cc, G = D + Cc, H = B - C::mul_a(A);
   mul2(X3, Y3, E, Fv, G, H);
-  mul2(T3, Z3, E, H, Fv, G);
-  r->X = X3; r->Y = Y3; r->T = T3; r->Z = Z3;
+  r->X = X3; r->Y = Y3;
+  if (want_t) { F T3; mul2(T3, Z3, E, H, Fv, G); r->T = T3; r->Z = Z3; } else r->Z = Fv * G;
 }
 // r = 2p (4S + 4M; T of the result is skipped when the next operation is another doubling)
 template <class C> HD_NOINLINE void te_dbl(TEPoint<C>* r, const TEPoint<C>* p, bool want_t) {
