@@ -103,9 +103,12 @@ HD_INLINE void pairing_lane_op(Fq381* R, const PairingOp& op) {
   }
   copy_words16(&R[d], &r);
 }
+// the operation of `lane` in `step` (a step stores only its real operations; the other lanes idle)
 HD_INLINE PairingOp pairing_op_load(uint32_t step, unsigned lane) {
   PairingOp op;
-  copy_words16(&op, reinterpret_cast<const PairingOp*>(PAIRING_STEPS) + (size_t)step * PairingProg::LANES + lane);
+  const uint32_t first = PAIRING_STEP_OFF[step], n = PAIRING_STEP_OFF[step + 1] - first;
+  if (lane < n) copy_words16(&op, reinterpret_cast<const PairingOp*>(PAIRING_OPS) + first + lane);
+  else { op.w[0] = 0; op.w[1] = 0; op.w[2] = 0; op.w[3] = 0; }
   return op;
 }
 

@@ -33,6 +33,7 @@ Q = P.Q
 LANES = int(os.environ.get("PAIRING_LANES", "64"))   # 64: two warps per product (2.19 ms on a B200; 32 lanes: 2.48 ms)
 NPAIRS = 2
 SCHED_LIN_FIRST = int(os.environ.get("SCHED_LIN_FIRST", "1"))
+MILLER_GROUP = int(os.environ.get("PAIRING_MILLER_GROUP", "4"))     # Miller iterations per segment
 
 NOP, MUL, ADD, SUB, HALF, INV = 0, 1, 2, 3, 4, 5
 IN = 9                       # pseudo-kind: a value that already sits in a pinned register
@@ -248,36 +249,41 @@ def blk_g2proj(t, regs):
     return ((e[0], e[1]), (e[2], e[3]), (e[4], e[5]))
 def consts(t): return {nm: (E(t, t.pin(rr[0])), E(t, t.pin(rr[1]))) for nm, (rr, _) in CONST_F2.items()}
 
-def seg_miller(t, with_add, first):
-    """one iteration of the Miller loop for NPAIRS pairs: f <- f^2 * prod lines; R_k <- 2 R_k (+ Q_k)"""
+def seg_miller(t, bits, first):
+    """len(bits) consecutive iterations of the Miller loop for NPAIRS pairs (bits[i] = 1: iteration i also adds Q_k):
+    f <- f^2 * prod lines,  R_k <- 2 R_k (+ Q_k).  Several iterations per segment let the scheduler run the chain of the points
+    R_k (two levels of multiplications per iteration, independent of f) AHEAD of the chain of f, so that a segment of n iterations
+    needs ~2n + 3 levels of multiplications instead of 5n."""
     zero2 = (E(t, t.pin(R_ZERO)), E(t, t.pin(R_ZERO)))
     one = E(t, t.pin(R_ONE))
-    if first:
-        f = (((one, zero2[0]), zero2, zero2), (zero2, zero2, zero2))
-    else:
-        f = blk12(t, BLOCKS["F"])
-    outs = []
-    lines = []
+    f = (((one, zero2[0]), zero2, zero2), (zero2, zero2, zero2)) if first else blk12(t, BLOCKS["F"])
+    ps, qs, rs = [], [], []
     for k in range(NPAIRS):
-        p = (E(t, t.pin(R_P[k][0])), E(t, t.pin(R_P[k][1])))
+        ps.append((E(t, t.pin(R_P[k][0])), E(t, t.pin(R_P[k][1]))))
         q = ((E(t, t.pin(R_Q[k][0])), E(t, t.pin(R_Q[k][1]))), (E(t, t.pin(R_Q[k][2])), E(t, t.pin(R_Q[k][3]))))
-        r = (q[0], q[1], (one, zero2[0])) if first else blk_g2proj(t, R_R[k])
-        r, co = doubling_step(r)
-        lines.append(line_at(co, p))
-        if with_add:
-            r, co = addition_step(r, q)
-            lines.append(line_at(co, p))
-        outs += list(zip([c for f2 in r for c in f2], R_R[k]))
-    f = f12_sqr(f)
-    # lines are multiplied pairwise first (off the critical path of f), then folded into f
-    prods = []
-    for i in range(0, len(lines) - 1, 2):
-        prods.append(mul_lines(lines[i], lines[i + 1], zero2))
-    if len(lines) & 1:
-        prods.append(sparse_to_f12(lines[-1], zero2))
-    while len(prods) > 1:
-        prods = [f12_mul(prods[i], prods[i + 1]) if i + 1 < len(prods) else prods[i] for i in range(0, len(prods), 2)]
-    f = f12_mul(f, prods[0])
+        qs.append(q)
+        rs.append((q[0], q[1], (one, zero2[0])) if first else blk_g2proj(t, R_R[k]))
+    for with_add in bits:
+        lines = []
+        for k in range(NPAIRS):
+            rs[k], co = doubling_step(rs[k])
+            lines.append(line_at(co, ps[k]))
+            if with_add:
+                rs[k], co = addition_step(rs[k], qs[k])
+                lines.append(line_at(co, ps[k]))
+        f = f12_sqr(f)
+        # lines are multiplied pairwise first (off the critical path of f), then folded into f
+        prods = []
+        for i in range(0, len(lines) - 1, 2):
+            prods.append(mul_lines(lines[i], lines[i + 1], zero2))
+        if len(lines) & 1:
+            prods.append(sparse_to_f12(lines[-1], zero2))
+        while len(prods) > 1:
+            prods = [f12_mul(prods[i], prods[i + 1]) if i + 1 < len(prods) else prods[i] for i in range(0, len(prods), 2)]
+        f = f12_mul(f, prods[0])
+    outs = []
+    for k in range(NPAIRS):
+        outs += list(zip([c for f2 in rs[k] for c in f2], R_R[k]))
     outs += list(zip(flat12(f), BLOCKS["F"]))
     return outs
 
@@ -601,9 +607,13 @@ def build_all():
     order = []
     def add(name, fn):
         segs[name] = compile_segment(name, fn); order.append(name)
-    add("miller_first", lambda t: seg_miller(t, True, True))     # X_ABS = 0b1101...: the bit after the leading one is set
-    add("miller_dbl", lambda t: seg_miller(t, False, False))
-    add("miller_dbladd", lambda t: seg_miller(t, True, False))
+    bits = [int(b) for b in bin(P.X_ABS)[3:]]           # 63 iterations; bit = 1: the iteration also adds Q
+    macro = []
+    for i0 in range(0, len(bits), MILLER_GROUP):
+        grp = tuple(bits[i0:i0 + MILLER_GROUP])
+        name = "miller_%s%s" % ("first_" if i0 == 0 else "", "".join(map(str, grp)))
+        if name not in segs: add(name, lambda t, grp=grp, first=(i0 == 0): seg_miller(t, grp, first))
+        macro.append(name)
     add("easy", seg_easy)
     add("cyc", seg_cyc)
     add("mulb", seg_mulb)
@@ -612,13 +622,10 @@ def build_all():
     add("glue_c", lambda t: seg_glue(t, "BV", "CV", "frob1"))
     add("xx", seg_xx)
     add("last", seg_last)
-    bits = bin(P.X_ABS)[3:]
-    assert bits[0] == "1"
-    macro = ["miller_first"] + ["miller_dbladd" if b == "1" else "miller_dbl" for b in bits[1:]]
     expx = []
     for b in bits:
         expx.append("cyc")
-        if b == "1": expx.append("mulb")
+        if b: expx.append("mulb")
     macro += ["easy"] + expx + ["glue_a"] + expx + ["glue_b"] + expx + ["glue_c"] + expx + ["xx"] + expx + ["last"]
     return segs, order, macro
 
@@ -676,17 +683,22 @@ def main():
          "  static constexpr uint32_t QOFF_TOP = %du, Q_RECIP = %du;" % (QOFF >> 384, Q_RECIP),
          "  static HD_INLINE uint32_t qoff(int i) { constexpr uint32_t t[12] = {%s}; return t[i]; }" % ", ".join("0x%08xu" % ((QOFF >> (32 * i)) & 0xFFFFFFFF) for i in range(12)),
          "};"]
-    offs, tab = [], []
+    # steps are stored densely: PAIRING_STEP_OFF[s] .. PAIRING_STEP_OFF[s + 1] are the operations of step s (lane l takes the l-th)
+    offs, step_off, tab = [], [0], []
     for nm in order:
-        offs.append(len(tab) // (4 * LANES))
+        offs.append(len(step_off) - 1)
         for row in segs[nm]["steps"]:
             for o in row: tab += encode(o)
-            tab += [0] * (4 * (LANES - len(row)))
-    offs.append(len(tab) // (4 * LANES))
+            step_off.append(len(tab) // 4)
+    offs.append(len(step_off) - 1)
     L.append("// segments: " + ", ".join("%d %s" % (i, nm) for i, nm in enumerate(order)))
     L.append("VRFS_GLOBAL_TABLE uint32_t PAIRING_SEG_OFF[%d] = {%s};" % (len(offs), ", ".join(map(str, offs))))
     L.append("VRFS_GLOBAL_TABLE uint8_t PAIRING_MACRO[%d] = {%s};" % (len(macro), ", ".join(str(order.index(m)) for m in macro)))
-    L.append("alignas(16) VRFS_GLOBAL_TABLE uint32_t PAIRING_STEPS[%d] = {" % len(tab))
+    L.append("VRFS_GLOBAL_TABLE uint32_t PAIRING_STEP_OFF[%d] = {" % len(step_off))
+    for i in range(0, len(step_off), 24):
+        L.append("  " + ", ".join(map(str, step_off[i:i + 24])) + ",")
+    L.append("};")
+    L.append("alignas(16) VRFS_GLOBAL_TABLE uint32_t PAIRING_OPS[%d] = {" % len(tab))
     for i in range(0, len(tab), 16):
         L.append("  " + ", ".join("0x%08xu" % x for x in tab[i:i + 16]) + ",")
     L.append("};")
@@ -700,7 +712,7 @@ def main():
         return
     if "--dry" in sys.argv: return
     open(OUT, "w").write(text)
-    print("wrote %s (%d steps of %d lanes, %d registers)" % (OUT, len(tab) // (4 * LANES), LANES, nreg))
+    print("wrote %s (%d steps, %d operations, <= %d lanes, %d registers)" % (OUT, len(step_off) - 1, len(tab) // 4, LANES, nreg))
 
 
 if __name__ == "__main__":
