@@ -169,9 +169,9 @@ static void f_sub(const fctx *F, fe *r, const fe *a, const fe *b) {
 }
 static void f_neg(const fctx *F, fe *r, const fe *a) { fe z; f_zero(&z); f_sub(F, r, &z, a); }
 static void f_dbl(const fctx *F, fe *r, const fe *a) { f_add(F, r, a, a); }
-/* CIOS Montgomery product */
-static void f_mul(const fctx *F, fe *r, const fe *a, const fe *b) {
-    int n = F->n;
+/* CIOS Montgomery product (the loop bounds are compile-time constants for the two limb counts in use, so the compiler unrolls
+ * them the way ark-ff's generated N-limb code is unrolled) */
+static inline __attribute__((always_inline)) void f_mul_n(const fctx *F, fe *r, const fe *a, const fe *b, const int n) {
     u64 t[MAXL + 2] = {0};
     for (int i = 0; i < n; i++) {
         u64 c = 0;
@@ -185,6 +185,9 @@ static void f_mul(const fctx *F, fe *r, const fe *a, const fe *b) {
     fe o; f_zero(&o); for (int i = 0; i < n; i++) o.v[i] = t[i];
     if (t[n] || raw_cmp(F, &o, &F->p) >= 0) raw_sub(n, &o, &o, &F->p);
     *r = o;
+}
+static void f_mul(const fctx *F, fe *r, const fe *a, const fe *b) {
+    if (F->n == 4) f_mul_n(F, r, a, b, 4); else if (F->n == 6) f_mul_n(F, r, a, b, 6); else f_mul_n(F, r, a, b, F->n);
 }
 static void f_sqr(const fctx *F, fe *r, const fe *a) { f_mul(F, r, a, a); }
 static void f_from_raw(const fctx *F, fe *r, const fe *a) { f_mul(F, r, a, &F->r2); }  /* a < 2^(64n) */
