@@ -920,6 +920,127 @@ __global__ void __launch_bounds__(256) k_msm_wbits(MsmPlan p, const G1Pt* in, G1
   }
 }
 
+// =================================================================================================
+// TABLE mode of a prepared SRS (round 2): for the short domains ring commitments actually have (ring size <= 2^11) the bucket
+// pipeline is bound by its nine dependent launches and by the weighted bucket sums, not by the additions.  With the SRS fixed,
+// memory buys them off: T[w][i][d-1] = d 2^(8w) P_i for d = 1 .. 128 (affine, 96 B; 393 KB per base - 0.8 GB for a 2^11-point SRS
+// of the 180 GB), every scalar is 32 signed radix-256 digits (digit_w = byte_w(k + 0x80..80) - 128, no carry chain), and a
+// commitment is the plain SUM of the n x 32 table entries its digits select: no sort, no buckets, no weights.
+//   k_msm_table_build   (once per SRS) the 128 multiples of every Q[w][i] = 2^(8w) P_i, normalised 16 at a time (Montgomery's trick)
+//   k_msm_table_sum     every thread adds the entries of its strided share of the (window, base) pairs of one column (XYZZ mixed
+//                       additions, the next entry prefetched), block tree -> one partial per block
+//   k_msm_table_reduce  one block per column adds the blocks' partials;  k_msm_final2 normalises / exchanges as before
+// Ring-shaped columns (a repeated padding point, a 0/1 selector) cost exactly what random columns cost: there is no bucket to overfill.
+// =================================================================================================
+#define MSM_TABLE_C 8
+#define MSM_TABLE_D (1 << (MSM_TABLE_C - 1))              // 128 multiples per (window, base)
+#define MSM_TABLE_WINDOWS 32                               // signed radix-256 digits of a scalar < r < 2^255 (the bias addition cannot overflow: 0x73 + 0x80 < 0x100)
+#define MSM_TABLE_CHUNK 16
+__global__ void __launch_bounds__(128) k_msm_table_build(uint32_t n, const G1Aff* Q /*[32][n]*/, G1Aff* T /*[32][n][128]*/) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;     // = w * n + i
+  if (idx >= (size_t)MSM_TABLE_WINDOWS * n) return;
+  Fq381 bx, by;
+  const bool finite = g1_load_aff_xy(bx, by, Q + idx, false);
+  G1Aff* out = T + idx * MSM_TABLE_D;
+  G1Xyzz cur; xyzz_set_identity(cur);
+  G1Xyzz st[MSM_TABLE_CHUNK];
+  Fq381 pre[MSM_TABLE_CHUNK];
+#pragma unroll 1
+  for (int d0 = 0; d0 < MSM_TABLE_D; d0 += MSM_TABLE_CHUNK) {
+    unsigned infmask = 0;
+    for (int j = 0; j < MSM_TABLE_CHUNK; j++) {
+      if (finite) xyzz_madd(&cur, &bx, &by);
+      st[j] = cur;
+      const bool inf = cur.ZZ.is_zero();                 // a base of small order (or the identity itself): that multiple is the identity
+      if (inf) infmask |= 1u << j;
+      const Fq381 wj = select(inf, Fq381::one(), cur.ZZ * cur.ZZZ);
+      pre[j] = j ? pre[j - 1] * wj : wj;
+    }
+    Fq381 acc = fq381_inv_fast(pre[MSM_TABLE_CHUNK - 1]);
+    for (int j = MSM_TABLE_CHUNK - 1; j >= 0; j--) {
+      const bool inf = (infmask >> j) & 1u;
+      const Fq381 wj = select(inf, Fq381::one(), st[j].ZZ * st[j].ZZZ);
+      const Fq381 wi = j ? acc * pre[j - 1] : acc;       // 1 / (ZZ ZZZ)
+      if (j) acc = acc * wj;
+      G1Aff a;
+      a.x = st[j].X * (wi * st[j].ZZZ);                  // X / ZZ
+      a.y = st[j].Y * (wi * st[j].ZZ);                   // Y / ZZZ
+      if (inf) { a.x = Fq381::zero(); a.y = Fq381::zero(); }
+      copy_words16(&out[d0 + j], &a);
+    }
+  }
+}
+// blockIdx.y = column; the blocks of a column stride together over its n * 32 (window, base) pairs
+__global__ void __launch_bounds__(128, 4) k_msm_table_sum(uint32_t n, const G1Aff* T, const uint8_t* scalars, G1Pt* partials) {
+  __shared__ uint4 sh_raw[128 * sizeof(G1Pt) / 16];
+  G1Pt* sh = reinterpret_cast<G1Pt*>(sh_raw);
+  const uint32_t col = blockIdx.y, t = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+  const uint32_t M = n * MSM_TABLE_WINDOWS;
+  const uint8_t* sc = scalars + (size_t)32 * n * col;
+  G1Xyzz acc; xyzz_set_identity(acc);
+  // term m = w * n + i; its table entry: the digit of scalar i in window w
+  auto entry_of = [&](uint32_t m, bool& negate) -> const G1Aff* {
+    const uint32_t w = m / n, i = m - w * n;
+    uint32_t k[9];
+    msm_load_scalar(k, sc + (size_t)32 * i);
+    k[8] = 0;
+    add_window_bias<9>(k, 0x80808080u, 8);
+    const int d = digit8(k, (int)w);
+    negate = d < 0;
+    const int mag = d < 0 ? -d : d;
+    return mag ? T + ((size_t)m * MSM_TABLE_D + (mag - 1)) : nullptr;
+  };
+  bool neg = false;
+  const G1Aff* e = t < M ? entry_of(t, neg) : nullptr;
+  if (e) prefetch_l1(e, (unsigned)sizeof(G1Aff));
+  for (uint32_t m = t; m < M; m += stride) {
+    bool nneg = false;
+    const G1Aff* ne = m + stride < M ? entry_of(m + stride, nneg) : nullptr;
+    if (ne) prefetch_l1(ne, (unsigned)sizeof(G1Aff));          // a random 96-byte record of a table far larger than L2
+    if (e) {
+      Fq381 x, y;
+      if (g1_load_aff_xy(x, y, e, neg)) xyzz_madd(&acc, &x, &y);
+    }
+    e = ne; neg = nneg;
+  }
+  G1Pt r;
+  xyzz_to_proj(r, acc);
+  copy_words16(&sh[threadIdx.x], &r);
+  __syncthreads();
+  block_tree_sum(sh, 128);
+  if (threadIdx.x == 0) copy_words16(&partials[(size_t)col * gridDim.x + blockIdx.x], &sh[0]);
+}
+// one block of 256 threads (32 cooperating groups) per column: sum of its nparts partials -> out[col]
+__global__ void __launch_bounds__(256) k_msm_table_reduce(int nparts, const G1Pt* partials, G1Pt* out) {
+  __shared__ uint4 sh_raw[32 * sizeof(G1Pt) / 16];
+  G1Pt* sh = reinterpret_cast<G1Pt*>(sh_raw);
+  const G1Pt* W = partials + (size_t)blockIdx.x * nparts;
+  const unsigned G = threadIdx.x >> 3, g = threadIdx.x & 7u;
+  G1Pt acc; sw_set_identity(acc);
+  for (int r = 0; r * 32 < nparts; r++) {
+    const int k = r * 32 + (int)G;
+    G1Pt e; sw_set_identity(e);
+    if (k < nparts) copy_words16(&e, W + k);
+    if (r == 0) acc = e;
+    else if ((r * 32 + (int)(G & ~3u)) < nparts) g1_coop_add(&acc, &acc, &e);
+  }
+  if (g == 0) copy_words16(&sh[G], &acc);
+  __syncthreads();
+  int live = 1; while (live < nparts && live < 32) live <<= 1;
+  for (int s = live >> 1; s > 0; s >>= 1) {
+    if ((int)(G & ~3u) < s) {
+      G1Pt a2, b2, z;
+      copy_words16(&a2, &sh[(int)G < s ? G : (unsigned)s]);
+      copy_words16(&b2, &sh[(int)G < s ? G + s : (unsigned)s]);
+      g1_coop_add(&z, &a2, &b2);
+      __syncwarp();
+      if ((int)G < s && g == 0) copy_words16(&sh[G], &z);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) copy_words16(&out[blockIdx.x], &sh[0]);
+}
+
 // ---- multi-GPU exchange of the per-rank partial sums ("MSM splits by point range, with only a tiny NCCL/NVLink
 // reduction of partial bucket sums").  Every rank owns a MAILBOX in its device memory that the other ranks of the node have mapped
 // (in-process: peer access; across processes: CUDA IPC).  The final kernel of a rank's MSM stores its projective partial straight

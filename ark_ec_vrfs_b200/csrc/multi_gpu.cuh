@@ -110,7 +110,7 @@ extern "C" vrfs_status vrfs_msm_g1_prepared_allgather(vrfs_ctx* ctx, const vrfs_
   const uint8_t* d_s; uint8_t* d_o;
   ST(stage_in(ctx, BUF_IN1, scalars, h->n * 32 * (size_t)n_columns, &d_s));
   ST(stage_out(ctx, BUF_OUT0, (size_t)96 * n_columns, &d_o));
-  ST(msm_dev(ctx, plan_for(h, n_columns), h->Q, d_s, d_o, 2, &pa));
+  ST(msm_prepared_dev(ctx, h, n_columns, 0, d_s, d_o, 2, &pa));
   ST(copy_out(ctx, out, d_o, (size_t)96 * n_columns));
   ST(finish_call(ctx));
   return peer_check(ctx);
@@ -128,9 +128,7 @@ extern "C" vrfs_status vrfs_ring_commit_rows_allgather(vrfs_ctx* ctx, const vrfs
   uint8_t *d_cols = nullptr, *d_o = nullptr;
   ST(ring_columns_dev(ctx, n, keyset_part_size, n_keys, keys_rows, padding, n_tail, tail, &d_cols, row_lo, false));
   ST(stage_out(ctx, BUF_OUT0, 3 * 96, &d_o));
-  MsmPlan plan = plan_for(srs_rows, 3);
-  plan.warp_agg = 1;
-  ST(msm_dev(ctx, plan, srs_rows->Q, d_cols, d_o, 2, &pa));
+  ST(msm_prepared_dev(ctx, srs_rows, 3, 1, d_cols, d_o, 2, &pa));
   ST(copy_out(ctx, out_commitment, d_o, 3 * 96));
   ST(finish_call(ctx));
   return peer_check(ctx);
@@ -293,7 +291,7 @@ extern "C" vrfs_status vrfs_multi_msm_g1_prepared(vrfs_mctx* m, const vrfs_multi
       if (e != cudaSuccess) return mfail(m, VRFS_CUDA_ERROR, "device %d: cudaMemcpyAsync: %s", g, cudaGetErrorString(e));
     }
     MST(m, g, stage_out(ctx, BUF_OUT0, (size_t)96 * n_columns, &d_o));
-    MST(m, g, msm_dev(ctx, plan_for(h->part[g], n_columns), h->part[g]->Q, (const uint8_t*)d_s, d_o, 2, &pa));
+    MST(m, g, msm_prepared_dev(ctx, h->part[g], n_columns, 0, (const uint8_t*)d_s, d_o, 2, &pa));
     if (g == 0) MST(m, g, copy_out(ctx, out, d_o, (size_t)96 * n_columns));
   }
   return multi_finish(m);
@@ -318,9 +316,7 @@ extern "C" vrfs_status vrfs_multi_ring_commit(vrfs_mctx* m, const vrfs_multi_bas
     uint8_t *d_cols = nullptr, *d_o = nullptr;
     MST(m, g, ring_columns_dev(ctx, cnt, keyset_part_size, n_keys, (keys && n_keys > lo) ? keys + lo * 64 : nullptr, padding, n_tail, tail, &d_cols, lo, false));
     MST(m, g, stage_out(ctx, BUF_OUT0, 3 * 96, &d_o));
-    MsmPlan plan = plan_for(h->part[g], 3);
-    plan.warp_agg = 1;
-    MST(m, g, msm_dev(ctx, plan, h->part[g]->Q, d_cols, d_o, 2, &pa));
+    MST(m, g, msm_prepared_dev(ctx, h->part[g], 3, 1, d_cols, d_o, 2, &pa));
     if (g == 0) MST(m, g, copy_out(ctx, out_commitment, d_o, 3 * 96));
   }
   return multi_finish(m);

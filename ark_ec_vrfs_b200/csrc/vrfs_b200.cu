@@ -1450,7 +1450,17 @@ struct vrfs_msm_bases {
   MsmPlan plan;     // the plan that sized and filled Q (window bits c, windows); per-call plans keep its c
   int tpb_hint;     // 0 = automatic
   void* Q;          // windows * n affine points (96 B each; identity = zeros)
+  void* T;          // table mode (msm.cuh "TABLE mode"): 32 * n * 128 affine multiples, or nullptr (bucket mode)
 };
+#ifndef VRFS_TABLE_TERMS
+#define VRFS_TABLE_TERMS 4       // table entries per thread of k_msm_table_sum (sweep: profiles/r3e_table_shapes.log)
+#endif
+#ifndef VRFS_TABLE_BLOCKS_PER_SM
+#define VRFS_TABLE_BLOCKS_PER_SM 2
+#endif
+#ifndef VRFS_MSM_TABLE_MAX_N
+#define VRFS_MSM_TABLE_MAX_N 8192   // SRS sizes up to this get the multiples table by default (393 KB per base: 3.2 GB at 8192; 2^13 x 3: 0.50 vs 0.67 ms)
+#endif
 // the plan of one call on prepared bases: window size and count are the handle's (they fix the layout of Q), only the
 // column count (and with it the threads per bucket) is per call
 static MsmPlan plan_for(const vrfs_msm_bases* h, int n_columns) {
@@ -1517,6 +1527,32 @@ static vrfs_status msm_dev(vrfs_ctx* ctx, MsmPlan p, const void* d_bases, const 
   LAUNCHED_AS(ctx, "msm_final");
   return VRFS_OK;
 }
+// prepared MSM of n_columns scalar columns (device) over a handle: the multiples table when the handle has one, else the buckets
+static vrfs_status msm_prepared_dev(vrfs_ctx* ctx, const vrfs_msm_bases* h, int n_columns, int warp_agg, const uint8_t* d_scalars, uint8_t* d_out, int out_mode,
+                                    const PeerArgs* peer = nullptr) {
+  MsmPlan p = plan_for(h, n_columns);
+  p.warp_agg = warp_agg;
+  if (!h->T) return msm_dev(ctx, p, h->Q, d_scalars, d_out, out_mode, peer);
+  const size_t n = h->n, M = n * MSM_TABLE_WINDOWS;
+  // ~8 table entries per thread, at most two blocks per SM and column set (the block trees and the reduction grow with the blocks)
+  size_t bpc = (M + 128 * VRFS_TABLE_TERMS - 1) / (128 * VRFS_TABLE_TERMS);
+  const size_t cap = (size_t)ctx->sms * VRFS_TABLE_BLOCKS_PER_SM / (size_t)n_columns;
+  if (bpc > cap) bpc = cap;
+  if (bpc < 1) bpc = 1;
+  void* scratch = nullptr;
+  ST(ensure(ctx, BUF_SLAB, ((size_t)n_columns * bpc + n_columns) * sizeof(G1Pt), &scratch));
+  G1Pt* partials = (G1Pt*)scratch;
+  G1Pt* sums = partials + (size_t)n_columns * bpc;
+  k_msm_table_sum<<<dim3((unsigned)bpc, (unsigned)n_columns), 128, 0, ctx->stream>>>((uint32_t)n, (const G1Aff*)h->T, d_scalars, partials);
+  LAUNCHED_AS(ctx, "msm_table_sum");
+  k_msm_table_reduce<<<(unsigned)n_columns, 256, 0, ctx->stream>>>((int)bpc, partials, sums);
+  LAUNCHED_AS(ctx, "msm_table_reduce");
+  PeerArgs pa = {};
+  if (out_mode == 2) { if (!peer) return fail(ctx, VRFS_BAD_ARG, "internal: peer exchange without a peer group"); pa = *peer; }
+  k_msm_final2<<<(unsigned)n_columns, 32, 0, ctx->stream>>>(p, 1, sums, d_out, out_mode, pa);
+  LAUNCHED_AS(ctx, "msm_final");
+  return VRFS_OK;
+}
 // the stateless MSM over Montgomery affine bases on the device: GLV halves over [P | -phi(P)] (msm.cuh), then the bucket pipeline
 static vrfs_status msm_stateless_dev(vrfs_ctx* ctx, size_t n, int ncol, const void* d_aff, const uint8_t* d_scalars, uint8_t* d_out, int out_mode, int window_bits = 0) {
   void *bases2 = nullptr, *scalars2 = nullptr;
@@ -1573,10 +1609,18 @@ static vrfs_status msm_prepare_impl(vrfs_ctx* ctx, size_t n, const uint8_t* base
   ST(begin_call(ctx, n));
   vrfs_msm_bases* h = new (std::nothrow) vrfs_msm_bases();
   if (!h) return fail(ctx, VRFS_CUDA_ERROR, "out of host memory");
-  h->ctx = ctx; h->n = n; h->tpb_hint = threads_per_bucket; h->plan = msm_plan((uint32_t)n, 1, 1, window_bits, threads_per_bucket); h->Q = nullptr;
+  // no hint and a short SRS: the multiples table (window size 8); a window / thread hint asks for the bucket pipeline
+  const bool table_mode = window_bits == 0 && threads_per_bucket == 0 && n <= VRFS_MSM_TABLE_MAX_N;
+  if (table_mode) window_bits = MSM_TABLE_C;
+  h->ctx = ctx; h->n = n; h->tpb_hint = threads_per_bucket; h->plan = msm_plan((uint32_t)n, 1, 1, window_bits, threads_per_bucket); h->Q = nullptr; h->T = nullptr;
   if (h->plan.windows > MSM_MAX_WINDOWS) { delete h; return fail(ctx, VRFS_BAD_ARG, "internal: %d windows exceed MSM_MAX_WINDOWS", h->plan.windows); }
   cudaError_t e = cudaMalloc(&h->Q, (size_t)h->plan.windows * n * sizeof(G1Aff));
   if (e != cudaSuccess) { delete h; return fail(ctx, VRFS_CUDA_ERROR, "cudaMalloc of the prepared table failed: %s", cudaGetErrorString(e)); }
+  if (table_mode) {
+    if (h->plan.windows != MSM_TABLE_WINDOWS) { cudaFree(h->Q); delete h; return fail(ctx, VRFS_BAD_ARG, "internal: table mode expects %d windows", MSM_TABLE_WINDOWS); }
+    e = cudaMalloc(&h->T, (size_t)MSM_TABLE_WINDOWS * n * MSM_TABLE_D * sizeof(G1Aff));
+    if (e != cudaSuccess) { cudaGetLastError(); h->T = nullptr; }          // no room for the table: the bucket pipeline serves the handle
+  }
   // a failure below must not leak the table (up to GBs) nor hand out a half-built handle
   auto build = [&]() -> vrfs_status {
     const uint8_t* d_b; void* bases_m = nullptr;
@@ -1586,10 +1630,14 @@ static vrfs_status msm_prepare_impl(vrfs_ctx* ctx, size_t n, const uint8_t* base
     LAUNCHED_AS(ctx, "msm_prep_bases");
     k_msm_prepare<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((uint32_t)n, h->plan.c, h->plan.windows, (const G1Aff*)bases_m, (G1Aff*)h->Q);
     LAUNCHED_AS(ctx, "msm_prepare");
+    if (h->T) {
+      k_msm_table_build<<<(unsigned)(((size_t)MSM_TABLE_WINDOWS * n + 127) / 128), 128, 0, ctx->stream>>>((uint32_t)n, (const G1Aff*)h->Q, (G1Aff*)h->T);
+      LAUNCHED_AS(ctx, "msm_table_build");
+    }
     return finish_call(ctx);
   };
   vrfs_status st = build();
-  if (st != VRFS_OK) { cudaStreamSynchronize(ctx->stream); cudaFree(h->Q); delete h; return st; }
+  if (st != VRFS_OK) { cudaStreamSynchronize(ctx->stream); cudaFree(h->Q); if (h->T) cudaFree(h->T); delete h; return st; }
   ctx->prepared.push_back(h);
   *out = h;
   return VRFS_OK;
@@ -1614,6 +1662,7 @@ extern "C" void vrfs_msm_g1_release(vrfs_msm_bases* h) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (h->Q) cudaFree(h->Q);
+    if (h->T) cudaFree(h->T);
     auto& v = ctx->prepared;
     v.erase(std::remove(v.begin(), v.end(), h), v.end());
   }
@@ -1621,7 +1670,7 @@ extern "C" void vrfs_msm_g1_release(vrfs_msm_bases* h) {
 }
 static void orphan_prepared(vrfs_ctx* ctx) {      // called by vrfs_ctx_destroy (device set, stream synchronised)
   std::lock_guard<std::mutex> g(g_handles_mu);
-  for (vrfs_msm_bases* h : ctx->prepared) { if (h->Q) cudaFree(h->Q); h->Q = nullptr; h->ctx = nullptr; }
+  for (vrfs_msm_bases* h : ctx->prepared) { if (h->Q) cudaFree(h->Q); if (h->T) cudaFree(h->T); h->Q = nullptr; h->T = nullptr; h->ctx = nullptr; }
   ctx->prepared.clear();
 }
 static vrfs_status msm_prepared_host(vrfs_ctx* ctx, const vrfs_msm_bases* h, const uint8_t* scalars, int n_columns, uint8_t* out, int out_mode) {
@@ -1633,8 +1682,7 @@ static vrfs_status msm_prepared_host(vrfs_ctx* ctx, const vrfs_msm_bases* h, con
   const uint8_t* d_s; uint8_t* d_o;
   ST(stage_in(ctx, BUF_IN1, scalars, h->n * 32 * (size_t)n_columns, &d_s));
   ST(stage_out(ctx, BUF_OUT0, ob * n_columns, &d_o));
-  MsmPlan p = plan_for(h, n_columns);
-  ST(msm_dev(ctx, p, h->Q, d_s, d_o, out_mode));
+  ST(msm_prepared_dev(ctx, h, n_columns, 0, d_s, d_o, out_mode));
   ST(copy_out(ctx, out, d_o, ob * n_columns));
   return finish_call(ctx);
 }
@@ -1727,9 +1775,8 @@ extern "C" vrfs_status vrfs_ring_commit(vrfs_ctx* ctx, const vrfs_msm_bases* srs
     ST(ntt_dev(ctx, logn, 3, 1, d_cols, d_cols));
   }
   ST(stage_out(ctx, BUF_OUT0, 3 * 96, &d_o));
-  MsmPlan plan = plan_for(srs, 3);
-  plan.warp_agg = srs_is_lagrange ? 1 : 0;       // evaluation-form columns repeat the padding point and hold a 0/1 selector
-  ST(msm_dev(ctx, plan, srs->Q, d_cols, d_o, 0));
+  // (evaluation-form columns repeat the padding point and hold a 0/1 selector: the bucket pipeline aggregates its atomics per warp)
+  ST(msm_prepared_dev(ctx, srs, 3, srs_is_lagrange ? 1 : 0, d_cols, d_o, 0));
   ST(copy_out(ctx, out_commitment, d_o, 3 * 96));
   return finish_call(ctx);
 }
@@ -1743,9 +1790,7 @@ extern "C" vrfs_status vrfs_ring_commit_rows_partial(vrfs_ctx* ctx, const vrfs_m
   uint8_t *d_cols = nullptr, *d_o = nullptr;
   ST(ring_columns_dev(ctx, n, keyset_part_size, n_keys, keys_rows, padding, n_tail, tail, &d_cols, row_lo, false));
   ST(stage_out(ctx, BUF_OUT0, 3 * 144, &d_o));
-  MsmPlan plan = plan_for(srs_rows, 3);
-  plan.warp_agg = 1;
-  ST(msm_dev(ctx, plan, srs_rows->Q, d_cols, d_o, 1));
+  ST(msm_prepared_dev(ctx, srs_rows, 3, 1, d_cols, d_o, 1));
   ST(copy_out(ctx, out_partial, d_o, 3 * 144));
   return finish_call(ctx);
 }
@@ -1764,7 +1809,7 @@ extern "C" vrfs_status vrfs_ring_commit_delta(vrfs_ctx* ctx, const vrfs_msm_base
   k_ring_delta_columns<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((uint32_t)n, (uint32_t)n_keys, d_k, d_p, (uint8_t*)cols);
   LAUNCHED_AS(ctx, "ring_delta_columns");
   ST(stage_out(ctx, BUF_OUT0, 2 * 96, &d_o));
-  ST(msm_dev(ctx, plan_for(srs_lagrange, 2), srs_lagrange->Q, (const uint8_t*)cols, d_o, 0));
+  ST(msm_prepared_dev(ctx, srs_lagrange, 2, 0, (const uint8_t*)cols, d_o, 0));
   ST(copy_out(ctx, out_delta, d_o, 2 * 96));
   return finish_call(ctx);
 }

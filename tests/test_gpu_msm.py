@@ -223,6 +223,33 @@ def test_msm_exceptional_and_skewed_inputs(eng, window_bits):
         assert np.array_equal(eng.msm_g1(b, s, 3), exp)
 
 
+def test_msm_table_mode_digit_extremes(eng):
+    """short SRS: vrfs_msm_g1_prepare keeps the 128 multiples of every 2^(8w) P_i (table mode) and a commitment is the sum of the
+    entries the signed radix-256 digits select.  Scalars that sit on the digit boundaries (bytes 0x7f / 0x80 / 0xff, r - 1, values
+    above r that the scalar decode reduces), against the oracle and against the bucket pipeline (a window hint selects it)"""
+    R_MOD = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
+    n = 96
+    bases, sc = synth(n, 3, b"table")
+    special = [0, 1, R_MOD - 1, R_MOD - 2, 0x80, 0x7f, 0x81, 0xff, 0x100, 0x8000, 0x7fff, 0x8080, 1 << 254, (1 << 254) - 1,
+               int.from_bytes(b"\x80" * 31 + b"\x00", "little"), int.from_bytes(b"\x7f" * 31 + b"\x00", "little"),
+               int.from_bytes(b"\x80" * 31 + b"\x73", "little") % R_MOD, int.from_bytes(b"\xff" * 31 + b"\x72", "little")]
+    s = sc.copy()
+    for j, v in enumerate(special):
+        s[j] = np.frombuffer(v.to_bytes(32, "little"), np.uint8)
+        s[n + j] = np.frombuffer(((R_MOD - v) % R_MOD).to_bytes(32, "little"), np.uint8)
+    s[2 * n] = 0xff                                              # 2^256 - 1: not canonical, reduced mod r like the reference's scalar decode
+    s[2 * n + 1] = np.frombuffer((R_MOD + 5).to_bytes(32, "little"), np.uint8)
+    exp = O.msm_g1(bases, s, 3)
+    table = eng.msm_g1_prepare(bases)
+    buckets = eng.msm_g1_prepare(bases, window_bits=10)
+    try:
+        assert np.array_equal(table.msm(s, 3), exp)
+        assert np.array_equal(buckets.msm(s, 3), exp)
+        assert np.array_equal(table.msm(s[:n], 1), exp[:1])
+    finally:
+        table.release(); buckets.release()
+
+
 def test_fq381_inverse_on_the_gpu(eng):
     """fq381_inv_fast as compiled for the GPU: correct, and its word-approximation GCD finishes by itself (no fallback)"""
     P_MOD = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
