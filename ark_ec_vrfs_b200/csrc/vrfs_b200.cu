@@ -1459,7 +1459,7 @@ struct vrfs_msm_bases {
 #define VRFS_TABLE_BLOCKS_PER_SM 2
 #endif
 #ifndef VRFS_MSM_TABLE_MAX_N
-#define VRFS_MSM_TABLE_MAX_N 8192   // SRS sizes up to this get the multiples table by default (393 KB per base: 3.2 GB at 8192; 2^13 x 3: 0.50 vs 0.67 ms)
+#define VRFS_MSM_TABLE_MAX_N 16384  // SRS sizes up to this get the multiples table by default (393 KB per base: 0.8 GB at 2^11, 6.4 GB at 2^14; 3 columns: 2^13 0.50 vs 0.67 ms, 2^14 0.83 vs 0.93 ms with buckets)
 #endif
 // the plan of one call on prepared bases: window size and count are the handle's (they fix the layout of Q), only the
 // column count (and with it the threads per bucket) is per call

@@ -166,8 +166,8 @@ vrfs_status vrfs_msm_g1_bls12_381_ex(vrfs_ctx*, size_t n, const uint8_t* bases /
 /* Prepared bases: the counterpart of `RingContext` holding the SRS.  `prepare` stores 2^(c*w) * P_i for every window
  * once (device memory: ceil(256/c) * n * 96 bytes, affine); `prepared` then computes n_columns commitments with one shared
  * bucket set per column and no Horner chain.  Results are identical to vrfs_msm_g1_bls12_381. */
-/* Short SRS (n <= 8192, i.e. ring sizes up to 2^12) prepared WITHOUT hints also get the table of the 128 multiples of every
- * 2^(8w) P_i (393 KB of device memory per base: 0.8 GB at n = 2^11, 3.2 GB at 2^13); a commitment is then the plain sum of the
+/* Short SRS (n <= 16384, i.e. ring sizes up to 2^13) prepared WITHOUT hints also get the table of the 128 multiples of every
+ * 2^(8w) P_i (393 KB of device memory per base: 0.8 GB at n = 2^11, 6.4 GB at 2^14); a commitment is then the plain sum of the
  * table entries the scalars' signed radix-256 digits select - no sort, no buckets (2^11 x 3 columns: 0.25 ms instead of 0.36).
  * If that allocation fails the handle silently keeps the bucket pipeline.  A window_bits / threads_per_bucket hint
  * (vrfs_msm_g1_prepare_ex) selects the bucket pipeline explicitly. */
