@@ -370,7 +370,12 @@ def config_msm(eng, rank, world, peak_mac, hbm_peak, sizes, steps=5):
         h = eng.msm_g1_prepare(srs[:n])
         ref = h.msm(sc, 3)
         wall1, kt1 = timed_host_call(eng, lambda: h.msm(sc, 3), steps)
-        r = {"single_gpu": {"device_ms": sum(kt1.values()), "e2e_ms": wall1 * 1e3, "kernel_ms": {k: round(v, 4) for k, v in kt1.items()}}}
+        r = {"single_gpu": {"device_ms": sum(kt1.values()), "e2e_ms": wall1 * 1e3, "kernel_ms": {k: round(v, 4) for k, v in kt1.items()},
+                            "mode": "table (128 multiples of every 2^(8w) P_i, no buckets)" if "msm_table_sum" in kt1 else "buckets"}}
+        # the stateless entry point (the literal VariableBaseMSM::msm signature: bases uploaded and converted per call, GLV halves, Horner over the windows)
+        assert np.array_equal(eng.msm_g1(srs[:n], sc, 3), ref), "stateless MSM differs from the prepared one at 2^%d" % logn
+        walls, kts = timed_host_call(eng, lambda: eng.msm_g1(srs[:n], sc, 3), steps)
+        r["single_gpu"]["stateless_device_ms"] = sum(kts.values()); r["single_gpu"]["stateless_e2e_ms"] = walls * 1e3
         c = msm_window(logn)
         entries = 3 * n * ((255 + c) // c)
         acc_ms = kt1.get("msm_accumulate")
@@ -381,6 +386,18 @@ def config_msm(eng, rank, world, peak_mac, hbm_peak, sizes, steps=5):
             if peak_mac:
                 rl["frac_of_mac32_peak"] = rl["achieved_tmac32"] * 1e12 / peak_mac
                 r["single_gpu"]["whole_call_frac_of_mac32_peak"] = entries * 3000 / (sum(kt1.values()) * 1e-3) / peak_mac
+            if hbm_peak:
+                rl["frac_of_hbm_peak"] = rl["hbm_gbps"] / hbm_peak
+            r["single_gpu"]["roofline"] = rl
+        tab_ms = kt1.get("msm_table_sum")
+        if tab_ms:
+            # table mode: every non-zero signed radix-256 digit is one XYZZ mixed addition (10 x 300 MAC32) over a random 96-byte table record
+            ent = 3 * n * 32
+            rl = {"kernel": "k_msm_table_sum", "ms": tab_ms, "share_of_call": tab_ms / sum(kt1.values()), "mixed_additions": ent,
+                  "achieved_tmac32": ent * 3000 / (tab_ms * 1e-3) / 1e12, "hbm_gbps": ent * 96 / (tab_ms * 1e-3) / 1e9}
+            if peak_mac:
+                rl["frac_of_mac32_peak"] = rl["achieved_tmac32"] * 1e12 / peak_mac
+                r["single_gpu"]["whole_call_frac_of_mac32_peak"] = ent * 3000 / (sum(kt1.values()) * 1e-3) / peak_mac
             if hbm_peak:
                 rl["frac_of_hbm_peak"] = rl["hbm_gbps"] / hbm_peak
             r["single_gpu"]["roofline"] = rl
