@@ -157,7 +157,10 @@ vrfs_status vrfs_pedersen_verify_wire_batch(vrfs_ctx*, vrfs_suite, size_t n, con
 
 /* ring commitment MSM (ark-ec VariableBaseMSM::msm behind ring-proof's KZG commit):
  * n_columns scalar columns (column-major, n*32 bytes each) over one base vector of n affine G1 points.
- * out: n_columns * 96 bytes affine. */
+ * out: n_columns * 96 bytes affine.
+ * Precondition (what a `G1Affine` obtained by validated deserialisation guarantees): the bases lie in the prime-order subgroup G1.
+ * The stateless form splits every scalar with G1's endomorphism (k = k1 + q z^2 over [P | -phi(P)]), which equals the plain sum
+ * only there; vrfs_g1_decompress_batch(check_subgroup = 1) is the validating loader.  The prepared forms below use no endomorphism. */
 vrfs_status vrfs_msm_g1_bls12_381(vrfs_ctx*, size_t n, const uint8_t* bases /*n*96*/, const uint8_t* scalars /*n_columns*n*32*/,
                                   int n_columns, uint8_t* out /*n_columns*96*/);
 /* the same with a tuning hint: window_bits (0 = automatic, else 7..16).  The result never depends on it. */
@@ -290,7 +293,8 @@ vrfs_status vrfs_g1_decompress_batch(vrfs_ctx*, size_t n, const uint8_t* enc /*n
  * product's value.  Points are NOT subgroup-checked here. */
 vrfs_status vrfs_pairing_product_batch(vrfs_ctx*, size_t n, int n_pairs, const uint8_t* g1 /*n*n_pairs*96*/, const uint8_t* g2 /*n*n_pairs*192*/,
                                        const uint32_t* negate_masks /*n*/, uint8_t* out_ok /*n*/, uint8_t* out_gt /*n*576*/);
-/* k KZG openings (commitment C_i, point z_i, value v_i, proof W_i; scalars 32-byte LE, reduced mod r) checked at once against the
+/* (check_points 0 and 1 presume that C_i, W_i are in G1, as typed `G1Affine` values are; only level 2 detects a point of the curve outside it.)
+ * k KZG openings (commitment C_i, point z_i, value v_i, proof W_i; scalars 32-byte LE, reduced mod r) checked at once against the
  * verifier key (G2, [tau]G2) with aggregation coefficients r_i:  e(sum r_i (C_i - [v_i]G1 + [z_i]W_i), G2) = e(sum r_i W_i, [tau]G2).
  * One 2-column MSM over 2k+1 points + one product of two pairings.  check_points: 0 = C_i, W_i are typed values (already
  * validated), 1 = canonical + on the curve, 2 = also in the prime-order subgroup (what CanonicalDeserialize validates).
