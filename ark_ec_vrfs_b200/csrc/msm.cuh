@@ -14,14 +14,13 @@
 //   k_msm_accumulate_big  one block per oversized bucket (top window / skewed scalar columns such as ring selectors)
 //   k_msm_rc / k_msm_wbits segment value sum_j j*B_j: row / column sums of the bucket matrix, then the two short weighted sums bit by bit
 //   k_msm_final2          one warp per column: Horner over the windows (stateless mode only); partial or affine out
-// Stateless mode (vrfs_msm_g1_bls12_381): segment = (column, window).  Prepared mode (vrfs_msm_g1_prepare + _prepared,
-// the analogue of RingContext holding the SRS): segment = column, no Horner chain (255 dependent doublings ~ 2.5 ms).
+// Stateless mode (vrfs_msm_g1_bls12_381): segment = (column, window) over the GLV halves of the scalars (2n bases [P | -phi(P)],
+// 128-bit scalars: half the windows, a Horner chain of 128 doublings).  Prepared mode (vrfs_msm_g1_prepare + _prepared, the analogue of
+// RingContext holding the SRS): segment = column, no Horner chain; short SRS (n <= 2^14) skip the whole bucket pipeline for a table of
+// the 128 multiples of every 2^(8w) P_i ("TABLE mode" below: k_msm_table_build / _sum / _reduce).
 #pragma once
 #include "lincomb.cuh"
 #include "gen/ntt_consts.cuh"
-#ifdef __CUDACC__
-#include <cooperative_groups.h>
-#endif
 
 namespace vrfs {
 
@@ -842,7 +841,7 @@ __global__ void __launch_bounds__(128) k_msm_rc(MsmPlan p, const G1Pt* buckets, 
 // msm_wbits(p) results of every part.  No cluster barriers and no chain longer than log2(nb) doublings: 0.04 ms where the
 // halving recursion W(x) = W(y) + sum_u x_{2u+1}, y_u = 2 (x_{2u} + x_{2u+1}) run by an 8-block cluster (round 1; in the history) took
 // 0.10 ms (m = 16 / 32 at N = 2^11), and 0.08 instead of 0.17 ms at N = 2^17.
-#define MSM_WBITS 10                                       // weights <= 512 < 2^10
+// (weights <= 512 < 2^10: at most ten results per weighted sum)
 VRFS_HD inline int msm_wbits(const MsmPlan& p) {           // bits of the largest weight of a plan's weighted sums
   const int wmax = p.rc_h ? p.rc_h : p.nb;                 // columns / buckets carry weights 1 .. H (or nb); rows 0 .. R - 1 < H
   int b = 0; while ((1 << b) <= wmax) b++;

@@ -658,8 +658,6 @@ def self_check(segs, macro):
     print("lane programs == twin == oracle (2 random products, 1 cancelling product)")
 
 
-def limbs13(x): return ", ".join("0x%08xu" % ((x >> (32 * i)) & 0xFFFFFFFF) for i in range(13))
-
 def main():
     segs, order, macro = build_all()
     tot_steps = sum(len(segs[nm]["steps"]) for nm in macro)
