@@ -34,6 +34,7 @@ LANES = int(os.environ.get("PAIRING_LANES", "64"))   # 64: two warps per product
 NPAIRS = 2
 SCHED_LIN_FIRST = int(os.environ.get("SCHED_LIN_FIRST", "1"))
 MILLER_GROUP = int(os.environ.get("PAIRING_MILLER_GROUP", "4"))     # Miller iterations per segment
+CYC_RUNS = [int(x) for x in os.environ.get("PAIRING_CYC_RUNS", "1").split(",")]     # cyclotomic squarings per segment (1 must be present; 1,2,4 measured: no fewer steps)
 
 NOP, MUL, ADD, SUB, HALF, INV = 0, 1, 2, 3, 4, 5
 IN = 9                       # pseudo-kind: a value that already sits in a pinned register
@@ -295,7 +296,11 @@ def seg_easy(t):
     m = f12_mul(f12_frob(r, 2, C), r)
     fm = flat12(m)
     return list(zip(fm, BLOCKS["M"])) + list(zip(fm, BLOCKS["X"])) + list(zip(fm, BLOCKS["B"]))
-def seg_cyc(t): return list(zip(flat12(f12_cyc_sqr(blk12(t, BLOCKS["X"]))), BLOCKS["X"]))
+def seg_cyc(t, times=1):
+    """X <- X^(2^times) by Granger-Scott squarings (several per segment: the sums after one squaring merge with those before the next)"""
+    x = blk12(t, BLOCKS["X"])
+    for _ in range(times): x = f12_cyc_sqr(x)
+    return list(zip(flat12(x), BLOCKS["X"]))
 def seg_mulb(t): return list(zip(flat12(f12_mul(blk12(t, BLOCKS["X"]), blk12(t, BLOCKS["B"]))), BLOCKS["X"]))
 def seg_glue(t, other, dst, how):
     """dst = conj(X) * g(other) with g = conj / frob1; X = B = dst   (conj(X) = other^x after the square-and-multiply loop)"""
@@ -325,7 +330,7 @@ LINC_K = int(os.environ.get("PAIRING_LINC_K", "8"))       # sources per sum; eve
 LINC_MAXW = 60                                               # bound on sum |coefficient| of one sum (range of the quotient estimate)
 COST2 = {K_MUL: 10.0, K_LINC: 3.0, K_HALF: 1.0, K_INV: 400.0, IN: 0.0}
 
-def lower(t, outs):
+def lower(t, outs, name=""):
     sys.setrecursionlimit(100000)
     n = len(t.kind)
     is_lin = lambda i: t.kind[i] in (ADD, SUB)
@@ -404,6 +409,7 @@ def lower(t, outs):
                     if f + fields(c) <= LINC_K and w + abs(c) <= LINC_MAXW and (a not in emitted or True):
                         grp[a] = c; f += fields(c); w += abs(c)
                     else: rest.append((a, c))
+                assert len(grp) >= 2, "a sum of %s cannot be cut (one coefficient above LINC_MAXW?)" % name
                 sid = n + len(syn)
                 syn[sid] = grp; depth[sid] = term_depth(grp)
                 items = rest + [(sid, 1)]
@@ -453,7 +459,7 @@ def lower(t, outs):
 def compile_segment(name, build, nreg_cap=512):
     t = Trace()
     outs = build(t)                                   # [(E, pinned reg)]
-    g = lower(t, outs)
+    g = lower(t, outs, name)
     ids = sorted(g)
     users = {i: [] for i in ids}
     for i in ids:
@@ -615,17 +621,24 @@ def build_all():
         if name not in segs: add(name, lambda t, grp=grp, first=(i0 == 0): seg_miller(t, grp, first))
         macro.append(name)
     add("easy", seg_easy)
-    add("cyc", seg_cyc)
+    for k in CYC_RUNS: add("cyc%d" % k, lambda t, k=k: seg_cyc(t, k))
     add("mulb", seg_mulb)
     add("glue_a", lambda t: seg_glue(t, "M", "A", "conj"))
     add("glue_b", lambda t: seg_glue(t, "A", "BV", "conj"))
     add("glue_c", lambda t: seg_glue(t, "BV", "CV", "frob1"))
     add("xx", seg_xx)
     add("last", seg_last)
-    expx = []
+    expx, run = [], 0
+    def flush(run):
+        while run:                                     # a run of squarings as the largest segments available
+            k = max(c for c in CYC_RUNS if c <= run)
+            expx.append("cyc%d" % k); run -= k
     for b in bits:
-        expx.append("cyc")
-        if b: expx.append("mulb")
+        run += 1
+        if b:
+            flush(run); run = 0
+            expx.append("mulb")
+    flush(run)
     macro += ["easy"] + expx + ["glue_a"] + expx + ["glue_b"] + expx + ["glue_c"] + expx + ["xx"] + expx + ["last"]
     return segs, order, macro
 
