@@ -31,6 +31,9 @@ using namespace vrfs;
 #ifndef LINCOMB_MINBLOCKS
 #define LINCOMB_MINBLOCKS 2
 #endif
+#ifndef VRFS_PAIR_WAVES
+#define VRFS_PAIR_WAVES 6                // verify batches below this many resident waves run both linear combinations in one grid (0 = never)
+#endif
 #ifndef VRFS_SPLIT_ITEMS_PER_SM
 #define VRFS_SPLIT_ITEMS_PER_SM 256      // a verify batch of up to this many items per SM runs its two linear combinations on two streams
 #endif
@@ -64,6 +67,37 @@ __global__ void __launch_bounds__(LINCOMB_THREADS, LINCOMB_MINBLOCKS) k_lincomb(
       bool ok = lincomb_item<C, NV, NF>(A, item, slab, acc);
       Grp<C>::store_xyz(A.out_xyz + (size_t)item * 24, acc);
       if (A.valid != nullptr && !ok) A.valid[item] = 0;
+    }
+    __syncwarp();
+  }
+}
+
+// Both linear combinations of a verify batch in ONE grid: U = s*G - c*Y (<1,1>) and V = s*I - c*O (<2,0>) as 2 * ceil(n/32) warp
+// tasks handed out from one counter, the long ones (V) first.  A mid-size batch - what one GPU gets when a caller spreads 2^20 items
+// over eight - is 1.7 resident waves of each kernel: two launches round that up to 2 + 2 half-empty waves, one task queue does not.
+template <class C>
+__global__ void __launch_bounds__(LINCOMB_THREADS, LINCOMB_MINBLOCKS) k_lincomb_verify_pair(LincombArgs U, LincombArgs V) {
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31u;
+  typename Grp<C>::Entry* slab = reinterpret_cast<typename Grp<C>::Entry*>(V.slab + (size_t)tid * slab_bytes<C>(2));
+  const uint32_t groups = (V.n + 31u) / 32u;
+  for (;;) {
+    uint32_t task = 0;
+    if (lane == 0) task = atomicAdd(V.next_item, 1u);
+    task = __shfl_sync(0xffffffffu, task, 0);
+    if (task >= 2u * groups) break;
+    const bool is_v = task < groups;                      // warp-uniform
+    const uint32_t item = (is_v ? task : task - groups) * 32u + lane;
+    if (item < V.n) {
+      typename Grp<C>::Pt acc;
+      if (is_v) {
+        const bool ok = lincomb_item<C, 2, 0>(V, item, slab, acc);
+        Grp<C>::store_xyz(V.out_xyz + (size_t)item * 24, acc);
+        if (V.valid != nullptr && !ok) V.valid[item] = 0;
+      } else {
+        const bool ok = lincomb_item<C, 1, 1>(U, item, slab, acc);
+        Grp<C>::store_xyz(U.out_xyz + (size_t)item * 24, acc);
+        if (U.valid != nullptr && !ok) U.valid[item] = 0;
+      }
     }
     __syncwarp();
   }
@@ -461,6 +495,24 @@ static vrfs_status launch_lincomb(vrfs_ctx* ctx, LincombArgs A, bool side = fals
   return VRFS_OK;
 }
 
+template <class C>
+static vrfs_status launch_lincomb_verify_pair(vrfs_ctx* ctx, LincombArgs U, LincombArgs V) {
+  int per_sm = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lincomb_verify_pair<C>, LINCOMB_THREADS, 0));
+  if (per_sm < 1) per_sm = 1;
+  uint32_t blocks = (uint32_t)(ctx->sms * per_sm);
+  const uint32_t need = (2u * V.n + LINCOMB_THREADS - 1) / LINCOMB_THREADS;
+  if (blocks > need) blocks = need;
+  void* slab = nullptr;
+  ST(ensure(ctx, BUF_SLAB, (size_t)blocks * LINCOMB_THREADS * slab_bytes<C>(2) + 256, &slab));
+  U.slab = V.slab = (uint8_t*)slab;
+  U.next_item = V.next_item = reinterpret_cast<uint32_t*>((uint8_t*)slab + (size_t)blocks * LINCOMB_THREADS * slab_bytes<C>(2));
+  CU(cudaMemsetAsync(V.next_item, 0, sizeof(uint32_t), ctx->stream));
+  k_lincomb_verify_pair<C><<<blocks, LINCOMB_THREADS, 0, ctx->stream>>>(U, V);
+  LAUNCHED_AS(ctx, "lincomb<1,1>+<2,0>");
+  return VRFS_OK;
+}
+
 // =================================================================================================
 // ietf verify
 // =================================================================================================
@@ -482,6 +534,21 @@ static vrfs_status ietf_verify_dev(vrfs_ctx* ctx, size_t n, const uint8_t* pk, c
   // (overlapping the two launches of a LARGE batch the same way was measured at +0.3 %: not worth losing per-kernel timing)
   const bool split = n <= (size_t)ctx->sms * VRFS_SPLIT_ITEMS_PER_SM;
   const uint32_t cbits = S::CLEN < 32 ? 8u * S::CLEN : 0u;     // a CHALLENGE_LEN-byte challenge: half of its windows are empty
+  // mid-size batches (between the two-stream case and VRFS_PAIR_WAVES resident waves): one grid for both combinations
+  if (!split && VRFS_PAIR_WAVES > 0 && n < (size_t)ctx->sms * LINCOMB_THREADS * LINCOMB_MINBLOCKS * VRFS_PAIR_WAVES) {
+    LincombArgs U = A, V = A;
+    U.var[0] = {pk, 64, c, 32, 1, cbits};
+    U.fix[0] = {s, 32, 0, ctx->fixtab[S::ID][0]};
+    U.out_xyz = (uint32_t*)u;
+    V.var[0] = {input, 64, s, 32, 0, 0};
+    V.var[1] = {output, 64, c, 32, 1, cbits};
+    V.out_xyz = (uint32_t*)v;
+    ST((launch_lincomb_verify_pair<C>(ctx, U, V)));
+    k_ietf_verify_finish<S><<<(unsigned)((n + 128 * FINISH_K - 1) / (128 * FINISH_K)), 128, 0, ctx->stream>>>((uint32_t)n, pk, input, output, c, (const uint32_t*)u,
+                                                                                  (const uint32_t*)v, ad, ad_off, (const uint8_t*)valid, out_ok, out_status);
+    LAUNCHED_AS(ctx, "ietf_verify_finish");
+    return VRFS_OK;
+  }
   // U = s*G - c*Y
   A.var[0] = {pk, 64, c, 32, 1, cbits};
   A.fix[0] = {s, 32, 0, ctx->fixtab[S::ID][0]};
