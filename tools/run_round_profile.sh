@@ -14,10 +14,11 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 # full-set capture of the two lincomb kernels of one verify step
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_lincomb -s 8 -c 2 -f -o /tmp/${tag}_lincomb python bench.py --steps 1 --warmup 3 --headline-only --no-cpu-baseline > gpurun_out/${tag}_lincomb_ncu.log 2>&1
 ncu -i /tmp/${tag}_lincomb.ncu-rep --page raw --csv > gpurun_out/${tag}_lincomb_raw.csv 2>/dev/null
-for logn in 17 11; do
-  MSM_LOGN=$logn timeout 600 ncu --set full --clock-control none -k regex:k_msm -s 12 -c 12 -f -o /tmp/${tag}_msm_$logn python tools/msm_profile_run.py > gpurun_out/${tag}_msm_${logn}_ncu.log 2>&1
-  ncu -i /tmp/${tag}_msm_$logn.ncu-rep --page raw --csv > gpurun_out/${tag}_msm_${logn}_raw.csv 2>/dev/null
-done
+# MSM: the second call of tools/msm_profile_run.py.  2^17 = bucket pipeline (3 preparation + 9 kernels per call), 2^11 = table mode (3 + 3 per call)
+MSM_LOGN=17 timeout 600 ncu --set full --clock-control none -k regex:k_msm -s 12 -c 9 -f -o /tmp/${tag}_msm_17 python tools/msm_profile_run.py > gpurun_out/${tag}_msm_17_ncu.log 2>&1
+ncu -i /tmp/${tag}_msm_17.ncu-rep --page raw --csv > gpurun_out/${tag}_msm_17_raw.csv 2>/dev/null
+MSM_LOGN=11 timeout 600 ncu --set full --clock-control none -k regex:k_msm -s 6 -c 3 -f -o /tmp/${tag}_msm_11 python tools/msm_profile_run.py > gpurun_out/${tag}_msm_11_ncu.log 2>&1
+ncu -i /tmp/${tag}_msm_11.ncu-rep --page raw --csv > gpurun_out/${tag}_msm_11_raw.csv 2>/dev/null
 timeout 300 ncu --set full --clock-control none -k regex:k_pairing_products_lanes -s 1 -c 1 -f -o /tmp/${tag}_pairing python tools/pairing_one.py > gpurun_out/${tag}_pairing_ncu.log 2>&1
 ncu -i /tmp/${tag}_pairing.ncu-rep --page raw --csv > gpurun_out/${tag}_pairing_raw.csv 2>/dev/null
 ls -la gpurun_out | tail -20
