@@ -723,13 +723,15 @@ __device__ __forceinline__ void msm_accumulate_entries(G1Pt& out, const void* ba
 #define MSM_ACC_MINBLOCKS 4   // 128 registers: 16 warps/SM instead of 8 (measured 4.59 -> 4.17 ms at 2^17 x 3)
 #endif
 template <bool PREP>
+// (b_begin, b_end): the range of buckets this launch covers - large calls run the last buckets as a second launch with more threads per
+// bucket on a side stream, so that the slots the main launch frees while it drains are filled with SHORT tasks (msm_dev)
 __global__ void __launch_bounds__(128, MSM_ACC_MINBLOCKS) k_msm_accumulate(MsmPlan p, const void* bases, const uint32_t* counts, const uint32_t* offsets,
-                                                         const uint32_t* list, G1Pt* buckets) {
+                                                         const uint32_t* list, G1Pt* buckets, size_t b_begin, size_t b_end) {
   __shared__ uint4 sh_raw[128 * sizeof(G1Pt) / 16];
   G1Pt* sh = reinterpret_cast<G1Pt*>(sh_raw);
-  const size_t total = (size_t)p.ncol * p.seg_windows * p.nb;
+  const size_t total = b_end;
   const uint32_t lane = threadIdx.x % p.tpb;
-  const size_t b = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) / p.tpb;
+  const size_t b = b_begin + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) / p.tpb;
   const bool live = b < total;
   uint32_t cnt = live ? counts[b] : 0u;
   if (cnt > p.big) cnt = 0;                       // handled by the big path (which also writes the bucket)

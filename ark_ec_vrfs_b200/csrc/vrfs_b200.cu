@@ -31,6 +31,9 @@ using namespace vrfs;
 #ifndef LINCOMB_MINBLOCKS
 #define LINCOMB_MINBLOCKS 2
 #endif
+#ifndef VRFS_MSM_TAIL_16THS
+#define VRFS_MSM_TAIL_16THS 2            // sixteenths of the buckets of a large STATELESS MSM accumulated by the short-task tail launch (0 = off)
+#endif
 #ifndef VRFS_PAIR_WAVES
 #define VRFS_PAIR_WAVES 6                // verify batches below this many resident waves run both linear combinations in one grid (0 = never)
 #endif
@@ -1561,17 +1564,40 @@ static vrfs_status msm_dev(vrfs_ctx* ctx, MsmPlan p, const void* d_bases, const 
   LAUNCHED_AS(ctx, "msm_scan");
   k_msm_scatter<<<tsc, 128, 0, ctx->stream>>>(p, d_scalars, offsets, cursors, (uint32_t*)list);
   LAUNCHED_AS(ctx, "msm_scatter");
-  const unsigned ab = (unsigned)((nbuckets * p.tpb + 127) / 128);
   const unsigned bigb = (unsigned)(ctx->sms * 4);
-  if (p.prepared) {
-    k_msm_accumulate<true><<<ab, 128, 0, ctx->stream>>>(p, d_bases, (const uint32_t*)counts, offsets, (const uint32_t*)list, (G1Pt*)buckets);
-    LAUNCHED_AS(ctx, "msm_accumulate");
-    k_msm_accumulate_big<true><<<bigb, MSM_BIG_THREADS, 0, ctx->stream>>>(p, d_bases, (const uint32_t*)counts, offsets, (const uint32_t*)list, big_list, big_count, bigpart);
-  } else {
-    k_msm_accumulate<false><<<ab, 128, 0, ctx->stream>>>(p, d_bases, (const uint32_t*)counts, offsets, (const uint32_t*)list, (G1Pt*)buckets);
-    LAUNCHED_AS(ctx, "msm_accumulate");
-    k_msm_accumulate_big<false><<<bigb, MSM_BIG_THREADS, 0, ctx->stream>>>(p, d_bases, (const uint32_t*)counts, offsets, (const uint32_t*)list, big_list, big_count, bigpart);
+  // Large calls (several resident waves of 4 blocks per SM): the main launch takes the first buckets, the last VRFS_MSM_TAIL_16THS
+  // sixteenths run as a second launch with 4 x the threads per bucket on the side stream.  Its tasks are 4 x shorter and start as
+  // the main launch drains, so the end of the accumulation is not one long task per idle SM.
+  size_t b_main = nbuckets;
+  MsmPlan pt = p;
+  // (measured, profiles/r3i_msm_tail_ab.log: the stateless mode gains 3-7 % at 2^16 / 2^17 - its (column, window) segments load their
+  //  buckets unevenly -, the prepared mode LOSES 4 % at 2^17 - uniform buckets, and the tail's deeper trees cost more than they save)
+  if (VRFS_MSM_TAIL_16THS > 0 && !p.prepared && p.tpb * 4 <= 32 && nbuckets * p.tpb > (size_t)ctx->sms * 4 * 128 * 2) {
+    b_main = nbuckets / 16 * (16 - VRFS_MSM_TAIL_16THS);
+    b_main -= b_main % (128 / p.tpb);                               // whole blocks
+    pt.tpb = p.tpb * 4;
   }
+  const unsigned ab = (unsigned)((b_main * p.tpb + 127) / 128);
+  const unsigned ab_tail = (unsigned)(((nbuckets - b_main) * pt.tpb + 127) / 128);
+  if (ab_tail) {
+    CU(cudaEventRecord(ctx->ev_chunk[2], ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_chunk[2], 0));
+  }
+  if (p.prepared) {
+    k_msm_accumulate<true><<<ab, 128, 0, ctx->stream>>>(p, d_bases, (const uint32_t*)counts, offsets, (const uint32_t*)list, (G1Pt*)buckets, (size_t)0, b_main);
+    if (ab_tail) k_msm_accumulate<true><<<ab_tail, 128, 0, ctx->copy_stream>>>(pt, d_bases, (const uint32_t*)counts, offsets, (const uint32_t*)list, (G1Pt*)buckets, b_main, nbuckets);
+  } else {
+    k_msm_accumulate<false><<<ab, 128, 0, ctx->stream>>>(p, d_bases, (const uint32_t*)counts, offsets, (const uint32_t*)list, (G1Pt*)buckets, (size_t)0, b_main);
+    if (ab_tail) k_msm_accumulate<false><<<ab_tail, 128, 0, ctx->copy_stream>>>(pt, d_bases, (const uint32_t*)counts, offsets, (const uint32_t*)list, (G1Pt*)buckets, b_main, nbuckets);
+  }
+  if (ab_tail) {
+    CU(cudaEventRecord(ctx->ev_chunk[3], ctx->copy_stream));
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[3], 0));
+    ctx->launches++;
+  }
+  LAUNCHED_AS(ctx, "msm_accumulate");
+  if (p.prepared) k_msm_accumulate_big<true><<<bigb, MSM_BIG_THREADS, 0, ctx->stream>>>(p, d_bases, (const uint32_t*)counts, offsets, (const uint32_t*)list, big_list, big_count, bigpart);
+  else k_msm_accumulate_big<false><<<bigb, MSM_BIG_THREADS, 0, ctx->stream>>>(p, d_bases, (const uint32_t*)counts, offsets, (const uint32_t*)list, big_list, big_count, bigpart);
   LAUNCHED_AS(ctx, "msm_accumulate_big");
   k_msm_big_combine<<<bigb, MSM_BIG_THREADS, 0, ctx->stream>>>(big_list, big_count, bigpart, (G1Pt*)buckets);
   LAUNCHED_AS(ctx, "msm_big_combine");
