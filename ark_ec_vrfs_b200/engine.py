@@ -279,12 +279,14 @@ class Engine:
         self._call("vrfs_ietf_sign_wire_batch", suite, C.c_size_t(n), _p(sk), _p(data), _p(doff), _p(adb), _p(off), _p(sig), _p(ok))
         return sig, ok
 
-    def ietf_verify_wire(self, suite, pk_enc, datas, sig, ad=None, want_hash=True, status=False):
+    def ietf_verify_wire(self, suite, pk_enc, datas, sig, ad=None, want_hash=True, status=False, out_ok=None, out_hash=None):
         """serialised public keys + VRF input data + signatures -> (ok, beta) with beta = Output::hash of accepted items
-        (status=True appends the per-item vrfs_item_status)."""
+        (status=True appends the per-item vrfs_item_status).  out_ok / out_hash: caller-owned result arrays (page-locked ones
+        make the device -> host copies asynchronous and full speed)."""
         pk_enc = _u8(pk_enc, (-1, self.point_enc_len(suite))); n = len(pk_enc)
         sig = _u8(sig, (n, self.ietf_signature_len(suite))); data, doff = pack_var(datas, n); adb, off = pack_var(ad, n)
-        ok = np.zeros(n, np.uint8); h = np.zeros((n, self.hash_len(suite)), np.uint8) if want_hash else None
+        ok = _u8(out_ok, (n,)) if out_ok is not None else np.zeros(n, np.uint8)
+        h = (_u8(out_hash, (n, self.hash_len(suite))) if out_hash is not None else np.zeros((n, self.hash_len(suite)), np.uint8)) if want_hash else None
         st = np.zeros(n, np.uint8) if status else None
         self._call("vrfs_ietf_verify_wire_batch", suite, C.c_size_t(n), _p(pk_enc), _p(data), _p(doff), _p(sig), _p(adb), _p(off), _p(ok), _p(h), _p(st))
         res = (ok, h) if want_hash else (ok,)

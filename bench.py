@@ -481,9 +481,13 @@ def config_wire(eng, n):
     sig, ok = eng.ietf_sign_wire(vrfs.BANDERSNATCH, sk, datas)
     assert ok.all()
     sig[::64, 40] ^= 1
+    # page-locked host buffers in and out (as the headline's e2e leg): pageable ones make every copy a staged, synchronous one
+    pk_enc, sig = pinned(pk_enc), pinned(sig)
+    datas = (pinned(datas[0]), pinned(datas[1].view(np.uint8)).view(np.uint64))
+    out_ok, out_hash = pinned_zeros((n,)), pinned_zeros((n, 64))
     best = None
     for _ in range(3):
-        t0 = time.perf_counter(); okv, beta = eng.ietf_verify_wire(vrfs.BANDERSNATCH, pk_enc, datas, sig); dt = time.perf_counter() - t0
+        t0 = time.perf_counter(); okv, beta = eng.ietf_verify_wire(vrfs.BANDERSNATCH, pk_enc, datas, sig, out_ok=out_ok, out_hash=out_hash); dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
     assert int(okv.sum()) == n - n // 64
     return {"what": "Bandersnatch: serialised keys + input data + 96-byte signatures (host) -> verdicts + 64-byte VRF outputs, %d items, 1/64 corrupted" % n,
