@@ -882,6 +882,34 @@ static vrfs_status stage_secret(vrfs_ctx* ctx, int which, const void* host, size
   mark_secret(ctx, which, bytes);
   return stage_in(ctx, which, host, bytes, dev);
 }
+// Host inputs of a large batch call in TWO pieces - one resident wave of the lincomb grid, then the rest - copied on the copy stream:
+// the second piece (93 % of a 2^20 batch) travels while the first one computes, as vrfs_ietf_verify_batch does for its inputs.
+// The caller runs its device function per piece after cudaStreamWaitEvent(stream, ev_chunk[k]).
+struct HostIn { int buf; const void* host; size_t stride; bool secret; uint8_t* dev; };
+static vrfs_status stage_in_pieces(vrfs_ctx* ctx, size_t n, HostIn* in, int nin, size_t cut[3], int* pieces) {
+  const size_t wave = (size_t)ctx->sms * LINCOMB_MINBLOCKS * LINCOMB_THREADS;
+  cut[0] = 0; cut[1] = n > 3 * wave ? wave : n; cut[2] = n;
+  *pieces = cut[1] < n ? 2 : 1;
+  for (int j = 0; j < nin; j++) {
+    void* d = nullptr;
+    ST(ensure(ctx, in[j].buf, n * in[j].stride, &d));
+    in[j].dev = (uint8_t*)d;
+    if (in[j].secret) mark_secret(ctx, in[j].buf, n * in[j].stride);
+  }
+  for (int k = 0; k < *pieces; k++) {
+    const size_t o = cut[k], m = cut[k + 1] - cut[k];
+    for (int j = 0; j < nin; j++)
+      CU(cudaMemcpyAsync(in[j].dev + o * in[j].stride, (const uint8_t*)in[j].host + o * in[j].stride, m * in[j].stride, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CU(cudaEventRecord(ctx->ev_chunk[k], ctx->copy_stream));
+  }
+  return VRFS_OK;
+}
+static vrfs_status piece_ready(vrfs_ctx* ctx, int k) {
+  CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[k], 0));
+  // kernel timing: the first kernel's interval starts after its inputs arrived, not at the start of the call
+  if (ctx->timing && ctx->tev[0] && ctx->n_timed == 0) CU(cudaEventRecord(ctx->tev[0], ctx->stream));
+  return VRFS_OK;
+}
 // batched inversion of the Z coordinates of NP projective results per item (k_zinv): returns the device array of n x 8 words
 template <class C, int NP> static vrfs_status launch_zinv(vrfs_ctx* ctx, size_t n, const void* p0, const void* p1, const void* p2, const uint32_t** out) {
   void* z = nullptr;
@@ -942,12 +970,18 @@ extern "C" vrfs_status vrfs_ietf_prove_batch(vrfs_ctx* ctx, vrfs_suite suite, si
   if (!sk || !input || !output || !out_c || !out_s) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite >= VRFS_SUITE_COUNT) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
   ST(begin_call(ctx, n));
-  const uint8_t *d_sk, *d_in, *d_out, *d_ad; const uint64_t* d_off; uint8_t *d_c, *d_s;
-  ST(stage_secret(ctx, BUF_IN0, sk, n * 32, &d_sk)); ST(stage_in(ctx, BUF_IN1, input, n * 64, &d_in)); ST(stage_in(ctx, BUF_IN2, output, n * 64, &d_out));
+  const uint8_t* d_ad; const uint64_t* d_off; uint8_t *d_c, *d_s;
+  HostIn in[3] = {{BUF_IN0, sk, 32, true, nullptr}, {BUF_IN1, input, 64, false, nullptr}, {BUF_IN2, output, 64, false, nullptr}};
+  size_t cut[3]; int pieces = 1;
+  ST(stage_in_pieces(ctx, n, in, 3, cut, &pieces));
   ST(stage_ad(ctx, n, ad, ad_off, &d_ad, &d_off));
   ST(stage_out(ctx, BUF_OUT0, n * 32, &d_c)); ST(stage_out(ctx, BUF_OUT1, n * 32, &d_s));
-  vrfs_status st = with_suite(ctx, suite, [&](auto S_) { typedef decltype(S_) S; return ietf_prove_dev<S>(ctx, n, d_sk, d_in, d_out, d_ad, d_off, d_c, d_s); });
-  ST(st);
+  for (int k = 0; k < pieces; k++) {
+    const size_t o = cut[k], m = cut[k + 1] - cut[k];
+    ST(piece_ready(ctx, k));
+    ST(with_suite(ctx, suite, [&](auto S_) { typedef decltype(S_) S;
+      return ietf_prove_dev<S>(ctx, m, in[0].dev + o * 32, in[1].dev + o * 64, in[2].dev + o * 64, d_ad, d_off ? d_off + o : nullptr, d_c + o * 32, d_s + o * 32); }));
+  }
   ST(copy_out(ctx, out_c, d_c, n * 32)); ST(copy_out(ctx, out_s, d_s, n * 32));
   return finish_call(ctx);
 }
@@ -1128,12 +1162,19 @@ extern "C" vrfs_status vrfs_pedersen_prove_batch(vrfs_ctx* ctx, vrfs_suite suite
   if (!sk || !input || !output || !out_proof || !out_blinding) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite >= VRFS_SUITE_COUNT) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
   ST(begin_call(ctx, n));
-  const uint8_t *d_sk, *d_in, *d_out, *d_ad; const uint64_t* d_off; uint8_t *d_pr, *d_bl;
-  ST(stage_secret(ctx, BUF_IN0, sk, n * 32, &d_sk)); ST(stage_in(ctx, BUF_IN1, input, n * 64, &d_in)); ST(stage_in(ctx, BUF_IN2, output, n * 64, &d_out));
+  const uint8_t* d_ad; const uint64_t* d_off; uint8_t *d_pr, *d_bl;
+  HostIn in[3] = {{BUF_IN0, sk, 32, true, nullptr}, {BUF_IN1, input, 64, false, nullptr}, {BUF_IN2, output, 64, false, nullptr}};
+  size_t cut[3]; int pieces = 1;
+  ST(stage_in_pieces(ctx, n, in, 3, cut, &pieces));
   ST(stage_ad(ctx, n, ad, ad_off, &d_ad, &d_off));
   ST(stage_out(ctx, BUF_OUT0, n * 256, &d_pr)); ST(stage_out(ctx, BUF_OUT1, n * 32, &d_bl));
   mark_secret(ctx, BUF_OUT1, n * 32);
-  ST(with_suite(ctx, suite, [&](auto S_) { typedef decltype(S_) S; return pedersen_prove_dev<S>(ctx, n, d_sk, d_in, d_out, d_ad, d_off, d_pr, d_bl); }));
+  for (int k = 0; k < pieces; k++) {
+    const size_t o = cut[k], m = cut[k + 1] - cut[k];
+    ST(piece_ready(ctx, k));
+    ST(with_suite(ctx, suite, [&](auto S_) { typedef decltype(S_) S;
+      return pedersen_prove_dev<S>(ctx, m, in[0].dev + o * 32, in[1].dev + o * 64, in[2].dev + o * 64, d_ad, d_off ? d_off + o : nullptr, d_pr + o * 256, d_bl + o * 32); }));
+  }
   ST(copy_out(ctx, out_proof, d_pr, n * 256)); ST(copy_out(ctx, out_blinding, d_bl, n * 32));
   return finish_call(ctx);
 }
@@ -1170,12 +1211,19 @@ extern "C" vrfs_status vrfs_pedersen_verify_batch(vrfs_ctx* ctx, vrfs_suite suit
   if (!input || !output || !proof || !out_ok) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite >= VRFS_SUITE_COUNT) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
   ST(begin_call(ctx, n));
-  const uint8_t *d_in, *d_out, *d_pr, *d_ad; const uint64_t* d_off; uint8_t *d_ok, *d_st = nullptr;
-  ST(stage_in(ctx, BUF_IN0, input, n * 64, &d_in)); ST(stage_in(ctx, BUF_IN1, output, n * 64, &d_out)); ST(stage_in(ctx, BUF_IN2, proof, n * 256, &d_pr));
+  const uint8_t* d_ad; const uint64_t* d_off; uint8_t *d_ok, *d_st = nullptr;
+  HostIn in[3] = {{BUF_IN0, input, 64, false, nullptr}, {BUF_IN1, output, 64, false, nullptr}, {BUF_IN2, proof, 256, false, nullptr}};
+  size_t cut[3]; int pieces = 1;
+  ST(stage_in_pieces(ctx, n, in, 3, cut, &pieces));
   ST(stage_ad(ctx, n, ad, ad_off, &d_ad, &d_off));
   ST(stage_out(ctx, BUF_OUT0, n, &d_ok));
   if (out_status) ST(stage_out(ctx, BUF_OUT1, n, &d_st));
-  ST(with_suite(ctx, suite, [&](auto S_) { typedef decltype(S_) S; return pedersen_verify_dev<S>(ctx, n, d_in, d_out, d_pr, d_ad, d_off, d_ok, d_st); }));
+  for (int k = 0; k < pieces; k++) {
+    const size_t o = cut[k], m = cut[k + 1] - cut[k];
+    ST(piece_ready(ctx, k));
+    ST(with_suite(ctx, suite, [&](auto S_) { typedef decltype(S_) S;
+      return pedersen_verify_dev<S>(ctx, m, in[0].dev + o * 64, in[1].dev + o * 64, in[2].dev + o * 256, d_ad, d_off ? d_off + o : nullptr, d_ok + o, d_st ? d_st + o : nullptr); }));
+  }
   ST(copy_out(ctx, out_ok, d_ok, n));
   if (out_status) ST(copy_out(ctx, out_status, d_st, n));
   return finish_call(ctx);
