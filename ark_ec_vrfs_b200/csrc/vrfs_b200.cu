@@ -237,6 +237,9 @@ enum { BUF_IN0, BUF_IN1, BUF_IN2, BUF_IN3, BUF_IN4, BUF_AD, BUF_OFF, BUF_OUT0, B
        BUF_X0, BUF_X1, BUF_X2, BUF_X3, BUF_X4, BUF_X5, BUF_ZINV, BUF_SLAB2, BUF_COUNT };   // X*: wire-format staging (encoded keys, signatures, h2c data, flags)
 
 #define MAX_TIMED 64
+#ifndef VRFS_HOST_PIECES
+#define VRFS_HOST_PIECES 6   // host-buffer calls: at most this many pieces per batch (stage_in_pieces)
+#endif
 struct vrfs_ctx {
   int device = 0, sms = 0;
   bool timing = false;
@@ -247,6 +250,7 @@ struct vrfs_ctx {
   cudaStream_t copy_stream = nullptr;                 // H2D of later chunks overlaps the kernels of earlier ones
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t ev_chunk[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_in[VRFS_HOST_PIECES] = {nullptr}, ev_out[VRFS_HOST_PIECES] = {nullptr};   // per-piece host transfers (stage_in_pieces / pieces_copy_out)
   char err[512] = {0};
   std::recursive_mutex mu;            // entry points serialise per context ("internally synchronised")
   uint64_t launches = 0;
@@ -402,6 +406,7 @@ extern "C" vrfs_status vrfs_ctx_create(int device, vrfs_ctx** out) {
   CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   for (int i = 0; i < 4; i++) CU(cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming));
+  for (int i = 0; i < VRFS_HOST_PIECES; i++) { CU(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming)); }
   CU(cudaEventCreate(&ctx->ev0));
   CU(cudaEventCreate(&ctx->ev1));
   return VRFS_OK;                      // fixed-base tables: built on first use per suite (need_tables)
@@ -417,6 +422,7 @@ extern "C" void vrfs_ctx_destroy(vrfs_ctx* ctx) {
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   for (int i = 0; i < 4; i++) if (ctx->ev_chunk[i]) cudaEventDestroy(ctx->ev_chunk[i]);
+  for (int i = 0; i < VRFS_HOST_PIECES; i++) { if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]); if (ctx->ev_out[i]) cudaEventDestroy(ctx->ev_out[i]); }
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -882,32 +888,60 @@ static vrfs_status stage_secret(vrfs_ctx* ctx, int which, const void* host, size
   mark_secret(ctx, which, bytes);
   return stage_in(ctx, which, host, bytes, dev);
 }
-// Host inputs of a large batch call in TWO pieces - one resident wave of the lincomb grid, then the rest - copied on the copy stream:
-// the second piece (93 % of a 2^20 batch) travels while the first one computes, as vrfs_ietf_verify_batch does for its inputs.
-// The caller runs its device function per piece after cudaStreamWaitEvent(stream, ev_chunk[k]).
+// Host buffers of a large batch call travel in PIECES on the copy stream: one resident wave of the lincomb grid first, then the
+// rest in up to max_pieces - 1 runs of whole waves.  Piece k's kernels wait only for piece k's inputs, so all but the first
+// ~20 MB of the input transfer hides behind arithmetic (as in vrfs_ietf_verify_batch), and piece k's results go back to the
+// host while piece k + 1 computes (pieces_copy_out) - what matters for the prove calls, whose outputs are 64-288 B per item.
 struct HostIn { int buf; const void* host; size_t stride; bool secret; uint8_t* dev; };
-static vrfs_status stage_in_pieces(vrfs_ctx* ctx, size_t n, HostIn* in, int nin, size_t cut[3], int* pieces) {
+struct HostOut { void* host; const uint8_t* dev; size_t stride; };
+struct Pieces { size_t cut[VRFS_HOST_PIECES + 1]; int count; };
+static vrfs_status stage_in_pieces(vrfs_ctx* ctx, size_t n, HostIn* in, int nin, Pieces* pc, int max_pieces) {
   const size_t wave = (size_t)ctx->sms * LINCOMB_MINBLOCKS * LINCOMB_THREADS;
-  cut[0] = 0; cut[1] = n > 3 * wave ? wave : n; cut[2] = n;
-  *pieces = cut[1] < n ? 2 : 1;
+  pc->cut[0] = 0; pc->cut[1] = n; pc->count = 1;
+  if (n > 3 * wave && max_pieces >= 2) {
+    if (max_pieces > VRFS_HOST_PIECES) max_pieces = VRFS_HOST_PIECES;
+    const size_t rest_waves = (n - wave + wave - 1) / wave;
+    const size_t q = rest_waves < (size_t)(max_pieces - 1) ? rest_waves : (size_t)(max_pieces - 1);
+    const size_t per = (rest_waves + q - 1) / q * wave;
+    pc->cut[1] = wave;
+    while (pc->cut[pc->count] < n) {
+      const size_t next = pc->cut[pc->count] + per;
+      pc->count++;
+      pc->cut[pc->count] = next < n ? next : n;
+    }
+  }
   for (int j = 0; j < nin; j++) {
     void* d = nullptr;
     ST(ensure(ctx, in[j].buf, n * in[j].stride, &d));
     in[j].dev = (uint8_t*)d;
     if (in[j].secret) mark_secret(ctx, in[j].buf, n * in[j].stride);
   }
-  for (int k = 0; k < *pieces; k++) {
-    const size_t o = cut[k], m = cut[k + 1] - cut[k];
+  for (int k = 0; k < pc->count; k++) {
+    const size_t o = pc->cut[k], m = pc->cut[k + 1] - pc->cut[k];
     for (int j = 0; j < nin; j++)
       CU(cudaMemcpyAsync(in[j].dev + o * in[j].stride, (const uint8_t*)in[j].host + o * in[j].stride, m * in[j].stride, cudaMemcpyHostToDevice, ctx->copy_stream));
-    CU(cudaEventRecord(ctx->ev_chunk[k], ctx->copy_stream));
+    CU(cudaEventRecord(ctx->ev_in[k], ctx->copy_stream));
   }
   return VRFS_OK;
 }
 static vrfs_status piece_ready(vrfs_ctx* ctx, int k) {
-  CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[k], 0));
+  CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[k], 0));
   // kernel timing: the first kernel's interval starts after its inputs arrived, not at the start of the call
   if (ctx->timing && ctx->tev[0] && ctx->n_timed == 0) CU(cudaEventRecord(ctx->tev[0], ctx->stream));
+  return VRFS_OK;
+}
+// results of piece k back to the host on the copy stream, behind the kernels of piece k; the last piece makes the main stream
+// wait for every copy, so that finish_call (and the wipe of secret buffers after it) sees them all done
+static vrfs_status pieces_copy_out(vrfs_ctx* ctx, const Pieces& pc, int k, const HostOut* out, int nout) {
+  const size_t o = pc.cut[k], m = pc.cut[k + 1] - pc.cut[k];
+  CU(cudaEventRecord(ctx->ev_out[k], ctx->stream));
+  CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_out[k], 0));
+  for (int j = 0; j < nout; j++)
+    CU(cudaMemcpyAsync((uint8_t*)out[j].host + o * out[j].stride, out[j].dev + o * out[j].stride, m * out[j].stride, cudaMemcpyDeviceToHost, ctx->copy_stream));
+  if (k == pc.count - 1) {
+    CU(cudaEventRecord(ctx->ev_out[k], ctx->copy_stream));
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_out[k], 0));
+  }
   return VRFS_OK;
 }
 // batched inversion of the Z coordinates of NP projective results per item (k_zinv): returns the device array of n x 8 words
@@ -972,17 +1006,18 @@ extern "C" vrfs_status vrfs_ietf_prove_batch(vrfs_ctx* ctx, vrfs_suite suite, si
   ST(begin_call(ctx, n));
   const uint8_t* d_ad; const uint64_t* d_off; uint8_t *d_c, *d_s;
   HostIn in[3] = {{BUF_IN0, sk, 32, true, nullptr}, {BUF_IN1, input, 64, false, nullptr}, {BUF_IN2, output, 64, false, nullptr}};
-  size_t cut[3]; int pieces = 1;
-  ST(stage_in_pieces(ctx, n, in, 3, cut, &pieces));
+  Pieces pc;   // two pieces: every further piece costs ~1 % in kernel tails, more than hiding the rest of the 64 B/item of results returns
+  ST(stage_in_pieces(ctx, n, in, 3, &pc, 2));
   ST(stage_ad(ctx, n, ad, ad_off, &d_ad, &d_off));
   ST(stage_out(ctx, BUF_OUT0, n * 32, &d_c)); ST(stage_out(ctx, BUF_OUT1, n * 32, &d_s));
-  for (int k = 0; k < pieces; k++) {
-    const size_t o = cut[k], m = cut[k + 1] - cut[k];
+  const HostOut out[2] = {{out_c, d_c, 32}, {out_s, d_s, 32}};
+  for (int k = 0; k < pc.count; k++) {
+    const size_t o = pc.cut[k], m = pc.cut[k + 1] - pc.cut[k];
     ST(piece_ready(ctx, k));
     ST(with_suite(ctx, suite, [&](auto S_) { typedef decltype(S_) S;
       return ietf_prove_dev<S>(ctx, m, in[0].dev + o * 32, in[1].dev + o * 64, in[2].dev + o * 64, d_ad, d_off ? d_off + o : nullptr, d_c + o * 32, d_s + o * 32); }));
+    ST(pieces_copy_out(ctx, pc, k, out, 2));
   }
-  ST(copy_out(ctx, out_c, d_c, n * 32)); ST(copy_out(ctx, out_s, d_s, n * 32));
   return finish_call(ctx);
 }
 
@@ -1164,18 +1199,19 @@ extern "C" vrfs_status vrfs_pedersen_prove_batch(vrfs_ctx* ctx, vrfs_suite suite
   ST(begin_call(ctx, n));
   const uint8_t* d_ad; const uint64_t* d_off; uint8_t *d_pr, *d_bl;
   HostIn in[3] = {{BUF_IN0, sk, 32, true, nullptr}, {BUF_IN1, input, 64, false, nullptr}, {BUF_IN2, output, 64, false, nullptr}};
-  size_t cut[3]; int pieces = 1;
-  ST(stage_in_pieces(ctx, n, in, 3, cut, &pieces));
+  Pieces pc;   // 288 B/item of results: worth VRFS_HOST_PIECES pieces (measured 2^20: e2e 19.4 -> 20.8 M/s, kernels 21.8 -> 20.9 M/s)
+  ST(stage_in_pieces(ctx, n, in, 3, &pc, VRFS_HOST_PIECES));
   ST(stage_ad(ctx, n, ad, ad_off, &d_ad, &d_off));
   ST(stage_out(ctx, BUF_OUT0, n * 256, &d_pr)); ST(stage_out(ctx, BUF_OUT1, n * 32, &d_bl));
   mark_secret(ctx, BUF_OUT1, n * 32);
-  for (int k = 0; k < pieces; k++) {
-    const size_t o = cut[k], m = cut[k + 1] - cut[k];
+  const HostOut out[2] = {{out_proof, d_pr, 256}, {out_blinding, d_bl, 32}};
+  for (int k = 0; k < pc.count; k++) {
+    const size_t o = pc.cut[k], m = pc.cut[k + 1] - pc.cut[k];
     ST(piece_ready(ctx, k));
     ST(with_suite(ctx, suite, [&](auto S_) { typedef decltype(S_) S;
       return pedersen_prove_dev<S>(ctx, m, in[0].dev + o * 32, in[1].dev + o * 64, in[2].dev + o * 64, d_ad, d_off ? d_off + o : nullptr, d_pr + o * 256, d_bl + o * 32); }));
+    ST(pieces_copy_out(ctx, pc, k, out, 2));
   }
-  ST(copy_out(ctx, out_proof, d_pr, n * 256)); ST(copy_out(ctx, out_blinding, d_bl, n * 32));
   return finish_call(ctx);
 }
 template <class S>
@@ -1213,13 +1249,13 @@ extern "C" vrfs_status vrfs_pedersen_verify_batch(vrfs_ctx* ctx, vrfs_suite suit
   ST(begin_call(ctx, n));
   const uint8_t* d_ad; const uint64_t* d_off; uint8_t *d_ok, *d_st = nullptr;
   HostIn in[3] = {{BUF_IN0, input, 64, false, nullptr}, {BUF_IN1, output, 64, false, nullptr}, {BUF_IN2, proof, 256, false, nullptr}};
-  size_t cut[3]; int pieces = 1;
-  ST(stage_in_pieces(ctx, n, in, 3, cut, &pieces));
+  Pieces pc;
+  ST(stage_in_pieces(ctx, n, in, 3, &pc, 2));
   ST(stage_ad(ctx, n, ad, ad_off, &d_ad, &d_off));
   ST(stage_out(ctx, BUF_OUT0, n, &d_ok));
   if (out_status) ST(stage_out(ctx, BUF_OUT1, n, &d_st));
-  for (int k = 0; k < pieces; k++) {
-    const size_t o = cut[k], m = cut[k + 1] - cut[k];
+  for (int k = 0; k < pc.count; k++) {
+    const size_t o = pc.cut[k], m = pc.cut[k + 1] - pc.cut[k];
     ST(piece_ready(ctx, k));
     ST(with_suite(ctx, suite, [&](auto S_) { typedef decltype(S_) S;
       return pedersen_verify_dev<S>(ctx, m, in[0].dev + o * 64, in[1].dev + o * 64, in[2].dev + o * 256, d_ad, d_off ? d_off + o : nullptr, d_ok + o, d_st ? d_st + o : nullptr); }));
@@ -1376,9 +1412,15 @@ extern "C" vrfs_status vrfs_ietf_verify_wire_batch(vrfs_ctx* ctx, vrfs_suite sui
   if ((unsigned)suite >= VRFS_SUITE_COUNT) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
   ST(begin_call(ctx, n));
   const size_t sl = (size_t)vrfs_suite_ietf_signature_len(suite), el = (size_t)vrfs_suite_point_enc_len(suite), hl = (size_t)vrfs_suite_hash_len(suite);
-  const uint8_t *d_pke, *d_sig, *d_ad, *d_data; const uint64_t *d_off, *d_doff;
+  const uint8_t *d_ad, *d_data; const uint64_t *d_off, *d_doff;
   uint8_t *d_pk, *d_in, *d_out, *d_c, *d_s, *d_flags, *d_ok, *d_hash = nullptr, *d_st = nullptr;
-  ST(stage_in(ctx, BUF_X0, pk_enc, n * el, &d_pke)); ST(stage_in(ctx, BUF_X1, sig, n * sl, &d_sig));
+  // keys and signatures on the copy stream, enqueued first: the host-side checks of the offset arrays below run while they
+  // travel; the variable-length data and ad go on the main stream.  ONE piece: with [one wave, rest] the decode and
+  // hash-to-curve kernels of the small first piece run below their full-batch rate and the call as a whole was 1.3 % slower
+  // (2^20 Bandersnatch items, 9.07 -> 8.96 M/s).
+  HostIn in[2] = {{BUF_X0, pk_enc, el, false, nullptr}, {BUF_X1, sig, sl, false, nullptr}};
+  Pieces pc;
+  ST(stage_in_pieces(ctx, n, in, 2, &pc, 1));
   ST(stage_ad(ctx, n, ad, ad_off, &d_ad, &d_off));
   ST(stage_var(ctx, BUF_X2, BUF_X3, n, data, data_off, &d_data, &d_doff));
   ST(stage_out(ctx, BUF_IN0, n * 64, &d_pk)); ST(stage_out(ctx, BUF_IN1, n * 64, &d_in)); ST(stage_out(ctx, BUF_IN2, n * 64, &d_out));
@@ -1386,10 +1428,18 @@ extern "C" vrfs_status vrfs_ietf_verify_wire_batch(vrfs_ctx* ctx, vrfs_suite sui
   ST(stage_out(ctx, BUF_OUT0, n, &d_ok));
   if (out_hash) ST(stage_out(ctx, BUF_OUT1, n * hl, &d_hash));
   if (out_status) ST(stage_out(ctx, BUF_X5, n, &d_st));
-  ST(with_suite(ctx, suite, [&](auto S_) { typedef decltype(S_) S; return ietf_verify_wire_dev<S>(ctx, n, d_pke, d_data, d_doff, d_sig, d_ad, d_off, d_pk, d_in, d_out, d_c, d_s, d_flags, d_ok, d_hash, d_st); }));
-  ST(copy_out(ctx, out_ok, d_ok, n));
-  if (out_hash) ST(copy_out(ctx, out_hash, d_hash, n * hl));
-  if (out_status) ST(copy_out(ctx, out_status, d_st, n));
+  HostOut out[3] = {{out_ok, d_ok, 1}, {nullptr, nullptr, 0}, {nullptr, nullptr, 0}};
+  int nout = 1;
+  if (out_hash) out[nout++] = {out_hash, d_hash, hl};
+  if (out_status) out[nout++] = {out_status, d_st, 1};
+  for (int k = 0; k < pc.count; k++) {
+    const size_t o = pc.cut[k], m = pc.cut[k + 1] - pc.cut[k];
+    ST(piece_ready(ctx, k));
+    ST(with_suite(ctx, suite, [&](auto S_) { typedef decltype(S_) S;
+      return ietf_verify_wire_dev<S>(ctx, m, in[0].dev + o * el, d_data, d_doff + o, in[1].dev + o * sl, d_ad, d_off ? d_off + o : nullptr, d_pk + o * 64, d_in + o * 64,
+                                     d_out + o * 64, d_c + o * 32, d_s + o * 32, d_flags + o * 4, d_ok + o, d_hash ? d_hash + o * hl : nullptr, d_st ? d_st + o : nullptr); }));
+    ST(pieces_copy_out(ctx, pc, k, out, nout));
+  }
   return finish_call(ctx);
 }
 
