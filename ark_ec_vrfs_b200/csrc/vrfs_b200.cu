@@ -1,6 +1,7 @@
 // vrfs_b200: kernels + the C ABI of include/vrfs_b200.h.  sm_100a only; no CPU fallback - every entry
 // point launches kernels on the context's device and reports CUDA failures as VRFS_CUDA_ERROR.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -279,6 +280,12 @@ static vrfs_status fail(vrfs_ctx* c, vrfs_status st, const char* fmt, ...) {
 //    holding sk are zeroed before release"; the buffers are pooled, so "release" is the end of the call);
 //  * after a failure both streams are drained, so that no copy is still reading the caller's host buffers when the error
 //    code reaches the caller.
+// one NVTX range per ABI call, named after the entry point (`ncu --nvtx --nvtx-include "vrfs_ietf_verify_batch/"` profiles the
+// kernels of one kind of call; header-only NVTX 3: a no-op unless a tool is attached)
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 struct CallGuard {
   vrfs_ctx* ctx;
   explicit CallGuard(vrfs_ctx* c) : ctx(c) { ctx->mu.lock(); if (ctx->depth++ == 0) ctx->failed = false; }
@@ -331,7 +338,7 @@ static vrfs_status note_kernel(vrfs_ctx* ctx, const char* name) {
 }
 extern "C" vrfs_status vrfs_ctx_enable_kernel_timing(vrfs_ctx* ctx, int on) {
   if (!ctx) return VRFS_BAD_ARG;
-  CallGuard guard_(ctx);
+  CallGuard guard_(ctx); NvtxRange range_(__func__);
   ctx->timing = on != 0;
   ctx->n_timed = 0;
   return VRFS_OK;
@@ -339,7 +346,7 @@ extern "C" vrfs_status vrfs_ctx_enable_kernel_timing(vrfs_ctx* ctx, int on) {
 // device time of every kernel of the most recent *_batch / *_batch_dev call (after a sync); returns the count
 extern "C" int vrfs_ctx_kernel_timings(vrfs_ctx* ctx, const char** names, float* ms, int cap) {
   if (!ctx || !ctx->timing) return 0;
-  CallGuard guard_(ctx);
+  CallGuard guard_(ctx); NvtxRange range_(__func__);
   if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return 0;
   int n = ctx->n_timed < cap ? ctx->n_timed : cap;
   for (int i = 0; i < n; i++) {
@@ -429,7 +436,7 @@ extern "C" void vrfs_ctx_destroy(vrfs_ctx* ctx) {
 }
 extern "C" vrfs_status vrfs_ctx_sync(vrfs_ctx* ctx) {
   if (!ctx) return VRFS_BAD_ARG;
-  CallGuard guard_(ctx);
+  CallGuard guard_(ctx); NvtxRange range_(__func__);
   CU(cudaStreamSynchronize(ctx->stream));
   return VRFS_OK;
 }
@@ -437,7 +444,7 @@ extern "C" vrfs_status vrfs_ctx_sync(vrfs_ctx* ctx) {
 // order, e.g. slot 0 holds `sk` during a prove call).  tests/ use it to check that key material is gone after a call returned.
 extern "C" vrfs_status vrfs_ctx_debug_read_staging(vrfs_ctx* ctx, int slot, size_t offset, uint8_t* out, size_t n) {
   if (!ctx || !out) return VRFS_BAD_ARG;
-  CallGuard guard_(ctx);
+  CallGuard guard_(ctx); NvtxRange range_(__func__);
   if (slot < 0 || slot >= BUF_COUNT) return fail(ctx, VRFS_BAD_ARG, "no such staging buffer");
   const DevBuf& b = ctx->buf[slot];
   if (!b.p || offset + n > b.cap) return fail(ctx, VRFS_BAD_ARG, "range outside the staging buffer (capacity %zu)", b.cap);
@@ -586,7 +593,7 @@ extern "C" vrfs_status vrfs_ietf_verify_batch_dev(vrfs_ctx* ctx, vrfs_suite suit
                                                   const uint8_t* output, const uint8_t* c, const uint8_t* s, const uint8_t* ad,
                                                   const uint64_t* ad_off, uint8_t* out_ok, uint8_t* out_status) {
   if (!ctx) return VRFS_BAD_ARG;
-  CallGuard guard_(ctx);
+  CallGuard guard_(ctx); NvtxRange range_(__func__);
   if (n == 0) return VRFS_OK;
   if (!pk || !input || !output || !c || !s || !out_ok || (ad && !ad_off)) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if (n > 0x7fffffffu) return fail(ctx, VRFS_BAD_ARG, "batch too large (n < 2^31)");
@@ -676,7 +683,7 @@ extern "C" vrfs_status vrfs_ietf_verify_batch(vrfs_ctx* ctx, vrfs_suite suite, s
                                               const uint8_t* output, const uint8_t* c, const uint8_t* s, const uint8_t* ad,
                                               const uint64_t* ad_off, uint8_t* out_ok, uint8_t* out_status) {
   if (!ctx) return VRFS_BAD_ARG;
-  CallGuard guard_(ctx);
+  CallGuard guard_(ctx); NvtxRange range_(__func__);
   if (n == 0) return VRFS_OK;
   ST(ietf_verify_host_enqueue(ctx, suite, n, pk, input, output, c, s, ad, ad_off, out_ok, out_status));
   CU(cudaStreamSynchronize(ctx->stream));
@@ -688,7 +695,7 @@ extern "C" vrfs_status vrfs_ietf_verify_batch(vrfs_ctx* ctx, vrfs_suite suite, s
 // =================================================================================================
 extern "C" vrfs_status vrfs_measure_mac32_peak(vrfs_ctx* ctx, int variant, double* out_mac_per_s, double* out_sm_mhz_est) {
   if (!ctx || !out_mac_per_s) return VRFS_BAD_ARG;
-  CallGuard guard_(ctx);
+  CallGuard guard_(ctx); NvtxRange range_(__func__);
   CU(cudaSetDevice(ctx->device));
   const int threads = 256, blocks = ctx->sms * 8;
   void *out = nullptr, *cyc = nullptr;
@@ -999,7 +1006,7 @@ static vrfs_status ietf_prove_dev(vrfs_ctx* ctx, size_t n, const uint8_t* sk, co
 extern "C" vrfs_status vrfs_ietf_prove_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* sk, const uint8_t* input, const uint8_t* output,
                                              const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_c, uint8_t* out_s) {
   if (!ctx) return VRFS_BAD_ARG;
-  CallGuard guard_(ctx);
+  CallGuard guard_(ctx); NvtxRange range_(__func__);
   if (n == 0) return VRFS_OK;
   if (!sk || !input || !output || !out_c || !out_s) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite >= VRFS_SUITE_COUNT) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
@@ -1037,7 +1044,7 @@ template <class S> static vrfs_status output_dev(vrfs_ctx* ctx, size_t n, const 
 }
 extern "C" vrfs_status vrfs_output_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* sk, const uint8_t* input, uint8_t* out_output) {
   if (!ctx) return VRFS_BAD_ARG;
-  CallGuard guard_(ctx);
+  CallGuard guard_(ctx); NvtxRange range_(__func__);
   if (n == 0) return VRFS_OK;
   if (!sk || !input || !out_output) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite >= VRFS_SUITE_COUNT) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
@@ -1068,7 +1075,7 @@ template <class S> static vrfs_status from_seed_dev(vrfs_ctx* ctx, size_t n, con
 extern "C" vrfs_status vrfs_secret_from_seed_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* seeds, const uint64_t* seed_off,
                                                    uint8_t* out_sk, uint8_t* out_pk) {
   if (!ctx) return VRFS_BAD_ARG;
-  CallGuard guard_(ctx);
+  CallGuard guard_(ctx); NvtxRange range_(__func__);
   if (n == 0) return VRFS_OK;
   if (!seed_off || !out_sk) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite >= VRFS_SUITE_COUNT) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
@@ -1086,7 +1093,7 @@ extern "C" vrfs_status vrfs_secret_from_seed_batch(vrfs_ctx* ctx, vrfs_suite sui
 }
 extern "C" vrfs_status vrfs_nonce_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* sk, const uint8_t* input, uint8_t* out_k) {
   if (!ctx) return VRFS_BAD_ARG;
-  CallGuard guard_(ctx);
+  CallGuard guard_(ctx); NvtxRange range_(__func__);
   if (n == 0) return VRFS_OK;
   if (!sk || !input || !out_k) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite >= VRFS_SUITE_COUNT) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
@@ -1101,7 +1108,7 @@ extern "C" vrfs_status vrfs_nonce_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t 
 }
 extern "C" vrfs_status vrfs_point_to_hash_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* pts, uint8_t* out_hash) {
   if (!ctx) return VRFS_BAD_ARG;
-  CallGuard guard_(ctx);
+  CallGuard guard_(ctx); NvtxRange range_(__func__);
   if (n == 0) return VRFS_OK;
   if (!pts || !out_hash) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite >= VRFS_SUITE_COUNT) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
@@ -1116,7 +1123,7 @@ extern "C" vrfs_status vrfs_point_to_hash_batch(vrfs_ctx* ctx, vrfs_suite suite,
 }
 extern "C" vrfs_status vrfs_point_encode_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* pts, uint8_t* out_enc) {
   if (!ctx) return VRFS_BAD_ARG;
-  CallGuard guard_(ctx);
+  CallGuard guard_(ctx); NvtxRange range_(__func__);
   if (n == 0) return VRFS_OK;
   if (!pts || !out_enc) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite >= VRFS_SUITE_COUNT) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
@@ -1131,7 +1138,7 @@ extern "C" vrfs_status vrfs_point_encode_batch(vrfs_ctx* ctx, vrfs_suite suite, 
 }
 extern "C" vrfs_status vrfs_point_decode_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* enc, uint8_t* out_pts, uint8_t* out_ok) {
   if (!ctx) return VRFS_BAD_ARG;
-  CallGuard guard_(ctx);
+  CallGuard guard_(ctx); NvtxRange range_(__func__);
   if (n == 0) return VRFS_OK;
   if (!enc || !out_pts || !out_ok) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite >= VRFS_SUITE_COUNT) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
@@ -1147,7 +1154,7 @@ extern "C" vrfs_status vrfs_point_decode_batch(vrfs_ctx* ctx, vrfs_suite suite, 
 extern "C" vrfs_status vrfs_data_to_point_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* data, const uint64_t* data_off,
                                                 uint8_t* out_pts, uint8_t* out_ok) {
   if (!ctx) return VRFS_BAD_ARG;
-  CallGuard guard_(ctx);
+  CallGuard guard_(ctx); NvtxRange range_(__func__);
   if (n == 0) return VRFS_OK;
   if (!data_off || !out_pts || !out_ok) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite >= VRFS_SUITE_COUNT) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
@@ -1192,7 +1199,7 @@ static vrfs_status pedersen_prove_dev(vrfs_ctx* ctx, size_t n, const uint8_t* sk
 extern "C" vrfs_status vrfs_pedersen_prove_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* sk, const uint8_t* input, const uint8_t* output,
                                                  const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_proof, uint8_t* out_blinding) {
   if (!ctx) return VRFS_BAD_ARG;
-  CallGuard guard_(ctx);
+  CallGuard guard_(ctx); NvtxRange range_(__func__);
   if (n == 0) return VRFS_OK;
   if (!sk || !input || !output || !out_proof || !out_blinding) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite >= VRFS_SUITE_COUNT) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
@@ -1242,7 +1249,7 @@ static vrfs_status pedersen_verify_dev(vrfs_ctx* ctx, size_t n, const uint8_t* i
 extern "C" vrfs_status vrfs_pedersen_verify_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* input, const uint8_t* output, const uint8_t* proof,
                                                   const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_ok, uint8_t* out_status) {
   if (!ctx) return VRFS_BAD_ARG;
-  CallGuard guard_(ctx);
+  CallGuard guard_(ctx); NvtxRange range_(__func__);
   if (n == 0) return VRFS_OK;
   if (!input || !output || !proof || !out_ok) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite >= VRFS_SUITE_COUNT) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
@@ -1325,7 +1332,7 @@ template <class S> static vrfs_status decode_checked_launch(vrfs_ctx* ctx, size_
 }
 extern "C" vrfs_status vrfs_point_decode_checked_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* enc, uint8_t* out_pts, uint8_t* out_ok) {
   if (!ctx) return VRFS_BAD_ARG;
-  CallGuard guard_(ctx);
+  CallGuard guard_(ctx); NvtxRange range_(__func__);
   if (n == 0) return VRFS_OK;
   if (!enc || !out_pts || !out_ok) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite >= VRFS_SUITE_COUNT) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
@@ -1339,7 +1346,7 @@ extern "C" vrfs_status vrfs_point_decode_checked_batch(vrfs_ctx* ctx, vrfs_suite
 }
 extern "C" vrfs_status vrfs_subgroup_check_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* pts, uint8_t* out_ok) {
   if (!ctx) return VRFS_BAD_ARG;
-  CallGuard guard_(ctx);
+  CallGuard guard_(ctx); NvtxRange range_(__func__);
   if (n == 0) return VRFS_OK;
   if (!pts || !out_ok) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite >= VRFS_SUITE_COUNT) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
@@ -1366,7 +1373,7 @@ template <class S> static vrfs_status ietf_sign_wire_dev(vrfs_ctx* ctx, size_t n
 extern "C" vrfs_status vrfs_ietf_sign_wire_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* sk, const uint8_t* data, const uint64_t* data_off,
                                                  const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_sig, uint8_t* out_ok) {
   if (!ctx) return VRFS_BAD_ARG;
-  CallGuard guard_(ctx);
+  CallGuard guard_(ctx); NvtxRange range_(__func__);
   if (n == 0) return VRFS_OK;
   if (!sk || !data_off || !out_sig) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite >= VRFS_SUITE_COUNT) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
@@ -1406,7 +1413,7 @@ template <class S> static vrfs_status ietf_verify_wire_dev(vrfs_ctx* ctx, size_t
 extern "C" vrfs_status vrfs_ietf_verify_wire_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* pk_enc, const uint8_t* data, const uint64_t* data_off,
                                                    const uint8_t* sig, const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_ok, uint8_t* out_hash, uint8_t* out_status) {
   if (!ctx) return VRFS_BAD_ARG;
-  CallGuard guard_(ctx);
+  CallGuard guard_(ctx); NvtxRange range_(__func__);
   if (n == 0) return VRFS_OK;
   if (!pk_enc || !data_off || !sig || !out_ok) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite >= VRFS_SUITE_COUNT) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
@@ -1502,7 +1509,7 @@ template <class S> static vrfs_status pedersen_sign_wire_dev(vrfs_ctx* ctx, size
 extern "C" vrfs_status vrfs_pedersen_sign_wire_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* sk, const uint8_t* data, const uint64_t* data_off,
                                                      const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_sig, uint8_t* out_blinding, uint8_t* out_ok) {
   if (!ctx) return VRFS_BAD_ARG;
-  CallGuard guard_(ctx);
+  CallGuard guard_(ctx); NvtxRange range_(__func__);
   if (n == 0) return VRFS_OK;
   if (!sk || !data_off || !out_sig || !out_blinding) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite >= VRFS_SUITE_COUNT) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
@@ -1539,7 +1546,7 @@ template <class S, int NP> static vrfs_status pedersen_verify_wire_dev(vrfs_ctx*
 extern "C" vrfs_status vrfs_pedersen_verify_wire_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* data, const uint64_t* data_off, const uint8_t* sig,
                                                        const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_ok, uint8_t* out_status) {
   if (!ctx) return VRFS_BAD_ARG;
-  CallGuard guard_(ctx);
+  CallGuard guard_(ctx); NvtxRange range_(__func__);
   if (n == 0) return VRFS_OK;
   if (!data_off || !sig || !out_ok) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite >= VRFS_SUITE_COUNT) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
@@ -1570,7 +1577,7 @@ template <class S> static vrfs_status pedersen_prove_compressed_dev(vrfs_ctx* ct
 extern "C" vrfs_status vrfs_pedersen_prove_compressed_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* sk, const uint8_t* input, const uint8_t* output,
                                                             const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_proof, uint8_t* out_blinding) {
   if (!ctx) return VRFS_BAD_ARG;
-  CallGuard guard_(ctx);
+  CallGuard guard_(ctx); NvtxRange range_(__func__);
   if (n == 0) return VRFS_OK;
   if (!sk || !input || !output || !out_proof || !out_blinding) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite >= VRFS_SUITE_COUNT) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
@@ -1588,7 +1595,7 @@ extern "C" vrfs_status vrfs_pedersen_prove_compressed_batch(vrfs_ctx* ctx, vrfs_
 extern "C" vrfs_status vrfs_pedersen_verify_compressed_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* input, const uint8_t* output, const uint8_t* proof,
                                                              const uint8_t* ad, const uint64_t* ad_off, uint8_t* out_ok, uint8_t* out_status) {
   if (!ctx) return VRFS_BAD_ARG;
-  CallGuard guard_(ctx);
+  CallGuard guard_(ctx); NvtxRange range_(__func__);
   if (n == 0) return VRFS_OK;
   if (!input || !output || !proof || !out_ok) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if ((unsigned)suite >= VRFS_SUITE_COUNT) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
@@ -1755,7 +1762,7 @@ static vrfs_status msm_stateless_dev(vrfs_ctx* ctx, size_t n, int ncol, const vo
 }
 static vrfs_status msm_host(vrfs_ctx* ctx, size_t n, const uint8_t* bases, const uint8_t* scalars, int ncol, uint8_t* out, int out_mode, int window_bits = 0) {
   if (!ctx) return VRFS_BAD_ARG;
-  CallGuard guard_(ctx);
+  CallGuard guard_(ctx); NvtxRange range_(__func__);
   if (ncol < 1 || ncol > 32) return fail(ctx, VRFS_BAD_ARG, "n_columns must be in 1..32");
   if (!out || (n && (!bases || !scalars))) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   const size_t ob = out_mode ? 144 : 96;
@@ -1789,7 +1796,7 @@ extern "C" vrfs_status vrfs_msm_g1_partial(vrfs_ctx* ctx, size_t n, const uint8_
 }
 static vrfs_status msm_prepare_impl(vrfs_ctx* ctx, size_t n, const uint8_t* bases, int window_bits, int threads_per_bucket, vrfs_msm_bases** out) {
   if (!ctx || !out) return VRFS_BAD_ARG;
-  CallGuard guard_(ctx);
+  CallGuard guard_(ctx); NvtxRange range_(__func__);
   *out = nullptr;
   if (n == 0 || !bases) return fail(ctx, VRFS_BAD_ARG, "empty base vector");
   if (n > (1u << 24)) return fail(ctx, VRFS_BAD_ARG, "prepared MSM size above 2^24 is not supported");
@@ -1848,7 +1855,7 @@ extern "C" void vrfs_msm_g1_release(vrfs_msm_bases* h) {
   vrfs_ctx* ctx;
   { std::lock_guard<std::mutex> g(g_handles_mu); ctx = h->ctx; }
   if (ctx) {
-    CallGuard guard_(ctx);
+    CallGuard guard_(ctx); NvtxRange range_(__func__);
     std::lock_guard<std::mutex> g(g_handles_mu);
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
@@ -1866,7 +1873,7 @@ static void orphan_prepared(vrfs_ctx* ctx) {      // called by vrfs_ctx_destroy 
 }
 static vrfs_status msm_prepared_host(vrfs_ctx* ctx, const vrfs_msm_bases* h, const uint8_t* scalars, int n_columns, uint8_t* out, int out_mode) {
   if (!ctx || !h || h->ctx != ctx) return VRFS_BAD_ARG;
-  CallGuard guard_(ctx);
+  CallGuard guard_(ctx); NvtxRange range_(__func__);
   if (n_columns < 1 || n_columns > 32 || !scalars || !out) return fail(ctx, VRFS_BAD_ARG, "bad argument");
   ST(begin_call(ctx, h->n));
   const size_t ob = out_mode ? 144 : 96;
@@ -1911,7 +1918,7 @@ static vrfs_status ntt_dev(vrfs_ctx* ctx, int logn, uint32_t ncol, int inverse, 
 }
 extern "C" vrfs_status vrfs_fr_fft_batch(vrfs_ctx* ctx, int log_n, int n_columns, int inverse, const uint8_t* in, uint8_t* out) {
   if (!ctx) return VRFS_BAD_ARG;
-  CallGuard guard_(ctx);
+  CallGuard guard_(ctx); NvtxRange range_(__func__);
   if (log_n < 0 || log_n > 26 || n_columns < 1 || n_columns > 32 || !in || !out) return fail(ctx, VRFS_BAD_ARG, "bad argument (0 <= log_n <= 26, 1 <= n_columns <= 32)");
   const size_t bytes = ((size_t)n_columns << log_n) * 32;
   ST(begin_call(ctx, (size_t)1 << log_n));
@@ -1944,7 +1951,7 @@ static vrfs_status ring_columns_dev(vrfs_ctx* ctx, size_t n, size_t keyset_part,
 extern "C" vrfs_status vrfs_ring_fixed_columns(vrfs_ctx* ctx, size_t domain_size, size_t keyset_part_size, size_t n_keys, const uint8_t* keys,
                                                const uint8_t* padding, size_t n_tail, const uint8_t* tail, uint8_t* out_columns) {
   if (!ctx) return VRFS_BAD_ARG;
-  CallGuard guard_(ctx);
+  CallGuard guard_(ctx); NvtxRange range_(__func__);
   if (!out_columns) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   ST(begin_call(ctx, domain_size));
   uint8_t* d_cols = nullptr;
@@ -1955,7 +1962,7 @@ extern "C" vrfs_status vrfs_ring_fixed_columns(vrfs_ctx* ctx, size_t domain_size
 extern "C" vrfs_status vrfs_ring_commit(vrfs_ctx* ctx, const vrfs_msm_bases* srs, int srs_is_lagrange, size_t keyset_part_size, size_t n_keys,
                                         const uint8_t* keys, const uint8_t* padding, size_t n_tail, const uint8_t* tail, uint8_t* out_commitment) {
   if (!ctx || !srs || srs->ctx != ctx) return VRFS_BAD_ARG;
-  CallGuard guard_(ctx);
+  CallGuard guard_(ctx); NvtxRange range_(__func__);
   if (!out_commitment) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   const size_t n = srs->n;
   ST(begin_call(ctx, n));
@@ -1974,7 +1981,7 @@ extern "C" vrfs_status vrfs_ring_commit(vrfs_ctx* ctx, const vrfs_msm_bases* srs
 extern "C" vrfs_status vrfs_ring_commit_rows_partial(vrfs_ctx* ctx, const vrfs_msm_bases* srs_rows, size_t row_lo, size_t keyset_part_size, size_t n_keys,
                                                      const uint8_t* keys_rows, const uint8_t* padding, size_t n_tail, const uint8_t* tail, uint8_t* out_partial) {
   if (!ctx || !srs_rows || srs_rows->ctx != ctx) return VRFS_BAD_ARG;
-  CallGuard guard_(ctx);
+  CallGuard guard_(ctx); NvtxRange range_(__func__);
   if (!out_partial) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   const size_t n = srs_rows->n;
   ST(begin_call(ctx, n));
@@ -1988,7 +1995,7 @@ extern "C" vrfs_status vrfs_ring_commit_rows_partial(vrfs_ctx* ctx, const vrfs_m
 extern "C" vrfs_status vrfs_ring_commit_delta(vrfs_ctx* ctx, const vrfs_msm_bases* srs_lagrange, size_t n_keys, const uint8_t* keys,
                                               const uint8_t* padding, uint8_t* out_delta) {
   if (!ctx || !srs_lagrange || srs_lagrange->ctx != ctx) return VRFS_BAD_ARG;
-  CallGuard guard_(ctx);
+  CallGuard guard_(ctx); NvtxRange range_(__func__);
   const size_t n = srs_lagrange->n;
   if (!out_delta || !padding || (n_keys && !keys) || n_keys > n) return fail(ctx, VRFS_BAD_ARG, "bad argument (n_keys <= domain size, non-null buffers)");
   ST(begin_call(ctx, n));
@@ -2006,7 +2013,7 @@ extern "C" vrfs_status vrfs_ring_commit_delta(vrfs_ctx* ctx, const vrfs_msm_base
 }
 extern "C" vrfs_status vrfs_g1_compress_batch(vrfs_ctx* ctx, size_t n, const uint8_t* points, uint8_t* out) {
   if (!ctx) return VRFS_BAD_ARG;
-  CallGuard guard_(ctx);
+  CallGuard guard_(ctx); NvtxRange range_(__func__);
   if (n && (!points || !out)) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if (n == 0) return VRFS_OK;
   ST(begin_call(ctx, n));
@@ -2020,7 +2027,7 @@ extern "C" vrfs_status vrfs_g1_compress_batch(vrfs_ctx* ctx, size_t n, const uin
 }
 extern "C" vrfs_status vrfs_g1_decompress_batch(vrfs_ctx* ctx, size_t n, const uint8_t* enc, int check_subgroup, uint8_t* out_points, uint8_t* out_ok) {
   if (!ctx) return VRFS_BAD_ARG;
-  CallGuard guard_(ctx);
+  CallGuard guard_(ctx); NvtxRange range_(__func__);
   if (n && (!enc || !out_points || !out_ok)) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if (n == 0) return VRFS_OK;
   ST(begin_call(ctx, n));
@@ -2059,7 +2066,7 @@ __global__ void k_fq381_inv_batch(uint32_t n, const uint8_t* in, uint8_t* out, u
 }
 extern "C" vrfs_status vrfs_fq381_inv_batch(vrfs_ctx* ctx, size_t n, const uint8_t* in, uint8_t* out, uint8_t* out_ok) {
   if (!ctx) return VRFS_BAD_ARG;
-  CallGuard guard_(ctx);
+  CallGuard guard_(ctx); NvtxRange range_(__func__);
   if (n && (!in || !out || !out_ok)) return fail(ctx, VRFS_BAD_ARG, "null buffer");
   if (n == 0) return VRFS_OK;
   ST(begin_call(ctx, n));
@@ -2073,7 +2080,7 @@ extern "C" vrfs_status vrfs_fq381_inv_batch(vrfs_ctx* ctx, size_t n, const uint8
 }
 extern "C" vrfs_status vrfs_g1_sum_partials(vrfs_ctx* ctx, int n_parts, int n_columns, const uint8_t* partials, uint8_t* out) {
   if (!ctx) return VRFS_BAD_ARG;
-  CallGuard guard_(ctx);
+  CallGuard guard_(ctx); NvtxRange range_(__func__);
   if (n_parts < 1 || n_columns < 1 || n_columns > 32 || !partials || !out) return fail(ctx, VRFS_BAD_ARG, "bad argument");
   ST(begin_call(ctx, 1));
   const uint8_t* d_p; uint8_t* d_o;
