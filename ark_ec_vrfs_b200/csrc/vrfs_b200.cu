@@ -440,6 +440,26 @@ extern "C" vrfs_status vrfs_ctx_sync(vrfs_ctx* ctx) {
   CU(cudaStreamSynchronize(ctx->stream));
   return VRFS_OK;
 }
+// Page-locked host memory for callers that have no CUDA runtime of their own (a Rust shim): the batch calls copy straight from / into
+// the caller's buffers, and only page-locked ones let those copies run beside the kernels.  No context involved (portable across devices).
+extern "C" vrfs_status vrfs_host_alloc(size_t bytes, void** out) {
+  if (!out) return VRFS_BAD_ARG;
+  *out = nullptr;
+  if (bytes == 0) return VRFS_OK;
+  return cudaHostAlloc(out, bytes, cudaHostAllocPortable) == cudaSuccess ? VRFS_OK : (cudaGetLastError(), VRFS_CUDA_ERROR);
+}
+extern "C" vrfs_status vrfs_host_free(void* p) {
+  if (!p) return VRFS_OK;
+  return cudaFreeHost(p) == cudaSuccess ? VRFS_OK : (cudaGetLastError(), VRFS_BAD_ARG);
+}
+extern "C" vrfs_status vrfs_host_register(void* p, size_t bytes) {
+  if (!p || bytes == 0) return VRFS_BAD_ARG;
+  return cudaHostRegister(p, bytes, cudaHostRegisterPortable) == cudaSuccess ? VRFS_OK : (cudaGetLastError(), VRFS_CUDA_ERROR);
+}
+extern "C" vrfs_status vrfs_host_unregister(void* p) {
+  if (!p) return VRFS_BAD_ARG;
+  return cudaHostUnregister(p) == cudaSuccess ? VRFS_OK : (cudaGetLastError(), VRFS_BAD_ARG);
+}
 // test hook: bytes of an internal staging buffer (slot = position in the buffer pool; 0..4 are the input staging buffers in call
 // order, e.g. slot 0 holds `sk` during a prove call).  tests/ use it to check that key material is gone after a call returned.
 extern "C" vrfs_status vrfs_ctx_debug_read_staging(vrfs_ctx* ctx, int slot, size_t offset, uint8_t* out, size_t n) {

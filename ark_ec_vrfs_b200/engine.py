@@ -100,6 +100,32 @@ class PreparedBases:
                 self.engine._prepared.remove(self)
 
 
+def host_buffer(shape):
+    """A zeroed uint8 array in page-locked host memory (vrfs_host_alloc): batch calls on such buffers copy beside their kernels.
+    The allocation is freed when the array (and every view of it) is gone."""
+    import weakref
+    lib = _lib.load()
+    shape = (int(shape),) if np.isscalar(shape) else tuple(int(x) for x in shape)
+    nbytes = int(np.prod(shape)) if shape else 1
+    p = C.c_void_p()
+    st = lib.vrfs_host_alloc(C.c_size_t(max(nbytes, 1)), C.byref(p))
+    if st != _lib.OK or not p.value:
+        raise _lib.VrfsError(st, "page-locked host allocation of %d bytes failed" % nbytes)
+    raw = (C.c_uint8 * max(nbytes, 1)).from_address(p.value)
+    weakref.finalize(raw, lib.vrfs_host_free, C.c_void_p(p.value))
+    a = np.frombuffer(raw, dtype=np.uint8, count=nbytes).reshape(shape)
+    a[...] = 0
+    return a
+
+
+def host_copy(a):
+    """the same bytes in page-locked host memory"""
+    a = np.ascontiguousarray(a)
+    out = host_buffer(a.nbytes)
+    out[:] = a.view(np.uint8).reshape(-1)
+    return out.reshape(a.shape) if a.dtype == np.uint8 else out.view(a.dtype).reshape(a.shape)
+
+
 class Engine:
     """One context on one GPU (`device` = CUDA ordinal).  Not thread-safe; one per process per GPU."""
 

@@ -138,6 +138,50 @@ def test_secret_staging_buffers_are_wiped(eng):
 
 
 @pytest.mark.gpu
+def test_piecewise_host_calls_equal_small_calls(eng):
+    """Host-buffer calls above three resident waves are cut into pieces whose copies overlap the kernels (two pieces; six for
+    Pedersen prove): every item's result must be the one the same item gets in a small single-piece call.  Inputs and outputs live
+    in page-locked memory from the library's own allocator (vrfs_host_alloc), one input array is page-locked in place
+    (vrfs_host_register)."""
+    import ctypes as C
+    import ark_ec_vrfs_b200 as vrfs
+    from ark_ec_vrfs_b200 import _lib
+    base, n, chunk = 1024, 250_000, 50_000
+    sk0, pk0, inp0, out0 = V.make_keys_inputs(O.BANDERSNATCH, base)
+    idx = np.arange(n) % base
+    sk, pk, inp, out = (vrfs.host_copy(a[idx]) for a in (sk0, pk0, inp0, out0))
+    ads = [int(i).to_bytes(8, "little") for i in range(n)]          # distinct transcripts, so distinct proofs
+    c, s = vrfs.host_buffer((n, 32)), vrfs.host_buffer((n, 32))
+    eng.ietf_prove(vrfs.BANDERSNATCH, sk, inp, out, ads, out=(c, s))
+    proof, bl = vrfs.host_buffer((n, 256)), vrfs.host_buffer((n, 32))
+    eng.pedersen_prove(vrfs.BANDERSNATCH, sk, inp, out, ads, out=(proof, bl))
+    assert not eng.debug_read_staging(0, n * 32).any()               # sk of all six pieces: wiped
+    assert not eng.debug_read_staging(8, n * 32).any()               # and the blinding factors
+    for lo in range(0, n, chunk):
+        hi = lo + chunk
+        cc, ss = eng.ietf_prove(vrfs.BANDERSNATCH, sk[lo:hi], inp[lo:hi], out[lo:hi], ads[lo:hi])
+        assert np.array_equal(cc, c[lo:hi]) and np.array_equal(ss, s[lo:hi])
+        pp, bb = eng.pedersen_prove(vrfs.BANDERSNATCH, sk[lo:hi], inp[lo:hi], out[lo:hi], ads[lo:hi])
+        assert np.array_equal(pp, proof[lo:hi]) and np.array_equal(bb, bl[lo:hi])
+    # the first 1 024 items against the oracle
+    co, so = O.ietf_prove(O.BANDERSNATCH, sk0, inp0, out0, ads[:base])
+    assert np.array_equal(co, c[:base]) and np.array_equal(so, s[:base])
+    # verifiers: corrupt a spread of items (in every piece), expect exactly those to fail
+    bad = np.zeros(n, bool); bad[::997] = True; bad[-1] = True
+    s2 = np.array(s); s2[bad, 0] ^= 1
+    lib = _lib.load()
+    assert lib.vrfs_host_register(C.c_void_p(s2.ctypes.data), C.c_size_t(s2.nbytes)) == _lib.OK
+    try:
+        ok = eng.ietf_verify(vrfs.BANDERSNATCH, pk, inp, out, c, s2, ads)
+    finally:
+        assert lib.vrfs_host_unregister(C.c_void_p(s2.ctypes.data)) == _lib.OK
+    assert np.array_equal(ok.astype(bool), ~bad)
+    proof2 = np.array(proof); proof2[bad, 200] ^= 1
+    ok = eng.pedersen_verify(vrfs.BANDERSNATCH, inp, out, proof2, ads)
+    assert np.array_equal(ok.astype(bool), ~bad)
+
+
+@pytest.mark.gpu
 def test_fixed_base_tables_are_built_on_first_use():
     import ark_ec_vrfs_b200 as vrfs
     with vrfs.Engine(0) as e:
