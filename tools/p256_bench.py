@@ -14,8 +14,13 @@ with vrfs.Engine(0) as e:
         inp, ok = e.data_to_point(suite, alphas)
         out = e.output(suite, sk, inp)
         e.enable_kernel_timing(True)
-        c, s = e.ietf_prove(suite, sk, inp, out); kp = dict(e.kernel_timings())
-        okv = e.ietf_verify(suite, pk, inp, out, c, s); kv = dict(e.kernel_timings())
+        def summed():          # a piece-wise host call lists every kernel once per piece
+            d = {}
+            for k, ms in e.kernel_timings():
+                d[k] = d.get(k, 0.0) + ms
+            return d
+        c, s = e.ietf_prove(suite, sk, inp, out); kp = summed()
+        okv = e.ietf_verify(suite, pk, inp, out, c, s); kv = summed()
         e.enable_kernel_timing(False)
         assert okv.all()
         print("%-12s prove %.2f M/s %s   verify %.2f M/s %s" % (name, n / sum(kp.values()) / 1e3, {k: round(v, 1) for k, v in kp.items()},
