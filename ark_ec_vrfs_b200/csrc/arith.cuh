@@ -324,7 +324,19 @@ HD_INLINE void mont_sqr_limbs(uint32_t* out, const uint32_t* a) {
   if ((P::FULL && !P::SOLINAS_P256) || !VRFS_DEDICATED_SQR) { mont_mul_limbs<P>(out, a, a); return; }
   uint32_t t[2 * N];
   if constexpr (P::PM_C != 0) { C::sqr_wide(t, a); pm_fold<P>(out, t); return; }
-  else if constexpr (P::SOLINAS_P256) { C::mul_wide(t, a, a); p256_fold<P>(out, t); return; }   // a may use all 256 bits: sqr_wide needs the top bit clear
+  else if constexpr (P::SOLINAS_P256) {
+    // a may use all 256 bits and sqr_wide needs the top bit clear: a = a' + b 2^255, a^2 = a'^2 + b 2^256 a' + b 2^510
+    uint32_t lo[N], add[N];
+    const uint32_t mask = 0u - (a[N - 1] >> 31);
+    for (int i = 0; i < N; i++) lo[i] = a[i];
+    lo[N - 1] &= 0x7fffffffu;
+    C::sqr_wide(t, lo);
+    for (int i = 0; i < N; i++) add[i] = lo[i] & mask;
+    add[N - 1] += mask & 0x40000000u;                 // 2^510 = 2^(256 + 224 + 30); the top limb of a' is below 2^31, so this cannot wrap
+    C::add(t + N, t + N, add);                        // a^2 < 2^512: no carry out
+    p256_fold<P>(out, t);
+    return;
+  }
   else {
     C::sqr_wide(t, a);
     mont_reduce_wide<P>(out, t);
