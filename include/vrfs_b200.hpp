@@ -67,6 +67,23 @@ class Engine {
   vrfs_ctx* ctx_ = nullptr;
 };
 
+// Page-locks an existing buffer (e.g. the storage of a long-lived Bytes) for the guard's lifetime (vrfs_host_register): batch calls
+// copy from / into such memory beside their kernels instead of staging it synchronously.  Registration is an optimisation only: if
+// the driver refuses (`ok()` false), the calls still work on the pageable buffer.
+class HostRegistration {
+ public:
+  HostRegistration(const void* p, size_t bytes) : p_(const_cast<void*>(p)) { ok_ = p_ && bytes && vrfs_host_register(p_, bytes) == VRFS_OK; }
+  explicit HostRegistration(const Bytes& b) : HostRegistration(b.data(), b.size()) {}
+  ~HostRegistration() { if (ok_) vrfs_host_unregister(p_); }
+  HostRegistration(const HostRegistration&) = delete;
+  HostRegistration& operator=(const HostRegistration&) = delete;
+  bool ok() const { return ok_; }
+
+ private:
+  void* p_;
+  bool ok_ = false;
+};
+
 // ark_vrf::Suite: one ciphersuite bound to one engine
 struct Suite {
   vrfs_suite id;

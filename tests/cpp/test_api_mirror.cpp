@@ -88,6 +88,8 @@ int main() {
     CHECK(hex(sig.data(), 96) == "e7aa5154103450f0a0525a36a441f827296ee489ef30ed8787cff8df1bef223f"
                                  "439fd9495643314fa623f2581f4b3d7d6037394468084f4ad7d8031479d9d101"
                                  "828bedd2ad95380b11f67a05ea0a76f0c3fef2bee9f043f4dffdddde09f55c01");
+    HostRegistration pinned_sig(sig);                    // the signature bytes page-locked in place for the verify call
+    CHECK(pinned_sig.ok());
     auto [vok, beta] = Public::verify_signatures(s, k.public_().serialize_compressed(), {Bytes{}}, sig, {Bytes{}});
     CHECK(vok[0] == 1);
     CHECK(hex(beta.data(), 64) == "fdeb377a4ffd7f95ebe48e5b43a88d069ce62188e49493500315ad55ee04d7442b93c4c91d5475370e9380496f4bc0b838c2483bce4e133c6f18b0adbb9e4722");
