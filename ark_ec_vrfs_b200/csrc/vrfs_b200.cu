@@ -1603,13 +1603,22 @@ extern "C" vrfs_status vrfs_pedersen_prove_compressed_batch(vrfs_ctx* ctx, vrfs_
   if ((unsigned)suite >= VRFS_SUITE_COUNT) return fail(ctx, VRFS_BAD_ARG, "unknown suite %d", (int)suite);
   ST(begin_call(ctx, n));
   const size_t pl = (size_t)vrfs_suite_pedersen_proof_len(suite);
-  const uint8_t *d_sk, *d_in, *d_out, *d_ad; const uint64_t* d_off; uint8_t *d_pr, *d_bl, *d_enc;
-  ST(stage_secret(ctx, BUF_IN0, sk, n * 32, &d_sk)); ST(stage_in(ctx, BUF_IN1, input, n * 64, &d_in)); ST(stage_in(ctx, BUF_IN2, output, n * 64, &d_out));
+  const uint8_t* d_ad; const uint64_t* d_off; uint8_t *d_pr, *d_bl, *d_enc;
+  HostIn in[3] = {{BUF_IN0, sk, 32, true, nullptr}, {BUF_IN1, input, 64, false, nullptr}, {BUF_IN2, output, 64, false, nullptr}};
+  Pieces pc;   // in pieces like vrfs_pedersen_prove_batch: 192 B/item of results (Bandersnatch) return beside the next piece's kernels
+  ST(stage_in_pieces(ctx, n, in, 3, &pc, VRFS_HOST_PIECES));
   ST(stage_ad(ctx, n, ad, ad_off, &d_ad, &d_off));
   ST(stage_out(ctx, BUF_OUT0, n * 256, &d_pr)); ST(stage_out(ctx, BUF_OUT1, n * 32, &d_bl)); ST(stage_out(ctx, BUF_X1, n * pl, &d_enc));
   mark_secret(ctx, BUF_OUT1, n * 32);
-  ST(with_suite(ctx, suite, [&](auto S_) { typedef decltype(S_) S; return pedersen_prove_compressed_dev<S>(ctx, n, d_sk, d_in, d_out, d_ad, d_off, d_pr, d_bl, d_enc); }));
-  ST(copy_out(ctx, out_proof, d_enc, n * pl)); ST(copy_out(ctx, out_blinding, d_bl, n * 32));
+  const HostOut out[2] = {{out_proof, d_enc, pl}, {out_blinding, d_bl, 32}};
+  for (int k = 0; k < pc.count; k++) {
+    const size_t o = pc.cut[k], m = pc.cut[k + 1] - pc.cut[k];
+    ST(piece_ready(ctx, k));
+    ST(with_suite(ctx, suite, [&](auto S_) { typedef decltype(S_) S;
+      return pedersen_prove_compressed_dev<S>(ctx, m, in[0].dev + o * 32, in[1].dev + o * 64, in[2].dev + o * 64, d_ad, d_off ? d_off + o : nullptr,
+                                              d_pr + o * 256, d_bl + o * 32, d_enc + o * pl); }));
+    ST(pieces_copy_out(ctx, pc, k, out, 2));
+  }
   return finish_call(ctx);
 }
 extern "C" vrfs_status vrfs_pedersen_verify_compressed_batch(vrfs_ctx* ctx, vrfs_suite suite, size_t n, const uint8_t* input, const uint8_t* output, const uint8_t* proof,

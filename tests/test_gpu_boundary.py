@@ -163,6 +163,14 @@ def test_piecewise_host_calls_equal_small_calls(eng):
         assert np.array_equal(cc, c[lo:hi]) and np.array_equal(ss, s[lo:hi])
         pp, bb = eng.pedersen_prove(vrfs.BANDERSNATCH, sk[lo:hi], inp[lo:hi], out[lo:hi], ads[lo:hi])
         assert np.array_equal(pp, proof[lo:hi]) and np.array_equal(bb, bl[lo:hi])
+    # the serialised proof form goes through the same pieces: it must be the encoding of the proofs above
+    enc, bl2 = eng.pedersen_prove_compressed(vrfs.BANDERSNATCH, sk, inp, out, ads)
+    assert np.array_equal(bl2, bl)
+    enc_small, _ = eng.pedersen_prove_compressed(vrfs.BANDERSNATCH, sk[:chunk], inp[:chunk], out[:chunk], ads[:chunk])
+    assert np.array_equal(enc_small, enc[:chunk])
+    tail_small, _ = eng.pedersen_prove_compressed(vrfs.BANDERSNATCH, sk[-chunk:], inp[-chunk:], out[-chunk:], ads[-chunk:])
+    assert np.array_equal(tail_small, enc[-chunk:])
+    assert eng.pedersen_verify_compressed(vrfs.BANDERSNATCH, inp, out, enc, ads).all()
     # the first 1 024 items against the oracle
     co, so = O.ietf_prove(O.BANDERSNATCH, sk0, inp0, out0, ads[:base])
     assert np.array_equal(co, c[:base]) and np.array_equal(so, s[:base])
