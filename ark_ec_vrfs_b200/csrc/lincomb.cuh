@@ -81,12 +81,14 @@ template <class C> struct Grp<C, true> {
   static HD_INLINE void add_fix(Pt* acc, const FixEntry* e, bool negate, bool want_t = true) { te_madd<C>(acc, acc, e, negate, want_t); }
   static HD_INLINE void dbl4(Pt* acc) { te_dbl<C>(acc, acc, false); te_dbl<C>(acc, acc, false); te_dbl<C>(acc, acc, false); te_dbl<C>(acc, acc, true); }
   static HD_INLINE void dbl(Pt* acc) { te_dbl<C>(acc, acc, true); }
-  static HD_INLINE void dbl_entry(Pt* r, const Entry* e) { Pt p; p.X = e->X; p.Y = e->Y; p.Z = e->Z; p.T = e->Z; te_dbl<C>(r, &p, true); }   // the doubling does not read T
+  static HD_INLINE void dbl_entry(Pt* r, const Entry* e) { Pt p; te_from_cached_xyz<C>(p, *e); te_dbl<C>(r, &p, true); }   // the doubling does not read T
   static HD_INLINE void add(Pt* r, const Pt* p, const Pt* q) { te_add<C>(r, p, q); }
   static HD_INLINE void endo(Pt* r, const Pt* p) { band_endo(reinterpret_cast<TEPoint<BandCurve>*>(r), reinterpret_cast<const TEPoint<BandCurve>*>(p)); }
   static HD_INLINE void to_fix(FixEntry& e, const Pt& P) {
     typename C::F zi = inv(P.Z);
-    e.x = P.X * zi; e.y = P.Y * zi; e.dt = e.x * e.y * C::d();
+    typename C::F x = P.X * zi, y = P.Y * zi, dt = x * y * C::d();
+    if constexpr (C::A_IS_M1) { e.x = y + x; e.y = y - x; e.dt = dt + dt; }       // te.cuh: the a = -1 entry form
+    else { e.x = x; e.y = y; e.dt = dt; }
   }
   static HD_INLINE void store_xyz(uint32_t* o, const Pt& P) { store_fp_xyz(o, P.X, P.Y, P.Z); }
 };

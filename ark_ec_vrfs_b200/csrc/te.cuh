@@ -18,6 +18,7 @@ struct BandCurve {
   typedef Fp<Fq> F;
   static constexpr int COF_LOG2 = 2;
   static constexpr bool IS_TE = true;
+  static constexpr bool A_IS_M1 = false;
   static constexpr bool HAS_GLV = true;
   static HD_INLINE F mul_a(const F& x) { F t = dbl(dbl(x)); return neg(t + x); }   // a = -5
   static HD_INLINE F d() { return fconst<Fq, K::D>(); }
@@ -33,6 +34,7 @@ struct EdCurve {
   typedef Fp<Fq> F;
   static constexpr int COF_LOG2 = 3;
   static constexpr bool IS_TE = true;
+  static constexpr bool A_IS_M1 = true;
   static constexpr bool HAS_GLV = false;
   static HD_INLINE F mul_a(const F& x) { return neg(x); }                           // a = -1
   static HD_INLINE F d() { return fconst<Fq, K::D>(); }
@@ -51,6 +53,7 @@ struct JubCurve {
   typedef Fp<Fq> F;
   static constexpr int COF_LOG2 = 3;
   static constexpr bool IS_TE = true;
+  static constexpr bool A_IS_M1 = true;
   static constexpr bool HAS_GLV = false;
   static HD_INLINE F mul_a(const F& x) { return neg(x); }
   static HD_INLINE F d() { return fconst<Fq, K::D>(); }
@@ -66,6 +69,7 @@ struct BjjCurve {
   typedef Fp<Fq> F;
   static constexpr int COF_LOG2 = 3;
   static constexpr bool IS_TE = true;
+  static constexpr bool A_IS_M1 = false;
   static constexpr bool HAS_GLV = false;
   static HD_INLINE F mul_a(const F& x) { return x; }
   static HD_INLINE F d() { return fconst<Fq, K::D>(); }
@@ -76,7 +80,10 @@ struct BjjCurve {
 };
 
 template <class C> struct TEPoint { typename C::F X, Y, Z, T; };
-// table entry forms: "cached" = (X, Y, Z, d*T); "affine cached" = (x, y, d*x*y) with Z = 1
+// table entry forms: "cached" = (X, Y, Z, d*T); "affine cached" = (x, y, d*x*y) with Z = 1.
+// Curves with a = -1 (C::A_IS_M1: Ed25519, Jubjub) keep the same structs but store (Y+X, Y-X, 2Z, 2d*T) and (y+x, y-x, 2d*x*y):
+// add-2008-hwcd-3 then takes 8 products (7 against an affine entry) instead of 9 (8), five field additions fewer, and negating an
+// entry is a swap of its first two fields.
 template <class C> struct TECached { typename C::F X, Y, Z, dT; };
 template <class C> struct TEAffCached { typename C::F x, y, dt; };
 
@@ -92,7 +99,14 @@ template <class C> HD_INLINE bool te_on_curve(const typename C::F& x, const type
   return C::mul_a(xx) + yy == C::F::one() + C::d() * xx * yy;
 }
 template <class C> HD_INLINE void te_to_cached(TECached<C>& r, const TEPoint<C>& P) {
-  r.X = P.X; r.Y = P.Y; r.Z = P.Z; r.dT = P.T * C::d();
+  if constexpr (C::A_IS_M1) { r.X = P.Y + P.X; r.Y = P.Y - P.X; r.Z = dbl(P.Z); r.dT = dbl(P.T * C::d()); }
+  else { r.X = P.X; r.Y = P.Y; r.Z = P.Z; r.dT = P.T * C::d(); }
+}
+// the point a cached entry stands for, as (X : Y : Z) up to a common factor (what a doubling reads)
+template <class C> HD_INLINE void te_from_cached_xyz(TEPoint<C>& P, const TECached<C>& e) {
+  if constexpr (C::A_IS_M1) { P.X = e.X - e.Y; P.Y = e.X + e.Y; P.Z = e.Z; }      // (2X : 2Y : 2Z)
+  else { P.X = e.X; P.Y = e.Y; P.Z = e.Z; }
+  P.T = P.Z;                                                                        // not read by the doubling
 }
 
 // r = p + q (9M + 1 by d)
@@ -107,12 +121,19 @@ template <class C> HD_NOINLINE void te_add(TEPoint<C>* r, const TEPoint<C>* p, c
 // (want_t = false: T of the result is not computed - the next operation is a doubling, which does not read it, or the end)
 template <class C> HD_NOINLINE void te_add_cached(TEPoint<C>* r, const TEPoint<C>* p, const TECached<C>* q, bool negate, bool want_t = true) {
   typedef typename C::F F;
-  F qX = cneg(q->X, negate), qdT = cneg(q->dT, negate);
-  F A, B, Cc, D, E, X3, Y3, Z3;
-  mul2(A, B, p->X, qX, p->Y, q->Y);
-  mul2(Cc, D, p->T, qdT, p->Z, q->Z);
-  E = (p->X + p->Y) * (qX + q->Y) - A - B;
-  F Fv = D - Cc, G = D + Cc, H = B - C::mul_a(A);
+  F A, B, Cc, D, E, Fv, G, H, X3, Y3, Z3;
+  if constexpr (C::A_IS_M1) {
+    F ypx = select(negate, q->Y, q->X), ymx = select(negate, q->X, q->Y), q2dT = cneg(q->dT, negate);
+    mul2(A, B, p->Y - p->X, ymx, p->Y + p->X, ypx);
+    mul2(Cc, D, p->T, q2dT, p->Z, q->Z);
+    E = B - A; Fv = D - Cc; G = D + Cc; H = B + A;
+  } else {
+    F qX = cneg(q->X, negate), qdT = cneg(q->dT, negate);
+    mul2(A, B, p->X, qX, p->Y, q->Y);
+    mul2(Cc, D, p->T, qdT, p->Z, q->Z);
+    E = (p->X + p->Y) * (qX + q->Y) - A - B;
+    Fv = D - Cc; G = D + Cc; H = B - C::mul_a(A);
+  }
   mul2(X3, Y3, E, Fv, G, H);
   r->X = X3; r->Y = Y3;
   if (want_t) { F T3; mul2(T3, Z3, E, H, Fv, G); r->T = T3; r->Z = Z3; } else r->Z = Fv * G;
@@ -120,12 +141,21 @@ template <class C> HD_NOINLINE void te_add_cached(TEPoint<C>* r, const TEPoint<C
 // r = p + q, q affine cached, optionally negated (8M)
 template <class C> HD_NOINLINE void te_madd(TEPoint<C>* r, const TEPoint<C>* p, const TEAffCached<C>* q, bool negate, bool want_t = true) {
   typedef typename C::F F;
-  F qx = cneg(q->x, negate), qdt = cneg(q->dt, negate);
-  F A, B, Cc, E, D = p->Z, X3, Y3, Z3;
-  mul2(A, B, p->X, qx, p->Y, q->y);
-  mul2(Cc, E, p->T, qdt, p->X + p->Y, qx + q->y);
-  E = E - A - B;
-  F Fv = D - Cc, G = D + Cc, H = B - C::mul_a(A);
+  F A, B, Cc, E, D, Fv, G, H, X3, Y3, Z3;
+  if constexpr (C::A_IS_M1) {
+    F ypx = select(negate, q->y, q->x), ymx = select(negate, q->x, q->y), q2dt = cneg(q->dt, negate);
+    mul2(A, B, p->Y - p->X, ymx, p->Y + p->X, ypx);
+    Cc = p->T * q2dt;
+    D = dbl(p->Z);
+    E = B - A; Fv = D - Cc; G = D + Cc; H = B + A;
+  } else {
+    F qx = cneg(q->x, negate), qdt = cneg(q->dt, negate);
+    D = p->Z;
+    mul2(A, B, p->X, qx, p->Y, q->y);
+    mul2(Cc, E, p->T, qdt, p->X + p->Y, qx + q->y);
+    E = E - A - B;
+    Fv = D - Cc; G = D + Cc; H = B - C::mul_a(A);
+  }
   mul2(X3, Y3, E, Fv, G, H);
   r->X = X3; r->Y = Y3;
   if (want_t) { F T3; mul2(T3, Z3, E, H, Fv, G); r->T = T3; r->Z = Z3; } else r->Z = Fv * G;

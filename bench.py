@@ -60,12 +60,13 @@ def kernel_muls(suite, kernel):
     if suite == 0:
         t = {"lincomb<2,0>": 2110, "lincomb<1,1>": 1820, "lincomb<1,0>": 1560, "lincomb<0,1>": 128, "lincomb<0,2>": 256, "lincomb<1,2>": 1560 + 256,
              "ietf_verify_finish": 275, "zinv": 45}
-    elif suite == 1:     # 252 doublings (4S + 3..4M), 64 cached additions (9M), one 8-entry table
-        var = 252 * 7.25 + 64 * 9 + 71
-        t = {"lincomb<2,0>": 252 * 7.25 + 2 * (64 * 9 + 71), "lincomb<1,1>": var + 128, "lincomb<1,0>": var, "lincomb<0,1>": 128, "lincomb<0,2>": 256, "lincomb<1,2>": var + 256}
-    else:                # 64 quadruple doublings of 38 products, 65 complete additions of 12, one table; fixed base: 17 complete additions
-        var = 64 * 38 + 65 * 12 + 84
-        t = {"lincomb<2,0>": 64 * 38 + 2 * (65 * 12 + 84), "lincomb<1,1>": var + 17 * 12, "lincomb<1,0>": var, "lincomb<0,1>": 17 * 12, "lincomb<0,2>": 34 * 12, "lincomb<1,2>": var + 34 * 12}
+    elif suite == 1:     # 252 doublings (4S + 3..4M), 64 cached additions (a = -1 entry form: 8M; 7M against the affine fixed-base entries), one 8-entry table
+        var = 252 * 7.25 + 64 * 8 + 68
+        t = {"lincomb<2,0>": 252 * 7.25 + 2 * (64 * 8 + 68), "lincomb<1,1>": var + 112, "lincomb<1,0>": var, "lincomb<0,1>": 112, "lincomb<0,2>": 224, "lincomb<1,2>": var + 224}
+    else:                # 64 quadruple doublings of 16M + 22S (a squaring is 36 of a product's 64 wide multiplies: counted as 0.5625),
+                         # 65 complete additions of 12, one table; fixed base: 17 complete additions
+        var = 64 * (16 + 22 * 0.5625) + 65 * 12 + 84
+        t = {"lincomb<2,0>": 64 * (16 + 22 * 0.5625) + 2 * (65 * 12 + 84), "lincomb<1,1>": var + 17 * 12, "lincomb<1,0>": var, "lincomb<0,1>": 17 * 12, "lincomb<0,2>": 34 * 12, "lincomb<1,2>": var + 34 * 12}
     return t.get(kernel)
 
 
