@@ -21,6 +21,7 @@ struct BandCurve {
   static constexpr bool A_IS_M1 = false;
   static constexpr bool HAS_GLV = true;
   static HD_INLINE F mul_a(const F& x) { F t = dbl(dbl(x)); return neg(t + x); }   // a = -5
+  static HD_INLINE F mul_neg_a(const F& x) { return dbl(dbl(x)) + x; }              // -a x = 5x (no negation: see te_dbl)
   static HD_INLINE F d() { return fconst<Fq, K::D>(); }
   static HD_INLINE F gx() { return fconst<Fq, K::GX>(); }
   static HD_INLINE F gy() { return fconst<Fq, K::GY>(); }
@@ -37,6 +38,7 @@ struct EdCurve {
   static constexpr bool A_IS_M1 = true;
   static constexpr bool HAS_GLV = false;
   static HD_INLINE F mul_a(const F& x) { return neg(x); }                           // a = -1
+  static HD_INLINE F mul_neg_a(const F& x) { return x; }
   static HD_INLINE F d() { return fconst<Fq, K::D>(); }
   static HD_INLINE F gx() { return fconst<Fq, K::GX>(); }
   static HD_INLINE F gy() { return fconst<Fq, K::GY>(); }
@@ -56,6 +58,7 @@ struct JubCurve {
   static constexpr bool A_IS_M1 = true;
   static constexpr bool HAS_GLV = false;
   static HD_INLINE F mul_a(const F& x) { return neg(x); }
+  static HD_INLINE F mul_neg_a(const F& x) { return x; }
   static HD_INLINE F d() { return fconst<Fq, K::D>(); }
   static HD_INLINE F gx() { return fconst<Fq, K::GX>(); }
   static HD_INLINE F gy() { return fconst<Fq, K::GY>(); }
@@ -72,6 +75,7 @@ struct BjjCurve {
   static constexpr bool A_IS_M1 = false;
   static constexpr bool HAS_GLV = false;
   static HD_INLINE F mul_a(const F& x) { return x; }
+  static HD_INLINE F mul_neg_a(const F& x) { return neg(x); }
   static HD_INLINE F d() { return fconst<Fq, K::D>(); }
   static HD_INLINE F gx() { return fconst<Fq, K::GX>(); }
   static HD_INLINE F gy() { return fconst<Fq, K::GY>(); }
@@ -114,7 +118,7 @@ template <class C> HD_NOINLINE void te_add(TEPoint<C>* r, const TEPoint<C>* p, c
   typedef typename C::F F;
   F A = p->X * q->X, B = p->Y * q->Y, Cc = p->T * q->T * C::d(), D = p->Z * q->Z;
   F E = (p->X + p->Y) * (q->X + q->Y) - A - B;
-  F Fv = D - Cc, G = D + Cc, H = B - C::mul_a(A);
+  F Fv = D - Cc, G = D + Cc, H = B + C::mul_neg_a(A);
   r->X = E * Fv; r->Y = G * H; r->T = E * H; r->Z = Fv * G;
 }
 // r = p + q, q cached, optionally negated (9M)
@@ -132,7 +136,7 @@ template <class C> HD_NOINLINE void te_add_cached(TEPoint<C>* r, const TEPoint<C
     mul2(A, B, p->X, qX, p->Y, q->Y);
     mul2(Cc, D, p->T, qdT, p->Z, q->Z);
     E = (p->X + p->Y) * (qX + q->Y) - A - B;
-    Fv = D - Cc; G = D + Cc; H = B - C::mul_a(A);
+    Fv = D - Cc; G = D + Cc; H = B + C::mul_neg_a(A);
   }
   mul2(X3, Y3, E, Fv, G, H);
   r->X = X3; r->Y = Y3;
@@ -154,22 +158,24 @@ template <class C> HD_NOINLINE void te_madd(TEPoint<C>* r, const TEPoint<C>* p, 
     mul2(A, B, p->X, qx, p->Y, q->y);
     mul2(Cc, E, p->T, qdt, p->X + p->Y, qx + q->y);
     E = E - A - B;
-    Fv = D - Cc; G = D + Cc; H = B - C::mul_a(A);
+    Fv = D - Cc; G = D + Cc; H = B + C::mul_neg_a(A);
   }
   mul2(X3, Y3, E, Fv, G, H);
   r->X = X3; r->Y = Y3;
   if (want_t) { F T3; mul2(T3, Z3, E, H, Fv, G); r->T = T3; r->Z = Z3; } else r->Z = Fv * G;
 }
-// r = 2p (4S + 4M; T of the result is skipped when the next operation is another doubling)
+// r = 2p (4S + 4M; T of the result is skipped when the next operation is another doubling).
+// dbl-2008-hwcd with D = a A, G = D + B, F = G - C, H = D - B.  Computed with Dn = -a A (a = -5: 5A, three additions and no negation),
+// G = B - Dn and the NEGATED F and H (Fv = C - G, H = Dn + B): all four coordinates come out negated, which is the same point.
 template <class C> HD_NOINLINE void te_dbl(TEPoint<C>* r, const TEPoint<C>* p, bool want_t) {
   typedef typename C::F F;
   F A, B, Cc, E, X3, Y3, Z3;
   sqr2(A, B, p->X, p->Y);
   sqr2(Cc, E, p->Z, p->X + p->Y);
   Cc = dbl(Cc);
-  F D = C::mul_a(A);
+  F Dn = C::mul_neg_a(A);
   E = E - A - B;
-  F G = D + B, Fv = G - Cc, H = D - B;
+  F G = B - Dn, Fv = Cc - G, H = Dn + B;
   mul2(X3, Y3, E, Fv, G, H);
   r->X = X3; r->Y = Y3;
   if (want_t) { F T3; mul2(Z3, T3, Fv, G, E, H); r->Z = Z3; r->T = T3; } else r->Z = Fv * G;
